@@ -1,0 +1,89 @@
+"""ctypes binding of libemrt_b200.so (the C ABI declared in include/emrt_b200.h).
+
+There is no CPU fallback: if the shared library is missing or fails to load, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libemrt_b200.so")
+
+# enums (mirror include/emrt_b200.h)
+F32, BF16, F16, I32, U8 = 0, 1, 2, 3, 4
+LOC_NORMALIZED, LOC_PIXEL_OFFSET = 0, 1
+EPI_NONE, EPI_ROW_MASK, EPI_RELU, EPI_RESIDUAL_LN, EPI_MSDA_QPROJ = 0, 1, 2, 4, 8
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+
+
+class EmrtError(RuntimeError):
+    pass
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
+        ("rows", C.c_int64), ("K", C.c_int32), ("N", C.c_int32),
+        ("x_dtype", C.c_int32), ("w_dtype", C.c_int32), ("y_dtype", C.c_int32), ("w_transposed", C.c_int32),
+        ("epilogue", C.c_int32),
+        ("row_scale", C.c_void_p),
+        ("residual", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
+        ("y2", C.c_void_p), ("qproj_group", C.c_int32),
+        ("impl", C.c_int32),
+    ]
+
+
+_P, _I, _L = C.c_void_p, C.c_int, C.c_int64
+_I32P = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); exactly the symbols include/emrt_b200.h declares
+SIGNATURES = {
+    "emrt_version": (C.c_int, []),
+    "emrt_last_error": (C.c_char_p, []),
+    "emrt_device_check": (C.c_int, []),
+    "emrt_launch_count": (C.c_int64, []),
+    "emrt_reset_launch_count": (None, []),
+    "emrt_msda_gather_fwd": (C.c_int, [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P, _I, _I, _I, _P]),
+    "emrt_msda_gather_bwd": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P,
+                                       _I, _I, _I, _P]),
+    "emrt_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _P]),
+    "emrt_pack_weight": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
+    "emrt_msda_softmax_loc": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I32P, _I, _I, _P]),
+    "emrt_add_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, C.c_float, _I, _P]),
+    "emrt_upsample2x": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "emrt_window_accumulate": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "emrt_finalize_argmax": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "emrt_stitch_argmax_fused": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "emrt_calculate_area": (C.c_int, [_P, _P, _L, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every declared symbol.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EmrtError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(emrt_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = load().emrt_last_error()
+        raise EmrtError(f"emrt_b200 error {status}: {msg.decode() if msg else ''}")
+
+
+def i32_array(values):
+    arr = (C.c_int32 * len(values))(*[int(v) for v in values])
+    return arr

@@ -1,0 +1,125 @@
+// Shared helpers for the emrt_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/emrt_b200.h"
+
+namespace emrt {
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+char* last_error_buffer();                 // thread-local, 512 bytes
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define EMRT_REQUIRE(cond, ...)                                                            \
+  do {                                                                                     \
+    if (!(cond)) return ::emrt::set_error(EMRT_ERR_INVALID_ARGUMENT, __VA_ARGS__);         \
+  } while (0)
+
+#define EMRT_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::emrt::set_error(EMRT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                \
+  } while (0)
+
+#define EMRT_LAUNCH_CHECK()                                                                \
+  do {                                                                                     \
+    ::emrt::count_launch();                                                                \
+    EMRT_CUDA_CHECK(cudaGetLastError());                                                   \
+  } while (0)
+
+// ---- level tables passed by value into kernels -----------------------------------------------------------
+struct LevelTable {
+  int32_t H[EMRT_MAX_LEVELS];
+  int32_t W[EMRT_MAX_LEVELS];
+  int32_t start[EMRT_MAX_LEVELS];
+};
+
+inline int fill_levels(LevelTable& t, int L, const int32_t* shapes_hw, const int32_t* level_start, int Lv) {
+  if (L < 1 || L > EMRT_MAX_LEVELS) return set_error(EMRT_ERR_INVALID_ARGUMENT, "L=%d out of [1,%d]", L, EMRT_MAX_LEVELS);
+  if (!shapes_hw) return set_error(EMRT_ERR_INVALID_ARGUMENT, "shapes_hw_host is NULL");
+  int64_t acc = 0;
+  for (int l = 0; l < L; ++l) {
+    t.H[l] = shapes_hw[2 * l];
+    t.W[l] = shapes_hw[2 * l + 1];
+    if (t.H[l] <= 0 || t.W[l] <= 0) return set_error(EMRT_ERR_INVALID_ARGUMENT, "level %d has non-positive shape", l);
+    t.start[l] = level_start ? level_start[l] : (int32_t)acc;
+    if (level_start && level_start[l] != acc)
+      return set_error(EMRT_ERR_INVALID_ARGUMENT, "level_start[%d]=%d but prefix sum of shapes is %lld", l, level_start[l], (long long)acc);
+    acc += (int64_t)t.H[l] * t.W[l];
+  }
+  // the reference asserts sum(h*w) == Len_v (transformer_encoder_decoder.py:81)
+  if (Lv >= 0 && acc != Lv) return set_error(EMRT_ERR_INVALID_ARGUMENT, "sum(H*W)=%lld != Lv=%d", (long long)acc, Lv);
+  for (int l = L; l < EMRT_MAX_LEVELS; ++l) t.H[l] = t.W[l] = t.start[l] = 0;
+  return EMRT_OK;
+}
+
+// ---- dtype helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+
+// 16-byte vector of T, unpacked to fp32
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 r = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace emrt

@@ -1,0 +1,318 @@
+// Segmentation-head tail: UpHead's last x2 bilinear upsample (paddle_EMRT.py:178-180), slide_inference's
+// window accumulation / divide (src/api/infer.py:69-79), ss_inference's resize + softmax + argmax
+// (infer.py:150-154, predict.py:162-166) and calculate_area (src/utils/metrics.py:20-69).
+//
+// All of it is HBM-bound byte/float work.  The fused kernel reads only the half-resolution window logits and
+// writes only the label map: per pixel it upsamples every covering window on the fly and sums them in window
+// order (deterministic, no atomics, no full-resolution fp32 canvas round trip).
+#include "common.cuh"
+
+namespace emrt {
+
+// half-pixel source coordinate for align_corners=False: src = (dst + 0.5) * scale - 0.5, clamped at 0
+struct Tap { int i0, i1; float f; };
+__device__ __forceinline__ Tap make_tap(int dst, int n_in, float scale) {
+  float s = ((float)dst + 0.5f) * scale - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  Tap t;
+  t.i0 = min((int)s, n_in - 1);
+  t.i1 = min(t.i0 + 1, n_in - 1);
+  t.f = s - (float)t.i0;
+  return t;
+}
+
+template <typename T>
+__device__ __forceinline__ float bilerp(const T* __restrict__ plane, int w, const Tap& ty, const Tap& tx) {
+  const float a = to_float(plane[ty.i0 * w + tx.i0]);
+  const float b = to_float(plane[ty.i0 * w + tx.i1]);
+  const float c = to_float(plane[ty.i1 * w + tx.i0]);
+  const float d = to_float(plane[ty.i1 * w + tx.i1]);
+  const float top = a + tx.f * (b - a);
+  const float bot = c + tx.f * (d - c);
+  return top + ty.f * (bot - top);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t planes, int h, int w) {
+  const int H = 2 * h, W = 2 * w;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= planes * H * W) return;
+  const int ox = (int)(idx % W);
+  const int oy = (int)((idx / W) % H);
+  const int64_t pl = idx / ((int64_t)W * H);
+  out[idx] = bilerp<T>(in + pl * h * w, w, make_tap(oy, h, 0.5f), make_tap(ox, w, 0.5f));
+}
+
+// ---- ordered list of the windows that touch a CTA's pixel tile ---------------------------------------------
+constexpr int TILE_X = 32, TILE_Y = 8, MAX_LIST = 64;
+
+struct WinList {
+  int n;            // number of entries, or -1 when more than MAX_LIST windows touch the tile (scan globally)
+  int idx[MAX_LIST];
+};
+
+__device__ __forceinline__ void build_window_list(WinList& wl, int* warp_cnt, int n_win, int img, int ty0, int tx0,
+                                                  int hc, int wc, const int32_t* __restrict__ win_img,
+                                                  const int32_t* __restrict__ win_y0,
+                                                  const int32_t* __restrict__ win_x0) {
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  if (t == 0) wl.n = 0;
+  __syncthreads();
+  for (int base = 0; base < n_win; base += 256) {
+    const int w = base + t;
+    bool hit = false;
+    if (w < n_win && __ldg(win_img + w) == img) {
+      const int y0 = __ldg(win_y0 + w), x0 = __ldg(win_x0 + w);
+      hit = (y0 < ty0 + TILE_Y) && (y0 + hc > ty0) && (x0 < tx0 + TILE_X) && (x0 + wc > tx0);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[warp] = __popc(ballot);
+    __syncthreads();
+    int off = wl.n, total = 0;
+    for (int i = 0; i < 8; ++i) { if (i < warp) off += warp_cnt[i]; total += warp_cnt[i]; }
+    off += __popc(ballot & ((1u << lane) - 1u));
+    if (hit && off >= 0 && off < MAX_LIST) wl.idx[off] = w;
+    __syncthreads();
+    if (t == 0) wl.n = (wl.n < 0 || wl.n + total > MAX_LIST) ? -1 : wl.n + total;
+    __syncthreads();
+  }
+}
+
+// softmax(axis=1) -> argmax(axis=1) with first-max tie rule (infer.py:152-153).
+template <int NC>
+__device__ __forceinline__ int softmax_argmax(const float (&l)[NC], int nc, float (&prob)[NC]) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) if (c < nc) mx = fmaxf(mx, l[c]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) if (c < nc) { prob[c] = expf(l[c] - mx); s += prob[c]; }
+  const float inv = 1.f / s;
+  int best = 0;
+  float bv = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) if (c < nc) {
+    prob[c] *= inv;
+    if (prob[c] > bv) { bv = prob[c]; best = c; }
+  }
+  return best;
+}
+
+__device__ __forceinline__ void store_label(void* labels, int label_dtype, int64_t i, int v) {
+  if (label_dtype == EMRT_U8) reinterpret_cast<uint8_t*>(labels)[i] = (uint8_t)v;
+  else reinterpret_cast<int32_t*>(labels)[i] = v;
+}
+
+// a6 accumulate on a full-resolution canvas: canvas += sum of window logits (window order), count += cover.
+__global__ void __launch_bounds__(256)
+window_accumulate_kernel(const float* __restrict__ win_logits, float* __restrict__ canvas, float* __restrict__ count,
+                         int n_win, int nc, int hc, int wc, int H, int W, const int32_t* __restrict__ win_img,
+                         const int32_t* __restrict__ win_y0, const int32_t* __restrict__ win_x0) {
+  __shared__ WinList wl;
+  __shared__ int warp_cnt[8];
+  const int img = blockIdx.z;
+  const int tx0 = blockIdx.x * TILE_X, ty0 = blockIdx.y * TILE_Y;
+  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, hc, wc, win_img, win_y0, win_x0);
+  const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int n = wl.n < 0 ? n_win : wl.n;
+  float cnt = 0.f;
+  const int64_t plane = (int64_t)H * W;
+  float* cv = canvas + (int64_t)img * nc * plane + (int64_t)y * W + x;
+  for (int i = 0; i < n; ++i) {
+    const int w = wl.n < 0 ? i : wl.idx[i];
+    if (wl.n < 0 && __ldg(win_img + w) != img) continue;
+    const int ly = y - __ldg(win_y0 + w), lx = x - __ldg(win_x0 + w);
+    if (ly < 0 || ly >= hc || lx < 0 || lx >= wc) continue;
+    cnt += 1.f;
+    const float* src = win_logits + ((int64_t)w * nc * hc + ly) * wc + lx;
+    for (int c = 0; c < nc; ++c) cv[c * plane] += __ldg(src + (int64_t)c * hc * wc);
+  }
+  if (count) count[(int64_t)img * plane + (int64_t)y * W + x] += cnt;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+finalize_argmax_kernel(const float* __restrict__ canvas, const float* __restrict__ count, void* __restrict__ labels,
+                       int label_dtype, float* __restrict__ probs_out, float* __restrict__ logits_out, int n_img,
+                       int nc, int H, int W, int Ho, int Wo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t oplane = (int64_t)Ho * Wo, plane = (int64_t)H * W;
+  if (idx >= n_img * oplane) return;
+  const int img = (int)(idx / oplane);
+  const int oy = (int)((idx % oplane) / Wo), ox = (int)(idx % Wo);
+  const float* cv = canvas + (int64_t)img * nc * plane;
+  const float* ct = count ? count + (int64_t)img * plane : nullptr;
+  float l[NC], prob[NC];
+  if (Ho == H && Wo == W) {
+    const int64_t o = (int64_t)oy * W + ox;
+    const float c0 = ct ? ct[o] : 1.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) if (c < nc) l[c] = cv[c * plane + o] / c0;   // logit / count (infer.py:79)
+    if (logits_out) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) if (c < nc) logits_out[((int64_t)img * nc + c) * plane + o] = l[c];
+    }
+  } else {
+    // F.interpolate(logit, ori_shape, 'bilinear', align_corners=False) on the averaged logits (infer.py:151)
+    const Tap ty = make_tap(oy, H, (float)H / (float)Ho), tx = make_tap(ox, W, (float)W / (float)Wo);
+    const int64_t o00 = (int64_t)ty.i0 * W + tx.i0, o01 = (int64_t)ty.i0 * W + tx.i1;
+    const int64_t o10 = (int64_t)ty.i1 * W + tx.i0, o11 = (int64_t)ty.i1 * W + tx.i1;
+    const float c00 = ct ? ct[o00] : 1.f, c01 = ct ? ct[o01] : 1.f, c10 = ct ? ct[o10] : 1.f, c11 = ct ? ct[o11] : 1.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) if (c < nc) {
+      const float* p = cv + c * plane;
+      const float a = p[o00] / c00, b = p[o01] / c01, cc = p[o10] / c10, d = p[o11] / c11;
+      const float top = a + tx.f * (b - a), bot = cc + tx.f * (d - cc);
+      l[c] = top + ty.f * (bot - top);
+    }
+  }
+  const int best = softmax_argmax<NC>(l, nc, prob);
+  store_label(labels, label_dtype, idx, best);
+  if (probs_out) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) if (c < nc) probs_out[((int64_t)img * nc + c) * oplane + (int64_t)oy * Wo + ox] = prob[c];
+  }
+}
+
+// a5 + a6 + a7 in one pass over the label map.
+template <typename T, int NC>
+__global__ void __launch_bounds__(256)
+stitch_argmax_fused_kernel(const T* __restrict__ half_logits, void* __restrict__ labels, int label_dtype,
+                           float* __restrict__ logits_out, int n_win, int nc, int hc, int wc, int H, int W,
+                           const int32_t* __restrict__ win_img, const int32_t* __restrict__ win_y0,
+                           const int32_t* __restrict__ win_x0) {
+  __shared__ WinList wl;
+  __shared__ int warp_cnt[8];
+  const int img = blockIdx.z;
+  const int tx0 = blockIdx.x * TILE_X, ty0 = blockIdx.y * TILE_Y;
+  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, hc, wc, win_img, win_y0, win_x0);
+  const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int hh = hc / 2, hw = wc / 2;
+  const int n = wl.n < 0 ? n_win : wl.n;
+  float acc[NC], prob[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+  float cnt = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const int w = wl.n < 0 ? i : wl.idx[i];
+    if (wl.n < 0 && __ldg(win_img + w) != img) continue;
+    const int ly = y - __ldg(win_y0 + w), lx = x - __ldg(win_x0 + w);
+    if (ly < 0 || ly >= hc || lx < 0 || lx >= wc) continue;
+    cnt += 1.f;
+    const Tap ty = make_tap(ly, hh, 0.5f), tx = make_tap(lx, hw, 0.5f);
+    const T* src = half_logits + (int64_t)w * nc * hh * hw;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) if (c < nc) acc[c] += bilerp<T>(src + (int64_t)c * hh * hw, hw, ty, tx);
+  }
+  const int64_t plane = (int64_t)H * W, o = (int64_t)y * W + x;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) if (c < nc) acc[c] = acc[c] / cnt;
+  if (logits_out) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) if (c < nc) logits_out[((int64_t)img * nc + c) * plane + o] = acc[c];
+  }
+  const int best = softmax_argmax<NC>(acc, nc, prob);
+  store_label(labels, label_dtype, (int64_t)img * plane + o, best);
+}
+
+__global__ void __launch_bounds__(256)
+calculate_area_kernel(const int32_t* __restrict__ pred, const int32_t* __restrict__ label, int64_t n, int nc,
+                      int ignore_index, unsigned long long* __restrict__ areas) {
+  extern __shared__ unsigned int hist[];   // 3*nc
+  for (int i = threadIdx.x; i < 3 * nc; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = label[i], p = pred[i];
+    if (l == ignore_index) continue;            // mask = label != ignore_index (metrics.py:44)
+    if (p >= 0 && p < nc) atomicAdd(&hist[nc + p], 1u);
+    if (l >= 0 && l < nc) atomicAdd(&hist[2 * nc + l], 1u);
+    if (p == l && p >= 0 && p < nc) atomicAdd(&hist[p], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * nc; i += blockDim.x)
+    if (hist[i]) atomicAdd(areas + i, (unsigned long long)hist[i]);
+}
+
+}  // namespace emrt
+
+using namespace emrt;
+
+extern "C" int emrt_upsample2x(const void* in, float* out, int n, int nc, int h, int w, int in_dtype, void* stream) {
+  EMRT_REQUIRE(in && out && n > 0 && nc > 0 && h > 0 && w > 0, "bad upsample2x arguments");
+  const int64_t total = (int64_t)n * nc * 4 * h * w;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = as_stream(stream);
+  if (in_dtype == EMRT_F32) upsample2x_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, out, (int64_t)n * nc, h, w);
+  else if (in_dtype == EMRT_BF16) upsample2x_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, out, (int64_t)n * nc, h, w);
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad in_dtype %d", in_dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_window_accumulate(const float* win_logits, float* canvas, float* count, int n_win, int n_img,
+                                      int nc, int hc, int wc, int H, int W, const int32_t* win_img,
+                                      const int32_t* win_y0, const int32_t* win_x0, void* stream) {
+  EMRT_REQUIRE(win_logits && canvas && win_img && win_y0 && win_x0, "NULL pointer");
+  EMRT_REQUIRE(n_win > 0 && n_img > 0 && nc > 0 && hc > 0 && wc > 0 && H > 0 && W > 0, "non-positive dimension");
+  dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, n_img), block(TILE_X, TILE_Y);
+  window_accumulate_kernel<<<grid, block, 0, as_stream(stream)>>>(win_logits, canvas, count, n_win, nc, hc, wc, H, W,
+                                                                   win_img, win_y0, win_x0);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_finalize_argmax(const float* canvas, const float* count, void* labels, int label_dtype,
+                                    float* probs_out, float* logits_out, int n_img, int nc, int H, int W, int Ho,
+                                    int Wo, void* stream) {
+  EMRT_REQUIRE(canvas && labels, "NULL pointer");
+  EMRT_REQUIRE(n_img > 0 && nc > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "non-positive dimension");
+  EMRT_REQUIRE(label_dtype == EMRT_I32 || label_dtype == EMRT_U8, "label_dtype must be I32 or U8");
+  EMRT_REQUIRE(!logits_out || (Ho == H && Wo == W), "logits_out needs Ho==H and Wo==W");
+  if (nc > 32) return set_error(EMRT_ERR_UNSUPPORTED, "nc=%d > 32", nc);
+  const int64_t total = (int64_t)n_img * Ho * Wo;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = as_stream(stream);
+  if (nc <= 8)
+    finalize_argmax_kernel<8><<<blocks, 256, 0, st>>>(canvas, count, labels, label_dtype, probs_out, logits_out, n_img, nc, H, W, Ho, Wo);
+  else
+    finalize_argmax_kernel<32><<<blocks, 256, 0, st>>>(canvas, count, labels, label_dtype, probs_out, logits_out, n_img, nc, H, W, Ho, Wo);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_stitch_argmax_fused(const void* half_logits, int in_dtype, void* labels, int label_dtype,
+                                        float* logits_out, int n_win, int n_img, int nc, int hc, int wc, int H, int W,
+                                        const int32_t* win_img, const int32_t* win_y0, const int32_t* win_x0,
+                                        void* stream) {
+  EMRT_REQUIRE(half_logits && labels && win_img && win_y0 && win_x0, "NULL pointer");
+  EMRT_REQUIRE(n_win > 0 && n_img > 0 && nc > 0 && hc > 0 && wc > 0 && H > 0 && W > 0, "non-positive dimension");
+  EMRT_REQUIRE(hc % 2 == 0 && wc % 2 == 0, "window size must be even (x2 upsample of the half-resolution logits)");
+  EMRT_REQUIRE(label_dtype == EMRT_I32 || label_dtype == EMRT_U8, "label_dtype must be I32 or U8");
+  if (nc > 32) return set_error(EMRT_ERR_UNSUPPORTED, "nc=%d > 32", nc);
+  dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, n_img), block(TILE_X, TILE_Y);
+  cudaStream_t st = as_stream(stream);
+#define EMRT_ST(T, NC)                                                                                           \
+  stitch_argmax_fused_kernel<T, NC><<<grid, block, 0, st>>>((const T*)half_logits, labels, label_dtype, logits_out, \
+                                                            n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0)
+  if (in_dtype == EMRT_F32) { if (nc <= 8) EMRT_ST(float, 8); else EMRT_ST(float, 32); }
+  else if (in_dtype == EMRT_BF16) { if (nc <= 8) EMRT_ST(__nv_bfloat16, 8); else EMRT_ST(__nv_bfloat16, 32); }
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad in_dtype %d", in_dtype);
+#undef EMRT_ST
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_calculate_area(const int32_t* pred, const int32_t* label, int64_t n, int nc, int ignore_index,
+                                   long long* areas, void* stream) {
+  EMRT_REQUIRE(pred && label && areas && n > 0 && nc > 0 && nc <= 1024, "bad calculate_area arguments");
+  const int64_t want = (n + 255) / 256;
+  const unsigned blocks = (unsigned)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  calculate_area_kernel<<<blocks, 256, 3 * nc * sizeof(unsigned int), as_stream(stream)>>>(
+      pred, label, n, nc, ignore_index, reinterpret_cast<unsigned long long*>(areas));
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}

@@ -1,0 +1,188 @@
+"""Host-side mirror of the reference's multi-scale deformable attention surface.
+
+Mirrors (same names, argument meaning, state-dict keys, error behaviour):
+  * ``MSDeformableAttention``  — src/models/EMRT_utils/transformer_encoder_decoder.py:21-107
+  * ``deformable_attention_core_func`` — src/models/EMRT_utils/utils.py:64-97
+Paddle is not installable in this image, so the tensor container here is torch (device memory + streams only);
+``emrt_b200/paddle_shim.py`` is the same shim over ``paddle.Tensor``.  All arithmetic runs in libemrt_b200.so.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+
+_shape_cache = {}
+
+
+def shapes_to_host(value_spatial_shapes) -> Tuple[Tuple[int, int], ...]:
+    """The reference passes an int64 Tensor [L,2] and calls .tolist()/.numpy() on it >= 3 times per forward
+    (utils.py:77,82; t_e_d.py:81,167-169 — each a device sync).  We read it once and cache by storage."""
+    if isinstance(value_spatial_shapes, torch.Tensor):
+        key = (value_spatial_shapes.data_ptr(), value_spatial_shapes._version, tuple(value_spatial_shapes.shape))
+        hit = _shape_cache.get(key)
+        if hit is None:
+            hit = tuple((int(h), int(w)) for h, w in value_spatial_shapes.tolist())
+            if len(_shape_cache) > 64:
+                _shape_cache.clear()
+            _shape_cache[key] = hit
+        return hit
+    return tuple((int(h), int(w)) for h, w in value_spatial_shapes)
+
+
+def deformable_attention_core_func(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """Drop-in for utils.py:64-97.  value [bs,Lv,M,D]; sampling_locations [bs,Lq,M,L,P,2] in [0,1];
+    attention_weights [bs,Lq,M,L,P] -> [bs,Lq,M*D].  fp32 or bf16 value; loc/attn fp32, fp16 or bf16."""
+    shapes = shapes_to_host(value_spatial_shapes)
+    loc, attn = sampling_locations, attention_weights
+    if value.dtype == torch.float32 and loc.dtype != torch.float32:
+        loc, attn = loc.float(), attn.float()
+    return ops.msda_gather_fwd(value.contiguous(), loc.contiguous(), attn.contiguous(), shapes,
+                               mode=L.LOC_NORMALIZED)
+
+
+class PaddleLinear(nn.Module):
+    """paddle.nn.Linear parameter container: weight [in, out], bias [out]; y = x @ W + b."""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        bound = 1.0 / math.sqrt(in_features)
+        self.weight = nn.Parameter(torch.empty(in_features, out_features).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.zeros(out_features))
+
+
+class MSDeformableAttention(nn.Module):
+    """Multi-Scale Deformable Attention Module (transformer_encoder_decoder.py:21-107) on sm_100a kernels.
+
+    fp32 inputs run the parity path (fp32 SIMT projections, fp32 gather).  bf16 inputs run the B200 path:
+    bf16 weights packed once into K-major [out,in] operands, tcgen05/TMEM/TMA projections with the
+    softmax + offset epilogue fused, fp16 pixel offsets, bf16x8 gather.
+    """
+
+    def __init__(self, embed_dim=256, num_heads=8, num_levels=4, num_points=4, lr_mult=0.1):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.num_levels = num_levels
+        self.num_points = num_points
+        self.total_points = num_heads * num_levels * num_points
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == self.embed_dim, "embed_dim must be divisible by num_heads"
+        self.sampling_offsets = PaddleLinear(embed_dim, self.total_points * 2)
+        self.attention_weights = PaddleLinear(embed_dim, self.total_points)
+        self.value_proj = PaddleLinear(embed_dim, embed_dim)
+        self.output_proj = PaddleLinear(embed_dim, embed_dim)
+        self.lr_mult = lr_mult
+        self.gemm_impl = L.IMPL_AUTO      # tests may force L.IMPL_SIMT / L.IMPL_TCGEN05
+        self._packed = None
+        self._reset_parameters()
+
+    @torch.no_grad()
+    def _reset_parameters(self):
+        # transformer_encoder_decoder.py:46-63
+        self.sampling_offsets.weight.zero_()
+        thetas = torch.arange(self.num_heads, dtype=torch.float32) * (2.0 * math.pi / self.num_heads)
+        grid_init = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid_init = grid_init / grid_init.abs().max(-1, keepdim=True)[0]
+        grid_init = grid_init.reshape(self.num_heads, 1, 1, 2).repeat(1, self.num_levels, self.num_points, 1)
+        scaling = torch.arange(1, self.num_points + 1, dtype=torch.float32).reshape(1, 1, -1, 1)
+        grid_init = grid_init * scaling
+        self.sampling_offsets.bias.copy_(grid_init.flatten())
+        self.attention_weights.weight.zero_()
+        self.attention_weights.bias.zero_()
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        self.value_proj.bias.zero_()
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        self.output_proj.bias.zero_()
+
+    # -- weight packing for the bf16 path ----------------------------------------------------------------
+    def _weights_version(self):
+        ps = (self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
+              self.attention_weights.bias, self.value_proj.weight, self.value_proj.bias,
+              self.output_proj.weight, self.output_proj.bias)
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def packed_weights(self):
+        """bf16 [out,in] (K-major) operands for the tcgen05 projections: Wv [C,C], Wq [3*MLP, C] =
+        [sampling_offsets ; attention_weights], Wo [C,C]; fp32 biases.  Re-packed only when a parameter changed."""
+        ver = self._weights_version()
+        if self._packed is not None and self._packed[0] == ver:
+            return self._packed[1]
+        C_, tp = self.embed_dim, self.total_points
+        dev = self.value_proj.weight.device
+        wv = torch.empty((C_, C_), dtype=torch.bfloat16, device=dev)
+        wq = torch.empty((3 * tp, C_), dtype=torch.bfloat16, device=dev)
+        wo = torch.empty((C_, C_), dtype=torch.bfloat16, device=dev)
+        with torch.no_grad():
+            ops.pack_weight(self.value_proj.weight.detach().contiguous(), wv)
+            ops.pack_weight(self.sampling_offsets.weight.detach().contiguous(), wq, 0)
+            ops.pack_weight(self.attention_weights.weight.detach().contiguous(), wq, 2 * tp)
+            ops.pack_weight(self.output_proj.weight.detach().contiguous(), wo)
+            bq = torch.cat([self.sampling_offsets.bias.detach(), self.attention_weights.bias.detach()]).float().contiguous()
+            packed = dict(wv=wv, wq=wq, wo=wo, bv=self.value_proj.bias.detach().float().contiguous(), bq=bq,
+                          bo=self.output_proj.bias.detach().float().contiguous())
+        self._packed = (ver, packed)
+        return packed
+
+    # -- forward -----------------------------------------------------------------------------------------
+    def forward(self, query, reference_points, value, value_spatial_shapes, value_mask=None):
+        """
+        query [bs, Lq, C]; reference_points [bs, Lq, n_levels, 2] in [0,1]; value [bs, Lv, C];
+        value_spatial_shapes [n_levels, 2] (H, W); value_mask [bs, Lv] (non-zero = keep)  ->  [bs, Lq, C]
+        """
+        bs, Len_q = query.shape[:2]
+        Len_v = value.shape[1]
+        shapes = shapes_to_host(value_spatial_shapes)
+        assert sum(h * w for h, w in shapes) == Len_v          # transformer_encoder_decoder.py:81
+        assert len(shapes) == self.num_levels
+        if not query.is_cuda:
+            raise L.EmrtError("emrt_b200.MSDeformableAttention needs CUDA tensors (no CPU fallback)")
+        if query.dtype == torch.float32:
+            return self._forward_fp32(query, reference_points, value, shapes, value_mask)
+        if query.dtype == torch.bfloat16:
+            return self._forward_bf16(query, reference_points, value, shapes, value_mask)
+        raise L.EmrtError(f"unsupported dtype {query.dtype}")
+
+    def _forward_fp32(self, query, ref, value, shapes, value_mask):
+        M, P, D = self.num_heads, self.num_points, self.head_dim
+        bs, Len_q = query.shape[:2]
+        mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
+        v = ops.linear(value.contiguous(), self.value_proj.weight.detach(), self.value_proj.bias.detach(),
+                       epilogue=L.EPI_ROW_MASK if mask is not None else L.EPI_NONE, row_scale=mask, impl=L.IMPL_SIMT)
+        off = ops.linear(query.contiguous(), self.sampling_offsets.weight.detach(), self.sampling_offsets.bias.detach(),
+                         impl=L.IMPL_SIMT)
+        logit = ops.linear(query.contiguous(), self.attention_weights.weight.detach(),
+                           self.attention_weights.bias.detach(), impl=L.IMPL_SIMT)
+        loc, attn = ops.msda_softmax_loc(off, logit, shapes, M, P, ref=ref.float().contiguous(),
+                                         out_dtype=torch.float32, mode=L.LOC_NORMALIZED)
+        out = ops.msda_gather_fwd(v.view(bs, -1, M, D), loc, attn, shapes, mode=L.LOC_NORMALIZED)
+        return ops.linear(out, self.output_proj.weight.detach(), self.output_proj.bias.detach(), impl=L.IMPL_SIMT)
+
+    def _forward_bf16(self, query, ref, value, shapes, value_mask):
+        M, P, D = self.num_heads, self.num_points, self.head_dim
+        LP = self.num_levels * P
+        bs, Len_q = query.shape[:2]
+        pk = self.packed_weights()
+        mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
+        impl = self.gemm_impl
+        v = ops.linear(value.contiguous(), pk["wv"], pk["bv"], w_transposed=True,
+                       epilogue=L.EPI_ROW_MASK if mask is not None else L.EPI_NONE, row_scale=mask, impl=impl)
+        ref32 = ref.float().contiguous()
+        if impl == L.IMPL_SIMT:
+            raw = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float32,
+                             impl=L.IMPL_SIMT)
+            tp2 = 2 * self.total_points
+            off_px, attn = ops.msda_softmax_loc(raw[..., :tp2], raw[..., tp2:], shapes, M, P, out_dtype=torch.float16,
+                                                mode=L.LOC_PIXEL_OFFSET)
+        else:
+            off_px, attn = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True,
+                                      y_dtype=torch.float16, epilogue=L.EPI_MSDA_QPROJ, qproj_group=LP, impl=impl)
+            off_px = off_px.view(bs, Len_q, M, self.num_levels, P, 2)
+            attn = attn.view(bs, Len_q, M, self.num_levels, P)
+        out = ops.msda_gather_fwd(v.view(bs, -1, M, D), off_px, attn, shapes, ref=ref32, mode=L.LOC_PIXEL_OFFSET)
+        return ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl)

@@ -1,0 +1,208 @@
+"""Operator layer: one Python function per C-ABI entry point, taking torch CUDA tensors.
+
+torch is used for device memory and streams only; all arithmetic happens inside libemrt_b200.so.
+Every function raises on a non-CUDA tensor — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16, torch.int32: L.I32, torch.uint8: L.U8}
+_TD = {v: k for k, v in _DT.items()}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise L.EmrtError(f"unsupported dtype {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise L.EmrtError("emrt_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise L.EmrtError("emrt_b200 ops need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def level_tables(shapes: Sequence[Tuple[int, int]]):
+    hw, start, acc = [], [], 0
+    for h, w in shapes:
+        hw += [int(h), int(w)]
+        start.append(acc)
+        acc += int(h) * int(w)
+    return L.i32_array(hw), L.i32_array(start), acc
+
+
+def device_check():
+    L.check(L.load().emrt_device_check())
+
+
+def launch_count() -> int:
+    return int(L.load().emrt_launch_count())
+
+
+def reset_launch_count():
+    L.load().emrt_reset_launch_count()
+
+
+# ---- a3 ------------------------------------------------------------------------------------------------------
+def msda_gather_fwd(value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, out=None):
+    """value [B,Lv,M,D]; loc [B,Lq,M,L,P,2]; attn [B,Lq,M,L,P]; ref [Bref,Lq,L,2] f32 (PIXEL_OFFSET) -> [B,Lq,M*D]."""
+    lib = L.load()
+    B, Lv, M, D = value.shape
+    _, Lq, _, nL, P, _ = loc.shape
+    hw, start, total = level_tables(shapes)
+    if out is None:
+        out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    rbs = 0 if ref is None or ref.shape[0] == 1 else Lq * nL * 2
+    L.check(lib.emrt_msda_gather_fwd(_ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(out), B, Lq, Lv, M, D,
+                                     nL, P, hw, start, _dt(value), _dt(loc), mode, _stream()))
+    return out
+
+
+def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED):
+    lib = L.load()
+    B, Lv, M, D = value.shape
+    _, Lq, _, nL, P, _ = loc.shape
+    hw, start, total = level_tables(shapes)
+    gv = torch.zeros((B, Lv, M, D), dtype=torch.float32, device=value.device)
+    gl = torch.empty(tuple(loc.shape), dtype=torch.float32, device=value.device)
+    ga = torch.empty(tuple(attn.shape), dtype=torch.float32, device=value.device)
+    rbs = 0 if ref is None or ref.shape[0] == 1 else Lq * nL * 2
+    L.check(lib.emrt_msda_gather_bwd(_ptr(grad_out), _ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(gv),
+                                     _ptr(gl), _ptr(ga), B, Lq, Lv, M, D, nL, P, hw, start, _dt(value), _dt(loc), mode,
+                                     _stream()))
+    return gv, gl, ga
+
+
+# ---- nn.Linear -----------------------------------------------------------------------------------------------
+def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_NONE, row_scale=None, residual=None,
+           ln_gamma=None, ln_beta=None, ln_eps=1e-5, qproj_group=0, impl=L.IMPL_AUTO, out=None, out2=None):
+    """y = epilogue(x @ W + bias).  x [..., K]; W [K,N] (Paddle layout) or [N,K] when w_transposed."""
+    lib = L.load()
+    K = x.shape[-1]
+    rows = x.numel() // K
+    N = w.shape[0] if w_transposed else w.shape[1]
+    assert (w.shape[1] if w_transposed else w.shape[0]) == K, "weight/in-feature mismatch"
+    ydt = y_dtype if y_dtype is not None else x.dtype
+    if epilogue & L.EPI_MSDA_QPROJ:
+        n_pts = N // 3
+        if out is None:
+            out = torch.empty((*x.shape[:-1], 2 * n_pts), dtype=ydt, device=x.device)
+        if out2 is None:
+            out2 = torch.empty((*x.shape[:-1], n_pts), dtype=ydt, device=x.device)
+    elif out is None:
+        out = torch.empty((*x.shape[:-1], N), dtype=ydt, device=x.device)
+    a = L.LinearArgs()
+    a.x, a.w, a.bias, a.y = _ptr(x), _ptr(w), _ptr(bias), _ptr(out)
+    a.rows, a.K, a.N = rows, K, N
+    a.x_dtype, a.w_dtype, a.y_dtype, a.w_transposed = _dt(x), _dt(w), _DT[ydt], int(bool(w_transposed))
+    a.epilogue = int(epilogue)
+    a.row_scale = _ptr(row_scale)
+    a.residual, a.ln_gamma, a.ln_beta, a.ln_eps = _ptr(residual), _ptr(ln_gamma), _ptr(ln_beta), float(ln_eps)
+    a.y2 = _ptr(out2)
+    a.qproj_group = int(qproj_group)
+    a.impl = int(impl)
+    L.check(lib.emrt_linear_fwd(C.byref(a), _stream()))
+    return (out, out2) if (epilogue & L.EPI_MSDA_QPROJ) else out
+
+
+def pack_weight(src, dst, dst_row0=0):
+    """dst[dst_row0 + n, k] = bf16(src[k, n]); src is a Paddle-layout [K,N] weight."""
+    K, N = src.shape
+    assert dst.dtype == torch.bfloat16 and dst.shape[1] == K and dst.shape[0] >= dst_row0 + N
+    L.check(L.load().emrt_pack_weight(_ptr(src), _dt(src), _ptr(dst), K, N, int(dst_row0), _stream()))
+    return dst
+
+
+def msda_softmax_loc(off_raw, logit_raw, shapes, M, P, ref=None, out_dtype=torch.float32, mode=L.LOC_NORMALIZED):
+    """off_raw f32 [B,Lq,M*L*P*2] (may be a column slice view with row stride), logit_raw f32 [B,Lq,M*L*P]."""
+    lib = L.load()
+    B, Lq = off_raw.shape[:2]
+    nL = len(shapes)
+    hw, _, _ = level_tables(shapes)
+    for t in (off_raw, logit_raw):
+        if not t.is_cuda or t.dtype != torch.float32 or t.stride(-1) != 1:
+            raise L.EmrtError("softmax_loc needs f32 CUDA inputs with unit inner stride")
+    loc = torch.empty((B, Lq, M, nL, P, 2), dtype=out_dtype, device=off_raw.device)
+    attn = torch.empty((B, Lq, M, nL, P), dtype=out_dtype, device=off_raw.device)
+    rbs = 0 if ref is None or ref.shape[0] == 1 else Lq * nL * 2
+    L.check(lib.emrt_msda_softmax_loc(C.c_void_p(off_raw.data_ptr()), off_raw.stride(-2),
+                                      C.c_void_p(logit_raw.data_ptr()), logit_raw.stride(-2), _ptr(ref), rbs,
+                                      _ptr(loc), _ptr(attn), B, Lq, M, nL, P, hw, _DT[out_dtype], mode, _stream()))
+    return loc, attn
+
+
+def add_layernorm(x, residual, gamma, beta, eps=1e-5, out=None):
+    N = x.shape[-1]
+    rows = x.numel() // N
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().emrt_add_layernorm(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out), rows, N,
+                                        float(eps), _dt(x), _stream()))
+    return out
+
+
+# ---- head tail -----------------------------------------------------------------------------------------------
+def upsample2x(x):
+    n, nc, h, w = x.shape
+    out = torch.empty((n, nc, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    L.check(L.load().emrt_upsample2x(_ptr(x), _ptr(out), n, nc, h, w, _dt(x), _stream()))
+    return out
+
+
+def window_accumulate(win_logits, canvas, count, win_img, win_y0, win_x0):
+    n_win, nc, hc, wc = win_logits.shape
+    n_img, _, H, W = canvas.shape
+    assert win_logits.dtype == torch.float32 and canvas.dtype == torch.float32
+    L.check(L.load().emrt_window_accumulate(_ptr(win_logits), _ptr(canvas), _ptr(count), n_win, n_img, nc, hc, wc, H,
+                                            W, _ptr(win_img), _ptr(win_y0), _ptr(win_x0), _stream()))
+    return canvas, count
+
+
+def finalize_argmax(canvas, count=None, out_hw=None, label_dtype=torch.int32, want_probs=False, want_logits=False):
+    n_img, nc, H, W = canvas.shape
+    Ho, Wo = (H, W) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+    labels = torch.empty((n_img, 1, Ho, Wo), dtype=label_dtype, device=canvas.device)
+    probs = torch.empty((n_img, nc, Ho, Wo), dtype=torch.float32, device=canvas.device) if want_probs else None
+    logits = torch.empty((n_img, nc, H, W), dtype=torch.float32, device=canvas.device) if want_logits else None
+    L.check(L.load().emrt_finalize_argmax(_ptr(canvas), _ptr(count), _ptr(labels), _DT[label_dtype], _ptr(probs),
+                                          _ptr(logits), n_img, nc, H, W, Ho, Wo, _stream()))
+    return labels, probs, logits
+
+
+def stitch_argmax_fused(half_logits, win_img, win_y0, win_x0, n_img, H, W, label_dtype=torch.int32,
+                        want_logits=False, labels=None):
+    n_win, nc, hh, hw = half_logits.shape
+    if labels is None:
+        labels = torch.empty((n_img, 1, H, W), dtype=label_dtype, device=half_logits.device)
+    logits = torch.empty((n_img, nc, H, W), dtype=torch.float32, device=half_logits.device) if want_logits else None
+    L.check(L.load().emrt_stitch_argmax_fused(_ptr(half_logits), _dt(half_logits), _ptr(labels), _dt(labels),
+                                              _ptr(logits), n_win, n_img, nc, 2 * hh, 2 * hw, H, W, _ptr(win_img),
+                                              _ptr(win_y0), _ptr(win_x0), _stream()))
+    return labels, logits
+
+
+def calculate_area(pred, label, num_classes, ignore_index=255):
+    """-> int64 [3, num_classes] = (intersect, pred, label) areas (src/utils/metrics.py:20-69)."""
+    pred = pred.reshape(-1).to(torch.int32).contiguous()
+    label = label.reshape(-1).to(torch.int32).contiguous()
+    if pred.shape != label.shape:
+        raise ValueError("Shape of `pred` and `label should be equal")
+    areas = torch.zeros((3, num_classes), dtype=torch.int64, device=pred.device)
+    L.check(L.load().emrt_calculate_area(_ptr(pred), _ptr(label), pred.numel(), num_classes, int(ignore_index),
+                                         _ptr(areas), _stream()))
+    return areas

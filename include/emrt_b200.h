@@ -1,0 +1,166 @@
+/* emrt_b200 — C ABI of the B200-native (sm_100a) EMRT hot path.
+ *
+ * The reference (peach-xiao/EMRT) has no FFI / custom-op interface: its hot path is a composition of
+ * PaddlePaddle Python ops.  Each entry point below names the reference code it replaces; the Python shims in
+ * emrt_b200/{msda,infer,paddle_shim}.py bind them with ctypes.
+ * Paths are relative to /root/reference/semantic_segmentation/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - the library allocates nothing the caller can see; scratch is passed in (query *_workspace_bytes);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value: 0 on success, negative emrt_status otherwise; emrt_last_error() gives the text
+ *     (thread-local);
+ *   - shapes / level tables are HOST int32 arrays, copied by value into the launch (no device->host sync);
+ *   - no CPU fallback and no other architecture: emrt_device_check() fails unless the current device is
+ *     compute capability 10.x.
+ */
+#ifndef EMRT_B200_H_
+#define EMRT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMRT_ABI_VERSION 1
+#define EMRT_MAX_LEVELS 8
+
+typedef enum emrt_status {
+  EMRT_OK = 0,
+  EMRT_ERR_INVALID_ARGUMENT = -1,
+  EMRT_ERR_CUDA = -2,
+  EMRT_ERR_UNSUPPORTED = -3,
+  EMRT_ERR_ARCH = -4,
+  EMRT_ERR_WORKSPACE = -5
+} emrt_status;
+
+typedef enum emrt_dtype { EMRT_F32 = 0, EMRT_BF16 = 1, EMRT_F16 = 2, EMRT_I32 = 3, EMRT_U8 = 4 } emrt_dtype;
+
+/* How sampling positions are given to the gather kernels. */
+typedef enum emrt_loc_mode {
+  /* `loc` holds normalised absolute locations [B,Lq,M,L,P,2] (x,y) in [0,1] — exactly the
+   * `sampling_locations` argument of deformable_attention_core_func (src/models/EMRT_utils/utils.py:64). */
+  EMRT_LOC_NORMALIZED = 0,
+  /* `loc` holds the raw sampling_offsets output in PIXELS [B,Lq,M,L,P,2] and `ref` the reference points
+   * [Bref,Lq,L,2] (Bref = B or 1) in [0,1]; the kernel forms x = ref_x*W_l + off_x - 0.5, which is
+   * transformer_encoder_decoder.py:98-102 folded into utils.py:79,87. */
+  EMRT_LOC_PIXEL_OFFSET = 1
+} emrt_loc_mode;
+
+/* Epilogues of emrt_linear_fwd (bit flags). */
+typedef enum emrt_epilogue {
+  EMRT_EPI_NONE = 0,
+  EMRT_EPI_ROW_MASK = 1,      /* y[r,:] *= row_scale[r]      (value_mask, t_e_d.py:84-86)              */
+  EMRT_EPI_RELU = 2,          /* y = max(y,0)                 (FFN activation, t_e_d.py:158)            */
+  EMRT_EPI_RESIDUAL_LN = 4,   /* y = LayerNorm(residual + y)  (t_e_d.py:199-200; N must be 256)         */
+  EMRT_EPI_MSDA_QPROJ = 8     /* N = M*L*P*3: [offsets | logits] -> pixel offsets + softmax(L*P)         */
+} emrt_epilogue;
+
+int emrt_version(void);
+const char* emrt_last_error(void);
+/* 0 iff the current CUDA device is a compute-capability-10.x part (B200). */
+int emrt_device_check(void);
+/* Number of kernels this library has launched since load / last reset (bench.py's gpu_launches). */
+int64_t emrt_launch_count(void);
+void emrt_reset_launch_count(void);
+
+/* ---- a3: deformable_attention_core_func (src/models/EMRT_utils/utils.py:64-97) -------------------------
+ * value [B,Lv,M,D] (value_dtype: F32|BF16), loc/attn per `mode` (loc_dtype: F32|F16|BF16),
+ * out [B,Lq,M*D] (value_dtype).  shapes_hw_host = {H0,W0,H1,W1,...}, level_start_host = {0,H0*W0,...}.
+ * ref (mode PIXEL_OFFSET only) is F32 [Bref,Lq,L,2], ref_batch_stride = 0 (shared) or Lq*L*2.            */
+int emrt_msda_gather_fwd(const void* value, const void* loc, const void* attn, const float* ref,
+                         int64_t ref_batch_stride, void* out, int B, int Lq, int Lv, int M, int D, int L,
+                         int P, const int32_t* shapes_hw_host, const int32_t* level_start_host,
+                         int value_dtype, int loc_dtype, int mode, void* stream);
+
+/* Backward of the above (what Paddle autograd derives through F.grid_sample, utils.py:87-94).
+ * grad_out [B,Lq,M*D] (value_dtype); grad_value F32 [B,Lv,M,D] MUST be zeroed by the caller (accumulated);
+ * grad_loc F32 [B,Lq,M,L,P,2] (d/d loc in the units of `mode`), grad_attn F32 [B,Lq,M,L,P].              */
+int emrt_msda_gather_bwd(const void* grad_out, const void* value, const void* loc, const void* attn,
+                         const float* ref, int64_t ref_batch_stride, float* grad_value, float* grad_loc,
+                         float* grad_attn, int B, int Lq, int Lv, int M, int D, int L, int P,
+                         const int32_t* shapes_hw_host, const int32_t* level_start_host, int value_dtype,
+                         int loc_dtype, int mode, void* stream);
+
+/* ---- nn.Linear (transformer_encoder_decoder.py:36-42,83,89,92,106,118,121) ------------------------------
+ * y[rows,N] = epilogue(x[rows,K] @ W + bias).  W is given either in Paddle's own layout [K,N]
+ * (w_transposed = 0) or pre-packed [N,K] (w_transposed = 1, see emrt_pack_weight).  x_dtype F32 runs the
+ * fp32 SIMT path (parity mode); BF16 runs the tcgen05/TMEM/TMA path (w must then be BF16 [N,K]).
+ * bias is always F32 [N].  y_dtype: F32|BF16|F16.  Extra operands by epilogue flag:
+ *   ROW_MASK: row_scale F32 [rows];  RESIDUAL_LN: residual (x_dtype) [rows,N], ln_gamma/ln_beta F32 [N];
+ *   MSDA_QPROJ: y = pixel offsets [rows, 2N/3] (y_dtype), y2 = softmax'd weights [rows, N/3] (y_dtype),
+ *               softmax group = qproj_group (= L*P).                                                      */
+typedef struct emrt_linear_args {
+  const void* x; const void* w; const float* bias; void* y;
+  int64_t rows; int32_t K; int32_t N;
+  int32_t x_dtype; int32_t w_dtype; int32_t y_dtype; int32_t w_transposed;
+  int32_t epilogue;
+  const float* row_scale;
+  const void* residual; const float* ln_gamma; const float* ln_beta; float ln_eps;
+  void* y2; int32_t qproj_group;
+  int32_t impl;               /* 0 = auto, 1 = force SIMT, 2 = force tcgen05 */
+} emrt_linear_args;
+int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
+
+/* Pack Paddle-layout weights: dst[n, k] (BF16, [N_total,K]) = src[k, n] (F32|BF16, [K,N]) for n in
+ * [0,N), written at row offset dst_row0 — lets sampling_offsets.weight and attention_weights.weight be
+ * concatenated into one [M*L*P*3, K] operand.                                                             */
+int emrt_pack_weight(const void* src, int src_dtype, void* dst_bf16, int K, int N, int dst_row0,
+                     void* stream);
+
+/* softmax(L*P) + location arithmetic on raw projections (transformer_encoder_decoder.py:92-102), for the
+ * un-fused path.  off_raw F32 [rows, M*L*P*2] (+bias already applied), logit_raw F32 [rows, M*L*P].
+ * mode NORMALIZED: loc_out = ref + off/(W_l,H_l) (out_dtype), needs ref [Bref,Lq,L,2];
+ * mode PIXEL_OFFSET: loc_out = off_raw converted.  attn_out = softmax (out_dtype).                         */
+int emrt_msda_softmax_loc(const float* off_raw, int64_t off_ld, const float* logit_raw, int64_t logit_ld,
+                          const float* ref, int64_t ref_batch_stride, void* loc_out, void* attn_out, int B,
+                          int Lq, int M, int L, int P, const int32_t* shapes_hw_host, int out_dtype,
+                          int mode, void* stream);
+
+/* y = LayerNorm(residual + x) * gamma + beta over the last dim N (nn.LayerNorm eps 1e-5;
+ * transformer_encoder_decoder.py:199-200, 159-160).  residual may be NULL.  dtype F32|BF16 (x, residual, y). */
+int emrt_add_layernorm(const void* x, const void* residual, const float* gamma, const float* beta, void* y,
+                       int64_t rows, int N, float eps, int dtype, void* stream);
+
+/* ---- a5: UpHead tail (src/models/paddle_EMRT.py:178-180): x2 bilinear, align_corners=False ------------
+ * in [n,nc,h,w] (in_dtype F32|BF16) -> out F32 [n,nc,2h,2w].                                              */
+int emrt_upsample2x(const void* in, float* out, int n, int nc, int h, int w, int in_dtype, void* stream);
+
+/* ---- a6: slide_inference accumulation (src/api/infer.py:69-73) -----------------------------------------
+ * canvas F32 [n_img,nc,H,W] += window logits F32 [n_win,nc,hc,wc] at (win_y0,win_x0) of image win_img;
+ * count F32 [n_img,1,H,W] += 1.  Deterministic: every canvas pixel sums its covering windows in window-index
+ * order (the reference's r-major, c order when windows are listed that way).  win_* are DEVICE int32 arrays. */
+int emrt_window_accumulate(const float* win_logits, float* canvas, float* count, int n_win, int n_img,
+                           int nc, int hc, int wc, int H, int W, const int32_t* win_img,
+                           const int32_t* win_y0, const int32_t* win_x0, void* stream);
+
+/* ---- a6 (divide) + a7: ss_inference tail (src/api/infer.py:75-79,150-154; predict.py:162-166) -----------
+ * logits = canvas/count (count may be NULL => 1); optional bilinear resize to (Ho,Wo) (align_corners=False);
+ * softmax(axis=1); argmax (first max) -> labels (I32 or U8) [n_img,1,Ho,Wo]; probs_out (F32, optional)
+ * [n_img,nc,Ho,Wo]; logits_out (F32, optional, only when Ho==H && Wo==W) = canvas/count.                  */
+int emrt_finalize_argmax(const float* canvas, const float* count, void* labels, int label_dtype,
+                         float* probs_out, float* logits_out, int n_img, int nc, int H, int W, int Ho, int Wo,
+                         void* stream);
+
+/* ---- a5+a6+a7 fused: half-resolution window logits -> label map, no canvas ------------------------------
+ * half_logits [n_win,nc,hc/2,wc/2] (in_dtype) are the class logits BEFORE UpHead's last x2 upsample.
+ * For every pixel of every image the kernel upsamples each covering window on the fly, sums them in window
+ * index order, divides by the cover count, and takes softmax+argmax.  win_* are DEVICE int32 arrays sorted by
+ * (image, r, c) — the reference order.  labels [n_img,1,H,W] (I32|U8); logits_out optional F32 [n_img,nc,H,W]. */
+int emrt_stitch_argmax_fused(const void* half_logits, int in_dtype, void* labels, int label_dtype,
+                             float* logits_out, int n_win, int n_img, int nc, int hc, int wc, int H, int W,
+                             const int32_t* win_img, const int32_t* win_y0, const int32_t* win_x0,
+                             void* stream);
+
+/* ---- a8: metrics.calculate_area (src/utils/metrics.py:20-69) --------------------------------------------
+ * pred I32 [n], label I32 [n]; areas I64 [3*nc] = {intersect[nc], pred[nc], label[nc]} MUST be zeroed.     */
+int emrt_calculate_area(const int32_t* pred, const int32_t* label, int64_t n, int nc, int ignore_index,
+                        long long* areas, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMRT_B200_H_ */

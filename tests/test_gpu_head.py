@@ -1,0 +1,123 @@
+"""GPU parity tests of the head tail: upsample, window accumulation, finalize, fused stitch+argmax, areas."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import emrt_b200
+from emrt_b200 import ops, infer
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_upsample2x_matches_oracle(cuda_dev):
+    rng = np.random.Generator(np.random.PCG64(0))
+    for shape in [(2, 6, 16, 20), (1, 7, 5, 3), (3, 1, 1, 1)]:
+        x = O.rng_normal(rng, shape)
+        got = ops.upsample2x(torch.from_numpy(x).to(cuda_dev)).cpu()
+        assert (got - O.upsample2x(x)).abs().max() < 1e-5
+        assert np.abs(got.numpy() - O.upsample2x_loop(x)).max() < 1e-5
+        xb = torch.from_numpy(x).bfloat16()
+        gotb = ops.upsample2x(xb.to(cuda_dev)).cpu()
+        assert (gotb - O.upsample2x(xb.float())).abs().max() < 1e-5
+
+
+class LinearPixelModel:
+    """logits = W @ rgb per pixel; exposes the half-resolution logits the fused path consumes."""
+
+    def __init__(self, wmat, dev):
+        self.w = torch.from_numpy(wmat).to(dev)
+
+    def __call__(self, batch):
+        return (torch.einsum("oc,nchw->nohw", self.w, batch.float()),)
+
+
+def test_slide_inference_golden(cuda_dev):
+    g = np.load(os.path.join(GOLD, "slide_small.npz"))
+    model = LinearPixelModel(g["wmat"], cuda_dev)
+    imgs = [torch.from_numpy(g["img0"]).to(cuda_dev), torch.from_numpy(g["img1"]).to(cuda_dev)]
+    crop, stride = tuple(int(v) for v in g["crop"]), tuple(int(v) for v in g["stride"])
+    logits = emrt_b200.slide_inference(model, imgs, crop, stride, 6)
+    for i in range(2):
+        assert tuple(logits[i].shape) == tuple(g[f"logit{i}"].shape)
+        assert np.abs(logits[i].cpu().numpy() - g[f"logit{i}"]).max() < 1e-4
+    ori = [tuple(int(v) for v in o) for o in g["ori"]]
+    preds = emrt_b200.ss_inference(model, imgs, ori, True, None, stride, crop, 6)
+    for i in range(2):
+        assert preds[i].dtype == torch.int32 and tuple(preds[i].shape) == (1, 1) + ori[i]
+        assert (preds[i].cpu().numpy() == g[f"pred{i}"]).mean() >= 0.999
+
+
+class HalfModel:
+    """A model whose full-resolution logits are UpHead's x2 upsample of a half-resolution tensor."""
+
+    def __init__(self, wmat, dev, dtype=torch.float32):
+        self.w = torch.from_numpy(wmat).to(dev)
+        self.dtype = dtype
+
+    def forward_half_logits(self, batch):
+        half = torch.nn.functional.avg_pool2d(batch.float(), 2)
+        return torch.einsum("oc,nchw->nohw", self.w, half).to(self.dtype).contiguous()
+
+    def __call__(self, batch):
+        return (ops.upsample2x(self.forward_half_logits(batch)),)
+
+
+@pytest.mark.parametrize("H,W,crop,stride,nc", [(1024, 1024, 512, 384, 7), (96, 130, 64, 48, 6), (200, 200, 64, 40, 6)])
+def test_fused_stitch_argmax_matches_oracle_and_unfused(cuda_dev, H, W, crop, stride, nc):
+    rng = np.random.Generator(np.random.PCG64(2))
+    wmat = O.rng_normal(rng, (nc, 3), 0.8)
+    imgs = [torch.from_numpy(O.rng_normal(rng, (3, H, W))).to(cuda_dev) for _ in range(2)]
+    model = HalfModel(wmat, cuda_dev)
+    ori = [(H, W)] * 2
+    fused = emrt_b200.ss_inference(model, imgs, ori, True, None, (stride, stride), (crop, crop), nc)
+
+    class NoHalf:           # same model without the fast-path hook -> canvas path
+        def __call__(self, b):
+            return model(b)
+    unfused = emrt_b200.ss_inference(NoHalf(), imgs, ori, True, None, (stride, stride), (crop, crop), nc)
+
+    def cpu_model(b):       # oracle: same half logits, oracle upsample
+        half = torch.nn.functional.avg_pool2d(b, 2)
+        return (O.upsample2x(torch.einsum("oc,nchw->nohw", torch.from_numpy(wmat), half)),)
+    want = O.ss_inference(cpu_model, [i.cpu() for i in imgs], ori, True, None, (stride, stride), (crop, crop), nc)
+    for i in range(2):
+        assert (fused[i].cpu() == want[i]).float().mean().item() >= 0.999
+        assert (unfused[i].cpu() == want[i]).float().mean().item() >= 0.999
+        assert (fused[i] == unfused[i]).float().mean().item() >= 0.9999
+
+
+def test_finalize_resize_softmax_argmax(cuda_dev):
+    rng = np.random.Generator(np.random.PCG64(3))
+    logit = O.rng_normal(rng, (1, 6, 37, 53))
+    for shape in [(37, 53), (80, 64), (20, 100)]:
+        labels, probs, _ = ops.finalize_argmax(torch.from_numpy(logit).to(cuda_dev), None, out_hw=shape, want_probs=True)
+        want = O.ss_inference_tail(logit, shape)
+        assert (labels.cpu() == want).float().mean().item() >= 0.999
+        wp = torch.softmax(O.interpolate_bilinear(logit, shape), 1)
+        assert (probs.cpu() - wp).abs().max() < 1e-5
+    lab8, _, _ = ops.finalize_argmax(torch.from_numpy(logit).to(cuda_dev), None, label_dtype=torch.uint8)
+    assert lab8.dtype == torch.uint8 and torch.equal(lab8.cpu().int(), O.ss_inference_tail(logit, (37, 53)))
+    # ties -> first maximal index
+    tie = torch.zeros(1, 6, 4, 4)
+    tie[:, 2] = 1.0
+    tie[:, 4] = 1.0
+    lab, _, _ = ops.finalize_argmax(tie.to(cuda_dev), None)
+    assert torch.all(lab == 2)
+
+
+def test_calculate_area_matches_oracle(cuda_dev):
+    rng = np.random.Generator(np.random.PCG64(4))
+    n = 512 * 512
+    pred = rng.integers(0, 6, size=n).astype(np.int32)
+    label = rng.integers(0, 6, size=n).astype(np.int32)
+    label[rng.uniform(size=n) < 0.02] = 255
+    got = emrt_b200.calculate_area(torch.from_numpy(pred).to(cuda_dev).reshape(1, 1, 512, 512),
+                                   torch.from_numpy(label).to(cuda_dev).reshape(1, 1, 512, 512), 6).cpu().numpy()
+    ia, pa, la = O.calculate_area(pred, label, 6)
+    assert np.array_equal(got[0], ia) and np.array_equal(got[1], pa) and np.array_equal(got[2], la)
+    with pytest.raises(ValueError):
+        emrt_b200.calculate_area(torch.zeros(4, device=cuda_dev), torch.zeros(5, device=cuda_dev), 6)

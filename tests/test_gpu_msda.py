@@ -1,0 +1,217 @@
+"""GPU parity tests of the MSDA path: CUDA kernels (through the C ABI) vs the CPU oracle on the same seeded inputs.
+Tolerances: fp32 1e-4 relative (of the output's max magnitude), bf16 1e-2 relative (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import emrt_b200
+from emrt_b200 import ops, _lib as L
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FP32_TOL, BF16_TOL = 1e-4, 1e-2
+
+
+def rel_err(got, want):
+    want = torch.as_tensor(want).double()
+    return ((got.detach().double().cpu() - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+def _gather_case(seed, shapes, B, M, D, P, Lq, spread=0.3):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    _, Lv = O.level_tables(shapes)
+    L_ = len(shapes)
+    value = O.rng_normal(rng, (B, Lv, M, D))
+    loc = rng.uniform(-spread, 1 + spread, size=(B, Lq, M, L_, P, 2)).astype(np.float32)
+    attn = rng.uniform(0, 1, size=(B, Lq, M, L_, P)).astype(np.float32)
+    attn /= attn.reshape(B, Lq, M, -1).sum(-1)[..., None, None]
+    return value, loc, attn
+
+
+CASES = [
+    # shapes, B, M, D, P, Lq
+    ([(32, 32), (16, 16), (8, 8)], 2, 8, 32, 6, 1344),       # cfg 1 / cfg 2 geometry (encoder)
+    ([(32, 32), (16, 16), (8, 8)], 3, 8, 32, 6, 110),        # decoder cross-attention, Lq != Lv
+    ([(8, 6), (4, 3), (2, 2)], 1, 2, 32, 6, 37),             # non-square levels, B = 1
+    ([(5, 9)], 2, 3, 16, 5, 13),                             # single level, odd P, M not a power of two, D = 16
+    ([(7, 3), (2, 5)], 2, 4, 64, 3, 9),                      # D = 64
+]
+
+
+@pytest.mark.parametrize("shapes,B,M,D,P,Lq", CASES)
+def test_gather_fwd_fp32_matches_oracle(cuda_dev, shapes, B, M, D, P, Lq):
+    value, loc, attn = _gather_case(0, shapes, B, M, D, P, Lq)
+    want = O.gather_corner_loop(value, shapes, loc, attn)
+    got = emrt_b200.deformable_attention_core_func(torch.from_numpy(value).to(cuda_dev), shapes,
+                                                   torch.from_numpy(loc).to(cuda_dev), torch.from_numpy(attn).to(cuda_dev))
+    assert got.shape == (B, Lq, M * D)
+    assert rel_err(got, want) < FP32_TOL
+    lib_want = O.deformable_attention_core_func(value, shapes, loc, attn)    # the reference's own op composition
+    assert rel_err(got, lib_want) < FP32_TOL
+
+
+@pytest.mark.parametrize("shapes,B,M,D,P,Lq", CASES)
+@pytest.mark.parametrize("loc_dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_gather_fwd_bf16_matches_oracle(cuda_dev, shapes, B, M, D, P, Lq, loc_dtype):
+    value, loc, attn = _gather_case(1, shapes, B, M, D, P, Lq)
+    v16 = torch.from_numpy(value).bfloat16()
+    l16 = torch.from_numpy(loc).to(loc_dtype)
+    a16 = torch.from_numpy(attn).to(loc_dtype)
+    # oracle on exactly the rounded inputs, float64 arithmetic: only the output rounding differs
+    want = O.gather_corner_loop(v16.float().numpy(), shapes, l16.float().numpy(), a16.float().numpy())
+    got = emrt_b200.deformable_attention_core_func(v16.to(cuda_dev), shapes, l16.to(cuda_dev), a16.to(cuda_dev))
+    assert got.dtype == torch.bfloat16
+    assert rel_err(got.float(), want) < BF16_TOL
+
+
+def test_gather_pixel_offset_mode_equals_normalized_mode(cuda_dev):
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    B, M, D, P = 2, 8, 32, 6
+    rng = np.random.Generator(np.random.PCG64(3))
+    _, Lv = O.level_tables(shapes)
+    Lq = Lv
+    value = O.rng_normal(rng, (B, Lv, M, D))
+    off = O.rng_normal(rng, (B, Lq, M, 3, P, 2), 3.0)
+    attn = rng.uniform(0, 1, size=(B, Lq, M, 3, P)).astype(np.float32)
+    ref = O.encoder_reference_points(shapes, B).numpy()
+    norm = np.array([[w, h] for h, w in shapes], np.float32).reshape(1, 1, 1, 3, 1, 2)
+    loc = ref.reshape(B, Lq, 1, 3, 1, 2) + off / norm
+    want = O.gather_corner_loop(value, shapes, loc, attn)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    got = ops.msda_gather_fwd(d(value), d(off), d(attn), shapes, ref=d(ref), mode=L.LOC_PIXEL_OFFSET)
+    assert rel_err(got, want) < FP32_TOL
+    got_shared = ops.msda_gather_fwd(d(value), d(off), d(attn), shapes, ref=d(ref[:1]), mode=L.LOC_PIXEL_OFFSET)
+    assert torch.equal(got, got_shared)          # batch-shared reference points (stride 0)
+    # bf16 value + fp16 pixel offsets (the fused path's storage format)
+    v16, o16, a16 = d(value).bfloat16(), d(off).half(), d(attn).half()
+    loc16 = ref.reshape(B, Lq, 1, 3, 1, 2) + o16.float().cpu().numpy() / norm
+    want16 = O.gather_corner_loop(v16.float().cpu().numpy(), shapes, loc16, a16.float().cpu().numpy())
+    got16 = ops.msda_gather_fwd(v16, o16, a16, shapes, ref=d(ref), mode=L.LOC_PIXEL_OFFSET)
+    assert rel_err(got16.float(), want16) < BF16_TOL
+
+
+def test_gather_properties(cuda_dev):
+    shapes = [(16, 12), (8, 6)]
+    value, loc, attn = _gather_case(5, shapes, 2, 4, 32, 4, 50)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    f = lambda v, l=loc, a=attn: emrt_b200.deformable_attention_core_func(d(v), shapes, d(l), d(a))
+    # all samples outside -> exact zero
+    assert torch.all(f(value, loc * 0 + 2.5) == 0)
+    assert torch.all(f(value, loc * 0 - 1.5) == 0)
+    # linearity in value
+    v2 = np.roll(value, 3, axis=1)
+    assert rel_err(f(2 * value + 3 * v2), (2 * f(value) + 3 * f(v2)).cpu()) < 1e-5
+    # permuting heads permutes output channel blocks
+    perm = [2, 0, 3, 1]
+    out = f(value).reshape(2, 50, 4, 32)
+    outp = f(value[:, :, perm], loc[:, :, perm], attn[:, :, perm]).reshape(2, 50, 4, 32)
+    assert torch.equal(outp, out[:, :, perm])
+    # NaN / huge coordinates contribute nothing (guarded float->int conversion)
+    loc_bad = loc.copy()
+    loc_bad[0, 0, 0, 0, 0] = [1e30, -1e30]
+    assert torch.isfinite(f(value, loc_bad)).all()
+
+
+@pytest.mark.parametrize("mode", ["normalized", "pixel"])
+def test_gather_bwd_matches_autograd_of_oracle(cuda_dev, mode):
+    shapes = [(12, 10), (6, 5), (3, 3)]
+    B, M, D, P, Lq = 2, 4, 32, 6, 40
+    value, loc, attn = _gather_case(7, shapes, B, M, D, P, Lq, spread=0.2)
+    rng = np.random.Generator(np.random.PCG64(8))
+    gout = O.rng_normal(rng, (B, Lq, M * D))
+    tv = torch.from_numpy(value).double().requires_grad_()
+    tl = torch.from_numpy(loc).double().requires_grad_()
+    ta = torch.from_numpy(attn).double().requires_grad_()
+    O.deformable_attention_core_func(tv, shapes, tl, ta).backward(torch.from_numpy(gout).double())
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    if mode == "normalized":
+        gv, gl, ga = ops.msda_gather_bwd(d(gout), d(value), d(loc), d(attn), shapes)
+        want_gl = tl.grad
+    else:
+        # same sample positions expressed as pixel offsets from random reference points
+        ref = rng.uniform(0, 1, size=(B, Lq, len(shapes), 2)).astype(np.float32)
+        norm = np.array([[w, h] for h, w in shapes], np.float64).reshape(1, 1, 1, -1, 1, 2)
+        off = ((loc.astype(np.float64) - ref.reshape(B, Lq, 1, -1, 1, 2)) * norm).astype(np.float32)
+        gv, gl, ga = ops.msda_gather_bwd(d(gout), d(value), d(off), d(attn), shapes, ref=d(ref), mode=L.LOC_PIXEL_OFFSET)
+        want_gl = tl.grad / torch.from_numpy(norm)       # d/d off_px = d/d loc / (W, H)
+    tol = 2e-4 if mode == "normalized" else 2e-3         # pixel mode re-derives positions in fp32
+    assert rel_err(gv, tv.grad) < tol
+    assert rel_err(ga, ta.grad) < tol
+    assert rel_err(gl, want_gl) < tol
+
+
+@pytest.mark.parametrize("rows,K,N,wt", [(300, 256, 256, False), (129, 256, 432, True), (64, 96, 40, False),
+                                         (1000, 1024, 256, True)])
+def test_linear_simt_fp32(cuda_dev, rows, K, N, wt):
+    rng = np.random.Generator(np.random.PCG64(9))
+    x, w, b = O.rng_normal(rng, (rows, K)), O.rng_normal(rng, (K, N), 0.1), O.rng_normal(rng, (N,))
+    scale = rng.uniform(0, 1, size=(rows,)).astype(np.float32)
+    want = np.maximum((x.astype(np.float64) @ w.astype(np.float64) + b) * scale[:, None], 0)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_dev)
+    got = ops.linear(d(x), d(w.T if wt else w), d(b), w_transposed=wt, epilogue=L.EPI_ROW_MASK | L.EPI_RELU,
+                     row_scale=d(scale), impl=L.IMPL_SIMT)
+    assert rel_err(got, want) < 1e-5
+
+
+def _load_module(params, C, M, Lv, P, dev):
+    m = emrt_b200.MSDeformableAttention(C, M, Lv, P).to(dev)
+    with torch.no_grad():
+        for name, arr in params.items():
+            mod, leaf = name.split(".")
+            getattr(getattr(m, mod), leaf).copy_(torch.from_numpy(arr))
+    return m
+
+
+def test_msda_module_fp32_golden(cuda_dev):
+    g = np.load(os.path.join(GOLD, "msda_small.npz"))
+    shapes = [tuple(s) for s in g["shapes"].tolist()]
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p.")}
+    m = _load_module(params, 64, 2, 3, 6, cuda_dev)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    got = m(d(g["query"]), d(g["ref"]), d(g["value"]), torch.tensor(shapes), d(g["mask"]))
+    assert rel_err(got, g["out"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("Lq_mode", ["encoder", "decoder"])
+def test_msda_module_fp32_cfg1_shape(cuda_dev, Lq_mode):
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    B, C, M, P = 2, 256, 8, 6
+    rng = np.random.Generator(np.random.PCG64(0))
+    _, Lv = O.level_tables(shapes)
+    params = O.make_msda_params(1234, C, M, 3, P)
+    v = O.rng_normal(rng, (B, Lv, C))
+    if Lq_mode == "encoder":
+        q, ref = O.rng_normal(rng, (B, Lv, C)), O.encoder_reference_points(shapes, B).numpy()
+    else:
+        q = O.rng_normal(rng, (B, 110, C))
+        ref = np.repeat(rng.uniform(0, 1, size=(B, 110, 1, 2)).astype(np.float32), 3, axis=2)
+    want = O.msda_forward(params, q, ref, v, shapes, None, M, P, dtype=torch.float64)
+    m = _load_module(params, C, M, 3, P, cuda_dev)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    got = m(d(q), d(ref), d(v), shapes)
+    assert rel_err(got, want) < FP32_TOL
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+def test_msda_module_bf16(cuda_dev, impl):
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    B, C, M, P = 4, 256, 8, 6
+    rng = np.random.Generator(np.random.PCG64(1))
+    _, Lv = O.level_tables(shapes)
+    params = O.make_msda_params(1234, C, M, 3, P)
+    q, v = O.rng_normal(rng, (B, Lv, C)), O.rng_normal(rng, (B, Lv, C))
+    ref = O.encoder_reference_points(shapes, B).numpy()
+    mask = (rng.uniform(size=(B, Lv)) > 0.05).astype(np.float32)
+    # oracle in float64 on the bf16-rounded inputs and weights
+    r = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    p16 = {k: (r(a) if k.endswith("weight") else a) for k, a in params.items()}
+    want = O.msda_forward(p16, r(q), ref, r(v), shapes, mask, M, P, dtype=torch.float64)
+    m = _load_module(params, C, M, 3, P, cuda_dev)
+    m.gemm_impl = L.IMPL_SIMT if impl == "simt" else L.IMPL_TCGEN05
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    got = m(d(q).bfloat16(), d(ref), d(v).bfloat16(), shapes, d(mask))
+    assert got.dtype == torch.bfloat16
+    assert rel_err(got.float(), want) < BF16_TOL

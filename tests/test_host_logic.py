@@ -1,0 +1,93 @@
+"""Host-side logic on CPU: window planning vs the oracle's restatement of infer.py, sharding, and the N>1
+partition under a world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from emrt_b200 import infer, sharding
+
+
+@pytest.mark.parametrize("size,crop,stride", [(1024, 512, 384), (6000, 512, 384), (256, 512, 384), (513, 512, 384),
+                                               (50, 24, 16), (70, 32, 20), (41, 24, 16), (33, 32, 20)])
+def test_window_origins_equal_oracle(size, crop, stride):
+    assert infer.window_origins(size, crop, stride) == O.window_origins(size, crop, stride)
+
+
+def test_plan_windows_reproduces_reference_accumulation():
+    """Accumulate an index-valued 'logit' with our plan and with the oracle's slide_inference: identical canvases."""
+    rng = np.random.Generator(np.random.PCG64(0))
+    imgs = [torch.from_numpy(O.rng_normal(rng, (3, 50, 70))), torch.from_numpy(O.rng_normal(rng, (3, 41, 33)))]
+    crop, stride = (32, 24), (20, 16)
+    want = O.slide_inference(lambda b: (b,), imgs, crop, stride, 3)
+    plan, mh, mw = infer.plan_windows([(50, 70), (41, 33)], crop, stride)
+    canvas = torch.zeros(2, 3, mh, mw)
+    count = torch.zeros(2, 1, mh, mw)
+    for (i, y0, x0, wh, ww) in plan:
+        canvas[i, :, y0:y0 + wh, x0:x0 + ww] += imgs[i][:, y0:y0 + wh, x0:x0 + ww]
+        count[i, :, y0:y0 + wh, x0:x0 + ww] += 1
+    for i, (h, w) in enumerate([(50, 70), (41, 33)]):
+        assert torch.equal(canvas[i:i + 1, :, :h, :w] / count[i:i + 1, :, :h, :w], want[i])
+
+
+def test_plan_counts_for_baseline_configs():
+    plan, _, _ = infer.plan_windows([(1024, 1024)], (512, 512), (384, 384))
+    assert len(plan) == 9 and sorted({p[1] for p in plan}) == [0, 384, 512]
+    plan, _, _ = infer.plan_windows([(6000, 6000)], (512, 512), (384, 384))
+    assert len(plan) == 256 and max(p[1] for p in plan) == 5488
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 9, 72, 256):
+        for world in (1, 2, 4, 8):
+            got = []
+            for r in range(world):
+                b, e = sharding.shard_range(n, r, world)
+                got += list(range(b, e))
+            assert got == list(range(n))
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
+
+
+def test_shard_scene_rows_cover_all_label_rows_once():
+    rows = O.window_origins(6000, 512, 384)
+    for world in (1, 2, 4, 8):
+        covered = np.zeros(6000, int)
+        for r in range(world):
+            own, y0, y1, halo = sharding.shard_scene_rows(rows, 512, r, world)
+            covered[y0:y1] += 1
+            have = set(own) | set(halo)
+            for y in (y0, (y0 + y1) // 2, y1 - 1):     # every window row covering these label rows is local
+                need = {k for k, o in enumerate(rows) if o <= y < o + 512}
+                assert need <= have
+        assert (covered == 1).all()
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sharding.shard_images(9, rank, world)
+    t = torch.zeros(9)
+    t[mine] = 1
+    dist.all_reduce(t)                         # test-only check that the shards tile the image set exactly once
+    areas = torch.tensor([float(len(mine)), 1.0])
+    dist.all_reduce(areas)                     # the val.py:168-170 metric reduction, 3 x [num_classes] there
+    q.put((rank, t.tolist(), areas.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(60) for p in ps]
+    for _, cover, areas in res:
+        assert cover == [1.0] * 9 and areas == [9.0, 2.0]

@@ -1,0 +1,155 @@
+"""CPU tests of the oracle: two independent formulations, analytic cases, golden fixtures.
+PARITY UNPINNED (see oracle/emrt_oracle.py): the reference ships no vectors and cannot run here."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _case(seed=0, shapes=((8, 6), (4, 3), (2, 2)), B=2, M=2, D=16, P=4, Lq=19, spread=0.4):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    _, Lv = O.level_tables(shapes)
+    L = len(shapes)
+    value = O.rng_normal(rng, (B, Lv, M, D))
+    loc = rng.uniform(-spread, 1 + spread, size=(B, Lq, M, L, P, 2)).astype(np.float32)
+    attn = rng.uniform(0, 1, size=(B, Lq, M, L, P)).astype(np.float32)
+    return value, loc, attn, list(shapes)
+
+
+def test_two_gather_formulations_agree():
+    value, loc, attn, shapes = _case()
+    a = O.deformable_attention_core_func(torch.from_numpy(value).double(), shapes, torch.from_numpy(loc).double(),
+                                         torch.from_numpy(attn).double()).numpy()
+    b = O.gather_corner_loop(value, shapes, loc, attn)
+    assert np.abs(a - b).max() < 1e-10
+    a32 = O.deformable_attention_core_func(value, shapes, loc, attn).numpy()
+    assert np.abs(a32 - b).max() < 1e-5
+
+
+def test_all_samples_outside_give_exact_zero():
+    value, loc, attn, shapes = _case()
+    loc = loc * 0 + 3.0
+    assert np.all(O.gather_corner_loop(value, shapes, loc, attn) == 0)
+    assert torch.all(O.deformable_attention_core_func(value, shapes, loc, attn) == 0)
+
+
+def test_pixel_centre_samples_pick_the_pixel():
+    shapes = [(4, 5)]
+    rng = np.random.Generator(np.random.PCG64(1))
+    value = O.rng_normal(rng, (1, 20, 1, 16))
+    ref = O.encoder_reference_points(shapes, 1).numpy()            # [1,20,1,2] pixel centres
+    loc = ref.reshape(1, 20, 1, 1, 1, 2)
+    attn = np.ones((1, 20, 1, 1, 1), np.float32)
+    out = O.gather_corner_loop(value, shapes, loc, attn)
+    assert np.abs(out - value.reshape(1, 20, 16)).max() < 1e-6
+
+
+def test_linearity_in_value():
+    value, loc, attn, shapes = _case(3)
+    value = value.astype(np.float64)
+    v2 = np.roll(value, 1, axis=1)
+    f = lambda v: O.gather_corner_loop(v, shapes, loc, attn)
+    assert np.abs(f(2 * value + 3 * v2) - (2 * f(value) + 3 * f(v2))).max() < 1e-9
+
+
+def test_uniform_attention_zero_offsets_is_mean_of_reference_samples():
+    shapes = [(8, 8), (4, 4), (2, 2)]
+    B, C, M, P = 1, 64, 2, 6
+    p = O.make_msda_params(5, C, M, 3, P)
+    p["sampling_offsets.weight"][:] = 0
+    p["sampling_offsets.bias"][:] = 0
+    p["attention_weights.weight"][:] = 0
+    p["attention_weights.bias"][:] = 0
+    rng = np.random.Generator(np.random.PCG64(2))
+    _, Lv = O.level_tables(shapes)
+    q, v = O.rng_normal(rng, (B, Lv, C)), O.rng_normal(rng, (B, Lv, C))
+    ref = O.encoder_reference_points(shapes, B)
+    vp, loc, aw = O.msda_intermediates(p, q, ref, v, shapes, None, M, P)
+    assert torch.allclose(aw, torch.full_like(aw, 1.0 / 18))
+    core = O.deformable_attention_core_func(vp, shapes, loc, aw)
+    # every point of a level samples the reference point itself
+    one = O.deformable_attention_core_func(vp, shapes, loc[:, :, :, :, :1], torch.full_like(aw[:, :, :, :, :1], 1 / 3))
+    assert torch.allclose(core, one, atol=1e-5)
+
+
+def test_reference_init_bias_matches_closed_form():
+    b = O.msda_reset_parameters(256, 8, 3, 6).reshape(8, 3, 6, 2)
+    assert np.allclose(b[0, 0, :, 0], np.arange(1, 7)) and np.allclose(b[0, :, :, 1], 0, atol=1e-6)
+    assert np.allclose(b[2, 1, 3], [0, 4], atol=1e-5)          # head 2 points along +y
+    assert np.allclose(np.abs(b).max(-1)[:, 0, :], np.arange(1, 7)[None])
+
+
+def test_upsample_two_formulations_and_edges():
+    rng = np.random.Generator(np.random.PCG64(4))
+    x = O.rng_normal(rng, (2, 3, 5, 7))
+    a, b = O.upsample2x(x).numpy(), O.upsample2x_loop(x)
+    assert np.abs(a - b).max() < 1e-6
+    assert np.allclose(b[..., 0, 0], x[..., 0, 0]) and np.allclose(b[..., -1, -1], x[..., -1, -1])
+    assert np.allclose(b[..., 1, 0], 0.75 * x[..., 0, 0] + 0.25 * x[..., 1, 0])
+
+
+def test_window_origins_match_survey():
+    assert O.window_origins(1024, 512, 384) == [0, 384, 512]
+    o = O.window_origins(6000, 512, 384)
+    assert len(o) == 16 and o[-2:] == [5376, 5488] and o[:3] == [0, 384, 768]
+    assert O.window_origins(256, 512, 384) == [0]
+    assert O.window_origins(512, 512, 384) == [0]
+
+
+def test_slide_inference_identity_model_reproduces_image():
+    rng = np.random.Generator(np.random.PCG64(5))
+    img = torch.from_numpy(O.rng_normal(rng, (3, 50, 70)))
+    out = O.slide_inference(lambda b: (b,), [img], (32, 24), (20, 16), 3)
+    assert torch.allclose(out[0][0], img, atol=1e-6)
+
+
+def test_calculate_area_ignore_index():
+    pred = np.array([0, 1, 2, 2, 1, 0, 5])
+    label = np.array([0, 1, 1, 255, 255, 2, 5])
+    ia, pa, la = O.calculate_area(pred, label, 6)
+    assert ia.tolist() == [1, 1, 0, 0, 0, 1]
+    assert pa.tolist() == [2, 1, 1, 0, 0, 1]
+    assert la.tolist() == [1, 2, 1, 0, 0, 1]
+
+
+def test_golden_msda_small():
+    g = np.load(os.path.join(GOLD, "msda_small.npz"))
+    shapes = [tuple(s) for s in g["shapes"].tolist()]
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p.")}
+    vp, loc, aw = O.msda_intermediates(params, g["query"], g["ref"], g["value"], shapes, g["mask"], 2, 6)
+    assert np.abs(vp.numpy() - g["value_proj"]).max() < 1e-4
+    assert np.abs(loc.numpy() - g["loc"]).max() < 1e-5
+    assert np.abs(aw.numpy() - g["attn"]).max() < 1e-6
+    core = O.deformable_attention_core_func(vp, shapes, loc, aw).numpy()
+    assert np.abs(core - g["core"]).max() < 1e-4
+    out = O.msda_forward(params, g["query"], g["ref"], g["value"], shapes, g["mask"], 2, 6).numpy()
+    assert np.abs(out - g["out"]).max() < 2e-4 * np.abs(g["out"]).max()
+
+
+def test_golden_slide_small():
+    g = np.load(os.path.join(GOLD, "slide_small.npz"))
+    wmat = torch.from_numpy(g["wmat"])
+    model = lambda b: (torch.einsum("oc,nchw->nohw", wmat, b),)
+    imgs = [torch.from_numpy(g["img0"]), torch.from_numpy(g["img1"])]
+    logits = O.slide_inference(model, imgs, tuple(g["crop"]), tuple(g["stride"]), 6)
+    for i in range(2):
+        assert np.abs(logits[i].numpy() - g[f"logit{i}"]).max() < 1e-5
+        pred = O.ss_inference_tail(logits[i], tuple(g["ori"][i])).numpy()
+        assert (pred == g[f"pred{i}"]).mean() > 0.9999
+
+
+def test_encoder_decoder_oracle_runs_and_is_data_dependent():
+    p = O.make_encoder_decoder_params(3)
+    torch.manual_seed(0)
+    feats = [torch.randn(1, 512, 8, 8), torch.randn(1, 1024, 4, 4), torch.randn(1, 2048, 2, 2)]
+    psp = torch.randn(1, 256, 110)
+    hs, mem, shapes = O.encoder_decoder_forward(p, feats, psp, num_enc=1, num_dec=1)
+    assert hs.shape == (1, 1, 110, 256) and mem.shape == (1, 84, 256) and shapes == [(8, 8), (4, 4), (2, 2)]
+    feats[0] = feats[0] + 1
+    hs2, _, _ = O.encoder_decoder_forward(p, feats, psp, num_enc=1, num_dec=1)
+    assert (hs - hs2).abs().max() > 1e-3
