@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — EMRT hot path on B200: images/s (512x512 windows) and MPix/s.
+
+A "step" = one pass of the hot path over one batch of synthetic input:
+  4 encoder + 2 decoder MSDeformableAttention calls (value/offset/weight/output projections, softmax over
+  levels x points, multiscale bilinear gather) on the C3-C5 token maps of W 512x512 windows, then the head tail
+  (x2 bilinear upsample + sliding-window overlap stitch + softmax + argmax) that turns the windows' half-resolution
+  class logits into 1024x1024 LoveDA-shaped label maps (9 windows per image, window 512 stride 384).
+Out of the step (out of scope / "next" rows): ResNet-50 backbone, conv heads, LayerNorm/FFN glue.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference ...                           the reference path's CPU restatement (oracle)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE = 512
+NC = 7                      # LoveDA
+WINDOWS_PER_IMAGE = 9       # 1024x1024, window 512, stride 384 -> origins {0, 384, 512}^2
+SCENE = 1024
+METRIC = "images/s (512x512 windows through the EMRT hot path: 6x MSDeformableAttention + upsample/stitch/argmax)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=2, help="1024x1024 scenes per GPU per step (9 windows each)")
+    ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-windows", type=int, default=4)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk = float(f[1]); mx = float(f[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:      # timed region shorter than the sampling period: use every sample we have
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1])); mx = float(f[2])
+                except Exception:
+                    pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def window_tables(n_img):
+    import emrt_b200
+    plan, H, W = emrt_b200.plan_windows([(SCENE, SCENE)] * n_img, (TILE, TILE), (384, 384))
+    assert len(plan) == n_img * WINDOWS_PER_IMAGE
+    return plan, H, W
+
+
+def gather_bytes(B, Lq, Lv, M, D, L, P, sv, sl):
+    """Algorithmic bytes of one gather launch (BASELINE.md §3 / SURVEY.md §8d)."""
+    return sv * B * Lv * M * D + sl * B * Lq * M * L * P * 3 + sv * B * Lq * M * D
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference path's CPU restatement (the oracle), on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_hot_path(n_windows, threads, repeats=1, warmup=0):
+    """Times the oracle (torch-CPU fp32 restatement of the reference's Paddle op composition) on `n_windows`
+    512x512 windows of the same workload.  Returns (images/s, seconds per pass)."""
+    import numpy as np
+    import torch
+    import oracle as O
+    torch.set_num_threads(threads)
+    shapes = [(TILE // 8,) * 2, (TILE // 16,) * 2, (TILE // 32,) * 2]
+    _, Lv = O.level_tables(shapes)
+    rng = np.random.Generator(np.random.PCG64(0))
+    params = [{k: torch.from_numpy(v) for k, v in O.make_msda_params(1234 + i).items()} for i in range(6)]
+    src = torch.from_numpy(O.rng_normal(rng, (n_windows, Lv, 256)))
+    pos = torch.from_numpy(O.rng_normal(rng, (1, Lv, 256)))
+    tgt = torch.from_numpy(O.rng_normal(rng, (n_windows, 110, 256)))
+    qpos = torch.from_numpy(O.rng_normal(rng, (1, 110, 256)))
+    half = torch.from_numpy(O.rng_normal(rng, (n_windows, NC, TILE // 2, TILE // 2)))
+    ref_enc = O.encoder_reference_points(shapes, n_windows)
+    ref_dec = torch.rand(n_windows, 110, 1, 2).expand(-1, -1, 3, -1).contiguous()
+    mask = torch.ones(n_windows, Lv)
+
+    def one_pass():
+        x = src
+        for i in range(4):
+            x = O.msda_forward(params[i], x + pos, ref_enc, x, shapes, mask)
+        t = tgt
+        for i in range(4, 6):
+            t = O.msda_forward(params[i], t + qpos, ref_dec, x, shapes, mask)
+        full = O.upsample2x(half)                       # UpHead tail
+        return O.ss_inference_tail(full, (TILE, TILE)), t   # softmax + argmax (stitching is index work only)
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one_pass()
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            one_pass()
+        dt = (time.perf_counter() - t0) / repeats
+    return n_windows / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nwin = max(1, args.cpu_sample_windows)
+    ips, dt = cpu_hot_path(nwin, cores, repeats=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": max(1, min(args.steps, 3)), "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mpix_per_s": ips * TILE * TILE / 1e6,
+        "config": {"workload": f"cfg3-shaped: {TILE}x{TILE} windows of 1024x1024 LoveDA scenes, {NC} classes, "
+                               "window 512 stride 384; hot path only (6x MSDA + head tail)",
+                   "note": "reference = CPU restatement of the reference's Paddle op composition (oracle/, torch-CPU "
+                           "fp32); PaddlePaddle itself cannot be installed in this image"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{nwin} window(s) of the {args.images * WINDOWS_PER_IMAGE}-window step, all host threads"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import emrt_b200
+    from emrt_b200 import ops, _lib as L
+    from emrt_b200.hotpath import HotPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.device_check()
+
+    impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tcgen05": L.IMPL_TCGEN05}[args.gemm]
+    hp = HotPath(dev, TILE, NC, gemm_impl=impl)
+    n_img = args.images
+    B = n_img * WINDOWS_PER_IMAGE
+    plan, H, W = window_tables(n_img)
+    Lv, C, Nq = hp.Lv, hp.C, hp.num_queries
+    ti = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+    win = dict(win_img=ti([p[0] for p in plan]), win_y0=ti([p[1] for p in plan]), win_x0=ti([p[2] for p in plan]),
+               n_img=n_img, H=H, W=W)
+    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    pos = torch.randn((1, Lv, C), generator=g).bfloat16().to(dev)
+    qpos = torch.randn((1, Nq, C), generator=g).bfloat16().to(dev)
+    mask = torch.ones((B, Lv), dtype=torch.float32, device=dev)
+
+    # host (pinned) inputs for the e2e path and N_SETS resident device copies for the kernel-only path; rotating
+    # over N_SETS input sets (> 126 MB L2 in total) keeps every timed step's inputs cold.
+    N_SETS = 4
+    host_sets, dev_sets = [], []
+    for s in range(N_SETS):
+        h = dict(src=torch.randn((B, Lv, C), generator=g).bfloat16().pin_memory(),
+                 tgt=torch.randn((B, Nq, C), generator=g).bfloat16().pin_memory(),
+                 half_logits=torch.randn((B, NC, TILE // 2, TILE // 2), generator=g).bfloat16().pin_memory())
+        host_sets.append(h)
+        d = {k: v.to(dev) for k, v in h.items()}
+        d.update(pos=pos, qpos=qpos, mask=mask, **win)
+        dev_sets.append(d)
+    in_bytes = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+    labels_dev = torch.empty((n_img, 1, H, W), dtype=torch.uint8, device=dev)
+    labels_host = torch.empty((n_img, 1, H, W), dtype=torch.uint8).pin_memory()
+    hs_host = torch.empty((B, Nq, C), dtype=torch.bfloat16).pin_memory()
+    out_bytes = labels_host.numel() + hs_host.numel() * 2
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- kernel-only: inputs resident in HBM -------------------------------------------------------------
+    with torch.no_grad():
+        for i in range(args.warmup):
+            hp.step(dev_sets[i % N_SETS], labels_dev)
+        sync_all()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        ops.kernel_events = []
+        ops.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t_wall0 = time.time()
+        e0.record()
+        for i in range(args.steps):
+            hp.step(dev_sets[i % N_SETS], labels_dev)
+        e1.record()
+        sync_all()
+        t_wall1 = time.time()
+        launches = ops.launch_count()
+        events, ops.kernel_events = ops.kernel_events, None
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+
+        # ---- e2e: host buffers in, host labels out, every step -------------------------------------------
+        def e2e_step(i):
+            h = host_sets[i % N_SETS]
+            d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+            d.update(pos=pos, qpos=qpos, mask=mask, **win)
+            lab, hs = hp.step(d, labels_dev)
+            labels_host.copy_(lab, non_blocking=True)
+            hs_host.copy_(hs, non_blocking=True)
+        for i in range(min(args.warmup, 3)):
+            e2e_step(i)
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        f1.record()
+        sync_all()
+        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+
+    # ---- roofline of the dominant kernel (the encoder gather) --------------------------------------------
+    enc = [(dims, ev[0].elapsed_time(ev[1])) for (name, dims, ev) in events if dims[1] == Lv]
+    hbm_peak, peak_src = peaks()
+    roof = None
+    if enc:
+        avg_ms = sum(t for _, t in enc) / len(enc)
+        gb = gather_bytes(*enc[0][0]) / 1e9
+        ach = gb / (avg_ms * 1e-3)
+        roof = {"kernel": "msda_gather_fwd (encoder call, Lq=Lv=%d, B=%d)" % (Lv, B), "bound": "hbm",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "algorithmic_bytes": gb * 1e9, "avg_launch_ms": avg_ms, "launches_timed": len(enc),
+                "share_of_step": avg_ms * len(enc) / args.steps / ms_step, "peak_source": peak_src}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "mpix_per_s": value * TILE * TILE / 1e6,
+        "config": {"workload": f"cfg3-shaped: {B} {TILE}x{TILE} windows per GPU per step = {n_img} LoveDA 1024x1024 "
+                               f"scenes (window 512, stride 384), {NC} classes; hot path only (6x MSDA + head tail)",
+                   "windows_per_gpu": B, "tokens_per_window": Lv, "gemm": args.gemm,
+                   "l2": f"inputs rotate over {N_SETS} resident sets ({N_SETS * in_bytes / 1e6:.0f} MB > 126 MB L2); "
+                         "each step also streams > 1 GB of intermediates",
+                   "parallelism": f"windows sharded over {world} GPU(s), no collective"},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        ips, dt = cpu_hot_path(max(1, args.cpu_sample_windows), cores, repeats=2, warmup=1)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{max(1, args.cpu_sample_windows)} window(s) of the {B}-window step, "
+                                          f"torch-CPU fp32 oracle, {cores} threads, {dt:.2f} s per pass"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

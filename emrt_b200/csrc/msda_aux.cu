@@ -83,9 +83,41 @@ add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residual, co
   }
 }
 
+// out[i] = a[i] + b[i % b_period]  (with_pos_embed, transformer_encoder_decoder.py:154-155,198), 16 B per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_bcast_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n_vec,
+                 int64_t period_vec) {
+  constexpr int VEC = Vec16<T>::N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float x[VEC], y[VEC];
+    Vec16<T>::load(a + i * VEC, x);
+    Vec16<T>::load(b + (i % period_vec) * VEC, y);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) x[k] += y[k];
+    Vec16<T>::store(out + i * VEC, x);
+  }
+}
+
 }  // namespace emrt
 
 using namespace emrt;
+
+extern "C" int emrt_add_bcast(const void* a, const void* b, void* out, int64_t n, int64_t b_period, int dtype,
+                              void* stream) {
+  EMRT_REQUIRE(a && b && out && n > 0 && b_period > 0 && n % b_period == 0, "bad add_bcast arguments");
+  const int vec = dtype == EMRT_F32 ? 4 : 8;
+  EMRT_REQUIRE(n % vec == 0 && b_period % vec == 0, "sizes must be multiples of the 16-byte vector width");
+  const int64_t nv = n / vec, pv = b_period / vec;
+  const int64_t want = (nv + 255) / 256;
+  const unsigned blocks = (unsigned)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == EMRT_F32) add_bcast_kernel<float><<<blocks, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, nv, pv);
+  else if (dtype == EMRT_BF16) add_bcast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, nv, pv);
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
 
 extern "C" int emrt_msda_softmax_loc(const float* off_raw, int64_t off_ld, const float* logit_raw, int64_t logit_ld,
                                      const float* ref, int64_t ref_batch_stride, void* loc_out, void* attn_out,

@@ -1,0 +1,63 @@
+"""The hot path as one callable: 4 encoder + 2 decoder MSDeformableAttention calls (paddle_EMRT.py:242-250,
+transformer_encoder_decoder.py:198,288) followed by the head tail (x2 upsample + sliding-window stitch + softmax +
+argmax; paddle_EMRT.py:178-180, src/api/infer.py:69-79,150-154).  The LayerNorm / FFN / conv glue between the
+attention calls is a "next" row and is not part of this step."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .msda import MSDeformableAttention
+from . import synthetic
+
+
+class HotPath:
+    def __init__(self, device, tile=512, num_classes=7, embed_dim=256, num_heads=8, num_points=6, num_enc=4,
+                 num_dec=2, num_queries=110, seed=1234, gemm_impl=L.IMPL_AUTO):
+        self.device = device
+        self.tile, self.nc, self.C = tile, num_classes, embed_dim
+        self.shapes = synthetic.level_shapes(tile)
+        self.Lv = sum(h * w for h, w in self.shapes)
+        self.num_queries = num_queries
+        self.enc: List[MSDeformableAttention] = []
+        self.dec: List[MSDeformableAttention] = []
+        for i in range(num_enc + num_dec):
+            m = MSDeformableAttention(embed_dim, num_heads, len(self.shapes), num_points).to(device)
+            st = synthetic.msda_state(seed + i, embed_dim, num_heads, len(self.shapes), num_points)
+            with torch.no_grad():
+                for name, arr in st.items():
+                    mod, leaf = name.split(".")
+                    getattr(getattr(m, mod), leaf).copy_(torch.from_numpy(arr))
+            m.gemm_impl = gemm_impl
+            (self.enc if i < num_enc else self.dec).append(m)
+        rng = np.random.Generator(np.random.PCG64(seed + 100))
+        self.ref_enc = torch.from_numpy(synthetic.encoder_reference_points(self.shapes)).to(device)
+        ref_dec = rng.uniform(0.05, 0.95, size=(1, num_queries, 1, 2)).astype(np.float32)
+        self.ref_dec = torch.from_numpy(np.ascontiguousarray(np.repeat(ref_dec, len(self.shapes), axis=2))).to(device)
+        self.gather_events: Optional[list] = None
+
+    def msda_stack(self, src, pos, tgt, qpos, mask=None):
+        """src [B,Lv,C], pos [1|B,Lv,C], tgt [B,Nq,C], qpos [1,Nq,C] -> (memory [B,Lv,C], hs [B,Nq,C])."""
+        x = src
+        for m in self.enc:
+            q = ops.add_bcast(x, pos)                              # with_pos_embed (t_e_d.py:198)
+            x = m(q, self.ref_enc, x, self.shapes, mask)
+        t = tgt
+        for m in self.dec:
+            q = ops.add_bcast(t, qpos)                             # t_e_d.py:288
+            t = m(q, self.ref_dec, x, self.shapes, mask)
+        return x, t
+
+    def head_tail(self, half_logits, win_img, win_y0, win_x0, n_img, H, W, labels=None):
+        return ops.stitch_argmax_fused(half_logits, win_img, win_y0, win_x0, n_img, H, W, label_dtype=torch.uint8,
+                                       labels=labels)[0]
+
+    def step(self, batch, labels=None):
+        mem, hs = self.msda_stack(batch["src"], batch["pos"], batch["tgt"], batch["qpos"], batch.get("mask"))
+        lab = self.head_tail(batch["half_logits"], batch["win_img"], batch["win_y0"], batch["win_x0"],
+                             batch["n_img"], batch["H"], batch["W"], labels)
+        return lab, hs

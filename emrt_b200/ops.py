@@ -16,6 +16,9 @@ _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16, torch
 _TD = {v: k for k, v in _DT.items()}
 
 
+kernel_events = None   # set to a list to collect (name, dims, (start, end)) CUDA-event pairs per launch
+
+
 def _dt(t: torch.Tensor) -> int:
     try:
         return _DT[t.dtype]
@@ -68,8 +71,15 @@ def msda_gather_fwd(value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, o
     if out is None:
         out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
     rbs = 0 if ref is None or ref.shape[0] == 1 else Lq * nL * 2
+    ev = None
+    if kernel_events is not None:      # bench.py: CUDA events around this launch, on the launching stream
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     L.check(lib.emrt_msda_gather_fwd(_ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(out), B, Lq, Lv, M, D,
                                      nL, P, hw, start, _dt(value), _dt(loc), mode, _stream()))
+    if ev is not None:
+        ev[1].record()
+        kernel_events.append(("msda_gather_fwd", (B, Lq, Lv, M, D, nL, P, value.element_size(), loc.element_size()), ev))
     return out
 
 
@@ -153,6 +163,14 @@ def add_layernorm(x, residual, gamma, beta, eps=1e-5, out=None):
         out = torch.empty_like(x)
     L.check(L.load().emrt_add_layernorm(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out), rows, N,
                                         float(eps), _dt(x), _stream()))
+    return out
+
+
+def add_bcast(a, b, out=None):
+    """out = a + b with b broadcast over leading dims (b.numel() divides a.numel()): with_pos_embed."""
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(L.load().emrt_add_bcast(_ptr(a), _ptr(b), _ptr(out), a.numel(), b.numel(), _dt(a), _stream()))
     return out
 
 

@@ -1,0 +1,51 @@
+"""Synthetic weights / inputs for benchmarks and smoke runs (SURVEY.md §8d distributions; numpy PCG64).
+There is no network for datasets or checkpoints; shapes follow Potsdam / LoveDA tiles."""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+
+
+def msda_state(seed=1234, embed_dim=256, num_heads=8, num_levels=3, num_points=6, offset_std=0.05, attn_std=0.1
+               ) -> Dict[str, np.ndarray]:
+    """Non-trivial MSDeformableAttention weights with Paddle state-dict keys / layouts ([in, out]).  The reference
+    init zeroes sampling_offsets.weight and attention_weights.* (t_e_d.py:47-58), which would make the sampled
+    positions input-independent; benchmarks must exercise the data-dependent path."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    C, tp = embed_dim, num_heads * num_levels * num_points
+    xav = math.sqrt(6.0 / (C + C))
+    thetas = np.arange(num_heads, dtype=np.float32) * np.float32(2.0 * math.pi / num_heads)
+    grid = np.stack([np.cos(thetas), np.sin(thetas)], -1)
+    grid = grid / np.abs(grid).max(-1, keepdims=True)
+    grid = np.tile(grid.reshape(num_heads, 1, 1, 2), (1, num_levels, num_points, 1))
+    grid = grid * np.arange(1, num_points + 1, dtype=np.float32).reshape(1, 1, -1, 1)
+    f = np.float32
+    return {
+        "sampling_offsets.weight": (rng.standard_normal((C, tp * 2)) * offset_std).astype(f),
+        "sampling_offsets.bias": grid.reshape(-1).astype(f),
+        "attention_weights.weight": (rng.standard_normal((C, tp)) * attn_std).astype(f),
+        "attention_weights.bias": rng.uniform(-0.1, 0.1, (tp,)).astype(f),
+        "value_proj.weight": rng.uniform(-xav, xav, (C, C)).astype(f),
+        "value_proj.bias": rng.uniform(-0.1, 0.1, (C,)).astype(f),
+        "output_proj.weight": rng.uniform(-xav, xav, (C, C)).astype(f),
+        "output_proj.bias": rng.uniform(-0.1, 0.1, (C,)).astype(f),
+    }
+
+
+def encoder_reference_points(shapes) -> np.ndarray:
+    """[1, Lv, L, 2] pixel-centre reference points (t_e_d.py:213-228 with valid_ratios == 1)."""
+    pts = []
+    for (H, W) in shapes:
+        ys = (np.arange(H, dtype=np.float32) + 0.5) / np.float32(H)
+        xs = (np.arange(W, dtype=np.float32) + 0.5) / np.float32(W)
+        yy, xx = np.meshgrid(ys, xs, indexing="ij")
+        pts.append(np.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+    ref = np.concatenate(pts, 0)[None, :, None, :]
+    return np.ascontiguousarray(np.broadcast_to(ref, (1, ref.shape[1], len(shapes), 2))).astype(np.float32)
+
+
+def level_shapes(tile: int):
+    """C3..C5 feature-map shapes of a tile x tile input (strides 8/16/32; paddle_EMRT.py:254)."""
+    return [(tile // 8, tile // 8), (tile // 16, tile // 16), (tile // 32, tile // 32)]

@@ -125,6 +125,11 @@ int emrt_msda_softmax_loc(const float* off_raw, int64_t off_ld, const float* log
 int emrt_add_layernorm(const void* x, const void* residual, const float* gamma, const float* beta, void* y,
                        int64_t rows, int N, float eps, int dtype, void* stream);
 
+/* out[i] = a[i] + b[i % b_period]: with_pos_embed (transformer_encoder_decoder.py:154-155,198,283,288);
+ * b_period = n for a plain add, Lq*C for a batch-shared positional embedding.  dtype F32|BF16.             */
+int emrt_add_bcast(const void* a, const void* b, void* out, int64_t n, int64_t b_period, int dtype,
+                   void* stream);
+
 /* ---- a5: UpHead tail (src/models/paddle_EMRT.py:178-180): x2 bilinear, align_corners=False ------------
  * in [n,nc,h,w] (in_dtype F32|BF16) -> out F32 [n,nc,2h,2w].                                              */
 int emrt_upsample2x(const void* in, float* out, int n, int nc, int h, int w, int in_dtype, void* stream);
