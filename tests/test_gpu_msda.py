@@ -215,3 +215,43 @@ def test_msda_module_bf16(cuda_dev, impl):
     got = m(d(q).bfloat16(), d(ref), d(v).bfloat16(), shapes, d(mask))
     assert got.dtype == torch.bfloat16
     assert rel_err(got.float(), want) < BF16_TOL
+
+
+@pytest.mark.parametrize("rows,K,N,epi", [
+    (300, 256, 256, "none"), (128, 256, 256, "mask"), (1000, 256, 432, "qproj"), (129, 1024, 256, "none"),
+    (77, 256, 1024, "relu"), (5000, 256, 64, "none"), (260, 64, 128, "mask"), (20000, 256, 256, "none"),
+    (96768, 256, 432, "qproj"),
+])
+def test_linear_tcgen05_matches_fp64(cuda_dev, rows, K, N, epi):
+    """tcgen05/TMEM/TMA GEMM vs float64 on the same bf16-rounded operands (fp32 accumulation: ~1e-6 relative)."""
+    rng = np.random.Generator(np.random.PCG64(rows + N))
+    x = torch.from_numpy(O.rng_normal(rng, (rows, K))).bfloat16()
+    w = torch.from_numpy(O.rng_normal(rng, (K, N), 0.1)).bfloat16()          # Paddle layout [in, out]
+    b = torch.from_numpy(O.rng_normal(rng, (N,)))
+    wt = torch.empty((N, K), dtype=torch.bfloat16, device=cuda_dev)
+    ops.pack_weight(w.to(cuda_dev), wt)
+    assert torch.equal(wt.cpu(), w.t().contiguous())
+    ref = x.double() @ w.double() + b.double()
+    xd, bd = x.to(cuda_dev), b.to(cuda_dev)
+    if epi == "qproj":
+        tp = N // 3
+        off, attn = ops.linear(xd, wt, bd, w_transposed=True, y_dtype=torch.float16, epilogue=L.EPI_MSDA_QPROJ,
+                               qproj_group=18, impl=L.IMPL_TCGEN05)
+        assert off.shape == (rows, 2 * tp) and attn.shape == (rows, tp)
+        assert rel_err(off.float(), ref[:, :2 * tp]) < 2e-3                   # fp16 storage of the offsets
+        want = torch.softmax(ref[:, 2 * tp:].reshape(rows, -1, 18), -1).reshape(rows, tp)
+        assert (attn.float().cpu().double() - want).abs().max() < 2e-3
+        assert (attn.float().reshape(rows, -1, 18).sum(-1) - 1).abs().max() < 5e-3
+        return
+    scale = torch.from_numpy(rng.uniform(0, 1, size=(rows,)).astype(np.float32))
+    flags, kw = L.EPI_NONE, {}
+    if epi == "mask":
+        flags, kw, ref = L.EPI_ROW_MASK, dict(row_scale=scale.to(cuda_dev)), ref * scale.double()[:, None]
+    if epi == "relu":
+        flags, ref = L.EPI_RELU, ref.clamp_min(0)
+    got32 = ops.linear(xd, wt, bd, w_transposed=True, y_dtype=torch.float32, epilogue=flags, impl=L.IMPL_TCGEN05, **kw)
+    assert rel_err(got32, ref) < 1e-5
+    got16 = ops.linear(xd, wt, bd, w_transposed=True, epilogue=flags, impl=L.IMPL_TCGEN05, **kw)
+    assert got16.dtype == torch.bfloat16 and rel_err(got16.float(), ref) < 1e-2
+    simt = ops.linear(xd, wt, bd, w_transposed=True, y_dtype=torch.float32, epilogue=flags, impl=L.IMPL_SIMT, **kw)
+    assert rel_err(got32, simt.cpu()) < 1e-5
