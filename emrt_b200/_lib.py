@@ -12,8 +12,8 @@ LIB_PATH = os.path.join(HERE, "libemrt_b200.so")
 
 # enums (mirror include/emrt_b200.h)
 F32, BF16, F16, I32, U8 = 0, 1, 2, 3, 4
-LOC_NORMALIZED, LOC_PIXEL_OFFSET = 0, 1
-EPI_NONE, EPI_ROW_MASK, EPI_RELU, EPI_RESIDUAL_LN, EPI_MSDA_QPROJ = 0, 1, 2, 4, 8
+LOC_NORMALIZED, LOC_PIXEL_OFFSET, VALUE_HEAD_MAJOR = 0, 1, 2
+EPI_NONE, EPI_ROW_MASK, EPI_RELU, EPI_RESIDUAL_LN, EPI_MSDA_QPROJ, EPI_HEAD_MAJOR = 0, 1, 2, 4, 8, 16
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
 
@@ -31,6 +31,7 @@ class LinearArgs(C.Structure):
         ("residual", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
         ("y2", C.c_void_p), ("qproj_group", C.c_int32),
         ("impl", C.c_int32),
+        ("hm_rows", C.c_int32), ("hm_D", C.c_int32),
     ]
 
 

@@ -38,6 +38,7 @@ struct GemmParams {
   int32_t y_dtype;
   int32_t flags;
   int32_t group;       // QPROJ: softmax group (L*P)
+  int32_t hm_rows, hm_D;   // HEAD_MAJOR: rows per batch element, head dim
   int32_t tiles_m, tiles_n;
 };
 
@@ -269,6 +270,11 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       if (EPI == EPI_KIND_GENERIC) {
         const float rs = (p.flags & EMRT_EPI_ROW_MASK) ? (row_ok ? __ldg(p.row_scale + row) : 0.f) : 1.f;
         const bool relu = p.flags & EMRT_EPI_RELU;
+        // HEAD_MAJOR: element (row = b*hm_rows + pix, col = m*hm_D + d) goes to [b][m][pix][d]
+        const bool hm = p.flags & EMRT_EPI_HEAD_MAJOR;
+        int64_t hm_b = 0, hm_pix = 0;
+        if (hm && row_ok) { hm_b = row / p.hm_rows; hm_pix = row - hm_b * p.hm_rows; }
+        const int hm_heads = hm ? p.N / p.hm_D : 1;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
           uint32_t r[2][16];
@@ -286,7 +292,9 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 const float x = (__uint_as_float(r[h >> 1][(h & 1) * 8 + i]) + s.bias[col + i]) * rs;
                 v[i] = relu ? fmaxf(x, 0.f) : x;
               }
-              store8(p.y, p.y_dtype, row * p.N + col, v);
+              const int64_t dst = hm ? ((hm_b * hm_heads + col / p.hm_D) * p.hm_rows + hm_pix) * p.hm_D + col % p.hm_D
+                                     : row * p.N + col;
+              store8(p.y, p.y_dtype, dst, v);
             }
           }
         }
@@ -419,6 +427,11 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.bias = a->bias; p.row_scale = a->row_scale; p.y = a->y; p.y2 = a->y2;
   p.rows = a->rows; p.K = a->K; p.N = a->N; p.y_dtype = a->y_dtype; p.flags = a->epilogue; p.group = a->qproj_group;
+  p.hm_rows = a->hm_rows; p.hm_D = a->hm_D;
+  if (a->epilogue & EMRT_EPI_HEAD_MAJOR) {
+    if (a->hm_rows <= 0 || a->hm_D <= 0 || a->hm_D % 8 != 0 || a->N % a->hm_D != 0 || a->rows % a->hm_rows != 0)
+      return set_error(EMRT_ERR_INVALID_ARGUMENT, "HEAD_MAJOR needs hm_D %% 8 == 0, N %% hm_D == 0, rows %% hm_rows == 0");
+  }
   if (a->epilogue & EMRT_EPI_MSDA_QPROJ) {
     if (a->epilogue != EMRT_EPI_MSDA_QPROJ) return set_error(EMRT_ERR_UNSUPPORTED, "MSDA_QPROJ cannot be combined");
     if (a->N != 3 * 144) return set_error(EMRT_ERR_UNSUPPORTED, "MSDA_QPROJ epilogue is built for M*L*P = 144 (N = 432), got N=%d", a->N);
@@ -426,7 +439,7 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
       return set_error(EMRT_ERR_UNSUPPORTED, "MSDA_QPROJ needs y2 and softmax group L*P = 18 (EMRT: 3 levels x 6 points), got %d", a->qproj_group);
     return launch_tc<144, 6, EPI_KIND_QPROJ, 18>(p, a, st);
   }
-  if (a->epilogue & ~(EMRT_EPI_ROW_MASK | EMRT_EPI_RELU))
+  if (a->epilogue & ~(EMRT_EPI_ROW_MASK | EMRT_EPI_RELU | EMRT_EPI_HEAD_MAJOR))
     return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 linear: unsupported epilogue flags %d", a->epilogue);
   if (a->N <= 64) return launch_tc<64, 8, EPI_KIND_GENERIC, 2>(p, a, st);
   if (a->N <= 128) return launch_tc<128, 6, EPI_KIND_GENERIC, 2>(p, a, st);

@@ -8,66 +8,11 @@
 // (bf16x8 / f32x4) of all four bilinear corners, so every corner fetch is one LDG.128 and a warp's 32 lanes
 // cover 32/G items.  Corners outside the map get weight 0 and a clamped (always valid, nearby) address: no
 // divergent branches, loads of consecutive points can overlap.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "msda_common.cuh"
 
 namespace emrt {
-
-template <typename TL> struct Pair;
-template <> struct Pair<float> {
-  __device__ static __forceinline__ float2 load(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-};
-template <> struct Pair<__half> {
-  __device__ static __forceinline__ float2 load(const __half* p) {
-    unsigned int r = __ldg(reinterpret_cast<const unsigned int*>(p));
-    return __half22float2(*reinterpret_cast<__half2*>(&r));
-  }
-};
-template <> struct Pair<__nv_bfloat16> {
-  __device__ static __forceinline__ float2 load(const __nv_bfloat16* p) {
-    unsigned int r = __ldg(reinterpret_cast<const unsigned int*>(p));
-    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
-  }
-};
-template <typename TL> __device__ __forceinline__ float load1(const TL* p) { return to_float(__ldg(p)); }
-template <> __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __uint_as_float(((unsigned int)__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
-}
-template <> __device__ __forceinline__ float load1<__half>(const __half* p) {
-  unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(p));
-  return __half2float(*reinterpret_cast<__half*>(&r));
-}
-
-// One bilinear footprint: 4 clamped pixel indices (relative to the level start) + 4 weights (0 when outside).
-struct Footprint {
-  int i00, i01, i10, i11;
-  float w00, w01, w10, w11;
-  float fx, fy;
-  bool v00, v01, v10, v11;
-};
-
-__device__ __forceinline__ Footprint make_footprint(float x, float y, int H, int W) {
-  Footprint f;
-  // grid_sample(align_corners=False, padding_mode='zeros'): corners (floor, floor+1), each dropped if outside.
-  // Reject NaN / far-away samples before the float->int conversion.
-  const bool any = (x > -1.f) && (y > -1.f) && (x < (float)W) && (y < (float)H);
-  const float xs = any ? x : 0.f, ys = any ? y : 0.f;
-  const float x0f = floorf(xs), y0f = floorf(ys);
-  const int x0 = (int)x0f, y0 = (int)y0f;
-  f.fx = xs - x0f;
-  f.fy = ys - y0f;
-  const bool xl = any && x0 >= 0, xh = any && (x0 + 1) < W;
-  const bool yl = any && y0 >= 0, yh = any && (y0 + 1) < H;
-  f.v00 = xl && yl; f.v01 = xh && yl; f.v10 = xl && yh; f.v11 = xh && yh;
-  const int xa = max(x0, 0), xb = min(x0 + 1, W - 1);
-  const int ya = max(y0, 0), yb = min(y0 + 1, H - 1);
-  f.i00 = ya * W + xa; f.i01 = ya * W + xb; f.i10 = yb * W + xa; f.i11 = yb * W + xb;
-  const float gx = 1.f - f.fx, gy = 1.f - f.fy;
-  f.w00 = f.v00 ? gx * gy : 0.f;
-  f.w01 = f.v01 ? f.fx * gy : 0.f;
-  f.w10 = f.v10 ? gx * f.fy : 0.f;
-  f.w11 = f.v11 ? f.fx * f.fy : 0.f;
-  return f;
-}
 
 template <typename TV, typename TL, int MODE, int D>
 __global__ void __launch_bounds__(256)
@@ -270,15 +215,17 @@ static int check_common(const void* value, const void* loc, const void* attn, co
   EMRT_REQUIRE(B > 0 && Lq > 0 && Lv > 0 && M > 0 && D > 0 && P > 0, "non-positive dimension");
   EMRT_REQUIRE(value_dtype == EMRT_F32 || value_dtype == EMRT_BF16, "value_dtype must be F32 or BF16");
   EMRT_REQUIRE(loc_dtype == EMRT_F32 || loc_dtype == EMRT_F16 || loc_dtype == EMRT_BF16, "bad loc_dtype");
-  EMRT_REQUIRE(mode == EMRT_LOC_NORMALIZED || mode == EMRT_LOC_PIXEL_OFFSET, "bad loc mode");
-  EMRT_REQUIRE(mode != EMRT_LOC_PIXEL_OFFSET || ref != nullptr, "PIXEL_OFFSET mode needs reference points");
+  EMRT_REQUIRE((mode & ~(EMRT_LOC_PIXEL_OFFSET | EMRT_VALUE_HEAD_MAJOR)) == 0, "bad mode flags");
+  EMRT_REQUIRE(!(mode & EMRT_LOC_PIXEL_OFFSET) || ref != nullptr, "PIXEL_OFFSET mode needs reference points");
   (void)L;
   return EMRT_OK;
 }
 
 #define EMRT_GATHER_DISPATCH(LAUNCH, ...)                                                                      \
   do {                                                                                                         \
-    const bool px = (mode == EMRT_LOC_PIXEL_OFFSET);                                                           \
+    if (mode & EMRT_VALUE_HEAD_MAJOR)                                                                          \
+      return set_error(EMRT_ERR_UNSUPPORTED, "head-major value layout needs bf16, D=32, L=3, P=6 (forward)");   \
+    const bool px = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;                                                       \
     if (value_dtype == EMRT_F32) {                                                                             \
       if (loc_dtype != EMRT_F32) return set_error(EMRT_ERR_UNSUPPORTED, "F32 value needs F32 loc/attn");       \
       if (px) { EMRT_DISPATCH_D(float, float, 1, LAUNCH, __VA_ARGS__) }                                        \
@@ -305,6 +252,10 @@ extern "C" int emrt_msda_gather_fwd(const void* value, const void* loc, const vo
   if (int e = fill_levels(lv, L, shapes_hw_host, level_start_host, Lv)) return e;
   const int64_t n_items = (int64_t)B * Lq * M;
   cudaStream_t st = as_stream(stream);
+  if (value_dtype == EMRT_BF16 && !getenv("EMRT_GATHER_V0")) {
+    const int e = gather_fwd_v1(value, loc, attn, ref, ref_batch_stride, out, B, Lq, Lv, M, D, L, P, lv, loc_dtype, mode, st);
+    if (e != EMRT_ERR_UNSUPPORTED) return e;
+  }
   EMRT_GATHER_DISPATCH(launch_fwd, value, loc, attn, ref, ref_batch_stride, out, Lq, Lv, M, L, P, lv, n_items, st);
 }
 

@@ -79,6 +79,7 @@ class MSDeformableAttention(nn.Module):
         self.output_proj = PaddleLinear(embed_dim, embed_dim)
         self.lr_mult = lr_mult
         self.gemm_impl = L.IMPL_AUTO      # tests may force L.IMPL_SIMT / L.IMPL_TCGEN05
+        self.head_major = True            # bf16 path: value_proj writes [B,M,Lv,D] for the specialised gather
         self._packed = None
         self._reset_parameters()
 
@@ -170,8 +171,11 @@ class MSDeformableAttention(nn.Module):
         pk = self.packed_weights()
         mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
         impl = self.gemm_impl
-        v = ops.linear(value.contiguous(), pk["wv"], pk["bv"], w_transposed=True,
-                       epilogue=L.EPI_ROW_MASK if mask is not None else L.EPI_NONE, row_scale=mask, impl=impl)
+        # head-major value layout [B,M,Lv,D]: written by the value_proj epilogue, read by the specialised gather
+        head_major = (impl != L.IMPL_SIMT and self.head_major and D == 32 and self.num_levels == 3 and P == 6)
+        epi = (L.EPI_ROW_MASK if mask is not None else L.EPI_NONE) | (L.EPI_HEAD_MAJOR if head_major else 0)
+        v = ops.linear(value.contiguous(), pk["wv"], pk["bv"], w_transposed=True, epilogue=epi, row_scale=mask,
+                       impl=impl, hm_rows=value.shape[1] if head_major else 0, hm_D=D if head_major else 0)
         ref32 = ref.float().contiguous()
         if impl == L.IMPL_SIMT:
             raw = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float32,
@@ -184,5 +188,9 @@ class MSDeformableAttention(nn.Module):
                                       y_dtype=torch.float16, epilogue=L.EPI_MSDA_QPROJ, qproj_group=LP, impl=impl)
             off_px = off_px.view(bs, Len_q, M, self.num_levels, P, 2)
             attn = attn.view(bs, Len_q, M, self.num_levels, P)
-        out = ops.msda_gather_fwd(v.view(bs, -1, M, D), off_px, attn, shapes, ref=ref32, mode=L.LOC_PIXEL_OFFSET)
+        if head_major:
+            out = ops.msda_gather_fwd(v.view(bs, M, -1, D), off_px, attn, shapes, ref=ref32,
+                                      mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR)
+        else:
+            out = ops.msda_gather_fwd(v.view(bs, -1, M, D), off_px, attn, shapes, ref=ref32, mode=L.LOC_PIXEL_OFFSET)
         return ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl)

@@ -65,7 +65,10 @@ def reset_launch_count():
 def msda_gather_fwd(value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, out=None):
     """value [B,Lv,M,D]; loc [B,Lq,M,L,P,2]; attn [B,Lq,M,L,P]; ref [Bref,Lq,L,2] f32 (PIXEL_OFFSET) -> [B,Lq,M*D]."""
     lib = L.load()
-    B, Lv, M, D = value.shape
+    if mode & L.VALUE_HEAD_MAJOR:
+        B, M, Lv, D = value.shape
+    else:
+        B, Lv, M, D = value.shape
     _, Lq, _, nL, P, _ = loc.shape
     hw, start, total = level_tables(shapes)
     if out is None:
@@ -100,7 +103,8 @@ def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NOR
 
 # ---- nn.Linear -----------------------------------------------------------------------------------------------
 def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_NONE, row_scale=None, residual=None,
-           ln_gamma=None, ln_beta=None, ln_eps=1e-5, qproj_group=0, impl=L.IMPL_AUTO, out=None, out2=None):
+           ln_gamma=None, ln_beta=None, ln_eps=1e-5, qproj_group=0, impl=L.IMPL_AUTO, out=None, out2=None, hm_rows=0,
+           hm_D=0):
     """y = epilogue(x @ W + bias).  x [..., K]; W [K,N] (Paddle layout) or [N,K] when w_transposed."""
     lib = L.load()
     K = x.shape[-1]
@@ -126,6 +130,7 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     a.y2 = _ptr(out2)
     a.qproj_group = int(qproj_group)
     a.impl = int(impl)
+    a.hm_rows, a.hm_D = int(hm_rows), int(hm_D)
     L.check(lib.emrt_linear_fwd(C.byref(a), _stream()))
     return (out, out2) if (epilogue & L.EPI_MSDA_QPROJ) else out
 

@@ -47,7 +47,10 @@ typedef enum emrt_loc_mode {
   /* `loc` holds the raw sampling_offsets output in PIXELS [B,Lq,M,L,P,2] and `ref` the reference points
    * [Bref,Lq,L,2] (Bref = B or 1) in [0,1]; the kernel forms x = ref_x*W_l + off_x - 0.5, which is
    * transformer_encoder_decoder.py:98-102 folded into utils.py:79,87. */
-  EMRT_LOC_PIXEL_OFFSET = 1
+  EMRT_LOC_PIXEL_OFFSET = 1,
+  /* flag, OR-ed into `mode`: `value` is laid out head-major [B,M,Lv,D] (what emrt_linear_fwd writes with
+   * EMRT_EPI_HEAD_MAJOR) instead of the reference's [B,Lv,M,D].  Forward only; bf16, D=32, L=3, P=6. */
+  EMRT_VALUE_HEAD_MAJOR = 2
 } emrt_loc_mode;
 
 /* Epilogues of emrt_linear_fwd (bit flags). */
@@ -56,7 +59,9 @@ typedef enum emrt_epilogue {
   EMRT_EPI_ROW_MASK = 1,      /* y[r,:] *= row_scale[r]      (value_mask, t_e_d.py:84-86)              */
   EMRT_EPI_RELU = 2,          /* y = max(y,0)                 (FFN activation, t_e_d.py:158)            */
   EMRT_EPI_RESIDUAL_LN = 4,   /* y = LayerNorm(residual + y)  (t_e_d.py:199-200; N must be 256)         */
-  EMRT_EPI_MSDA_QPROJ = 8     /* N = M*L*P*3: [offsets | logits] -> pixel offsets + softmax(L*P)         */
+  EMRT_EPI_MSDA_QPROJ = 8,    /* N = M*L*P*3: [offsets | logits] -> pixel offsets + softmax(L*P)         */
+  EMRT_EPI_HEAD_MAJOR = 16    /* store y[b, n/hm_D, r % hm_rows, n % hm_D] (r = b*hm_rows + pix): the value    *
+                               * tensor laid out [B,M,Lv,D] for the gather; needs hm_rows, hm_D (tcgen05 only) */
 } emrt_epilogue;
 
 int emrt_version(void);
@@ -102,6 +107,7 @@ typedef struct emrt_linear_args {
   const void* residual; const float* ln_gamma; const float* ln_beta; float ln_eps;
   void* y2; int32_t qproj_group;
   int32_t impl;               /* 0 = auto, 1 = force SIMT, 2 = force tcgen05 */
+  int32_t hm_rows; int32_t hm_D;   /* HEAD_MAJOR: rows per batch element (Lv) and head dim */
 } emrt_linear_args;
 int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 

@@ -255,3 +255,39 @@ def test_linear_tcgen05_matches_fp64(cuda_dev, rows, K, N, epi):
     assert got16.dtype == torch.bfloat16 and rel_err(got16.float(), ref) < 1e-2
     simt = ops.linear(xd, wt, bd, w_transposed=True, y_dtype=torch.float32, epilogue=flags, impl=L.IMPL_SIMT, **kw)
     assert rel_err(got32, simt.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("Lq,B", [(1344, 2), (110, 3), (5376, 1), (77, 1)])
+@pytest.mark.parametrize("loc_dtype", [torch.float16, torch.float32])
+def test_gather_v1_specialised_kernel_all_layouts(cuda_dev, Lq, B, loc_dtype):
+    """bf16 / D=32 / 3x6 specialised kernel: pixel-major and head-major value layouts, both loc modes, against the
+    float64 oracle and against the generic kernel (EMRT_GATHER_V0=1)."""
+    shapes = [(32, 32), (16, 16), (8, 8)] if Lq != 5376 else [(64, 64), (32, 32), (16, 16)]
+    M, D, P = 8, 32, 6
+    rng = np.random.Generator(np.random.PCG64(Lq))
+    _, Lv = O.level_tables(shapes)
+    value = torch.from_numpy(O.rng_normal(rng, (B, Lv, M, D))).bfloat16()
+    off = torch.from_numpy(O.rng_normal(rng, (B, Lq, M, 3, P, 2), 4.0)).to(loc_dtype)
+    attn = torch.from_numpy(rng.uniform(0, 1, size=(B, Lq, M, 3, P)).astype(np.float32)).to(loc_dtype)
+    ref = rng.uniform(0, 1, size=(B, Lq, 3, 2)).astype(np.float32)
+    norm = np.array([[w, h] for h, w in shapes], np.float32).reshape(1, 1, 1, 3, 1, 2)
+    loc = ref.reshape(B, Lq, 1, 3, 1, 2) + off.float().numpy() / norm
+    want = O.gather_corner_loop(value.float().numpy(), shapes, loc, attn.float().numpy())
+    d = lambda t: (torch.from_numpy(t) if isinstance(t, np.ndarray) else t).to(cuda_dev)
+    vd, od, ad, rd = d(value), d(off), d(attn), d(ref)
+    v_hm = vd.permute(0, 2, 1, 3).contiguous()
+    got_pm = ops.msda_gather_fwd(vd, od, ad, shapes, ref=rd, mode=L.LOC_PIXEL_OFFSET)
+    got_hm = ops.msda_gather_fwd(v_hm, od, ad, shapes, ref=rd, mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR)
+    os.environ["EMRT_GATHER_V0"] = "1"
+    try:
+        got_v0 = ops.msda_gather_fwd(vd, od, ad, shapes, ref=rd, mode=L.LOC_PIXEL_OFFSET)
+    finally:
+        del os.environ["EMRT_GATHER_V0"]
+    assert rel_err(got_pm.float(), want) < BF16_TOL
+    assert torch.equal(got_pm, got_hm)                      # same arithmetic, different value layout
+    assert rel_err(got_pm.float(), got_v0.float().cpu()) < BF16_TOL
+    # normalised-location mode through the same kernel
+    locd = d(loc.astype(np.float32)).to(loc_dtype)
+    want_n = O.gather_corner_loop(value.float().numpy(), shapes, locd.float().cpu().numpy(), attn.float().numpy())
+    got_n = ops.msda_gather_fwd(v_hm, locd, ad, shapes, mode=L.LOC_NORMALIZED | L.VALUE_HEAD_MAJOR)
+    assert rel_err(got_n.float(), want_n) < BF16_TOL
