@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libemrt_b200.so")
 
 # enums (mirror include/emrt_b200.h)
 F32, BF16, F16, I32, U8 = 0, 1, 2, 3, 4
-LOC_NORMALIZED, LOC_PIXEL_OFFSET, VALUE_HEAD_MAJOR = 0, 1, 2
+LOC_NORMALIZED, LOC_PIXEL_OFFSET, VALUE_HEAD_MAJOR, QUERY_PIXEL_GRID = 0, 1, 2, 4
 EPI_NONE, EPI_ROW_MASK, EPI_RELU, EPI_RESIDUAL_LN, EPI_MSDA_QPROJ, EPI_HEAD_MAJOR = 0, 1, 2, 4, 8, 16
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 

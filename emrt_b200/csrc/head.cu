@@ -5,6 +5,8 @@
 // All of it is HBM-bound byte/float work.  The fused kernel reads only the half-resolution window logits and
 // writes only the label map: per pixel it upsamples every covering window on the fly and sums them in window
 // order (deterministic, no atomics, no full-resolution fp32 canvas round trip).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace emrt {
@@ -53,7 +55,8 @@ struct WinList {
 };
 
 __device__ __forceinline__ void build_window_list(WinList& wl, int* warp_cnt, int n_win, int img, int ty0, int tx0,
-                                                  int hc, int wc, const int32_t* __restrict__ win_img,
+                                                  int tile_h, int tile_w, int hc, int wc,
+                                                  const int32_t* __restrict__ win_img,
                                                   const int32_t* __restrict__ win_y0,
                                                   const int32_t* __restrict__ win_x0) {
   const int t = threadIdx.y * blockDim.x + threadIdx.x;
@@ -65,7 +68,7 @@ __device__ __forceinline__ void build_window_list(WinList& wl, int* warp_cnt, in
     bool hit = false;
     if (w < n_win && __ldg(win_img + w) == img) {
       const int y0 = __ldg(win_y0 + w), x0 = __ldg(win_x0 + w);
-      hit = (y0 < ty0 + TILE_Y) && (y0 + hc > ty0) && (x0 < tx0 + TILE_X) && (x0 + wc > tx0);
+      hit = (y0 < ty0 + tile_h) && (y0 + hc > ty0) && (x0 < tx0 + tile_w) && (x0 + wc > tx0);
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) warp_cnt[warp] = __popc(ballot);
@@ -114,7 +117,7 @@ window_accumulate_kernel(const float* __restrict__ win_logits, float* __restrict
   __shared__ int warp_cnt[8];
   const int img = blockIdx.z;
   const int tx0 = blockIdx.x * TILE_X, ty0 = blockIdx.y * TILE_Y;
-  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, hc, wc, win_img, win_y0, win_x0);
+  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, TILE_Y, TILE_X, hc, wc, win_img, win_y0, win_x0);
   const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
   if (x >= W || y >= H) return;
   const int n = wl.n < 0 ? n_win : wl.n;
@@ -188,7 +191,7 @@ stitch_argmax_fused_kernel(const T* __restrict__ half_logits, void* __restrict__
   __shared__ int warp_cnt[8];
   const int img = blockIdx.z;
   const int tx0 = blockIdx.x * TILE_X, ty0 = blockIdx.y * TILE_Y;
-  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, hc, wc, win_img, win_y0, win_x0);
+  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, TILE_Y, TILE_X, hc, wc, win_img, win_y0, win_x0);
   const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
   if (x >= W || y >= H) return;
   const int hh = hc / 2, hw = wc / 2;
@@ -217,6 +220,132 @@ stitch_argmax_fused_kernel(const T* __restrict__ half_logits, void* __restrict__
   }
   const int best = softmax_argmax<NC>(acc, nc, prob);
   store_label(labels, label_dtype, (int64_t)img * plane + o, best);
+}
+
+// a5 + a6 + a7, one 2x2 quad of label pixels per thread (H, W even).  For x2 upsampling the four pixels of a quad read
+// at most a 3x3 patch of the half-resolution logits, so a window costs 9 loads per class for 4 outputs instead of
+// 16, and the tap / address arithmetic is shared.  PY / PX = parity of the quad's first row / column in the
+// window's own coordinates (uniform per CTA and window); the per-pixel arithmetic is make_tap + bilerp unchanged,
+// so results equal the one-pixel kernel bit for bit.
+template <typename T, int NC, int PY, int PX>
+__device__ __forceinline__ void quad_accumulate(const T* __restrict__ src, int nc, int hh, int hw, int ly, int lx,
+                                                float (&acc)[4][NC]) {
+  // rows / columns of the patch: local coordinate 2k -> taps (k-1, k); 2k+1 -> taps (k, k+1); clamped loads reproduce
+  // make_tap's edge rule exactly (a + f * (a - a) == a)
+  constexpr int NR = PY ? 2 : 3, NCOL = PX ? 2 : 3;
+  const int ky = ly >> 1, kx = lx >> 1;
+  int ry[NR], rx[NCOL];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) ry[i] = min(max(ky - (PY ? 0 : 1) + i, 0), hh - 1) * hw;
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i) rx[i] = min(max(kx - (PX ? 0 : 1) + i, 0), hw - 1);
+  // output row j (0,1) uses patch rows (a, a+1) with fraction f: even local -> (0,1) f = 0.75 ; odd local -> (k,k+1) f = 0.25
+  // PY == 0: row 0 is even -> rows (0,1) f .75 ; row 1 odd -> rows (1,2) f .25.   PY == 1: row 0 odd -> (0,1) f .25 ; row 1 even -> (0,1) f .75
+  constexpr int ra[2] = {0, PY ? 0 : 1}, ca[2] = {0, PX ? 0 : 1};
+  float fy[2], fx[2];
+  fy[0] = make_tap(ly, hh, 0.5f).f; fy[1] = make_tap(ly + 1, hh, 0.5f).f;
+  fx[0] = make_tap(lx, hw, 0.5f).f; fx[1] = make_tap(lx + 1, hw, 0.5f).f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < nc) {
+      const T* pl = src + (int64_t)c * hh * hw;
+      float v[NR][NCOL];
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) v[i][j] = to_float(pl[ry[i] + rx[j]]);
+#pragma unroll
+      for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+          const float a = v[ra[oy]][ca[ox]], b = v[ra[oy]][ca[ox] + 1];
+          const float cc = v[ra[oy] + 1][ca[ox]], d = v[ra[oy] + 1][ca[ox] + 1];
+          const float top = a + fx[ox] * (b - a);
+          const float bot = cc + fx[ox] * (d - cc);
+          acc[oy * 2 + ox][c] += top + fy[oy] * (bot - top);
+        }
+    }
+  }
+}
+
+constexpr int QTILE = 32;   // label pixels per CTA side: 16 x 16 threads, one quad each
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(256)
+stitch_argmax_quad_kernel(const T* __restrict__ half_logits, void* __restrict__ labels, int label_dtype,
+                          float* __restrict__ logits_out, int n_win, int nc, int hc, int wc, int H, int W,
+                          const int32_t* __restrict__ win_img, const int32_t* __restrict__ win_y0,
+                          const int32_t* __restrict__ win_x0) {
+  __shared__ WinList wl;
+  __shared__ int warp_cnt[8];
+  const int img = blockIdx.z;
+  const int tx0 = blockIdx.x * QTILE, ty0 = blockIdx.y * QTILE;
+  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, QTILE, QTILE, hc, wc, win_img, win_y0, win_x0);
+  const int x = tx0 + 2 * threadIdx.x, y = ty0 + 2 * threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int hh = hc / 2, hw = wc / 2;
+  const int n = wl.n < 0 ? n_win : wl.n;
+  float acc[4][NC];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[k][c] = 0.f;
+  float cnt[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < n; ++i) {
+    const int w = wl.n < 0 ? i : wl.idx[i];
+    if (wl.n < 0 && __ldg(win_img + w) != img) continue;
+    const int ly = y - __ldg(win_y0 + w), lx = x - __ldg(win_x0 + w);
+    const T* src = half_logits + (int64_t)w * nc * hh * hw;
+    if (ly >= 0 && ly + 1 < hc && lx >= 0 && lx + 1 < wc) {
+      // whole quad inside the window (always the case for even origins and sizes)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cnt[k] += 1.f;
+      switch ((ly & 1) * 2 + (lx & 1)) {
+        case 0: quad_accumulate<T, NC, 0, 0>(src, nc, hh, hw, ly, lx, acc); break;
+        case 1: quad_accumulate<T, NC, 0, 1>(src, nc, hh, hw, ly, lx, acc); break;
+        case 2: quad_accumulate<T, NC, 1, 0>(src, nc, hh, hw, ly, lx, acc); break;
+        default: quad_accumulate<T, NC, 1, 1>(src, nc, hh, hw, ly, lx, acc); break;
+      }
+    } else {
+      // quad straddles the window border (odd origin): per-pixel path
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int py = ly + (k >> 1), px = lx + (k & 1);
+        if (py < 0 || py >= hc || px < 0 || px >= wc) continue;
+        cnt[k] += 1.f;
+        const Tap ty = make_tap(py, hh, 0.5f), tx = make_tap(px, hw, 0.5f);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) if (c < nc) acc[k][c] += bilerp<T>(src + (int64_t)c * hh * hw, hw, ty, tx);
+      }
+    }
+  }
+  const int64_t plane = (int64_t)H * W;
+  int best[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float prob[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) if (c < nc) acc[k][c] = acc[k][c] / cnt[k];
+    best[k] = softmax_argmax<NC>(acc[k], nc, prob);
+  }
+#pragma unroll
+  for (int oy = 0; oy < 2; ++oy) {
+    const int64_t o = (int64_t)(y + oy) * W + x;
+    if (logits_out) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c < nc)
+          *reinterpret_cast<float2*>(logits_out + ((int64_t)img * nc + c) * plane + o) =
+              make_float2(acc[oy * 2][c], acc[oy * 2 + 1][c]);
+    }
+    if (label_dtype == EMRT_U8) {
+      *reinterpret_cast<uchar2*>(reinterpret_cast<uint8_t*>(labels) + (int64_t)img * plane + o) =
+          make_uchar2((unsigned char)best[oy * 2], (unsigned char)best[oy * 2 + 1]);
+    } else {
+      *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(labels) + (int64_t)img * plane + o) =
+          make_int2(best[oy * 2], best[oy * 2 + 1]);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -293,8 +422,20 @@ extern "C" int emrt_stitch_argmax_fused(const void* half_logits, int in_dtype, v
   EMRT_REQUIRE(hc % 2 == 0 && wc % 2 == 0, "window size must be even (x2 upsample of the half-resolution logits)");
   EMRT_REQUIRE(label_dtype == EMRT_I32 || label_dtype == EMRT_U8, "label_dtype must be I32 or U8");
   if (nc > 32) return set_error(EMRT_ERR_UNSUPPORTED, "nc=%d > 32", nc);
-  dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, n_img), block(TILE_X, TILE_Y);
   cudaStream_t st = as_stream(stream);
+  if (H % 2 == 0 && W % 2 == 0 && nc <= 8 && !getenv("EMRT_STITCH_PIXEL")) {
+    dim3 qgrid((W + QTILE - 1) / QTILE, (H + QTILE - 1) / QTILE, n_img), qblock(16, 16);
+    if (in_dtype == EMRT_F32)
+      stitch_argmax_quad_kernel<float, 8><<<qgrid, qblock, 0, st>>>((const float*)half_logits, labels, label_dtype, logits_out,
+                                                                     n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0);
+    else if (in_dtype == EMRT_BF16)
+      stitch_argmax_quad_kernel<__nv_bfloat16, 8><<<qgrid, qblock, 0, st>>>((const __nv_bfloat16*)half_logits, labels, label_dtype,
+                                                                             logits_out, n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0);
+    else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad in_dtype %d", in_dtype);
+    EMRT_LAUNCH_CHECK();
+    return EMRT_OK;
+  }
+  dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, n_img), block(TILE_X, TILE_Y);
 #define EMRT_ST(T, NC)                                                                                           \
   stitch_argmax_fused_kernel<T, NC><<<grid, block, 0, st>>>((const T*)half_logits, labels, label_dtype, logits_out, \
                                                             n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0)

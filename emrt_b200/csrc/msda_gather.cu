@@ -215,7 +215,7 @@ static int check_common(const void* value, const void* loc, const void* attn, co
   EMRT_REQUIRE(B > 0 && Lq > 0 && Lv > 0 && M > 0 && D > 0 && P > 0, "non-positive dimension");
   EMRT_REQUIRE(value_dtype == EMRT_F32 || value_dtype == EMRT_BF16, "value_dtype must be F32 or BF16");
   EMRT_REQUIRE(loc_dtype == EMRT_F32 || loc_dtype == EMRT_F16 || loc_dtype == EMRT_BF16, "bad loc_dtype");
-  EMRT_REQUIRE((mode & ~(EMRT_LOC_PIXEL_OFFSET | EMRT_VALUE_HEAD_MAJOR)) == 0, "bad mode flags");
+  EMRT_REQUIRE((mode & ~(EMRT_LOC_PIXEL_OFFSET | EMRT_VALUE_HEAD_MAJOR | EMRT_QUERY_PIXEL_GRID)) == 0, "bad mode flags");
   EMRT_REQUIRE(!(mode & EMRT_LOC_PIXEL_OFFSET) || ref != nullptr, "PIXEL_OFFSET mode needs reference points");
   (void)L;
   return EMRT_OK;
@@ -252,6 +252,11 @@ extern "C" int emrt_msda_gather_fwd(const void* value, const void* loc, const vo
   if (int e = fill_levels(lv, L, shapes_hw_host, level_start_host, Lv)) return e;
   const int64_t n_items = (int64_t)B * Lq * M;
   cudaStream_t st = as_stream(stream);
+  if (value_dtype == EMRT_BF16 && (mode & EMRT_QUERY_PIXEL_GRID) && !getenv("EMRT_GATHER_NO_WIN")) {
+    const int e = gather_fwd_win(value, loc, attn, ref, ref_batch_stride, out, B, Lq, Lv, M, D, L, P, lv, loc_dtype, mode, st);
+    if (e != EMRT_ERR_UNSUPPORTED) return e;
+  }
+  mode &= ~EMRT_QUERY_PIXEL_GRID;
   if (value_dtype == EMRT_BF16 && !getenv("EMRT_GATHER_V0")) {
     const int e = gather_fwd_v1(value, loc, attn, ref, ref_batch_stride, out, B, Lq, Lv, M, D, L, P, lv, loc_dtype, mode, st);
     if (e != EMRT_ERR_UNSUPPORTED) return e;

@@ -1,0 +1,458 @@
+// Forward sampling-gather with the value windows staged in shared memory by TMA (encoder self-attention).
+//
+// ncu on the L1-path kernel (profiles/r1b_gather_ncu.txt) shows it bound by the SM's L1 data pipe
+// (l1tex__data_pipe_lsu_wavefronts 84 % of peak): every bilinear corner is a 64-byte segment of another 128-byte
+// line, so one LDG.128 costs ~6 wavefronts for 512 bytes.  HBM traffic is already minimal (168 MB for 183 MB
+// algorithmic).  The remaining lever is wavefronts per byte, so this kernel
+//   1. lets one CTA own a REGION of the image (TH x TW level-0 pixels and the co-located pixels of the coarser
+//      levels — all of them queries) for one (batch, head), and has TMA copy the three value windows that region
+//      can reach (region +- R pixels) into shared memory, out-of-map pixels zero-filled by the tensor map — which
+//      IS grid_sample's zeros padding, so the fast path has no validity logic at all;
+//   2. computes each bilinear footprint once (one lane per (query, point)) into a 16-byte record
+//      {smem address of the top pixel pair, of the bottom pair, bf16 weights left (top,bottom), right (top,bottom)};
+//   3. gathers with 8 lanes per query: lanes 0-3 read the left pixel's 64 bytes, lanes 4-7 the right pixel's — one
+//      contiguous 128-byte span per query and row, i.e. a conflict-free LDS.128 at the full 128 B/clk;
+//   4. accumulates with the sm_100 mixed-precision FMA (fma.rn.f32.bf16, SASS FHFMA.BF16): bf16 x bf16 + fp32 with the
+//      half-word selected inside the instruction, so there is no unpack work.
+// A sample that lands outside the staged window but inside the map (|offset| > R) takes a per-point slow path
+// that reads global memory with explicit validity weights, so results do not depend on R.
+// The query -> region mapping is only a locality promise (EMRT_QUERY_PIXEL_GRID): any reference points give
+// correct results, far-away ones just run the slow path.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "msda_common.cuh"
+#include "tc_common.cuh"
+
+namespace emrt {
+
+int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
+constexpr int WIN_L = 3, WIN_P = 6, WIN_LP = WIN_L * WIN_P, WIN_D = 32;
+constexpr int WIN_WARPS = 8;
+constexpr int WIN_QPB = 4;                   // queries per warp batch (one LDS.128 serves 4 queries x 128 bytes)
+constexpr uint32_t WIN_SLOW = 0x80000000u;   // record flag: take the global-memory path for this point
+
+struct WinParams {
+  CUtensorMap tmap[WIN_L];       // level l: {32 ch, W_l, H_l, B*M} bf16, box {32, WW_l, WH_l, 1}, zero OOB fill
+  int32_t WW[WIN_L], WH[WIN_L];  // window size in pixels
+  uint32_t win_off[WIN_L];       // byte offset of window l in dynamic shared memory (offset 0 holds 128 zero bytes)
+  uint32_t rec_off;              // byte offset of the footprint records
+  int32_t R, TH, TW, regions_x, regions_y;
+  int32_t Lq, Lv, M;
+  LevelTable lv;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// acc += bf16(half of word) * bf16(half of wpair), fp32 accumulate (FHFMA.BF16)
+template <int HI, int WHI>
+__device__ __forceinline__ void fhfma(float& acc, uint32_t word, uint32_t wpair) {
+  unsigned short a_lo, a_hi, w_lo, w_hi;
+  asm("mov.b32 {%0,%1}, %2;" : "=h"(a_lo), "=h"(a_hi) : "r"(word));
+  asm("mov.b32 {%0,%1}, %2;" : "=h"(w_lo), "=h"(w_hi) : "r"(wpair));
+  asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(HI ? a_hi : a_lo), "h"(WHI ? w_hi : w_lo));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 8 channels of one pixel row pair: acc[2i] += lo(d[i]) * w, acc[2i+1] += hi(d[i]) * w, with w = half WHI of wpair
+template <int WHI>
+__device__ __forceinline__ void fma_row(float (&acc)[8], const uint4& d, uint32_t wpair) {
+  fhfma<0, WHI>(acc[0], d.x, wpair); fhfma<1, WHI>(acc[1], d.x, wpair);
+  fhfma<0, WHI>(acc[2], d.y, wpair); fhfma<1, WHI>(acc[3], d.y, wpair);
+  fhfma<0, WHI>(acc[4], d.z, wpair); fhfma<1, WHI>(acc[5], d.z, wpair);
+  fhfma<0, WHI>(acc[6], d.w, wpair); fhfma<1, WHI>(acc[7], d.w, wpair);
+}
+
+// local query index inside the region (level-0 pixels first, then level 1, ...) -> global query index
+__device__ __forceinline__ int region_query(const WinParams& p, int k, int ry, int rx) {
+  int th = p.TH, tw = p.TW;
+#pragma unroll
+  for (int l = 0; l < WIN_L; ++l) {
+    const int n = th * tw;
+    if (k < n || l == WIN_L - 1) {
+      const int y = k / tw, x = k - y * tw;
+      return p.lv.start[l] + (ry * th + y) * p.lv.W[l] + rx * tw + x;
+    }
+    k -= n;
+    th >>= 1; tw >>= 1;
+  }
+  return 0;
+}
+
+template <typename TL, int MODE>
+__device__ __forceinline__ void sample_xy(const WinParams& p, const TL* __restrict__ loc, const TL* __restrict__ attn,
+                                          const float* __restrict__ ref, int64_t ref_bs, int b, int q, int m, int pt,
+                                          float& x, float& y, float& aw) {
+  const int l = pt / WIN_P;
+  const int64_t item = ((int64_t)b * p.Lq + q) * p.M + m;
+  const float2 xy = Pair<TL>::load(loc + (item * WIN_LP + pt) * 2);
+  aw = load1<TL>(attn + item * WIN_LP + pt);
+  const float W = (float)p.lv.W[l], H = (float)p.lv.H[l];
+  if (MODE == EMRT_LOC_PIXEL_OFFSET) {
+    const float2 rf = __ldg(reinterpret_cast<const float2*>(ref + b * ref_bs + ((int64_t)q * WIN_L + l) * 2));
+    x = rf.x * W - 0.5f + xy.x;
+    y = rf.y * H - 0.5f + xy.y;
+  } else {
+    x = xy.x * W - 0.5f;
+    y = xy.y * H - 0.5f;
+  }
+}
+
+__device__ __forceinline__ int sel3(int l, int a0, int a1, int a2) { return l == 0 ? a0 : (l == 1 ? a1 : a2); }
+
+// Slow path of one point: it left the staged window (|offset| > R) but not the map.  Global loads with the explicit
+// zero-padding weights of make_footprint; out-of-line so the unrolled fast path stays small.
+template <typename TL, int MODE>
+__device__ __noinline__ void slow_point(const WinParams& p, const __nv_bfloat16* __restrict__ value,
+                                        const TL* __restrict__ loc, const TL* __restrict__ attn,
+                                        const float* __restrict__ ref, int64_t ref_bs, int b, int q, int m, int pt, int s,
+                                        uint4* d0, uint4* d1, uint32_t* wp) {
+  float x, y, aw;
+  sample_xy<TL, MODE>(p, loc, attn, ref, ref_bs, b, q, m, pt, x, y, aw);
+  const int l = pt / WIN_P, side = s >> 2;
+  const Footprint f = make_footprint(x, y, p.lv.H[l], p.lv.W[l]);
+  const int64_t plane = ((int64_t)b * p.M + m) * p.Lv * WIN_D;
+  const char* base = reinterpret_cast<const char*>(value + plane + (int64_t)p.lv.start[l] * WIN_D) + (s & 3) * 16;
+  *d0 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(side ? f.i01 : f.i00) * (WIN_D * 2)));
+  *d1 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(side ? f.i11 : f.i10) * (WIN_D * 2)));
+  *wp = side ? pack_bf16(f.w01 * aw, f.w11 * aw) : pack_bf16(f.w00 * aw, f.w10 * aw);
+}
+
+// Raw inputs of one (query, point) as they sit in global memory; fetched one batch ahead of their use.
+template <typename TL> struct RawLoc;
+template <> struct RawLoc<float> { float2 xy; float aw; };
+template <> struct RawLoc<__half> { unsigned int xy; unsigned short aw; };
+template <> struct RawLoc<__nv_bfloat16> { unsigned int xy; unsigned short aw; };
+__device__ __forceinline__ void raw_fetch(RawLoc<float>& r, const float* lp, const float* ap) {
+  r.xy = __ldg(reinterpret_cast<const float2*>(lp)); r.aw = __ldg(ap);
+}
+template <typename TL> __device__ __forceinline__ void raw_fetch(RawLoc<TL>& r, const TL* lp, const TL* ap) {
+  r.xy = __ldg(reinterpret_cast<const unsigned int*>(lp));
+  r.aw = __ldg(reinterpret_cast<const unsigned short*>(ap));
+}
+__device__ __forceinline__ void raw_decode(const RawLoc<float>& r, float& x, float& y, float& aw) { x = r.xy.x; y = r.xy.y; aw = r.aw; }
+__device__ __forceinline__ void raw_decode(const RawLoc<__half>& r, float& x, float& y, float& aw) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r.xy));
+  x = f.x; y = f.y; aw = __half2float(*reinterpret_cast<const __half*>(&r.aw));
+}
+__device__ __forceinline__ void raw_decode(const RawLoc<__nv_bfloat16>& r, float& x, float& y, float& aw) {
+  x = __uint_as_float(r.xy << 16); y = __uint_as_float(r.xy & 0xffff0000u); aw = __uint_as_float((unsigned int)r.aw << 16);
+}
+
+constexpr int WIN_ROUNDS = (WIN_QPB * WIN_LP + 31) / 32;   // stage-A rounds: one (query, point) per lane per round
+constexpr int WIN_MAX_Q = 512;                             // queries per region (TH*TW*(1 + 1/4 + 1/16)), upper bound
+
+template <typename TL, int MODE, bool REC64>
+__global__ void __launch_bounds__(WIN_WARPS * 32, 2)
+msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __restrict__ loc,
+                           const TL* __restrict__ attn, const float* __restrict__ ref, int64_t ref_bs,
+                           __nv_bfloat16* __restrict__ out, const __grid_constant__ WinParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t s_bar;
+  __shared__ int s_next;
+  __shared__ int s_qtab[WIN_MAX_Q + WIN_QPB];     // region-local query index -> global query index (-1 = padding)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.x = ((b * regions + region) * M + m): the M heads of a region run back to back (shared loc rows)
+  const int m = blockIdx.x % p.M;
+  const int br = blockIdx.x / p.M;
+  const int n_regions = p.regions_x * p.regions_y;
+  const int region = br % n_regions;
+  const int b = br / n_regions;
+  const int ry = region / p.regions_x, rx = region - ry * p.regions_x;
+  const uint32_t smem_base = smem_u32(smem);
+
+  // window origins (level coordinates; may start at -1: the zero halo)
+  int ox[WIN_L], oy[WIN_L];
+#pragma unroll
+  for (int l = 0; l < WIN_L; ++l) {
+    const int x0 = (rx * p.TW) >> l, y0 = (ry * p.TH) >> l;
+    ox[l] = min(max(x0 - p.R, -1), p.lv.W[l] + 1 - p.WW[l]);
+    oy[l] = min(max(y0 - p.R, -1), p.lv.H[l] + 1 - p.WH[l]);
+  }
+  // queries of this region: TH*TW at level 0, a quarter of that at each coarser level
+  int n_queries = 0;
+#pragma unroll
+  for (int l = 0; l < WIN_L; ++l) n_queries += (p.TH >> l) * (p.TW >> l);
+  const int n_batches = (n_queries + WIN_QPB - 1) / WIN_QPB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    s_next = WIN_WARPS;                      // batches 0..WIN_WARPS-1 are taken statically, one per warp
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(smem)[threadIdx.x] = 0u;   // what weight-0 records point at
+  for (int k = threadIdx.x; k < n_batches * WIN_QPB; k += WIN_WARPS * 32)
+    s_qtab[k] = k < n_queries ? region_query(p, k, ry, rx) : -1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t bytes = 0;
+#pragma unroll
+    for (int l = 0; l < WIN_L; ++l) bytes += (uint32_t)(p.WW[l] * p.WH[l]) * (WIN_D * 2);
+    mbar_arrive_expect_tx(&s_bar, bytes);
+#pragma unroll
+    for (int l = WIN_L - 1; l >= 0; --l)
+      tma_load_4d(smem_base + p.win_off[l], &p.tmap[l], &s_bar, 0, ox[l], oy[l], b * p.M + m);
+  }
+
+  const uint32_t rec_base = smem_base + p.rec_off + (uint32_t)warp * (WIN_QPB * WIN_LP * 16);
+  const int g = lane >> 3, s = lane & 7, side = s >> 2;
+
+  // ---- per-lane stage-A constants: round r handles (query qi[r], point pt[r]) of every batch ------------------------
+  int a_qi[WIN_ROUNDS], a_pt[WIN_ROUNDS], a_ox[WIN_ROUNDS], a_oy[WIN_ROUNDS], a_ww[WIN_ROUNDS], a_wh[WIN_ROUNDS];
+  uint32_t a_base[WIN_ROUNDS];
+  float a_W[WIN_ROUNDS], a_H[WIN_ROUNDS];
+  bool a_on[WIN_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < WIN_ROUNDS; ++r) {
+    const int j = r * 32 + lane;
+    a_on[r] = j < WIN_QPB * WIN_LP;
+    a_qi[r] = a_on[r] ? j / WIN_LP : 0;
+    a_pt[r] = a_on[r] ? j - a_qi[r] * WIN_LP : 0;
+    const int l = a_pt[r] / WIN_P;
+    a_ox[r] = sel3(l, ox[0], ox[1], ox[2]);
+    a_oy[r] = sel3(l, oy[0], oy[1], oy[2]);
+    a_ww[r] = p.WW[l];
+    a_wh[r] = p.WH[l];
+    a_base[r] = smem_base + p.win_off[l];
+    a_W[r] = (float)p.lv.W[l];
+    a_H[r] = (float)p.lv.H[l];
+  }
+
+  RawLoc<TL> raw[WIN_ROUNDS];
+  float2 rref[WIN_ROUNDS];
+  // issue the global loads of one batch (no dependent branches: one memory latency per batch)
+  // 32-bit element offsets from per-(b, m) base pointers (the host checks they fit)
+  const TL* loc_bm = loc + (((int64_t)b * p.Lq) * p.M + m) * (WIN_LP * 2);
+  const TL* attn_bm = attn + (((int64_t)b * p.Lq) * p.M + m) * WIN_LP;
+  const float* ref_b = ref + (MODE == EMRT_LOC_PIXEL_OFFSET ? b * ref_bs : 0);
+  auto fetch = [&](int batch) {
+#pragma unroll
+    for (int r = 0; r < WIN_ROUNDS; ++r) {
+      const int q = s_qtab[batch * WIN_QPB + a_qi[r]];
+      const uint32_t qq = q < 0 ? 0u : (uint32_t)q;
+      const uint32_t e = qq * (uint32_t)p.M * WIN_LP + (uint32_t)a_pt[r];
+      raw_fetch(raw[r], loc_bm + 2u * e, attn_bm + e);
+      if (MODE == EMRT_LOC_PIXEL_OFFSET)
+        rref[r] = __ldg(reinterpret_cast<const float2*>(ref_b + (qq * WIN_L + (uint32_t)(a_pt[r] / WIN_P)) * 2u));
+    }
+  };
+
+  int batch = warp;
+  if (batch < n_batches) fetch(batch);
+  bool windows_ready = false;
+
+  while (batch < n_batches) {
+    // ---- stage A: one footprint record per (query, point), from the prefetched inputs -----------------------------
+#pragma unroll
+    for (int r = 0; r < WIN_ROUNDS; ++r) {
+      if (a_on[r]) {
+        const int q = s_qtab[batch * WIN_QPB + a_qi[r]];
+        float x, y, aw;
+        raw_decode(raw[r], x, y, aw);
+        if (MODE == EMRT_LOC_PIXEL_OFFSET) {
+          x = rref[r].x * a_W[r] - 0.5f + x;
+          y = rref[r].y * a_H[r] - 0.5f + y;
+        } else {
+          x = x * a_W[r] - 0.5f;
+          y = y * a_H[r] - 0.5f;
+        }
+        // a sample whose four corners are all outside the map contributes exactly zero (also rejects NaN / inf)
+        const bool live = (q >= 0) && (x > -1.f) && (y > -1.f) && (x < a_W[r]) && (y < a_H[r]);
+        const float xs = live ? x : 0.f, ys = live ? y : 0.f;
+        const float x0f = floorf(xs), y0f = floorf(ys);
+        const float fx = xs - x0f, fy = ys - y0f;
+        const int wx = (int)x0f - a_ox[r], wy = (int)y0f - a_oy[r];
+        const bool inwin = (unsigned)wx < (unsigned)(a_ww[r] - 1) && (unsigned)wy < (unsigned)(a_wh[r] - 1);
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        const bool fast = live && inwin;
+        // not live: weight 0 on the zero block.  live but outside the window: same, plus the SLOW flag
+        const uint32_t addr = fast ? a_base[r] + (uint32_t)(wy * a_ww[r] + wx) * (WIN_D * 2)
+                                   : (smem_base | (live ? WIN_SLOW : 0u));
+        const uint32_t wl = fast ? pack_bf16(gx * gy * aw, gx * fy * aw) : 0u;   // left pixel: top, bottom
+        const uint32_t wr = fast ? pack_bf16(fx * gy * aw, fx * fy * aw) : 0u;   // right pixel: top, bottom
+        if (REC64) sts128(rec_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 16, addr, wl, addr, wr);
+        else sts128(rec_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 16, addr, wl, wr, 0u);
+      }
+    }
+    // next batch: claim it and start its loads now, they land while this batch gathers
+    const int cur = batch;
+    if (lane == 0) batch = atomicAdd(&s_next, 1);
+    batch = __shfl_sync(0xffffffffu, batch, 0);
+    if (batch < n_batches) fetch(batch);
+    __syncwarp();
+    if (!windows_ready) {
+      mbar_wait(&s_bar, 0);
+      windows_ready = true;
+    }
+
+    // ---- stage B: 8 lanes per query; lane s reads bytes [16 s, 16 s + 16) of the 128-byte pixel pair ----------------
+    const int q = s_qtab[cur * WIN_QPB + g];
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const uint32_t my_rec = rec_base + (uint32_t)g * (WIN_LP * 16);
+#pragma unroll 1
+    for (int l = 0; l < WIN_L; ++l) {
+      const uint32_t row_bytes = (uint32_t)p.WW[l] * (WIN_D * 2);
+      // the level's six records first: {address, this side's weight pair}
+      uint32_t addr[WIN_P], wpair[WIN_P];
+      uint32_t flags = 0u;
+#pragma unroll
+      for (int pp = 0; pp < WIN_P; ++pp) {
+        const uint32_t ra = my_rec + (l * WIN_P + pp) * 16;
+        if (REC64) {      // {addr, w_side}: 8 bytes per lane
+          asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(addr[pp]), "=r"(wpair[pp]) : "r"(ra + side * 8));
+        } else {
+          const uint4 rec = lds128(ra);
+          addr[pp] = rec.x;
+          wpair[pp] = side ? rec.z : rec.y;
+        }
+        flags |= addr[pp];
+      }
+      // branch-free fast path: twelve independent LDS.128 in flight, then 96 FHFMA (flagged records carry weight 0)
+      uint4 d0[WIN_P], d1[WIN_P];
+#pragma unroll
+      for (int pp = 0; pp < WIN_P; ++pp) {
+        const uint32_t a = (addr[pp] & ~WIN_SLOW) + s * 16;
+        d0[pp] = lds128(a);
+        d1[pp] = lds128(a + row_bytes);
+      }
+#pragma unroll
+      for (int pp = 0; pp < WIN_P; ++pp) {
+        fma_row<0>(acc, d0[pp], wpair[pp]);
+        fma_row<1>(acc, d1[pp], wpair[pp]);
+      }
+      if (__any_sync(0xffffffffu, (flags & WIN_SLOW) != 0u)) {
+        // fix-ups: points that left the staged window but not the map read global memory
+#pragma unroll 1
+        for (int pp = 0; pp < WIN_P; ++pp) {
+          uint32_t a = addr[0];
+#pragma unroll
+          for (int k = 1; k < WIN_P; ++k) { if (pp == k) a = addr[k]; }
+          if (a & WIN_SLOW) {
+            uint4 e0, e1;
+            uint32_t w;
+            slow_point<TL, MODE>(p, value, loc, attn, ref, ref_bs, b, q, m, l * WIN_P + pp, s, &e0, &e1, &w);
+            fma_row<0>(acc, e0, w);
+            fma_row<1>(acc, e1, w);
+          }
+        }
+      }
+    }
+    // left + right pixel halves: lane s keeps channels [8 (s&3) + 4 side, +4)
+    float keep[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float mine = side ? acc[4 + i] : acc[i];
+      const float send = side ? acc[i] : acc[4 + i];
+      keep[i] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    if (q >= 0) {
+      uint2 o;
+      o.x = pack_bf16(keep[0], keep[1]);
+      o.y = pack_bf16(keep[2], keep[3]);
+      *reinterpret_cast<uint2*>(out + (((int64_t)b * p.Lq + q) * p.M + m) * WIN_D + (s & 3) * 8 + side * 4) = o;
+    }
+    __syncwarp();   // records are rewritten by the next batch
+  }
+  if (!windows_ready) mbar_wait(&s_bar, 0);   // never leave with a TMA still writing this CTA's shared memory
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <typename TL, int MODE, bool REC64>
+static int launch_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
+                      int B, const WinParams& p, size_t smem_bytes, cudaStream_t st) {
+  auto kern = msda_gather_fwd_win_kernel<TL, MODE, REC64>;
+  static size_t attr = 0;
+  if (smem_bytes > attr) {
+    EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    attr = smem_bytes;
+  }
+  const int64_t grid = (int64_t)B * p.regions_x * p.regions_y * p.M;
+  if (grid > 0x7fffffffLL) return EMRT_ERR_UNSUPPORTED;
+  kern<<<(unsigned)grid, WIN_WARPS * 32, smem_bytes, st>>>((const __nv_bfloat16*)value, (const TL*)loc, (const TL*)attn,
+                                                           ref, ref_bs, (__nv_bfloat16*)out, p);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+// Returns EMRT_ERR_UNSUPPORTED (error text untouched) when the shape is not a regular 3-level pyramid this kernel
+// tiles; the caller then falls back to the L1-path kernel.
+int gather_fwd_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
+                   int B, int Lq, int Lv, int M, int D, int L, int P, const LevelTable& lv, int loc_dtype, int mode,
+                   cudaStream_t st) {
+  if (D != WIN_D || L != WIN_L || P != WIN_P || Lq != Lv || !(mode & EMRT_VALUE_HEAD_MAJOR)) return EMRT_ERR_UNSUPPORTED;
+  for (int l = 1; l < L; ++l)
+    if (lv.H[l] != (lv.H[0] >> l) || lv.W[l] != (lv.W[0] >> l) || (lv.H[l] << l) != lv.H[0] || (lv.W[l] << l) != lv.W[0])
+      return EMRT_ERR_UNSUPPORTED;
+  WinParams p;
+  memset(&p, 0, sizeof(p));
+  p.R = env_int("EMRT_WIN_R", 7);
+  p.TH = env_int("EMRT_WIN_TH", 8);
+  p.TW = env_int("EMRT_WIN_TW", 16);
+  if (p.R < 1 || p.TH < 4 || p.TW < 4 || (p.TH & 3) || (p.TW & 3) || lv.H[0] % p.TH || lv.W[0] % p.TW) return EMRT_ERR_UNSUPPORTED;
+  if ((int64_t)Lq * M * WIN_LP * 2 >= (1LL << 31)) return EMRT_ERR_UNSUPPORTED;   // 32-bit per-batch-element offsets
+  if (p.TH * p.TW + (p.TH >> 1) * (p.TW >> 1) + (p.TH >> 2) * (p.TW >> 2) > WIN_MAX_Q) return EMRT_ERR_UNSUPPORTED;
+  p.regions_x = lv.W[0] / p.TW;
+  p.regions_y = lv.H[0] / p.TH;
+  p.Lq = Lq; p.Lv = Lv; p.M = M; p.lv = lv;
+  uint32_t off = 128;   // [0,128): zero block
+  for (int l = 0; l < L; ++l) {
+    p.WW[l] = std::min((p.TW >> l) + 2 * p.R + 1, lv.W[l] + 2);
+    p.WH[l] = std::min((p.TH >> l) + 2 * p.R + 1, lv.H[l] + 2);
+    if (p.WW[l] > 256 || p.WH[l] > 256) return EMRT_ERR_UNSUPPORTED;
+    p.win_off[l] = off;
+    off += ((uint32_t)(p.WW[l] * p.WH[l]) * (WIN_D * 2) + 127u) & ~127u;
+    const uint64_t dims[4] = {(uint64_t)WIN_D, (uint64_t)lv.W[l], (uint64_t)lv.H[l], (uint64_t)B * M};
+    const uint64_t strides[3] = {(uint64_t)WIN_D * 2, (uint64_t)lv.W[l] * WIN_D * 2, (uint64_t)Lv * WIN_D * 2};
+    const uint32_t box[4] = {(uint32_t)WIN_D, (uint32_t)p.WW[l], (uint32_t)p.WH[l], 1u};
+    const __nv_bfloat16* base = (const __nv_bfloat16*)value + (int64_t)lv.start[l] * WIN_D;
+    if (int e = make_tensor_map(&p.tmap[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box,
+                                CU_TENSOR_MAP_SWIZZLE_NONE))
+      return e;
+  }
+  p.rec_off = off;
+  const size_t smem_bytes = (size_t)off + (size_t)WIN_WARPS * WIN_QPB * WIN_LP * 16;
+  if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(value) & 15) != 0) return EMRT_ERR_UNSUPPORTED;
+  const bool px = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;
+  const bool rec64 = env_int("EMRT_WIN_REC64", 1) != 0;
+#define EMRT_WIN(TL)                                                                                          \
+  if (rec64) return px ? launch_win<TL, 1, true>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)    \
+                       : launch_win<TL, 0, true>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);   \
+  return px ? launch_win<TL, 1, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)              \
+            : launch_win<TL, 0, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)
+  switch (loc_dtype) {
+    case EMRT_F32: EMRT_WIN(float);
+    case EMRT_F16: EMRT_WIN(__half);
+    case EMRT_BF16: EMRT_WIN(__nv_bfloat16);
+    default: return EMRT_ERR_UNSUPPORTED;
+  }
+#undef EMRT_WIN
+}
+
+}  // namespace emrt

@@ -12,6 +12,7 @@ import torch
 from . import _lib as L
 from . import ops
 from .msda import MSDeformableAttention
+from . import refpoints
 from . import synthetic
 
 
@@ -35,7 +36,7 @@ class HotPath:
             m.gemm_impl = gemm_impl
             (self.enc if i < num_enc else self.dec).append(m)
         rng = np.random.Generator(np.random.PCG64(seed + 100))
-        self.ref_enc = torch.from_numpy(synthetic.encoder_reference_points(self.shapes)).to(device)
+        self.ref_enc = refpoints.get_reference_points(self.shapes, device=device)   # cached + tagged pixel_grid
         ref_dec = rng.uniform(0.05, 0.95, size=(1, num_queries, 1, 2)).astype(np.float32)
         self.ref_dec = torch.from_numpy(np.ascontiguousarray(np.repeat(ref_dec, len(self.shapes), axis=2))).to(device)
         self.gather_events: Optional[list] = None

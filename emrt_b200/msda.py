@@ -176,7 +176,7 @@ class MSDeformableAttention(nn.Module):
         epi = (L.EPI_ROW_MASK if mask is not None else L.EPI_NONE) | (L.EPI_HEAD_MAJOR if head_major else 0)
         v = ops.linear(value.contiguous(), pk["wv"], pk["bv"], w_transposed=True, epilogue=epi, row_scale=mask,
                        impl=impl, hm_rows=value.shape[1] if head_major else 0, hm_D=D if head_major else 0)
-        ref32 = ref.float().contiguous()
+        ref32 = ref if (ref.dtype == torch.float32 and ref.is_contiguous()) else ref.float().contiguous()
         if impl == L.IMPL_SIMT:
             raw = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float32,
                              impl=L.IMPL_SIMT)
@@ -189,8 +189,10 @@ class MSDeformableAttention(nn.Module):
             off_px = off_px.view(bs, Len_q, M, self.num_levels, P, 2)
             attn = attn.view(bs, Len_q, M, self.num_levels, P)
         if head_major:
+            # encoder self-attention (queries = the pyramid's own pixels): window-staged kernel
+            grid = L.QUERY_PIXEL_GRID if (getattr(ref, "pixel_grid", False) and Len_q == value.shape[1]) else 0
             out = ops.msda_gather_fwd(v.view(bs, M, -1, D), off_px, attn, shapes, ref=ref32,
-                                      mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR)
+                                      mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR | grid)
         else:
             out = ops.msda_gather_fwd(v.view(bs, -1, M, D), off_px, attn, shapes, ref=ref32, mode=L.LOC_PIXEL_OFFSET)
         return ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl)

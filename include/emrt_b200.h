@@ -50,7 +50,12 @@ typedef enum emrt_loc_mode {
   EMRT_LOC_PIXEL_OFFSET = 1,
   /* flag, OR-ed into `mode`: `value` is laid out head-major [B,M,Lv,D] (what emrt_linear_fwd writes with
    * EMRT_EPI_HEAD_MAJOR) instead of the reference's [B,Lv,M,D].  Forward only; bf16, D=32, L=3, P=6. */
-  EMRT_VALUE_HEAD_MAJOR = 2
+  EMRT_VALUE_HEAD_MAJOR = 2,
+  /* flag, OR-ed into `mode`: a locality promise, never a correctness condition.  The Lq == Lv queries are the
+   * pixels of the value pyramid in level-major raster order and their reference points lie near their own pixel
+   * centres (TransformerEncoder.get_reference_points, transformer_encoder_decoder.py:213-228).  Selects the
+   * window-staged forward kernel (TMA -> shared-memory windows); needs EMRT_VALUE_HEAD_MAJOR. */
+  EMRT_QUERY_PIXEL_GRID = 4
 } emrt_loc_mode;
 
 /* Epilogues of emrt_linear_fwd (bit flags). */

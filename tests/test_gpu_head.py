@@ -121,3 +121,39 @@ def test_calculate_area_matches_oracle(cuda_dev):
     assert np.array_equal(got[0], ia) and np.array_equal(got[1], pa) and np.array_equal(got[2], la)
     with pytest.raises(ValueError):
         emrt_b200.calculate_area(torch.zeros(4, device=cuda_dev), torch.zeros(5, device=cuda_dev), 6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_quad_stitch_kernel_equals_pixel_kernel_any_window_parity(cuda_dev, dtype):
+    """The 2x2-quad stitch kernel (3x3 patch per window) must equal the one-pixel kernel bit for bit — logits and
+    labels — including windows at ODD origins (quads straddling window borders) and partially covered pixels."""
+    import os
+    rng = np.random.Generator(np.random.PCG64(21))
+    nc, H, W, hc, wc = 7, 70, 90, 32, 48
+    wins = [(0, 0, 0), (0, 0, 42), (0, 17, 5), (0, 38, 11), (0, 38, 42), (0, 3, 33), (1, 0, 0), (1, 38, 42), (1, 19, 21)]
+    # fill the rest so every pixel is covered at least once
+    for img in (0, 1):
+        for y in range(0, H - hc + 1, 19):
+            for x in range(0, W - wc + 1, 21):
+                wins.append((img, y, x))
+        wins += [(img, H - hc, x) for x in range(0, W - wc + 1, 21)] + [(img, y, W - wc) for y in range(0, H - hc + 1, 19)]
+        wins.append((img, H - hc, W - wc))
+    wins.sort(key=lambda w: w[0])
+    half = torch.from_numpy(O.rng_normal(rng, (len(wins), nc, hc // 2, wc // 2))).to(cuda_dev).to(dtype)
+    t = lambda k: torch.tensor([w[k] for w in wins], dtype=torch.int32, device=cuda_dev)
+    lab_q, log_q = ops.stitch_argmax_fused(half, t(0), t(1), t(2), 2, H, W, want_logits=True)
+    os.environ["EMRT_STITCH_PIXEL"] = "1"
+    try:
+        lab_p, log_p = ops.stitch_argmax_fused(half, t(0), t(1), t(2), 2, H, W, want_logits=True)
+    finally:
+        del os.environ["EMRT_STITCH_PIXEL"]
+    assert torch.equal(log_q, log_p)
+    assert torch.equal(lab_q, lab_p)
+    # and against the oracle's canvas formulation
+    full = O.upsample2x(half.float().cpu())
+    canvas, cnt = torch.zeros(2, nc, H, W), torch.zeros(2, 1, H, W)
+    for k, (i, y, x) in enumerate(wins):
+        canvas[i, :, y:y + hc, x:x + wc] += full[k]
+        cnt[i, :, y:y + hc, x:x + wc] += 1
+    assert (cnt > 0).all()
+    assert torch.allclose(log_q.cpu(), canvas / cnt, rtol=1e-5, atol=1e-5)

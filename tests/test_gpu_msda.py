@@ -291,3 +291,65 @@ def test_gather_v1_specialised_kernel_all_layouts(cuda_dev, Lq, B, loc_dtype):
     want_n = O.gather_corner_loop(value.float().numpy(), shapes, locd.float().cpu().numpy(), attn.float().numpy())
     got_n = ops.msda_gather_fwd(v_hm, locd, ad, shapes, mode=L.LOC_NORMALIZED | L.VALUE_HEAD_MAJOR)
     assert rel_err(got_n.float(), want_n) < BF16_TOL
+
+
+@pytest.mark.parametrize("tile,B,spread,R", [(512, 2, 3.0, None), (256, 3, 3.0, None), (512, 1, 9.0, None),
+                                              (256, 2, 3.0, "2"), (128, 2, 2.0, None)])
+@pytest.mark.parametrize("loc_dtype", [torch.float16, torch.float32])
+def test_gather_window_staged_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
+    """EMRT_QUERY_PIXEL_GRID (TMA-staged value windows, fma.rn.f32.bf16): encoder geometry, pixel-centre reference
+    points, offsets = reference-init directions + noise.  Checked against the float64 oracle and the L1-path kernel.
+    spread 9 / R=2 push many samples out of the staged window (slow path) and out of the map (zero padding)."""
+    shapes = [(tile // 8,) * 2, (tile // 16,) * 2, (tile // 32,) * 2]
+    M, D, P = 8, 32, 6
+    rng = np.random.Generator(np.random.PCG64(tile + B))
+    _, Lv = O.level_tables(shapes)
+    Lq = Lv
+    value = torch.from_numpy(O.rng_normal(rng, (B, Lv, M, D))).bfloat16()
+    bias = O.msda_reset_parameters(M * D, M, 3, P).reshape(1, 1, M, 3, P, 2)
+    off = torch.from_numpy(bias + O.rng_normal(rng, (B, Lq, M, 3, P, 2), spread)).to(loc_dtype)
+    attn = torch.from_numpy(rng.uniform(0, 1, size=(B, Lq, M, 3, P)).astype(np.float32)).to(loc_dtype)
+    ref_t = emrt_b200.get_reference_points(shapes, device=cuda_dev)
+    assert getattr(ref_t, "pixel_grid", False) and tuple(ref_t.shape) == (1, Lv, 3, 2)
+    assert torch.equal(ref_t.cpu(), O.encoder_reference_points(shapes, 1))
+    ref = ref_t.cpu().numpy()
+    norm = np.array([[w, h] for h, w in shapes], np.float32).reshape(1, 1, 1, 3, 1, 2)
+    loc = ref.reshape(1, Lq, 1, 3, 1, 2) + off.float().numpy() / norm
+    want = O.gather_corner_loop(value.float().numpy(), shapes, loc, attn.float().numpy())
+    d = lambda t: (torch.from_numpy(t) if isinstance(t, np.ndarray) else t).to(cuda_dev)
+    v_hm, od, ad = d(value).permute(0, 2, 1, 3).contiguous(), d(off), d(attn)
+    base = L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR
+    got_l1 = ops.msda_gather_fwd(v_hm, od, ad, shapes, ref=ref_t, mode=base)
+    if R is not None:
+        os.environ["EMRT_WIN_R"] = R
+    try:
+        before = ops.launch_count()
+        got = ops.msda_gather_fwd(v_hm, od, ad, shapes, ref=ref_t, mode=base | L.QUERY_PIXEL_GRID)
+        assert ops.launch_count() == before + 1
+        # normalised-location mode through the same kernel
+        locd = d(loc.astype(np.float32)).to(loc_dtype)
+        got_n = ops.msda_gather_fwd(v_hm, locd, ad, shapes, mode=L.LOC_NORMALIZED | L.VALUE_HEAD_MAJOR | L.QUERY_PIXEL_GRID)
+    finally:
+        os.environ.pop("EMRT_WIN_R", None)
+    torch.cuda.synchronize()
+    assert rel_err(got.float(), want) < BF16_TOL
+    assert rel_err(got.float(), got_l1.float().cpu()) < BF16_TOL
+    want_n = O.gather_corner_loop(value.float().numpy(), shapes, locd.float().cpu().numpy(), attn.float().numpy())
+    assert rel_err(got_n.float(), want_n) < BF16_TOL
+
+
+def test_gather_window_staged_arbitrary_reference_points(cuda_dev):
+    """The pixel-grid flag is only a locality promise: random reference points (almost every sample leaves its
+    region's window) must still give the oracle's result."""
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    M, D, P, B = 8, 32, 6, 1
+    rng = np.random.Generator(np.random.PCG64(5))
+    _, Lv = O.level_tables(shapes)
+    value = torch.from_numpy(O.rng_normal(rng, (B, Lv, M, D))).bfloat16()
+    loc = rng.uniform(-0.2, 1.2, size=(B, Lv, M, 3, P, 2)).astype(np.float32)
+    attn = rng.uniform(0, 1, size=(B, Lv, M, 3, P)).astype(np.float32)
+    want = O.gather_corner_loop(value.float().numpy(), shapes, loc, attn)
+    v_hm = value.to(cuda_dev).permute(0, 2, 1, 3).contiguous()
+    got = ops.msda_gather_fwd(v_hm, torch.from_numpy(loc).to(cuda_dev), torch.from_numpy(attn).to(cuda_dev), shapes,
+                              mode=L.LOC_NORMALIZED | L.VALUE_HEAD_MAJOR | L.QUERY_PIXEL_GRID)
+    assert rel_err(got.float(), want) < BF16_TOL

@@ -91,3 +91,18 @@ def test_two_rank_gloo_sharding():
     [p.join(60) for p in ps]
     for _, cover, areas in res:
         assert cover == [1.0] * 9 and areas == [9.0, 2.0]
+
+
+@pytest.mark.parametrize("shapes", [[(64, 64), (32, 32), (16, 16)], [(8, 6), (4, 3), (2, 2)], [(47, 33), (23, 17)]])
+def test_reference_points_host_mirror_equals_oracle(shapes):
+    """get_reference_points (t_e_d.py:213-228) host mirror == the oracle restatement, bit for bit; a non-trivial
+    valid_ratios follows the same arithmetic."""
+    import numpy as np
+    import oracle as O
+    from emrt_b200.refpoints import reference_points_host
+    got = reference_points_host(shapes)
+    assert got.shape == (1, sum(h * w for h, w in shapes), len(shapes), 2)
+    assert np.array_equal(got, O.encoder_reference_points(shapes, 1).numpy())
+    vr = np.full((2, len(shapes), 2), 0.75, np.float32)
+    got_vr = reference_points_host(shapes, vr)
+    assert got_vr.shape[0] == 2 and np.allclose(got_vr, got, atol=1e-6)     # (x / (vr * W)) * vr == x / W
