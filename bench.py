@@ -276,21 +276,56 @@ def run_ours(args):
         ms_total = max_over_ranks(e0.elapsed_time(e1))
 
         # ---- e2e: host buffers in, host labels out, every step -------------------------------------------
+        # Three streams: H2D of step i+1 (pinned -> device slot) overlaps the kernels of step i, and the D2H of step
+        # i's labels / decoder states overlaps step i+1.  Every step's copies are inside the timed region.
+        cur = torch.cuda.current_stream()
+        h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        slots = [{k: torch.empty_like(v, device=dev) for k, v in host_sets[0].items()} for _ in range(2)]
+        lab_slots = [torch.empty_like(labels_dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        drained = [torch.cuda.Event() for _ in range(2)]
+        hs_keep = [None, None]
+        for ev in free + drained:
+            ev.record(cur)
+
         def e2e_step(i):
+            sl = i % 2
             h = host_sets[i % N_SETS]
-            d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+            with torch.cuda.stream(h2d):
+                h2d.wait_event(free[sl])               # the kernels of step i-2 are done with this slot
+                for k, v in h.items():
+                    slots[sl][k].copy_(v, non_blocking=True)
+                ready[sl].record(h2d)
+            cur.wait_event(ready[sl])
+            cur.wait_event(drained[sl])                # step i-2's labels have left lab_slots[sl]
+            d = dict(slots[sl])
             d.update(pos=pos, qpos=qpos, mask=mask, **win)
-            lab, hs = hp.step(d, labels_dev)
-            labels_host.copy_(lab, non_blocking=True)
-            hs_host.copy_(hs, non_blocking=True)
+            lab, hs = hp.step(d, lab_slots[sl])
+            hs_keep[sl] = hs
+            free[sl].record(cur)
+            done[sl].record(cur)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done[sl])
+                labels_host.copy_(lab, non_blocking=True)
+                hs_host.copy_(hs, non_blocking=True)
+                hs.record_stream(d2h)
+                drained[sl].record(d2h)
+
+        def e2e_sync():
+            h2d.synchronize(); d2h.synchronize()
         for i in range(min(args.warmup, 3)):
             e2e_step(i)
+        e2e_sync()
         sync_all()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for i in range(args.steps):
             e2e_step(i)
+        cur.wait_stream(d2h)                           # the last labels are on the host when f1 fires
         f1.record()
+        e2e_sync()
         sync_all()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
 

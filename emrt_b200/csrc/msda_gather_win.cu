@@ -31,9 +31,9 @@ int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const vo
                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
 constexpr int WIN_L = 3, WIN_P = 6, WIN_LP = WIN_L * WIN_P, WIN_D = 32;
-constexpr int WIN_WARPS = 8;
 constexpr int WIN_QPB = 4;                   // queries per warp batch (one LDS.128 serves 4 queries x 128 bytes)
-constexpr uint32_t WIN_SLOW = 0x80000000u;   // record flag: take the global-memory path for this point
+constexpr uint32_t WIN_SLOW = 0x80000000u;   // record flag (sign bit of the bottom weight, weights are >= 0):
+                                             // take the global-memory path for this point
 
 struct WinParams {
   CUtensorMap tmap[WIN_L];       // level l: {32 ch, W_l, H_l, B*M} bf16, box {32, WW_l, WH_l, 1}, zero OOB fill
@@ -161,7 +161,7 @@ __device__ __forceinline__ void raw_decode(const RawLoc<__nv_bfloat16>& r, float
 constexpr int WIN_ROUNDS = (WIN_QPB * WIN_LP + 31) / 32;   // stage-A rounds: one (query, point) per lane per round
 constexpr int WIN_MAX_Q = 512;                             // queries per region (TH*TW*(1 + 1/4 + 1/16)), upper bound
 
-template <typename TL, int MODE, bool REC64>
+template <typename TL, int MODE, int WIN_WARPS>
 __global__ void __launch_bounds__(WIN_WARPS * 32, 2)
 msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __restrict__ loc,
                            const TL* __restrict__ attn, const float* __restrict__ ref, int64_t ref_bs,
@@ -286,12 +286,12 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
         const float gx = 1.f - fx, gy = 1.f - fy;
         const bool fast = live && inwin;
         // not live: weight 0 on the zero block.  live but outside the window: same, plus the SLOW flag
-        const uint32_t addr = fast ? a_base[r] + (uint32_t)(wy * a_ww[r] + wx) * (WIN_D * 2)
-                                   : (smem_base | (live ? WIN_SLOW : 0u));
-        const uint32_t wl = fast ? pack_bf16(gx * gy * aw, gx * fy * aw) : 0u;   // left pixel: top, bottom
-        const uint32_t wr = fast ? pack_bf16(fx * gy * aw, fx * fy * aw) : 0u;   // right pixel: top, bottom
-        if (REC64) sts128(rec_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 16, addr, wl, addr, wr);
-        else sts128(rec_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 16, addr, wl, wr, 0u);
+        // not live: weight 0 on the zero block.  live but outside the window: same, with the SLOW flag (= weights -0.0)
+        const uint32_t addr = fast ? a_base[r] + (uint32_t)(wy * a_ww[r] + wx) * (WIN_D * 2) : smem_base;
+        const uint32_t wnone = live ? WIN_SLOW : 0u;
+        const uint32_t wl = fast ? pack_bf16(gx * gy * aw, gx * fy * aw) : wnone;   // left pixel: top, bottom
+        const uint32_t wr = fast ? pack_bf16(fx * gy * aw, fx * fy * aw) : wnone;   // right pixel: top, bottom
+        sts128(rec_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 16, addr, wl, addr, wr);
       }
     }
     // next batch: claim it and start its loads now, they land while this batch gathers
@@ -311,47 +311,44 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     const uint32_t my_rec = rec_base + (uint32_t)g * (WIN_LP * 16);
-#pragma unroll 1
+#pragma unroll
     for (int l = 0; l < WIN_L; ++l) {
       const uint32_t row_bytes = (uint32_t)p.WW[l] * (WIN_D * 2);
-      // the level's six records first: {address, this side's weight pair}
+      // the level's six records first: {address, this side's weight pair}, 8 bytes per lane
       uint32_t addr[WIN_P], wpair[WIN_P];
       uint32_t flags = 0u;
 #pragma unroll
       for (int pp = 0; pp < WIN_P; ++pp) {
-        const uint32_t ra = my_rec + (l * WIN_P + pp) * 16;
-        if (REC64) {      // {addr, w_side}: 8 bytes per lane
-          asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(addr[pp]), "=r"(wpair[pp]) : "r"(ra + side * 8));
-        } else {
-          const uint4 rec = lds128(ra);
-          addr[pp] = rec.x;
-          wpair[pp] = side ? rec.z : rec.y;
+        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(addr[pp]), "=r"(wpair[pp])
+                     : "r"(my_rec + (l * WIN_P + pp) * 16 + side * 8));
+        flags |= wpair[pp];
+      }
+      // branch-free fast path in two halves of three points: six independent LDS.128 in flight, then 48 FHFMA
+      // (flagged records carry weight -0.0 on the zero block)
+#pragma unroll
+      for (int h = 0; h < WIN_P; h += 3) {
+        uint4 d0[3], d1[3];
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp) {
+          const uint32_t a = addr[h + pp] + s * 16;
+          d0[pp] = lds128(a);
+          d1[pp] = lds128(a + row_bytes);
         }
-        flags |= addr[pp];
-      }
-      // branch-free fast path: twelve independent LDS.128 in flight, then 96 FHFMA (flagged records carry weight 0)
-      uint4 d0[WIN_P], d1[WIN_P];
 #pragma unroll
-      for (int pp = 0; pp < WIN_P; ++pp) {
-        const uint32_t a = (addr[pp] & ~WIN_SLOW) + s * 16;
-        d0[pp] = lds128(a);
-        d1[pp] = lds128(a + row_bytes);
-      }
-#pragma unroll
-      for (int pp = 0; pp < WIN_P; ++pp) {
-        fma_row<0>(acc, d0[pp], wpair[pp]);
-        fma_row<1>(acc, d1[pp], wpair[pp]);
+        for (int pp = 0; pp < 3; ++pp) {
+          fma_row<0>(acc, d0[pp], wpair[h + pp]);
+          fma_row<1>(acc, d1[pp], wpair[h + pp]);
+        }
       }
       if (__any_sync(0xffffffffu, (flags & WIN_SLOW) != 0u)) {
         // fix-ups: points that left the staged window but not the map read global memory
 #pragma unroll 1
         for (int pp = 0; pp < WIN_P; ++pp) {
-          uint32_t a = addr[0];
+          uint32_t w = wpair[0];
 #pragma unroll
-          for (int k = 1; k < WIN_P; ++k) { if (pp == k) a = addr[k]; }
-          if (a & WIN_SLOW) {
+          for (int k = 1; k < WIN_P; ++k) { if (pp == k) w = wpair[k]; }
+          if (w & WIN_SLOW) {
             uint4 e0, e1;
-            uint32_t w;
             slow_point<TL, MODE>(p, value, loc, attn, ref, ref_bs, b, q, m, l * WIN_P + pp, s, &e0, &e1, &w);
             fma_row<0>(acc, e0, w);
             fma_row<1>(acc, e1, w);
@@ -383,10 +380,10 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <typename TL, int MODE, bool REC64>
+template <typename TL, int MODE, int NW>
 static int launch_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
                       int B, const WinParams& p, size_t smem_bytes, cudaStream_t st) {
-  auto kern = msda_gather_fwd_win_kernel<TL, MODE, REC64>;
+  auto kern = msda_gather_fwd_win_kernel<TL, MODE, NW>;
   static size_t attr = 0;
   if (smem_bytes > attr) {
     EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -394,7 +391,7 @@ static int launch_win(const void* value, const void* loc, const void* attn, cons
   }
   const int64_t grid = (int64_t)B * p.regions_x * p.regions_y * p.M;
   if (grid > 0x7fffffffLL) return EMRT_ERR_UNSUPPORTED;
-  kern<<<(unsigned)grid, WIN_WARPS * 32, smem_bytes, st>>>((const __nv_bfloat16*)value, (const TL*)loc, (const TL*)attn,
+  kern<<<(unsigned)grid, NW * 32, smem_bytes, st>>>((const __nv_bfloat16*)value, (const TL*)loc, (const TL*)attn,
                                                            ref, ref_bs, (__nv_bfloat16*)out, p);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
@@ -436,16 +433,16 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
       return e;
   }
   p.rec_off = off;
-  const size_t smem_bytes = (size_t)off + (size_t)WIN_WARPS * WIN_QPB * WIN_LP * 16;
+  const int warps = env_int("EMRT_WIN_WARPS", 8) == 12 ? 12 : 8;
+  const size_t smem_bytes = (size_t)off + (size_t)warps * WIN_QPB * WIN_LP * 16;
   if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(value) & 15) != 0) return EMRT_ERR_UNSUPPORTED;
   const bool px = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;
-  const bool rec64 = env_int("EMRT_WIN_REC64", 1) != 0;
-#define EMRT_WIN(TL)                                                                                          \
-  if (rec64) return px ? launch_win<TL, 1, true>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)    \
-                       : launch_win<TL, 0, true>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);   \
-  return px ? launch_win<TL, 1, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)              \
-            : launch_win<TL, 0, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)
+#define EMRT_WIN(TL)                                                                                             \
+  if (warps == 12) return px ? launch_win<TL, 1, 12>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)     \
+                             : launch_win<TL, 0, 12>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);    \
+  return px ? launch_win<TL, 1, 8>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)                       \
+            : launch_win<TL, 0, 8>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)
   switch (loc_dtype) {
     case EMRT_F32: EMRT_WIN(float);
     case EMRT_F16: EMRT_WIN(__half);
