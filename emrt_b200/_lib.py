@@ -50,6 +50,9 @@ SIGNATURES = {
                                        _I, _I, _I, _P]),
     "emrt_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _P]),
     "emrt_pack_weight": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
+    "emrt_linear_bwd_weight": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "emrt_msda_qproj_bwd": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I32P, _I, _I, _I, _P]),
+    "emrt_scale_rows_cast": (C.c_int, [_P, _P, _P, _L, _I, _I, _P]),
     "emrt_msda_softmax_loc": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I32P, _I, _I, _P]),
     "emrt_add_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, C.c_float, _I, _P]),
     "emrt_add_bcast": (C.c_int, [_P, _P, _P, _L, _L, _I, _P]),

@@ -1,0 +1,181 @@
+// Backward-pass kernels of the MSDA module (what Paddle autograd derives for transformer_encoder_decoder.py:83-106):
+//   * weight / bias gradients of nn.Linear:   dW[K,N] += x[rows,K]^T dy[rows,N],  db[N] += sum_rows dy
+//   * softmax(L*P) + sampling-location backward:  (grad_loc, grad_attn, attn) -> d[offsets | logits]
+//   * dV row-mask + cast
+// The data gradient of nn.Linear (dx = dy W^T) needs no kernel of its own: Paddle's [in,out] weight layout is exactly
+// the pre-packed [N',K'] operand of emrt_linear_fwd for that product.
+// dW here is an fp32-accumulate SIMT tile kernel with split-row partial sums (atomics into the fp32 gradient); it is
+// the parity implementation — the tcgen05 version (MN-major operands) is the next step.
+#include "common.cuh"
+
+namespace emrt {
+
+constexpr int WG_T = 64;      // output tile: 64 (k) x 64 (n)
+constexpr int WG_R = 16;      // rows per smem step
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p) { return to_float(__ldg(p)); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float(((unsigned int)__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+linear_bwd_weight_kernel(const TX* __restrict__ x, const TY* __restrict__ dy, float* __restrict__ dw,
+                         float* __restrict__ db, int64_t rows, int K, int N, int rows_per_cta) {
+  __shared__ float xs[WG_R][WG_T + 1];
+  __shared__ float ys[WG_R][WG_T + 1];
+  const int k0 = blockIdx.x * WG_T, n0 = blockIdx.y * WG_T;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_cta;
+  const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
+  const int t = threadIdx.x;
+  const int tk = (t / 16) * 4, tn = (t % 16) * 4;      // 4 x 4 outputs per thread
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;                                      // column sum of dy (threads 0..63 of the k-tile-0 CTAs)
+  const int lr = t / 16, lc = (t % 16) * 4;             // loader: row lr, 4 consecutive columns
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += WG_R) {
+    const int64_t r = r0 + lr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + lc + i, n = n0 + lc + i;
+      xs[lr][lc + i] = (r < r_end && k < K) ? ldf<TX>(x + r * K + k) : 0.f;
+      ys[lr][lc + i] = (r < r_end && n < N) ? ldf<TY>(dy + r * N + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < WG_R; ++rr) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = xs[rr][tk + i]; b[i] = ys[rr][tn + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (db != nullptr && blockIdx.x == 0 && t < WG_T) {
+#pragma unroll
+      for (int rr = 0; rr < WG_R; ++rr) bsum += ys[rr][t];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk + i, n = n0 + tn + j;
+      if (k < K && n < N) atomicAdd(dw + (int64_t)k * N + n, acc[i][j]);
+    }
+  if (db != nullptr && blockIdx.x == 0 && t < WG_T && n0 + t < N) atomicAdd(db + n0 + t, bsum);
+}
+
+// One thread per (row, head): d_logit_i = a_i (g_i - sum_j a_j g_j) over the head's L*P weights (softmax backward,
+// t_e_d.py:95), d_offset = grad_loc (pixel-offset mode) or grad_loc / (W_l, H_l) (normalised mode, t_e_d.py:98-102).
+// dq [rows, 3*M*L*P] = [offset grads (2*M*L*P) | logit grads (M*L*P)], the layout of the fused query projection.
+template <typename TA, typename TO, int MODE>
+__global__ void __launch_bounds__(256)
+msda_qproj_bwd_kernel(const float* __restrict__ grad_loc, const float* __restrict__ grad_attn,
+                      const TA* __restrict__ attn, TO* __restrict__ dq, int M, int L, int P,
+                      const __grid_constant__ LevelTable lv, int64_t n_items) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  const int m = (int)(item % M);
+  const int64_t row = item / M;
+  const int LP = L * P, tp = M * LP;
+  const float* ga = grad_attn + item * LP;
+  const TA* a = attn + item * LP;
+  float dot = 0.f;
+  for (int i = 0; i < LP; ++i) dot = fmaf(to_float(a[i]), __ldg(ga + i), dot);
+  TO* out = dq + row * (3 * tp);
+  for (int i = 0; i < LP; ++i)
+    out[2 * tp + m * LP + i] = from_float<TO>(to_float(a[i]) * (__ldg(ga + i) - dot));
+  const float* gl = grad_loc + item * LP * 2;
+  for (int l = 0; l < L; ++l) {
+    const float sx = MODE == EMRT_LOC_NORMALIZED ? 1.f / (float)lv.W[l] : 1.f;
+    const float sy = MODE == EMRT_LOC_NORMALIZED ? 1.f / (float)lv.H[l] : 1.f;
+    for (int p = 0; p < P; ++p) {
+      const int i = (l * P + p) * 2;
+      out[m * LP * 2 + i] = from_float<TO>(__ldg(gl + i) * sx);
+      out[m * LP * 2 + i + 1] = from_float<TO>(__ldg(gl + i + 1) * sy);
+    }
+  }
+}
+
+// dst[r, c] = src[r, c] * row_scale[r] (row_scale may be NULL), fp32 -> TO; 4 elements per thread
+template <typename TO>
+__global__ void __launch_bounds__(256)
+scale_rows_cast_kernel(const float* __restrict__ src, const float* __restrict__ row_scale, TO* __restrict__ dst,
+                       int64_t rows, int cols) {
+  const int64_t n4 = rows * cols / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    const float s = row_scale ? __ldg(row_scale + (i * 4) / cols) : 1.f;
+    dst[i * 4 + 0] = from_float<TO>(v.x * s);
+    dst[i * 4 + 1] = from_float<TO>(v.y * s);
+    dst[i * 4 + 2] = from_float<TO>(v.z * s);
+    dst[i * 4 + 3] = from_float<TO>(v.w * s);
+  }
+}
+
+}  // namespace emrt
+
+using namespace emrt;
+
+extern "C" int emrt_linear_bwd_weight(const void* x, const void* dy, float* dw, float* db, int64_t rows, int K, int N,
+                                      int x_dtype, int dy_dtype, void* stream) {
+  EMRT_REQUIRE(x && dy && dw, "NULL tensor pointer");
+  EMRT_REQUIRE(rows > 0 && K > 0 && N > 0, "non-positive dimension");
+  int rows_per_cta = 1024;
+  int64_t chunks = (rows + rows_per_cta - 1) / rows_per_cta;
+  if (chunks > 65535) { rows_per_cta = (int)((rows + 65534) / 65535); rows_per_cta = (rows_per_cta + WG_R - 1) / WG_R * WG_R; chunks = (rows + rows_per_cta - 1) / rows_per_cta; }
+  dim3 grid((K + WG_T - 1) / WG_T, (N + WG_T - 1) / WG_T, (unsigned)chunks);
+  cudaStream_t st = as_stream(stream);
+#define EMRT_WG(TX, TY) linear_bwd_weight_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX*)x, (const TY*)dy, dw, db, rows, K, N, rows_per_cta)
+  if (x_dtype == EMRT_F32 && dy_dtype == EMRT_F32) EMRT_WG(float, float);
+  else if (x_dtype == EMRT_BF16 && dy_dtype == EMRT_BF16) EMRT_WG(__nv_bfloat16, __nv_bfloat16);
+  else if (x_dtype == EMRT_BF16 && dy_dtype == EMRT_F32) EMRT_WG(__nv_bfloat16, float);
+  else if (x_dtype == EMRT_F32 && dy_dtype == EMRT_BF16) EMRT_WG(float, __nv_bfloat16);
+  else return set_error(EMRT_ERR_UNSUPPORTED, "linear_bwd_weight: unsupported dtypes %d/%d", x_dtype, dy_dtype);
+#undef EMRT_WG
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_msda_qproj_bwd(const float* grad_loc, const float* grad_attn, const void* attn, void* dq,
+                                   int64_t rows, int M, int L, int P, const int32_t* shapes_hw_host, int attn_dtype,
+                                   int dq_dtype, int mode, void* stream) {
+  EMRT_REQUIRE(grad_loc && grad_attn && attn && dq, "NULL tensor pointer");
+  EMRT_REQUIRE(rows > 0 && M > 0 && P > 0, "non-positive dimension");
+  EMRT_REQUIRE(mode == EMRT_LOC_NORMALIZED || mode == EMRT_LOC_PIXEL_OFFSET, "bad loc mode");
+  LevelTable lv;
+  if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, -1)) return e;
+  const int64_t n_items = rows * M;
+  const unsigned blocks = (unsigned)((n_items + 255) / 256);
+  cudaStream_t st = as_stream(stream);
+#define EMRT_QB(TA, TO, MODE) msda_qproj_bwd_kernel<TA, TO, MODE><<<blocks, 256, 0, st>>>(grad_loc, grad_attn, (const TA*)attn, (TO*)dq, M, L, P, lv, n_items)
+  const bool px = mode == EMRT_LOC_PIXEL_OFFSET;
+  if (attn_dtype == EMRT_F32 && dq_dtype == EMRT_F32) { if (px) EMRT_QB(float, float, 1); else EMRT_QB(float, float, 0); }
+  else if (attn_dtype == EMRT_F16 && dq_dtype == EMRT_BF16) { if (px) EMRT_QB(__half, __nv_bfloat16, 1); else EMRT_QB(__half, __nv_bfloat16, 0); }
+  else if (attn_dtype == EMRT_BF16 && dq_dtype == EMRT_BF16) { if (px) EMRT_QB(__nv_bfloat16, __nv_bfloat16, 1); else EMRT_QB(__nv_bfloat16, __nv_bfloat16, 0); }
+  else if (attn_dtype == EMRT_F16 && dq_dtype == EMRT_F32) { if (px) EMRT_QB(__half, float, 1); else EMRT_QB(__half, float, 0); }
+  else return set_error(EMRT_ERR_UNSUPPORTED, "qproj_bwd: unsupported dtypes attn %d / dq %d", attn_dtype, dq_dtype);
+#undef EMRT_QB
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_scale_rows_cast(const float* src, const float* row_scale, void* dst, int64_t rows, int cols,
+                                    int dst_dtype, void* stream) {
+  EMRT_REQUIRE(src && dst && rows > 0 && cols > 0 && cols % 4 == 0, "bad scale_rows_cast arguments");
+  const int64_t n4 = rows * cols / 4;
+  const int64_t want = (n4 + 255) / 256;
+  const unsigned blocks = (unsigned)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  cudaStream_t st = as_stream(stream);
+  if (dst_dtype == EMRT_F32) scale_rows_cast_kernel<float><<<blocks, 256, 0, st>>>(src, row_scale, (float*)dst, rows, cols);
+  else if (dst_dtype == EMRT_BF16) scale_rows_cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, row_scale, (__nv_bfloat16*)dst, rows, cols);
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dst_dtype %d", dst_dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}

@@ -56,6 +56,85 @@ class PaddleLinear(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_features))
 
 
+class _MSDAFunction(torch.autograd.Function):
+    """fwd + bwd of MSDeformableAttention.forward (t_e_d.py:65-107) through the C ABI.  The training path keeps the
+    projected value pixel-major ([B,Lv,M,D], the layout emrt_msda_gather_bwd scatters into) and saves the module's
+    intermediates (projected value, offsets, softmax weights, gathered tokens) instead of recomputing them."""
+
+    @staticmethod
+    def forward(ctx, mod, query, ref, value, mask, shapes, w_off, b_off, w_attn, b_attn, w_val, b_val, w_out, b_out):
+        M, P, D, nL = mod.num_heads, mod.num_points, mod.head_dim, mod.num_levels
+        bs, Len_q = query.shape[:2]
+        query, value = query.contiguous(), value.contiguous()
+        fast = query.dtype == torch.bfloat16
+        if fast:
+            pk = mod.packed_weights()
+            impl = mod.gemm_impl
+            v = ops.linear(value, pk["wv"], pk["bv"], w_transposed=True, impl=impl,
+                           epilogue=L.EPI_ROW_MASK if mask is not None else L.EPI_NONE, row_scale=mask)
+            if impl == L.IMPL_SIMT:
+                raw = ops.linear(query, pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float32, impl=impl)
+                tp2 = 2 * mod.total_points
+                loc, attn = ops.msda_softmax_loc(raw[..., :tp2], raw[..., tp2:], shapes, M, P, out_dtype=torch.float16,
+                                                 mode=L.LOC_PIXEL_OFFSET)
+            else:
+                loc, attn = ops.linear(query, pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float16,
+                                       epilogue=L.EPI_MSDA_QPROJ, qproj_group=nL * P, impl=impl)
+                loc = loc.view(bs, Len_q, M, nL, P, 2)
+                attn = attn.view(bs, Len_q, M, nL, P)
+            mode = L.LOC_PIXEL_OFFSET
+            g = ops.msda_gather_fwd(v.view(bs, -1, M, D), loc, attn, shapes, ref=ref, mode=mode)
+            out = ops.linear(g, pk["wo"], pk["bo"], w_transposed=True, impl=impl)
+        else:
+            v = ops.linear(value, w_val.detach(), b_val.detach(), impl=L.IMPL_SIMT,
+                           epilogue=L.EPI_ROW_MASK if mask is not None else L.EPI_NONE, row_scale=mask)
+            off = ops.linear(query, w_off.detach(), b_off.detach(), impl=L.IMPL_SIMT)
+            logit = ops.linear(query, w_attn.detach(), b_attn.detach(), impl=L.IMPL_SIMT)
+            mode = L.LOC_NORMALIZED
+            loc, attn = ops.msda_softmax_loc(off, logit, shapes, M, P, ref=ref, out_dtype=torch.float32, mode=mode)
+            g = ops.msda_gather_fwd(v.view(bs, -1, M, D), loc, attn, shapes, mode=mode)
+            out = ops.linear(g, w_out.detach(), b_out.detach(), impl=L.IMPL_SIMT)
+        ctx.mod, ctx.shapes, ctx.mode, ctx.fast = mod, shapes, mode, fast
+        ctx.save_for_backward(query, value, ref, mask, v, loc, attn, g, w_off, w_attn, w_val, w_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        mod, shapes, mode, fast = ctx.mod, ctx.shapes, ctx.mode, ctx.fast
+        query, value, ref, mask, v, loc, attn, g, w_off, w_attn, w_val, w_out = ctx.saved_tensors
+        M, P, D, nL = mod.num_heads, mod.num_points, mod.head_dim, mod.num_levels
+        C_, tp = mod.embed_dim, mod.total_points
+        bs, Len_q = query.shape[:2]
+        dev = query.device
+        d_out = d_out.contiguous()
+        cdt = torch.bfloat16 if fast else torch.float32
+        impl = mod.gemm_impl if fast else L.IMPL_SIMT
+        # Paddle's [in,out] layout IS the packed operand of the data-gradient GEMM (dx = dy W^T)
+        wo_kn, wv_kn = w_out.detach().to(cdt).contiguous(), w_val.detach().to(cdt).contiguous()
+        wq_kn = torch.cat([w_off.detach(), w_attn.detach()], 1).to(cdt).contiguous()           # [C, 3*tp]
+        f32 = dict(dtype=torch.float32, device=dev)
+        # output_proj
+        d_g = ops.linear(d_out, wo_kn, None, w_transposed=True, impl=impl)
+        dw_out, db_out = torch.zeros((C_, C_), **f32), torch.zeros((C_,), **f32)
+        ops.linear_bwd_weight(g, d_out, dw_out, db_out)
+        # gather
+        ref_arg = ref if mode == L.LOC_PIXEL_OFFSET else None
+        gv, gl, ga = ops.msda_gather_bwd(d_g, v.view(bs, -1, M, D), loc, attn, shapes, ref=ref_arg, mode=mode)
+        # softmax + offsets -> fused query projection
+        dq = ops.msda_qproj_bwd(gl, ga, attn, shapes, M, P, out_dtype=cdt, mode=mode)
+        d_query = ops.linear(dq, wq_kn, None, w_transposed=True, impl=impl)
+        dw_q, db_q = torch.zeros((C_, 3 * tp), **f32), torch.zeros((3 * tp,), **f32)
+        ops.linear_bwd_weight(query, dq, dw_q, db_q)
+        # value_proj (mask backward folded into the cast of the fp32 scatter buffer)
+        d_v = ops.scale_rows_cast(gv.view(bs, -1, C_), mask, cdt)
+        d_value = ops.linear(d_v, wv_kn, None, w_transposed=True, impl=impl)
+        dw_val, db_val = torch.zeros((C_, C_), **f32), torch.zeros((C_,), **f32)
+        ops.linear_bwd_weight(value, d_v, dw_val, db_val)
+        return (None, d_query, None, d_value, None, None,
+                dw_q[:, :2 * tp].contiguous(), db_q[:2 * tp].contiguous(), dw_q[:, 2 * tp:].contiguous(),
+                db_q[2 * tp:].contiguous(), dw_val, db_val, dw_out, db_out)
+
+
 class MSDeformableAttention(nn.Module):
     """Multi-Scale Deformable Attention Module (transformer_encoder_decoder.py:21-107) on sm_100a kernels.
 
@@ -143,6 +222,17 @@ class MSDeformableAttention(nn.Module):
         assert len(shapes) == self.num_levels
         if not query.is_cuda:
             raise L.EmrtError("emrt_b200.MSDeformableAttention needs CUDA tensors (no CPU fallback)")
+        if query.dtype not in (torch.float32, torch.bfloat16):
+            raise L.EmrtError(f"unsupported dtype {query.dtype}")
+        if torch.is_grad_enabled() and (query.requires_grad or value.requires_grad
+                                        or any(p.requires_grad for p in self.parameters())):
+            mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
+            ref32 = reference_points.detach().float().contiguous()
+            return _MSDAFunction.apply(self, query, ref32, value, mask, shapes,
+                                       self.sampling_offsets.weight, self.sampling_offsets.bias,
+                                       self.attention_weights.weight, self.attention_weights.bias,
+                                       self.value_proj.weight, self.value_proj.bias,
+                                       self.output_proj.weight, self.output_proj.bias)
         if query.dtype == torch.float32:
             return self._forward_fp32(query, reference_points, value, shapes, value_mask)
         if query.dtype == torch.bfloat16:

@@ -161,6 +161,37 @@ def msda_softmax_loc(off_raw, logit_raw, shapes, M, P, ref=None, out_dtype=torch
     return loc, attn
 
 
+# ---- backward pieces ---------------------------------------------------------------------------------------------
+def linear_bwd_weight(x, dy, dw, db=None):
+    """dw [K,N] f32 += x[rows,K]^T dy[rows,N]; db [N] f32 += column sums of dy.  Accumulates into dw / db."""
+    K, N = dw.shape
+    rows = x.numel() // K
+    assert dy.numel() == rows * N and dw.dtype == torch.float32
+    L.check(L.load().emrt_linear_bwd_weight(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), rows, K, N, _dt(x), _dt(dy), _stream()))
+    return dw, db
+
+
+def msda_qproj_bwd(grad_loc, grad_attn, attn, shapes, M, P, out_dtype=torch.float32, mode=L.LOC_NORMALIZED):
+    """-> dq [..., 3*M*L*P] = [offset grads | logit grads] (softmax + location backward)."""
+    nL = len(shapes)
+    lead = attn.shape[:-3]
+    rows = attn.numel() // (M * nL * P)
+    hw, _, _ = level_tables(shapes)
+    dq = torch.empty((*lead, 3 * M * nL * P), dtype=out_dtype, device=attn.device)
+    L.check(L.load().emrt_msda_qproj_bwd(_ptr(grad_loc), _ptr(grad_attn), _ptr(attn), _ptr(dq), rows, M, nL, P, hw,
+                                         _dt(attn), _DT[out_dtype], mode, _stream()))
+    return dq
+
+
+def scale_rows_cast(src, row_scale, out_dtype):
+    """dst[r, :] = src[r, :] * row_scale[r] (row_scale may be None), fp32 -> out_dtype."""
+    cols = src.shape[-1]
+    rows = src.numel() // cols
+    dst = torch.empty(src.shape, dtype=out_dtype, device=src.device)
+    L.check(L.load().emrt_scale_rows_cast(_ptr(src), _ptr(row_scale), _ptr(dst), rows, cols, _DT[out_dtype], _stream()))
+    return dst
+
+
 def add_layernorm(x, residual, gamma, beta, eps=1e-5, out=None):
     N = x.shape[-1]
     rows = x.numel() // N

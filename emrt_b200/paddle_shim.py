@@ -1,0 +1,319 @@
+"""PaddlePaddle binding of libemrt_b200.so — the shim a maintainer adds to peach-xiao/EMRT.
+
+NOT EXECUTABLE IN THIS IMAGE: PaddlePaddle cannot be installed here (no wheel for Python 3.12, no network), so this
+file is written against the Paddle >= 2.5 API (``Tensor.data_ptr()``, ``paddle.device.cuda.current_stream()``,
+``paddle.autograd.PyLayer``) and is exercised only by an import-guard test.  It is deliberately thin: every
+function forwards Paddle tensors' device pointers to the same C entry points (include/emrt_b200.h) that the torch
+adapter in ``emrt_b200/ops.py`` drives and that the GPU parity tests cover; no arithmetic happens in Python.
+
+Mirrors, with the reference's names / signatures / state-dict keys:
+  MSDeformableAttention            src/models/EMRT_utils/transformer_encoder_decoder.py:21-107
+  deformable_attention_core_func   src/models/EMRT_utils/utils.py:64-97
+  slide_inference, ss_inference    src/api/infer.py:22-157
+``patch_reference()`` installs them into the reference's modules so train.py / val.py / predict.py run unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+try:
+    import paddle
+    import paddle.nn as nn
+    import paddle.nn.functional as F
+    from paddle.autograd import PyLayer
+except ImportError as e:  # pragma: no cover - Paddle is absent in the build image
+    raise ImportError("emrt_b200.paddle_shim needs PaddlePaddle >= 2.5 (GPU build); use the torch adapter "
+                      "`emrt_b200` where Paddle is not installed") from e
+
+from . import _lib as L
+from .infer import plan_windows
+
+_DT = {paddle.float32: L.F32, paddle.bfloat16: L.BF16, paddle.float16: L.F16, paddle.int32: L.I32, paddle.uint8: L.U8}
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.place.is_gpu_place():
+        raise L.EmrtError("emrt_b200 ops need GPU tensors (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(paddle.device.cuda.current_stream().cuda_stream)
+
+
+def _shapes(value_spatial_shapes):
+    """[L,2] (H,W) as host ints, read once (the reference syncs on it >= 3 times per call)."""
+    if isinstance(value_spatial_shapes, paddle.Tensor):
+        value_spatial_shapes = value_spatial_shapes.numpy().tolist()
+    return tuple((int(h), int(w)) for h, w in value_spatial_shapes)
+
+
+def _tables(shapes):
+    hw, start, acc = [], [], 0
+    for h, w in shapes:
+        hw += [h, w]
+        start.append(acc)
+        acc += h * w
+    return L.i32_array(hw), L.i32_array(start), acc
+
+
+def _linear(x, w, bias, *, w_transposed, y_dtype=None, epilogue=L.EPI_NONE, row_scale=None, qproj_group=0,
+            hm_rows=0, hm_D=0):
+    K = x.shape[-1]
+    rows = int(math.prod(x.shape[:-1]))
+    N = w.shape[0] if w_transposed else w.shape[1]
+    ydt = y_dtype or x.dtype
+    lead = list(x.shape[:-1])
+    out2 = None
+    if epilogue & L.EPI_MSDA_QPROJ:
+        out = paddle.empty(lead + [2 * N // 3], dtype=ydt)
+        out2 = paddle.empty(lead + [N // 3], dtype=ydt)
+    else:
+        out = paddle.empty(lead + [N], dtype=ydt)
+    a = L.LinearArgs()
+    a.x, a.w, a.bias, a.y = _ptr(x), _ptr(w), _ptr(bias), _ptr(out)
+    a.rows, a.K, a.N = rows, K, N
+    a.x_dtype, a.w_dtype, a.y_dtype, a.w_transposed = _DT[x.dtype], _DT[w.dtype], _DT[ydt], int(w_transposed)
+    a.epilogue, a.row_scale, a.y2, a.qproj_group = int(epilogue), _ptr(row_scale), _ptr(out2), int(qproj_group)
+    a.impl, a.hm_rows, a.hm_D = L.IMPL_AUTO, int(hm_rows), int(hm_D)
+    L.check(L.load().emrt_linear_fwd(C.byref(a), _stream()))
+    return (out, out2) if out2 is not None else out
+
+
+def _gather_fwd(value, loc, attn, shapes, ref, mode):
+    if mode & L.VALUE_HEAD_MAJOR:
+        B, M, Lv, D = value.shape
+    else:
+        B, Lv, M, D = value.shape
+    Lq, nL, P = loc.shape[1], loc.shape[3], loc.shape[4]
+    hw, start, _ = _tables(shapes)
+    out = paddle.empty([B, Lq, M * D], dtype=value.dtype)
+    rbs = 0 if ref is None or ref.shape[0] == 1 else Lq * nL * 2
+    L.check(L.load().emrt_msda_gather_fwd(_ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(out), B, Lq, Lv, M,
+                                          D, nL, P, hw, start, _DT[value.dtype], _DT[loc.dtype], mode, _stream()))
+    return out
+
+
+def _gather_bwd(grad_out, value, loc, attn, shapes, ref, mode):
+    B, Lv, M, D = value.shape
+    Lq, nL, P = loc.shape[1], loc.shape[3], loc.shape[4]
+    hw, start, _ = _tables(shapes)
+    gv = paddle.zeros([B, Lv, M, D], dtype=paddle.float32)
+    gl = paddle.empty(loc.shape, dtype=paddle.float32)
+    ga = paddle.empty(attn.shape, dtype=paddle.float32)
+    rbs = 0 if ref is None or ref.shape[0] == 1 else Lq * nL * 2
+    L.check(L.load().emrt_msda_gather_bwd(_ptr(grad_out), _ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(gv),
+                                          _ptr(gl), _ptr(ga), B, Lq, Lv, M, D, nL, P, hw, start, _DT[value.dtype],
+                                          _DT[loc.dtype], mode, _stream()))
+    return gv, gl, ga
+
+
+class _CoreFunc(PyLayer):
+    """deformable_attention_core_func with its backward (utils.py:64-97 and Paddle autograd through grid_sample)."""
+
+    @staticmethod
+    def forward(ctx, value, loc, attn, shapes):
+        ctx.shapes = shapes
+        ctx.save_for_backward(value, loc, attn)
+        return _gather_fwd(value, loc, attn, shapes, None, L.LOC_NORMALIZED)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        value, loc, attn = ctx.saved_tensor()
+        gv, gl, ga = _gather_bwd(grad_out.contiguous(), value, loc, attn, ctx.shapes, None, L.LOC_NORMALIZED)
+        return gv.astype(value.dtype), gl.astype(loc.dtype), ga.astype(attn.dtype)
+
+
+def deformable_attention_core_func(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """Drop-in for src/models/EMRT_utils/utils.py:64-97."""
+    shapes = _shapes(value_spatial_shapes)
+    loc, attn = sampling_locations, attention_weights
+    if value.dtype == paddle.float32 and loc.dtype != paddle.float32:
+        loc, attn = loc.astype("float32"), attn.astype("float32")
+    return _CoreFunc.apply(value.contiguous(), loc.contiguous(), attn.contiguous(), shapes)
+
+
+class MSDeformableAttention(nn.Layer):
+    """Multi-Scale Deformable Attention Module (transformer_encoder_decoder.py:21-107) on sm_100a kernels.
+    Same constructor, sub-layer names (state-dict keys) and forward signature as the reference class.  Inference runs
+    the fused B200 path; with gradients enabled the forward falls back to the reference's own op composition around
+    the custom gather (so Paddle autograd supplies the Linear / softmax backward) — the fully native backward is the
+    torch adapter's `_MSDAFunction`, to be mirrored here once it can be tested under Paddle."""
+
+    def __init__(self, embed_dim=256, num_heads=8, num_levels=4, num_points=4, lr_mult=0.1):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.num_levels, self.num_points = embed_dim, num_heads, num_levels, num_points
+        self.total_points = num_heads * num_levels * num_points
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == self.embed_dim, "embed_dim must be divisible by num_heads"
+        self.sampling_offsets = nn.Linear(embed_dim, self.total_points * 2,
+                                          weight_attr=paddle.ParamAttr(learning_rate=lr_mult),
+                                          bias_attr=paddle.ParamAttr(learning_rate=lr_mult))
+        self.attention_weights = nn.Linear(embed_dim, self.total_points)
+        self.value_proj = nn.Linear(embed_dim, embed_dim)
+        self.output_proj = nn.Linear(embed_dim, embed_dim)
+        self._packed = None
+        self._reset_parameters()
+
+    def _reset_parameters(self):   # transformer_encoder_decoder.py:46-63
+        self.sampling_offsets.weight.set_value(paddle.zeros_like(self.sampling_offsets.weight))
+        thetas = paddle.arange(self.num_heads, dtype=paddle.float32) * (2.0 * math.pi / self.num_heads)
+        grid_init = paddle.stack([thetas.cos(), thetas.sin()], -1)
+        grid_init = grid_init / grid_init.abs().max(-1, keepdim=True)
+        grid_init = grid_init.reshape([self.num_heads, 1, 1, 2]).tile([1, self.num_levels, self.num_points, 1])
+        grid_init = grid_init * paddle.arange(1, self.num_points + 1, dtype=paddle.float32).reshape([1, 1, -1, 1])
+        self.sampling_offsets.bias.set_value(grid_init.flatten())
+        self.attention_weights.weight.set_value(paddle.zeros_like(self.attention_weights.weight))
+        self.attention_weights.bias.set_value(paddle.zeros_like(self.attention_weights.bias))
+        for lin in (self.value_proj, self.output_proj):
+            bound = math.sqrt(6.0 / (self.embed_dim + self.embed_dim))        # xavier_uniform_
+            lin.weight.set_value(paddle.uniform(lin.weight.shape, min=-bound, max=bound))
+            lin.bias.set_value(paddle.zeros_like(lin.bias))
+
+    def _packed_weights(self):
+        """bf16 K-major [out,in] operands (emrt_pack_weight); re-packed when the module is told weights changed
+        (call ``invalidate_packed()`` after loading a checkpoint or an optimiser step)."""
+        if self._packed is not None:
+            return self._packed
+        C_, tp = self.embed_dim, self.total_points
+        lib = L.load()
+
+        def pack(src, dst, row0):
+            K, N = src.shape
+            L.check(lib.emrt_pack_weight(_ptr(src), _DT[src.dtype], _ptr(dst), K, N, row0, _stream()))
+        wv = paddle.empty([C_, C_], dtype=paddle.bfloat16)
+        wq = paddle.empty([3 * tp, C_], dtype=paddle.bfloat16)
+        wo = paddle.empty([C_, C_], dtype=paddle.bfloat16)
+        pack(self.value_proj.weight, wv, 0)
+        pack(self.sampling_offsets.weight, wq, 0)
+        pack(self.attention_weights.weight, wq, 2 * tp)
+        pack(self.output_proj.weight, wo, 0)
+        bq = paddle.concat([self.sampling_offsets.bias, self.attention_weights.bias]).astype("float32")
+        self._packed = dict(wv=wv, wq=wq, wo=wo, bv=self.value_proj.bias.astype("float32"), bq=bq,
+                            bo=self.output_proj.bias.astype("float32"))
+        return self._packed
+
+    def invalidate_packed(self):
+        self._packed = None
+
+    def forward(self, query, reference_points, value, value_spatial_shapes, value_mask=None):
+        bs, Len_q = query.shape[:2]
+        Len_v = value.shape[1]
+        shapes = _shapes(value_spatial_shapes)
+        assert sum(h * w for h, w in shapes) == Len_v                      # transformer_encoder_decoder.py:81
+        M, P, D, nL = self.num_heads, self.num_points, self.head_dim, self.num_levels
+        needs_grad = paddle.is_grad_enabled() and not (query.stop_gradient and value.stop_gradient
+                                                       and all(p.stop_gradient for p in self.parameters()))
+        if needs_grad or query.dtype != paddle.bfloat16:
+            # reference composition (t_e_d.py:83-106) around the native gather
+            v = self.value_proj(value)
+            if value_mask is not None:
+                v = v * value_mask.astype(v.dtype).unsqueeze(-1)
+            v = v.reshape([bs, Len_v, M, D])
+            off = self.sampling_offsets(query).reshape([bs, Len_q, M, nL, P, 2])
+            aw = F.softmax(self.attention_weights(query).reshape([bs, Len_q, M, nL * P]), -1)
+            aw = aw.reshape([bs, Len_q, M, nL, P])
+            normalizer = paddle.to_tensor([[float(w), float(h)] for h, w in shapes], dtype=off.dtype)
+            loc = reference_points.reshape([bs, Len_q, 1, nL, 1, 2]) + off / normalizer.reshape([1, 1, 1, nL, 1, 2])
+            out = deformable_attention_core_func(v, shapes, loc, aw)
+            return self.output_proj(out)
+        # bf16 inference: fused B200 path (same calls as emrt_b200.msda.MSDeformableAttention._forward_bf16)
+        pk = self._packed_weights()
+        mask = None if value_mask is None else value_mask.reshape([-1]).astype("float32")
+        head_major = D == 32 and nL == 3 and P == 6
+        epi = (L.EPI_ROW_MASK if mask is not None else 0) | (L.EPI_HEAD_MAJOR if head_major else 0)
+        v = _linear(value, pk["wv"], pk["bv"], w_transposed=True, epilogue=epi, row_scale=mask,
+                    hm_rows=Len_v if head_major else 0, hm_D=D if head_major else 0)
+        off_px, aw = _linear(query, pk["wq"], pk["bq"], w_transposed=True, y_dtype=paddle.float16,
+                             epilogue=L.EPI_MSDA_QPROJ, qproj_group=nL * P)
+        off_px = off_px.reshape([bs, Len_q, M, nL, P, 2])
+        aw = aw.reshape([bs, Len_q, M, nL, P])
+        ref32 = reference_points.astype("float32")
+        mode = L.LOC_PIXEL_OFFSET | (L.VALUE_HEAD_MAJOR if head_major else 0)
+        if head_major and Len_q == Len_v:
+            mode |= L.QUERY_PIXEL_GRID     # encoder self-attention: reference points are the pixel centres
+        v = v.reshape([bs, M, Len_v, D] if head_major else [bs, Len_v, M, D])
+        out = _gather_fwd(v, off_px, aw, shapes, ref32, mode)
+        return _linear(out, pk["wo"], pk["bo"], w_transposed=True)
+
+
+def _stitch_argmax_fused(half_logits, win_img, win_y0, win_x0, n_img, H, W, label_dtype=paddle.int32):
+    n_win, nc, hh, hw = half_logits.shape
+    labels = paddle.empty([n_img, 1, H, W], dtype=label_dtype)
+    L.check(L.load().emrt_stitch_argmax_fused(_ptr(half_logits), _DT[half_logits.dtype], _ptr(labels), _DT[label_dtype],
+                                              None, n_win, n_img, nc, 2 * hh, 2 * hw, H, W, _ptr(win_img), _ptr(win_y0),
+                                              _ptr(win_x0), _stream()))
+    return labels
+
+
+def slide_inference(model, imgs, crop_size, stride_size, num_classes, window_batch=64):
+    """Drop-in for src/api/infer.py:22-80 (windows batched; accumulate / divide in head.cu)."""
+    img_hw = [(int(i.shape[-2]), int(i.shape[-1])) for i in imgs]
+    plan, max_h, max_w = plan_windows(img_hw, crop_size, stride_size)
+    canvas = paddle.zeros([len(imgs), num_classes, max_h, max_w], dtype=paddle.float32)
+    count = paddle.zeros([len(imgs), 1, max_h, max_w], dtype=paddle.float32)
+    lib = L.load()
+    groups = {}
+    for (i, y0, x0, wh, ww) in plan:
+        groups.setdefault((wh, ww), []).append((i, y0, x0))
+    for (wh, ww), wins in groups.items():
+        for s in range(0, len(wins), window_batch):
+            part = wins[s:s + window_batch]
+            batch = paddle.stack([imgs[i][:, y0:y0 + wh, x0:x0 + ww] for (i, y0, x0) in part], 0)
+            logits = model(batch)[0].astype("float32")
+            idx = paddle.to_tensor([w[0] for w in part], dtype=paddle.int32)
+            ys = paddle.to_tensor([w[1] for w in part], dtype=paddle.int32)
+            xs = paddle.to_tensor([w[2] for w in part], dtype=paddle.int32)
+            L.check(lib.emrt_window_accumulate(_ptr(logits), _ptr(canvas), _ptr(count), len(part), len(imgs),
+                                               num_classes, wh, ww, max_h, max_w, _ptr(idx), _ptr(ys), _ptr(xs), _stream()))
+    out = paddle.empty(canvas.shape, dtype=paddle.float32)
+    labels = paddle.empty([len(imgs), 1, max_h, max_w], dtype=paddle.int32)
+    L.check(lib.emrt_finalize_argmax(_ptr(canvas), _ptr(count), _ptr(labels), L.I32, None, _ptr(out), len(imgs),
+                                     num_classes, max_h, max_w, max_h, max_w, _stream()))
+    return [out[i:i + 1, :, :h, :w] for i, (h, w) in enumerate(img_hw)]
+
+
+def ss_inference(model, img, ori_shape, is_slide, base_size, stride_size, crop_size, num_classes,
+                 rescale_from_ori=False):
+    """Drop-in for src/api/infer.py:82-157 (is_slide=True path as val.py:145 uses it; otherwise the reference code)."""
+    if not is_slide or rescale_from_ori:
+        import src.api.infer as ref_infer                      # keep the reference behaviour for the paths we do not own
+        return ref_infer._emrt_original_ss_inference(model, img, ori_shape, is_slide, base_size, stride_size, crop_size,
+                                                     num_classes, rescale_from_ori)
+    logit_list = slide_inference(model, img, crop_size, stride_size, num_classes)
+    if ori_shape is None:
+        return logit_list
+    lib = L.load()
+    preds = []
+    for i, logit in enumerate(logit_list):
+        Ho, Wo = int(ori_shape[i][0]), int(ori_shape[i][1])
+        lab = paddle.empty([1, 1, Ho, Wo], dtype=paddle.int32)
+        logit = logit.contiguous()
+        L.check(lib.emrt_finalize_argmax(_ptr(logit), None, _ptr(lab), L.I32, None, None, 1, num_classes,
+                                         logit.shape[2], logit.shape[3], Ho, Wo, _stream()))
+        preds.append(lab)
+    return preds
+
+
+def patch_reference():
+    """Install the drop-ins into the reference's modules (run from the reference's semantic_segmentation/ directory)."""
+    import src.api.infer as infer
+    import src.models.EMRT_utils.transformer_encoder_decoder as ted
+    import src.models.EMRT_utils.utils as U
+    L.check(L.load().emrt_device_check())
+    mods = [ted]
+    try:
+        import src.models.EMRT_utils.transformer_encoder_decoder_cswin as ted_cswin
+        mods.append(ted_cswin)
+    except ImportError:
+        pass
+    for mod in mods:
+        mod.MSDeformableAttention = MSDeformableAttention
+        mod.deformable_attention_core_func = deformable_attention_core_func
+    U.deformable_attention_core_func = deformable_attention_core_func
+    infer._emrt_original_ss_inference = infer.ss_inference
+    infer.slide_inference = slide_inference
+    infer.ss_inference = ss_inference

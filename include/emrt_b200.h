@@ -116,6 +116,28 @@ typedef struct emrt_linear_args {
 } emrt_linear_args;
 int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 
+/* ---- backward of nn.Linear (what Paddle autograd derives for transformer_encoder_decoder.py:83,89,92,106) --------
+ * Data gradient dx = dy W^T needs no entry point of its own: call emrt_linear_fwd with x = dy, K = N_fwd,
+ * N = K_fwd, bias = NULL and w = the Paddle-layout weight [in,out] passed as w_transposed = 1.
+ * Weight / bias gradient: dw F32 [K,N] += x[rows,K]^T dy[rows,N]; db F32 [N] += column sums of dy (db may be NULL).
+ * dw / db are ACCUMULATED (caller zeroes them or keeps accumulating over micro-batches).  x, dy: F32 | BF16.       */
+int emrt_linear_bwd_weight(const void* x, const void* dy, float* dw, float* db, int64_t rows, int K, int N,
+                           int x_dtype, int dy_dtype, void* stream);
+
+/* Backward of softmax(L*P) + sampling-location arithmetic (transformer_encoder_decoder.py:92-102):
+ * grad_loc F32 [rows,M,L,P,2] and grad_attn F32 [rows,M,L,P] (from emrt_msda_gather_bwd), attn [rows,M,L,P] (the
+ * saved softmax output; attn_dtype F32|F16|BF16) -> dq [rows, 3*M*L*P] = [offset grads | logit grads] (dq_dtype
+ * F32|BF16), the column layout of the fused [sampling_offsets | attention_weights] projection.  `mode` is the loc
+ * mode the gather ran in (NORMALIZED divides the offset grads by (W_l, H_l)).                                       */
+int emrt_msda_qproj_bwd(const float* grad_loc, const float* grad_attn, const void* attn, void* dq, int64_t rows,
+                        int M, int L, int P, const int32_t* shapes_hw_host, int attn_dtype, int dq_dtype, int mode,
+                        void* stream);
+
+/* dst[r,c] = src[r,c] * row_scale[r] (row_scale may be NULL): value_mask backward + cast of the fp32 grad_value
+ * (transformer_encoder_decoder.py:84-86).  dst_dtype F32|BF16; cols % 4 == 0.                                       */
+int emrt_scale_rows_cast(const float* src, const float* row_scale, void* dst, int64_t rows, int cols, int dst_dtype,
+                         void* stream);
+
 /* Pack Paddle-layout weights: dst[n, k] (BF16, [N_total,K]) = src[k, n] (F32|BF16, [K,N]) for n in
  * [0,N), written at row offset dst_row0 — lets sampling_offsets.weight and attention_weights.weight be
  * concatenated into one [M*L*P*3, K] operand.                                                             */

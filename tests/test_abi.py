@@ -64,3 +64,22 @@ def test_state_dict_keys_match_reference_layout():
     assert set(k.split(".")[0] for k in sd) == {"sampling_offsets", "attention_weights", "value_proj", "output_proj"}
     import oracle as O
     assert abs(sd["sampling_offsets.bias"].numpy() - O.msda_reset_parameters(256, 8, 3, 6)).max() < 1e-6
+
+
+def test_paddle_shim_parses_and_refuses_to_import_without_paddle():
+    """emrt_b200/paddle_shim.py cannot run here (no PaddlePaddle); it must at least be valid Python, bind only symbols the
+    C ABI exports, and fail with a clear ImportError instead of degrading to anything else."""
+    import ast
+    import importlib
+    import re
+    path = os.path.join(ROOT, "emrt_b200", "paddle_shim.py")
+    src = open(path).read()
+    ast.parse(src)
+    from emrt_b200 import _lib
+    for name in set(re.findall(r"\.(emrt_[a-z0-9_]+)\(", src)):
+        assert name in _lib.SIGNATURES, name
+    try:
+        import paddle  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="PaddlePaddle"):
+            importlib.import_module("emrt_b200.paddle_shim")

@@ -156,12 +156,13 @@ def test_linear_simt_fp32(cuda_dev, rows, K, N, wt):
     assert rel_err(got, want) < 1e-5
 
 
-def _load_module(params, C, M, Lv, P, dev):
+def _load_module(params, C, M, Lv, P, dev, train=False):
     m = emrt_b200.MSDeformableAttention(C, M, Lv, P).to(dev)
     with torch.no_grad():
         for name, arr in params.items():
             mod, leaf = name.split(".")
             getattr(getattr(m, mod), leaf).copy_(torch.from_numpy(arr))
+    m.requires_grad_(train)        # frozen parameters -> the inference path; trainable -> the autograd path
     return m
 
 
@@ -353,3 +354,88 @@ def test_gather_window_staged_arbitrary_reference_points(cuda_dev):
     got = ops.msda_gather_fwd(v_hm, torch.from_numpy(loc).to(cuda_dev), torch.from_numpy(attn).to(cuda_dev), shapes,
                               mode=L.LOC_NORMALIZED | L.VALUE_HEAD_MAJOR | L.QUERY_PIXEL_GRID)
     assert rel_err(got.float(), want) < BF16_TOL
+
+
+def _oracle_msda_grads(params, q, ref, v, shapes, mask, M, P, d_out, dtype=torch.float64):
+    """Gradients of the oracle's MSDA forward w.r.t. query, value and the eight parameters (torch autograd through
+    the grid_sample formulation — what Paddle autograd derives for the reference module)."""
+    tp = {k: torch.from_numpy(a).to(dtype).requires_grad_(True) for k, a in params.items()}
+    tq = torch.from_numpy(q).to(dtype).requires_grad_(True)
+    tv = torch.from_numpy(v).to(dtype).requires_grad_(True)
+    out = O.msda_forward(tp, tq, torch.from_numpy(ref).to(dtype), tv, shapes,
+                         None if mask is None else torch.from_numpy(mask).to(dtype), M, P, dtype=dtype)
+    out.backward(torch.from_numpy(d_out).to(dtype))
+    grads = {k: t.grad for k, t in tp.items()}
+    grads["query"], grads["value"] = tq.grad, tv.grad
+    return out.detach(), grads
+
+
+@pytest.mark.parametrize("case", ["encoder", "decoder"])
+def test_msda_module_backward_fp32(cuda_dev, case):
+    """Training path, fp32: fwd + bwd through the autograd Function vs autograd of the oracle (1e-4)."""
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    B, C, M, P = 2, 256, 8, 6
+    rng = np.random.Generator(np.random.PCG64(11))
+    _, Lv = O.level_tables(shapes)
+    Lq = Lv if case == "encoder" else 37
+    params = O.make_msda_params(77, C, M, 3, P)
+    q, v = O.rng_normal(rng, (B, Lq, C)), O.rng_normal(rng, (B, Lv, C))
+    ref = (O.encoder_reference_points(shapes, B).numpy() if case == "encoder"
+           else rng.uniform(0.1, 0.9, size=(B, Lq, 3, 2)).astype(np.float32))
+    mask = (rng.uniform(size=(B, Lv)) > 0.1).astype(np.float32)
+    d_out = O.rng_normal(rng, (B, Lq, C))
+    want, wg = _oracle_msda_grads(params, q, ref, v, shapes, mask, M, P, d_out)
+    m = _load_module(params, C, M, 3, P, cuda_dev, train=True)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    tq, tv = d(q).requires_grad_(True), d(v).requires_grad_(True)
+    out = m(tq, d(ref), tv, shapes, d(mask))
+    out.backward(d(d_out))
+    assert rel_err(out, want) < FP32_TOL
+    assert rel_err(tq.grad, wg["query"]) < 5e-4 and rel_err(tv.grad, wg["value"]) < 5e-4
+    for name, g in wg.items():
+        if "." in name:
+            mod, leaf = name.split(".")
+            got = getattr(getattr(m, mod), leaf).grad
+            assert got is not None and rel_err(got, g) < 5e-4, name
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+def test_msda_module_backward_bf16(cuda_dev, impl):
+    """Training path, bf16 activations: gradients vs the float64 oracle on the bf16-rounded inputs / weights."""
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    B, C, M, P = 2, 256, 8, 6
+    rng = np.random.Generator(np.random.PCG64(12))
+    _, Lv = O.level_tables(shapes)
+    params = O.make_msda_params(78, C, M, 3, P)
+    q, v = O.rng_normal(rng, (B, Lv, C)), O.rng_normal(rng, (B, Lv, C))
+    ref = O.encoder_reference_points(shapes, B).numpy()
+    mask = (rng.uniform(size=(B, Lv)) > 0.1).astype(np.float32)
+    d_out = O.rng_normal(rng, (B, Lv, C))
+    r = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    p16 = {k: (r(a) if k.endswith("weight") else a) for k, a in params.items()}
+    want, wg = _oracle_msda_grads(p16, r(q), ref, r(v), shapes, mask, M, P, r(d_out))
+    m = _load_module(params, C, M, 3, P, cuda_dev, train=True)
+    m.gemm_impl = L.IMPL_SIMT if impl == "simt" else L.IMPL_TCGEN05
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    tq, tv = d(q).bfloat16().requires_grad_(True), d(v).bfloat16().requires_grad_(True)
+    out = m(tq, d(ref), tv, shapes, d(mask))
+    out.backward(d(d_out).bfloat16())
+    # bf16 activations, fp16 offsets / weights and bf16 gradient tensors between the kernels.  The gradient w.r.t. a
+    # sampling position is DISCONTINUOUS at pixel boundaries, and fp16-rounded offsets put ~1 % of the samples in the
+    # neighbouring bilinear cell of the float64 oracle, so everything downstream of grad_loc (query, sampling_offsets)
+    # is judged by its relative L2 error; the rest by the max-norm error.
+    def l2_err(got, want):
+        want = torch.as_tensor(want).double()
+        return ((got.detach().double().cpu() - want).norm() / want.norm().clamp_min(1e-30)).item()
+    errs = {"out": rel_err(out.float(), want), "value": rel_err(tv.grad.float(), wg["value"]),
+            "query(l2)": l2_err(tq.grad.float(), wg["query"])}
+    for name, g in wg.items():
+        if "." in name:
+            mod, leaf = name.split(".")
+            got = getattr(getattr(m, mod), leaf).grad
+            assert got is not None, name
+            errs[name + ("(l2)" if mod == "sampling_offsets" else "")] = (
+                l2_err(got.float(), g) if mod == "sampling_offsets" else rel_err(got.float(), g))
+    assert errs["out"] < BF16_TOL, errs
+    bad = {k: v for k, v in errs.items() if v >= (1e-1 if k.endswith("(l2)") else 3e-2)}
+    assert not bad, errs

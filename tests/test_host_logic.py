@@ -106,3 +106,37 @@ def test_reference_points_host_mirror_equals_oracle(shapes):
     vr = np.full((2, len(shapes), 2), 0.75, np.float32)
     got_vr = reference_points_host(shapes, vr)
     assert got_vr.shape[0] == 2 and np.allclose(got_vr, got, atol=1e-6)     # (x / (vr * W)) * vr == x / W
+
+
+def _grad_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from emrt_b200.train import GradientBuckets
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(256, 288)), torch.nn.Parameter(torch.zeros(288)),
+              torch.nn.Parameter(torch.zeros(256, 256)), torch.nn.Parameter(torch.zeros(7))]
+    gb = GradientBuckets(params, bucket_mb=0.3)            # forces several buckets
+    assert len(gb.buckets) >= 2 and gb.nbytes == 4 * sum(p.numel() for p in params)
+    loss = sum(((rank + 1) * (i + 1)) * p.sum() for i, p in enumerate(params[:3]))     # params[3] never gets a grad
+    loss.backward()
+    assert all(p.grad.data_ptr() >= gb.buckets[0].data_ptr() for p in params[:1])      # grads live in the buckets
+    gb.all_reduce()
+    mean = sum(r + 1 for r in range(world)) / world
+    ok = all(torch.allclose(p.grad, torch.full_like(p, mean * (i + 1))) for i, p in enumerate(params[:3]))
+    ok = ok and bool((params[3].grad == 0).all())
+    gb.zero()
+    ok = ok and all(float(p.grad.abs().sum()) == 0 for p in params)
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_buckets_average_in_place():
+    """cfg 4's exchange step (DataParallel grad sync, train.py:116-123,153): bucketed in-place average over 2 ranks."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
