@@ -35,10 +35,10 @@ METRIC = "images/s (512x512 windows through the EMRT hot path: 6x MSDeformableAt
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images", type=int, default=2, help="1024x1024 scenes per GPU per step (9 windows each)")
+    ap.add_argument("--images", type=int, default=8, help="1024x1024 scenes per GPU per step (9 windows each)")
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-windows", type=int, default=4)

@@ -103,6 +103,17 @@ __device__ __forceinline__ int softmax_argmax(const float (&l)[NC], int nc, floa
   return best;
 }
 
+// argmax over the logits themselves: argmax(softmax(l)) == argmax(l) (exp is monotonic; equal logits give equal
+// probabilities, so the first-max tie rule picks the same class) — used whenever probabilities are not requested.
+template <int NC>
+__device__ __forceinline__ int argmax_first(const float (&l)[NC], int nc) {
+  int best = 0;
+  float bv = l[0];
+#pragma unroll
+  for (int c = 1; c < NC; ++c) if (c < nc && l[c] > bv) { bv = l[c]; best = c; }
+  return best;
+}
+
 __device__ __forceinline__ void store_label(void* labels, int label_dtype, int64_t i, int v) {
   if (label_dtype == EMRT_U8) reinterpret_cast<uint8_t*>(labels)[i] = (uint8_t)v;
   else reinterpret_cast<int32_t*>(labels)[i] = v;
@@ -172,7 +183,7 @@ finalize_argmax_kernel(const float* __restrict__ canvas, const float* __restrict
       l[c] = top + ty.f * (bot - top);
     }
   }
-  const int best = softmax_argmax<NC>(l, nc, prob);
+  const int best = probs_out ? softmax_argmax<NC>(l, nc, prob) : argmax_first<NC>(l, nc);
   store_label(labels, label_dtype, idx, best);
   if (probs_out) {
 #pragma unroll
@@ -196,7 +207,7 @@ stitch_argmax_fused_kernel(const T* __restrict__ half_logits, void* __restrict__
   if (x >= W || y >= H) return;
   const int hh = hc / 2, hw = wc / 2;
   const int n = wl.n < 0 ? n_win : wl.n;
-  float acc[NC], prob[NC];
+  float acc[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) acc[c] = 0.f;
   float cnt = 0.f;
@@ -212,14 +223,14 @@ stitch_argmax_fused_kernel(const T* __restrict__ half_logits, void* __restrict__
     for (int c = 0; c < NC; ++c) if (c < nc) acc[c] += bilerp<T>(src + (int64_t)c * hh * hw, hw, ty, tx);
   }
   const int64_t plane = (int64_t)H * W, o = (int64_t)y * W + x;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) if (c < nc) acc[c] = acc[c] / cnt;
   if (logits_out) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) if (c < nc) logits_out[((int64_t)img * nc + c) * plane + o] = acc[c];
+    for (int c = 0; c < NC; ++c) if (c < nc) {
+      acc[c] = acc[c] / cnt;                                   // logit / count (infer.py:79)
+      logits_out[((int64_t)img * nc + c) * plane + o] = acc[c];
+    }
   }
-  const int best = softmax_argmax<NC>(acc, nc, prob);
-  store_label(labels, label_dtype, (int64_t)img * plane + o, best);
+  store_label(labels, label_dtype, (int64_t)img * plane + o, argmax_first<NC>(acc, nc));
 }
 
 // a5 + a6 + a7, one 2x2 quad of label pixels per thread (H, W even).  For x2 upsampling the four pixels of a quad read
@@ -323,10 +334,13 @@ stitch_argmax_quad_kernel(const T* __restrict__ half_logits, void* __restrict__ 
   int best[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    float prob[NC];
+    if (logits_out) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) if (c < nc) acc[k][c] = acc[k][c] / cnt[k];
-    best[k] = softmax_argmax<NC>(acc[k], nc, prob);
+      for (int c = 0; c < NC; ++c) if (c < nc) acc[k][c] = acc[k][c] / cnt[k];     // logit / count (infer.py:79)
+    }
+    // argmax(softmax(sum / count)) == argmax(sum): exp and the division by a positive count are monotonic, and equal
+    // sums give equal probabilities, so the first-max tie rule (infer.py:152-153) picks the same class
+    best[k] = argmax_first<NC>(acc[k], nc);
   }
 #pragma unroll
   for (int oy = 0; oy < 2; ++oy) {

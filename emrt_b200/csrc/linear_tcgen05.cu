@@ -496,7 +496,7 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
   if (a->epilogue & ~(EMRT_EPI_ROW_MASK | EMRT_EPI_RELU | EMRT_EPI_HEAD_MAJOR))
     return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 linear: unsupported epilogue flags %d", a->epilogue);
   if (a->N <= 64) return pick_tc<64, 8, 8, 8, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
-  if (a->N <= 128) return pick_tc<128, 8, 8, 6, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
+  if (a->N <= 128 || getenv("EMRT_GEMM_BN128")) return pick_tc<128, 8, 8, 6, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
   return pick_tc<256, 4, 5, 4, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
 }
 

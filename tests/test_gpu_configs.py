@@ -1,0 +1,178 @@
+"""BASELINE.json's configurations as parity cases: the hot path at each config's geometry against the
+CPU oracle, plus size-independent properties at the sizes the oracle cannot finish in seconds."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import emrt_b200
+from emrt_b200 import ops, sharding, _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, want):
+    want = torch.as_tensor(want).double()
+    return ((got.detach().double().cpu() - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+def _module(params, dev, M=8, P=6, C=256):
+    m = emrt_b200.MSDeformableAttention(C, M, 3, P).to(dev)
+    with torch.no_grad():
+        for name, arr in params.items():
+            mod, leaf = name.split(".")
+            getattr(getattr(m, mod), leaf).copy_(torch.from_numpy(arr))
+    return m.requires_grad_(False)
+
+
+def _stack(params_list, src, pos, tgt, qpos, ref_dec, shapes, mask, dev, dtype):
+    """4 encoder + 2 decoder MSDA calls as EncoderDecoder chains them (t_e_d.py:198,288), on the kernels."""
+    d = lambda a: torch.from_numpy(a).to(dev).to(dtype)
+    mods = [_module(p, dev) for p in params_list]
+    ref_enc = emrt_b200.get_reference_points(shapes, device=dev)
+    x, t = d(src), d(tgt)
+    maskd = None if mask is None else torch.from_numpy(mask).to(dev)
+    with torch.no_grad():
+        for m in mods[:4]:
+            x = m(ops.add_bcast(x, d(pos)), ref_enc, x, shapes, maskd)
+        for m in mods[4:]:
+            t = m(ops.add_bcast(t, d(qpos)), torch.from_numpy(ref_dec).to(dev), x, shapes, maskd)
+    return x, t
+
+
+def _oracle_stack(params_list, src, pos, tgt, qpos, ref_dec, shapes, mask, dtype=torch.float64, round_bf16=False):
+    r = (lambda a: torch.from_numpy(a).bfloat16().to(dtype)) if round_bf16 else (lambda a: torch.from_numpy(a).to(dtype))
+    rb = (lambda t: t.bfloat16().to(dtype)) if round_bf16 else (lambda t: t)
+    B = src.shape[0]
+    ref_enc = O.encoder_reference_points(shapes, B)
+    x, t = r(src), r(tgt)
+    for p in params_list[:4]:
+        pp = {k: (r(a) if k.endswith("weight") else torch.from_numpy(a).to(dtype)) for k, a in p.items()}
+        x = rb(O.msda_forward(pp, rb(x + r(pos)), ref_enc, x, shapes, mask, dtype=dtype))
+    for p in params_list[4:]:
+        pp = {k: (r(a) if k.endswith("weight") else torch.from_numpy(a).to(dtype)) for k, a in p.items()}
+        t = rb(O.msda_forward(pp, rb(t + r(qpos)), ref_dec, x, shapes, mask, dtype=dtype))
+    return x, t
+
+
+def _inputs(seed, B, shapes, Nq=110, C=256):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    _, Lv = O.level_tables(shapes)
+    params = [O.make_msda_params(1234 + i) for i in range(6)]
+    src, tgt = O.rng_normal(rng, (B, Lv, C), 0.5), O.rng_normal(rng, (B, Nq, C), 0.5)
+    pos, qpos = O.rng_normal(rng, (1, Lv, C), 0.5), O.rng_normal(rng, (1, Nq, C), 0.5)
+    ref_dec = np.repeat(rng.uniform(0.05, 0.95, size=(B, Nq, 1, 2)).astype(np.float32), 3, axis=2)
+    return params, src, pos, tgt, qpos, ref_dec
+
+
+def test_cfg1_fp32_single_256_tile_msda_stack_and_head(cuda_dev):
+    """configs[0]: one 1x3x256x256 tile, 6 classes, fp32: the six chained MSDA calls within 1e-4 of the oracle, then
+    the head tail (x2 upsample + softmax + argmax) on 128x128 class logits with >= 99.9 % label agreement."""
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    params, src, pos, tgt, qpos, ref_dec = _inputs(1, 1, shapes)
+    mem, hs = _stack(params, src, pos, tgt, qpos, ref_dec, shapes, None, cuda_dev, torch.float32)
+    wmem, whs = _oracle_stack(params, src, pos, tgt, qpos, ref_dec, shapes, None)
+    assert rel_err(mem, wmem) < 1e-4 and rel_err(hs, whs) < 1e-4
+    rng = np.random.Generator(np.random.PCG64(2))
+    half = O.rng_normal(rng, (1, 6, 128, 128))
+    want = O.ss_inference_tail(O.upsample2x(torch.from_numpy(half)), (256, 256))
+    z = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+    lab, logits = ops.stitch_argmax_fused(torch.from_numpy(half).to(cuda_dev), z, z, z, 1, 256, 256, want_logits=True)
+    assert rel_err(logits, O.upsample2x(torch.from_numpy(half))) < 1e-6
+    assert (lab.cpu() == want).float().mean().item() >= 0.999
+
+
+def test_cfg2_bf16_batch64_256_tiles(cuda_dev):
+    """configs[1]: batch 64 of 256x256 tiles, bf16: one encoder + one decoder MSDA call at the full batch within 1e-2 of
+    the float64 oracle evaluated on the bf16-rounded inputs, and label agreement >= 99.9 % for the 64 label maps."""
+    shapes = [(32, 32), (16, 16), (8, 8)]
+    B = 64
+    params, src, pos, tgt, qpos, ref_dec = _inputs(3, B, shapes)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev).bfloat16()
+    r = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    mods = [_module(params[0], cuda_dev), _module(params[4], cuda_dev)]
+    ref_enc = emrt_b200.get_reference_points(shapes, device=cuda_dev)
+    with torch.no_grad():
+        x = d(src)
+        q = ops.add_bcast(x, d(pos))
+        mem = mods[0](q, ref_enc, x, shapes)
+        t = d(tgt)
+        hs = mods[1](ops.add_bcast(t, d(qpos)), torch.from_numpy(ref_dec).to(cuda_dev), mem, shapes)
+    p0 = {k: (r(a) if k.endswith("weight") else a) for k, a in params[0].items()}
+    p4 = {k: (r(a) if k.endswith("weight") else a) for k, a in params[4].items()}
+    want_mem = O.msda_forward(p0, q.float().cpu().numpy(), O.encoder_reference_points(shapes, B), r(src), shapes,
+                              dtype=torch.float32)
+    assert rel_err(mem.float(), want_mem) < 1e-2
+    want_hs = O.msda_forward(p4, ops.add_bcast(t, d(qpos)).float().cpu().numpy(), ref_dec, mem.float().cpu().numpy(),
+                             shapes, dtype=torch.float32)
+    assert rel_err(hs.float(), want_hs) < 1e-2
+    rng = np.random.Generator(np.random.PCG64(4))
+    half = torch.from_numpy(O.rng_normal(rng, (B, 6, 128, 128))).bfloat16()
+    want = O.ss_inference_tail(O.upsample2x(half.float()), (256, 256))
+    idx = torch.arange(B, dtype=torch.int32, device=cuda_dev)
+    z = torch.zeros(B, dtype=torch.int32, device=cuda_dev)
+    lab, _ = ops.stitch_argmax_fused(half.to(cuda_dev), idx, z, z, B, 256, 256, label_dtype=torch.uint8)
+    assert (lab.cpu().to(torch.int32) == want).float().mean().item() >= 0.999
+
+
+def test_cfg3_bf16_512_windows_encoder_call(cuda_dev):
+    """configs[2] geometry (512x512 windows of a 1024x1024 scene, Lv = 5376): the window-staged encoder call and a
+    decoder call at 9 windows vs the oracle (bf16, 1e-2).  The stitching side of cfg 3 is in test_gpu_head.py."""
+    shapes = [(64, 64), (32, 32), (16, 16)]
+    B = 9
+    params, src, pos, tgt, qpos, ref_dec = _inputs(5, B, shapes)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev).bfloat16()
+    r = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    m = _module(params[1], cuda_dev)
+    ref_enc = emrt_b200.get_reference_points(shapes, device=cuda_dev)
+    with torch.no_grad():
+        x = d(src)
+        q = ops.add_bcast(x, d(pos))
+        before = ops.launch_count()
+        mem = m(q, ref_enc, x, shapes)
+        assert ops.launch_count() == before + 4           # value proj, fused query proj, gather, output proj
+    p1 = {k: (r(a) if k.endswith("weight") else a) for k, a in params[1].items()}
+    want = O.msda_forward(p1, q.float().cpu().numpy(), O.encoder_reference_points(shapes, B), r(src), shapes,
+                          dtype=torch.float32)
+    assert rel_err(mem.float(), want) < 1e-2
+
+
+@pytest.mark.parametrize("world", [8])
+def test_cfg5_6000_scene_row_bands_equal_single_gpu_stitch(cuda_dev, world):
+    """configs[4]: one 6000x6000 scene, window 512 stride 384 -> 16 x 16 = 256 windows.  (i) Full-size property: with
+    per-window constant logits the stitched logits are the cover-count-weighted mean of the constants (checked on
+    sampled pixels against a host computation from the window plan) and labels are their argmax.  (ii) Sharding: the
+    label map assembled from `world` row bands (shard_scene_rows: owned + recomputed halo window rows, no
+    communication) equals the single-device label map exactly."""
+    H = W = 6000
+    crop, stride, nc = 512, 384, 3
+    plan, mh, mw = emrt_b200.plan_windows([(H, W)], (crop, crop), (stride, stride))
+    assert len(plan) == 256 and (mh, mw) == (H, W)
+    rng = np.random.Generator(np.random.PCG64(6))
+    consts = rng.standard_normal((len(plan), nc)).astype(np.float32)
+    half = torch.from_numpy(consts).to(cuda_dev).reshape(len(plan), nc, 1, 1).expand(-1, -1, crop // 2, crop // 2).contiguous()
+    ti = lambda v: torch.tensor(v, dtype=torch.int32, device=cuda_dev)
+    lab, logits = ops.stitch_argmax_fused(half, ti([p[0] for p in plan]), ti([p[1] for p in plan]),
+                                          ti([p[2] for p in plan]), 1, H, W, label_dtype=torch.uint8, want_logits=True)
+    ys = rng.integers(0, H, 4000)
+    xs = rng.integers(0, W, 4000)
+    cov = np.array([[(p[1] <= y < p[1] + crop) and (p[2] <= x < p[2] + crop) for p in plan] for y, x in zip(ys, xs)])
+    assert cov.sum(1).min() >= 1 and cov.sum(1).max() >= 4
+    want = np.stack([consts[c].astype(np.float64).sum(0) / c.sum() for c in cov])          # [n, nc]
+    got = logits[0][:, torch.from_numpy(ys).to(cuda_dev), torch.from_numpy(xs).to(cuda_dev)].T.cpu().numpy()
+    assert np.abs(got - want).max() < 1e-5
+    assert np.array_equal(lab[0, 0].cpu().numpy()[ys, xs], got.argmax(1).astype(np.uint8))
+    del logits
+    # (ii) row bands
+    rows = O.window_origins(H, crop, stride)
+    assembled = torch.empty_like(lab)
+    for rank in range(world):
+        own, y0, y1, halo = sharding.shard_scene_rows(rows, crop, rank, world)
+        use = sorted(set(own) | set(halo))
+        sel = [k for k, p in enumerate(plan) if rows.index(p[1]) in use]      # windows of those rows, plan order
+        band_y0 = min(plan[k][1] for k in sel)
+        band_h = max(plan[k][1] for k in sel) + crop - band_y0
+        lab_b, _ = ops.stitch_argmax_fused(half[sel].contiguous(), ti([0] * len(sel)), ti([plan[k][1] - band_y0 for k in sel]),
+                                           ti([plan[k][2] for k in sel]), 1, band_h, W, label_dtype=torch.uint8)
+        assembled[0, 0, y0:y1] = lab_b[0, 0, y0 - band_y0:y1 - band_y0]
+    assert torch.equal(assembled, lab)
