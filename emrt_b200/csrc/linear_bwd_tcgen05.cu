@@ -1,0 +1,204 @@
+// Weight gradient of nn.Linear on tcgen05: dW[K,N] += x[rows,K]^T dy[rows,N] (bf16 operands, fp32 accumulate).
+//
+// GEMM view: D[M = k][N = n] = sum_r A[m][r] B[r][n] with the REDUCTION running over the rows.  Both operands are
+// row-major [rows, *] in HBM, i.e. MN-major for this product, so the smem descriptors use the MN-major SWIZZLE_128B
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: a TMA box {64 elements, 64 rows} lands as 64 rows of
+// 128 swizzled bytes = eight 1024-byte atoms (SBO = 1024 B between 8-row groups); a 128-wide operand is two such boxes
+// (LBO = 8192 B).  The instruction descriptor sets the a_major / b_major (transpose) bits.
+// Split-K: every output tile (128 k x 128 n) is shared by gridDim.x / tiles CTAs, each reducing a contiguous range of
+// 64-row chunks into one TMEM accumulator and adding its partial tile to dW with red.global.add.v4.f32.
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace emrt {
+
+int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
+constexpr int DW_T = 128;        // tile: 128 (k) x 128 (n)
+constexpr int DW_R = 64;         // rows per pipeline stage
+constexpr int DW_STAGES = 6;
+constexpr int DW_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+
+struct DwParams {
+  CUtensorMap tma_x;    // x  [rows, K] bf16, box {64, 64}
+  CUtensorMap tma_dy;   // dy [rows, N] bf16, box {64, 64}
+  float* dw;
+  int32_t K, N;
+  int32_t tiles_k, tiles_n, splits, chunks;
+};
+
+struct DwSmem {
+  __nv_bfloat16 a[DW_STAGES][2][DW_R * 64];   // [stage][64-wide k block][64 rows x 64 elements]
+  __nv_bfloat16 b[DW_STAGES][2][DW_R * 64];
+  uint64_t full[DW_STAGES];
+  uint64_t empty[DW_STAGES];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+// MN-major SWIZZLE_128B descriptor: LBO = 8192 B (next 64-element block), SBO = 1024 B (next 8 reduction rows)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor, D = f32, A = B = bf16, both operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+linear_bwd_weight_tc_kernel(const __grid_constant__ DwParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  DwSmem& s = *reinterpret_cast<DwSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  const int tk = tile / p.tiles_n, tn = tile % p.tiles_n;
+  const int per = (p.chunks + p.splits - 1) / p.splits;
+  const int c_begin = split * per, c_end = min(c_begin + per, p.chunks);
+  constexpr uint32_t STAGE_BYTES = 4 * DW_R * 64 * 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_x);
+    tma_prefetch_desc(&p.tma_dy);
+#pragma unroll
+    for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    mbar_init(&s.acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tma_load_2d(s.a[stage][h], &p.tma_x, &s.full[stage], tk * DW_T + h * 64, c * DW_R);
+          tma_load_2d(s.b[stage][h], &p.tma_dy, &s.full[stage], tn * DW_T + h * 64, c * DW_R);
+        }
+        if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_mn(DW_T, DW_T);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&s.full[stage], phase);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_mn(smem_u32(s.a[stage][0]));
+        const uint64_t db = make_smem_desc_mn(smem_u32(s.b[stage][0]));
+#pragma unroll
+        for (int k = 0; k < DW_R / 16; ++k)   // 16 reduction rows = two 1024-byte atoms = +2048 bytes
+          umma_bf16(tmem_base, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, (c > c_begin || k > 0) ? 1u : 0u);
+        umma_commit(&s.empty[stage]);
+        if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&s.acc_full);
+    }
+  } else if (c_end > c_begin) {
+    const int q = warp & 3;
+    mbar_wait(&s.acc_full, 0);
+    tc_fence_after();
+    const int k = tk * DW_T + q * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < DW_T; c += 32) {
+      uint32_t r[32];
+      TMEM_LD_X32(t_row + c, r);
+      TMEM_WAIT_X32(r);
+      if (k < p.K) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = tn * DW_T + c + j;
+          if (n < p.N)     // N % 4 == 0
+            red_add_v4(p.dw + (int64_t)k * p.N + n, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+// column sums of dy (the bias gradient): grid-stride over row blocks, fp32 atomics per CTA
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ dy, float* __restrict__ db, int64_t rows, int N, int rows_per_cta) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += to_float(dy[r * N + n]);
+    atomicAdd(db + n, acc);
+  }
+}
+
+int colsum(const void* dy, float* db, int64_t rows, int N, int dtype, cudaStream_t st) {
+  const int rows_per_cta = 256;
+  const unsigned blocks = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+  if (dtype == EMRT_BF16) colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, db, rows, N, rows_per_cta);
+  else if (dtype == EMRT_F32) colsum_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, db, rows, N, rows_per_cta);
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "colsum: bad dtype %d", dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+// Returns EMRT_ERR_UNSUPPORTED (error text untouched) when the tensor-core path does not apply.
+int linear_bwd_weight_tc(const void* x, const void* dy, float* dw, int64_t rows, int K, int N, cudaStream_t st) {
+  if (K % 8 != 0 || N % 8 != 0 || rows >= (1LL << 31)) return EMRT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dw)) & 15) return EMRT_ERR_UNSUPPORTED;
+  DwParams p;
+  memset(&p, 0, sizeof(p));
+  const uint32_t box[2] = {64u, (uint32_t)DW_R};
+  const uint64_t dx[2] = {(uint64_t)K, (uint64_t)rows}, sx[1] = {(uint64_t)K * 2};
+  if (int e = make_tensor_map(&p.tma_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dx, sx, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  const uint64_t dd[2] = {(uint64_t)N, (uint64_t)rows}, sd[1] = {(uint64_t)N * 2};
+  if (int e = make_tensor_map(&p.tma_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dy, dd, sd, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  p.dw = dw; p.K = K; p.N = N;
+  p.tiles_k = (K + DW_T - 1) / DW_T;
+  p.tiles_n = (N + DW_T - 1) / DW_T;
+  p.chunks = (int)((rows + DW_R - 1) / DW_R);
+  const int tiles = p.tiles_k * p.tiles_n;
+  p.splits = num_sms() / tiles;
+  if (p.splits < 1) p.splits = 1;
+  if (p.splits > p.chunks) p.splits = p.chunks;
+  const int smem_bytes = (int)sizeof(DwSmem) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EMRT_CUDA_CHECK(cudaFuncSetAttribute(linear_bwd_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  linear_bwd_weight_tc_kernel<<<tiles * p.splits, DW_THREADS, smem_bytes, st>>>(p);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+}  // namespace emrt

@@ -6,6 +6,8 @@
 // the pre-packed [N',K'] operand of emrt_linear_fwd for that product.
 // dW here is an fp32-accumulate SIMT tile kernel with split-row partial sums (atomics into the fp32 gradient); it is
 // the parity implementation — the tcgen05 version (MN-major operands) is the next step.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace emrt {
@@ -123,10 +125,21 @@ scale_rows_cast_kernel(const float* __restrict__ src, const float* __restrict__ 
 
 using namespace emrt;
 
+namespace emrt {
+int linear_bwd_weight_tc(const void* x, const void* dy, float* dw, int64_t rows, int K, int N, cudaStream_t st);
+int colsum(const void* dy, float* db, int64_t rows, int N, int dtype, cudaStream_t st);
+}
+
 extern "C" int emrt_linear_bwd_weight(const void* x, const void* dy, float* dw, float* db, int64_t rows, int K, int N,
                                       int x_dtype, int dy_dtype, void* stream) {
   EMRT_REQUIRE(x && dy && dw, "NULL tensor pointer");
   EMRT_REQUIRE(rows > 0 && K > 0 && N > 0, "non-positive dimension");
+  if (x_dtype == EMRT_BF16 && dy_dtype == EMRT_BF16 && !getenv("EMRT_DW_SIMT")) {
+    // tensor-core path (MN-major tcgen05, split-K); the bias gradient is a separate column-sum pass over dy
+    const int e = linear_bwd_weight_tc(x, dy, dw, rows, K, N, as_stream(stream));
+    if (e == EMRT_OK) return db ? colsum(dy, db, rows, N, dy_dtype, as_stream(stream)) : EMRT_OK;
+    if (e != EMRT_ERR_UNSUPPORTED) return e;
+  }
   int rows_per_cta = 1024;
   int64_t chunks = (rows + rows_per_cta - 1) / rows_per_cta;
   if (chunks > 65535) { rows_per_cta = (int)((rows + 65534) / 65535); rows_per_cta = (rows_per_cta + WG_R - 1) / WG_R * WG_R; chunks = (rows + rows_per_cta - 1) / rows_per_cta; }

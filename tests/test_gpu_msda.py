@@ -439,3 +439,31 @@ def test_msda_module_backward_bf16(cuda_dev, impl):
     assert errs["out"] < BF16_TOL, errs
     bad = {k: v for k, v in errs.items() if v >= (1e-1 if k.endswith("(l2)") else 3e-2)}
     assert not bad, errs
+
+
+@pytest.mark.parametrize("rows,K,N", [(1000, 256, 432), (129, 96, 40), (20000, 256, 256), (64, 256, 1024)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_bwd_weight(cuda_dev, rows, K, N, dtype):
+    """dW += x^T dy, db += colsum(dy): fp32 SIMT path and bf16 tcgen05 (MN-major operands, split-K) path vs float64;
+    accumulation semantics (a second call doubles the result); the SIMT kernel on the same bf16 data as cross-check."""
+    rng = np.random.Generator(np.random.PCG64(rows + N))
+    x = torch.from_numpy(O.rng_normal(rng, (rows, K))).to(dtype)
+    dy = torch.from_numpy(O.rng_normal(rng, (rows, N))).to(dtype)
+    want_w = x.double().T @ dy.double()
+    want_b = dy.double().sum(0)
+    xd, dyd = x.to(cuda_dev), dy.to(cuda_dev)
+    dw = torch.zeros((K, N), dtype=torch.float32, device=cuda_dev)
+    db = torch.zeros((N,), dtype=torch.float32, device=cuda_dev)
+    ops.linear_bwd_weight(xd, dyd, dw, db)
+    tol = 1e-5 if dtype == torch.float32 else 1e-4          # bf16 inputs are exact products, fp32 accumulation
+    assert rel_err(dw, want_w) < tol and rel_err(db, want_b) < tol
+    ops.linear_bwd_weight(xd, dyd, dw, db)
+    assert rel_err(dw, 2 * want_w) < tol and rel_err(db, 2 * want_b) < tol
+    if dtype == torch.bfloat16:
+        os.environ["EMRT_DW_SIMT"] = "1"
+        try:
+            dw2 = torch.zeros_like(dw)
+            ops.linear_bwd_weight(xd, dyd, dw2, None)
+        finally:
+            del os.environ["EMRT_DW_SIMT"]
+        assert rel_err(dw2, want_w) < tol
