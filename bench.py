@@ -2,11 +2,13 @@
 """bench.py — EMRT hot path on B200: images/s (512x512 windows) and MPix/s.
 
 A "step" = one pass of the hot path over one batch of synthetic input:
-  4 encoder + 2 decoder MSDeformableAttention calls (value/offset/weight/output projections, softmax over
-  levels x points, multiscale bilinear gather) on the C3-C5 token maps of W 512x512 windows, then the head tail
-  (x2 bilinear upsample + sliding-window overlap stitch + softmax + argmax) that turns the windows' half-resolution
-  class logits into 1024x1024 LoveDA-shaped label maps (9 windows per image, window 512 stride 384).
-Out of the step (out of scope / "next" rows): ResNet-50 backbone, conv heads, LayerNorm/FFN glue.
+  the 4-layer TransformerEncoder (per layer: 3x3 conv branch + GroupNorm + GELU, MSDeformableAttention [value / offset /
+  weight / output projections, softmax over levels x points, multiscale bilinear gather], LayerNorm, FFN 256-1024-256,
+  LayerNorm) and the 2 decoder cross-attention MSDeformableAttention calls on the C3-C5 token maps of W 512x512
+  windows, then the head tail (x2 bilinear upsample + sliding-window overlap stitch + softmax + argmax) that turns the
+  windows' half-resolution class logits into 1024x1024 LoveDA-shaped label maps (9 windows per image, window 512,
+  stride 384).
+Out of the step (out of scope / "next" rows): ResNet-50 backbone, conv heads, decoder self-attention glue.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun)
   python bench.py --impl reference ...                           the reference path's CPU restatement (oracle)
@@ -29,7 +31,8 @@ TILE = 512
 NC = 7                      # LoveDA
 WINDOWS_PER_IMAGE = 9       # 1024x1024, window 512, stride 384 -> origins {0, 384, 512}^2
 SCENE = 1024
-METRIC = "images/s (512x512 windows through the EMRT hot path: 6x MSDeformableAttention + upsample/stitch/argmax)"
+METRIC = ("images/s (512x512 windows through the EMRT hot path: 4-layer TransformerEncoder [conv branch + "
+          "MSDeformableAttention + LayerNorm + FFN] + 2 decoder MSDeformableAttention + upsample/stitch/argmax)")
 
 
 def parse():
@@ -41,7 +44,8 @@ def parse():
     ap.add_argument("--images", type=int, default=8, help="1024x1024 scenes per GPU per step (9 windows each)")
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-windows", type=int, default=4)
+    ap.add_argument("--cpu-sample-windows", type=int, default=8)
+    ap.add_argument("--msda-only", action="store_true", help="round-1 starting definition: 4 + 2 bare MSDA calls + head tail")
     return ap.parse_args()
 
 
@@ -107,6 +111,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(B):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, keyed by windows per launch), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        e = d["msda_gather_fwd_win"].get(str(B))
+        return None if e is None else float(e["dram_bytes_read"]) + float(e["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def window_tables(n_img):
     import emrt_b200
     plan, H, W = emrt_b200.plan_windows([(SCENE, SCENE)] * n_img, (TILE, TILE), (384, 384))
@@ -128,11 +144,16 @@ def cpu_hot_path(n_windows, threads, repeats=1, warmup=0):
     import numpy as np
     import torch
     import oracle as O
+    from emrt_b200 import synthetic
     torch.set_num_threads(threads)
     shapes = [(TILE // 8,) * 2, (TILE // 16,) * 2, (TILE // 32,) * 2]
     _, Lv = O.level_tables(shapes)
     rng = np.random.Generator(np.random.PCG64(0))
-    params = [{k: torch.from_numpy(v) for k, v in O.make_msda_params(1234 + i).items()} for i in range(6)]
+    enc = {}
+    for i in range(4):
+        for k, v in synthetic.encoder_layer_state(1234 + 10 * i).items():
+            enc[f"encoder.layers.{i}.{k}"] = torch.from_numpy(v)
+    dec = [{k: torch.from_numpy(v) for k, v in O.make_msda_params(1234 + i).items()} for i in range(4, 6)]
     src = torch.from_numpy(O.rng_normal(rng, (n_windows, Lv, 256)))
     pos = torch.from_numpy(O.rng_normal(rng, (1, Lv, 256)))
     tgt = torch.from_numpy(O.rng_normal(rng, (n_windows, 110, 256)))
@@ -145,10 +166,10 @@ def cpu_hot_path(n_windows, threads, repeats=1, warmup=0):
     def one_pass():
         x = src
         for i in range(4):
-            x = O.msda_forward(params[i], x + pos, ref_enc, x, shapes, mask)
+            x = O.encoder_layer_forward(enc, f"encoder.layers.{i}.", x, ref_enc, shapes, mask, pos)
         t = tgt
-        for i in range(4, 6):
-            t = O.msda_forward(params[i], t + qpos, ref_dec, x, shapes, mask)
+        for i in range(2):
+            t = O.msda_forward(dec[i], t + qpos, ref_dec, x, shapes, mask)
         full = O.upsample2x(half)                       # UpHead tail
         return O.ss_inference_tail(full, (TILE, TILE)), t   # softmax + argmax (stitching is index work only)
 
@@ -175,7 +196,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mpix_per_s": ips * TILE * TILE / 1e6,
         "config": {"workload": f"cfg3-shaped: {TILE}x{TILE} windows of 1024x1024 LoveDA scenes, {NC} classes, "
-                               "window 512 stride 384; hot path only (6x MSDA + head tail)",
+                               "window 512 stride 384; hot path only (4-layer encoder + 2 decoder MSDA + head tail)",
                    "note": "reference = CPU restatement of the reference's Paddle op composition (oracle/, torch-CPU "
                            "fp32); PaddlePaddle itself cannot be installed in this image"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
@@ -207,7 +228,7 @@ def run_ours(args):
     ops.device_check()
 
     impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tcgen05": L.IMPL_TCGEN05}[args.gemm]
-    hp = HotPath(dev, TILE, NC, gemm_impl=impl)
+    hp = HotPath(dev, TILE, NC, gemm_impl=impl, full_encoder=not args.msda_only)
     n_img = args.images
     B = n_img * WINDOWS_PER_IMAGE
     plan, H, W = window_tables(n_img)
@@ -343,7 +364,7 @@ def run_ours(args):
         gb = gather_bytes(*enc[0][0]) / 1e9
         ach = gb / (avg_ms * 1e-3)
         roof = {"kernel": "msda_gather_fwd (encoder call, Lq=Lv=%d, B=%d)" % (Lv, B), "bound": "hbm",
-                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": measured_traffic(B),
                 "algorithmic_bytes": gb * 1e9, "avg_launch_ms": avg_ms, "launches_timed": len(enc),
                 "share_of_step": avg_ms * len(enc) / args.steps / ms_step, "peak_source": peak_src}
 
@@ -356,7 +377,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "mpix_per_s": value * TILE * TILE / 1e6,
         "config": {"workload": f"cfg3-shaped: {B} {TILE}x{TILE} windows per GPU per step = {n_img} LoveDA 1024x1024 "
-                               f"scenes (window 512, stride 384), {NC} classes; hot path only (6x MSDA + head tail)",
+                               f"scenes (window 512, stride 384), {NC} classes; hot path only (4-layer encoder + 2 decoder MSDA + head tail)",
                    "windows_per_gpu": B, "tokens_per_window": Lv, "gemm": args.gemm,
                    "l2": f"inputs rotate over {N_SETS} resident sets ({N_SETS * in_bytes / 1e6:.0f} MB > 126 MB L2); "
                          "each step also streams > 1 GB of intermediates",

@@ -1,0 +1,243 @@
+// 3x3 convolution of the encoder layer's conv branch as an implicit GEMM on tcgen05
+// (conv{l}: Conv2D(256, 256, 3, padding 1, no bias), transformer_encoder_decoder.py:125-144,187-189).
+//
+// The tokens [B, Lv, 256] are NHWC per level, so the nine taps are nine SHIFTED TMA loads of the same tensor: a 4-D box
+// {64 ch, W_l, rows, images} whose (x, y) start is the tile origin + (kx-1, ky-1); out-of-map pixels come back as zeros,
+// which is the convolution's zero padding.  Every tap contributes a K = 256 GEMM against its [Cout, Cin] weight slab,
+// all 36 k-blocks accumulating into one TMEM tile: D[128 pixels x 256] = sum_tap A_tap[128 x 256] W_tap^T.
+// Same warp-specialised skeleton as linear_tcgen05.cu (TMA producer / MMA issuer / 8 epilogue warps, two TMEM
+// accumulators, staged TMA-store epilogue); one launch covers the three levels (different weights per level).
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace emrt {
+
+int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
+constexpr int CV_BM = 128, CV_BK = 64, CV_N = 256, CV_STAGES = 4;
+constexpr int CV_EPI_WARP0 = 2, CV_EPI_WARPS = 8, CV_THREADS = 32 * (CV_EPI_WARP0 + CV_EPI_WARPS);
+constexpr int CV_MAX_L = 4;
+
+struct ConvParams {
+  CUtensorMap tma_x[CV_MAX_L];   // level l: {256 ch, W, H, B} bf16, box {64, W, rows, imgs}, SWIZZLE_128B
+  CUtensorMap tma_y[CV_MAX_L];   // level l: {256 ch, H*W, B} bf16, box {32, 32, 1}, SWIZZLE_64B
+  CUtensorMap tma_w;             // [L*9*256, 256] bf16 (row = (l*9 + tap)*256 + cout), box {64, 256}, SWIZZLE_128B
+  int32_t tile_start[CV_MAX_L + 1];
+  int32_t tiles_per_img[CV_MAX_L];   // >= 1 when H*W >= 128, else 0
+  int32_t imgs_per_tile[CV_MAX_L];
+  int32_t rows_per_tile[CV_MAX_L];
+  int32_t W[CV_MAX_L], HW[CV_MAX_L];
+  int32_t L;
+};
+
+struct ConvSmem {
+  __nv_bfloat16 a[CV_STAGES][CV_BM * CV_BK];
+  __nv_bfloat16 b[CV_STAGES][CV_N * CV_BK];
+  uint8_t stage[CV_EPI_WARPS * 32 * 64];
+  uint64_t full[CV_STAGES];
+  uint64_t empty[CV_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+struct ConvTile { int l, b0, y0; };
+__device__ __forceinline__ ConvTile conv_tile(const ConvParams& p, int t) {
+  ConvTile c;
+  c.l = 0;
+  while (c.l + 1 < p.L && t >= p.tile_start[c.l + 1]) ++c.l;
+  const int tl = t - p.tile_start[c.l];
+  if (p.tiles_per_img[c.l] > 0) {
+    c.b0 = tl / p.tiles_per_img[c.l];
+    c.y0 = (tl - c.b0 * p.tiles_per_img[c.l]) * p.rows_per_tile[c.l];
+  } else {
+    c.b0 = tl * p.imgs_per_tile[c.l];
+    c.y0 = 0;
+  }
+  return c;
+}
+
+__device__ __forceinline__ void tma_load_4d_cv(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tile_start[p.L];
+  constexpr uint32_t STAGE_BYTES = (CV_BM * CV_BK + CV_N * CV_BK) * 2;
+  constexpr int KB = CV_N / CV_BK;          // k-blocks per tap (Cin = 256)
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < p.L; ++l) { tma_prefetch_desc(&p.tma_x[l]); tma_prefetch_desc(&p.tma_y[l]); }
+    tma_prefetch_desc(&p.tma_w);
+#pragma unroll
+    for (int i = 0; i < CV_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], CV_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const ConvTile c = conv_tile(p, t);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&s.empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
+            tma_load_4d_cv(s.a[stage], &p.tma_x[c.l], &s.full[stage], kb * CV_BK, kx - 1, c.y0 + ky - 1, c.b0);
+            tma_load_2d(s.b[stage], &p.tma_w, &s.full[stage], kb * CV_BK, (c.l * 9 + tap) * CV_N);
+            if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(CV_BM, CV_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CV_N);
+        for (int ks = 0; ks < 9 * KB; ++ks) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(s.a[stage]));
+          const uint64_t db = make_smem_desc(smem_u32(s.b[stage]));
+#pragma unroll
+          for (int k = 0; k < CV_BK / 16; ++k)
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit(&s.empty[stage]);
+          if (ks == 9 * KB - 1) umma_commit(&s.tmem_full[acc]);
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - CV_EPI_WARP0) >> 2;
+    constexpr int HALF_N = CV_N / 2;
+    const uint32_t stage_addr = smem_u32(s.stage) + (uint32_t)(warp - CV_EPI_WARP0) * (32 * 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const ConvTile c = conv_tile(p, t);
+      mbar_wait(&s.tmem_full[acc], acc_phase);
+      tc_fence_after();
+      // this warp's 32 pixels: tile pixel q*32.. -> (image, pixel inside the level map)
+      const int tp = q * 32;
+      const int img = c.b0 + tp / p.HW[c.l];
+      const int pix = c.y0 * p.W[c.l] + tp % p.HW[c.l];
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CV_N + half * HALF_N);
+#pragma unroll 1
+      for (int cc = 0; cc < HALF_N; cc += 32) {
+        uint32_t r[32];
+        TMEM_LD_X32(t_row + cc, r);
+        TMEM_WAIT_X32(r);
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), EMRT_BF16);
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          sts128(stage_addr + lane * 64 + ((h ^ ((lane >> 1) & 3)) << 4), o[h * 4], o[h * 4 + 1], o[h * 4 + 2], o[h * 4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&p.tma_y[c.l], stage_addr, half * HALF_N + cc, pix, img);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// Returns EMRT_ERR_UNSUPPORTED (error text untouched) for shapes this kernel does not tile.
+int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L, const LevelTable& lv,
+                      cudaStream_t st) {
+  if (C != CV_N || L > CV_MAX_L) return EMRT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(y)) & 15) return EMRT_ERR_UNSUPPORTED;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = L;
+  int tiles = 0;
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l], HW = H * W;
+    if (W > CV_BM || CV_BM % W != 0 || HW % 32 != 0) return EMRT_ERR_UNSUPPORTED;
+    p.W[l] = W; p.HW[l] = HW;
+    p.tile_start[l] = tiles;
+    uint32_t box_rows, box_imgs;
+    if (HW >= CV_BM) {
+      if (HW % CV_BM != 0) return EMRT_ERR_UNSUPPORTED;
+      p.tiles_per_img[l] = HW / CV_BM; p.imgs_per_tile[l] = 1; p.rows_per_tile[l] = CV_BM / W;
+      box_rows = CV_BM / W; box_imgs = 1;
+      tiles += B * p.tiles_per_img[l];
+    } else {
+      if (CV_BM % HW != 0) return EMRT_ERR_UNSUPPORTED;
+      p.tiles_per_img[l] = 0; p.imgs_per_tile[l] = CV_BM / HW; p.rows_per_tile[l] = H;
+      box_rows = H; box_imgs = CV_BM / HW;
+      tiles += (B + p.imgs_per_tile[l] - 1) / p.imgs_per_tile[l];
+    }
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x + (int64_t)lv.start[l] * C;
+    const uint64_t dx[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t sx[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)Lv * C * 2};
+    const uint32_t bx[4] = {(uint32_t)CV_BK, (uint32_t)W, box_rows, box_imgs};
+    if (int e = make_tensor_map(&p.tma_x[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xb, dx, sx, bx, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y + (int64_t)lv.start[l] * C;
+    const uint64_t dy[3] = {(uint64_t)C, (uint64_t)HW, (uint64_t)B};
+    const uint64_t sy[2] = {(uint64_t)C * 2, (uint64_t)Lv * C * 2};
+    const uint32_t by[3] = {32u, 32u, 1u};
+    if (int e = make_tensor_map(&p.tma_y[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, yb, dy, sy, by, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+  }
+  p.tile_start[L] = tiles;
+  const uint64_t dw[2] = {(uint64_t)C, (uint64_t)L * 9 * C};
+  const uint64_t sw[1] = {(uint64_t)C * 2};
+  const uint32_t bw[2] = {(uint32_t)CV_BK, (uint32_t)CV_N};
+  if (int e = make_tensor_map(&p.tma_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  const int smem_bytes = (int)sizeof(ConvSmem) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EMRT_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tokens_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv3x3_tokens_tc_kernel<<<grid, CV_THREADS, smem_bytes, st>>>(p);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+}  // namespace emrt

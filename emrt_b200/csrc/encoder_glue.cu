@@ -1,0 +1,324 @@
+// Glue of TransformerEncoderLayer around the MSDA module (transformer_encoder_decoder.py:184-204):
+//   * y = LayerNorm(x + residual) * gamma + beta (+ post_add)        norm1 / norm2 (:199-200,159-160) and the final
+//                                                                    `src + src_flatten` (:203) folded into norm2's pass
+//   * 3x3 conv branch, reference (SIMT) implementation                conv{l}: Conv2D(256,256,3,pad 1,no bias) (:125-144)
+//   * GroupNorm(32) + exact GELU + skip on the conv output            (:187-189)
+// All of it works on the token layout [B, Lv, C] (NHWC per level), so the reference's seq2_2D / flatten / transpose /
+// concat copies (:163-196) do not exist here.
+#include "common.cuh"
+
+namespace emrt {
+
+// ---- LayerNorm(x + residual) (+ post_add): one warp per row, 16-byte vectors, N <= 1024, N % (32 * VEC) == 0 ----------
+template <typename T, int PER>   // PER = 16-byte vectors per lane
+__global__ void __launch_bounds__(256)
+residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const T* __restrict__ post_add, T* __restrict__ y,
+                          int64_t rows, int N, float eps) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int RPW = PER <= 2 ? 2 : 1;                    // rows per warp in flight (more loads outstanding)
+  const int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW;
+  const int lane = threadIdx.x & 31;
+  if (row0 >= rows) return;
+  float v[RPW][PER][VEC];
+  float s[RPW], ss[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int64_t row = row0 + r < rows ? row0 + r : rows - 1;
+    s[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) Vec16<T>::load(x + row * N + (i * 32 + lane) * VEC, v[r][i]);
+  }
+  if (residual) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int64_t row = row0 + r < rows ? row0 + r : rows - 1;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        float t[VEC];
+        Vec16<T>::load(residual + row * N + (i * 32 + lane) * VEC, t);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[r][i][k] += t[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) s[r] += v[r][i][k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    s[r] /= (float)N;       // mean
+    ss[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { const float d = v[r][i][k] - s[r]; ss[r] = fmaf(d, d, ss[r]); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = (i * 32 + lane) * VEC;
+    float g[VEC], bt[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; k += 4) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c + k));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c + k));
+      g[k] = g4.x; g[k + 1] = g4.y; g[k + 2] = g4.z; g[k + 3] = g4.w;
+      bt[k] = b4.x; bt[k + 1] = b4.y; bt[k + 2] = b4.z; bt[k + 3] = b4.w;
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (row0 + r >= rows) continue;
+      const float rstd = rsqrtf(ss[r] / (float)N + eps);
+      float o[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = (v[r][i][k] - s[r]) * rstd * g[k] + bt[k];
+      if (post_add) {
+        float p[VEC];
+        Vec16<T>::load(post_add + (row0 + r) * N + c, p);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] += p[k];
+      }
+      Vec16<T>::store(y + (row0 + r) * N + c, o);
+    }
+  }
+}
+
+// ---- 3x3 conv on tokens, SIMT reference: one thread per (pixel, 4 output channels) ---------------------------------
+// w: [L][9][Cout][Cin] (tap = ky*3 + kx), the packing emrt_pack_conv3x3_weight produces (TW = float or bf16).
+template <typename T, typename TW>
+__global__ void __launch_bounds__(256)
+conv3x3_tokens_simt_kernel(const T* __restrict__ x, const TW* __restrict__ w, T* __restrict__ y, int B, int Lv, int C,
+                           int L, const __grid_constant__ LevelTable lv) {
+  const int cq = C / 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * Lv * cq) return;
+  const int co = (int)(idx % cq) * 4;
+  const int64_t tok = idx / cq;
+  const int t = (int)(tok % Lv);
+  const int64_t b = tok / Lv;
+  int l = 0;
+  while (l + 1 < L && t >= lv.start[l + 1]) ++l;
+  const int H = lv.H[l], W = lv.W[l];
+  const int py = (t - lv.start[l]) / W, px = (t - lv.start[l]) % W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const T* xp = x + (b * Lv + lv.start[l] + yy * W + xx) * C;
+      const TW* wp = w + (((int64_t)l * 9 + ky * 3 + kx) * C + co) * C;
+      for (int ci = 0; ci < C; ++ci) {
+        const float xv = to_float(xp[ci]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, to_float(wp[(int64_t)j * C + ci]), acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) y[tok * C + co + j] = from_float<T>(acc[j]);
+}
+
+// dst[l][tap][co][ci] = src_l[co][ci][ky][kx] (Paddle Conv2D weight [Cout, Cin, 3, 3]) for one level
+template <typename TD>
+__global__ void pack_conv3x3_kernel(const float* __restrict__ src, TD* __restrict__ dst, int C) {
+  const int64_t n = (int64_t)9 * C * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C);
+    const int co = (int)((i / C) % C);
+    const int tap = (int)(i / ((int64_t)C * C));
+    dst[i] = from_float<TD>(src[((int64_t)co * C + ci) * 9 + tap]);
+  }
+}
+
+// ---- GroupNorm statistics: sum / sum of squares per (batch, level, group) ----------------------------------------------
+// grid (B * L, splits); block 256 threads = (C / 8 groups-of-8-channels lanes) x pixel slots.  fp32 atomics into stats.
+template <typename T>
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int Lv, int C, int L, int G,
+                       const __grid_constant__ LevelTable lv) {
+  const int bl = blockIdx.x, l = bl % L;
+  const int64_t b = bl / L;
+  const int npix = lv.H[l] * lv.W[l];
+  const int vec_per_pix = C / 8;                           // 16-byte vectors of 8 channels (bf16) or 2 x float4
+  const int slots = 256 / vec_per_pix;                     // pixels handled concurrently by the CTA
+  const int v = threadIdx.x % vec_per_pix, slot = threadIdx.x / vec_per_pix;
+  const int cpg = C / G;                                   // channels per group (8 for EMRT)
+  float s = 0.f, ss = 0.f;
+  if (slot < slots) {
+    constexpr int VEC = Vec16<T>::N;
+    for (int p = blockIdx.y * slots + slot; p < npix; p += gridDim.y * slots) {
+      const T* xp = x + ((b * Lv + lv.start[l] + p) * C) + v * 8;
+#pragma unroll
+      for (int j = 0; j < 8 / VEC; ++j) {
+        float a[VEC];
+        Vec16<T>::load(xp + j * VEC, a);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { s += a[k]; ss = fmaf(a[k], a[k], ss); }
+      }
+    }
+  }
+  // reduce over the CTA's pixel slots, then one atomic pair per 8-channel vector
+  __shared__ float sh[256][2];
+  sh[threadIdx.x][0] = s;
+  sh[threadIdx.x][1] = ss;
+  __syncthreads();
+  if (threadIdx.x < vec_per_pix) {
+    for (int k = 1; k < slots; ++k) { s += sh[k * vec_per_pix + threadIdx.x][0]; ss += sh[k * vec_per_pix + threadIdx.x][1]; }
+    // this vector's 8 channels lie in group (v * 8) / cpg (EMRT: cpg == 8, one group per vector)
+    const int g = (v * 8) / cpg;
+    atomicAdd(stats + ((b * L + l) * G + g) * 2, s);
+    atomicAdd(stats + ((b * L + l) * G + g) * 2 + 1, ss);
+  }
+}
+
+// y = gelu((c - mean) * rstd * gamma_l + beta_l) + x   (exact erf GELU, nn.GELU default)
+template <typename T>
+__global__ void __launch_bounds__(256)
+groupnorm_gelu_residual_kernel(const T* __restrict__ conv, const T* __restrict__ x, const float* __restrict__ stats,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
+                               int64_t n_vec, int Lv, int C, int L, int G, float eps,
+                               const __grid_constant__ LevelTable lv) {
+  constexpr int VEC = Vec16<T>::N;
+  const int vec_per_tok = C / VEC;
+  const int cpg = C / G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vec_per_tok) * VEC;
+    const int64_t tok = i / vec_per_tok;
+    const int t = (int)(tok % Lv);
+    const int64_t b = tok / Lv;
+    int l = 0;
+    while (l + 1 < L && t >= lv.start[l + 1]) ++l;
+    const float cnt = (float)(lv.H[l] * lv.W[l] * cpg);
+    float cv[VEC], xv[VEC], o[VEC];
+    Vec16<T>::load(conv + i * VEC, cv);
+    Vec16<T>::load(x + i * VEC, xv);
+    float mean = 0.f, rstd = 0.f;
+    int g_cur = -1;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int c = c0 + k, g = c / cpg;
+      if (g != g_cur) {                       // cpg >= 8 and VEC <= 8: at most one group change per vector
+        const float* st = stats + ((b * L + l) * G + g) * 2;
+        mean = __ldg(st) / cnt;
+        rstd = rsqrtf(fmaxf(__ldg(st + 1) / cnt - mean * mean, 0.f) + eps);
+        g_cur = g;
+      }
+      const float h = (cv[k] - mean) * rstd * __ldg(gamma + l * C + c) + __ldg(beta + l * C + c);
+      o[k] = 0.5f * h * (1.f + erff(h * 0.70710678118654752f)) + xv[k];
+    }
+    Vec16<T>::store(y + i * VEC, o);
+  }
+}
+
+}  // namespace emrt
+
+using namespace emrt;
+
+namespace emrt {
+int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L, const LevelTable& lv,
+                      cudaStream_t st);
+}
+
+extern "C" int emrt_residual_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
+                                       const void* post_add, void* y, int64_t rows, int N, float eps, int dtype,
+                                       void* stream) {
+  EMRT_REQUIRE(x && gamma && beta && y && rows > 0, "bad residual_layernorm arguments");
+  const int vec = dtype == EMRT_F32 ? 4 : 8;
+  EMRT_REQUIRE(N > 0 && N % (32 * vec) == 0 && N / (32 * vec) <= 8, "N must be a multiple of 32 16-byte vectors, at most 8 per lane");
+  cudaStream_t st = as_stream(stream);
+  const int per = N / (32 * vec);
+  const int64_t warps = per <= 2 ? (rows + 1) / 2 : rows;       // RPW rows per warp
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+#define EMRT_LN(T, PER) residual_layernorm_kernel<T, PER><<<blocks, 256, 0, st>>>((const T*)x, (const T*)residual, gamma, beta, (const T*)post_add, (T*)y, rows, N, eps)
+#define EMRT_LN_PER(T)                                                                       \
+  switch (per) {                                                                               \
+    case 1: EMRT_LN(T, 1); break; case 2: EMRT_LN(T, 2); break; case 3: EMRT_LN(T, 3); break;  \
+    case 4: EMRT_LN(T, 4); break; case 5: EMRT_LN(T, 5); break; case 6: EMRT_LN(T, 6); break;  \
+    case 7: EMRT_LN(T, 7); break; default: EMRT_LN(T, 8); break;                               \
+  }
+  if (dtype == EMRT_F32) { EMRT_LN_PER(float) }
+  else if (dtype == EMRT_BF16) { EMRT_LN_PER(__nv_bfloat16) }
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+#undef EMRT_LN_PER
+#undef EMRT_LN
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_pack_conv3x3_weight(const float* src, void* dst, int C, int level, int dst_dtype, void* stream) {
+  EMRT_REQUIRE(src && dst && C > 0 && level >= 0, "bad pack_conv3x3_weight arguments");
+  const int64_t n = (int64_t)9 * C * C;
+  cudaStream_t st = as_stream(stream);
+  if (dst_dtype == EMRT_F32) pack_conv3x3_kernel<float><<<256, 256, 0, st>>>(src, (float*)dst + level * n, C);
+  else if (dst_dtype == EMRT_BF16) pack_conv3x3_kernel<__nv_bfloat16><<<256, 256, 0, st>>>(src, (__nv_bfloat16*)dst + level * n, C);
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dst_dtype %d", dst_dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_conv3x3_tokens_fwd(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L,
+                                       const int32_t* shapes_hw_host, int dtype, int w_dtype, int impl, void* stream) {
+  EMRT_REQUIRE(x && w_packed && y && B > 0 && C > 0 && C % 8 == 0, "bad conv3x3_tokens arguments");
+  LevelTable lv;
+  if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, Lv)) return e;
+  cudaStream_t st = as_stream(stream);
+  if (impl != 1 && dtype == EMRT_BF16 && w_dtype == EMRT_BF16) {
+    const int e = conv3x3_tokens_tc(x, w_packed, y, B, Lv, C, L, lv, st);
+    if (e != EMRT_ERR_UNSUPPORTED) return e;
+    if (impl == 2) return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 conv3x3 does not support this shape");
+  }
+  const int64_t total = (int64_t)B * Lv * (C / 4);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (dtype == EMRT_F32 && w_dtype == EMRT_F32)
+    conv3x3_tokens_simt_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)x, (const float*)w_packed, (float*)y, B, Lv, C, L, lv);
+  else if (dtype == EMRT_BF16 && w_dtype == EMRT_BF16)
+    conv3x3_tokens_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_packed, (__nv_bfloat16*)y, B, Lv, C, L, lv);
+  else return set_error(EMRT_ERR_UNSUPPORTED, "conv3x3_tokens: x / w dtypes must both be F32 or both BF16");
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_groupnorm_gelu_residual(const void* conv, const void* x, const float* gamma, const float* beta,
+                                            void* y, float* stats_workspace, int B, int Lv, int C, int L, int groups,
+                                            float eps, const int32_t* shapes_hw_host, int dtype, void* stream) {
+  EMRT_REQUIRE(conv && x && gamma && beta && y && stats_workspace, "NULL pointer");
+  EMRT_REQUIRE(B > 0 && C > 0 && groups > 0 && C % groups == 0 && C % 8 == 0 && C <= 2048, "bad channel / group counts");
+  const int cpg = C / groups;
+  EMRT_REQUIRE(cpg % 8 == 0 || 8 % cpg == 0, "channels per group must divide or be a multiple of 8");
+  if (8 % cpg == 0 && cpg != 8) return set_error(EMRT_ERR_UNSUPPORTED, "channels per group < 8 not supported");
+  LevelTable lv;
+  if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, Lv)) return e;
+  cudaStream_t st = as_stream(stream);
+  EMRT_CUDA_CHECK(cudaMemsetAsync(stats_workspace, 0, sizeof(float) * 2 * B * L * groups, st));
+  dim3 sgrid((unsigned)(B * L), 16);
+  const int64_t n_elem = (int64_t)B * Lv * C;
+  const int vec = dtype == EMRT_F32 ? 4 : 8;
+  const int64_t n_vec = n_elem / vec;
+  const int64_t want = (n_vec + 255) / 256;
+  const unsigned blocks = (unsigned)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  if (dtype == EMRT_F32) {
+    groupnorm_stats_kernel<float><<<sgrid, 256, 0, st>>>((const float*)conv, stats_workspace, Lv, C, L, groups, lv);
+    count_launch();
+    groupnorm_gelu_residual_kernel<float><<<blocks, 256, 0, st>>>((const float*)conv, (const float*)x, stats_workspace, gamma, beta, (float*)y, n_vec, Lv, C, L, groups, eps, lv);
+  } else if (dtype == EMRT_BF16) {
+    groupnorm_stats_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>((const __nv_bfloat16*)conv, stats_workspace, Lv, C, L, groups, lv);
+    count_launch();
+    groupnorm_gelu_residual_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)conv, (const __nv_bfloat16*)x, stats_workspace, gamma, beta, (__nv_bfloat16*)y, n_vec, Lv, C, L, groups, eps, lv);
+  } else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}

@@ -120,15 +120,11 @@ __device__ __forceinline__ void sample_xy(const WinParams& p, const TL* __restri
 __device__ __forceinline__ int sel3(int l, int a0, int a1, int a2) { return l == 0 ? a0 : (l == 1 ? a1 : a2); }
 
 // Slow path of one point: it left the staged window (|offset| > R) but not the map.  Global loads with the explicit
-// zero-padding weights of make_footprint; out-of-line so the unrolled fast path stays small.
-template <typename TL, int MODE>
-__device__ __noinline__ void slow_point(const WinParams& p, const __nv_bfloat16* __restrict__ value,
-                                        const TL* __restrict__ loc, const TL* __restrict__ attn,
-                                        const float* __restrict__ ref, int64_t ref_bs, int b, int q, int m, int pt, int s,
-                                        uint4* d0, uint4* d1, uint32_t* wp) {
-  float x, y, aw;
-  sample_xy<TL, MODE>(p, loc, attn, ref, ref_bs, b, q, m, pt, x, y, aw);
-  const int l = pt / WIN_P, side = s >> 2;
+// zero-padding weights of make_footprint, from the sample position stage A kept; out-of-line so the unrolled fast path
+// stays small.
+__device__ __noinline__ void slow_point(const WinParams& p, const __nv_bfloat16* __restrict__ value, int b, int m, int l,
+                                        float x, float y, float aw, int s, uint4* d0, uint4* d1, uint32_t* wp) {
+  const int side = s >> 2;
   const Footprint f = make_footprint(x, y, p.lv.H[l], p.lv.W[l]);
   const int64_t plane = ((int64_t)b * p.M + m) * p.Lv * WIN_D;
   const char* base = reinterpret_cast<const char*>(value + plane + (int64_t)p.lv.start[l] * WIN_D) + (s & 3) * 16;
@@ -215,6 +211,7 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
   }
 
   const uint32_t rec_base = smem_base + p.rec_off + (uint32_t)warp * (WIN_QPB * WIN_LP * 16);
+  const uint32_t xy_base = smem_base + p.rec_off + (uint32_t)WIN_WARPS * (WIN_QPB * WIN_LP * 16) + (uint32_t)warp * (WIN_QPB * WIN_LP * 8);
   const int g = lane >> 3, s = lane & 7, side = s >> 2;
 
   // ---- per-lane stage-A constants: round r handles (query qi[r], point pt[r]) of every batch ------------------------
@@ -286,9 +283,13 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
         const float gx = 1.f - fx, gy = 1.f - fy;
         const bool fast = live && inwin;
         // not live: weight 0 on the zero block.  live but outside the window: same, plus the SLOW flag
-        // not live: weight 0 on the zero block.  live but outside the window: same, with the SLOW flag (= weights -0.0)
+        // not live: weight 0 on the zero block.  live but outside the window: the zero block again (so the fast path adds
+        // nothing), the SLOW flag in the sign bit of the bottom weight, the attention weight in the low half and the sample
+        // position in the side buffer for the fix-up
         const uint32_t addr = fast ? a_base[r] + (uint32_t)(wy * a_ww[r] + wx) * (WIN_D * 2) : smem_base;
-        const uint32_t wnone = live ? WIN_SLOW : 0u;
+        const uint32_t wnone = live ? (WIN_SLOW | (pack_bf16(aw, 0.f) & 0xffffu)) : 0u;
+        if (live && !inwin)
+          asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(xy_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 8), "f"(x), "f"(y) : "memory");
         const uint32_t wl = fast ? pack_bf16(gx * gy * aw, gx * fy * aw) : wnone;   // left pixel: top, bottom
         const uint32_t wr = fast ? pack_bf16(fx * gy * aw, fx * fy * aw) : wnone;   // right pixel: top, bottom
         sts128(rec_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 16, addr, wl, addr, wr);
@@ -348,8 +349,10 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
 #pragma unroll
           for (int k = 1; k < WIN_P; ++k) { if (pp == k) w = wpair[k]; }
           if (w & WIN_SLOW) {
+            float sx, sy;
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(sx), "=f"(sy) : "r"(xy_base + (uint32_t)(g * WIN_LP + l * WIN_P + pp) * 8));
             uint4 e0, e1;
-            slow_point<TL, MODE>(p, value, loc, attn, ref, ref_bs, b, q, m, l * WIN_P + pp, s, &e0, &e1, &w);
+            slow_point(p, value, b, m, l, sx, sy, __uint_as_float(w << 16), s, &e0, &e1, &w);
             fma_row<0>(acc, e0, w);
             fma_row<1>(acc, e1, w);
           }
@@ -434,7 +437,7 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
   }
   p.rec_off = off;
   const int warps = env_int("EMRT_WIN_WARPS", 8) == 12 ? 12 : 8;
-  const size_t smem_bytes = (size_t)off + (size_t)warps * WIN_QPB * WIN_LP * 16;
+  const size_t smem_bytes = (size_t)off + (size_t)warps * WIN_QPB * WIN_LP * (16 + 8);   // records + slow-point positions
   if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(value) & 15) != 0) return EMRT_ERR_UNSUPPORTED;
   const bool px = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;

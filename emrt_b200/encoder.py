@@ -1,0 +1,128 @@
+"""Host-side mirror of the reference's encoder around the MSDA module:
+  * ``TransformerEncoderLayer`` — src/models/EMRT_utils/transformer_encoder_decoder.py:109-204
+  * ``TransformerEncoder``      — :207-239
+Same constructor arguments, sub-layer names (state-dict keys: ``self_attn.*``, ``norm1``, ``linear1``, ``linear2``,
+``norm2``, ``conv{0,1,2}.0.weight`` [Cout,Cin,3,3], ``conv{l}.1.weight/bias`` GroupNorm) and forward signatures.
+Inference only (dropout is the identity in eval mode); all arithmetic runs in libemrt_b200.so on the token layout
+[B, Lv, C], so the reference's seq2_2D / flatten / transpose / concat copies (:163-196) do not exist here.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .msda import MSDeformableAttention, PaddleLinear, shapes_to_host
+from .refpoints import get_reference_points
+
+
+class _Norm(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n))
+        self.bias = nn.Parameter(torch.zeros(n))
+
+
+class _ConvGN(nn.Module):
+    """nn.Sequential(Conv2D(C, C, 3, padding=1, bias_attr=False), GroupNorm(32, C), GELU()) parameter container with the
+    reference's key names ``0.weight``, ``1.weight``, ``1.bias``."""
+
+    def __init__(self, c):
+        super().__init__()
+        conv = nn.Module()
+        conv.weight = nn.Parameter(torch.empty(c, c, 3, 3))
+        nn.init.kaiming_uniform_(conv.weight, a=math.sqrt(5))
+        self.add_module("0", conv)
+        self.add_module("1", _Norm(c))
+
+
+class TransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model=256, n_head=8, dim_feedforward=1024, dropout=0.1, activation="relu", n_levels=4,
+                 n_points=4, weight_attr=None, bias_attr=None):
+        super().__init__()
+        if activation != "relu":
+            raise L.EmrtError("emrt_b200.TransformerEncoderLayer implements the reference's activation='relu' only")
+        self.d_model, self.n_levels = d_model, n_levels
+        self.self_attn = MSDeformableAttention(d_model, n_head, n_levels, n_points)
+        self.norm1 = _Norm(d_model)
+        self.linear1 = PaddleLinear(d_model, dim_feedforward)
+        self.linear2 = PaddleLinear(dim_feedforward, d_model)
+        self.norm2 = _Norm(d_model)
+        for l in range(3):                                   # the reference hard-codes conv0..conv2 (:125-144)
+            self.add_module(f"conv{l}", _ConvGN(d_model))
+        nn.init.xavier_uniform_(self.linear1.weight)
+        nn.init.xavier_uniform_(self.linear2.weight)
+        self.gemm_impl = L.IMPL_AUTO
+        self._packed = None
+
+    def _version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _packed_weights(self, dtype):
+        ver = (self._version(), dtype)
+        if self._packed is not None and self._packed[0] == ver:
+            return self._packed[1]
+        convs = [getattr(self, f"conv{l}") for l in range(3)]
+        f32 = lambda t: t.detach().float().contiguous()
+        pk = dict(conv_w=ops.pack_conv3x3_weights([getattr(c, "0").weight for c in convs], dtype),
+                  gn_w=torch.stack([f32(getattr(c, "1").weight) for c in convs]).contiguous(),
+                  gn_b=torch.stack([f32(getattr(c, "1").bias) for c in convs]).contiguous(),
+                  n1w=f32(self.norm1.weight), n1b=f32(self.norm1.bias), n2w=f32(self.norm2.weight),
+                  n2b=f32(self.norm2.bias), b1=f32(self.linear1.bias), b2=f32(self.linear2.bias))
+        if dtype == torch.bfloat16:
+            C_, F_ = self.d_model, self.linear1.weight.shape[1]
+            w1 = torch.empty((F_, C_), dtype=torch.bfloat16, device=self.linear1.weight.device)
+            w2 = torch.empty((C_, F_), dtype=torch.bfloat16, device=self.linear1.weight.device)
+            ops.pack_weight(f32(self.linear1.weight), w1)
+            ops.pack_weight(f32(self.linear2.weight), w2)
+            pk.update(w1=w1, w2=w2)
+        self._packed = (ver, pk)
+        return pk
+
+    @torch.no_grad()
+    def forward(self, src, reference_points, spatial_shapes, src_mask=None, pos_embed=None):
+        shapes = shapes_to_host(spatial_shapes)
+        if len(shapes) != 3:
+            raise L.EmrtError("the reference's encoder layer is written for 3 feature levels (conv0..conv2)")
+        src = src.contiguous()
+        pk = self._packed_weights(src.dtype)
+        fast = src.dtype == torch.bfloat16
+        impl = self.gemm_impl if fast else L.IMPL_SIMT
+        # conv branch (:185-196): conv3x3 -> GroupNorm(32) -> GELU, + skip, on the token layout
+        conv = ops.conv3x3_tokens(src, pk["conv_w"], shapes, impl=L.IMPL_AUTO if impl != L.IMPL_SIMT else L.IMPL_SIMT)
+        branch = ops.groupnorm_gelu_residual(conv, src, pk["gn_w"], pk["gn_b"], shapes, groups=32, out=conv)
+        # self attention (:198) + norm1 (:199-200)
+        q = src if pos_embed is None else ops.add_bcast(src, pos_embed.to(src.dtype).contiguous())
+        src2 = self.self_attn(q, reference_points, src, shapes, src_mask)
+        x = ops.residual_layernorm(src2, src, pk["n1w"], pk["n1b"], out=src2)
+        # ffn (:157-160) + the layer's final add of the conv branch (:203)
+        if fast:
+            h = ops.linear(x, pk["w1"], pk["b1"], w_transposed=True, epilogue=L.EPI_RELU, impl=impl)
+            f = ops.linear(h, pk["w2"], pk["b2"], w_transposed=True, impl=impl)
+        else:
+            h = ops.linear(x, self.linear1.weight.detach(), pk["b1"], epilogue=L.EPI_RELU, impl=L.IMPL_SIMT)
+            f = ops.linear(h, self.linear2.weight.detach(), pk["b2"], impl=L.IMPL_SIMT)
+        return ops.residual_layernorm(f, x, pk["n2w"], pk["n2b"], post_add=branch, out=f)
+
+
+class TransformerEncoder(nn.Module):
+    """transformer_encoder_decoder.py:207-239: reference points once (cached constant), then the layers."""
+
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        import copy
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])   # _get_clones
+        self.num_layers = num_layers
+
+    get_reference_points = staticmethod(get_reference_points)
+
+    @torch.no_grad()
+    def forward(self, src, spatial_shapes, src_mask=None, pos_embed=None, valid_ratios=None):
+        output = src
+        reference_points = get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        for layer in self.layers:
+            output = layer(output, reference_points, spatial_shapes, src_mask, pos_embed)
+        return output

@@ -1,7 +1,8 @@
-"""The hot path as one callable: 4 encoder + 2 decoder MSDeformableAttention calls (paddle_EMRT.py:242-250,
-transformer_encoder_decoder.py:198,288) followed by the head tail (x2 upsample + sliding-window stitch + softmax +
-argmax; paddle_EMRT.py:178-180, src/api/infer.py:69-79,150-154).  The LayerNorm / FFN / conv glue between the
-attention calls is a "next" row and is not part of this step."""
+"""The hot path as one callable: the TransformerEncoder (4 layers: conv branch + MSDeformableAttention + LayerNorm + FFN,
+transformer_encoder_decoder.py:109-239), the 2 decoder cross-attention MSDeformableAttention calls (:288), and the head
+tail (x2 upsample + sliding-window stitch + softmax + argmax; paddle_EMRT.py:178-180, src/api/infer.py:69-79,150-154).
+The decoder's 110-token self-attention / LayerNorm / FFN glue is a "next" row and is not part
+of this step.  ``full_encoder=False`` gives the bare 4 + 2 MSDA calls (the round-1 starting definition)."""
 from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
@@ -18,7 +19,7 @@ from . import synthetic
 
 class HotPath:
     def __init__(self, device, tile=512, num_classes=7, embed_dim=256, num_heads=8, num_points=6, num_enc=4,
-                 num_dec=2, num_queries=110, seed=1234, gemm_impl=L.IMPL_AUTO):
+                 num_dec=2, num_queries=110, seed=1234, gemm_impl=L.IMPL_AUTO, full_encoder=True):
         self.device = device
         self.tile, self.nc, self.C = tile, num_classes, embed_dim
         self.shapes = synthetic.level_shapes(tile)
@@ -35,6 +36,21 @@ class HotPath:
                     getattr(getattr(m, mod), leaf).copy_(torch.from_numpy(arr))
             m.gemm_impl = gemm_impl
             (self.enc if i < num_enc else self.dec).append(m)
+        self.encoder = None
+        if full_encoder:
+            from .encoder import TransformerEncoder, TransformerEncoderLayer
+            enc = TransformerEncoder(TransformerEncoderLayer(embed_dim, num_heads, 1024, 0.1, "relu", len(self.shapes),
+                                                             num_points), num_enc)
+            with torch.no_grad():
+                for i, layer in enumerate(enc.layers):
+                    st = synthetic.encoder_layer_state(seed + 10 * i, embed_dim, 1024, num_heads, len(self.shapes), num_points)
+                    sd = layer.state_dict()
+                    for k in sd:
+                        sd[k].copy_(torch.from_numpy(st[k]))
+                    layer.gemm_impl = gemm_impl
+                    layer.self_attn.gemm_impl = gemm_impl
+            self.encoder = enc.to(device).requires_grad_(False)
+            self.shapes_t = torch.tensor(self.shapes)
         rng = np.random.Generator(np.random.PCG64(seed + 100))
         self.ref_enc = refpoints.get_reference_points(self.shapes, device=device)   # cached + tagged pixel_grid
         ref_dec = rng.uniform(0.05, 0.95, size=(1, num_queries, 1, 2)).astype(np.float32)
@@ -44,9 +60,12 @@ class HotPath:
     def msda_stack(self, src, pos, tgt, qpos, mask=None):
         """src [B,Lv,C], pos [1|B,Lv,C], tgt [B,Nq,C], qpos [1,Nq,C] -> (memory [B,Lv,C], hs [B,Nq,C])."""
         x = src
-        for m in self.enc:
-            q = ops.add_bcast(x, pos)                              # with_pos_embed (t_e_d.py:198)
-            x = m(q, self.ref_enc, x, self.shapes, mask)
+        if self.encoder is not None:
+            x = self.encoder(x, self.shapes, mask, pos)           # reference points cached inside (t_e_d.py:230-239)
+        else:
+            for m in self.enc:
+                q = ops.add_bcast(x, pos)                          # with_pos_embed (t_e_d.py:198)
+                x = m(q, self.ref_enc, x, self.shapes, mask)
         t = tgt
         for m in self.dec:
             q = ops.add_bcast(t, qpos)                             # t_e_d.py:288

@@ -9,6 +9,7 @@ Paddle is not installable in this image, so the tensor container here is torch (
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -22,16 +23,21 @@ _shape_cache = {}
 
 def shapes_to_host(value_spatial_shapes) -> Tuple[Tuple[int, int], ...]:
     """The reference passes an int64 Tensor [L,2] and calls .tolist()/.numpy() on it >= 3 times per forward
-    (utils.py:77,82; t_e_d.py:81,167-169 — each a device sync).  We read it once and cache by storage."""
+    (utils.py:77,82; t_e_d.py:81,167-169 — each a device sync).  A CUDA tensor is read once and remembered for as long as
+    that very tensor object is alive and unmodified (weak reference + version counter, so a recycled address can never
+    alias a stale entry); CPU tensors and sequences are cheap to read every time."""
     if isinstance(value_spatial_shapes, torch.Tensor):
-        key = (value_spatial_shapes.data_ptr(), value_spatial_shapes._version, tuple(value_spatial_shapes.shape))
-        hit = _shape_cache.get(key)
-        if hit is None:
-            hit = tuple((int(h), int(w)) for h, w in value_spatial_shapes.tolist())
-            if len(_shape_cache) > 64:
-                _shape_cache.clear()
-            _shape_cache[key] = hit
-        return hit
+        t = value_spatial_shapes
+        if not t.is_cuda:
+            return tuple((int(h), int(w)) for h, w in t.tolist())
+        hit = _shape_cache.get(id(t))
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            return hit[2]
+        val = tuple((int(h), int(w)) for h, w in t.tolist())
+        if len(_shape_cache) > 64:
+            _shape_cache.clear()
+        _shape_cache[id(t)] = (weakref.ref(t), t._version, val)
+        return val
     return tuple((int(h), int(w)) for h, w in value_spatial_shapes)
 
 

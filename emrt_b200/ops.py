@@ -202,6 +202,51 @@ def add_layernorm(x, residual, gamma, beta, eps=1e-5, out=None):
     return out
 
 
+def residual_layernorm(x, residual, gamma, beta, post_add=None, eps=1e-5, out=None):
+    """y = LayerNorm(x + residual) * gamma + beta (+ post_add) over the last dim (t_e_d.py:199-200,159-160,203)."""
+    N = x.shape[-1]
+    rows = x.numel() // N
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().emrt_residual_layernorm(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(post_add), _ptr(out),
+                                             rows, N, float(eps), _dt(x), _stream()))
+    return out
+
+
+def pack_conv3x3_weights(weights, dtype):
+    """[Cout,Cin,3,3] fp32 per level (Paddle Conv2D layout) -> [L, 9, Cout, Cin] `dtype` conv operand."""
+    C = weights[0].shape[0]
+    dst = torch.empty((len(weights), 9, C, C), dtype=dtype, device=weights[0].device)
+    for l, w in enumerate(weights):
+        assert tuple(w.shape) == (C, C, 3, 3)
+        L.check(L.load().emrt_pack_conv3x3_weight(_ptr(w.detach().float().contiguous()), _ptr(dst), C, l, _DT[dtype], _stream()))
+    return dst
+
+
+def conv3x3_tokens(x, w_packed, shapes, impl=L.IMPL_AUTO, out=None):
+    """Per-level 3x3 conv (pad 1, no bias) on tokens x [B, Lv, C]; w_packed from pack_conv3x3_weights."""
+    B, Lv, C = x.shape
+    hw, _, total = level_tables(shapes)
+    assert total == Lv
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().emrt_conv3x3_tokens_fwd(_ptr(x), _ptr(w_packed), _ptr(out), B, Lv, C, len(shapes), hw, _dt(x),
+                                             _dt(w_packed), int(impl), _stream()))
+    return out
+
+
+def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, out=None):
+    """GELU(GroupNorm_l(conv)) + x per level; gamma / beta f32 [L, C]."""
+    B, Lv, C = x.shape
+    hw, _, _ = level_tables(shapes)
+    if out is None:
+        out = torch.empty_like(x)
+    ws = torch.empty((2 * B * len(shapes) * groups,), dtype=torch.float32, device=x.device)
+    L.check(L.load().emrt_groupnorm_gelu_residual(_ptr(conv), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(ws), B, Lv,
+                                                  C, len(shapes), groups, float(eps), hw, _dt(x), _stream()))
+    return out
+
+
 def add_bcast(a, b, out=None):
     """out = a + b with b broadcast over leading dims (b.numel() divides a.numel()): with_pos_embed."""
     if out is None:

@@ -49,3 +49,32 @@ def encoder_reference_points(shapes) -> np.ndarray:
 def level_shapes(tile: int):
     """C3..C5 feature-map shapes of a tile x tile input (strides 8/16/32; paddle_EMRT.py:254)."""
     return [(tile // 8, tile // 8), (tile // 16, tile // 16), (tile // 32, tile // 32)]
+
+
+def encoder_layer_state(seed=1234, C=256, ffn=1024, heads=8, levels=3, points=6) -> Dict[str, np.ndarray]:
+    """Non-trivial TransformerEncoderLayer weights with the reference's state-dict keys and Paddle layouts
+    (transformer_encoder_decoder.py:109-147): Linear [in,out], Conv2D [out,in,3,3], norm affine gamma ~ U(0.5,1.5),
+    beta ~ N(0,0.1)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f = np.float32
+    p: Dict[str, np.ndarray] = {}
+    for k, v in msda_state(int(rng.integers(1 << 30)), C, heads, levels, points).items():
+        p["self_attn." + k] = v
+
+    def norm(name):
+        p[name + ".weight"] = rng.uniform(0.5, 1.5, size=(C,)).astype(f)
+        p[name + ".bias"] = (rng.standard_normal((C,)) * 0.1).astype(f)
+
+    def linear(name, i, o):
+        b = math.sqrt(6.0 / (i + o))
+        p[name + ".weight"] = rng.uniform(-b, b, (i, o)).astype(f)
+        p[name + ".bias"] = rng.uniform(-0.1, 0.1, (o,)).astype(f)
+    norm("norm1")
+    linear("linear1", C, ffn)
+    linear("linear2", ffn, C)
+    norm("norm2")
+    for l in range(3):
+        b = math.sqrt(6.0 / (2 * 9 * C))
+        p[f"conv{l}.0.weight"] = rng.uniform(-b, b, (C, C, 3, 3)).astype(f)
+        norm(f"conv{l}.1")
+    return p

@@ -158,6 +158,29 @@ int emrt_msda_softmax_loc(const float* off_raw, int64_t off_ld, const float* log
 int emrt_add_layernorm(const void* x, const void* residual, const float* gamma, const float* beta, void* y,
                        int64_t rows, int N, float eps, int dtype, void* stream);
 
+/* ---- TransformerEncoderLayer glue (transformer_encoder_decoder.py:184-204) -------------
+ * y = LayerNorm(x + residual) * gamma + beta (+ post_add): norm1 / norm2 (:199-200, :159-160) with the layer's final
+ * `src + src_flatten` (:203) folded in as post_add.  residual / post_add may be NULL.  dtype F32|BF16 (x, residual,
+ * post_add, y); N a multiple of 128 (F32) / 256 (BF16), <= 8 16-byte vectors per lane.                                      */
+int emrt_residual_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
+                            const void* post_add, void* y, int64_t rows, int N, float eps, int dtype, void* stream);
+
+/* Pack one level's Conv2D weight (Paddle layout [Cout, Cin, 3, 3], F32) into the conv operand
+ * dst[level][tap = ky*3+kx][Cout][Cin] (dst_dtype F32|BF16; dst holds all levels, 9*C*C elements each).             */
+int emrt_pack_conv3x3_weight(const float* src, void* dst, int C, int level, int dst_dtype, void* stream);
+
+/* The conv branch's convolutions (conv{l}: 3x3, stride 1, zero padding 1, no bias, :125-144) applied per level directly
+ * on the token layout: x, y [B, Lv, C] (dtype F32|BF16), level l using w_packed[l].  BF16 runs the tcgen05 implicit
+ * GEMM (nine shifted TMA loads per tile; C = 256); impl: 0 = auto, 1 = force SIMT, 2 = force tcgen05.                  */
+int emrt_conv3x3_tokens_fwd(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L,
+                            const int32_t* shapes_hw_host, int dtype, int w_dtype, int impl, void* stream);
+
+/* y = GELU(GroupNorm_l(conv)) + x per level (GroupNorm(groups, C) eps, exact erf GELU, :187-189); conv, x, y
+ * [B, Lv, C] (dtype F32|BF16); gamma, beta F32 [L, C]; stats_workspace F32 [2 * B * L * groups] (scratch).         */
+int emrt_groupnorm_gelu_residual(const void* conv, const void* x, const float* gamma, const float* beta, void* y,
+                                 float* stats_workspace, int B, int Lv, int C, int L, int groups, float eps,
+                                 const int32_t* shapes_hw_host, int dtype, void* stream);
+
 /* out[i] = a[i] + b[i % b_period]: with_pos_embed (transformer_encoder_decoder.py:154-155,198,283,288);
  * b_period = n for a plain add, Lq*C for a batch-shared positional embedding.  dtype F32|BF16.             */
 int emrt_add_bcast(const void* a, const void* b, void* out, int64_t n, int64_t b_period, int dtype,

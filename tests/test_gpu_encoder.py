@@ -1,0 +1,140 @@
+"""GPU parity of the encoder-layer glue: LayerNorm fusions, the 3x3 conv branch (SIMT and
+tcgen05 implicit GEMM), GroupNorm + GELU + skip, and the whole TransformerEncoderLayer / TransformerEncoder against
+the oracle's restatement of transformer_encoder_decoder.py:109-239."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle as O
+import emrt_b200
+from emrt_b200 import ops, _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, want):
+    want = torch.as_tensor(want).double()
+    return ((got.detach().double().cpu() - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("dtype,N", [(torch.float32, 256), (torch.bfloat16, 256), (torch.float32, 1024), (torch.bfloat16, 512)])
+def test_residual_layernorm(cuda_dev, dtype, N):
+    rng = np.random.Generator(np.random.PCG64(N))
+    rows = 777
+    x, r, pa = (torch.from_numpy(O.rng_normal(rng, (rows, N))).to(dtype) for _ in range(3))
+    g = torch.from_numpy(rng.uniform(0.5, 1.5, size=(N,)).astype(np.float32))
+    b = torch.from_numpy(O.rng_normal(rng, (N,), 0.1))
+    want = F.layer_norm(x.double() + r.double(), (N,), g.double(), b.double(), 1e-5) + pa.double()
+    d = lambda t: t.to(cuda_dev)
+    got = ops.residual_layernorm(d(x), d(r), d(g), d(b), post_add=d(pa))
+    assert rel_err(got.float(), want) < (1e-5 if dtype == torch.float32 else 1e-2)
+    got2 = ops.residual_layernorm(d(x), None, d(g), d(b))
+    assert rel_err(got2.float(), F.layer_norm(x.double(), (N,), g.double(), b.double(), 1e-5)) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+def _conv_ref(x_tok, weights, shapes, dtype=torch.float64):
+    """per-level F.conv2d on tokens [B, Lv, C] -> tokens (oracle formulation, t_e_d.py:163-196)."""
+    B, Lv, C = x_tok.shape
+    start, _ = O.level_tables(shapes)
+    outs = []
+    for l, (h, w) in enumerate(shapes):
+        x = x_tok[:, start[l]:start[l] + h * w].to(dtype).permute(0, 2, 1).reshape(B, C, h, w)
+        y = F.conv2d(x, weights[l].to(dtype), None, 1, 1)
+        outs.append(y.flatten(2).permute(0, 2, 1))
+    return torch.cat(outs, 1)
+
+
+@pytest.mark.parametrize("tile,B", [(512, 3), (256, 3), (256, 4), (128, 5)])
+def test_conv3x3_tokens_tcgen05_and_simt(cuda_dev, tile, B):
+    """Implicit-GEMM conv (nine shifted TMA loads, zero padding from the tensor map) vs F.conv2d in float64 on the
+    bf16-rounded operands; the SIMT kernel on the same data as cross-check.  B odd + a 64-pixel level exercises the
+    two-images-per-tile box with an out-of-range image."""
+    shapes = [(tile // 8,) * 2, (tile // 16,) * 2, (tile // 32,) * 2]
+    C = 256
+    rng = np.random.Generator(np.random.PCG64(tile + B))
+    _, Lv = O.level_tables(shapes)
+    x = torch.from_numpy(O.rng_normal(rng, (B, Lv, C))).bfloat16()
+    ws = [torch.from_numpy(O.rng_uniform(rng, (C, C, 3, 3), 0.05)) for _ in shapes]
+    want = _conv_ref(x.float(), [w.bfloat16().float() for w in ws], shapes)
+    wp = ops.pack_conv3x3_weights([w.to(cuda_dev) for w in ws], torch.bfloat16)
+    got_simt = ops.conv3x3_tokens(x.to(cuda_dev), wp, shapes, impl=L.IMPL_SIMT)
+    assert rel_err(got_simt.float(), want) < 1e-2
+    if tile >= 256:
+        got_tc = ops.conv3x3_tokens(x.to(cuda_dev), wp, shapes, impl=L.IMPL_TCGEN05)
+        assert rel_err(got_tc.float(), want) < 1e-2
+        assert rel_err(got_tc.float(), got_simt.float().cpu()) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_groupnorm_gelu_residual(cuda_dev, dtype):
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    B, C = 3, 256
+    rng = np.random.Generator(np.random.PCG64(9))
+    start, Lv = O.level_tables(shapes)
+    conv = torch.from_numpy(O.rng_normal(rng, (B, Lv, C), 2.0) + 0.5).to(dtype)
+    x = torch.from_numpy(O.rng_normal(rng, (B, Lv, C))).to(dtype)
+    gw = torch.from_numpy(rng.uniform(0.5, 1.5, size=(3, C)).astype(np.float32))
+    gb = torch.from_numpy(O.rng_normal(rng, (3, C), 0.1))
+    outs = []
+    for l, (h, w) in enumerate(shapes):
+        c = conv[:, start[l]:start[l] + h * w].double().permute(0, 2, 1).reshape(B, C, h, w)
+        y = F.gelu(F.group_norm(c, 32, gw[l].double(), gb[l].double(), 1e-5))
+        outs.append(y.flatten(2).permute(0, 2, 1) + x[:, start[l]:start[l] + h * w].double())
+    want = torch.cat(outs, 1)
+    d = lambda t: t.to(cuda_dev)
+    got = ops.groupnorm_gelu_residual(d(conv), d(x), d(gw), d(gb), shapes)
+    assert rel_err(got.float(), want) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
+def _load_layer(layer, params, prefix):
+    with torch.no_grad():
+        sd = layer.state_dict()
+        for k in sd:
+            sd[k].copy_(torch.as_tensor(params[prefix + k]))
+    return layer
+
+
+def test_encoder_layer_fp32_matches_oracle(cuda_dev):
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    B, C = 2, 256
+    params = O.make_encoder_decoder_params(21, num_enc=1, num_dec=0)
+    rng = np.random.Generator(np.random.PCG64(22))
+    _, Lv = O.level_tables(shapes)
+    src = torch.from_numpy(O.rng_normal(rng, (B, Lv, C)))
+    pos = torch.from_numpy(O.rng_normal(rng, (B, Lv, C), 0.5))
+    ref = O.encoder_reference_points(shapes, B)
+    p64 = {k: torch.as_tensor(v).double() for k, v in params.items()}
+    want = O.encoder_layer_forward(p64, "encoder.layers.0.", src.double(), ref.double(), shapes, torch.ones(B, Lv).double(), pos.double())
+    layer = _load_layer(emrt_b200.TransformerEncoderLayer(C, 8, 1024, 0.1, "relu", 3, 6), params, "encoder.layers.0.").to(cuda_dev)
+    d = lambda t: t.to(cuda_dev)
+    got = layer(d(src), d(ref), torch.tensor(shapes), d(torch.ones(B, Lv)), d(pos))
+    assert rel_err(got, want) < 2e-4
+
+
+@pytest.mark.parametrize("tile", [256, 512])
+def test_encoder_bf16_two_layers_matches_oracle(cuda_dev, tile):
+    """TransformerEncoder (reference points + 2 layers) in bf16 on the B200 path (tcgen05 conv / projections / FFN,
+    window-staged gather) vs the float64 oracle on bf16-rounded inputs and weights."""
+    shapes = [(tile // 8,) * 2, (tile // 16,) * 2, (tile // 32,) * 2]
+    B, C = 2, 256
+    params = O.make_encoder_decoder_params(23, num_enc=2, num_dec=0)
+    rng = np.random.Generator(np.random.PCG64(24))
+    _, Lv = O.level_tables(shapes)
+    r16 = lambda a: torch.as_tensor(a).bfloat16()
+    src = r16(O.rng_normal(rng, (B, Lv, C), 0.5))
+    pos = r16(O.rng_normal(rng, (1, Lv, C), 0.5))
+    p64 = {k: (r16(v).double() if v.ndim >= 2 else torch.as_tensor(v).double()) for k, v in params.items()}
+    ref = O.encoder_reference_points(shapes, B).double()
+    want = src.double()
+    for i in range(2):
+        want = O.encoder_layer_forward(p64, f"encoder.layers.{i}.", want, ref, shapes, torch.ones(B, Lv).double(),
+                                       pos.double().expand(B, -1, -1))
+    layer = emrt_b200.TransformerEncoderLayer(C, 8, 1024, 0.1, "relu", 3, 6)
+    enc = emrt_b200.TransformerEncoder(layer, 2)
+    for i in range(2):
+        _load_layer(enc.layers[i], params, f"encoder.layers.{i}.")
+    enc = enc.to(cuda_dev)
+    got = enc(src.to(cuda_dev), torch.tensor(shapes), None, pos.to(cuda_dev))
+    assert got.dtype == torch.bfloat16
+    assert rel_err(got.float(), want) < 3e-2

@@ -140,3 +140,17 @@ def test_two_rank_gloo_gradient_buckets_average_in_place():
     out = mgr.dict()
     mp.spawn(_grad_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_shapes_to_host_never_returns_a_stale_entry():
+    """Regression: the shape cache used to be keyed on data_ptr, so a NEW tensor that reused a freed tensor's address got
+    the old shapes.  CPU tensors are read every time; equal-looking temporaries must give their own values."""
+    import torch
+    from emrt_b200.msda import shapes_to_host
+    seen = []
+    for shapes in ([(32, 32), (16, 16), (8, 8)], [(64, 64), (32, 32), (16, 16)], [(8, 6), (4, 3), (2, 2)]):
+        t = torch.tensor(shapes)
+        seen.append(shapes_to_host(t))
+        del t
+    assert seen == [((32, 32), (16, 16), (8, 8)), ((64, 64), (32, 32), (16, 16)), ((8, 6), (4, 3), (2, 2))]
+    assert shapes_to_host([(5, 9)]) == ((5, 9),)
