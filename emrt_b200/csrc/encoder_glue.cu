@@ -186,42 +186,43 @@ groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int L
 }
 
 // y = gelu((c - mean) * rstd * gamma_l + beta_l) + x   (exact erf GELU, nn.GELU default)
+// grid (ceil(Lv * C / VEC / 256), B): 32-bit index math, one (mean, rstd) per 16-byte vector (VEC <= channels per group)
 template <typename T>
 __global__ void __launch_bounds__(256)
 groupnorm_gelu_residual_kernel(const T* __restrict__ conv, const T* __restrict__ x, const float* __restrict__ stats,
                                const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
-                               int64_t n_vec, int Lv, int C, int L, int G, float eps,
-                               const __grid_constant__ LevelTable lv) {
+                               int Lv, int C, int L, int G, float eps, const __grid_constant__ LevelTable lv) {
   constexpr int VEC = Vec16<T>::N;
-  const int vec_per_tok = C / VEC;
+  const uint32_t vec_per_tok = (uint32_t)C / VEC;
+  const uint32_t vi = blockIdx.x * 256u + threadIdx.x;           // vector index inside this image
+  if (vi >= (uint32_t)Lv * vec_per_tok) return;
+  const uint32_t t = vi / vec_per_tok;
+  const int c0 = (int)(vi - t * vec_per_tok) * VEC;
+  const int b = blockIdx.y;
+  int l = 0;
+  while (l + 1 < L && (int)t >= lv.start[l + 1]) ++l;
   const int cpg = C / G;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vec_per_tok) * VEC;
-    const int64_t tok = i / vec_per_tok;
-    const int t = (int)(tok % Lv);
-    const int64_t b = tok / Lv;
-    int l = 0;
-    while (l + 1 < L && t >= lv.start[l + 1]) ++l;
-    const float cnt = (float)(lv.H[l] * lv.W[l] * cpg);
-    float cv[VEC], xv[VEC], o[VEC];
-    Vec16<T>::load(conv + i * VEC, cv);
-    Vec16<T>::load(x + i * VEC, xv);
-    float mean = 0.f, rstd = 0.f;
-    int g_cur = -1;
+  const float inv_cnt = 1.f / (float)(lv.H[l] * lv.W[l] * cpg);
+  const float* st = stats + ((b * L + l) * G + c0 / cpg) * 2;   // VEC <= cpg: the whole vector lies in one group
+  const float mean = __ldg(st) * inv_cnt;
+  const float rstd = rsqrtf(fmaxf(__ldg(st + 1) * inv_cnt - mean * mean, 0.f) + eps);
+  const int64_t off = ((int64_t)b * Lv * vec_per_tok + vi) * VEC;
+  float cv[VEC], xv[VEC], o[VEC], g[VEC], bt[VEC];
+  Vec16<T>::load(conv + off, cv);
+  Vec16<T>::load(x + off, xv);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const int c = c0 + k, g = c / cpg;
-      if (g != g_cur) {                       // cpg >= 8 and VEC <= 8: at most one group change per vector
-        const float* st = stats + ((b * L + l) * G + g) * 2;
-        mean = __ldg(st) / cnt;
-        rstd = rsqrtf(fmaxf(__ldg(st + 1) / cnt - mean * mean, 0.f) + eps);
-        g_cur = g;
-      }
-      const float h = (cv[k] - mean) * rstd * __ldg(gamma + l * C + c) + __ldg(beta + l * C + c);
-      o[k] = 0.5f * h * (1.f + erff(h * 0.70710678118654752f)) + xv[k];
-    }
-    Vec16<T>::store(y + i * VEC, o);
+  for (int k = 0; k < VEC; k += 4) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + l * C + c0 + k));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + l * C + c0 + k));
+    g[k] = g4.x; g[k + 1] = g4.y; g[k + 2] = g4.z; g[k + 3] = g4.w;
+    bt[k] = b4.x; bt[k + 1] = b4.y; bt[k + 2] = b4.z; bt[k + 3] = b4.w;
   }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float h = (cv[k] - mean) * rstd * g[k] + bt[k];
+    o[k] = 0.5f * h * (1.f + erff(h * 0.70710678118654752f)) + xv[k];
+  }
+  Vec16<T>::store(y + off, o);
 }
 
 }  // namespace emrt
@@ -305,19 +306,17 @@ extern "C" int emrt_groupnorm_gelu_residual(const void* conv, const void* x, con
   cudaStream_t st = as_stream(stream);
   EMRT_CUDA_CHECK(cudaMemsetAsync(stats_workspace, 0, sizeof(float) * 2 * B * L * groups, st));
   dim3 sgrid((unsigned)(B * L), 16);
-  const int64_t n_elem = (int64_t)B * Lv * C;
   const int vec = dtype == EMRT_F32 ? 4 : 8;
-  const int64_t n_vec = n_elem / vec;
-  const int64_t want = (n_vec + 255) / 256;
-  const unsigned blocks = (unsigned)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  EMRT_REQUIRE((int64_t)Lv * (C / vec) < (1LL << 31) && B <= 65535, "image too large for the GroupNorm apply grid");
+  dim3 agrid((unsigned)(((int64_t)Lv * (C / vec) + 255) / 256), (unsigned)B);
   if (dtype == EMRT_F32) {
     groupnorm_stats_kernel<float><<<sgrid, 256, 0, st>>>((const float*)conv, stats_workspace, Lv, C, L, groups, lv);
     count_launch();
-    groupnorm_gelu_residual_kernel<float><<<blocks, 256, 0, st>>>((const float*)conv, (const float*)x, stats_workspace, gamma, beta, (float*)y, n_vec, Lv, C, L, groups, eps, lv);
+    groupnorm_gelu_residual_kernel<float><<<agrid, 256, 0, st>>>((const float*)conv, (const float*)x, stats_workspace, gamma, beta, (float*)y, Lv, C, L, groups, eps, lv);
   } else if (dtype == EMRT_BF16) {
     groupnorm_stats_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>((const __nv_bfloat16*)conv, stats_workspace, Lv, C, L, groups, lv);
     count_launch();
-    groupnorm_gelu_residual_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)conv, (const __nv_bfloat16*)x, stats_workspace, gamma, beta, (__nv_bfloat16*)y, n_vec, Lv, C, L, groups, eps, lv);
+    groupnorm_gelu_residual_kernel<__nv_bfloat16><<<agrid, 256, 0, st>>>((const __nv_bfloat16*)conv, (const __nv_bfloat16*)x, stats_workspace, gamma, beta, (__nv_bfloat16*)y, Lv, C, L, groups, eps, lv);
   } else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
