@@ -225,6 +225,53 @@ groupnorm_gelu_residual_kernel(const T* __restrict__ conv, const T* __restrict__
   Vec16<T>::store(y + off, o);
 }
 
+
+// ---- input_proj glue (EncoderDecoder.forward, transformer_encoder_decoder.py:417-436) ---------------------------------
+// y[b, p, c] = x[b, c, p]: backbone feature maps / PSP tokens arrive NCHW ([B, C, H*W]); the path works on tokens.
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_tokens_kernel(const T* __restrict__ x, T* __restrict__ y, int C, int P) {
+  __shared__ T tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    if (c < C && p < P) tile[i][tx] = x[(b * C + c) * P + p];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (c < C && p < P) y[(b * P + p) * C + c] = tile[tx][i];
+  }
+}
+
+// GroupNorm(groups, C) of one level's tokens x [B, P, C] (no activation), written into the level's slot of the
+// concatenated token tensor: y + b * y_batch_stride + p * C.  Statistics come from groupnorm_stats_kernel (L = 1).
+template <typename T>
+__global__ void __launch_bounds__(256)
+groupnorm_tokens_kernel(const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, T* __restrict__ y, int64_t y_batch_stride, int P, int C, int G,
+                        float eps) {
+  constexpr int VEC = Vec16<T>::N;
+  const uint32_t vec_per_tok = (uint32_t)C / VEC;
+  const uint32_t vi = blockIdx.x * 256u + threadIdx.x;
+  if (vi >= (uint32_t)P * vec_per_tok) return;
+  const uint32_t t = vi / vec_per_tok;
+  const int c0 = (int)(vi - t * vec_per_tok) * VEC;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  const float inv_cnt = 1.f / (float)(P * cpg);
+  const float* st = stats + (b * G + c0 / cpg) * 2;
+  const float mean = __ldg(st) * inv_cnt;
+  const float rstd = rsqrtf(fmaxf(__ldg(st + 1) * inv_cnt - mean * mean, 0.f) + eps);
+  float v[VEC], o[VEC];
+  Vec16<T>::load(x + ((int64_t)b * P * vec_per_tok + vi) * VEC, v);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) o[k] = (v[k] - mean) * rstd * __ldg(gamma + c0 + k) + __ldg(beta + c0 + k);
+  Vec16<T>::store(y + (int64_t)b * y_batch_stride + (int64_t)t * C + c0, o);
+}
+
 }  // namespace emrt
 
 using namespace emrt;
@@ -317,6 +364,44 @@ extern "C" int emrt_groupnorm_gelu_residual(const void* conv, const void* x, con
     groupnorm_stats_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>((const __nv_bfloat16*)conv, stats_workspace, Lv, C, L, groups, lv);
     count_launch();
     groupnorm_gelu_residual_kernel<__nv_bfloat16><<<agrid, 256, 0, st>>>((const __nv_bfloat16*)conv, (const __nv_bfloat16*)x, stats_workspace, gamma, beta, (__nv_bfloat16*)y, Lv, C, L, groups, eps, lv);
+  } else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_nchw_to_tokens(const void* x, void* y, int B, int C, int P, int dtype, void* stream) {
+  EMRT_REQUIRE(x && y && B > 0 && C > 0 && P > 0 && B <= 65535, "bad nchw_to_tokens arguments");
+  dim3 grid((P + 31) / 32, (C + 31) / 32, B);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == EMRT_F32) nchw_to_tokens_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, C, P);
+  else if (dtype == EMRT_BF16) nchw_to_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, C, P);
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_groupnorm_tokens(const void* x, const float* gamma, const float* beta, void* y,
+                                     int64_t y_batch_stride, float* stats_workspace, int B, int P, int C, int groups,
+                                     float eps, int dtype, void* stream) {
+  EMRT_REQUIRE(x && gamma && beta && y && stats_workspace, "NULL pointer");
+  EMRT_REQUIRE(B > 0 && B <= 65535 && P > 0 && C > 0 && groups > 0 && C % groups == 0 && (C / groups) % 8 == 0 && C <= 2048,
+               "bad shape: channels per group must be a multiple of 8");
+  LevelTable lv;
+  const int32_t hw[2] = {P, 1};
+  if (int e = fill_levels(lv, 1, hw, nullptr, P)) return e;
+  cudaStream_t st = as_stream(stream);
+  EMRT_CUDA_CHECK(cudaMemsetAsync(stats_workspace, 0, sizeof(float) * 2 * B * groups, st));
+  dim3 sgrid((unsigned)B, 16);
+  const int vec = dtype == EMRT_F32 ? 4 : 8;
+  dim3 agrid((unsigned)(((int64_t)P * (C / vec) + 255) / 256), (unsigned)B);
+  if (dtype == EMRT_F32) {
+    groupnorm_stats_kernel<float><<<sgrid, 256, 0, st>>>((const float*)x, stats_workspace, P, C, 1, groups, lv);
+    count_launch();
+    groupnorm_tokens_kernel<float><<<agrid, 256, 0, st>>>((const float*)x, stats_workspace, gamma, beta, (float*)y, y_batch_stride, P, C, groups, eps);
+  } else if (dtype == EMRT_BF16) {
+    groupnorm_stats_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>((const __nv_bfloat16*)x, stats_workspace, P, C, 1, groups, lv);
+    count_launch();
+    groupnorm_tokens_kernel<__nv_bfloat16><<<agrid, 256, 0, st>>>((const __nv_bfloat16*)x, stats_workspace, gamma, beta, (__nv_bfloat16*)y, y_batch_stride, P, C, groups, eps);
   } else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;

@@ -1,0 +1,245 @@
+"""Host-side mirror of the reference's decoder and of EncoderDecoder:
+  * ``MultiHeadAttention``       — src/models/EMRT_utils/layers.py:144-311 (fused in_proj_weight [C, 3C], out_proj)
+  * ``TransformerDecoderLayer``  — src/models/EMRT_utils/transformer_encoder_decoder.py:242-295
+  * ``TransformerDecoder``       — :298-334
+  * ``EncoderDecoder``           — :337-473 (input_proj 1x1 conv + GroupNorm, sine position embedding + level embed,
+                                    query embeddings, reference-point Linear + sigmoid, encoder, decoder)
+Same constructor arguments, parameter names (state-dict keys) and forward signatures; inference only.  All arithmetic on
+activations runs in libemrt_b200.so; what is computed on the host is input-independent and cached: the sine position
+embedding (position_encoding.py:51-75 with an all-ones mask) + level embedding, and the decoder reference points
+sigmoid(Linear(query_pos_embed.weight)) (:466) — functions of the weights and the level shapes only.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .encoder import TransformerEncoder, TransformerEncoderLayer, _Norm
+from .msda import MSDeformableAttention, PaddleLinear, shapes_to_host
+
+
+def position_embedding_sine_host(h: int, w: int, num_pos_feats=128, temperature=10000.0, offset=-0.5, eps=1e-6,
+                                 scale=2.0 * math.pi) -> np.ndarray:
+    """PositionEmbedding.forward (position_encoding.py:51-75) for an all-ones mask, float32 -> [h*w, 2*num_pos_feats]
+    (pos_y | pos_x), token-major (the `.flatten(2).transpose([0, 2, 1])` of t_e_d.py:446 already applied)."""
+    f = np.float32
+    y_embed = np.cumsum(np.ones((h, w), f), 0, dtype=f)
+    x_embed = np.cumsum(np.ones((h, w), f), 1, dtype=f)
+    y_embed = (y_embed + f(offset)) / (y_embed[-1:, :] + f(eps)) * f(scale)
+    x_embed = (x_embed + f(offset)) / (x_embed[:, -1:] + f(eps)) * f(scale)
+    dim_t = (2 * (np.arange(num_pos_feats) // 2)).astype(f)
+    dim_t = np.power(f(temperature), dim_t / f(num_pos_feats)).astype(f)
+    pos_x = x_embed[..., None] / dim_t
+    pos_y = y_embed[..., None] / dim_t
+    pos_x = np.stack((np.sin(pos_x[..., 0::2]), np.cos(pos_x[..., 1::2])), axis=3).reshape(h, w, -1)
+    pos_y = np.stack((np.sin(pos_y[..., 0::2]), np.cos(pos_y[..., 1::2])), axis=3).reshape(h, w, -1)
+    return np.concatenate((pos_y, pos_x), axis=2).reshape(h * w, -1).astype(f)
+
+
+class MultiHeadAttention(nn.Module):
+    """Parameter container + forward of layers.py:144-311 (self-attention use: q = k = tgt + pos, value = tgt)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0):
+        super().__init__()
+        self.embed_dim, self.num_heads = embed_dim, num_heads
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == self.embed_dim, "embed_dim must be divisible by num_heads"
+        self.in_proj_weight = nn.Parameter(torch.empty(embed_dim, 3 * embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = PaddleLinear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.xavier_uniform_(self.out_proj.weight)
+
+
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model=256, n_head=8, dim_feedforward=1024, dropout=0.1, activation="relu", n_levels=3,
+                 n_points=4, weight_attr=None, bias_attr=None):
+        super().__init__()
+        if activation != "relu":
+            raise L.EmrtError("emrt_b200.TransformerDecoderLayer implements the reference's activation='relu' only")
+        self.d_model, self.n_head = d_model, n_head
+        self.self_attn = MultiHeadAttention(d_model, n_head, dropout=dropout)
+        self.norm1 = _Norm(d_model)
+        self.cross_attn = MSDeformableAttention(d_model, n_head, n_levels, n_points)
+        self.norm2 = _Norm(d_model)
+        self.linear1 = PaddleLinear(d_model, dim_feedforward)
+        self.linear2 = PaddleLinear(dim_feedforward, d_model)
+        self.norm3 = _Norm(d_model)
+        nn.init.xavier_uniform_(self.linear1.weight)
+        nn.init.xavier_uniform_(self.linear2.weight)
+        self.gemm_impl = L.IMPL_AUTO
+        self._packed = None
+
+    def _packed_weights(self, dtype):
+        ver = (tuple((p.data_ptr(), p._version) for p in self.parameters()), dtype)
+        if self._packed is not None and self._packed[0] == ver:
+            return self._packed[1]
+        C_ = self.d_model
+        f32 = lambda t: t.detach().float().contiguous()
+        sa = self.self_attn
+        pk = dict(b_qk=f32(sa.in_proj_bias[:2 * C_]), b_v=f32(sa.in_proj_bias[2 * C_:]), b_o=f32(sa.out_proj.bias),
+                  b1=f32(self.linear1.bias), b2=f32(self.linear2.bias))
+        for i, n in ((1, self.norm1), (2, self.norm2), (3, self.norm3)):
+            pk[f"n{i}w"], pk[f"n{i}b"] = f32(n.weight), f32(n.bias)
+        srcs = dict(w_qk=sa.in_proj_weight[:, :2 * C_], w_v=sa.in_proj_weight[:, 2 * C_:], w_o=sa.out_proj.weight,
+                    w1=self.linear1.weight, w2=self.linear2.weight)
+        for name, w in srcs.items():
+            w = f32(w)
+            if dtype == torch.bfloat16:       # K-major bf16 [out, in] operands for the tcgen05 GEMMs
+                dst = torch.empty((w.shape[1], w.shape[0]), dtype=torch.bfloat16, device=w.device)
+                pk[name] = ops.pack_weight(w, dst)
+            else:
+                pk[name] = w                  # Paddle [in, out] layout, fp32 SIMT path
+        self._packed = (ver, pk)
+        return pk
+
+    @torch.no_grad()
+    def forward(self, tgt, reference_points, memory, memory_spatial_shapes, memory_mask=None, query_pos_embed=None):
+        shapes = shapes_to_host(memory_spatial_shapes)
+        tgt = tgt.contiguous()
+        fast = tgt.dtype == torch.bfloat16
+        impl = self.gemm_impl if fast else L.IMPL_SIMT
+        pk = self._packed_weights(tgt.dtype)
+        C_, M = self.d_model, self.n_head
+        lin = lambda x, w, b, **kw: ops.linear(x, pk[w], pk[b], w_transposed=fast, impl=impl, **kw)
+        pos = None if query_pos_embed is None else query_pos_embed.to(tgt.dtype).contiguous()
+        with_pos = lambda t: t if pos is None else ops.add_bcast(t, pos)
+        # self attention over the query tokens (layers.py:282-301): q = k = tgt + pos, value = tgt
+        qk = lin(with_pos(tgt), "w_qk", "b_qk")
+        v = lin(tgt, "w_v", "b_v")
+        att = ops.mha_small(qk[..., :C_], qk[..., C_:], v, M, float(C_ // M) ** -0.5)
+        tgt2 = lin(att, "w_o", "b_o")
+        tgt = ops.residual_layernorm(tgt2, tgt, pk["n1w"], pk["n1b"], out=tgt2)
+        # cross attention into the encoder memory
+        tgt2 = self.cross_attn(with_pos(tgt), reference_points, memory, shapes, memory_mask)
+        tgt = ops.residual_layernorm(tgt2, tgt, pk["n2w"], pk["n2b"], out=tgt2)
+        # ffn
+        h = lin(tgt, "w1", "b1", epilogue=L.EPI_RELU)
+        f = lin(h, "w2", "b2")
+        return ops.residual_layernorm(f, tgt, pk["n3w"], pk["n3b"], out=f)
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, decoder_layer, num_layers, return_intermediate=False):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(decoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.return_intermediate = return_intermediate
+
+    @torch.no_grad()
+    def forward(self, tgt, memory, reference_points, memory_spatial_shapes, memory_mask=None, query_pos_embed=None,
+                valid_ratios=None):
+        output = tgt
+        intermediate = []
+        for layer in self.layers:
+            output = layer(output, reference_points, memory, memory_spatial_shapes, memory_mask, query_pos_embed)
+            if self.return_intermediate:
+                intermediate.append(output)
+        if self.return_intermediate:
+            return torch.stack(intermediate)
+        return output.unsqueeze(0)
+
+
+class _InputProj(nn.Module):
+    """nn.Sequential(Conv2D(Cin, C, 1), GroupNorm(32, C)) parameter container (keys ``0.weight``, ``0.bias``,
+    ``1.weight``, ``1.bias``)."""
+
+    def __init__(self, cin, c):
+        super().__init__()
+        conv = nn.Module()
+        conv.weight = nn.Parameter(torch.empty(c, cin, 1, 1))
+        conv.bias = nn.Parameter(torch.zeros(c))
+        nn.init.xavier_uniform_(conv.weight)
+        self.add_module("0", conv)
+        self.add_module("1", _Norm(c))
+
+
+class _Embedding(nn.Module):
+    def __init__(self, n, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(n, c))
+
+
+class EncoderDecoder(nn.Module):
+    def __init__(self, num_queries=110, position_embed_type="sine", return_intermediate_dec=False,
+                 backbone_num_channels=(512, 1024, 2048), num_feature_levels=3, nclass=6, num_encoder_points=4,
+                 num_decoder_points=4, hidden_dim=256, nhead=8, num_encoder_layers=6, num_decoder_layers=4,
+                 dim_feedforward=1024, dropout=0.1, activation="relu", lr_mult=0.1, weight_attr=None, bias_attr=None):
+        super().__init__()
+        if position_embed_type != "sine":
+            raise L.EmrtError("emrt_b200.EncoderDecoder implements position_embed_type='sine' (what EMRT uses)")
+        if len(backbone_num_channels) != num_feature_levels:
+            raise L.EmrtError("extra stride-2 input_proj levels (t_e_d.py:380-387) are not used by EMRT and not built")
+        self.hidden_dim, self.nhead, self.num_feature_levels = hidden_dim, nhead, num_feature_levels
+        self.encoder = TransformerEncoder(TransformerEncoderLayer(hidden_dim, nhead, dim_feedforward, dropout, activation,
+                                                                  num_feature_levels, num_encoder_points), num_encoder_layers)
+        self.decoder = TransformerDecoder(TransformerDecoderLayer(hidden_dim, nhead, dim_feedforward, dropout, activation,
+                                                                  num_feature_levels, num_decoder_points),
+                                          num_decoder_layers, return_intermediate_dec)
+        self.level_embed = _Embedding(num_feature_levels, hidden_dim)
+        self.tgt_embed = _Embedding(num_queries, hidden_dim)            # present in the checkpoint, never used (:368)
+        self.query_pos_embed = _Embedding(num_queries, hidden_dim)
+        self.reference_points = PaddleLinear(hidden_dim, 2)
+        self.input_proj = nn.ModuleList([_InputProj(c, hidden_dim) for c in backbone_num_channels])
+        self._const = None
+
+    def _constants(self, shapes, device, dtype):
+        """Input-independent tensors of the forward: position + level embedding [1, Lv, C], decoder reference points
+        [1, Nq, L, 2], query position embedding [1, Nq, C], packed input_proj weights."""
+        ver = (shapes, str(device), dtype, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        if self._const is not None and self._const[0] == ver:
+            return self._const[1]
+        C_ = self.hidden_dim
+        lvl = self.level_embed.weight.detach().float().cpu().numpy()
+        pos = np.concatenate([position_embedding_sine_host(h, w, C_ // 2) + lvl[l][None] for l, (h, w) in enumerate(shapes)], 0)
+        qpe = self.query_pos_embed.weight.detach().float().cpu().numpy()
+        rp = qpe @ self.reference_points.weight.detach().float().cpu().numpy() + self.reference_points.bias.detach().float().cpu().numpy()
+        rp = (1.0 / (1.0 + np.exp(-rp.astype(np.float64)))).astype(np.float32)                        # F.sigmoid (:466)
+        rp = np.ascontiguousarray(np.broadcast_to(rp[None, :, None, :], (1, rp.shape[0], len(shapes), 2)))
+        c = dict(pos=torch.from_numpy(pos[None]).to(device).to(dtype).contiguous(),
+                 ref_dec=torch.from_numpy(rp).to(device),
+                 qpos=torch.from_numpy(qpe[None]).to(device).to(dtype).contiguous(), w=[], b=[], gw=[], gb=[])
+        for ip in self.input_proj:
+            conv, gn = getattr(ip, "0"), getattr(ip, "1")
+            w_kn = conv.weight.detach().float().reshape(conv.weight.shape[0], -1).t().contiguous()     # [Cin, C] = [in, out]
+            if dtype == torch.bfloat16:
+                dst = torch.empty((w_kn.shape[1], w_kn.shape[0]), dtype=torch.bfloat16, device=w_kn.device)
+                c["w"].append(ops.pack_weight(w_kn, dst))
+            else:
+                c["w"].append(w_kn)
+            c["b"].append(conv.bias.detach().float().contiguous())
+            c["gw"].append(gn.weight.detach().float().contiguous())
+            c["gb"].append(gn.bias.detach().float().contiguous())
+        self._const = (ver, c)
+        return c
+
+    @torch.no_grad()
+    def forward(self, src_feats: Sequence[torch.Tensor], src_psp, src_mask=None):
+        if src_mask is not None:
+            raise L.EmrtError("EMRT never passes src_mask (paddle_EMRT.py:265); the masked path is not built")
+        x0 = src_feats[0]
+        B, dtype, dev = x0.shape[0], x0.dtype, x0.device
+        shapes = tuple((int(f.shape[2]), int(f.shape[3])) for f in src_feats)
+        Lv = sum(h * w for h, w in shapes)
+        c = self._constants(shapes, dev, dtype)
+        fast = dtype == torch.bfloat16
+        # input_proj (:417-419): 1x1 conv as a GEMM on tokens, GroupNorm written straight into the level's token slot
+        src = torch.empty((B, Lv, self.hidden_dim), dtype=dtype, device=dev)
+        off = 0
+        for l, f in enumerate(src_feats):
+            tok = ops.nchw_to_tokens(f)
+            y = ops.linear(tok, c["w"][l], c["b"][l], w_transposed=fast, impl=L.IMPL_AUTO if fast else L.IMPL_SIMT)
+            ops.groupnorm_tokens_into(y, c["gw"][l], c["gb"][l], src, off, groups=32)
+            off += shapes[l][0] * shapes[l][1]
+        mask = torch.ones((B, Lv), dtype=torch.float32, device=dev)                    # mask_flatten (:451)
+        memory = self.encoder(src, shapes, mask, c["pos"])
+        tgt = ops.nchw_to_tokens(src_psp)                                              # src_psp.transpose([0, 2, 1]) (:469)
+        hs = self.decoder(tgt, memory, c["ref_dec"], shapes, mask, c["qpos"])
+        return hs, memory

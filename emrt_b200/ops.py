@@ -247,6 +247,40 @@ def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, o
     return out
 
 
+def nchw_to_tokens(x):
+    """[B, C, *spatial] -> tokens [B, prod(spatial), C]."""
+    B, C_ = x.shape[:2]
+    P = x.numel() // (B * C_)
+    y = torch.empty((B, P, C_), dtype=x.dtype, device=x.device)
+    L.check(L.load().emrt_nchw_to_tokens(_ptr(x.contiguous()), _ptr(y), B, C_, P, _dt(x), _stream()))
+    return y
+
+
+def groupnorm_tokens_into(x, gamma, beta, out, token_offset, groups=32, eps=1e-5):
+    """GroupNorm of one level's tokens x [B, P, C] written into out[:, token_offset:token_offset+P, :] (out [B, Lv, C])."""
+    B, P, C_ = x.shape
+    assert out.is_contiguous() and out.shape[0] == B and out.shape[2] == C_ and out.dtype == x.dtype
+    ws = torch.empty((2 * B * groups,), dtype=torch.float32, device=x.device)
+    dst = C.c_void_p(out.data_ptr() + token_offset * C_ * out.element_size())
+    L.check(L.load().emrt_groupnorm_tokens(_ptr(x), _ptr(gamma), _ptr(beta), dst, out.shape[1] * C_, _ptr(ws), B, P, C_,
+                                           groups, float(eps), _dt(x), _stream()))
+    return out
+
+
+def mha_small(q, k, v, num_heads, scale):
+    """softmax(scale * q k^T) v per head on projected q/k/v [B, L, C] (last-dim-contiguous views allowed) -> [B, Lq, C]."""
+    B, Lq, C_ = q.shape
+    Lk = k.shape[1]
+    for t in (q, k, v):
+        if not t.is_cuda or t.stride(-1) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise L.EmrtError("mha_small needs CUDA tensors with unit inner stride and a uniform row stride")
+    out = torch.empty((B, Lq, C_), dtype=q.dtype, device=q.device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    L.check(L.load().emrt_mha_small(p(q), q.stride(1), p(k), k.stride(1), p(v), v.stride(1), _ptr(out), B, Lq, Lk,
+                                    num_heads, C_ // num_heads, float(scale), _dt(q), _stream()))
+    return out
+
+
 def add_bcast(a, b, out=None):
     """out = a + b with b broadcast over leading dims (b.numel() divides a.numel()): with_pos_embed."""
     if out is None:

@@ -181,6 +181,23 @@ int emrt_groupnorm_gelu_residual(const void* conv, const void* x, const float* g
                                  float* stats_workspace, int B, int Lv, int C, int L, int groups, float eps,
                                  const int32_t* shapes_hw_host, int dtype, void* stream);
 
+/* ---- input_proj glue (EncoderDecoder.forward, transformer_encoder_decoder.py:417-436,469) --------------------------
+ * y[b, p, c] = x[b, c, p]: NCHW feature maps [B, C, P = H*W] (or src_psp [B, 256, 110]) -> tokens [B, P, C].            */
+int emrt_nchw_to_tokens(const void* x, void* y, int B, int C, int P, int dtype, void* stream);
+
+/* GroupNorm(groups, C) of one level's projected tokens x [B, P, C] (input_proj[i][1], no activation) written into that
+ * level's slot of the concatenated token tensor: y + b * y_batch_stride + p * C (y_batch_stride in elements = Lv * C).
+ * stats_workspace F32 [2 * B * groups].                                                                               */
+int emrt_groupnorm_tokens(const void* x, const float* gamma, const float* beta, void* y, int64_t y_batch_stride,
+                          float* stats_workspace, int B, int P, int C, int groups, float eps, int dtype, void* stream);
+
+/* ---- TransformerDecoderLayer self-attention core (MultiHeadAttention, src/models/EMRT_utils/layers.py:282-301) ------
+ * out[b,q,m*D+d] = sum_k softmax_k(scale * <Q[b,q,m,:], K[b,k,m,:]>) V[b,k,m,d] on the projected q / k / v in the token
+ * layout [B, L, M*D] with row strides q_ld / k_ld / v_ld (elements), so a fused [q | k] projection is read in place.
+ * out [B, Lq, M*D] contiguous.  Built for the decoder's 110 query tokens: D = 32, Lk <= 256.  dtype F32|BF16.        */
+int emrt_mha_small(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, void* out,
+                   int B, int Lq, int Lk, int M, int D, float scale, int dtype, void* stream);
+
 /* out[i] = a[i] + b[i % b_period]: with_pos_embed (transformer_encoder_decoder.py:154-155,198,283,288);
  * b_period = n for a plain add, Lq*C for a batch-shared positional embedding.  dtype F32|BF16.             */
 int emrt_add_bcast(const void* a, const void* b, void* out, int64_t n, int64_t b_period, int dtype,

@@ -154,3 +154,26 @@ def test_shapes_to_host_never_returns_a_stale_entry():
         del t
     assert seen == [((32, 32), (16, 16), (8, 8)), ((64, 64), (32, 32), (16, 16)), ((8, 6), (4, 3), (2, 2))]
     assert shapes_to_host([(5, 9)]) == ((5, 9),)
+
+
+@pytest.mark.parametrize("h,w", [(64, 64), (8, 6), (5, 9)])
+def test_position_embedding_host_mirror_equals_oracle(h, w):
+    """PositionEmbedding (position_encoding.py:51-75, all-ones mask) host constant == the oracle restatement."""
+    import numpy as np
+    import oracle as O
+    from emrt_b200.decoder import position_embedding_sine_host
+    got = position_embedding_sine_host(h, w, 128)
+    want = O.position_embedding_sine(h, w, 128).numpy().reshape(h * w, 256)
+    assert got.shape == (h * w, 256) and np.abs(got - want).max() < 1e-6
+
+
+def test_encoder_decoder_state_dict_keys_match_the_reference_layout():
+    """The mirror's parameter names / shapes are the reference's (the oracle's generator lists them with Paddle key
+    names): a checkpoint's EncoderDecoder sub-dict loads without renaming."""
+    import oracle as O
+    import emrt_b200
+    m = emrt_b200.EncoderDecoder(110, "sine", False, (512, 1024, 2048), 3, 6, 6, 6, 256, 8, 4, 2, 1024)
+    p = O.make_encoder_decoder_params(1, num_enc=4, num_dec=2)
+    sd = m.state_dict()
+    assert set(sd) == set(p)
+    assert all(tuple(sd[k].shape) == tuple(p[k].shape) for k in sd)
