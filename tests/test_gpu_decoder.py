@@ -93,7 +93,8 @@ def test_encoder_decoder_bf16_matches_oracle(cuda_dev):
     rng = np.random.Generator(np.random.PCG64(44))
     feats, psp = _features(rng, 2, 256, torch.bfloat16)
     r16 = lambda v: torch.as_tensor(v).bfloat16().double()
-    p64 = {k: (r16(v) if v.ndim >= 2 and not k.endswith("embed.weight") else torch.as_tensor(v).double()) for k, v in params.items()}
+    keep = lambda k: k.endswith("embed.weight") or k == "reference_points.weight"     # host-side fp32 constants in our path
+    p64 = {k: (r16(v) if v.ndim >= 2 and not keep(k) else torch.as_tensor(v).double()) for k, v in params.items()}
     whs, wmem, _ = O.encoder_decoder_forward(p64, [f.double() for f in feats], psp.double(), num_enc=4, num_dec=2)
     m = emrt_b200.EncoderDecoder(110, "sine", False, (512, 1024, 2048), 3, 6, 6, 6, 256, 8, 4, 2, 1024)
     m = _load(m, params).to(cuda_dev)

@@ -1,0 +1,188 @@
+"""GPU parity against vectors produced by the REFERENCE'S OWN CODE (tests/golden/ref_*.npz; generator:
+tests/golden/make_reference_vectors.py — the reference's unmodified sources executed on oracle/paddle_on_torch.py).
+Every call goes through the public mirrors in emrt_b200 (and so through the C ABI).  fp32 path: 1e-4 relative
+(BASELINE.json); bf16 path: 1e-2 relative L2 / labels >= 99.9 %; integer work bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import emrt_b200
+from emrt_b200 import ops
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLD)
+import make_reference_vectors as G  # noqa: E402
+
+load = lambda name: np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def rel_err(got, want):
+    want = torch.as_tensor(np.asarray(want)).double()
+    return ((got.detach().double().cpu() - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+def l2_err(got, want):
+    want = torch.as_tensor(np.asarray(want)).double()
+    return ((got.detach().double().cpu() - want).norm() / want.norm()).item()
+
+
+def _load(module, params, prefix=""):
+    with torch.no_grad():
+        sd = module.state_dict()
+        for k in sd:
+            sd[k].copy_(torch.as_tensor(params[prefix + k]))
+    return module
+
+
+def test_msda_init_matches_reference(cuda_dev):
+    g = load("ref_msda_init")
+    m = emrt_b200.MSDeformableAttention(256, 8, 3, 6)
+    sd = m.state_dict()
+    assert np.abs(sd["sampling_offsets.bias"].numpy() - g["sampling_offsets_bias"]).max() < 1e-6
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(g["shape." + k]), k
+    assert float(sd["sampling_offsets.weight"].abs().max()) == 0 and float(sd["attention_weights.weight"].abs().max()) == 0
+    assert float(sd["attention_weights.bias"].abs().max()) == 0 and float(sd["value_proj.bias"].abs().max()) == 0
+    assert float(sd["value_proj.weight"].abs().max()) <= float(g["xavier_bound"]) * (1 + 1e-6)
+
+
+def test_msda_forward_fp32_matches_reference(cuda_dev):
+    g, c = load("ref_msda"), G.msda_inputs()
+    m = _load(emrt_b200.MSDeformableAttention(c["C"], c["M"], len(c["shapes"]), c["P"]), c["params"]).to(cuda_dev)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    got = m(d(c["query"]), d(c["ref"]), d(c["value"]), torch.tensor(c["shapes"]), d(c["mask"]))
+    assert rel_err(got, g["out"]) < 1e-4
+
+
+def test_msda_forward_bf16_matches_reference(cuda_dev):
+    g, c = load("ref_msda"), G.msda_inputs()
+    m = _load(emrt_b200.MSDeformableAttention(c["C"], c["M"], len(c["shapes"]), c["P"]), c["params"]).to(cuda_dev)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    got = m(d(c["query"]).bfloat16(), d(c["ref"]), d(c["value"]).bfloat16(), torch.tensor(c["shapes"]), d(c["mask"]))
+    assert got.dtype == torch.bfloat16
+    # the reference ran on the fp32 inputs and weights, so this includes rounding BOTH to bf16: on these tiny maps
+    # (2x2 coarsest level, 3x the usual offset spread) that rounding alone, followed by exact float64 arithmetic,
+    # is 1.19e-2 relative L2 (measured with the oracle); the kernels add < 1e-3 on top (1.23e-2 measured on B200)
+    assert l2_err(got.float(), g["out"]) < 1.5e-2 and rel_err(got.float(), g["out"]) < 3e-2
+
+
+def test_core_func_matches_reference(cuda_dev):
+    g, c = load("ref_core"), G.core_inputs()
+    d = lambda a: torch.from_numpy(a).to(cuda_dev)
+    got = emrt_b200.deformable_attention_core_func(d(c["value"]), torch.tensor(c["shapes"]), d(c["loc"]), d(c["attn"]))
+    assert rel_err(got, g["out"]) < 1e-4
+    got16 = emrt_b200.deformable_attention_core_func(d(c["value"]).bfloat16(), torch.tensor(c["shapes"]), d(c["loc"]), d(c["attn"]))
+    assert l2_err(got16.float(), g["out"]) < 1e-2
+
+
+def test_reference_points_match_reference(cuda_dev):
+    g = load("ref_refpoints")
+    for name in ("sq", "rect"):
+        shapes = [tuple(int(v) for v in s) for s in g[name + "_shapes"]]
+        got = emrt_b200.get_reference_points(torch.tensor(shapes), None, device=cuda_dev).cpu().numpy()
+        want = g[name]
+        assert got.shape[1:] == want.shape[1:]
+        assert np.abs(np.broadcast_to(got, want.shape) - want).max() < 1e-6
+
+
+def test_position_embedding_matches_reference(cuda_dev):
+    from emrt_b200.decoder import position_embedding_sine_host
+    p = load("ref_posembed")
+    for (h, w) in ((8, 6), (16, 16)):
+        got = position_embedding_sine_host(h, w, 128).reshape(h, w, 256).transpose(2, 0, 1)[None]
+        assert np.abs(got - p[f"pos_{h}x{w}"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_encoder_decoder_fp32_matches_reference(cuda_dev, tag):
+    g = load("ref_encdec_" + tag)
+    ne, nd = int(g["num_enc"]), int(g["num_dec"])
+    c = G.encdec_inputs(int(g["tile"]), int(g["B"]), int(g["seed"]), ne, nd)
+    # constructed exactly as EMRT does (paddle_EMRT.py:241-249)
+    m = emrt_b200.EncoderDecoder(hidden_dim=256, dim_feedforward=1024, backbone_num_channels=[512, 1024, 2048], dropout=0.1,
+                                 activation="relu", num_feature_levels=3, nhead=8, num_encoder_layers=ne,
+                                 num_decoder_layers=nd, num_encoder_points=6, num_decoder_points=6, nclass=6)
+    assert sorted(m.state_dict().keys()) == list(g["keys"])              # the reference's state-dict keys, all of them
+    m = _load(m, c["params"]).to(cuda_dev)
+    hs, mem = m([torch.from_numpy(f).to(cuda_dev) for f in c["feats"]], torch.from_numpy(c["psp"]).to(cuda_dev))
+    assert tuple(hs.shape) == tuple(g["hs"].shape) and tuple(mem.shape) == tuple(g["memory"].shape)
+    assert rel_err(mem, g["memory"]) < 5e-4 and rel_err(hs, g["hs"]) < 5e-4
+    assert l2_err(mem, g["memory"]) < 1e-4 and l2_err(hs, g["hs"]) < 1e-4
+
+
+def test_encoder_decoder_bf16_matches_reference(cuda_dev):
+    g = load("ref_encdec_full")
+    ne, nd = int(g["num_enc"]), int(g["num_dec"])
+    c = G.encdec_inputs(int(g["tile"]), int(g["B"]), int(g["seed"]), ne, nd)
+    m = emrt_b200.EncoderDecoder(hidden_dim=256, dim_feedforward=1024, backbone_num_channels=[512, 1024, 2048],
+                                 num_feature_levels=3, nhead=8, num_encoder_layers=ne, num_decoder_layers=nd,
+                                 num_encoder_points=6, num_decoder_points=6, nclass=6)
+    m = _load(m, c["params"]).to(cuda_dev)
+    hs, mem = m([torch.from_numpy(f).to(cuda_dev).bfloat16() for f in c["feats"]], torch.from_numpy(c["psp"]).to(cuda_dev).bfloat16())
+    # six layers deep in bf16 against the reference's fp32 run (input / weight rounding included)
+    assert l2_err(mem.float(), g["memory"]) < 2e-2 and l2_err(hs.float(), g["hs"]) < 2e-2
+
+
+def test_multi_head_attention_matches_reference(cuda_dev):
+    g, c = load("ref_mha"), G.mha_inputs()
+    p = {k: torch.as_tensor(v).to(cuda_dev) for k, v in c["params"].items()}
+    tgt = torch.from_numpy(c["tgt"]).to(cuda_dev)
+    q = torch.from_numpy(c["tgt"] + c["pos"]).to(cuda_dev)
+    C_ = 256
+    lin = lambda x, w, b: ops.linear(x, w.contiguous(), b.contiguous(), impl=emrt_b200._lib.IMPL_SIMT)
+    qk = lin(q, p["in_proj_weight"][:, :2 * C_], p["in_proj_bias"][:2 * C_])
+    v = lin(tgt, p["in_proj_weight"][:, 2 * C_:], p["in_proj_bias"][2 * C_:])
+    att = ops.mha_small(qk[..., :C_], qk[..., C_:], v, 8, 32 ** -0.5)
+    out = lin(att, p["out_proj.weight"], p["out_proj.bias"])
+    assert rel_err(out, g["out"]) < 1e-4
+
+
+def test_uphead_tail_matches_reference(cuda_dev):
+    g = load("ref_uphead")
+    got = ops.upsample2x(torch.from_numpy(g["half"]).to(cuda_dev))
+    assert rel_err(got, g["full"]) < 1e-6
+
+
+class _ToyModel:
+    """The generator's toy model: stride-2 conv -> half-resolution logits -> UpHead's last x2 upsample (our kernel)."""
+
+    def __init__(self, wconv, dev, half_hook=True):
+        self.w = torch.from_numpy(wconv).to(dev)
+        if half_hook:
+            self.forward_half_logits = lambda batch: torch.nn.functional.conv2d(batch.float(), self.w, stride=2).contiguous()
+
+    def __call__(self, batch):
+        return (ops.upsample2x(torch.nn.functional.conv2d(batch.float(), self.w, stride=2).contiguous()),)
+
+
+@pytest.mark.parametrize("half_hook", [False, True])
+def test_slide_and_ss_inference_match_reference(cuda_dev, half_hook):
+    g, c = load("ref_slide"), G.slide_inputs()
+    model = _ToyModel(c["wconv"], cuda_dev, half_hook)
+    imgs = [torch.from_numpy(i).to(cuda_dev) for i in c["imgs"]]
+    logits = emrt_b200.slide_inference(model, imgs, c["crop"], c["stride"], c["nc"])
+    for i in range(2):
+        assert tuple(logits[i].shape) == tuple(g[f"logit{i}"].shape)
+        assert rel_err(logits[i], g[f"logit{i}"]) < 1e-5
+    preds = emrt_b200.ss_inference(model, imgs, c["ori"], True, None, c["stride"], c["crop"], c["nc"])
+    for i in range(2):
+        assert preds[i].dtype == torch.int32 and tuple(preds[i].shape) == tuple(g[f"pred{i}"].shape)
+        assert (preds[i].cpu().numpy() == g[f"pred{i}"]).mean() >= 0.999
+    # same-size output for both images -> the fused upsample + stitch + argmax kernel when the model exposes half logits
+    same = [tuple(i.shape[-2:]) for i in imgs]
+    preds = emrt_b200.ss_inference(model, imgs, same, True, None, c["stride"], c["crop"], c["nc"])
+    for i in range(2):
+        want = np.argmax(g[f"logit{i}"], axis=1)[:, None].astype(np.int32)
+        assert (preds[i].cpu().numpy() == want).mean() >= 0.999
+
+
+def test_calculate_area_matches_reference(cuda_dev):
+    g, c = load("ref_area"), G.area_inputs()
+    got = emrt_b200.calculate_area(torch.from_numpy(c["pred"]).to(cuda_dev), torch.from_numpy(c["label"]).to(cuda_dev).int(),
+                                   c["nc"]).cpu().numpy()
+    for row, key in enumerate(("intersect", "pred", "label")):
+        assert np.array_equal(got[row].astype(np.int64), g[key].astype(np.int64).reshape(-1))

@@ -1,0 +1,164 @@
+"""Pins the oracle (oracle/emrt_oracle.py) to the REFERENCE'S OWN CODE.
+
+tests/golden/ref_*.npz were produced by executing the reference's unmodified sources (imported in place from
+/root/reference) on oracle/paddle_on_torch.py — see tests/golden/make_reference_vectors.py.  Part 1 compares the
+oracle with those committed vectors and runs anywhere.  Part 2 re-runs the reference live on further shapes when
+/root/reference is present (this container) and is skipped elsewhere (the GPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.emrt_oracle as O
+from oracle import run_reference as R
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLD)
+import make_reference_vectors as G  # noqa: E402  (the seeded input builders the fixtures were generated from)
+
+load = lambda name: np.load(os.path.join(GOLD, name + ".npz"))
+TOL = 2e-6          # fp32 evaluation order only: both sides compute the same formula in float32 / float64
+
+
+def close(got, want, tol=TOL):
+    got, want = np.asarray(torch.as_tensor(got).double()), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+    assert err < tol, err
+
+
+def same_inputs(g, arrays):
+    assert abs(float(g["check"]) - float(G.checksum(arrays))) <= 1e-9 * max(1.0, abs(float(g["check"]))), \
+        "seeded inputs drifted from the ones the fixture was generated with"
+
+
+# ---- part 1: committed vectors ----------------------------------------------------------------------------------------
+def test_msda_reset_parameters_matches_reference_init():
+    g = load("ref_msda_init")
+    bias = O.msda_reset_parameters(256, 8, 3, 6)
+    assert np.abs(bias - g["sampling_offsets_bias"]).max() < 1e-6        # cos / sin of torch vs numpy: last-ulp
+    ours = O.make_msda_params(1, 256, 8, 3, 6)
+    assert float(g["sampling_offsets_weight_absmax"]) == 0 and float(g["attention_weights_absmax"]) == 0
+    assert float(g["value_proj_bias_absmax"]) == 0
+    assert 0.9 * float(g["xavier_bound"]) < float(g["value_proj_weight_absmax"]) <= float(g["xavier_bound"]) * (1 + 1e-6)
+    for k in ("sampling_offsets.weight", "attention_weights.weight", "value_proj.weight", "output_proj.weight"):
+        assert tuple(g["shape." + k]) == tuple(ours[k].shape)            # Paddle [in, out] layouts
+
+
+def test_msda_forward_matches_reference():
+    g, c = load("ref_msda"), G.msda_inputs()
+    same_inputs(g, [c["query"], c["value"], c["ref"], c["mask"], *c["params"].values()])
+    out = O.msda_forward(c["params"], c["query"], c["ref"], c["value"], c["shapes"], c["mask"], c["M"], c["P"], dtype=torch.float64)
+    close(out, g["out"])
+
+
+def test_gather_matches_reference_core_func():
+    g, c = load("ref_core"), G.core_inputs()
+    same_inputs(g, [c["value"], c["loc"], c["attn"]])
+    close(O.gather_corner_loop(c["value"], c["shapes"], c["loc"], c["attn"]), g["out"])
+    close(O.deformable_attention_core_func(torch.from_numpy(c["value"]).double(), c["shapes"], torch.from_numpy(c["loc"]).double(),
+                                           torch.from_numpy(c["attn"]).double()), g["out"])
+
+
+def test_reference_points_and_position_embedding_match_reference():
+    g = load("ref_refpoints")
+    for name in ("sq", "rect"):
+        shapes = [tuple(int(v) for v in s) for s in g[name + "_shapes"]]
+        close(O.encoder_reference_points(shapes, 2), g[name], 1e-6)
+    p = load("ref_posembed")
+    for (h, w) in ((8, 6), (16, 16)):
+        want = p[f"pos_{h}x{w}"]                                           # [1, 256, h, w]
+        got = O.position_embedding_sine(h, w, 128)                         # [h*w, 256] token-major
+        close(torch.as_tensor(got).reshape(h, w, 256).permute(2, 0, 1)[None], want, 1e-5)
+
+
+def test_multi_head_attention_matches_reference():
+    g, c = load("ref_mha"), G.mha_inputs()
+    same_inputs(g, [c["tgt"], c["pos"], *c["params"].values()])
+    p = {"self_attn." + k: torch.as_tensor(v).double() for k, v in c["params"].items()}
+    q = torch.from_numpy(c["tgt"] + c["pos"]).double()
+    close(O.multi_head_attention(p, "self_attn.", q, q, torch.from_numpy(c["tgt"]).double()), g["out"])
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_encoder_decoder_matches_reference(tag):
+    g = load("ref_encdec_" + tag)
+    ne, nd = int(g["num_enc"]), int(g["num_dec"])
+    c = G.encdec_inputs(int(g["tile"]), int(g["B"]), int(g["seed"]), ne, nd)
+    same_inputs(g, [*c["feats"], c["psp"], *[v.numpy() for v in c["params"].values()]])
+    assert sorted(c["params"].keys()) == list(g["keys"])                  # the reference's state-dict keys
+    p64 = {k: v.double() for k, v in c["params"].items()}
+    hs, mem, _ = O.encoder_decoder_forward(p64, [torch.from_numpy(f).double() for f in c["feats"]],
+                                           torch.from_numpy(c["psp"]).double(), num_enc=ne, num_dec=nd)
+    close(mem, g["memory"], 2e-5)
+    close(hs, g["hs"], 2e-5)
+
+
+def test_uphead_tail_matches_reference():
+    g = load("ref_uphead")
+    close(O.upsample2x(torch.from_numpy(g["half"])), g["full"])
+    close(O.upsample2x_loop(g["half"]), g["full"])
+
+
+def _toy_model(wconv):
+    w = torch.from_numpy(wconv)
+    return lambda batch: (O.upsample2x(torch.nn.functional.conv2d(batch, w, stride=2)),)
+
+
+def test_slide_and_ss_inference_match_reference():
+    g, c = load("ref_slide"), G.slide_inputs()
+    same_inputs(g, [*c["imgs"], c["wconv"]])
+    imgs = [torch.from_numpy(i) for i in c["imgs"]]
+    logits = O.slide_inference(_toy_model(c["wconv"]), imgs, c["crop"], c["stride"], c["nc"])
+    preds = O.ss_inference(_toy_model(c["wconv"]), imgs, c["ori"], True, None, c["stride"], c["crop"], c["nc"])
+    for i in range(2):
+        close(logits[i], g[f"logit{i}"], 1e-6)
+        assert preds[i].dtype == torch.int32 and np.array_equal(preds[i].numpy(), g[f"pred{i}"])
+    origins = O.window_origins(50, 24, 16)
+    assert origins == [0, 16, 26]                                        # infer.py:52-59 (last window pulled back)
+
+
+def test_calculate_area_matches_reference():
+    g, c = load("ref_area"), G.area_inputs()
+    same_inputs(g, [c["pred"], c["label"]])
+    ia, pa, la = O.calculate_area(torch.from_numpy(c["pred"]), torch.from_numpy(c["label"]), c["nc"])
+    for got, key in ((ia, "intersect"), (pa, "pred"), (la, "label")):
+        assert np.array_equal(np.asarray(got, dtype=np.float64).reshape(-1), g[key].astype(np.float64).reshape(-1))
+
+
+# ---- part 2: the reference run live (this container only) -------------------------------------------------------------
+live = pytest.mark.skipif(not R.available(), reason="/root/reference is not present (GPU box)")
+
+
+@live
+@pytest.mark.parametrize("shapes,B,Lq,seed", [([(32, 32), (16, 16), (8, 8)], 1, None, 3), ([(5, 9)], 2, 13, 4),
+                                              ([(7, 3), (2, 5)], 2, 9, 5)])
+def test_live_reference_msda(shapes, B, Lq, seed):
+    ref = R.load()
+    import paddle
+    rng = np.random.Generator(np.random.PCG64(seed))
+    _, Lv = O.level_tables(shapes)
+    Lq = Lq or Lv
+    L = len(shapes)
+    params = O.make_msda_params(seed, 256, 8, L, 6)
+    q, v = O.rng_normal(rng, (B, Lq, 256)), O.rng_normal(rng, (B, Lv, 256))
+    rp = rng.uniform(0, 1, size=(B, Lq, L, 2)).astype(np.float32)
+    m = R.load_params(ref.ted.MSDeformableAttention(256, 8, L, 6), params)
+    want = m(paddle.to_tensor(q), paddle.to_tensor(rp), paddle.to_tensor(v), paddle.to_tensor(shapes, dtype="int64"))
+    close(O.msda_forward(params, q, rp, v, shapes, None, 8, 6), torch.as_tensor(want), 1e-5)
+
+
+@live
+def test_live_reference_slide_inference_potsdam_window_plan():
+    """The reference's own window loop at 6000 / 512 / 384 (cfg 5) and 1024 / 512 / 384 (cfg 3): cover counts."""
+    ref = R.load()
+    import paddle
+    for size, n in ((1024, 3), (6000, 16)):
+        img = paddle.zeros([1, size // 8, size // 8])                      # same plan at 1/8 scale: 64 / 48 windows
+        model = lambda b: (paddle.ones([b.shape[0], 1, b.shape[2], b.shape[3]]),)
+        out = ref.infer.slide_inference(model, [img], (64, 64), (48, 48), 1)
+        assert float(torch.as_tensor(out[0]).min()) == 1.0 == float(torch.as_tensor(out[0]).max())
+        assert len(O.window_origins(size, 512, 384)) == n
+        assert [o // 8 for o in O.window_origins(size, 512, 384)] == O.window_origins(size // 8, 64, 48)
