@@ -1,15 +1,19 @@
 """CPU restatement (torch-CPU / numpy) of the EMRT hot path.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED.  The reference has no tests / golden vectors / fixtures, and its arithmetic is
-delegated to the un-vendored third-party package ``paddlepaddle`` (README.md:16 "2.1.0+",
-README.md:29 ``paddlepaddle-gpu==2.1.2``; not pinned in requirements.txt), which cannot be installed
-in this image (no wheel, no network, needs Python <= 3.8).  The restatement is pinned instead by
+PARITY PINNED TO THE REFERENCE'S SOURCES, NOT TO PADDLE'S KERNELS.  The reference ships no tests / golden vectors /
+fixtures, and its arithmetic is delegated to the un-vendored third-party package ``paddlepaddle`` (README.md:16
+"2.1.0+", README.md:29 ``paddlepaddle-gpu==2.1.2``; not pinned in requirements.txt), which cannot be installed in
+this image (no wheel, no network, needs Python <= 3.8).  What pins this restatement:
+  (o)  the reference's own, unmodified Python sources executed in this container on a torch-CPU mapping of the
+       Paddle operators they call (oracle/paddle_on_torch.py + oracle/run_reference.py): tests/test_reference_pin.py
+       checks every function here against vectors generated that way (tests/golden/ref_*.npz, generator
+       tests/golden/make_reference_vectors.py) and against live runs of the reference on further shapes;
   (i)  two independent formulations of every sampled op (library ``grid_sample`` / ``interpolate``
        composition that mirrors the reference line by line vs. explicit closed-form corner loops),
   (ii) analytic cases (zero offsets, all-outside samples, linearity, uniform attention),
   (iii) float64 evaluation as the arbiter for fp32 / bf16 tolerances.
-Paddle semantics assumed (from the Paddle API documentation): ``nn.Linear`` is ``y = x @ W + b`` with
-``W`` stored ``[in, out]``; LayerNorm/GroupNorm eps 1e-5; GELU exact (erf); ``F.grid_sample`` grid last
+Still assumed (from the Paddle API documentation, uncheckable without Paddle): ``nn.Linear`` is ``y = x @ W + b``
+with ``W`` stored ``[in, out]``; LayerNorm/GroupNorm eps 1e-5; GELU exact (erf); ``F.grid_sample`` grid last
 dim is (x, y); ``F.interpolate(align_corners=False)`` uses half-pixel centres (align_mode=0);
 ``paddle.argmax`` returns the first maximal index.
 

@@ -54,8 +54,11 @@ def load():
         return types.SimpleNamespace(**_loaded)
     if not available():
         raise RuntimeError(f"reference sources not found under {REF_ROOT}")
-    from . import paddle_on_torch
-    paddle_on_torch.install()
+    if os.environ.get("EMRT_USE_REAL_PADDLE") == "1":
+        import paddle  # noqa: F401  (a real PaddlePaddle 2.1-2.4: INTEGRATION.md section 6)
+    else:
+        from . import paddle_on_torch
+        paddle_on_torch.install()
     src = os.path.join(REF_ROOT, "src")
     # namespace stubs instead of the reference's import-everything __init__ files
     for name, path in ((_PKG, src), (f"{_PKG}.models", f"{src}/models"), (f"{_PKG}.models.EMRT_utils", f"{src}/models/EMRT_utils"),

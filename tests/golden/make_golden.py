@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz from the CPU oracle (oracle/emrt_oracle.py).
 
-PARITY UNPINNED: the reference ships no golden vectors and cannot be executed here (no PaddlePaddle), so these
-fixtures are regression pins of the oracle itself (float64-evaluated where noted), not outputs of the reference.
+These two fixtures are regression pins of the oracle itself (float64-evaluated where noted).  The vectors that come
+from the reference's own code are the ref_*.npz files written by make_reference_vectors.py.
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import os

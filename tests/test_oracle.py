@@ -1,5 +1,5 @@
 """CPU tests of the oracle: two independent formulations, analytic cases, golden fixtures.
-PARITY UNPINNED (see oracle/emrt_oracle.py): the reference ships no vectors and cannot run here."""
+The pin against the reference's own sources is tests/test_reference_pin.py (see oracle/emrt_oracle.py)."""
 import os
 
 import numpy as np
