@@ -2,13 +2,17 @@
 """bench.py — EMRT hot path on B200: images/s (512x512 windows) and MPix/s.
 
 A "step" = one pass of the hot path over one batch of synthetic input:
-  the 4-layer TransformerEncoder (per layer: 3x3 conv branch + GroupNorm + GELU, MSDeformableAttention [value / offset /
-  weight / output projections, softmax over levels x points, multiscale bilinear gather], LayerNorm, FFN 256-1024-256,
-  LayerNorm) and the 2 decoder cross-attention MSDeformableAttention calls on the C3-C5 token maps of W 512x512
-  windows, then the head tail (x2 bilinear upsample + sliding-window overlap stitch + softmax + argmax) that turns the
-  windows' half-resolution class logits into 1024x1024 LoveDA-shaped label maps (9 windows per image, window 512,
-  stride 384).
-Out of the step (out of scope / "next" rows): ResNet-50 backbone, conv heads, decoder self-attention glue.
+  the reference's whole EncoderDecoder.forward(src_feats, src_psp) (transformer_encoder_decoder.py:416-473, built with
+  EMRT's own constructor arguments, paddle_EMRT.py:241-249) on the ResNet-50 C3-C5 feature maps of W 512x512 windows —
+  input_proj (1x1 conv + GroupNorm), position / level embedding, 4 encoder layers (3x3 conv branch + GroupNorm + GELU,
+  MSDeformableAttention [value / offset / weight / output projections, softmax over levels x points, multiscale bilinear
+  gather], LayerNorm, FFN 256-1024-256, LayerNorm), 2 decoder layers (110-token self-attention, MSDeformableAttention
+  cross-attention, FFN) — then the head tail (x2 bilinear upsample + sliding-window overlap stitch + softmax + argmax)
+  that turns the windows' half-resolution class logits into 1024x1024 LoveDA-shaped label maps (9 windows per image,
+  window 512, stride 384).
+Out of the step (out of scope): ResNet-50 backbone, spatial branch / PSP, EFP, conv heads.
+  --tokens     the earlier step definition (token inputs: TransformerEncoder + 2 bare decoder MSDA calls + head tail)
+  --msda-only  the round-1 starting definition (4 + 2 bare MSDA calls + head tail)
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun)
   python bench.py --impl reference ...                           the reference path's CPU restatement (oracle)
@@ -31,8 +35,13 @@ TILE = 512
 NC = 7                      # LoveDA
 WINDOWS_PER_IMAGE = 9       # 1024x1024, window 512, stride 384 -> origins {0, 384, 512}^2
 SCENE = 1024
-METRIC = ("images/s (512x512 windows through the EMRT hot path: 4-layer TransformerEncoder [conv branch + "
-          "MSDeformableAttention + LayerNorm + FFN] + 2 decoder MSDeformableAttention + upsample/stitch/argmax)")
+METRIC = ("images/s (512x512 windows through the EMRT hot path: EncoderDecoder.forward on the C3-C5 features [input_proj, "
+          "4 encoder layers with conv branch + MSDeformableAttention + LayerNorm + FFN, 2 decoder layers with self-attention + "
+          "MSDeformableAttention + FFN] + upsample/stitch/argmax)")
+FEAT_CH = (512, 1024, 2048)   # ResNet-50 C3..C5 (paddle_EMRT.py:191)
+WORKLOAD_TAIL = {"full": "hot path only (EncoderDecoder.forward on C3-C5 features + head tail)",
+                 "tokens": "hot path only (4-layer encoder + 2 decoder MSDA + head tail; token inputs)",
+                 "msda": "4 + 2 bare MSDeformableAttention calls + head tail"}
 
 
 def parse():
@@ -46,7 +55,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-windows", type=int, default=8)
     ap.add_argument("--msda-only", action="store_true", help="round-1 starting definition: 4 + 2 bare MSDA calls + head tail")
-    return ap.parse_args()
+    ap.add_argument("--tokens", action="store_true", help="earlier definition: token inputs, encoder + 2 bare decoder MSDA + head tail")
+    a = ap.parse_args()
+    a.mode = "msda" if a.msda_only else ("tokens" if a.tokens else "full")
+    return a
 
 
 def peaks():
@@ -138,14 +150,34 @@ def gather_bytes(B, Lq, Lv, M, D, L, P, sv, sl):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference path's CPU restatement (the oracle), on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_hot_path(n_windows, threads, repeats=1, warmup=0):
-    """Times the oracle (torch-CPU fp32 restatement of the reference's Paddle op composition) on `n_windows`
-    512x512 windows of the same workload.  Returns (images/s, seconds per pass)."""
+def cpu_hot_path(n_windows, threads, repeats=1, warmup=0, mode="full"):
+    """Times the oracle (torch-CPU fp32 restatement of the reference's Paddle op composition, checked against the
+    reference's own sources in tests/test_reference_pin.py) on `n_windows` 512x512 windows of the same workload.
+    Returns (images/s, seconds per pass)."""
     import numpy as np
     import torch
     import oracle as O
     from emrt_b200 import synthetic
     torch.set_num_threads(threads)
+    if mode == "full":
+        rng = np.random.Generator(np.random.PCG64(0))
+        params = {k: torch.from_numpy(v) for k, v in synthetic.encoder_decoder_state(1234).items()}
+        feats = [torch.from_numpy(O.rng_normal(rng, (n_windows, c, TILE // s, TILE // s), 0.5)) for c, s in zip(FEAT_CH, (8, 16, 32))]
+        psp = torch.from_numpy(O.rng_normal(rng, (n_windows, 256, 110), 0.5))
+        half = torch.from_numpy(O.rng_normal(rng, (n_windows, NC, TILE // 2, TILE // 2)))
+
+        def one_pass():
+            hs, mem, _ = O.encoder_decoder_forward(params, feats, psp, num_enc=4, num_dec=2)
+            full = O.upsample2x(half)                       # UpHead tail
+            return O.ss_inference_tail(full, (TILE, TILE)), hs
+        with torch.no_grad():
+            for _ in range(warmup):
+                one_pass()
+            t0 = time.perf_counter()
+            for _ in range(repeats):
+                one_pass()
+            dt = (time.perf_counter() - t0) / repeats
+        return n_windows / dt, dt
     shapes = [(TILE // 8,) * 2, (TILE // 16,) * 2, (TILE // 32,) * 2]
     _, Lv = O.level_tables(shapes)
     rng = np.random.Generator(np.random.PCG64(0))
@@ -189,16 +221,17 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     nwin = max(1, args.cpu_sample_windows)
-    ips, dt = cpu_hot_path(nwin, cores, repeats=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
+    ips, dt = cpu_hot_path(nwin, cores, repeats=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0, mode=args.mode)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": max(1, min(args.steps, 3)), "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mpix_per_s": ips * TILE * TILE / 1e6,
         "config": {"workload": f"cfg3-shaped: {TILE}x{TILE} windows of 1024x1024 LoveDA scenes, {NC} classes, "
-                               "window 512 stride 384; hot path only (4-layer encoder + 2 decoder MSDA + head tail)",
+                               "window 512 stride 384; " + WORKLOAD_TAIL[args.mode],
                    "note": "reference = CPU restatement of the reference's Paddle op composition (oracle/, torch-CPU "
-                           "fp32); PaddlePaddle itself cannot be installed in this image"},
+                           "fp32, verified equal to the reference's own sources in tests/test_reference_pin.py); "
+                           "PaddlePaddle itself cannot be installed in this image"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{nwin} window(s) of the {args.images * WINDOWS_PER_IMAGE}-window step, all host threads"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -228,7 +261,8 @@ def run_ours(args):
     ops.device_check()
 
     impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tcgen05": L.IMPL_TCGEN05}[args.gemm]
-    hp = HotPath(dev, TILE, NC, gemm_impl=impl, full_encoder=not args.msda_only)
+    hp = HotPath(dev, TILE, NC, gemm_impl=impl, mode=args.mode)
+    full = args.mode == "full"
     n_img = args.images
     B = n_img * WINDOWS_PER_IMAGE
     plan, H, W = window_tables(n_img)
@@ -243,17 +277,28 @@ def run_ours(args):
 
     # host (pinned) inputs for the e2e path and N_SETS resident device copies for the kernel-only path; rotating
     # over N_SETS input sets (> 126 MB L2 in total) keeps every timed step's inputs cold.
-    set_bytes = 2 * (B * Lv * C + B * Nq * C + B * NC * (TILE // 2) ** 2)
+    feat_elems = sum(c * (TILE // s) ** 2 for c, s in zip(FEAT_CH, (8, 16, 32)))
+    set_bytes = 2 * ((B * feat_elems + B * C * Nq if full else B * Lv * C + B * Nq * C) + B * NC * (TILE // 2) ** 2)
     N_SETS = 4 if set_bytes < 150e6 else 2          # either way the rotating sets exceed the 126 MB L2
+
+    def as_batch(d):
+        """flat dict of tensors (what travels host -> device) -> the step's argument dict"""
+        b = dict(d)
+        if full:
+            b["feats"] = [b.pop("c3"), b.pop("c4"), b.pop("c5")]
+        b.update(pos=pos, qpos=qpos, mask=mask, **win)
+        return b
+    rnd = lambda shape, std=1.0: (torch.randn(shape, generator=g) * std).bfloat16().pin_memory()
     host_sets, dev_sets = [], []
     for s in range(N_SETS):
-        h = dict(src=torch.randn((B, Lv, C), generator=g).bfloat16().pin_memory(),
-                 tgt=torch.randn((B, Nq, C), generator=g).bfloat16().pin_memory(),
-                 half_logits=torch.randn((B, NC, TILE // 2, TILE // 2), generator=g).bfloat16().pin_memory())
+        if full:        # ResNet-50 C3..C5 feature maps [B, 512|1024|2048, T/8|T/16|T/32, .] and the PSP tokens [B, 256, 110]
+            h = {name: rnd((B, c, TILE // st, TILE // st), 0.5) for name, c, st in zip(("c3", "c4", "c5"), FEAT_CH, (8, 16, 32))}
+            h["psp"] = rnd((B, C, Nq), 0.5)
+        else:
+            h = dict(src=rnd((B, Lv, C)), tgt=rnd((B, Nq, C)))
+        h["half_logits"] = rnd((B, NC, TILE // 2, TILE // 2))
         host_sets.append(h)
-        d = {k: v.to(dev) for k, v in h.items()}
-        d.update(pos=pos, qpos=qpos, mask=mask, **win)
-        dev_sets.append(d)
+        dev_sets.append(as_batch({k: v.to(dev) for k, v in h.items()}))
     in_bytes = sum(v.numel() * v.element_size() for v in host_sets[0].values())
     labels_dev = torch.empty((n_img, 1, H, W), dtype=torch.uint8, device=dev)
     labels_host = torch.empty((n_img, 1, H, W), dtype=torch.uint8).pin_memory()
@@ -322,9 +367,7 @@ def run_ours(args):
                 ready[sl].record(h2d)
             cur.wait_event(ready[sl])
             cur.wait_event(drained[sl])                # step i-2's labels have left lab_slots[sl]
-            d = dict(slots[sl])
-            d.update(pos=pos, qpos=qpos, mask=mask, **win)
-            lab, hs = hp.step(d, lab_slots[sl])
+            lab, hs = hp.step(as_batch(slots[sl]), lab_slots[sl])
             hs_keep[sl] = hs
             free[sl].record(cur)
             done[sl].record(cur)
@@ -377,7 +420,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "mpix_per_s": value * TILE * TILE / 1e6,
         "config": {"workload": f"cfg3-shaped: {B} {TILE}x{TILE} windows per GPU per step = {n_img} LoveDA 1024x1024 "
-                               f"scenes (window 512, stride 384), {NC} classes; hot path only (4-layer encoder + 2 decoder MSDA + head tail)",
+                               f"scenes (window 512, stride 384), {NC} classes; " + WORKLOAD_TAIL[args.mode],
                    "windows_per_gpu": B, "tokens_per_window": Lv, "gemm": args.gemm,
                    "l2": f"inputs rotate over {N_SETS} resident sets ({N_SETS * in_bytes / 1e6:.0f} MB > 126 MB L2); "
                          "each step also streams > 1 GB of intermediates",
@@ -390,7 +433,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        ips, dt = cpu_hot_path(max(1, args.cpu_sample_windows), cores, repeats=2, warmup=1)
+        ips, dt = cpu_hot_path(max(1, args.cpu_sample_windows), cores, repeats=2, warmup=1, mode=args.mode)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": f"{max(1, args.cpu_sample_windows)} window(s) of the {B}-window step, "
                                           f"torch-CPU fp32 oracle, {cores} threads, {dt:.2f} s per pass"}

@@ -1,8 +1,10 @@
-"""The hot path as one callable: the TransformerEncoder (4 layers: conv branch + MSDeformableAttention + LayerNorm + FFN,
-transformer_encoder_decoder.py:109-239), the 2 decoder cross-attention MSDeformableAttention calls (:288), and the head
-tail (x2 upsample + sliding-window stitch + softmax + argmax; paddle_EMRT.py:178-180, src/api/infer.py:69-79,150-154).
-The decoder's 110-token self-attention / LayerNorm / FFN glue is a "next" row and is not part
-of this step.  ``full_encoder=False`` gives the bare 4 + 2 MSDA calls (the round-1 starting definition)."""
+"""The hot path as one callable.  Default (``mode="full"``): the reference's whole ``EncoderDecoder.forward``
+(transformer_encoder_decoder.py:416-473, constructed as paddle_EMRT.py:241-249 does: input_proj on the C3-C5 features,
+position / level embedding, 4 encoder layers [conv branch + MSDeformableAttention + LayerNorm + FFN], reference-point head,
+2 decoder layers [110-token self-attention + MSDeformableAttention cross-attention + FFN]) followed by the head tail
+(x2 upsample + sliding-window stitch + softmax + argmax; paddle_EMRT.py:178-180, src/api/infer.py:69-79,150-154).
+``mode="tokens"`` is the earlier definition (token inputs: TransformerEncoder + the 2 bare decoder MSDA calls + head
+tail); ``mode="msda"`` the round-1 starting one (4 + 2 bare MSDA calls + head tail)."""
 from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
@@ -19,14 +21,34 @@ from . import synthetic
 
 class HotPath:
     def __init__(self, device, tile=512, num_classes=7, embed_dim=256, num_heads=8, num_points=6, num_enc=4,
-                 num_dec=2, num_queries=110, seed=1234, gemm_impl=L.IMPL_AUTO, full_encoder=True):
+                 num_dec=2, num_queries=110, seed=1234, gemm_impl=L.IMPL_AUTO, full_encoder=True, mode=None):
         self.device = device
+        self.mode = mode or ("tokens" if full_encoder else "msda")
+        full_encoder = self.mode == "tokens"
         self.tile, self.nc, self.C = tile, num_classes, embed_dim
         self.shapes = synthetic.level_shapes(tile)
         self.Lv = sum(h * w for h, w in self.shapes)
         self.num_queries = num_queries
         self.enc: List[MSDeformableAttention] = []
         self.dec: List[MSDeformableAttention] = []
+        self.model = None
+        if self.mode == "full":
+            from .decoder import EncoderDecoder
+            m = EncoderDecoder(hidden_dim=embed_dim, dim_feedforward=1024, backbone_num_channels=[512, 1024, 2048],
+                               dropout=0.1, activation="relu", num_feature_levels=3, nhead=num_heads,
+                               num_encoder_layers=num_enc, num_decoder_layers=num_dec, num_encoder_points=num_points,
+                               num_decoder_points=num_points, nclass=num_classes)
+            st = synthetic.encoder_decoder_state(seed, embed_dim, 1024, num_heads, 3, num_points, num_enc, num_dec)
+            with torch.no_grad():
+                sd = m.state_dict()
+                for k in sd:
+                    sd[k].copy_(torch.from_numpy(st[k]))
+            for mod in m.modules():
+                if hasattr(mod, "gemm_impl"):
+                    mod.gemm_impl = gemm_impl
+            self.model = m.to(device).requires_grad_(False)
+            self.encoder = None
+            return
         for i in range(num_enc + num_dec):
             m = MSDeformableAttention(embed_dim, num_heads, len(self.shapes), num_points).to(device)
             st = synthetic.msda_state(seed + i, embed_dim, num_heads, len(self.shapes), num_points)
@@ -77,6 +99,11 @@ class HotPath:
                                        labels=labels)[0]
 
     def step(self, batch, labels=None):
+        if self.model is not None:
+            hs, mem = self.model(batch["feats"], batch["psp"])               # EncoderDecoder.forward(src_feats, src_psp)
+            lab = self.head_tail(batch["half_logits"], batch["win_img"], batch["win_y0"], batch["win_x0"],
+                                 batch["n_img"], batch["H"], batch["W"], labels)
+            return lab, hs[0]
         mem, hs = self.msda_stack(batch["src"], batch["pos"], batch["tgt"], batch["qpos"], batch.get("mask"))
         lab = self.head_tail(batch["half_logits"], batch["win_img"], batch["win_y0"], batch["win_x0"],
                              batch["n_img"], batch["H"], batch["W"], labels)

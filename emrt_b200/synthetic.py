@@ -78,3 +78,50 @@ def encoder_layer_state(seed=1234, C=256, ffn=1024, heads=8, levels=3, points=6)
         p[f"conv{l}.0.weight"] = rng.uniform(-b, b, (C, C, 3, 3)).astype(f)
         norm(f"conv{l}.1")
     return p
+
+
+def encoder_decoder_state(seed=1234, C=256, ffn=1024, heads=8, levels=3, points=6, num_enc=4, num_dec=2,
+                          in_channels=(512, 1024, 2048), num_queries=110) -> Dict[str, np.ndarray]:
+    """Non-trivial weights for the whole EncoderDecoder (transformer_encoder_decoder.py:337-407) with the reference's
+    state-dict keys: encoder.layers.{i}.*, decoder.layers.{i}.{self_attn.in_proj_weight [C,3C], self_attn.in_proj_bias,
+    self_attn.out_proj.*, norm1-3, cross_attn.*, linear1-2}, level_embed / tgt_embed / query_pos_embed .weight,
+    reference_points.*, input_proj.{l}.{0,1}.*.  Same distributions as the per-module generators above."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f = np.float32
+    p: Dict[str, np.ndarray] = {}
+
+    def norm(name, c=C):
+        p[name + ".weight"] = rng.uniform(0.5, 1.5, size=(c,)).astype(f)
+        p[name + ".bias"] = (rng.standard_normal((c,)) * 0.1).astype(f)
+
+    def linear(name, i, o):
+        b = math.sqrt(6.0 / (i + o))
+        p[name + ".weight"] = rng.uniform(-b, b, (i, o)).astype(f)
+        p[name + ".bias"] = rng.uniform(-0.1, 0.1, (o,)).astype(f)
+
+    for i in range(num_enc):
+        for k, v in encoder_layer_state(int(rng.integers(1 << 30)), C, ffn, heads, levels, points).items():
+            p[f"encoder.layers.{i}.{k}"] = v
+    for i in range(num_dec):
+        pre = f"decoder.layers.{i}"
+        b = math.sqrt(6.0 / (C + 3 * C))
+        p[pre + ".self_attn.in_proj_weight"] = rng.uniform(-b, b, (C, 3 * C)).astype(f)
+        p[pre + ".self_attn.in_proj_bias"] = rng.uniform(-0.1, 0.1, (3 * C,)).astype(f)
+        linear(pre + ".self_attn.out_proj", C, C)
+        norm(pre + ".norm1")
+        for k, v in msda_state(int(rng.integers(1 << 30)), C, heads, levels, points).items():
+            p[f"{pre}.cross_attn.{k}"] = v
+        norm(pre + ".norm2")
+        linear(pre + ".linear1", C, ffn)
+        linear(pre + ".linear2", ffn, C)
+        norm(pre + ".norm3")
+    p["level_embed.weight"] = rng.standard_normal((levels, C)).astype(f)
+    p["tgt_embed.weight"] = rng.standard_normal((num_queries, C)).astype(f)
+    p["query_pos_embed.weight"] = rng.standard_normal((num_queries, C)).astype(f)
+    linear("reference_points", C, 2)
+    for l, cin in enumerate(in_channels):
+        b = math.sqrt(6.0 / (cin + C))
+        p[f"input_proj.{l}.0.weight"] = rng.uniform(-b, b, (C, cin, 1, 1)).astype(f)
+        p[f"input_proj.{l}.0.bias"] = rng.uniform(-0.1, 0.1, (C,)).astype(f)
+        norm(f"input_proj.{l}.1")
+    return p
