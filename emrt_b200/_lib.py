@@ -59,6 +59,9 @@ SIGNATURES = {
     "emrt_pack_conv3x3_weight": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "emrt_conv3x3_tokens_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I32P, _I, _I, _I, _P]),
     "emrt_groupnorm_gelu_residual": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_float, _I32P, _I, _P]),
+    "emrt_groupnorm_stats": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I32P, _I, _P]),
+    "emrt_residual_layernorm_gn": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_float, C.c_float,
+                                             _I32P, _I, _P]),
     "emrt_nchw_to_tokens": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "emrt_groupnorm_tokens": (C.c_int, [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, C.c_float, _I, _P]),
     "emrt_mha_small": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, C.c_float, _I, _P]),

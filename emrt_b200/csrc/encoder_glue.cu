@@ -5,18 +5,50 @@
 //   * GroupNorm(32) + exact GELU + skip on the conv output            (:187-189)
 // All of it works on the token layout [B, Lv, C] (NHWC per level), so the reference's seq2_2D / flatten / transpose /
 // concat copies (:163-196) do not exist here.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace emrt {
 
+// Exact (erf-form) GELU, nn.GELU's default: h * Phi(h), Phi(h) = erfc(-h / sqrt 2) / 2.  erfc(z), z >= 0, by Abramowitz &
+// Stegun 7.1.26 (|error| <= 1.5e-7 absolute) — one branch-free sequence with one MUFU.RCP and one MUFU.EX2 instead of
+// erff's two divergent branches; the negative side is evaluated as erfc directly, so there is no 1 - erf cancellation.
+__device__ __forceinline__ float gelu_erf(float h) {
+  const float z = fabsf(h) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * __expf(-z * z);      // erfc(z) / 2
+  return h * (h >= 0.f ? 1.f - half_erfc : half_erfc);
+}
+
 // ---- LayerNorm(x + residual) (+ post_add): one warp per row, 16-byte vectors, N <= 1024, N % (32 * VEC) == 0 ----------
-template <typename T, int PER>   // PER = 16-byte vectors per lane
+// GN = true: post_add is not a tensor but the encoder layer's conv branch evaluated on the fly,
+//   post_add[row, c] = GELU(GroupNorm_l(conv)[row, c]) + skip[row, c]      (transformer_encoder_decoder.py:187-189,203)
+// from the conv output, the layer input and the (sum, sum of squares) statistics of groupnorm_stats_kernel — the branch
+// tensor is never written or re-read.
+struct GnBranch {
+  const void* conv;
+  const void* skip;
+  const float* stats;     // [B, L, G, 2] sums from groupnorm_stats_kernel
+  const float* gamma;     // [L, C]
+  const float* beta;
+  int Lv, L, G;
+  float eps;
+  LevelTable lv;
+};
+
+template <typename T, int PER, bool GN>   // PER = 16-byte vectors per lane
 __global__ void __launch_bounds__(256)
 residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ gamma,
                           const float* __restrict__ beta, const T* __restrict__ post_add, T* __restrict__ y,
-                          int64_t rows, int N, float eps) {
+                          int64_t rows, int N, float eps, const __grid_constant__ GnBranch gn) {
   constexpr int VEC = Vec16<T>::N;
-  constexpr int RPW = PER <= 2 ? 2 : 1;                    // rows per warp in flight (more loads outstanding)
+  constexpr int RPW = (PER <= 2 && !GN) ? 2 : 1;           // rows per warp in flight (more loads outstanding); the
+                                                           // conv-branch variant keeps one row: registers -> occupancy
   const int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW;
   const int lane = threadIdx.x & 31;
   if (row0 >= rows) return;
@@ -84,7 +116,31 @@ residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residua
       float o[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) o[k] = (v[r][i][k] - s[r]) * rstd * g[k] + bt[k];
-      if (post_add) {
+      if (GN) {
+        const int64_t row = row0 + r;
+        const uint32_t row32 = (uint32_t)row;                       // the launcher checks rows < 2^31
+        const uint32_t b = row32 / (uint32_t)gn.Lv;
+        const int t = (int)(row32 - b * (uint32_t)gn.Lv);
+        int l = 0;
+        while (l + 1 < gn.L && t >= gn.lv.start[l + 1]) ++l;
+        const int cpg = N / gn.G;                                   // VEC <= cpg: the vector lies in one group
+        const float inv_cnt = 1.f / (float)(gn.lv.H[l] * gn.lv.W[l] * cpg);
+        const float2 st = __ldg(reinterpret_cast<const float2*>(gn.stats) + ((b * gn.L + l) * gn.G + c / cpg));
+        const float mean = st.x * inv_cnt;
+        const float grstd = rsqrtf(fmaxf(st.y * inv_cnt - mean * mean, 0.f) + gn.eps);
+        float cv[VEC], sk[VEC], gg[VEC], gb[VEC];
+        Vec16<T>::load(reinterpret_cast<const T*>(gn.conv) + row * N + c, cv);
+        Vec16<T>::load(reinterpret_cast<const T*>(gn.skip) + row * N + c, sk);
+#pragma unroll
+        for (int k = 0; k < VEC; k += 4) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gn.gamma + l * N + c + k));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(gn.beta + l * N + c + k));
+          gg[k] = g4.x * grstd; gg[k + 1] = g4.y * grstd; gg[k + 2] = g4.z * grstd; gg[k + 3] = g4.w * grstd;
+          gb[k] = b4.x; gb[k + 1] = b4.y; gb[k + 2] = b4.z; gb[k + 3] = b4.w;
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] += gelu_erf(fmaf(cv[k] - mean, gg[k], gb[k])) + sk[k];
+      } else if (post_add) {
         float p[VEC];
         Vec16<T>::load(post_add + (row0 + r) * N + c, p);
 #pragma unroll
@@ -220,7 +276,7 @@ groupnorm_gelu_residual_kernel(const T* __restrict__ conv, const T* __restrict__
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const float h = (cv[k] - mean) * rstd * g[k] + bt[k];
-    o[k] = 0.5f * h * (1.f + erff(h * 0.70710678118654752f)) + xv[k];
+    o[k] = gelu_erf(h) + xv[k];
   }
   Vec16<T>::store(y + off, o);
 }
@@ -243,6 +299,37 @@ nchw_to_tokens_kernel(const T* __restrict__ x, T* __restrict__ y, int C, int P) 
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
     if (c < C && p < P) y[(b * P + p) * C + c] = tile[tx][i];
+  }
+}
+
+// bf16, P % 64 == 0, C % 64 == 0: 64 x 64 tiles moved with 16-byte global accesses on both sides (full 128-byte lines:
+// a warp reads 4 channel rows x 64 pixels and writes 4 pixel rows x 64 channels); the transposition itself happens on
+// 2-byte shared-memory reads (row pitch 33 words: conflict-free 32-bit stores, 2-way conflicts on the 16-bit loads).
+__global__ void __launch_bounds__(256)
+nchw_to_tokens_bf16_64_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int P) {
+  __shared__ uint32_t tile[64 * 33];                         // [c][p / 2], pitch 33 words
+  const int64_t b = blockIdx.z;
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int r = threadIdx.x >> 3, ch = threadIdx.x & 7;      // 32 rows x 8 16-byte chunks per pass
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = r + 32 * h;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (b * C + c0 + c) * P + p0 + ch * 8));
+    uint32_t* dst = tile + c * 33 + ch * 4;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+  __syncthreads();
+  const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int pp = r + 32 * h;                               // pixel row of the output
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = t16[(ch * 8 + 2 * j) * 66 + pp], hi = t16[(ch * 8 + 2 * j + 1) * 66 + pp];
+      w[j] = lo | (hi << 16);
+    }
+    *reinterpret_cast<uint4*>(y + (b * P + p0 + pp) * C + c0 + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -281,22 +368,76 @@ int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int L
                       cudaStream_t st);
 }
 
+static int launch_residual_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
+                                     const void* post_add, void* y, int64_t rows, int N, float eps, int dtype,
+                                     const GnBranch* gnb, void* stream);
+
 extern "C" int emrt_residual_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
                                        const void* post_add, void* y, int64_t rows, int N, float eps, int dtype,
                                        void* stream) {
+  return launch_residual_layernorm(x, residual, gamma, beta, post_add, y, rows, N, eps, dtype, nullptr, stream);
+}
+
+static int check_gn_args(int B, int C, int groups) {
+  EMRT_REQUIRE(B > 0 && C > 0 && groups > 0 && C % groups == 0 && C % 8 == 0 && C <= 2048, "bad channel / group counts");
+  const int cpg = C / groups;
+  EMRT_REQUIRE(cpg % 8 == 0 || 8 % cpg == 0, "channels per group must divide or be a multiple of 8");
+  if (8 % cpg == 0 && cpg != 8) return set_error(EMRT_ERR_UNSUPPORTED, "channels per group < 8 not supported");
+  return EMRT_OK;
+}
+
+extern "C" int emrt_groupnorm_stats(const void* x, float* stats, int B, int Lv, int C, int L, int groups,
+                                    const int32_t* shapes_hw_host, int dtype, void* stream) {
+  EMRT_REQUIRE(x && stats, "NULL pointer");
+  if (int e = check_gn_args(B, C, groups)) return e;
+  LevelTable lv;
+  if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, Lv)) return e;
+  cudaStream_t st = as_stream(stream);
+  EMRT_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * L * groups, st));
+  dim3 sgrid((unsigned)(B * L), 16);
+  if (dtype == EMRT_F32) groupnorm_stats_kernel<float><<<sgrid, 256, 0, st>>>((const float*)x, stats, Lv, C, L, groups, lv);
+  else if (dtype == EMRT_BF16) groupnorm_stats_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>((const __nv_bfloat16*)x, stats, Lv, C, L, groups, lv);
+  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_residual_layernorm_gn(const void* x, const void* residual, const float* ln_gamma, const float* ln_beta,
+                                          const void* conv, const void* skip, const float* gn_stats, const float* gn_gamma,
+                                          const float* gn_beta, void* y, int B, int Lv, int C, int L, int groups,
+                                          float ln_eps, float gn_eps, const int32_t* shapes_hw_host, int dtype,
+                                          void* stream) {
+  EMRT_REQUIRE(conv && skip && gn_stats && gn_gamma && gn_beta, "NULL pointer");
+  if (int e = check_gn_args(B, C, groups)) return e;
+  GnBranch g;
+  if (int e = fill_levels(g.lv, L, shapes_hw_host, nullptr, Lv)) return e;
+  g.conv = conv; g.skip = skip; g.stats = gn_stats; g.gamma = gn_gamma; g.beta = gn_beta;
+  g.Lv = Lv; g.L = L; g.G = groups; g.eps = gn_eps;
+  EMRT_REQUIRE((int64_t)B * Lv < (1LL << 31), "B * Lv must fit 31 bits");
+  return launch_residual_layernorm(x, residual, ln_gamma, ln_beta, nullptr, y, (int64_t)B * Lv, C, ln_eps, dtype, &g, stream);
+}
+
+static int launch_residual_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
+                                     const void* post_add, void* y, int64_t rows, int N, float eps, int dtype,
+                                     const GnBranch* gnb, void* stream) {
   EMRT_REQUIRE(x && gamma && beta && y && rows > 0, "bad residual_layernorm arguments");
   const int vec = dtype == EMRT_F32 ? 4 : 8;
   EMRT_REQUIRE(N > 0 && N % (32 * vec) == 0 && N / (32 * vec) <= 8, "N must be a multiple of 32 16-byte vectors, at most 8 per lane");
   cudaStream_t st = as_stream(stream);
   const int per = N / (32 * vec);
-  const int64_t warps = per <= 2 ? (rows + 1) / 2 : rows;       // RPW rows per warp
+  const int64_t warps = (per <= 2 && !gnb) ? (rows + 1) / 2 : rows;       // RPW rows per warp
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
-#define EMRT_LN(T, PER) residual_layernorm_kernel<T, PER><<<blocks, 256, 0, st>>>((const T*)x, (const T*)residual, gamma, beta, (const T*)post_add, (T*)y, rows, N, eps)
+  GnBranch gn_arg;
+  memset(&gn_arg, 0, sizeof(gn_arg));
+  if (gnb) gn_arg = *gnb;
+#define EMRT_LN(T, PER)                                                                                                   \
+  if (gnb) residual_layernorm_kernel<T, PER, true><<<blocks, 256, 0, st>>>((const T*)x, (const T*)residual, gamma, beta, (const T*)post_add, (T*)y, rows, N, eps, gn_arg); \
+  else residual_layernorm_kernel<T, PER, false><<<blocks, 256, 0, st>>>((const T*)x, (const T*)residual, gamma, beta, (const T*)post_add, (T*)y, rows, N, eps, gn_arg)
 #define EMRT_LN_PER(T)                                                                       \
   switch (per) {                                                                               \
-    case 1: EMRT_LN(T, 1); break; case 2: EMRT_LN(T, 2); break; case 3: EMRT_LN(T, 3); break;  \
-    case 4: EMRT_LN(T, 4); break; case 5: EMRT_LN(T, 5); break; case 6: EMRT_LN(T, 6); break;  \
-    case 7: EMRT_LN(T, 7); break; default: EMRT_LN(T, 8); break;                               \
+    case 1: { EMRT_LN(T, 1); } break; case 2: { EMRT_LN(T, 2); } break; case 3: { EMRT_LN(T, 3); } break;  \
+    case 4: { EMRT_LN(T, 4); } break; case 5: { EMRT_LN(T, 5); } break; case 6: { EMRT_LN(T, 6); } break;  \
+    case 7: { EMRT_LN(T, 7); } break; default: { EMRT_LN(T, 8); } break;                               \
   }
   if (dtype == EMRT_F32) { EMRT_LN_PER(float) }
   else if (dtype == EMRT_BF16) { EMRT_LN_PER(__nv_bfloat16) }
@@ -374,8 +515,13 @@ extern "C" int emrt_nchw_to_tokens(const void* x, void* y, int B, int C, int P, 
   dim3 grid((P + 31) / 32, (C + 31) / 32, B);
   cudaStream_t st = as_stream(stream);
   if (dtype == EMRT_F32) nchw_to_tokens_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, C, P);
-  else if (dtype == EMRT_BF16) nchw_to_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, C, P);
-  else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  else if (dtype == EMRT_BF16) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (P % 64 == 0 && C % 64 == 0 && aligned && P / 64 <= 65535 && C / 64 <= 65535)
+      nchw_to_tokens_bf16_64_kernel<<<dim3(P / 64, C / 64, B), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, C, P);
+    else
+      nchw_to_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, C, P);
+  } else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
 }

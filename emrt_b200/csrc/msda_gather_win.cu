@@ -157,7 +157,10 @@ __device__ __forceinline__ void raw_decode(const RawLoc<__nv_bfloat16>& r, float
 constexpr int WIN_ROUNDS = (WIN_QPB * WIN_LP + 31) / 32;   // stage-A rounds: one (query, point) per lane per round
 constexpr int WIN_MAX_Q = 512;                             // queries per region (TH*TW*(1 + 1/4 + 1/16)), upper bound
 
-template <typename TL, int MODE, int WIN_WARPS>
+// STATIC: batches are dealt to the warps round-robin (no shared counter) — right when the batch count of a region is a
+// multiple of the warp count (168 queries = 42 batches = 7 warps x 6); otherwise the warps claim batches dynamically, so
+// none idles while the CTA's shared-memory windows stay resident.
+template <typename TL, int MODE, int WIN_WARPS, bool STATIC>
 __global__ void __launch_bounds__(WIN_WARPS * 32, 2)
 msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __restrict__ loc,
                            const TL* __restrict__ attn, const float* __restrict__ ref, int64_t ref_bs,
@@ -216,7 +219,7 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
 
   // ---- per-lane stage-A constants: round r handles (query qi[r], point pt[r]) of every batch ------------------------
   int a_qi[WIN_ROUNDS], a_pt[WIN_ROUNDS], a_ox[WIN_ROUNDS], a_oy[WIN_ROUNDS], a_ww[WIN_ROUNDS], a_wh[WIN_ROUNDS];
-  uint32_t a_base[WIN_ROUNDS];
+  uint32_t a_base[WIN_ROUNDS], a_rec[WIN_ROUNDS], a_l2[WIN_ROUNDS];
   float a_W[WIN_ROUNDS], a_H[WIN_ROUNDS];
   bool a_on[WIN_ROUNDS];
 #pragma unroll
@@ -231,6 +234,8 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
     a_ww[r] = p.WW[l];
     a_wh[r] = p.WH[l];
     a_base[r] = smem_base + p.win_off[l];
+    a_rec[r] = (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]);
+    a_l2[r] = (uint32_t)l * 2u;
     a_W[r] = (float)p.lv.W[l];
     a_H[r] = (float)p.lv.H[l];
   }
@@ -242,6 +247,7 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
   const TL* loc_bm = loc + (((int64_t)b * p.Lq) * p.M + m) * (WIN_LP * 2);
   const TL* attn_bm = attn + (((int64_t)b * p.Lq) * p.M + m) * WIN_LP;
   const float* ref_b = ref + (MODE == EMRT_LOC_PIXEL_OFFSET ? b * ref_bs : 0);
+  __nv_bfloat16* out_bm = out + (((int64_t)b * p.Lq) * p.M + m) * WIN_D + (s & 3) * 8 + side * 4;
   auto fetch = [&](int batch) {
 #pragma unroll
     for (int r = 0; r < WIN_ROUNDS; ++r) {
@@ -250,7 +256,7 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
       const uint32_t e = qq * (uint32_t)p.M * WIN_LP + (uint32_t)a_pt[r];
       raw_fetch(raw[r], loc_bm + 2u * e, attn_bm + e);
       if (MODE == EMRT_LOC_PIXEL_OFFSET)
-        rref[r] = __ldg(reinterpret_cast<const float2*>(ref_b + (qq * WIN_L + (uint32_t)(a_pt[r] / WIN_P)) * 2u));
+        rref[r] = __ldg(reinterpret_cast<const float2*>(ref_b + (qq * (WIN_L * 2u) + a_l2[r])));
     }
   };
 
@@ -260,6 +266,7 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
 
   while (batch < n_batches) {
     // ---- stage A: one footprint record per (query, point), from the prefetched inputs -----------------------------
+    unsigned slow_lv = 0u;
 #pragma unroll
     for (int r = 0; r < WIN_ROUNDS; ++r) {
       if (a_on[r]) {
@@ -273,32 +280,42 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
           x = x * a_W[r] - 0.5f;
           y = y * a_H[r] - 0.5f;
         }
-        // a sample whose four corners are all outside the map contributes exactly zero (also rejects NaN / inf)
-        const bool live = (q >= 0) && (x > -1.f) && (y > -1.f) && (x < a_W[r]) && (y < a_H[r]);
-        const float xs = live ? x : 0.f, ys = live ? y : 0.f;
-        const float x0f = floorf(xs), y0f = floorf(ys);
-        const float fx = xs - x0f, fy = ys - y0f;
-        const int wx = (int)x0f - a_ox[r], wy = (int)y0f - a_oy[r];
-        const bool inwin = (unsigned)wx < (unsigned)(a_ww[r] - 1) && (unsigned)wy < (unsigned)(a_wh[r] - 1);
+        // The window lies inside [-1, W] x [-1, H], so "both pixel pairs inside the window" implies the sample is live;
+        // the fmaxf sends NaN (whose float -> int conversion is 0) and -inf below every window origin (>= -1).
+        const float x0f = floorf(x), y0f = floorf(y);
+        const float fx = x - x0f, fy = y - y0f;
+        const int wx = (int)fmaxf(x0f, -2.f) - a_ox[r], wy = (int)fmaxf(y0f, -2.f) - a_oy[r];
+        const bool fast = (q >= 0) && (unsigned)wx < (unsigned)(a_ww[r] - 1) && (unsigned)wy < (unsigned)(a_wh[r] - 1);
         const float gx = 1.f - fx, gy = 1.f - fy;
-        const bool fast = live && inwin;
-        // not live: weight 0 on the zero block.  live but outside the window: same, plus the SLOW flag
-        // not live: weight 0 on the zero block.  live but outside the window: the zero block again (so the fast path adds
-        // nothing), the SLOW flag in the sign bit of the bottom weight, the attention weight in the low half and the sample
-        // position in the side buffer for the fix-up
-        const uint32_t addr = fast ? a_base[r] + (uint32_t)(wy * a_ww[r] + wx) * (WIN_D * 2) : smem_base;
-        const uint32_t wnone = live ? (WIN_SLOW | (pack_bf16(aw, 0.f) & 0xffffu)) : 0u;
-        if (live && !inwin)
-          asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(xy_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 8), "f"(x), "f"(y) : "memory");
-        const uint32_t wl = fast ? pack_bf16(gx * gy * aw, gx * fy * aw) : wnone;   // left pixel: top, bottom
-        const uint32_t wr = fast ? pack_bf16(fx * gy * aw, fx * fy * aw) : wnone;   // right pixel: top, bottom
-        sts128(rec_base + (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]) * 16, addr, wl, addr, wr);
+        const float gxa = gx * aw, fxa = fx * aw;
+        uint32_t addr = a_base[r] + (uint32_t)(wy * a_ww[r] + wx) * (WIN_D * 2);
+        uint32_t wl = pack_bf16(gxa * gy, gxa * fy);   // left pixel: top, bottom
+        uint32_t wr = pack_bf16(fxa * gy, fxa * fy);   // right pixel: top, bottom
+        if (!fast) {
+          // a sample whose four corners are all outside the map contributes exactly zero (also rejects NaN / inf):
+          // weight 0 on the zero block.  Live but outside the window: the zero block again (so the fast path adds
+          // nothing), the SLOW flag in the sign bit of the bottom weight, the attention weight in the low half and the
+          // sample position in the side buffer for the fix-up
+          const bool live = (q >= 0) && (x > -1.f) && (y > -1.f) && (x < a_W[r]) && (y < a_H[r]);
+          addr = smem_base;
+          wl = wr = live ? (WIN_SLOW | (pack_bf16(aw, 0.f) & 0xffffu)) : 0u;
+          if (live) {
+            asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(xy_base + a_rec[r] * 8), "f"(x), "f"(y) : "memory");
+            slow_lv |= 1u << (a_l2[r] >> 1);
+          }
+        }
+        sts128(rec_base + a_rec[r] * 16, addr, wl, addr, wr);
       }
     }
     // next batch: claim it and start its loads now, they land while this batch gathers
     const int cur = batch;
-    if (lane == 0) batch = atomicAdd(&s_next, 1);
-    batch = __shfl_sync(0xffffffffu, batch, 0);
+    if (STATIC) {
+      batch += WIN_WARPS;
+    } else {
+      if (lane == 0) batch = atomicAdd(&s_next, 1);
+      batch = __shfl_sync(0xffffffffu, batch, 0);
+    }
+    const unsigned slow_levels = __reduce_or_sync(0xffffffffu, slow_lv);   // levels of this batch with a fix-up point
     if (batch < n_batches) fetch(batch);
     __syncwarp();
     if (!windows_ready) {
@@ -317,13 +334,10 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
       const uint32_t row_bytes = (uint32_t)p.WW[l] * (WIN_D * 2);
       // the level's six records first: {address, this side's weight pair}, 8 bytes per lane
       uint32_t addr[WIN_P], wpair[WIN_P];
-      uint32_t flags = 0u;
 #pragma unroll
-      for (int pp = 0; pp < WIN_P; ++pp) {
+      for (int pp = 0; pp < WIN_P; ++pp)
         asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(addr[pp]), "=r"(wpair[pp])
                      : "r"(my_rec + (l * WIN_P + pp) * 16 + side * 8));
-        flags |= wpair[pp];
-      }
       // branch-free fast path in two halves of three points: six independent LDS.128 in flight, then 48 FHFMA
       // (flagged records carry weight -0.0 on the zero block)
 #pragma unroll
@@ -341,8 +355,8 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
           fma_row<1>(acc, d1[pp], wpair[h + pp]);
         }
       }
-      if (__any_sync(0xffffffffu, (flags & WIN_SLOW) != 0u)) {
-        // fix-ups: points that left the staged window but not the map read global memory
+      if (slow_levels & (1u << l)) {
+        // fix-ups (warp-uniform branch, rare): points that left the staged window but not the map read global memory
 #pragma unroll 1
         for (int pp = 0; pp < WIN_P; ++pp) {
           uint32_t w = wpair[0];
@@ -371,7 +385,7 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
       uint2 o;
       o.x = pack_bf16(keep[0], keep[1]);
       o.y = pack_bf16(keep[2], keep[3]);
-      *reinterpret_cast<uint2*>(out + (((int64_t)b * p.Lq + q) * p.M + m) * WIN_D + (s & 3) * 8 + side * 4) = o;
+      *reinterpret_cast<uint2*>(out_bm + (uint32_t)q * (uint32_t)(p.M * WIN_D)) = o;
     }
     __syncwarp();   // records are rewritten by the next batch
   }
@@ -383,10 +397,10 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <typename TL, int MODE, int NW>
+template <typename TL, int MODE, int NW, bool STATIC>
 static int launch_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
                       int B, const WinParams& p, size_t smem_bytes, cudaStream_t st) {
-  auto kern = msda_gather_fwd_win_kernel<TL, MODE, NW>;
+  auto kern = msda_gather_fwd_win_kernel<TL, MODE, NW, STATIC>;
   static size_t attr = 0;
   if (smem_bytes > attr) {
     EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -436,16 +450,23 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
       return e;
   }
   p.rec_off = off;
-  const int warps = env_int("EMRT_WIN_WARPS", 8) == 12 ? 12 : 8;
+  // 7 warps x 6 batches covers the default 8 x 16 region (42 batches of 4 queries) exactly: static dealing, no counter
+  const int n_batches = (p.TH * p.TW + (p.TH >> 1) * (p.TW >> 1) + (p.TH >> 2) * (p.TW >> 2) + WIN_QPB - 1) / WIN_QPB;
+  int warps = env_int("EMRT_WIN_WARPS", 8);
+  if (warps != 7 && warps != 12) warps = 8;
+  const bool stat = env_int("EMRT_WIN_STATIC", -1) >= 0 ? env_int("EMRT_WIN_STATIC", 0) != 0 : (n_batches % warps == 0);
   const size_t smem_bytes = (size_t)off + (size_t)warps * WIN_QPB * WIN_LP * (16 + 8);   // records + slow-point positions
   if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(value) & 15) != 0) return EMRT_ERR_UNSUPPORTED;
   const bool px = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;
-#define EMRT_WIN(TL)                                                                                             \
-  if (warps == 12) return px ? launch_win<TL, 1, 12>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)     \
-                             : launch_win<TL, 0, 12>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);    \
-  return px ? launch_win<TL, 1, 8>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)                       \
-            : launch_win<TL, 0, 8>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)
+#define EMRT_WIN_NW(TL, NW)                                                                                       \
+  if (warps == NW) {                                                                                               \
+    if (stat) return px ? launch_win<TL, 1, NW, true>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)    \
+                        : launch_win<TL, 0, NW, true>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);   \
+    return px ? launch_win<TL, 1, NW, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)             \
+              : launch_win<TL, 0, NW, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);            \
+  }
+#define EMRT_WIN(TL) EMRT_WIN_NW(TL, 7) EMRT_WIN_NW(TL, 12) EMRT_WIN_NW(TL, 8) return EMRT_ERR_UNSUPPORTED
   switch (loc_dtype) {
     case EMRT_F32: EMRT_WIN(float);
     case EMRT_F16: EMRT_WIN(__half);
@@ -453,6 +474,7 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
     default: return EMRT_ERR_UNSUPPORTED;
   }
 #undef EMRT_WIN
+#undef EMRT_WIN_NW
 }
 
 }  // namespace emrt

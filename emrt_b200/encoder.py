@@ -92,8 +92,9 @@ class TransformerEncoderLayer(nn.Module):
         fast = src.dtype == torch.bfloat16
         impl = self.gemm_impl if fast else L.IMPL_SIMT
         # conv branch (:185-196): conv3x3 -> GroupNorm(32) -> GELU, + skip, on the token layout
+        # (GroupNorm + GELU + skip are applied inside the last LayerNorm pass below: the branch tensor never exists)
         conv = ops.conv3x3_tokens(src, pk["conv_w"], shapes, impl=L.IMPL_AUTO if impl != L.IMPL_SIMT else L.IMPL_SIMT)
-        branch = ops.groupnorm_gelu_residual(conv, src, pk["gn_w"], pk["gn_b"], shapes, groups=32, out=conv)
+        gn_stats = ops.groupnorm_stats(conv, shapes, groups=32)
         # self attention (:198) + norm1 (:199-200)
         q = src if pos_embed is None else ops.add_bcast(src, pos_embed.to(src.dtype).contiguous())
         src2 = self.self_attn(q, reference_points, src, shapes, src_mask)
@@ -105,7 +106,8 @@ class TransformerEncoderLayer(nn.Module):
         else:
             h = ops.linear(x, self.linear1.weight.detach(), pk["b1"], epilogue=L.EPI_RELU, impl=L.IMPL_SIMT)
             f = ops.linear(h, self.linear2.weight.detach(), pk["b2"], impl=L.IMPL_SIMT)
-        return ops.residual_layernorm(f, x, pk["n2w"], pk["n2b"], post_add=branch, out=f)
+        return ops.residual_layernorm_gn(f, x, pk["n2w"], pk["n2b"], conv, src, gn_stats, pk["gn_w"], pk["gn_b"], shapes,
+                                         groups=32, out=f)
 
 
 class TransformerEncoder(nn.Module):

@@ -247,6 +247,29 @@ def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, o
     return out
 
 
+def groupnorm_stats(x, shapes, groups=32):
+    """(sum, sum of squares) per (batch, level, group) of x [B, Lv, C] -> f32 [B, L, groups, 2]."""
+    B, Lv, C = x.shape
+    hw, _, _ = level_tables(shapes)
+    st = torch.empty((B, len(shapes), groups, 2), dtype=torch.float32, device=x.device)
+    L.check(L.load().emrt_groupnorm_stats(_ptr(x), _ptr(st), B, Lv, C, len(shapes), groups, hw, _dt(x), _stream()))
+    return st
+
+
+def residual_layernorm_gn(x, residual, ln_gamma, ln_beta, conv, skip, gn_stats, gn_gamma, gn_beta, shapes, groups=32,
+                          ln_eps=1e-5, gn_eps=1e-5, out=None):
+    """y = LayerNorm(x + residual) * ln_gamma + ln_beta + GELU(GroupNorm_l(conv)) + skip (t_e_d.py:159-160,187-189,203):
+    the conv branch is evaluated inside the LayerNorm pass from the conv output and groupnorm_stats' sums."""
+    B, Lv, C = x.shape
+    hw, _, _ = level_tables(shapes)
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().emrt_residual_layernorm_gn(_ptr(x), _ptr(residual), _ptr(ln_gamma), _ptr(ln_beta), _ptr(conv), _ptr(skip),
+                                                _ptr(gn_stats), _ptr(gn_gamma), _ptr(gn_beta), _ptr(out), B, Lv, C,
+                                                len(shapes), groups, float(ln_eps), float(gn_eps), hw, _dt(x), _stream()))
+    return out
+
+
 def nchw_to_tokens(x):
     """[B, C, *spatial] -> tokens [B, prod(spatial), C]."""
     B, C_ = x.shape[:2]

@@ -181,6 +181,18 @@ int emrt_groupnorm_gelu_residual(const void* conv, const void* x, const float* g
                                  float* stats_workspace, int B, int Lv, int C, int L, int groups, float eps,
                                  const int32_t* shapes_hw_host, int dtype, void* stream);
 
+/* The same conv branch without ever materialising it: emrt_groupnorm_stats leaves the per (batch, level, group) sums
+ * (sum, sum of squares; F32 [B, L, groups, 2]) of x [B, Lv, C]; emrt_residual_layernorm_gn then evaluates
+ *   y = LayerNorm(x + residual) * ln_gamma + ln_beta + GELU(GroupNorm_l(conv)) + skip
+ * i.e. norm2 (:159-160) plus the layer's final `src + src_flatten` (:203) with src_flatten = conv branch (:187-196)
+ * computed on the fly from the conv output, the layer input (skip) and those sums.  All tensors [B, Lv, C].            */
+int emrt_groupnorm_stats(const void* x, float* stats, int B, int Lv, int C, int L, int groups,
+                         const int32_t* shapes_hw_host, int dtype, void* stream);
+int emrt_residual_layernorm_gn(const void* x, const void* residual, const float* ln_gamma, const float* ln_beta,
+                               const void* conv, const void* skip, const float* gn_stats, const float* gn_gamma,
+                               const float* gn_beta, void* y, int B, int Lv, int C, int L, int groups, float ln_eps,
+                               float gn_eps, const int32_t* shapes_hw_host, int dtype, void* stream);
+
 /* ---- input_proj glue (EncoderDecoder.forward, transformer_encoder_decoder.py:417-436,469) --------------------------
  * y[b, p, c] = x[b, c, p]: NCHW feature maps [B, C, P = H*W] (or src_psp [B, 256, 110]) -> tokens [B, P, C].            */
 int emrt_nchw_to_tokens(const void* x, void* y, int B, int C, int P, int dtype, void* stream);

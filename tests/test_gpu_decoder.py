@@ -105,3 +105,12 @@ def test_encoder_decoder_bf16_matches_oracle(cuda_dev):
     l2 = lambda got, want: ((got.double().cpu() - want).norm() / want.norm()).item()
     assert l2(mem.float(), wmem) < 2e-2 and l2(hs.float(), whs) < 2e-2
     assert rel_err(mem.float(), wmem) < 1e-1 and rel_err(hs.float(), whs) < 1e-1
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,C,P", [(2, 512, 4096), (3, 256, 110), (1, 2048, 64), (2, 64, 192), (1, 96, 64)])
+def test_nchw_to_tokens_is_an_exact_transpose(cuda_dev, dtype, B, C, P):
+    """Both kernels (generic 32x32 tiles; bf16 64x64 tiles with 16-byte accesses when C and P are multiples of 64)."""
+    x = torch.randn(B, C, P, generator=torch.Generator().manual_seed(P)).to(dtype)
+    got = ops.nchw_to_tokens(x.to(cuda_dev))
+    assert torch.equal(got.cpu(), x.permute(0, 2, 1).contiguous())

@@ -87,6 +87,36 @@ def test_groupnorm_gelu_residual(cuda_dev, dtype):
     assert rel_err(got.float(), want) < (1e-4 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_with_conv_branch_fused(cuda_dev, dtype):
+    """norm2 + the layer's final `src + src_flatten` with the conv branch (GroupNorm + GELU + skip) evaluated inside
+    the LayerNorm pass (emrt_groupnorm_stats + emrt_residual_layernorm_gn) against float64 torch."""
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    B, C = 3, 256
+    rng = np.random.Generator(np.random.PCG64(19))
+    start, Lv = O.level_tables(shapes)
+    mk = lambda std=1.0, shift=0.0: torch.from_numpy(O.rng_normal(rng, (B, Lv, C), std) + np.float32(shift)).to(dtype)
+    f, x, conv, src = mk(), mk(), mk(2.0, 0.5), mk()
+    lw = torch.from_numpy(rng.uniform(0.5, 1.5, size=(C,)).astype(np.float32))
+    lb = torch.from_numpy(O.rng_normal(rng, (C,), 0.1))
+    gw = torch.from_numpy(rng.uniform(0.5, 1.5, size=(3, C)).astype(np.float32))
+    gb = torch.from_numpy(O.rng_normal(rng, (3, C), 0.1))
+    outs = []
+    for l, (h, w) in enumerate(shapes):
+        c = conv[:, start[l]:start[l] + h * w].double().permute(0, 2, 1).reshape(B, C, h, w)
+        y = F.gelu(F.group_norm(c, 32, gw[l].double(), gb[l].double(), 1e-5))
+        outs.append(y.flatten(2).permute(0, 2, 1) + src[:, start[l]:start[l] + h * w].double())
+    want = F.layer_norm(f.double() + x.double(), (C,), lw.double(), lb.double(), 1e-5) + torch.cat(outs, 1)
+    d = lambda t: t.to(cuda_dev)
+    st = ops.groupnorm_stats(d(conv), shapes)
+    got = ops.residual_layernorm_gn(d(f), d(x), d(lw), d(lb), d(conv), d(src), st, d(gw), d(gb), shapes)
+    assert rel_err(got.float(), want) < (1e-4 if dtype == torch.float32 else 1e-2)
+    # and it equals the two-kernel formulation
+    branch = ops.groupnorm_gelu_residual(d(conv), d(src), d(gw), d(gb), shapes)
+    two = ops.residual_layernorm(d(f), d(x), d(lw), d(lb), post_add=branch)
+    assert rel_err(got.float(), two.float().cpu()) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
 def _load_layer(layer, params, prefix):
     with torch.no_grad():
         sd = layer.state_dict()
