@@ -70,6 +70,7 @@ SIGNATURES = {
     "emrt_window_accumulate": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "emrt_finalize_argmax": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "emrt_stitch_argmax_fused": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "emrt_stitch_argmax_eval": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "emrt_calculate_area": (C.c_int, [_P, _P, _L, _I, _I, _P, _P]),
 }
 

@@ -7,6 +7,8 @@
 // order (deterministic, no atomics, no full-resolution fp32 canvas round trip).
 #include <cstdlib>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace emrt {
@@ -281,19 +283,40 @@ __device__ __forceinline__ void quad_accumulate(const T* __restrict__ src, int n
 
 constexpr int QTILE = 32;   // label pixels per CTA side: 16 x 16 threads, one quad each
 
-template <typename T, int NC>
+// Evaluation extras of the fused kernel: the label map goes straight into
+//   * metrics.calculate_area's per-class areas (src/utils/metrics.py:20-69, ignore-index contract) per image, and
+//   * predict.py:171-174's palette image (uint8 [n_img, H, W, 3], colour = palette[class]),
+// so neither the one-hot tensors nor a second pass over the labels exist.
+struct StitchEval {
+  const void* gt;                // ground-truth labels [n_img, H, W] (I32 | U8) or NULL
+  int gt_dtype;
+  int ignore_index;
+  unsigned long long* areas;     // [n_img, 3, nc]: intersect, pred, label (accumulated)
+  const uint8_t* palette;        // [nc, 3] or NULL
+  uint8_t* color;                // [n_img, H, W, 3] or NULL
+};
+
+template <typename T, int NC, bool EVAL>
 __global__ void __launch_bounds__(256)
 stitch_argmax_quad_kernel(const T* __restrict__ half_logits, void* __restrict__ labels, int label_dtype,
                           float* __restrict__ logits_out, int n_win, int nc, int hc, int wc, int H, int W,
                           const int32_t* __restrict__ win_img, const int32_t* __restrict__ win_y0,
-                          const int32_t* __restrict__ win_x0) {
+                          const int32_t* __restrict__ win_x0, const __grid_constant__ StitchEval ev) {
   __shared__ WinList wl;
   __shared__ int warp_cnt[8];
+  __shared__ unsigned int hist[3 * NC];
   const int img = blockIdx.z;
   const int tx0 = blockIdx.x * QTILE, ty0 = blockIdx.y * QTILE;
+  if (EVAL) {
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < 3 * NC) hist[t] = 0u;          // ordered before its use by the barriers inside build_window_list
+  }
   build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, QTILE, QTILE, hc, wc, win_img, win_y0, win_x0);
   const int x = tx0 + 2 * threadIdx.x, y = ty0 + 2 * threadIdx.y;
-  if (x >= W || y >= H) return;
+  const bool inside = x < W && y < H;
+  if (!EVAL && !inside) return;
+  int gt_lab[4] = {0, 0, 0, 0}, pred_lab[4] = {-1, -1, -1, -1};
+  if (inside) {
   const int hh = hc / 2, hw = wc / 2;
   const int n = wl.n < 0 ? n_win : wl.n;
   float acc[4][NC];
@@ -359,6 +382,50 @@ stitch_argmax_quad_kernel(const T* __restrict__ half_logits, void* __restrict__ 
       *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(labels) + (int64_t)img * plane + o) =
           make_int2(best[oy * 2], best[oy * 2 + 1]);
     }
+    if (EVAL && ev.color) {
+      uint8_t* dst = ev.color + ((int64_t)img * plane + o) * 3;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) dst[k * 3 + ch] = __ldg(ev.palette + best[oy * 2 + k] * 3 + ch);
+    }
+    if (EVAL && ev.gt) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int64_t gi = (int64_t)img * plane + o + k;
+        gt_lab[oy * 2 + k] = ev.gt_dtype == EMRT_U8 ? (int)__ldg(reinterpret_cast<const uint8_t*>(ev.gt) + gi)
+                                                    : __ldg(reinterpret_cast<const int32_t*>(ev.gt) + gi);
+        pred_lab[oy * 2 + k] = best[oy * 2 + k];
+      }
+    }
+  }
+  }   // inside
+  if (EVAL && ev.gt) {
+    // metrics.calculate_area: mask = label != ignore_index; areas of pred / label / their intersection per class.
+    // One ballot per (pixel slot, class, area kind): a warp adds its counts with 3 * nc shared-memory atomics.
+    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c >= nc) break;
+      unsigned n_i = 0, n_p = 0, n_l = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool keep = inside && gt_lab[k] != ev.ignore_index;
+        const bool ip = keep && pred_lab[k] == c, il = keep && gt_lab[k] == c;
+        n_p += __popc(__ballot_sync(0xffffffffu, ip));
+        n_l += __popc(__ballot_sync(0xffffffffu, il));
+        n_i += __popc(__ballot_sync(0xffffffffu, ip && il));
+      }
+      if (lane == 0) {
+        if (n_i) atomicAdd(&hist[c], n_i);
+        if (n_p) atomicAdd(&hist[NC + c], n_p);
+        if (n_l) atomicAdd(&hist[2 * NC + c], n_l);
+      }
+    }
+    __syncthreads();
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < 3 * NC && (t % NC) < nc && hist[t])
+      atomicAdd(ev.areas + ((int64_t)img * 3 + t / NC) * nc + (t % NC), (unsigned long long)hist[t]);
   }
 }
 
@@ -427,28 +494,65 @@ extern "C" int emrt_finalize_argmax(const float* canvas, const float* count, voi
   return EMRT_OK;
 }
 
+static int stitch_argmax_launch(const void* half_logits, int in_dtype, void* labels, int label_dtype,
+                                float* logits_out, int n_win, int n_img, int nc, int hc, int wc, int H, int W,
+                                const int32_t* win_img, const int32_t* win_y0, const int32_t* win_x0,
+                                const StitchEval* eval, void* stream);
+
 extern "C" int emrt_stitch_argmax_fused(const void* half_logits, int in_dtype, void* labels, int label_dtype,
                                         float* logits_out, int n_win, int n_img, int nc, int hc, int wc, int H, int W,
                                         const int32_t* win_img, const int32_t* win_y0, const int32_t* win_x0,
                                         void* stream) {
+  return stitch_argmax_launch(half_logits, in_dtype, labels, label_dtype, logits_out, n_win, n_img, nc, hc, wc, H, W, win_img,
+                              win_y0, win_x0, nullptr, stream);
+}
+
+extern "C" int emrt_stitch_argmax_eval(const void* half_logits, int in_dtype, void* labels, int label_dtype, int n_win,
+                                       int n_img, int nc, int hc, int wc, int H, int W, const int32_t* win_img,
+                                       const int32_t* win_y0, const int32_t* win_x0, const void* gt, int gt_dtype,
+                                       int ignore_index, long long* areas, const uint8_t* palette, uint8_t* color,
+                                       void* stream) {
+  EMRT_REQUIRE((gt != nullptr) == (areas != nullptr), "gt and areas go together");
+  EMRT_REQUIRE((palette != nullptr) == (color != nullptr), "palette and color go together");
+  EMRT_REQUIRE(gt || color, "nothing to evaluate: use emrt_stitch_argmax_fused");
+  EMRT_REQUIRE(!gt || gt_dtype == EMRT_I32 || gt_dtype == EMRT_U8, "gt_dtype must be I32 or U8");
+  if (!(H % 2 == 0 && W % 2 == 0 && nc <= 8))
+    return set_error(EMRT_ERR_UNSUPPORTED, "the fused evaluation needs even H, W and nc <= 8 (got %d x %d, nc %d)", H, W, nc);
+  StitchEval ev;
+  ev.gt = gt; ev.gt_dtype = gt_dtype; ev.ignore_index = ignore_index;
+  ev.areas = reinterpret_cast<unsigned long long*>(areas); ev.palette = palette; ev.color = color;
+  return stitch_argmax_launch(half_logits, in_dtype, labels, label_dtype, nullptr, n_win, n_img, nc, hc, wc, H, W, win_img,
+                              win_y0, win_x0, &ev, stream);
+}
+
+static int stitch_argmax_launch(const void* half_logits, int in_dtype, void* labels, int label_dtype,
+                                float* logits_out, int n_win, int n_img, int nc, int hc, int wc, int H, int W,
+                                const int32_t* win_img, const int32_t* win_y0, const int32_t* win_x0,
+                                const StitchEval* eval, void* stream) {
   EMRT_REQUIRE(half_logits && labels && win_img && win_y0 && win_x0, "NULL pointer");
   EMRT_REQUIRE(n_win > 0 && n_img > 0 && nc > 0 && hc > 0 && wc > 0 && H > 0 && W > 0, "non-positive dimension");
   EMRT_REQUIRE(hc % 2 == 0 && wc % 2 == 0, "window size must be even (x2 upsample of the half-resolution logits)");
   EMRT_REQUIRE(label_dtype == EMRT_I32 || label_dtype == EMRT_U8, "label_dtype must be I32 or U8");
   if (nc > 32) return set_error(EMRT_ERR_UNSUPPORTED, "nc=%d > 32", nc);
   cudaStream_t st = as_stream(stream);
-  if (H % 2 == 0 && W % 2 == 0 && nc <= 8 && !getenv("EMRT_STITCH_PIXEL")) {
+  if (H % 2 == 0 && W % 2 == 0 && nc <= 8 && (eval || !getenv("EMRT_STITCH_PIXEL"))) {
     dim3 qgrid((W + QTILE - 1) / QTILE, (H + QTILE - 1) / QTILE, n_img), qblock(16, 16);
-    if (in_dtype == EMRT_F32)
-      stitch_argmax_quad_kernel<float, 8><<<qgrid, qblock, 0, st>>>((const float*)half_logits, labels, label_dtype, logits_out,
-                                                                     n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0);
-    else if (in_dtype == EMRT_BF16)
-      stitch_argmax_quad_kernel<__nv_bfloat16, 8><<<qgrid, qblock, 0, st>>>((const __nv_bfloat16*)half_logits, labels, label_dtype,
-                                                                             logits_out, n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0);
+    StitchEval ev;
+    memset(&ev, 0, sizeof(ev));
+    if (eval) ev = *eval;
+#define EMRT_QUAD(T)                                                                                                   \
+    if (eval) stitch_argmax_quad_kernel<T, 8, true><<<qgrid, qblock, 0, st>>>((const T*)half_logits, labels, label_dtype, \
+                  logits_out, n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0, ev);                                       \
+    else stitch_argmax_quad_kernel<T, 8, false><<<qgrid, qblock, 0, st>>>((const T*)half_logits, labels, label_dtype,       \
+                  logits_out, n_win, nc, hc, wc, H, W, win_img, win_y0, win_x0, ev)
+    if (in_dtype == EMRT_F32) { EMRT_QUAD(float); }
+    else if (in_dtype == EMRT_BF16) { EMRT_QUAD(__nv_bfloat16); }
     else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad in_dtype %d", in_dtype);
+#undef EMRT_QUAD
     EMRT_LAUNCH_CHECK();
     return EMRT_OK;
   }
+  if (eval) return set_error(EMRT_ERR_UNSUPPORTED, "the fused evaluation needs even H, W and nc <= 8");
   dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, n_img), block(TILE_X, TILE_Y);
 #define EMRT_ST(T, NC)                                                                                           \
   stitch_argmax_fused_kernel<T, NC><<<grid, block, 0, st>>>((const T*)half_logits, labels, label_dtype, logits_out, \

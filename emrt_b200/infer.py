@@ -162,3 +162,30 @@ def _ss_slide_fused(model, imgs, img_hw, crop_size, stride_size, window_batch, l
                                              xs[sel].contiguous(), 1, H, W, label_dtype=label_dtype)
             preds[i] = lab
     return preds
+
+
+def ss_inference_eval(model, img, labels, stride_size, crop_size, num_classes, ignore_index=255, palette=None,
+                      window_batch: int = 64, label_dtype=torch.int32):
+    """val.py:145-161 / predict.py:162-174 in one pass for same-size sliding-window inference: the predictions of
+    ``ss_inference(model, img, ori_shape=<image sizes>, is_slide=True, ...)`` plus, per image, the areas
+    ``metrics.calculate_area(pred[i], label[i], num_classes, ignore_index)`` (int64 [n_img, 3, nc]: intersect, pred, label)
+    and, with ``palette`` (uint8 [nc, 3]), predict.py's colour image — all produced by the fused upsample + stitch +
+    argmax kernel.  ``labels``: list of [1, H, W] / [H, W] integer tensors or None.
+    The model must expose ``forward_half_logits``; images must share one even size and num_classes <= 8, otherwise the
+    unfused calls (``ss_inference`` + ``calculate_area``) are the path to use (EmrtError says so)."""
+    imgs = img
+    img_hw = [(int(t.shape[-2]), int(t.shape[-1])) for t in imgs]
+    if not hasattr(model, "forward_half_logits"):
+        raise L.EmrtError("ss_inference_eval needs model.forward_half_logits (logits before UpHead's last x2 upsample)")
+    if len(set(img_hw)) != 1:
+        raise L.EmrtError("ss_inference_eval needs images of one size; use ss_inference + calculate_area")
+    H, W = img_hw[0]
+    plan, max_h, max_w = plan_windows(img_hw, crop_size, stride_size)
+    runs = _run_windows(model, imgs, plan, True, window_batch)
+    if len(runs) != 1:
+        raise L.EmrtError("ss_inference_eval needs one window size; use ss_inference + calculate_area")
+    (wh, ww), (half, idx, ys, xs) = next(iter(runs.items()))
+    gt = None if labels is None else torch.stack([l.reshape(H, W) for l in labels], 0)
+    pred, areas, color = ops.stitch_argmax_eval(half, idx, ys, xs, len(imgs), H, W, gt=gt, ignore_index=ignore_index,
+                                                palette=palette, label_dtype=label_dtype)
+    return [pred[i:i + 1] for i in range(len(imgs))], areas, color

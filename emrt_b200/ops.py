@@ -352,6 +352,33 @@ def stitch_argmax_fused(half_logits, win_img, win_y0, win_x0, n_img, H, W, label
     return labels, logits
 
 
+def stitch_argmax_eval(half_logits, win_img, win_y0, win_x0, n_img, H, W, gt=None, ignore_index=255, palette=None,
+                       label_dtype=torch.int32, labels=None):
+    """stitch_argmax_fused with the evaluation fused behind the argmax.
+    gt: ground-truth labels [n_img, (1,) H, W] (any integer dtype; stored as int32 / uint8) -> areas int64 [n_img, 3, nc]
+    (metrics.calculate_area per image); palette: uint8 [nc, 3] -> colour image uint8 [n_img, H, W, 3] (predict.py:171-174).
+    Returns (labels, areas | None, color | None)."""
+    n_win, nc, hh, hw = half_logits.shape
+    dev = half_logits.device
+    if labels is None:
+        labels = torch.empty((n_img, 1, H, W), dtype=label_dtype, device=dev)
+    areas = color = None
+    if gt is not None:
+        gt = gt.reshape(n_img, H, W)
+        if gt.dtype not in (torch.int32, torch.uint8):
+            gt = gt.to(torch.int32)
+        gt = gt.contiguous()
+        areas = torch.zeros((n_img, 3, nc), dtype=torch.int64, device=dev)
+    if palette is not None:
+        palette = palette.to(device=dev, dtype=torch.uint8).reshape(nc, 3).contiguous()
+        color = torch.empty((n_img, H, W, 3), dtype=torch.uint8, device=dev)
+    L.check(L.load().emrt_stitch_argmax_eval(_ptr(half_logits), _dt(half_logits), _ptr(labels), _dt(labels), n_win, n_img, nc,
+                                             2 * hh, 2 * hw, H, W, _ptr(win_img), _ptr(win_y0), _ptr(win_x0), _ptr(gt),
+                                             _dt(gt) if gt is not None else 0, int(ignore_index), _ptr(areas), _ptr(palette),
+                                             _ptr(color), _stream()))
+    return labels, areas, color
+
+
 def calculate_area(pred, label, num_classes, ignore_index=255):
     """-> int64 [3, num_classes] = (intersect, pred, label) areas (src/utils/metrics.py:20-69)."""
     pred = pred.reshape(-1).to(torch.int32).contiguous()

@@ -245,6 +245,18 @@ int emrt_stitch_argmax_fused(const void* half_logits, int in_dtype, void* labels
                              const int32_t* win_img, const int32_t* win_y0, const int32_t* win_x0,
                              void* stream);
 
+/* The same kernel with the evaluation fused behind the argmax:
+ *   gt [n_img, H, W] (gt_dtype I32|U8) + areas I64 [n_img, 3, nc] (zeroed by the caller; accumulated):
+ *     metrics.calculate_area (src/utils/metrics.py:20-69) per image — rows intersect / pred / label, pixels whose
+ *     ground truth equals ignore_index are dropped from all three;
+ *   palette U8 [nc, 3] + color U8 [n_img, H, W, 3]: predict.py:171-174's colour image (color = palette[class]).
+ * Either pair may be NULL (not both).  Needs even H, W and nc <= 8 (EMRT_ERR_UNSUPPORTED otherwise: run
+ * emrt_stitch_argmax_fused + emrt_calculate_area instead).                                                      */
+int emrt_stitch_argmax_eval(const void* half_logits, int in_dtype, void* labels, int label_dtype, int n_win, int n_img,
+                            int nc, int hc, int wc, int H, int W, const int32_t* win_img, const int32_t* win_y0,
+                            const int32_t* win_x0, const void* gt, int gt_dtype, int ignore_index, long long* areas,
+                            const uint8_t* palette, uint8_t* color, void* stream);
+
 /* ---- a8: metrics.calculate_area (src/utils/metrics.py:20-69) --------------------------------------------
  * pred I32 [n], label I32 [n]; areas I64 [3*nc] = {intersect[nc], pred[nc], label[nc]} MUST be zeroed.     */
 int emrt_calculate_area(const int32_t* pred, const int32_t* label, int64_t n, int nc, int ignore_index,

@@ -157,3 +157,36 @@ def test_quad_stitch_kernel_equals_pixel_kernel_any_window_parity(cuda_dev, dtyp
         cnt[i, :, y:y + hc, x:x + wc] += 1
     assert (cnt > 0).all()
     assert torch.allclose(log_q.cpu(), canvas / cnt, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype,gt_dtype", [(torch.float32, torch.int64), (torch.bfloat16, torch.uint8)])
+def test_fused_eval_areas_and_palette_match_unfused(cuda_dev, dtype, gt_dtype):
+    """argmax -> per-image calculate_area histogram (ignore-index contract) and palette image inside
+    the stitch kernel == ss_inference followed by calculate_area (oracle) and a palette lookup, bit for bit."""
+    rng = np.random.Generator(np.random.PCG64(31))
+    nc, H, W, crop, stride = 7, 200, 264, 64, 40          # W not a multiple of the 32-pixel CTA tile
+    wmat = O.rng_normal(rng, (nc, 3), 0.8)
+    imgs = [torch.from_numpy(O.rng_normal(rng, (3, H, W))).to(cuda_dev) for _ in range(3)]
+    gts = []
+    for _ in imgs:
+        g = rng.integers(0, nc, size=(1, H, W))
+        g[rng.uniform(size=g.shape) < 0.05] = 255
+        gts.append(torch.from_numpy(g).to(gt_dtype).to(cuda_dev))
+    palette = torch.from_numpy(rng.integers(0, 256, size=(nc, 3)).astype(np.uint8))
+    model = HalfModel(wmat, cuda_dev, dtype)
+    preds, areas, color = emrt_b200.ss_inference_eval(model, imgs, gts, (stride, stride), (crop, crop), nc, palette=palette)
+    want = emrt_b200.ss_inference(model, imgs, [(H, W)] * 3, True, None, (stride, stride), (crop, crop), nc)
+    assert areas.shape == (3, 3, nc) and areas.dtype == torch.int64 and color.shape == (3, H, W, 3)
+    for i in range(3):
+        assert torch.equal(preds[i], want[i])
+        ia, pa, la = O.calculate_area(want[i].cpu(), gts[i].cpu().long().reshape(1, 1, H, W), nc)
+        got = areas[i].cpu().numpy()
+        assert np.array_equal(got[0], np.asarray(ia, dtype=np.int64).reshape(-1))
+        assert np.array_equal(got[1], np.asarray(pa, dtype=np.int64).reshape(-1))
+        assert np.array_equal(got[2], np.asarray(la, dtype=np.int64).reshape(-1))
+        assert torch.equal(color[i].cpu(), palette[want[i].cpu().reshape(H, W).long()])
+    # areas only / palette only
+    _, a2, c2 = emrt_b200.ss_inference_eval(model, imgs, gts, (stride, stride), (crop, crop), nc)
+    assert c2 is None and torch.equal(a2, areas)
+    _, a3, c3 = emrt_b200.ss_inference_eval(model, imgs, None, (stride, stride), (crop, crop), nc, palette=palette)
+    assert a3 is None and torch.equal(c3, color)
