@@ -1,10 +1,13 @@
 """PaddlePaddle binding of libemrt_b200.so — the shim a maintainer adds to peach-xiao/EMRT.
 
-NOT EXECUTABLE IN THIS IMAGE: PaddlePaddle cannot be installed here (no wheel for Python 3.12, no network), so this
-file is written against the Paddle >= 2.5 API (``Tensor.data_ptr()``, ``paddle.device.cuda.current_stream()``,
-``paddle.autograd.PyLayer``) and is exercised only by an import-guard test.  It is deliberately thin: every
-function forwards Paddle tensors' device pointers to the same C entry points (include/emrt_b200.h) that the torch
-adapter in ``emrt_b200/ops.py`` drives and that the GPU parity tests cover; no arithmetic happens in Python.
+PaddlePaddle itself cannot be installed in this image (no wheel for Python 3.12, no network), so this file is
+written against the Paddle >= 2.5 API (``Tensor.data_ptr()``, ``paddle.device.cuda.current_stream()``,
+``paddle.autograd.PyLayer``) and is EXECUTED on a B200 on a torch-backed stand-in for that API
+(oracle/paddle_on_torch.py; tests/test_gpu_paddle_binding.py): every ctypes call below reaches the real kernels and
+is checked against vectors generated from the reference's own code — forward (fp32 and fused bf16), gradients,
+sliding-window inference and ``patch_reference()``.  What remains unverified is Paddle's own allocator / stream
+plumbing.  It is deliberately thin: every function forwards Paddle tensors' device pointers to the same C entry
+points (include/emrt_b200.h) that the torch adapter in ``emrt_b200/ops.py`` drives; no arithmetic happens in Python.
 
 Mirrors, with the reference's names / signatures / state-dict keys:
   MSDeformableAttention            src/models/EMRT_utils/transformer_encoder_decoder.py:21-107

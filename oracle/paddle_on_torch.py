@@ -34,6 +34,30 @@ import torch
 import torch.nn.functional as TF
 
 _T = torch.Tensor
+_DEVICE = [torch.device("cpu")]          # paddle.set_device("gpu") moves creation ops (and new parameters) to cuda:0
+
+
+def set_device(name):
+    name = str(name)
+    _DEVICE[0] = torch.device("cuda", int(name.split(":")[1]) if ":" in name else 0) if name.startswith("gpu") \
+        else torch.device("cpu")
+    return _DEVICE[0]
+
+
+def get_device():
+    d = _DEVICE[0]
+    return "cpu" if d.type == "cpu" else f"gpu:{d.index or 0}"
+
+
+class _Place:
+    def __init__(self, dev):
+        self._dev = dev
+
+    def is_gpu_place(self):
+        return self._dev.type == "cuda"
+
+    def is_cpu_place(self):
+        return self._dev.type == "cpu"
 
 _DTYPES = {
     "float32": torch.float32, "float64": torch.float64, "float16": torch.float16, "bfloat16": torch.bfloat16,
@@ -72,6 +96,18 @@ class Tensor(torch.Tensor):
     @property
     def shape(self):  # paddle: python list
         return list(_T.size(self))
+
+    @property
+    def place(self):
+        return _Place(_T.device.__get__(self))
+
+    @property
+    def stop_gradient(self):
+        return not _T.requires_grad.__get__(self)
+
+    @stop_gradient.setter
+    def stop_gradient(self, v):
+        _T.requires_grad_(self, not v)
 
     def numpy(self):
         a = _raw(self).detach().cpu().numpy()
@@ -189,7 +225,7 @@ def to_tensor(data, dtype=None, place=None, stop_gradient=True):
         t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(_dt(dtype))
-    return _wrap(t)
+    return _wrap(t.to(_DEVICE[0]))
 
 
 def _shape_arg(shape):
@@ -201,11 +237,23 @@ def _fdt(dtype):
 
 
 def zeros(shape, dtype=None):
-    return _wrap(torch.zeros(_shape_arg(shape), dtype=_fdt(dtype)))
+    return _wrap(torch.zeros(_shape_arg(shape), dtype=_fdt(dtype), device=_DEVICE[0]))
 
 
 def ones(shape, dtype=None):
-    return _wrap(torch.ones(_shape_arg(shape), dtype=_fdt(dtype)))
+    return _wrap(torch.ones(_shape_arg(shape), dtype=_fdt(dtype), device=_DEVICE[0]))
+
+
+def empty(shape, dtype=None):
+    return _wrap(torch.empty(_shape_arg(shape), dtype=_fdt(dtype), device=_DEVICE[0]))
+
+
+def zeros_like(x, dtype=None):
+    return _wrap(torch.zeros_like(_raw(x), dtype=_dt(dtype)))
+
+
+def is_grad_enabled():
+    return torch.is_grad_enabled()
 
 
 def full_like(x, fill_value, dtype=None):
@@ -216,11 +264,12 @@ def arange(start=0, end=None, step=1, dtype=None):
     if end is None:
         start, end = 0, start
     all_int = all(isinstance(v, (int, np.integer)) for v in (start, end, step))
-    return _wrap(torch.arange(start, end, step, dtype=_dt(dtype) if dtype is not None else (torch.int64 if all_int else torch.float32)))
+    return _wrap(torch.arange(start, end, step, device=_DEVICE[0],
+                              dtype=_dt(dtype) if dtype is not None else (torch.int64 if all_int else torch.float32)))
 
 
 def linspace(start, stop, num, dtype=None):
-    return _wrap(torch.linspace(float(start), float(stop), int(num), dtype=_fdt(dtype)))
+    return _wrap(torch.linspace(float(start), float(stop), int(num), dtype=_fdt(dtype), device=_DEVICE[0]))
 
 
 def meshgrid(*args):
@@ -277,15 +326,15 @@ def log(x):
 
 
 def uniform(shape, dtype=None, min=-1.0, max=1.0, seed=0):
-    return _wrap(torch.empty(_shape_arg(shape), dtype=_fdt(dtype)).uniform_(min, max))
+    return _wrap(torch.empty(_shape_arg(shape), dtype=_fdt(dtype), device=_DEVICE[0]).uniform_(min, max))
 
 
 def normal(mean=0.0, std=1.0, shape=None):
-    return _wrap(torch.empty(_shape_arg(shape), dtype=torch.float32).normal_(mean, std))
+    return _wrap(torch.empty(_shape_arg(shape), dtype=torch.float32, device=_DEVICE[0]).normal_(mean, std))
 
 
 def rand(shape, dtype=None):
-    return _wrap(torch.rand(_shape_arg(shape), dtype=_fdt(dtype)))
+    return _wrap(torch.rand(_shape_arg(shape), dtype=_fdt(dtype), device=_DEVICE[0]))
 
 
 class ParamAttr:
@@ -295,13 +344,13 @@ class ParamAttr:
 
 
 def _param(shape, fill=None):
-    t = torch.empty(list(shape), dtype=torch.float32)
+    t = torch.empty(list(shape), dtype=torch.float32, device=_DEVICE[0])
     if fill is None:
         bound = math.sqrt(6.0 / max(1, (shape[0] + shape[-1]))) if len(shape) >= 2 else 0.0
         t.uniform_(-bound, bound) if bound else t.zero_()
     else:
         t.fill_(fill)
-    return torch.nn.Parameter(t.as_subclass(Tensor), requires_grad=False)
+    return torch.nn.Parameter(t.as_subclass(Tensor), requires_grad=True)      # paddle: stop_gradient=False
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -385,8 +434,8 @@ class BatchNorm2D(Layer):
         super().__init__()
         self.epsilon = epsilon
         self.weight, self.bias = _param([num_features], 1.0), _param([num_features], 0.0)
-        self.register_buffer("_mean", torch.zeros(num_features))
-        self.register_buffer("_variance", torch.ones(num_features))
+        self.register_buffer("_mean", torch.zeros(num_features, device=_DEVICE[0]))
+        self.register_buffer("_variance", torch.ones(num_features, device=_DEVICE[0]))
 
     def forward(self, x):
         assert not self.training, "the shim runs BatchNorm in eval mode only"
@@ -552,6 +601,38 @@ class _NoGrad:
         return torch.no_grad()(fn)
 
 
+class PyLayer:
+    """paddle.autograd.PyLayer on torch.autograd.Function: ``forward(ctx, *args)`` / ``backward(ctx, *grads)`` static
+    methods, ``ctx.save_for_backward`` / ``ctx.saved_tensor()``; backward returns one gradient per TENSOR input."""
+
+    @classmethod
+    def apply(cls, *args):
+        is_t = [isinstance(a, torch.Tensor) for a in args]
+
+        class _Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, *a):
+                ctx.saved_tensor = lambda: tuple(_wrap(t) for t in ctx.saved_tensors)
+                out = cls.forward(ctx, *[_wrap(x) for x in a])
+                return tuple(_raw(o) for o in out) if isinstance(out, (tuple, list)) else _raw(out)
+
+            @staticmethod
+            def backward(ctx, *grads):
+                res = cls.backward(ctx, *[_wrap(g) for g in grads])
+                res = list(res) if isinstance(res, (tuple, list)) else [res]
+                assert len(res) == len([t for t in is_t if t]), "PyLayer.backward must return one gradient per tensor input"
+                it = iter(res)
+                return tuple((_raw(next(it)) if t else None) for t in is_t)
+
+        return _wrap(_Fn.apply(*[_raw(a) for a in args]))
+
+
+class _CudaStream:
+    @property
+    def cuda_stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+
 class _Init:
     def __init__(self, *a, **kw):
         pass
@@ -559,11 +640,23 @@ class _Init:
 
 def install():
     """Registers the shim as ``paddle`` (and sub-modules) in sys.modules.  Refuses to shadow a real PaddlePaddle."""
-    if "paddle" in sys.modules and not getattr(sys.modules["paddle"], "__emrt_shim__", False):
+    if "paddle" in sys.modules:
+        if getattr(sys.modules["paddle"], "__emrt_shim__", False):
+            return sys.modules["paddle"]
         raise RuntimeError("a real `paddle` is already imported; use it instead of the shim")
     me = sys.modules[__name__]
     paddle = types.ModuleType("paddle")
     paddle.__emrt_shim__ = True
+    for name in ("set_device", "get_device", "empty", "zeros_like", "is_grad_enabled"):
+        setattr(paddle, name, getattr(me, name))
+    autograd = types.ModuleType("paddle.autograd")
+    autograd.PyLayer = PyLayer
+    device = types.ModuleType("paddle.device")
+    device_cuda = types.ModuleType("paddle.device.cuda")
+    device_cuda.current_stream = lambda *a: _CudaStream()
+    device.cuda, device.set_device, device.get_device = device_cuda, set_device, get_device
+    paddle.autograd, paddle.device = autograd, device
+    sys.modules.update({"paddle.autograd": autograd, "paddle.device": device, "paddle.device.cuda": device_cuda})
     for name in ("Tensor", "to_tensor", "zeros", "ones", "full_like", "arange", "linspace", "meshgrid", "stack",
                  "concat", "split", "reshape", "transpose", "squeeze", "sum", "matmul", "argmax", "log", "uniform",
                  "normal", "rand", "ParamAttr"):
