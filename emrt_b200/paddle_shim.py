@@ -301,7 +301,73 @@ def ss_inference(model, img, ori_shape, is_slide, base_size, stride_size, crop_s
     return preds
 
 
-def patch_reference():
+# ---- whole EncoderDecoder ------------------------------------------------------------------
+def _to_torch(t):
+    """Zero-copy view of a Paddle GPU tensor as a torch tensor (DLPack): torch is the device-memory container of the
+    adapter in emrt_b200/ (encoder.py, decoder.py), which holds the launch sequence of the encoder / decoder layers."""
+    from torch.utils import dlpack as tdl
+    return tdl.from_dlpack(paddle.utils.dlpack.to_dlpack(t))
+
+
+def _from_torch(t):
+    from torch.utils import dlpack as tdl
+    return paddle.utils.dlpack.from_dlpack(tdl.to_dlpack(t))
+
+
+def make_fast_encoder_decoder(ref_cls):
+    """-> subclass of the reference's own ``EncoderDecoder`` (transformer_encoder_decoder.py:337-473): parameters, state-dict
+    keys, initialisation and the training forward are INHERITED from the reference class; in eval mode under
+    ``paddle.no_grad()`` (val.py / predict.py) ``forward(src_feats, src_psp)`` runs the native path — input_proj, the four
+    encoder layers, the two decoder layers — through ``emrt_b200.EncoderDecoder``, whose parameters alias this layer's
+    Paddle parameters (DLPack, no copies; bf16 operand packs are rebuilt when a parameter's version changes)."""
+
+    class EncoderDecoder(ref_cls):
+        _emrt_native = None
+
+        def _native_module(self):
+            import torch
+            import emrt_b200
+            params = dict(self.named_parameters())
+            ver = tuple((k, int(getattr(p, "inplace_version", 0))) for k, p in params.items())
+            if self._emrt_native is not None and self._emrt_native[0] == ver:
+                return self._emrt_native[1]
+            C_ = params["level_embed.weight"].shape[1]
+            nL = params["level_embed.weight"].shape[0]
+            num_enc = 1 + max(int(k.split(".")[2]) for k in params if k.startswith("encoder.layers."))
+            num_dec = 1 + max(int(k.split(".")[2]) for k in params if k.startswith("decoder.layers."))
+            heads = int(self.nhead)
+            pts_e = params["encoder.layers.0.self_attn.attention_weights.weight"].shape[1] // (heads * nL)
+            pts_d = params["decoder.layers.0.cross_attn.attention_weights.weight"].shape[1] // (heads * nL)
+            chans = [params[f"input_proj.{l}.0.weight"].shape[1] for l in range(nL)]
+            m = emrt_b200.EncoderDecoder(num_queries=params["query_pos_embed.weight"].shape[0],
+                                         backbone_num_channels=chans, num_feature_levels=nL, num_encoder_points=pts_e,
+                                         num_decoder_points=pts_d, hidden_dim=C_, nhead=heads, num_encoder_layers=num_enc,
+                                         num_decoder_layers=num_dec,
+                                         dim_feedforward=params["encoder.layers.0.linear1.weight"].shape[1])
+            own = dict(m.named_parameters())
+            if set(own) != set(params):
+                raise L.EmrtError("state-dict keys of the reference EncoderDecoder and of emrt_b200.EncoderDecoder differ: "
+                                  + str(sorted(set(own) ^ set(params))[:6]))
+            with torch.no_grad():
+                for k, p in params.items():
+                    own[k].data = _to_torch(p).reshape(own[k].shape)      # alias, not a copy
+            m.requires_grad_(False)
+            self._emrt_native = (ver, m)
+            return m
+
+        def forward(self, src_feats, src_psp, src_mask=None):
+            if self.training or src_mask is not None or paddle.is_grad_enabled():
+                return super().forward(src_feats, src_psp, src_mask)
+            m = self._native_module()
+            hs, memory = m([_to_torch(f) for f in src_feats], _to_torch(src_psp))
+            return _from_torch(hs), _from_torch(memory)
+
+    EncoderDecoder.__name__ = ref_cls.__name__
+    EncoderDecoder.__qualname__ = ref_cls.__qualname__
+    return EncoderDecoder
+
+
+def patch_reference(encoder_decoder=True):
     """Install the drop-ins into the reference's modules (run from the reference's semantic_segmentation/ directory)."""
     import src.api.infer as infer
     import src.models.EMRT_utils.transformer_encoder_decoder as ted
@@ -313,9 +379,17 @@ def patch_reference():
         mods.append(ted_cswin)
     except ImportError:
         pass
+    import sys
     for mod in mods:
         mod.MSDeformableAttention = MSDeformableAttention
         mod.deformable_attention_core_func = deformable_attention_core_func
+        ref_cls = getattr(mod, "EncoderDecoder", None)
+        if encoder_decoder and ref_cls is not None and not hasattr(ref_cls, "_emrt_native"):
+            fast = make_fast_encoder_decoder(ref_cls)
+            # the model files bind the class by name at import (paddle_EMRT.py:9): rebind it wherever it already went
+            for other in list(sys.modules.values()):
+                if other is not None and getattr(other, "EncoderDecoder", None) is ref_cls:
+                    other.EncoderDecoder = fast
     U.deformable_attention_core_func = deformable_attention_core_func
     infer._emrt_original_ss_inference = infer.ss_inference
     infer.slide_inference = slide_inference

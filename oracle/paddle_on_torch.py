@@ -32,6 +32,7 @@ from typing import Sequence
 import numpy as np
 import torch
 import torch.nn.functional as TF
+import torch.utils.dlpack
 
 _T = torch.Tensor
 _DEVICE = [torch.device("cpu")]          # paddle.set_device("gpu") moves creation ops (and new parameters) to cuda:0
@@ -655,6 +656,13 @@ def install():
     device_cuda = types.ModuleType("paddle.device.cuda")
     device_cuda.current_stream = lambda *a: _CudaStream()
     device.cuda, device.set_device, device.get_device = device_cuda, set_device, get_device
+    utils = types.ModuleType("paddle.utils")
+    dl = types.ModuleType("paddle.utils.dlpack")
+    dl.to_dlpack = lambda t: torch.utils.dlpack.to_dlpack(_raw(t).detach())
+    dl.from_dlpack = lambda cap: _wrap(torch.utils.dlpack.from_dlpack(cap))
+    utils.dlpack = dl
+    paddle.utils = utils
+    sys.modules.update({"paddle.utils": utils, "paddle.utils.dlpack": dl})
     paddle.autograd, paddle.device = autograd, device
     sys.modules.update({"paddle.autograd": autograd, "paddle.device": device, "paddle.device.cuda": device_cuda})
     for name in ("Tensor", "to_tensor", "zeros", "ones", "full_like", "arange", "linspace", "meshgrid", "stack",

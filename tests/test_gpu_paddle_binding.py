@@ -183,3 +183,56 @@ def test_binding_patch_reference_installs_the_drop_ins(binding):
                 sys.modules.pop(n, None)
             else:
                 sys.modules[n] = m
+
+
+def _fake_reference_encoder_decoder(P, params):
+    """A Layer with exactly the reference EncoderDecoder's parameter tree (the reference class itself is not on the GPU
+    box; tests/test_reference_pin.py::test_fast_encoder_decoder_subclasses_the_reference_class covers the real one on CPU).
+    Its own forward raises: the test proves the native path ran."""
+
+    class FakeRef(P.Layer):
+        def __init__(self):
+            super().__init__()
+            self.nhead = 8
+            for key, value in params.items():
+                node = self
+                *path, leaf = key.split(".")
+                for part in path:
+                    if part not in node._modules:
+                        node.add_module(part, P.Layer())
+                    node = node._modules[part]
+                t = torch.as_tensor(np.asarray(value)).cuda().as_subclass(P.Tensor)
+                node.register_parameter(leaf, torch.nn.Parameter(t, requires_grad=True))
+
+        def forward(self, src_feats, src_psp, src_mask=None):
+            raise AssertionError("the reference forward must not run in eval mode under no_grad")
+
+    return FakeRef
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_binding_fast_encoder_decoder_native_path(binding, dtype):
+    PS, paddle = binding
+    from oracle import paddle_on_torch as P
+    g = load("ref_encdec_full")
+    ne, nd = int(g["num_enc"]), int(g["num_dec"])
+    c = G.encdec_inputs(int(g["tile"]), int(g["B"]), int(g["seed"]), ne, nd)
+    Fast = PS.make_fast_encoder_decoder(_fake_reference_encoder_decoder(P, c["params"]))
+    m = Fast()
+    assert sorted(k for k, _ in m.named_parameters()) == list(g["keys"])
+    m.eval()
+    T = paddle.to_tensor
+    with paddle.no_grad():
+        hs, mem = m([T(f).astype(dtype) for f in c["feats"]], T(c["psp"]).astype(dtype))
+    assert hs.shape == list(g["hs"].shape) and mem.shape == list(g["memory"].shape)
+    tol = 5e-4 if dtype == "float32" else None
+    if tol:
+        assert rel_err(mem, g["memory"]) < tol and rel_err(hs, g["hs"]) < tol
+    else:
+        assert l2_err(mem.astype("float32"), g["memory"]) < 2e-2 and l2_err(hs.astype("float32"), g["hs"]) < 2e-2
+    # parameters are aliased, not copied: an in-place update of a Paddle parameter reaches the native module
+    native = m._native_module()
+    key = "decoder.layers.0.norm3.bias"
+    before = dict(native.named_parameters())[key].detach().clone()
+    dict(m.named_parameters())[key].as_subclass(torch.Tensor).data.add_(1.0)
+    assert torch.equal(dict(native.named_parameters())[key].detach(), before + 1.0)

@@ -162,3 +162,25 @@ def test_live_reference_slide_inference_potsdam_window_plan():
         assert float(torch.as_tensor(out[0]).min()) == 1.0 == float(torch.as_tensor(out[0]).max())
         assert len(O.window_origins(size, 512, 384)) == n
         assert [o // 8 for o in O.window_origins(size, 512, 384)] == O.window_origins(size // 8, 64, 48)
+
+
+@live
+def test_fast_encoder_decoder_subclasses_the_reference_class():
+    """emrt_b200/paddle_shim.py::make_fast_encoder_decoder on the REAL reference class: same parameter tree and keys,
+    and outside eval + no_grad the reference's own forward runs (bit-equal to the committed vector)."""
+    ref = R.load()
+    import paddle
+    import emrt_b200.paddle_shim as PS
+    g = load("ref_encdec_small")
+    ne, nd = int(g["num_enc"]), int(g["num_dec"])
+    c = G.encdec_inputs(int(g["tile"]), int(g["B"]), int(g["seed"]), ne, nd)
+    Fast = PS.make_fast_encoder_decoder(ref.ted.EncoderDecoder)
+    assert issubclass(Fast, ref.ted.EncoderDecoder) and Fast.__name__ == "EncoderDecoder"
+    m = Fast(hidden_dim=256, dim_feedforward=1024, backbone_num_channels=[512, 1024, 2048], dropout=0.1, activation="relu",
+             num_feature_levels=3, nhead=8, num_encoder_layers=ne, num_decoder_layers=nd, num_encoder_points=6,
+             num_decoder_points=6, nclass=6)
+    assert sorted(m.state_dict().keys()) == list(g["keys"])
+    R.load_params(m, c["params"])            # -> eval mode; gradients enabled here, so the reference path runs
+    hs, mem = m([paddle.to_tensor(f) for f in c["feats"]], paddle.to_tensor(c["psp"]))
+    close(torch.as_tensor(mem).detach(), g["memory"], 1e-7)
+    close(torch.as_tensor(hs).detach(), g["hs"], 1e-7)
