@@ -430,7 +430,32 @@ def run_ours(args):
     e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
 
     # ---- roofline of the dominant kernel (the encoder gather) --------------------------------------------
-    enc = [(dims, ev[0].elapsed_time(ev[1])) for (name, dims, ev) in events if dims[1] == Lv]
+    enc = [(dims, ev[0].elapsed_time(ev[1])) for (name, dims, ev) in events if name == "msda_gather_fwd" and dims[1] == Lv]
+    # the dense contractions of the step against both of their bounds (north_star: tensor-pipe fraction of the projections)
+    peaks_d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = float(peaks_d.get("bf16_tflops_sustained", 1407.0))      # kernels timed inside a long step: sustained figure
+    tf_burst = float(peaks_d.get("bf16_tflops", 1681.0))
+    dense = {}
+    for (name, dims, ev) in events:
+        if name == "linear" and dims[0] == B * Lv:
+            rows_, K_, N_, sx, sy = dims
+            key = f"linear rows={rows_} K={K_} N={N_}"
+            flops, byts = 2.0 * rows_ * K_ * N_, rows_ * (K_ * sx + N_ * sy) + K_ * N_ * sx
+        elif name == "conv3x3" and dims[0] == B * Lv:
+            rows_, C_, sx = dims
+            key = f"conv3x3 rows={rows_} C={C_}"
+            flops, byts = 2.0 * rows_ * 9 * C_ * C_, 2.0 * rows_ * C_ * sx + 3 * 9 * C_ * C_ * sx
+        else:
+            continue
+        d = dense.setdefault(key, {"ms": 0.0, "n": 0, "flops": flops, "bytes": byts})
+        d["ms"] += ev[0].elapsed_time(ev[1]); d["n"] += 1
+    dense_rows = []
+    for key, d in dense.items():
+        t = d["ms"] / d["n"] * 1e-3
+        dense_rows.append({"kernel": key, "launches_timed": d["n"], "avg_launch_ms": t * 1e3,
+                           "tflops": d["flops"] / t / 1e12, "frac_of_bf16_peak": d["flops"] / t / 1e12 / tf_peak,
+                           "frac_of_bf16_burst_peak": d["flops"] / t / 1e12 / tf_burst,
+                           "gbs": d["bytes"] / t / 1e9, "frac_of_hbm_peak": d["bytes"] / t / 1e9 / peaks()[0]})
     hbm_peak, peak_src = peaks()
     roof = None
     if enc:
@@ -462,6 +487,10 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
+        "dense_kernels": {"peak_tflops": tf_peak, "burst_peak_tflops": tf_burst,
+                          "peak_source": "MEASURED_PEAKS.json: bf16_tflops_sustained (cuBLAS back to back for 4 s — the figure for kernels "
+                                         "timed inside a long step; a tile kernel can exceed it) and bf16_tflops (burst)",
+                          "rows": dense_rows},
     }
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1

@@ -16,13 +16,15 @@ namespace emrt {
 // erff's two divergent branches; the negative side is evaluated as erfc directly, so there is no 1 - erf cancellation.
 __device__ __forceinline__ float gelu_erf(float h) {
   const float z = fabsf(h) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));        // 1 ulp: far below 1.5e-7
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (z * -1.4426950408889634f)));   // exp(-z^2)
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
   p = fmaf(t, p, 0.254829592f);
-  const float half_erfc = 0.5f * p * t * __expf(-z * z);      // erfc(z) / 2
-  return h * (h >= 0.f ? 1.f - half_erfc : half_erfc);
+  const float hh = h * (0.5f * p * t * e);                    // h * erfc(z) / 2
+  return h >= 0.f ? h - hh : hh;
 }
 
 // ---- LayerNorm(x + residual) (+ post_add): one warp per row, 16-byte vectors, N <= 1024, N % (32 * VEC) == 0 ----------
@@ -54,6 +56,7 @@ residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residua
   if (row0 >= rows) return;
   float v[RPW][PER][VEC];
   float s[RPW], ss[RPW];
+  const float inv_n = 1.f / (float)N;
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
     const int64_t row = row0 + r < rows ? row0 + r : rows - 1;
@@ -87,7 +90,7 @@ residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residua
     for (int r = 0; r < RPW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
-    s[r] /= (float)N;       // mean
+    s[r] *= inv_n;          // mean
     ss[r] = 0.f;
 #pragma unroll
     for (int i = 0; i < PER; ++i)
@@ -112,7 +115,7 @@ residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residua
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       if (row0 + r >= rows) continue;
-      const float rstd = rsqrtf(ss[r] / (float)N + eps);
+      const float rstd = rsqrtf(fmaf(ss[r], inv_n, eps));
       float o[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) o[k] = (v[r][i][k] - s[r]) * rstd * g[k] + bt[k];
@@ -124,7 +127,7 @@ residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residua
         int l = 0;
         while (l + 1 < gn.L && t >= gn.lv.start[l + 1]) ++l;
         const int cpg = N / gn.G;                                   // VEC <= cpg: the vector lies in one group
-        const float inv_cnt = 1.f / (float)(gn.lv.H[l] * gn.lv.W[l] * cpg);
+        const float inv_cnt = __frcp_rn((float)(gn.lv.H[l] * gn.lv.W[l] * cpg));
         const float2 st = __ldg(reinterpret_cast<const float2*>(gn.stats) + ((b * gn.L + l) * gn.G + c / cpg));
         const float mean = st.x * inv_cnt;
         const float grstd = rsqrtf(fmaxf(st.y * inv_cnt - mean * mean, 0.f) + gn.eps);

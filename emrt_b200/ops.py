@@ -19,6 +19,25 @@ _TD = {v: k for k, v in _DT.items()}
 kernel_events = None   # set to a list to collect (name, dims, (start, end)) CUDA-event pairs per launch
 
 
+class _Timed:
+    """CUDA events around one launch on the launching stream when bench.py has set ``kernel_events`` to a list."""
+
+    def __init__(self, name, dims):
+        self.name, self.dims, self.ev = name, dims, None
+
+    def __enter__(self):
+        if kernel_events is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            kernel_events.append((self.name, self.dims, self.ev))
+        return False
+
+
 def _dt(t: torch.Tensor) -> int:
     try:
         return _DT[t.dtype]
@@ -131,7 +150,8 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     a.qproj_group = int(qproj_group)
     a.impl = int(impl)
     a.hm_rows, a.hm_D = int(hm_rows), int(hm_D)
-    L.check(lib.emrt_linear_fwd(C.byref(a), _stream()))
+    with _Timed("linear", (rows, K, N, x.element_size(), out.element_size())):
+        L.check(lib.emrt_linear_fwd(C.byref(a), _stream()))
     return (out, out2) if (epilogue & L.EPI_MSDA_QPROJ) else out
 
 
@@ -230,8 +250,9 @@ def conv3x3_tokens(x, w_packed, shapes, impl=L.IMPL_AUTO, out=None):
     assert total == Lv
     if out is None:
         out = torch.empty_like(x)
-    L.check(L.load().emrt_conv3x3_tokens_fwd(_ptr(x), _ptr(w_packed), _ptr(out), B, Lv, C, len(shapes), hw, _dt(x),
-                                             _dt(w_packed), int(impl), _stream()))
+    with _Timed("conv3x3", (B * Lv, C, x.element_size())):
+        L.check(L.load().emrt_conv3x3_tokens_fwd(_ptr(x), _ptr(w_packed), _ptr(out), B, Lv, C, len(shapes), hw, _dt(x),
+                                                 _dt(w_packed), int(impl), _stream()))
     return out
 
 
