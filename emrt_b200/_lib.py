@@ -60,6 +60,7 @@ SIGNATURES = {
     "emrt_conv3x3_tokens_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I32P, _I, _I, _I, _P]),
     "emrt_groupnorm_gelu_residual": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_float, _I32P, _I, _P]),
     "emrt_groupnorm_stats": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I32P, _I, _P]),
+    "emrt_groupnorm_workspace_floats": (C.c_longlong, [_I, _I, _I]),
     "emrt_residual_layernorm_gn": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_float, C.c_float,
                                              _I32P, _I, _P]),
     "emrt_nchw_to_tokens": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),

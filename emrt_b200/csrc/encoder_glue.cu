@@ -204,13 +204,24 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ src, TD* __restric
 }
 
 // ---- GroupNorm statistics: sum / sum of squares per (batch, level, group) ----------------------------------------------
-// grid (B * L, splits); block 256 threads = (C / 8 groups-of-8-channels lanes) x pixel slots.  fp32 atomics into stats.
+// grid (B * L, GN_SPLITS); block 256 threads = (C / 8 groups-of-8-channels lanes) x pixel slots.  DETERMINISTIC: every
+// CTA writes its partial sums, the last CTA to finish a (batch, level) — found with a ticket counter — adds the GN_SPLITS
+// partials in split order, so the result does not depend on scheduling (no floating-point atomics; a run is bit-reproducible).
+// Workspace (floats): stats [B*L, G, 2] | partials [B*L, GN_SPLITS, G, 2] | tickets [B*L] (zeroed by the launcher).
+constexpr int GN_SPLITS = 16;
+
+inline int64_t gn_workspace_floats(int64_t BL, int G) { return 2 * BL * G * (1 + GN_SPLITS) + BL; }
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int Lv, int C, int L, int G,
+groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int Lv, int C, int L, int G,
                        const __grid_constant__ LevelTable lv) {
   const int bl = blockIdx.x, l = bl % L;
   const int64_t b = bl / L;
+  const int64_t BL = gridDim.x;
+  float* stats = ws;
+  float* partials = ws + 2 * BL * G;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + 2 * BL * G * (1 + GN_SPLITS));
   const int npix = lv.H[l] * lv.W[l];
   const int vec_per_pix = C / 8;                           // 16-byte vectors of 8 channels (bf16) or 2 x float4
   const int slots = 256 / vec_per_pix;                     // pixels handled concurrently by the CTA
@@ -230,17 +241,40 @@ groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int L
       }
     }
   }
-  // reduce over the CTA's pixel slots, then one atomic pair per 8-channel vector
+  // reduce over the CTA's pixel slots and over the vectors of one group, in a fixed order
   __shared__ float sh[256][2];
+  __shared__ bool last;
   sh[threadIdx.x][0] = s;
   sh[threadIdx.x][1] = ss;
   __syncthreads();
-  if (threadIdx.x < vec_per_pix) {
-    for (int k = 1; k < slots; ++k) { s += sh[k * vec_per_pix + threadIdx.x][0]; ss += sh[k * vec_per_pix + threadIdx.x][1]; }
-    // this vector's 8 channels lie in group (v * 8) / cpg (EMRT: cpg == 8, one group per vector)
-    const int g = (v * 8) / cpg;
-    atomicAdd(stats + ((b * L + l) * G + g) * 2, s);
-    atomicAdd(stats + ((b * L + l) * G + g) * 2 + 1, ss);
+  const int vpg = cpg >= 8 ? cpg / 8 : 1;                  // 8-channel vectors per group
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float gs = 0.f, gss = 0.f;
+    for (int k = 0; k < slots; ++k)
+      for (int j = 0; j < vpg; ++j) { gs += sh[k * vec_per_pix + g * vpg + j][0]; gss += sh[k * vec_per_pix + g * vpg + j][1]; }
+    float* dst = partials + (((int64_t)bl * GN_SPLITS + blockIdx.y) * G + g) * 2;
+    dst[0] = gs;
+    dst[1] = gss;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(tickets + bl, 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < G) {
+      const int g = threadIdx.x;
+      float gs = 0.f, gss = 0.f;
+      for (int k = 0; k < (int)gridDim.y; ++k) {
+        const float* src = partials + (((int64_t)bl * GN_SPLITS + k) * G + g) * 2;
+        gs += __ldcg(src);
+        gss += __ldcg(src + 1);
+      }
+      stats[((int64_t)bl * G + g) * 2] = gs;
+      stats[((int64_t)bl * G + g) * 2 + 1] = gss;
+    }
+    if (threadIdx.x == 0) tickets[bl] = 0u;                // ready for the next use of this workspace
   }
 }
 
@@ -389,6 +423,10 @@ static int check_gn_args(int B, int C, int groups) {
   return EMRT_OK;
 }
 
+extern "C" long long emrt_groupnorm_workspace_floats(int B, int L, int groups) {
+  return gn_workspace_floats((int64_t)B * L, groups);
+}
+
 extern "C" int emrt_groupnorm_stats(const void* x, float* stats, int B, int Lv, int C, int L, int groups,
                                     const int32_t* shapes_hw_host, int dtype, void* stream) {
   EMRT_REQUIRE(x && stats, "NULL pointer");
@@ -396,8 +434,9 @@ extern "C" int emrt_groupnorm_stats(const void* x, float* stats, int B, int Lv, 
   LevelTable lv;
   if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, Lv)) return e;
   cudaStream_t st = as_stream(stream);
-  EMRT_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * L * groups, st));
-  dim3 sgrid((unsigned)(B * L), 16);
+  EMRT_REQUIRE(groups <= 256, "at most 256 groups");
+  EMRT_CUDA_CHECK(cudaMemsetAsync(stats + 2 * (int64_t)B * L * groups * (1 + GN_SPLITS), 0, sizeof(float) * B * L, st));
+  dim3 sgrid((unsigned)(B * L), GN_SPLITS);
   if (dtype == EMRT_F32) groupnorm_stats_kernel<float><<<sgrid, 256, 0, st>>>((const float*)x, stats, Lv, C, L, groups, lv);
   else if (dtype == EMRT_BF16) groupnorm_stats_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>((const __nv_bfloat16*)x, stats, Lv, C, L, groups, lv);
   else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
@@ -495,8 +534,9 @@ extern "C" int emrt_groupnorm_gelu_residual(const void* conv, const void* x, con
   LevelTable lv;
   if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, Lv)) return e;
   cudaStream_t st = as_stream(stream);
-  EMRT_CUDA_CHECK(cudaMemsetAsync(stats_workspace, 0, sizeof(float) * 2 * B * L * groups, st));
-  dim3 sgrid((unsigned)(B * L), 16);
+  EMRT_REQUIRE(groups <= 256, "at most 256 groups");
+  EMRT_CUDA_CHECK(cudaMemsetAsync(stats_workspace + 2 * (int64_t)B * L * groups * (1 + GN_SPLITS), 0, sizeof(float) * B * L, st));
+  dim3 sgrid((unsigned)(B * L), GN_SPLITS);
   const int vec = dtype == EMRT_F32 ? 4 : 8;
   EMRT_REQUIRE((int64_t)Lv * (C / vec) < (1LL << 31) && B <= 65535, "image too large for the GroupNorm apply grid");
   dim3 agrid((unsigned)(((int64_t)Lv * (C / vec) + 255) / 256), (unsigned)B);
@@ -539,8 +579,9 @@ extern "C" int emrt_groupnorm_tokens(const void* x, const float* gamma, const fl
   const int32_t hw[2] = {P, 1};
   if (int e = fill_levels(lv, 1, hw, nullptr, P)) return e;
   cudaStream_t st = as_stream(stream);
-  EMRT_CUDA_CHECK(cudaMemsetAsync(stats_workspace, 0, sizeof(float) * 2 * B * groups, st));
-  dim3 sgrid((unsigned)B, 16);
+  EMRT_REQUIRE(groups <= 256, "at most 256 groups");
+  EMRT_CUDA_CHECK(cudaMemsetAsync(stats_workspace + 2 * (int64_t)B * groups * (1 + GN_SPLITS), 0, sizeof(float) * B, st));
+  dim3 sgrid((unsigned)B, GN_SPLITS);
   const int vec = dtype == EMRT_F32 ? 4 : 8;
   dim3 agrid((unsigned)(((int64_t)P * (C / vec) + 255) / 256), (unsigned)B);
   if (dtype == EMRT_F32) {

@@ -262,19 +262,20 @@ def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, o
     hw, _, _ = level_tables(shapes)
     if out is None:
         out = torch.empty_like(x)
-    ws = torch.empty((2 * B * len(shapes) * groups,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((int(L.load().emrt_groupnorm_workspace_floats(B, len(shapes), groups)),), dtype=torch.float32, device=x.device)
     L.check(L.load().emrt_groupnorm_gelu_residual(_ptr(conv), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(ws), B, Lv,
                                                   C, len(shapes), groups, float(eps), hw, _dt(x), _stream()))
     return out
 
 
 def groupnorm_stats(x, shapes, groups=32):
-    """(sum, sum of squares) per (batch, level, group) of x [B, Lv, C] -> f32 [B, L, groups, 2]."""
+    """(sum, sum of squares) per (batch, level, group) of x [B, Lv, C] -> the statistics workspace whose first
+    2 * B * L * groups floats are the sums [B, L, groups, 2] (deterministic fixed-order reduction)."""
     B, Lv, C = x.shape
     hw, _, _ = level_tables(shapes)
-    st = torch.empty((B, len(shapes), groups, 2), dtype=torch.float32, device=x.device)
+    st = torch.empty((int(L.load().emrt_groupnorm_workspace_floats(B, len(shapes), groups)),), dtype=torch.float32, device=x.device)
     L.check(L.load().emrt_groupnorm_stats(_ptr(x), _ptr(st), B, Lv, C, len(shapes), groups, hw, _dt(x), _stream()))
-    return st
+    return st       # the sums [B, L, groups, 2] are its first 2 * B * L * groups floats
 
 
 def residual_layernorm_gn(x, residual, ln_gamma, ln_beta, conv, skip, gn_stats, gn_gamma, gn_beta, shapes, groups=32,
@@ -304,7 +305,7 @@ def groupnorm_tokens_into(x, gamma, beta, out, token_offset, groups=32, eps=1e-5
     """GroupNorm of one level's tokens x [B, P, C] written into out[:, token_offset:token_offset+P, :] (out [B, Lv, C])."""
     B, P, C_ = x.shape
     assert out.is_contiguous() and out.shape[0] == B and out.shape[2] == C_ and out.dtype == x.dtype
-    ws = torch.empty((2 * B * groups,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((int(L.load().emrt_groupnorm_workspace_floats(B, 1, groups)),), dtype=torch.float32, device=x.device)
     dst = C.c_void_p(out.data_ptr() + token_offset * C_ * out.element_size())
     L.check(L.load().emrt_groupnorm_tokens(_ptr(x), _ptr(gamma), _ptr(beta), dst, out.shape[1] * C_, _ptr(ws), B, P, C_,
                                            groups, float(eps), _dt(x), _stream()))

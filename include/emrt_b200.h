@@ -176,13 +176,17 @@ int emrt_conv3x3_tokens_fwd(const void* x, const void* w_packed, void* y, int B,
                             const int32_t* shapes_hw_host, int dtype, int w_dtype, int impl, void* stream);
 
 /* y = GELU(GroupNorm_l(conv)) + x per level (GroupNorm(groups, C) eps, exact erf GELU, :187-189); conv, x, y
- * [B, Lv, C] (dtype F32|BF16); gamma, beta F32 [L, C]; stats_workspace F32 [2 * B * L * groups] (scratch).         */
+ * [B, Lv, C] (dtype F32|BF16); gamma, beta F32 [L, C]; stats_workspace F32
+ * [emrt_groupnorm_workspace_floats(B, L, groups)] (scratch: sums, per-CTA partials, ticket counters — the statistics are
+ * reduced in a fixed order, no floating-point atomics, so results are bit-reproducible run to run).                  */
+long long emrt_groupnorm_workspace_floats(int B, int L, int groups);
 int emrt_groupnorm_gelu_residual(const void* conv, const void* x, const float* gamma, const float* beta, void* y,
                                  float* stats_workspace, int B, int Lv, int C, int L, int groups, float eps,
                                  const int32_t* shapes_hw_host, int dtype, void* stream);
 
 /* The same conv branch without ever materialising it: emrt_groupnorm_stats leaves the per (batch, level, group) sums
- * (sum, sum of squares; F32 [B, L, groups, 2]) of x [B, Lv, C]; emrt_residual_layernorm_gn then evaluates
+ * (sum, sum of squares; F32 [B, L, groups, 2] at the start of a buffer of emrt_groupnorm_workspace_floats(B, L, groups)
+ * floats) of x [B, Lv, C]; emrt_residual_layernorm_gn then evaluates
  *   y = LayerNorm(x + residual) * ln_gamma + ln_beta + GELU(GroupNorm_l(conv)) + skip
  * i.e. norm2 (:159-160) plus the layer's final `src + src_flatten` (:203) with src_flatten = conv branch (:187-196)
  * computed on the fly from the conv output, the layer input (skip) and those sums.  All tensors [B, Lv, C].            */
@@ -199,7 +203,7 @@ int emrt_nchw_to_tokens(const void* x, void* y, int B, int C, int P, int dtype, 
 
 /* GroupNorm(groups, C) of one level's projected tokens x [B, P, C] (input_proj[i][1], no activation) written into that
  * level's slot of the concatenated token tensor: y + b * y_batch_stride + p * C (y_batch_stride in elements = Lv * C).
- * stats_workspace F32 [2 * B * groups].                                                                               */
+ * stats_workspace F32 [emrt_groupnorm_workspace_floats(B, 1, groups)].                                                */
 int emrt_groupnorm_tokens(const void* x, const float* gamma, const float* beta, void* y, int64_t y_batch_stride,
                           float* stats_workspace, int B, int P, int C, int groups, float eps, int dtype, void* stream);
 
