@@ -466,6 +466,15 @@ def run_ours(args):
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": measured_traffic(B),
                 "algorithmic_bytes": gb * 1e9, "avg_launch_ms": avg_ms, "launches_timed": len(enc),
                 "share_of_step": avg_ms * len(enc) / args.steps / ms_step, "peak_source": peak_src}
+        # what actually bounds it: every (query, head) reads L*P*4 corners x D x 2 B from shared memory
+        b_, lq_, _, m_, d_, l_, p_, sv_, _ = enc[0][0]
+        onchip = float(b_) * lq_ * m_ * l_ * p_ * 4 * d_ * sv_
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        pipe = torch.cuda.get_device_properties(dev).multi_processor_count * 128.0 * sm_clk * 1e6
+        roof["on_chip"] = {"what": "shared-memory data pipe (128 B/clk/SM): corner reads of the gather, a floor for any formulation "
+                                   "that reads each bilinear corner from on-chip memory",
+                           "bytes": onchip, "achieved_gbs": onchip / (avg_ms * 1e-3) / 1e9, "peak_gbs": pipe / 1e9,
+                           "frac": onchip / (avg_ms * 1e-3) / pipe}
 
     if rank != 0:
         if world > 1:
