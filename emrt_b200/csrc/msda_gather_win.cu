@@ -304,7 +304,11 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
             slow_lv |= 1u << (a_l2[r] >> 1);
           }
         }
-        sts128(rec_base + a_rec[r] * 16, addr, wl, addr, wr);
+        // records are kept per (query, side): 8-byte entries {address, that side's weight pair}, the 18 points of a
+        // (query, side) contiguous, so stage B fetches two points per LDS.128 (9 loads per lane instead of 18 LDS.64)
+        const uint32_t rdst = rec_base + ((uint32_t)(a_qi[r] * 2 * WIN_LP) + (uint32_t)a_pt[r]) * 8;
+        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(rdst), "r"(addr), "r"(wl) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(rdst + WIN_LP * 8), "r"(addr), "r"(wr) : "memory");
       }
     }
     // next batch: claim it and start its loads now, they land while this batch gathers
@@ -328,16 +332,16 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const uint32_t my_rec = rec_base + (uint32_t)g * (WIN_LP * 16);
+    const uint32_t my_rec = rec_base + (uint32_t)(g * 2 + side) * (WIN_LP * 8);
 #pragma unroll
     for (int l = 0; l < WIN_L; ++l) {
       const uint32_t row_bytes = (uint32_t)p.WW[l] * (WIN_D * 2);
       // the level's six records first: {address, this side's weight pair}, 8 bytes per lane
       uint32_t addr[WIN_P], wpair[WIN_P];
 #pragma unroll
-      for (int pp = 0; pp < WIN_P; ++pp)
-        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(addr[pp]), "=r"(wpair[pp])
-                     : "r"(my_rec + (l * WIN_P + pp) * 16 + side * 8));
+      for (int pp = 0; pp < WIN_P; pp += 2)
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(addr[pp]), "=r"(wpair[pp]), "=r"(addr[pp + 1]), "=r"(wpair[pp + 1])
+                     : "r"(my_rec + (l * WIN_P + pp) * 8));
       // branch-free fast path in two halves of three points: six independent LDS.128 in flight, then 48 FHFMA
       // (flagged records carry weight -0.0 on the zero block)
 #pragma unroll
