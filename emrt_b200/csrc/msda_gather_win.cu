@@ -161,7 +161,7 @@ constexpr int WIN_MAX_Q = 512;                             // queries per region
 // multiple of the warp count (168 queries = 42 batches = 7 warps x 6); otherwise the warps claim batches dynamically, so
 // none idles while the CTA's shared-memory windows stay resident.
 template <typename TL, int MODE, int WIN_WARPS, bool STATIC>
-__global__ void __launch_bounds__(WIN_WARPS * 32, 2)
+__global__ void __launch_bounds__(WIN_WARPS * 32, WIN_WARPS > 12 ? 1 : 2)
 msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __restrict__ loc,
                            const TL* __restrict__ attn, const float* __restrict__ ref, int64_t ref_bs,
                            __nv_bfloat16* __restrict__ out, const __grid_constant__ WinParams p) {
@@ -457,7 +457,7 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
   // 7 warps x 6 batches covers the default 8 x 16 region (42 batches of 4 queries) exactly: static dealing, no counter
   const int n_batches = (p.TH * p.TW + (p.TH >> 1) * (p.TW >> 1) + (p.TH >> 2) * (p.TW >> 2) + WIN_QPB - 1) / WIN_QPB;
   int warps = env_int("EMRT_WIN_WARPS", 8);
-  if (warps != 7 && warps != 12) warps = 8;
+  if (warps != 7 && warps != 12 && warps != 16 && warps != 24) warps = 8;
   const bool stat = env_int("EMRT_WIN_STATIC", -1) >= 0 ? env_int("EMRT_WIN_STATIC", 0) != 0 : (n_batches % warps == 0);
   const size_t smem_bytes = (size_t)off + (size_t)warps * WIN_QPB * WIN_LP * (16 + 8);   // records + slow-point positions
   if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
@@ -470,7 +470,7 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
     return px ? launch_win<TL, 1, NW, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)             \
               : launch_win<TL, 0, NW, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);            \
   }
-#define EMRT_WIN(TL) EMRT_WIN_NW(TL, 7) EMRT_WIN_NW(TL, 12) EMRT_WIN_NW(TL, 8) return EMRT_ERR_UNSUPPORTED
+#define EMRT_WIN(TL) EMRT_WIN_NW(TL, 7) EMRT_WIN_NW(TL, 12) EMRT_WIN_NW(TL, 16) EMRT_WIN_NW(TL, 24) EMRT_WIN_NW(TL, 8) return EMRT_ERR_UNSUPPORTED
   switch (loc_dtype) {
     case EMRT_F32: EMRT_WIN(float);
     case EMRT_F16: EMRT_WIN(__half);
