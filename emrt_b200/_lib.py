@@ -46,6 +46,7 @@ SIGNATURES = {
     "emrt_launch_count": (C.c_int64, []),
     "emrt_reset_launch_count": (None, []),
     "emrt_msda_gather_fwd": (C.c_int, [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P, _I, _I, _I, _P]),
+    "emrt_msda_gather_fwd_hint": (C.c_int, [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P, _I, _I, _I, _I32P, _P]),
     "emrt_msda_gather_bwd": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P,
                                        _I, _I, _I, _P]),
     "emrt_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _P]),

@@ -72,6 +72,6 @@ int gather_fwd_v1(const void* value, const void* loc, const void* attn, const fl
 // shared memory; same contract as gather_fwd_v1, additionally needs Lq == Lv on a regular 3-level pyramid.
 int gather_fwd_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
                    int B, int Lq, int Lv, int M, int D, int L, int P, const LevelTable& lv, int loc_dtype, int mode,
-                   cudaStream_t st);
+                   const int32_t* win_center_host, cudaStream_t st);
 
 }  // namespace emrt

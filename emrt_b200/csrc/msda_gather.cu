@@ -242,10 +242,11 @@ static int check_common(const void* value, const void* loc, const void* attn, co
     }                                                                                                          \
   } while (0)
 
-extern "C" int emrt_msda_gather_fwd(const void* value, const void* loc, const void* attn, const float* ref,
-                                    int64_t ref_batch_stride, void* out, int B, int Lq, int Lv, int M, int D,
-                                    int L, int P, const int32_t* shapes_hw_host, const int32_t* level_start_host,
-                                    int value_dtype, int loc_dtype, int mode, void* stream) {
+extern "C" int emrt_msda_gather_fwd_hint(const void* value, const void* loc, const void* attn, const float* ref,
+                                         int64_t ref_batch_stride, void* out, int B, int Lq, int Lv, int M, int D,
+                                         int L, int P, const int32_t* shapes_hw_host,
+                                         const int32_t* level_start_host, int value_dtype, int loc_dtype, int mode,
+                                         const int32_t* window_center_host, void* stream) {
   if (int e = check_common(value, loc, attn, ref, B, Lq, Lv, M, D, L, P, value_dtype, loc_dtype, mode)) return e;
   EMRT_REQUIRE(out != nullptr, "out is NULL");
   LevelTable lv;
@@ -253,7 +254,8 @@ extern "C" int emrt_msda_gather_fwd(const void* value, const void* loc, const vo
   const int64_t n_items = (int64_t)B * Lq * M;
   cudaStream_t st = as_stream(stream);
   if (value_dtype == EMRT_BF16 && (mode & EMRT_QUERY_PIXEL_GRID) && !getenv("EMRT_GATHER_NO_WIN")) {
-    const int e = gather_fwd_win(value, loc, attn, ref, ref_batch_stride, out, B, Lq, Lv, M, D, L, P, lv, loc_dtype, mode, st);
+    const int e = gather_fwd_win(value, loc, attn, ref, ref_batch_stride, out, B, Lq, Lv, M, D, L, P, lv, loc_dtype, mode,
+                                 window_center_host, st);
     if (e != EMRT_ERR_UNSUPPORTED) return e;
   }
   mode &= ~EMRT_QUERY_PIXEL_GRID;
@@ -262,6 +264,14 @@ extern "C" int emrt_msda_gather_fwd(const void* value, const void* loc, const vo
     if (e != EMRT_ERR_UNSUPPORTED) return e;
   }
   EMRT_GATHER_DISPATCH(launch_fwd, value, loc, attn, ref, ref_batch_stride, out, Lq, Lv, M, L, P, lv, n_items, st);
+}
+
+extern "C" int emrt_msda_gather_fwd(const void* value, const void* loc, const void* attn, const float* ref,
+                                    int64_t ref_batch_stride, void* out, int B, int Lq, int Lv, int M, int D,
+                                    int L, int P, const int32_t* shapes_hw_host, const int32_t* level_start_host,
+                                    int value_dtype, int loc_dtype, int mode, void* stream) {
+  return emrt_msda_gather_fwd_hint(value, loc, attn, ref, ref_batch_stride, out, B, Lq, Lv, M, D, L, P, shapes_hw_host,
+                                   level_start_host, value_dtype, loc_dtype, mode, nullptr, stream);
 }
 
 extern "C" int emrt_msda_gather_bwd(const void* grad_out, const void* value, const void* loc, const void* attn,

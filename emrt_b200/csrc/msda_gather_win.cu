@@ -31,6 +31,7 @@ int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const vo
                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
 constexpr int WIN_L = 3, WIN_P = 6, WIN_LP = WIN_L * WIN_P, WIN_D = 32;
+constexpr int WIN_MAX_M = 16;                // heads a window-centre hint can describe
 constexpr int WIN_QPB = 4;                   // queries per warp batch (one LDS.128 serves 4 queries x 128 bytes)
 constexpr uint32_t WIN_SLOW = 0x80000000u;   // record flag (sign bit of the bottom weight, weights are >= 0):
                                              // take the global-memory path for this point
@@ -40,7 +41,8 @@ struct WinParams {
   int32_t WW[WIN_L], WH[WIN_L];  // window size in pixels
   uint32_t win_off[WIN_L];       // byte offset of window l in dynamic shared memory (offset 0 holds 128 zero bytes)
   uint32_t rec_off;              // byte offset of the footprint records
-  int32_t R, TH, TW, regions_x, regions_y;
+  int32_t R, TH, TW, tw_shift, regions_x, regions_y;
+  int8_t cshift[WIN_MAX_M][WIN_L][2];   // per (head, level): window centre shift (x, y) in level pixels — a locality hint
   int32_t Lq, Lv, M;
   LevelTable lv;
 };
@@ -82,20 +84,18 @@ __device__ __forceinline__ void fma_row(float (&acc)[8], const uint4& d, uint32_
   fhfma<0, WHI>(acc[6], d.w, wpair); fhfma<1, WHI>(acc[7], d.w, wpair);
 }
 
-// local query index inside the region (level-0 pixels first, then level 1, ...) -> global query index
-__device__ __forceinline__ int region_query(const WinParams& p, int k, int ry, int rx) {
-  int th = p.TH, tw = p.TW;
-#pragma unroll
-  for (int l = 0; l < WIN_L; ++l) {
-    const int n = th * tw;
-    if (k < n || l == WIN_L - 1) {
-      const int y = k / tw, x = k - y * tw;
-      return p.lv.start[l] + (ry * th + y) * p.lv.W[l] + rx * tw + x;
-    }
-    k -= n;
-    th >>= 1; tw >>= 1;
-  }
-  return 0;
+// First global query index of a warp batch.  A region's queries are numbered level 0 first (TH x TW pixels, row-major),
+// then the co-located (TH/2 x TW/2) pixels of level 1, then level 2; TW is a power of two >= 16 (host-checked), so the
+// WIN_QPB = 4 queries of a batch are consecutive pixels of one row and the batch count is exact (no padding).
+// Warp-uniform selects and shifts only: no per-CTA lookup table to build.  qb[l] = index of the region's first query
+// of level l, n0 / n01 = batch counts of level 0 / levels 0 + 1, sh0 = log2(TW / 4).
+__device__ __forceinline__ int batch_query_base(const WinParams& p, const int (&qb)[WIN_L], int n0, int n01, int sh0, int batch) {
+  const bool l1 = batch >= n0, l2 = batch >= n01;
+  const int k = batch - (l2 ? n01 : (l1 ? n0 : 0));
+  const int sh = sh0 - (l2 ? 2 : (l1 ? 1 : 0));
+  const int y = k >> sh, x = k - (y << sh);
+  const int W = l2 ? p.lv.W[2] : (l1 ? p.lv.W[1] : p.lv.W[0]);
+  return (l2 ? qb[2] : (l1 ? qb[1] : qb[0])) + y * W + (x << 2);
 }
 
 template <typename TL, int MODE>
@@ -117,7 +117,6 @@ __device__ __forceinline__ void sample_xy(const WinParams& p, const TL* __restri
   }
 }
 
-__device__ __forceinline__ int sel3(int l, int a0, int a1, int a2) { return l == 0 ? a0 : (l == 1 ? a1 : a2); }
 
 // Slow path of one point: it left the staged window (|offset| > R) but not the map.  Global loads with the explicit
 // zero-padding weights of make_footprint, from the sample position stage A kept; out-of-line so the unrolled fast path
@@ -154,8 +153,7 @@ __device__ __forceinline__ void raw_decode(const RawLoc<__nv_bfloat16>& r, float
   x = __uint_as_float(r.xy << 16); y = __uint_as_float(r.xy & 0xffff0000u); aw = __uint_as_float((unsigned int)r.aw << 16);
 }
 
-constexpr int WIN_ROUNDS = (WIN_QPB * WIN_LP + 31) / 32;   // stage-A rounds: one (query, point) per lane per round
-constexpr int WIN_MAX_Q = 512;                             // queries per region (TH*TW*(1 + 1/4 + 1/16)), upper bound
+static_assert(WIN_QPB * WIN_P <= 32, "stage A: one level's records of a batch fit one warp round");
 
 // STATIC: batches are dealt to the warps round-robin (no shared counter) — right when the batch count of a region is a
 // multiple of the warp count (168 queries = 42 batches = 7 warps x 6); otherwise the warps claim batches dynamically, so
@@ -168,15 +166,12 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t s_bar;
   __shared__ int s_next;
-  __shared__ int s_qtab[WIN_MAX_Q + WIN_QPB];     // region-local query index -> global query index (-1 = padding)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // blockIdx.x = ((b * regions + region) * M + m): the M heads of a region run back to back (shared loc rows)
-  const int m = blockIdx.x % p.M;
-  const int br = blockIdx.x / p.M;
-  const int n_regions = p.regions_x * p.regions_y;
-  const int region = br % n_regions;
-  const int b = br / n_regions;
+  // grid (M, regions, B): the M heads of a region run back to back (they share the region's loc / attn rows)
+  const int m = blockIdx.x;
+  const int region = blockIdx.y;
+  const int b = blockIdx.z;
   const int ry = region / p.regions_x, rx = region - ry * p.regions_x;
   const uint32_t smem_base = smem_u32(smem);
 
@@ -185,14 +180,12 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
 #pragma unroll
   for (int l = 0; l < WIN_L; ++l) {
     const int x0 = (rx * p.TW) >> l, y0 = (ry * p.TH) >> l;
-    ox[l] = min(max(x0 - p.R, -1), p.lv.W[l] + 1 - p.WW[l]);
-    oy[l] = min(max(y0 - p.R, -1), p.lv.H[l] + 1 - p.WH[l]);
+    const int cx = m < WIN_MAX_M ? p.cshift[m][l][0] : 0, cy = m < WIN_MAX_M ? p.cshift[m][l][1] : 0;
+    ox[l] = min(max(x0 - p.R + cx, -1), p.lv.W[l] + 1 - p.WW[l]);
+    oy[l] = min(max(y0 - p.R + cy, -1), p.lv.H[l] + 1 - p.WH[l]);
   }
   // queries of this region: TH*TW at level 0, a quarter of that at each coarser level
-  int n_queries = 0;
-#pragma unroll
-  for (int l = 0; l < WIN_L; ++l) n_queries += (p.TH >> l) * (p.TW >> l);
-  const int n_batches = (n_queries + WIN_QPB - 1) / WIN_QPB;
+  const int n_batches = ((p.TH * p.TW) >> 2) + ((p.TH * p.TW) >> 4) + ((p.TH * p.TW) >> 6);
 
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
@@ -200,8 +193,6 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
     fence_barrier_init();
   }
   if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(smem)[threadIdx.x] = 0u;   // what weight-0 records point at
-  for (int k = threadIdx.x; k < n_batches * WIN_QPB; k += WIN_WARPS * 32)
-    s_qtab[k] = k < n_queries ? region_query(p, k, ry, rx) : -1;
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t bytes = 0;
@@ -217,46 +208,45 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
   const uint32_t xy_base = smem_base + p.rec_off + (uint32_t)WIN_WARPS * (WIN_QPB * WIN_LP * 16) + (uint32_t)warp * (WIN_QPB * WIN_LP * 8);
   const int g = lane >> 3, s = lane & 7, side = s >> 2;
 
-  // ---- per-lane stage-A constants: round r handles (query qi[r], point pt[r]) of every batch ------------------------
-  int a_qi[WIN_ROUNDS], a_pt[WIN_ROUNDS], a_ox[WIN_ROUNDS], a_oy[WIN_ROUNDS], a_ww[WIN_ROUNDS], a_wh[WIN_ROUNDS];
-  uint32_t a_base[WIN_ROUNDS], a_rec[WIN_ROUNDS], a_l2[WIN_ROUNDS];
-  float a_W[WIN_ROUNDS], a_H[WIN_ROUNDS];
-  bool a_on[WIN_ROUNDS];
+  // ---- stage A works level by level: round l handles the WIN_QPB x WIN_P records of level l, one per lane
+  // (lane -> query a_qi = lane % 4, point a_pp = lane / 4, the same in every round; lanes 24-31 idle), so everything
+  // that depends on the level (map size, window origin / pitch / base) is warp-uniform and compile-time indexed.
+  // With this lane order the 8-byte record stores of a half-warp hit 32 distinct banks (query stride 72 words = 8 banks).
+  const bool a_on = lane < WIN_QPB * WIN_P;
+  const int a_qi = a_on ? (lane & (WIN_QPB - 1)) : 0;
+  const int a_pp = a_on ? (lane >> 2) : 0;
+  // records are kept per (query, side): 8-byte entries {address, that side's weight pair}, the 18 points of a
+  // (query, side) contiguous, so stage B fetches two points per LDS.128 (9 loads per lane instead of 18 LDS.64)
+  const uint32_t a_rdst = rec_base + ((uint32_t)(a_qi * 2 * WIN_LP) + (uint32_t)a_pp) * 8;
+  const uint32_t a_xydst = xy_base + (uint32_t)(a_qi * WIN_LP + a_pp) * 8;
+  float fW[WIN_L], fH[WIN_L];
 #pragma unroll
-  for (int r = 0; r < WIN_ROUNDS; ++r) {
-    const int j = r * 32 + lane;
-    a_on[r] = j < WIN_QPB * WIN_LP;
-    a_qi[r] = a_on[r] ? j / WIN_LP : 0;
-    a_pt[r] = a_on[r] ? j - a_qi[r] * WIN_LP : 0;
-    const int l = a_pt[r] / WIN_P;
-    a_ox[r] = sel3(l, ox[0], ox[1], ox[2]);
-    a_oy[r] = sel3(l, oy[0], oy[1], oy[2]);
-    a_ww[r] = p.WW[l];
-    a_wh[r] = p.WH[l];
-    a_base[r] = smem_base + p.win_off[l];
-    a_rec[r] = (uint32_t)(a_qi[r] * WIN_LP + a_pt[r]);
-    a_l2[r] = (uint32_t)l * 2u;
-    a_W[r] = (float)p.lv.W[l];
-    a_H[r] = (float)p.lv.H[l];
-  }
+  for (int l = 0; l < WIN_L; ++l) { fW[l] = (float)p.lv.W[l]; fH[l] = (float)p.lv.H[l]; }
 
-  RawLoc<TL> raw[WIN_ROUNDS];
-  float2 rref[WIN_ROUNDS];
-  // issue the global loads of one batch (no dependent branches: one memory latency per batch)
-  // 32-bit element offsets from per-(b, m) base pointers (the host checks they fit)
-  const TL* loc_bm = loc + (((int64_t)b * p.Lq) * p.M + m) * (WIN_LP * 2);
-  const TL* attn_bm = attn + (((int64_t)b * p.Lq) * p.M + m) * WIN_LP;
+  RawLoc<TL> raw[WIN_L];
+  float2 rref[WIN_L];
+  // issue the global loads of one batch (no dependent branches: one memory latency per batch): one 64-bit address per
+  // tensor and batch, the three levels at immediate offsets from it
+  const TL* loc_lane = loc + (((int64_t)b * p.Lq) * p.M + m) * (WIN_LP * 2) + a_pp * 2;
+  const TL* attn_lane = attn + (((int64_t)b * p.Lq) * p.M + m) * WIN_LP + a_pp;
   const float* ref_b = ref + (MODE == EMRT_LOC_PIXEL_OFFSET ? b * ref_bs : 0);
-  __nv_bfloat16* out_bm = out + (((int64_t)b * p.Lq) * p.M + m) * WIN_D + (s & 3) * 8 + side * 4;
-  auto fetch = [&](int batch) {
+  __nv_bfloat16* out_lane = out + (((int64_t)b * p.Lq) * p.M + m) * WIN_D + g * (p.M * WIN_D) + (s & 3) * 8 + side * 4;
+  const uint32_t item_stride = (uint32_t)p.M * WIN_LP;
+  int q_next = 0;     // first query of the prefetched batch (warp-uniform)
+  int qb[WIN_L];
 #pragma unroll
-    for (int r = 0; r < WIN_ROUNDS; ++r) {
-      const int q = s_qtab[batch * WIN_QPB + a_qi[r]];
-      const uint32_t qq = q < 0 ? 0u : (uint32_t)q;
-      const uint32_t e = qq * (uint32_t)p.M * WIN_LP + (uint32_t)a_pt[r];
-      raw_fetch(raw[r], loc_bm + 2u * e, attn_bm + e);
-      if (MODE == EMRT_LOC_PIXEL_OFFSET)
-        rref[r] = __ldg(reinterpret_cast<const float2*>(ref_b + (qq * (WIN_L * 2u) + a_l2[r])));
+  for (int l = 0; l < WIN_L; ++l) qb[l] = p.lv.start[l] + ((ry * p.TH) >> l) * p.lv.W[l] + ((rx * p.TW) >> l);
+  const int n0 = (p.TH * p.TW) >> 2, n01 = n0 + (n0 >> 2), sh0 = p.tw_shift - 2;
+  auto fetch = [&](int batch) {
+    q_next = batch_query_base(p, qb, n0, n01, sh0, batch);
+    const uint32_t qq = (uint32_t)(q_next + a_qi);
+    const TL* lp = loc_lane + (size_t)(qq * item_stride) * 2;
+    const TL* ap = attn_lane + (size_t)(qq * item_stride);
+    const float* rp = ref_b + (size_t)(qq * (WIN_L * 2u));
+#pragma unroll
+    for (int l = 0; l < WIN_L; ++l) {
+      raw_fetch(raw[l], lp + l * (WIN_P * 2), ap + l * WIN_P);
+      if (MODE == EMRT_LOC_PIXEL_OFFSET) rref[l] = __ldg(reinterpret_cast<const float2*>(rp + 2 * l));
     }
   };
 
@@ -265,30 +255,36 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
   bool windows_ready = false;
 
   while (batch < n_batches) {
+    // claim the next batch now: the shared-memory atomic's latency hides under stage A
+    const int cur_q = q_next;
+    int next = batch + WIN_WARPS;
+    if (!STATIC && lane == 0)
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(next) : "r"(smem_u32(&s_next)) : "memory");
     // ---- stage A: one footprint record per (query, point), from the prefetched inputs -----------------------------
     unsigned slow_lv = 0u;
+    if (a_on) {
 #pragma unroll
-    for (int r = 0; r < WIN_ROUNDS; ++r) {
-      if (a_on[r]) {
-        const int q = s_qtab[batch * WIN_QPB + a_qi[r]];
+      for (int l = 0; l < WIN_L; ++l) {
         float x, y, aw;
-        raw_decode(raw[r], x, y, aw);
+        raw_decode(raw[l], x, y, aw);
         if (MODE == EMRT_LOC_PIXEL_OFFSET) {
-          x = rref[r].x * a_W[r] - 0.5f + x;
-          y = rref[r].y * a_H[r] - 0.5f + y;
+          x = rref[l].x * fW[l] - 0.5f + x;
+          y = rref[l].y * fH[l] - 0.5f + y;
         } else {
-          x = x * a_W[r] - 0.5f;
-          y = y * a_H[r] - 0.5f;
+          x = x * fW[l] - 0.5f;
+          y = y * fH[l] - 0.5f;
         }
         // The window lies inside [-1, W] x [-1, H], so "both pixel pairs inside the window" implies the sample is live;
-        // the fmaxf sends NaN (whose float -> int conversion is 0) and -inf below every window origin (>= -1).
-        const float x0f = floorf(x), y0f = floorf(y);
-        const float fx = x - x0f, fy = y - y0f;
-        const int wx = (int)fmaxf(x0f, -2.f) - a_ox[r], wy = (int)fmaxf(y0f, -2.f) - a_oy[r];
-        const bool fast = (q >= 0) && (unsigned)wx < (unsigned)(a_ww[r] - 1) && (unsigned)wy < (unsigned)(a_wh[r] - 1);
+        // the fmaxf sends NaN and -inf to -2, below every window origin (>= -1); +inf converts to INT_MAX, whose
+        // window coordinate fails the unsigned compare as well.
+        const float xs = fmaxf(x, -2.f), ys = fmaxf(y, -2.f);
+        const int xi = __float2int_rd(xs), yi = __float2int_rd(ys);
+        const float fx = xs - (float)xi, fy = ys - (float)yi;
+        const int wx = xi - ox[l], wy = yi - oy[l];
+        const bool fast = (unsigned)wx < (unsigned)(p.WW[l] - 1) && (unsigned)wy < (unsigned)(p.WH[l] - 1);
         const float gx = 1.f - fx, gy = 1.f - fy;
         const float gxa = gx * aw, fxa = fx * aw;
-        uint32_t addr = a_base[r] + (uint32_t)(wy * a_ww[r] + wx) * (WIN_D * 2);
+        uint32_t addr = smem_base + p.win_off[l] + (uint32_t)(wy * p.WW[l] + wx) * (WIN_D * 2);
         uint32_t wl = pack_bf16(gxa * gy, gxa * fy);   // left pixel: top, bottom
         uint32_t wr = pack_bf16(fxa * gy, fxa * fy);   // right pixel: top, bottom
         if (!fast) {
@@ -296,29 +292,20 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
           // weight 0 on the zero block.  Live but outside the window: the zero block again (so the fast path adds
           // nothing), the SLOW flag in the sign bit of the bottom weight, the attention weight in the low half and the
           // sample position in the side buffer for the fix-up
-          const bool live = (q >= 0) && (x > -1.f) && (y > -1.f) && (x < a_W[r]) && (y < a_H[r]);
+          const bool live = (x > -1.f) && (y > -1.f) && (x < fW[l]) && (y < fH[l]);
           addr = smem_base;
           wl = wr = live ? (WIN_SLOW | (pack_bf16(aw, 0.f) & 0xffffu)) : 0u;
           if (live) {
-            asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(xy_base + a_rec[r] * 8), "f"(x), "f"(y) : "memory");
-            slow_lv |= 1u << (a_l2[r] >> 1);
+            asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a_xydst + l * (WIN_P * 8)), "f"(x), "f"(y) : "memory");
+            slow_lv |= 1u << l;
           }
         }
-        // records are kept per (query, side): 8-byte entries {address, that side's weight pair}, the 18 points of a
-        // (query, side) contiguous, so stage B fetches two points per LDS.128 (9 loads per lane instead of 18 LDS.64)
-        const uint32_t rdst = rec_base + ((uint32_t)(a_qi[r] * 2 * WIN_LP) + (uint32_t)a_pt[r]) * 8;
-        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(rdst), "r"(addr), "r"(wl) : "memory");
-        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(rdst + WIN_LP * 8), "r"(addr), "r"(wr) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a_rdst + l * (WIN_P * 8)), "r"(addr), "r"(wl) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a_rdst + l * (WIN_P * 8) + WIN_LP * 8), "r"(addr), "r"(wr) : "memory");
       }
     }
-    // next batch: claim it and start its loads now, they land while this batch gathers
-    const int cur = batch;
-    if (STATIC) {
-      batch += WIN_WARPS;
-    } else {
-      if (lane == 0) batch = atomicAdd(&s_next, 1);
-      batch = __shfl_sync(0xffffffffu, batch, 0);
-    }
+    // next batch: start its loads now, they land while this batch gathers
+    batch = STATIC ? next : __shfl_sync(0xffffffffu, next, 0);
     const unsigned slow_levels = __reduce_or_sync(0xffffffffu, slow_lv);   // levels of this batch with a fix-up point
     if (batch < n_batches) fetch(batch);
     __syncwarp();
@@ -328,7 +315,6 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
     }
 
     // ---- stage B: 8 lanes per query; lane s reads bytes [16 s, 16 s + 16) of the 128-byte pixel pair ----------------
-    const int q = s_qtab[cur * WIN_QPB + g];
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -385,12 +371,10 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
       const float send = side ? acc[i] : acc[4 + i];
       keep[i] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
     }
-    if (q >= 0) {
-      uint2 o;
-      o.x = pack_bf16(keep[0], keep[1]);
-      o.y = pack_bf16(keep[2], keep[3]);
-      *reinterpret_cast<uint2*>(out_bm + (uint32_t)q * (uint32_t)(p.M * WIN_D)) = o;
-    }
+    uint2 o;
+    o.x = pack_bf16(keep[0], keep[1]);
+    o.y = pack_bf16(keep[2], keep[3]);
+    *reinterpret_cast<uint2*>(out_lane + (uint32_t)cur_q * (uint32_t)(p.M * WIN_D)) = o;
     __syncwarp();   // records are rewritten by the next batch
   }
   if (!windows_ready) mbar_wait(&s_bar, 0);   // never leave with a TMA still writing this CTA's shared memory
@@ -410,10 +394,10 @@ static int launch_win(const void* value, const void* loc, const void* attn, cons
     EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr = smem_bytes;
   }
-  const int64_t grid = (int64_t)B * p.regions_x * p.regions_y * p.M;
-  if (grid > 0x7fffffffLL) return EMRT_ERR_UNSUPPORTED;
-  kern<<<(unsigned)grid, NW * 32, smem_bytes, st>>>((const __nv_bfloat16*)value, (const TL*)loc, (const TL*)attn,
-                                                           ref, ref_bs, (__nv_bfloat16*)out, p);
+  const int n_regions = p.regions_x * p.regions_y;
+  if (B > 65535 || n_regions > 65535) return EMRT_ERR_UNSUPPORTED;
+  kern<<<dim3((unsigned)p.M, (unsigned)n_regions, (unsigned)B), NW * 32, smem_bytes, st>>>(
+      (const __nv_bfloat16*)value, (const TL*)loc, (const TL*)attn, ref, ref_bs, (__nv_bfloat16*)out, p);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
 }
@@ -422,7 +406,7 @@ static int launch_win(const void* value, const void* loc, const void* attn, cons
 // tiles; the caller then falls back to the L1-path kernel.
 int gather_fwd_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
                    int B, int Lq, int Lv, int M, int D, int L, int P, const LevelTable& lv, int loc_dtype, int mode,
-                   cudaStream_t st) {
+                   const int32_t* win_center_host, cudaStream_t st) {
   if (D != WIN_D || L != WIN_L || P != WIN_P || Lq != Lv || !(mode & EMRT_VALUE_HEAD_MAJOR)) return EMRT_ERR_UNSUPPORTED;
   for (int l = 1; l < L; ++l)
     if (lv.H[l] != (lv.H[0] >> l) || lv.W[l] != (lv.W[0] >> l) || (lv.H[l] << l) != lv.H[0] || (lv.W[l] << l) != lv.W[0])
@@ -432,12 +416,21 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
   p.R = env_int("EMRT_WIN_R", 7);
   p.TH = env_int("EMRT_WIN_TH", 8);
   p.TW = env_int("EMRT_WIN_TW", 16);
-  if (p.R < 1 || p.TH < 4 || p.TW < 4 || (p.TH & 3) || (p.TW & 3) || lv.H[0] % p.TH || lv.W[0] % p.TW) return EMRT_ERR_UNSUPPORTED;
+  // TW a power of two >= 16 and TH a multiple of 4: every level's region rows hold whole batches of 4 queries
+  if (p.R < 1 || p.TH < 4 || p.TW < 16 || (p.TH & 3) || (p.TW & (p.TW - 1)) || lv.H[0] % p.TH || lv.W[0] % p.TW) return EMRT_ERR_UNSUPPORTED;
+  for (p.tw_shift = 0; (1 << p.tw_shift) < p.TW; ++p.tw_shift) {}
   if ((int64_t)Lq * M * WIN_LP * 2 >= (1LL << 31)) return EMRT_ERR_UNSUPPORTED;   // 32-bit per-batch-element offsets
-  if (p.TH * p.TW + (p.TH >> 1) * (p.TW >> 1) + (p.TH >> 2) * (p.TW >> 2) > WIN_MAX_Q) return EMRT_ERR_UNSUPPORTED;
   p.regions_x = lv.W[0] / p.TW;
   p.regions_y = lv.H[0] / p.TH;
   p.Lq = Lq; p.Lv = Lv; p.M = M; p.lv = lv;
+  // window-centre hint [M, L, 2] (x, y) in pixels of level l: where head m's samples of level l lie relative to the
+  // reference point on average (the sampling_offsets bias).  Only moves the staged windows; any sample outside them
+  // still takes the global-memory path, so results never depend on it.
+  if (win_center_host && M <= WIN_MAX_M && !getenv("EMRT_WIN_NO_HINT"))
+    for (int mm = 0; mm < M; ++mm)
+      for (int l = 0; l < L; ++l)
+        for (int k = 0; k < 2; ++k)
+          p.cshift[mm][l][k] = (int8_t)std::min(std::max(win_center_host[(mm * L + l) * 2 + k], -100), 100);
   uint32_t off = 128;   // [0,128): zero block
   for (int l = 0; l < L; ++l) {
     p.WW[l] = std::min((p.TW >> l) + 2 * p.R + 1, lv.W[l] + 2);
@@ -456,8 +449,10 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
   p.rec_off = off;
   // 7 warps x 6 batches covers the default 8 x 16 region (42 batches of 4 queries) exactly: static dealing, no counter
   const int n_batches = (p.TH * p.TW + (p.TH >> 1) * (p.TW >> 1) + (p.TH >> 2) * (p.TW >> 2) + WIN_QPB - 1) / WIN_QPB;
-  int warps = env_int("EMRT_WIN_WARPS", 8);
-  if (warps != 7 && warps != 12 && warps != 16 && warps != 24) warps = 8;
+  // 10 warps x 2 CTAs per SM: 20 resident warps at 84 registers and 111 KB of windows + records per CTA (measured best of
+  // 8 / 10 / 12, profiles/r1s_gather_sweep.txt)
+  int warps = env_int("EMRT_WIN_WARPS", 10);
+  if (warps != 7 && warps != 8 && warps != 12 && warps != 16 && warps != 24) warps = 10;
   const bool stat = env_int("EMRT_WIN_STATIC", -1) >= 0 ? env_int("EMRT_WIN_STATIC", 0) != 0 : (n_batches % warps == 0);
   const size_t smem_bytes = (size_t)off + (size_t)warps * WIN_QPB * WIN_LP * (16 + 8);   // records + slow-point positions
   if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
@@ -470,7 +465,7 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
     return px ? launch_win<TL, 1, NW, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st)             \
               : launch_win<TL, 0, NW, false>(value, loc, attn, ref, ref_bs, out, B, p, smem_bytes, st);            \
   }
-#define EMRT_WIN(TL) EMRT_WIN_NW(TL, 7) EMRT_WIN_NW(TL, 12) EMRT_WIN_NW(TL, 16) EMRT_WIN_NW(TL, 24) EMRT_WIN_NW(TL, 8) return EMRT_ERR_UNSUPPORTED
+#define EMRT_WIN(TL) EMRT_WIN_NW(TL, 7) EMRT_WIN_NW(TL, 10) EMRT_WIN_NW(TL, 12) EMRT_WIN_NW(TL, 16) EMRT_WIN_NW(TL, 24) EMRT_WIN_NW(TL, 8) return EMRT_ERR_UNSUPPORTED
   switch (loc_dtype) {
     case EMRT_F32: EMRT_WIN(float);
     case EMRT_F16: EMRT_WIN(__half);

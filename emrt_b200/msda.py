@@ -212,6 +212,11 @@ class MSDeformableAttention(nn.Module):
             bq = torch.cat([self.sampling_offsets.bias.detach(), self.attention_weights.bias.detach()]).float().contiguous()
             packed = dict(wv=wv, wq=wq, wo=wo, bv=self.value_proj.bias.detach().float().contiguous(), bq=bq,
                           bo=self.output_proj.bias.detach().float().contiguous())
+            # window-centre hint of the staged gather: per (head, level) the rounded mid-range of the offset bias over
+            # the points (t_e_d.py:47-55 initialises it to one direction per head, 1..P pixels out), in level pixels
+            ob = self.sampling_offsets.bias.detach().float().view(self.num_heads, self.num_levels, self.num_points, 2)
+            mid = ((ob.amax(dim=2) + ob.amin(dim=2)) * 0.5).round().clamp(-100, 100).to(torch.int32).cpu()
+            packed["win_center"] = L.i32_array(mid.reshape(-1).tolist())
         self._packed = (ver, packed)
         return packed
 
@@ -288,7 +293,8 @@ class MSDeformableAttention(nn.Module):
             # encoder self-attention (queries = the pyramid's own pixels): window-staged kernel
             grid = L.QUERY_PIXEL_GRID if (getattr(ref, "pixel_grid", False) and Len_q == value.shape[1]) else 0
             out = ops.msda_gather_fwd(v.view(bs, M, -1, D), off_px, attn, shapes, ref=ref32,
-                                      mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR | grid)
+                                      mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR | grid,
+                                      win_center=pk["win_center"] if grid else None)
         else:
             out = ops.msda_gather_fwd(v.view(bs, -1, M, D), off_px, attn, shapes, ref=ref32, mode=L.LOC_PIXEL_OFFSET)
         return ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl)

@@ -81,8 +81,10 @@ def reset_launch_count():
 
 
 # ---- a3 ------------------------------------------------------------------------------------------------------
-def msda_gather_fwd(value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, out=None):
-    """value [B,Lv,M,D]; loc [B,Lq,M,L,P,2]; attn [B,Lq,M,L,P]; ref [Bref,Lq,L,2] f32 (PIXEL_OFFSET) -> [B,Lq,M*D]."""
+def msda_gather_fwd(value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, out=None, win_center=None):
+    """value [B,Lv,M,D]; loc [B,Lq,M,L,P,2]; attn [B,Lq,M,L,P]; ref [Bref,Lq,L,2] f32 (PIXEL_OFFSET) -> [B,Lq,M*D].
+    win_center: optional host int32 array [M*L*2] from `L.i32_array` — the window-centre hint of
+    emrt_msda_gather_fwd_hint (a locality hint for the window-staged kernel; results do not depend on it)."""
     lib = L.load()
     if mode & L.VALUE_HEAD_MAJOR:
         B, M, Lv, D = value.shape
@@ -97,8 +99,8 @@ def msda_gather_fwd(value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, o
     if kernel_events is not None:      # bench.py: CUDA events around this launch, on the launching stream
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    L.check(lib.emrt_msda_gather_fwd(_ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(out), B, Lq, Lv, M, D,
-                                     nL, P, hw, start, _dt(value), _dt(loc), mode, _stream()))
+    L.check(lib.emrt_msda_gather_fwd_hint(_ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(out), B, Lq, Lv, M,
+                                          D, nL, P, hw, start, _dt(value), _dt(loc), mode, win_center, _stream()))
     if ev is not None:
         ev[1].record()
         kernel_events.append(("msda_gather_fwd", (B, Lq, Lv, M, D, nL, P, value.element_size(), loc.element_size()), ev))

@@ -86,6 +86,17 @@ int emrt_msda_gather_fwd(const void* value, const void* loc, const void* attn, c
                          int P, const int32_t* shapes_hw_host, const int32_t* level_start_host,
                          int value_dtype, int loc_dtype, int mode, void* stream);
 
+/* Same, with a locality hint for the window-staged kernel (mode EMRT_QUERY_PIXEL_GRID): window_center_host is a host
+ * int32 [M,L,2] (x, y) in pixels of level l — where head m's samples of level l lie relative to the reference point
+ * on average, i.e. the rounded mid-range of the `sampling_offsets` bias (transformer_encoder_decoder.py:47-55 initialises
+ * it to one direction per head).  The staged windows are centred there.  NULL = centred on the reference points.
+ * Results never depend on the hint: a sample outside the staged window is read from global memory.               */
+int emrt_msda_gather_fwd_hint(const void* value, const void* loc, const void* attn, const float* ref,
+                              int64_t ref_batch_stride, void* out, int B, int Lq, int Lv, int M, int D, int L,
+                              int P, const int32_t* shapes_hw_host, const int32_t* level_start_host,
+                              int value_dtype, int loc_dtype, int mode, const int32_t* window_center_host,
+                              void* stream);
+
 /* Backward of the above (what Paddle autograd derives through F.grid_sample, utils.py:87-94).
  * grad_out [B,Lq,M*D] (value_dtype); grad_value F32 [B,Lv,M,D] MUST be zeroed by the caller (accumulated);
  * grad_loc F32 [B,Lq,M,L,P,2] (d/d loc in the units of `mode`), grad_attn F32 [B,Lq,M,L,P].              */

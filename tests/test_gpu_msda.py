@@ -330,10 +330,22 @@ def test_gather_window_staged_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
         # normalised-location mode through the same kernel
         locd = d(loc.astype(np.float32)).to(loc_dtype)
         got_n = ops.msda_gather_fwd(v_hm, locd, ad, shapes, mode=L.LOC_NORMALIZED | L.VALUE_HEAD_MAJOR | L.QUERY_PIXEL_GRID)
+        # window-centre hints (emrt_msda_gather_fwd_hint) only move the staged windows: the matching hint (mid-range of
+        # the offset bias per head and level) and a wild one (every sample leaves its window) give the same result
+        b4 = bias.reshape(M, 3, P, 2)
+        mid = np.rint((b4.max(axis=2) + b4.min(axis=2)) * 0.5).astype(np.int32)
+        got_hint = ops.msda_gather_fwd(v_hm, od, ad, shapes, ref=ref_t, mode=base | L.QUERY_PIXEL_GRID,
+                                       win_center=L.i32_array(mid.reshape(-1).tolist()))
+        wild = np.where(np.arange(M * 3 * 2) % 2 == 0, 40, -40).astype(np.int32)
+        got_wild = ops.msda_gather_fwd(v_hm, od, ad, shapes, ref=ref_t, mode=base | L.QUERY_PIXEL_GRID,
+                                       win_center=L.i32_array(wild.tolist()))
+        assert ops.launch_count() == before + 4
     finally:
         os.environ.pop("EMRT_WIN_R", None)
     torch.cuda.synchronize()
     assert rel_err(got.float(), want) < BF16_TOL
+    assert rel_err(got_hint.float(), want) < BF16_TOL
+    assert rel_err(got_wild.float(), want) < BF16_TOL
     assert rel_err(got.float(), got_l1.float().cpu()) < BF16_TOL
     want_n = O.gather_corner_loop(value.float().numpy(), shapes, locd.float().cpu().numpy(), attn.float().numpy())
     assert rel_err(got_n.float(), want_n) < BF16_TOL
