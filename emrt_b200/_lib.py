@@ -49,6 +49,8 @@ SIGNATURES = {
     "emrt_msda_gather_fwd_hint": (C.c_int, [_P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P, _I, _I, _I, _I32P, _P]),
     "emrt_msda_gather_bwd": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P,
                                        _I, _I, _I, _P]),
+    "emrt_msda_gather_bwd_hint": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P,
+                                            _I, _I, _I, _I32P, _P]),
     "emrt_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _P]),
     "emrt_pack_weight": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
     "emrt_linear_bwd_weight": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),

@@ -74,4 +74,11 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
                    int B, int Lq, int Lv, int M, int D, int L, int P, const LevelTable& lv, int loc_dtype, int mode,
                    const int32_t* win_center_host, cudaStream_t st);
 
+// Windowed backward (msda_gather_bwd_win.cu): grad_value accumulated in fixed point in shared-memory windows (integer
+// shared-memory reductions), one float reduction per window pixel to L2; same contract as the generic backward,
+// pixel-major bf16 value, Lq == Lv on a regular 3-level pyramid.
+int gather_bwd_win(const void* go, const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs,
+                   float* gv, float* gl, float* ga, int B, int Lq, int Lv, int M, int D, int L, int P,
+                   const LevelTable& lv, int loc_dtype, int mode, const int32_t* win_center_host, cudaStream_t st);
+
 }  // namespace emrt

@@ -274,17 +274,35 @@ extern "C" int emrt_msda_gather_fwd(const void* value, const void* loc, const vo
                                    level_start_host, value_dtype, loc_dtype, mode, nullptr, stream);
 }
 
-extern "C" int emrt_msda_gather_bwd(const void* grad_out, const void* value, const void* loc, const void* attn,
-                                    const float* ref, int64_t ref_batch_stride, float* grad_value, float* grad_loc,
-                                    float* grad_attn, int B, int Lq, int Lv, int M, int D, int L, int P,
-                                    const int32_t* shapes_hw_host, const int32_t* level_start_host,
-                                    int value_dtype, int loc_dtype, int mode, void* stream) {
+extern "C" int emrt_msda_gather_bwd_hint(const void* grad_out, const void* value, const void* loc, const void* attn,
+                                         const float* ref, int64_t ref_batch_stride, float* grad_value,
+                                         float* grad_loc, float* grad_attn, int B, int Lq, int Lv, int M, int D, int L,
+                                         int P, const int32_t* shapes_hw_host, const int32_t* level_start_host,
+                                         int value_dtype, int loc_dtype, int mode, const int32_t* window_center_host,
+                                         void* stream) {
   if (int e = check_common(value, loc, attn, ref, B, Lq, Lv, M, D, L, P, value_dtype, loc_dtype, mode)) return e;
   EMRT_REQUIRE(grad_out && grad_value && grad_loc && grad_attn, "NULL gradient pointer");
   LevelTable lv;
   if (int e = fill_levels(lv, L, shapes_hw_host, level_start_host, Lv)) return e;
   const int64_t n_items = (int64_t)B * Lq * M;
   cudaStream_t st = as_stream(stream);
+  if (value_dtype == EMRT_BF16 && (mode & EMRT_QUERY_PIXEL_GRID) && !(mode & EMRT_VALUE_HEAD_MAJOR) &&
+      !getenv("EMRT_GATHER_NO_WIN")) {
+    const int e = gather_bwd_win(grad_out, value, loc, attn, ref, ref_batch_stride, grad_value, grad_loc, grad_attn, B, Lq,
+                                 Lv, M, D, L, P, lv, loc_dtype, mode, window_center_host, st);
+    if (e != EMRT_ERR_UNSUPPORTED) return e;
+  }
+  mode &= ~EMRT_QUERY_PIXEL_GRID;
   EMRT_GATHER_DISPATCH(launch_bwd, grad_out, value, loc, attn, ref, ref_batch_stride, grad_value, grad_loc,
                        grad_attn, Lq, Lv, M, L, P, lv, n_items, st);
+}
+
+extern "C" int emrt_msda_gather_bwd(const void* grad_out, const void* value, const void* loc, const void* attn,
+                                    const float* ref, int64_t ref_batch_stride, float* grad_value, float* grad_loc,
+                                    float* grad_attn, int B, int Lq, int Lv, int M, int D, int L, int P,
+                                    const int32_t* shapes_hw_host, const int32_t* level_start_host,
+                                    int value_dtype, int loc_dtype, int mode, void* stream) {
+  return emrt_msda_gather_bwd_hint(grad_out, value, loc, attn, ref, ref_batch_stride, grad_value, grad_loc, grad_attn, B,
+                                   Lq, Lv, M, D, L, P, shapes_hw_host, level_start_host, value_dtype, loc_dtype, mode,
+                                   nullptr, stream);
 }

@@ -68,7 +68,7 @@ class _MSDAFunction(torch.autograd.Function):
     intermediates (projected value, offsets, softmax weights, gathered tokens) instead of recomputing them."""
 
     @staticmethod
-    def forward(ctx, mod, query, ref, value, mask, shapes, w_off, b_off, w_attn, b_attn, w_val, b_val, w_out, b_out):
+    def forward(ctx, mod, query, ref, value, mask, shapes, grid, w_off, b_off, w_attn, b_attn, w_val, b_val, w_out, b_out):
         M, P, D, nL = mod.num_heads, mod.num_points, mod.head_dim, mod.num_levels
         bs, Len_q = query.shape[:2]
         query, value = query.contiguous(), value.contiguous()
@@ -100,6 +100,9 @@ class _MSDAFunction(torch.autograd.Function):
             loc, attn = ops.msda_softmax_loc(off, logit, shapes, M, P, ref=ref, out_dtype=torch.float32, mode=mode)
             g = ops.msda_gather_fwd(v.view(bs, -1, M, D), loc, attn, shapes, mode=mode)
             out = ops.linear(g, w_out.detach(), b_out.detach(), impl=L.IMPL_SIMT)
+        # encoder self-attention on the pyramid's own pixels: the backward gather accumulates grad_value in windows
+        ctx.grid = L.QUERY_PIXEL_GRID if (grid and fast and Len_q == value.shape[1]) else 0
+        ctx.win_center = mod.packed_weights()["win_center"] if ctx.grid else None
         ctx.mod, ctx.shapes, ctx.mode, ctx.fast = mod, shapes, mode, fast
         ctx.save_for_backward(query, value, ref, mask, v, loc, attn, g, w_off, w_attn, w_val, w_out)
         return out
@@ -125,7 +128,8 @@ class _MSDAFunction(torch.autograd.Function):
         ops.linear_bwd_weight(g, d_out, dw_out, db_out)
         # gather
         ref_arg = ref if mode == L.LOC_PIXEL_OFFSET else None
-        gv, gl, ga = ops.msda_gather_bwd(d_g, v.view(bs, -1, M, D), loc, attn, shapes, ref=ref_arg, mode=mode)
+        gv, gl, ga = ops.msda_gather_bwd(d_g, v.view(bs, -1, M, D), loc, attn, shapes, ref=ref_arg, mode=mode | ctx.grid,
+                                         win_center=ctx.win_center)
         # softmax + offsets -> fused query projection
         dq = ops.msda_qproj_bwd(gl, ga, attn, shapes, M, P, out_dtype=cdt, mode=mode)
         d_query = ops.linear(dq, wq_kn, None, w_transposed=True, impl=impl)
@@ -136,7 +140,7 @@ class _MSDAFunction(torch.autograd.Function):
         d_value = ops.linear(d_v, wv_kn, None, w_transposed=True, impl=impl)
         dw_val, db_val = torch.zeros((C_, C_), **f32), torch.zeros((C_,), **f32)
         ops.linear_bwd_weight(value, d_v, dw_val, db_val)
-        return (None, d_query, None, d_value, None, None,
+        return (None, d_query, None, d_value, None, None, None,
                 dw_q[:, :2 * tp].contiguous(), db_q[:2 * tp].contiguous(), dw_q[:, 2 * tp:].contiguous(),
                 db_q[2 * tp:].contiguous(), dw_val, db_val, dw_out, db_out)
 
@@ -239,7 +243,8 @@ class MSDeformableAttention(nn.Module):
                                         or any(p.requires_grad for p in self.parameters())):
             mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
             ref32 = reference_points.detach().float().contiguous()
-            return _MSDAFunction.apply(self, query, ref32, value, mask, shapes,
+            grid = bool(getattr(reference_points, "pixel_grid", False))
+            return _MSDAFunction.apply(self, query, ref32, value, mask, shapes, grid,
                                        self.sampling_offsets.weight, self.sampling_offsets.bias,
                                        self.attention_weights.weight, self.attention_weights.bias,
                                        self.value_proj.weight, self.value_proj.bias,

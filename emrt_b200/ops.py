@@ -107,7 +107,9 @@ def msda_gather_fwd(value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, o
     return out
 
 
-def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED):
+def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NORMALIZED, win_center=None):
+    """-> grad_value f32 [B,Lv,M,D], grad_loc f32 [B,Lq,M,L,P,2], grad_attn f32 [B,Lq,M,L,P].  mode | QUERY_PIXEL_GRID
+    selects the windowed backward (shared-memory fixed-point accumulation) on encoder geometry."""
     lib = L.load()
     B, Lv, M, D = value.shape
     _, Lq, _, nL, P, _ = loc.shape
@@ -116,9 +118,9 @@ def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NOR
     gl = torch.empty(tuple(loc.shape), dtype=torch.float32, device=value.device)
     ga = torch.empty(tuple(attn.shape), dtype=torch.float32, device=value.device)
     rbs = 0 if ref is None or ref.shape[0] == 1 else Lq * nL * 2
-    L.check(lib.emrt_msda_gather_bwd(_ptr(grad_out), _ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(gv),
-                                     _ptr(gl), _ptr(ga), B, Lq, Lv, M, D, nL, P, hw, start, _dt(value), _dt(loc), mode,
-                                     _stream()))
+    L.check(lib.emrt_msda_gather_bwd_hint(_ptr(grad_out), _ptr(value), _ptr(loc), _ptr(attn), _ptr(ref), rbs, _ptr(gv),
+                                          _ptr(gl), _ptr(ga), B, Lq, Lv, M, D, nL, P, hw, start, _dt(value), _dt(loc),
+                                          mode, win_center, _stream()))
     return gv, gl, ga
 
 

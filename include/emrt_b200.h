@@ -106,6 +106,16 @@ int emrt_msda_gather_bwd(const void* grad_out, const void* value, const void* lo
                          const int32_t* shapes_hw_host, const int32_t* level_start_host, int value_dtype,
                          int loc_dtype, int mode, void* stream);
 
+/* Same, selecting the windowed backward when `mode` carries EMRT_QUERY_PIXEL_GRID (bf16 pixel-major value, D=32, L=3,
+ * P=6, Lq == Lv on a regular pyramid): grad_value is accumulated in fixed point in shared-memory windows with integer
+ * shared-memory reductions and sent to L2 once per window pixel (no float atomics on the hot path); window_center_host
+ * is the same optional hint as in emrt_msda_gather_fwd_hint.  Other shapes run the generic backward.               */
+int emrt_msda_gather_bwd_hint(const void* grad_out, const void* value, const void* loc, const void* attn,
+                              const float* ref, int64_t ref_batch_stride, float* grad_value, float* grad_loc,
+                              float* grad_attn, int B, int Lq, int Lv, int M, int D, int L, int P,
+                              const int32_t* shapes_hw_host, const int32_t* level_start_host, int value_dtype,
+                              int loc_dtype, int mode, const int32_t* window_center_host, void* stream);
+
 /* ---- nn.Linear (transformer_encoder_decoder.py:36-42,83,89,92,106,118,121) ------------------------------
  * y[rows,N] = epilogue(x[rows,K] @ W + bias).  W is given either in Paddle's own layout [K,N]
  * (w_transposed = 0) or pre-packed [N,K] (w_transposed = 1, see emrt_pack_weight).  x_dtype F32 runs the

@@ -351,6 +351,67 @@ def test_gather_window_staged_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
     assert rel_err(got_n.float(), want_n) < BF16_TOL
 
 
+@pytest.mark.parametrize("tile,B,spread,R,loc_dtype", [(256, 2, 1.0, None, torch.float16), (512, 1, 1.0, None, torch.float16),
+                                                        (128, 2, 3.0, None, torch.float32), (256, 1, 3.0, "2", torch.float16)])
+def test_gather_bwd_windowed_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
+    """EMRT_QUERY_PIXEL_GRID backward: grad_value accumulated in fixed point in shared-memory windows (integer
+    shared-memory reductions), grad_loc / grad_attn by shuffles.  Checked against the generic backward (float
+    reductions in L2) on the same bf16 inputs, against torch autograd through the float64 oracle, with and without a
+    window-centre hint, and in both location modes.  spread 3 / R=2 push samples out of the windows (global fallback)
+    and out of the map."""
+    shapes = [(tile // 8,) * 2, (tile // 16,) * 2, (tile // 32,) * 2]
+    M, D, P = 8, 32, 6
+    rng = np.random.Generator(np.random.PCG64(100 + tile + B))
+    _, Lv = O.level_tables(shapes)
+    Lq = Lv
+    value = torch.from_numpy(O.rng_normal(rng, (B, Lv, M, D))).bfloat16()
+    gout = torch.from_numpy(O.rng_normal(rng, (B, Lq, M * D), 3.0)).bfloat16()
+    bias = O.msda_reset_parameters(M * D, M, 3, P).reshape(1, 1, M, 3, P, 2)
+    off = torch.from_numpy(bias + O.rng_normal(rng, (B, Lq, M, 3, P, 2), spread)).to(loc_dtype)
+    attn = torch.from_numpy(rng.uniform(0, 1, size=(B, Lq, M, 3, P)).astype(np.float32)).to(loc_dtype)
+    ref_t = emrt_b200.get_reference_points(shapes, device=cuda_dev)
+    d = lambda t: t.to(cuda_dev)
+    vd, gd, od, ad = d(value), d(gout), d(off), d(attn)
+    base = L.LOC_PIXEL_OFFSET
+    want = ops.msda_gather_bwd(gd, vd, od, ad, shapes, ref=ref_t, mode=base)
+    b4 = bias.reshape(M, 3, P, 2)
+    mid = np.rint((b4.max(axis=2) + b4.min(axis=2)) * 0.5).astype(np.int32)
+    if R is not None:
+        os.environ["EMRT_BWD_WIN_R"] = R
+    try:
+        before = ops.launch_count()
+        got = ops.msda_gather_bwd(gd, vd, od, ad, shapes, ref=ref_t, mode=base | L.QUERY_PIXEL_GRID)
+        got_hint = ops.msda_gather_bwd(gd, vd, od, ad, shapes, ref=ref_t, mode=base | L.QUERY_PIXEL_GRID,
+                                       win_center=L.i32_array(mid.reshape(-1).tolist()))
+        # normalised locations through the same kernel
+        norm = np.array([[w, h] for h, w in shapes], np.float32).reshape(1, 1, 1, 3, 1, 2)
+        loc = (ref_t.cpu().numpy().reshape(1, Lq, 1, 3, 1, 2) + off.float().numpy() / norm).astype(np.float32)
+        locd = d(torch.from_numpy(loc))
+        ad32 = ad.float()
+        want_n = ops.msda_gather_bwd(gd, vd, locd, ad32, shapes, mode=L.LOC_NORMALIZED)
+        got_n = ops.msda_gather_bwd(gd, vd, locd, ad32, shapes, mode=L.LOC_NORMALIZED | L.QUERY_PIXEL_GRID)
+    finally:
+        os.environ.pop("EMRT_BWD_WIN_R", None)
+    torch.cuda.synchronize()
+    for name, g, w in [("plain", got, want), ("hint", got_hint, want), ("normalized", got_n, want_n)]:
+        # grad_value: fixed point with 2^-21 of the CTA's max |grad_out| per contribution; grad_loc / grad_attn: the same
+        # bf16 products summed in another order
+        assert rel_err(g[0], w[0].cpu()) < 2e-5, name
+        assert rel_err(g[1], w[1].cpu()) < 2e-5, name
+        assert rel_err(g[2], w[2].cpu()) < 2e-5, name
+    # and against autograd through the oracle on the same (bf16 / fp16-rounded) inputs
+    tv = value.double().requires_grad_()
+    tl = torch.from_numpy(loc).double().requires_grad_()
+    ta = attn.double().requires_grad_()
+    O.deformable_attention_core_func(tv, shapes, tl, ta).backward(gout.double().view(B, Lq, M * D))
+    # (a sample within ~1e-6 px of a pixel boundary lands in the neighbouring bilinear cell of the float64 oracle, where
+    # its own gradients differ by O(1): judge grad_loc / grad_attn by the fraction of such elements)
+    assert rel_err(got_n[0], tv.grad) < 2e-4
+    for g, w in [(got_n[2], ta.grad), (got_n[1], tl.grad)]:
+        bad = ((g.double().cpu() - w).abs() > 2e-3 * w.abs().max()).double().mean().item()
+        assert bad < 1e-4, bad
+
+
 def test_gather_window_staged_arbitrary_reference_points(cuda_dev):
     """The pixel-grid flag is only a locality promise: random reference points (almost every sample leaves its
     region's window) must still give the oracle's result."""
