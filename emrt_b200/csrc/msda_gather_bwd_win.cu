@@ -35,13 +35,14 @@
 namespace emrt {
 
 constexpr int BW_L = 3, BW_P = 6, BW_LP = BW_L * BW_P, BW_D = 32, BW_QPB = 4, BW_MAX_M = 16;
-constexpr int BW_WARPS = 7;                       // 42 batches of the default 8 x 16 region = 7 warps x 6, dealt statically
 constexpr float BW_MAGIC = 12582912.f;            // 1.5 * 2^23: (x + MAGIC) has x rounded to nearest in its low mantissa bits
 constexpr int BW_MAGIC_BITS = 0x4B400000;
 
 struct BwdWinParams {
   int32_t WW[BW_L], WH[BW_L];     // window size in pixels
   uint32_t win_off[BW_L];         // byte offset of the level's int32 window (levels 0 and 1 both start at 0: two passes)
+  uint32_t cnt_off[BW_L];         // byte offset of the level's per-pixel contribution counters (int32)
+  uint32_t pass_bytes[2];         // bytes to clear before each pass (windows + counters)
   uint32_t go_off;                // byte offset of the CTA's grad_out rows (bf16, 64 bytes per query)
   int32_t R, TH, TW, tw_shift, regions_x, regions_y;
   int32_t Lq, Lv, M;
@@ -101,7 +102,9 @@ __device__ __forceinline__ int bw_batch_query_base(const BwdWinParams& p, const 
   return (l2 ? qb[2] : (l1 ? qb[1] : qb[0])) + y * W + (x << 2);
 }
 
-template <typename TL, int MODE>
+// BW_WARPS warps per CTA, 2 CTAs per SM (8 warps: 128 registers, no spills; 10 warps: 96 registers); batches are claimed
+// dynamically from a shared counter, reset for each pass
+template <typename TL, int MODE, int BW_WARPS>
 __global__ void __launch_bounds__(BW_WARPS * 32, 2)
 msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __nv_bfloat16* __restrict__ value,
                            const TL* __restrict__ loc, const TL* __restrict__ attn, const float* __restrict__ ref,
@@ -109,6 +112,7 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
                            float* __restrict__ grad_attn, const __grid_constant__ BwdWinParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_max[BW_WARPS];
+  __shared__ int s_next;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x, region = blockIdx.y, b = blockIdx.z;
@@ -149,17 +153,17 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
 
   const int g = lane >> 3, s = lane & 7, side = s >> 2, sub = s & 3;
   const int rot = 2 * g + side;
-  const int64_t pix_stride = (int64_t)p.M * BW_D;
+  const int pix_stride = p.M * BW_D;      // elements between neighbouring pixels of one head (the host checks 32-bit offsets fit)
   const float sgn = side ? 1.f : -1.f;
 
   for (int pass = 0; pass < 2; ++pass) {
     // ---- zero this pass's windows ------------------------------------------------------------------------------------
-    const uint32_t pass_bytes = pass == 0 ? (uint32_t)(p.WW[0] * p.WH[0]) * (BW_D * 4)
-                                          : (uint32_t)(p.WW[1] * p.WH[1] + p.WW[2] * p.WH[2]) * (BW_D * 4);
+    const uint32_t pass_bytes = p.pass_bytes[pass];
     for (uint32_t o = threadIdx.x * 16; o < pass_bytes; o += BW_WARPS * 32 * 16) bw_sts128(smem_base + o, make_uint4(0, 0, 0, 0));
+    if (threadIdx.x == 0) s_next = BW_WARPS;
     __syncthreads();
 
-    for (int batch = warp; batch < n_batches; batch += BW_WARPS) {
+    for (int batch = warp; batch < n_batches;) {
       const int q = bw_batch_query_base(p, qb, n0, n01, sh0, batch) + g;
       const int64_t item = ((int64_t)b * p.Lq + q) * p.M + m;
       // this lane's eight grad_out channels: packed bf16 in natural order for the dot products, fp32 in the rotated
@@ -197,6 +201,7 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
         const int H = p.lv.H[l], W = p.lv.W[l], WWl = p.WW[l], WHl = p.WH[l];
         const float fW = (float)W, fH = (float)H;
         const uint32_t wbase = smem_base + p.win_off[l] + (uint32_t)sub * 32;
+        const uint32_t cbase = smem_base + p.cnt_off[l];
         const int64_t lvl_off = (((int64_t)b * p.Lv + p.lv.start[l]) * p.M + m) * BW_D + sub * 8;
         const __nv_bfloat16* vptr = value + lvl_off;
         float* gvptr = grad_value + lvl_off;
@@ -233,10 +238,10 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
             const bool vx = live && (unsigned)cx < (unsigned)W;
             vt_[i] = vx && (unsigned)yi_[i] < (unsigned)H;
             vb_[i] = vx && (unsigned)(yi_[i] + 1) < (unsigned)H;
-            const int64_t pix_t = (int64_t)(yi_[i] * W + cx) * pix_stride;
+            const int pix_t = (yi_[i] * W + cx) * pix_stride;
             tv_[i] = make_uint4(0, 0, 0, 0); bv_[i] = make_uint4(0, 0, 0, 0);
-            if (vt_[i]) tv_[i] = __ldg(reinterpret_cast<const uint4*>(vptr + pix_t));
-            if (vb_[i]) bv_[i] = __ldg(reinterpret_cast<const uint4*>(vptr + pix_t + W * pix_stride));
+            if (vt_[i]) tv_[i] = __ldg(reinterpret_cast<const uint4*>(vptr + (uint32_t)pix_t));
+            if (vb_[i]) bv_[i] = __ldg(reinterpret_cast<const uint4*>(vptr + (uint32_t)(pix_t + W * pix_stride)));
           }
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -261,16 +266,24 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
             const int wx = xi - ox[l], wy = yi - oy[l];
             const float wa = aw * wxs;
             if ((unsigned)wx < (unsigned)(WWl - 1) && (unsigned)wy < (unsigned)(WHl - 1)) {
-              const uint32_t a_t = wbase + (uint32_t)(wy * WWl + wx + side) * (BW_D * 4);
+              const uint32_t wpix = (uint32_t)(wy * WWl + wx + side);
+              const uint32_t a_t = wbase + wpix * (BW_D * 4);
               const uint32_t a_b = a_t + (uint32_t)WWl * (BW_D * 4);
               const float wst = wa * gy1 * scale, wsb = wa * fy * scale;
+              // the raw bits of (x + MAGIC) are MAGIC_BITS + round(x): the constant is taken out at the flush, from the
+              // pixel's contribution count (one red.shared per (query, side, row) instead of one subtraction per element)
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                bw_red_s32(a_t + koff[k], __float_as_int(fmaf(gr[k], wst, BW_MAGIC)) - BW_MAGIC_BITS);
-                bw_red_s32(a_b + koff[k], __float_as_int(fmaf(gr[k], wsb, BW_MAGIC)) - BW_MAGIC_BITS);
+                bw_red_s32(a_t + koff[k], __float_as_int(fmaf(gr[k], wst, BW_MAGIC)));
+                bw_red_s32(a_b + koff[k], __float_as_int(fmaf(gr[k], wsb, BW_MAGIC)));
+              }
+              if (sub == 0) {
+                const uint32_t c_t = cbase + wpix * 4;
+                bw_red_s32(c_t, 1);
+                bw_red_s32(c_t + (uint32_t)WWl * 4, 1);
               }
             } else {
-              const int64_t pix_t = (int64_t)(yi * W + xi + side) * pix_stride;
+              const int pix_t = (yi * W + xi + side) * pix_stride;
               if (vt_[i]) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) atomicAdd(gvptr + pix_t + (koff[k] >> 2), gr[k] * (wa * gy1));
@@ -283,6 +296,9 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
           }
         }
       }
+      int next = 0;
+      if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(next) : "r"(smem_u32(&s_next)) : "memory");
+      batch = __shfl_sync(0xffffffffu, next, 0);
     }
     __syncthreads();
 
@@ -297,10 +313,15 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
         const int wyp = pix / WWl, wxp = pix - wyp * WWl;
         const int X = ox[l] + wxp, Y = oy[l] + wyp;
         if ((unsigned)X < (unsigned)W && (unsigned)Y < (unsigned)H) {
-          const uint4 v = bw_lds128(smem_base + p.win_off[l] + (uint32_t)pix * (BW_D * 4) + c4 * 16);
-          if (v.x | v.y | v.z | v.w)
-            bw_red_add_v4(gbase + (int64_t)(Y * W + X) * pix_stride + c4 * 4, (float)(int)v.x * inv_scale,
-                          (float)(int)v.y * inv_scale, (float)(int)v.z * inv_scale, (float)(int)v.w * inv_scale);
+          uint32_t cnt;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cnt) : "r"(smem_base + p.cnt_off[l] + (uint32_t)pix * 4));
+          if (cnt) {
+            const uint4 v = bw_lds128(smem_base + p.win_off[l] + (uint32_t)pix * (BW_D * 4) + c4 * 16);
+            const uint32_t off = cnt * (uint32_t)BW_MAGIC_BITS;     // modulo 2^32, like the sums
+            bw_red_add_v4(gbase + (int64_t)(Y * W + X) * pix_stride + c4 * 4, (float)(int)(v.x - off) * inv_scale,
+                          (float)(int)(v.y - off) * inv_scale, (float)(int)(v.z - off) * inv_scale,
+                          (float)(int)(v.w - off) * inv_scale);
+          }
         }
       }
     }
@@ -313,11 +334,11 @@ static int bw_env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <typename TL, int MODE>
+template <typename TL, int MODE, int BW_WARPS>
 static int launch_bwd_win(const void* go, const void* value, const void* loc, const void* attn, const float* ref,
                           int64_t ref_bs, float* gv, float* gl, float* ga, int B, const BwdWinParams& p,
                           size_t smem_bytes, cudaStream_t st) {
-  auto kern = msda_gather_bwd_win_kernel<TL, MODE>;
+  auto kern = msda_gather_bwd_win_kernel<TL, MODE, BW_WARPS>;
   static size_t attr = 0;
   if (smem_bytes > attr) {
     EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -362,10 +383,17 @@ int gather_bwd_win(const void* go, const void* value, const void* loc, const voi
     p.WH[l] = std::min((p.TH >> l) + 2 * p.R + 1, lv.H[l] + 2);
     bytes[l] = (uint32_t)(p.WW[l] * p.WH[l]) * (BW_D * 4);
   }
+  // pass 0: [window 0][counters 0]; pass 1: [window 1][window 2][counters 1][counters 2]; both start at 0
   p.win_off[0] = 0;
+  p.cnt_off[0] = bytes[0];
+  p.pass_bytes[0] = (bytes[0] + bytes[0] / BW_D + 15u) & ~15u;
   p.win_off[1] = 0;
   p.win_off[2] = bytes[1];
-  p.go_off = (std::max(bytes[0], bytes[1] + bytes[2]) + 127u) & ~127u;
+  p.cnt_off[1] = bytes[1] + bytes[2];
+  p.cnt_off[2] = p.cnt_off[1] + bytes[1] / BW_D;
+  p.pass_bytes[1] = (p.cnt_off[2] + bytes[2] / BW_D + 15u) & ~15u;
+  p.go_off = (std::max(p.pass_bytes[0], p.pass_bytes[1]) + 127u) & ~127u;
+  if ((int64_t)Lv * M * D >= (1LL << 30)) return EMRT_ERR_UNSUPPORTED;   // 32-bit element offsets inside one level plane
   const int n_queries = p.TH * p.TW + ((p.TH * p.TW) >> 2) + ((p.TH * p.TW) >> 4);
   const size_t smem_bytes = (size_t)p.go_off + (size_t)n_queries * (BW_D * 2);
   if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
@@ -373,9 +401,13 @@ int gather_bwd_win(const void* go, const void* value, const void* loc, const voi
       (reinterpret_cast<uintptr_t>(gv) & 15) != 0)
     return EMRT_ERR_UNSUPPORTED;
   const bool px = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;
+  const int warps = bw_env_int("EMRT_BWD_WIN_WARPS", 8) == 10 ? 10 : 8;
 #define EMRT_BWIN(TL)                                                                                              \
-  return px ? launch_bwd_win<TL, 1>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)            \
-            : launch_bwd_win<TL, 0>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)
+  if (warps == 10)                                                                                                 \
+    return px ? launch_bwd_win<TL, 1, 10>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)      \
+              : launch_bwd_win<TL, 0, 10>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st);     \
+  return px ? launch_bwd_win<TL, 1, 8>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)         \
+            : launch_bwd_win<TL, 0, 8>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)
   switch (loc_dtype) {
     case EMRT_F32: EMRT_BWIN(float);
     case EMRT_F16: EMRT_BWIN(__half);
