@@ -58,8 +58,12 @@ __device__ __forceinline__ uint4 bw_lds128(uint32_t addr) {
 __device__ __forceinline__ void bw_sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// PLAIN = true replaces the reduction by a plain store: WRONG results, used only by the timing experiment that
+// measures how much of the kernel is the shared-memory atomic unit (EMRT_BWD_WIN_TIMING_PLAIN_STORES=1, never in tests)
+template <bool PLAIN>
 __device__ __forceinline__ void bw_red_s32(uint32_t addr, int v) {
-  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  if (PLAIN) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  else asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void bw_red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -104,7 +108,7 @@ __device__ __forceinline__ int bw_batch_query_base(const BwdWinParams& p, const 
 
 // BW_WARPS warps per CTA, 2 CTAs per SM (8 warps: 128 registers, no spills; 10 warps: 96 registers); batches are claimed
 // dynamically from a shared counter, reset for each pass
-template <typename TL, int MODE, int BW_WARPS>
+template <typename TL, int MODE, int BW_WARPS, bool PLAIN>
 __global__ void __launch_bounds__(BW_WARPS * 32, 2)
 msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __nv_bfloat16* __restrict__ value,
                            const TL* __restrict__ loc, const TL* __restrict__ attn, const float* __restrict__ ref,
@@ -274,13 +278,13 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
               // pixel's contribution count (one red.shared per (query, side, row) instead of one subtraction per element)
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                bw_red_s32(a_t + koff[k], __float_as_int(fmaf(gr[k], wst, BW_MAGIC)));
-                bw_red_s32(a_b + koff[k], __float_as_int(fmaf(gr[k], wsb, BW_MAGIC)));
+                bw_red_s32<PLAIN>(a_t + koff[k], __float_as_int(fmaf(gr[k], wst, BW_MAGIC)));
+                bw_red_s32<PLAIN>(a_b + koff[k], __float_as_int(fmaf(gr[k], wsb, BW_MAGIC)));
               }
               if (sub == 0) {
                 const uint32_t c_t = cbase + wpix * 4;
-                bw_red_s32(c_t, 1);
-                bw_red_s32(c_t + (uint32_t)WWl * 4, 1);
+                bw_red_s32<PLAIN>(c_t, 1);
+                bw_red_s32<PLAIN>(c_t + (uint32_t)WWl * 4, 1);
               }
             } else {
               const int pix_t = (yi * W + xi + side) * pix_stride;
@@ -334,11 +338,11 @@ static int bw_env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <typename TL, int MODE, int BW_WARPS>
+template <typename TL, int MODE, int BW_WARPS, bool PLAIN = false>
 static int launch_bwd_win(const void* go, const void* value, const void* loc, const void* attn, const float* ref,
                           int64_t ref_bs, float* gv, float* gl, float* ga, int B, const BwdWinParams& p,
                           size_t smem_bytes, cudaStream_t st) {
-  auto kern = msda_gather_bwd_win_kernel<TL, MODE, BW_WARPS>;
+  auto kern = msda_gather_bwd_win_kernel<TL, MODE, BW_WARPS, PLAIN>;
   static size_t attr = 0;
   if (smem_bytes > attr) {
     EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -402,6 +406,8 @@ int gather_bwd_win(const void* go, const void* value, const void* loc, const voi
     return EMRT_ERR_UNSUPPORTED;
   const bool px = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;
   const int warps = bw_env_int("EMRT_BWD_WIN_WARPS", 8) == 10 ? 10 : 8;
+  if (loc_dtype == EMRT_F16 && px && getenv("EMRT_BWD_WIN_TIMING_PLAIN_STORES"))
+    return launch_bwd_win<__half, 1, 8, true>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st);
 #define EMRT_BWIN(TL)                                                                                              \
   if (warps == 10)                                                                                                 \
     return px ? launch_bwd_win<TL, 1, 10>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)      \

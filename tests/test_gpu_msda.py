@@ -472,9 +472,11 @@ def test_msda_module_backward_fp32(cuda_dev, case):
             assert got is not None and rel_err(got, g) < 5e-4, name
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("impl", ["simt", "tcgen05", "tcgen05-windowed"])
 def test_msda_module_backward_bf16(cuda_dev, impl):
-    """Training path, bf16 activations: gradients vs the float64 oracle on the bf16-rounded inputs / weights."""
+    """Training path, bf16 activations: gradients vs the float64 oracle on the bf16-rounded inputs / weights.
+    "tcgen05-windowed": reference points from get_reference_points (tagged pixel grid), so the backward gather is the
+    windowed kernel (integer shared-memory accumulation) with the module's window-centre hint."""
     shapes = [(32, 32), (16, 16), (8, 8)]
     B, C, M, P = 2, 256, 8, 6
     rng = np.random.Generator(np.random.PCG64(12))
@@ -491,8 +493,29 @@ def test_msda_module_backward_bf16(cuda_dev, impl):
     m.gemm_impl = L.IMPL_SIMT if impl == "simt" else L.IMPL_TCGEN05
     d = lambda a: torch.from_numpy(a).to(cuda_dev)
     tq, tv = d(q).bfloat16().requires_grad_(True), d(v).bfloat16().requires_grad_(True)
-    out = m(tq, d(ref), tv, shapes, d(mask))
-    out.backward(d(d_out).bfloat16())
+    if impl.endswith("windowed"):
+        ref_t = emrt_b200.get_reference_points(shapes, device=cuda_dev)
+        assert getattr(ref_t, "pixel_grid", False) and torch.equal(ref_t.cpu()[0], torch.from_numpy(ref)[0])
+        m.packed_weights()                              # keep the one-off weight packing out of the launch counts
+        before = ops.launch_count()
+        out = m(tq, ref_t, tv, shapes, d(mask))
+        out.backward(d(d_out).bfloat16())
+        n_win = ops.launch_count() - before
+        os.environ["EMRT_GATHER_NO_WIN"] = "1"          # same call through the generic backward: same launch count
+        try:
+            tq2, tv2 = d(q).bfloat16().requires_grad_(True), d(v).bfloat16().requires_grad_(True)
+            m2 = _load_module(params, C, M, 3, P, cuda_dev, train=True)     # parameter .grad accumulates: a fresh copy
+            m2.gemm_impl = m.gemm_impl
+            m2.packed_weights()
+            before = ops.launch_count()
+            m2(tq2, ref_t, tv2, shapes, d(mask)).backward(d(d_out).bfloat16())
+            assert ops.launch_count() - before == n_win
+        finally:
+            del os.environ["EMRT_GATHER_NO_WIN"]
+        assert rel_err(tv.grad.float(), tv2.grad.float().cpu()) < 1e-2      # bf16 gradient tensors, different summation
+    else:
+        out = m(tq, d(ref), tv, shapes, d(mask))
+        out.backward(d(d_out).bfloat16())
     # bf16 activations, fp16 offsets / weights and bf16 gradient tensors between the kernels.  The gradient w.r.t. a
     # sampling position is DISCONTINUOUS at pixel boundaries, and fp16-rounded offsets put ~1 % of the samples in the
     # neighbouring bilinear cell of the float64 oracle, so everything downstream of grad_loc (query, sampling_offsets)
