@@ -333,6 +333,309 @@ msda_gather_bwd_win_kernel(const __nv_bfloat16* __restrict__ grad_out, const __n
   }
 }
 
+// =====================================================================================================================
+// v2: the forward window kernel's structure applied to the backward.  One CTA per SM (16 warps) owns (head, region, batch):
+//   * the region's three value windows are staged once by TMA — a 5-D tensor map {32 ch, M, W, H, B} cuts one head's
+//     window out of the pixel-major value tensor the training path keeps; out-of-map pixels are zero-filled, which is
+//     grid_sample's zeros padding, so the dot products need no validity logic;
+//   * stage A: one lane per (query, point) computes the footprint once into a 16-byte record {window pixel | slow / dead
+//     code, fx, fy, attention weight}; stage B: the query's 8 lanes read the record (one broadcast LDS.128), their
+//     16-byte slices of the top / bottom pixel from the value window, form the dot products for grad_loc / grad_attn and
+//     scatter w * grad_out into the fixed-point window exactly as v1 does.
+// Shared memory: fixed-point window + counters of one pass (96 KB, passes: level 0; levels 1 + 2), the three bf16 value
+// windows (91 KB), the CTA's grad_out rows (10.5 KB), records (1.1 KB per warp): 216 KB.
+constexpr uint32_t BW2_SLOW = 0x80000000u, BW2_DEAD = 0xffffffffu;
+
+struct Bwd2Params {
+  CUtensorMap tmap[BW_L];         // level l: {32, M, W_l, H_l, B} bf16 over the pixel-major value tensor, box {32,1,WW,WH,1}
+  int32_t WW[BW_L], WH[BW_L];
+  uint32_t val_off[BW_L];         // bf16 value windows
+  uint32_t win_off[BW_L], cnt_off[BW_L], pass_bytes[2];
+  uint32_t go_off, rec_off;
+  int32_t R, TH, TW, tw_shift, regions_x, regions_y;
+  int32_t Lq, Lv, M;
+  LevelTable lv;
+  int8_t cshift[BW_MAX_M][BW_L][2];
+};
+
+__device__ __forceinline__ void bw_tma_load_5d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+template <typename TL, int MODE, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+msda_gather_bwd_win2_kernel(const __nv_bfloat16* __restrict__ grad_out, const __nv_bfloat16* __restrict__ value,
+                            const TL* __restrict__ loc, const TL* __restrict__ attn, const float* __restrict__ ref,
+                            int64_t ref_bs, float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                            float* __restrict__ grad_attn, const __grid_constant__ Bwd2Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t s_bar;
+  __shared__ float s_max[NW];
+  __shared__ int s_next;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x, region = blockIdx.y, b = blockIdx.z;
+  const int ry = region / p.regions_x, rx = region - ry * p.regions_x;
+  const uint32_t smem_base = smem_u32(smem);
+
+  int ox[BW_L], oy[BW_L], qb[BW_L];
+#pragma unroll
+  for (int l = 0; l < BW_L; ++l) {
+    const int x0 = (rx * p.TW) >> l, y0 = (ry * p.TH) >> l;
+    const int cx = m < BW_MAX_M ? p.cshift[m][l][0] : 0, cy = m < BW_MAX_M ? p.cshift[m][l][1] : 0;
+    ox[l] = min(max(x0 - p.R + cx, -1), p.lv.W[l] + 1 - p.WW[l]);
+    oy[l] = min(max(y0 - p.R + cy, -1), p.lv.H[l] + 1 - p.WH[l]);
+    qb[l] = p.lv.start[l] + y0 * p.lv.W[l] + x0;
+  }
+  const int n0 = (p.TH * p.TW) >> 2, n01 = n0 + (n0 >> 2), n_batches = n01 + (n0 >> 4), sh0 = p.tw_shift - 2;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t bytes = 0;
+#pragma unroll
+    for (int l = 0; l < BW_L; ++l) bytes += (uint32_t)(p.WW[l] * p.WH[l]) * (BW_D * 2);
+    mbar_arrive_expect_tx(&s_bar, bytes);
+#pragma unroll
+    for (int l = 0; l < BW_L; ++l) bw_tma_load_5d(smem_base + p.val_off[l], &p.tmap[l], &s_bar, 0, m, ox[l], oy[l], b);
+  }
+
+  // ---- the CTA's grad_out rows (head m of its queries) into shared memory, and their largest magnitude ---------------
+  float mx = 0.f;
+  for (int idx = threadIdx.x; idx < n_batches * (BW_QPB * 4); idx += NW * 32) {
+    const int k = idx >> 2, part = idx & 3;
+    const bool l1 = (k >> 2) >= n0, l2 = (k >> 2) >= n01;
+    const int kk = (k >> 2) - (l2 ? n01 : (l1 ? n0 : 0));
+    const int sh = sh0 - (l2 ? 2 : (l1 ? 1 : 0));
+    const int yy = kk >> sh, xx = kk - (yy << sh);
+    const int Wl = l2 ? p.lv.W[2] : (l1 ? p.lv.W[1] : p.lv.W[0]);
+    const int q = (l2 ? qb[2] : (l1 ? qb[1] : qb[0])) + yy * Wl + (xx << 2) + (k & 3);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(grad_out + (((int64_t)b * p.Lq + q) * p.M + m) * BW_D + part * 8));
+    bw_sts128(smem_base + p.go_off + (uint32_t)idx * 16, v);
+    mx = bw_absmax8(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_max[warp] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < NW; ++w) mx = fmaxf(mx, s_max[w]);
+  const uint32_t ebits = (__float_as_uint(mx) >> 23) & 0xffu;
+  const bool scaled = ebits >= 20u && ebits < 255u;
+  const float scale = scaled ? __uint_as_float((273u - ebits) << 23) : 1.f;
+  const float inv_scale = scaled ? __uint_as_float((ebits - 19u) << 23) : 1.f;
+
+  const int g = lane >> 3, s = lane & 7, side = s >> 2, sub = s & 3;
+  const int rot = 2 * g + side;
+  const int pix_stride = p.M * BW_D;
+  const float sgn = side ? 1.f : -1.f;
+  const uint32_t rec_base = smem_base + p.rec_off + (uint32_t)warp * (BW_QPB * BW_LP * 16);
+  // stage-A identity: lane -> (query a_qi = lane % 4, point a_pp = lane / 4), lanes 24-31 idle
+  const bool a_on = lane < BW_QPB * BW_P;
+  const int a_qi = a_on ? (lane & 3) : 0, a_pp = a_on ? (lane >> 2) : 0;
+  uint32_t koff[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) koff[k] = (uint32_t)((k + rot) & 7) * 4;
+  bool windows_ready = false;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const uint32_t pass_bytes = p.pass_bytes[pass];
+    for (uint32_t o = threadIdx.x * 16; o < pass_bytes; o += NW * 32 * 16) bw_sts128(smem_base + o, make_uint4(0, 0, 0, 0));
+    if (threadIdx.x == 0) s_next = NW;
+    __syncthreads();
+    if (!windows_ready) {
+      mbar_wait(&s_bar, 0);
+      windows_ready = true;
+    }
+
+    for (int batch = warp; batch < n_batches;) {
+      const bool l1 = batch >= n0, l2 = batch >= n01;
+      const int kk = batch - (l2 ? n01 : (l1 ? n0 : 0));
+      const int sh = sh0 - (l2 ? 2 : (l1 ? 1 : 0));
+      const int yy = kk >> sh, xx = kk - (yy << sh);
+      const int Wq = l2 ? p.lv.W[2] : (l1 ? p.lv.W[1] : p.lv.W[0]);
+      const int q_base = (l2 ? qb[2] : (l1 ? qb[1] : qb[0])) + yy * Wq + (xx << 2);
+
+      // ---- stage A: footprint records of this pass's levels, one per lane ---------------------------------------------
+      if (a_on) {
+        const int64_t item = ((int64_t)b * p.Lq + (q_base + a_qi)) * p.M + m;
+        const TL* lp = loc + item * (BW_LP * 2) + a_pp * 2;
+        const TL* ap = attn + item * BW_LP + a_pp;
+        const float* rp = (MODE == EMRT_LOC_PIXEL_OFFSET) ? ref + b * ref_bs + (int64_t)(q_base + a_qi) * (BW_L * 2) : nullptr;
+#pragma unroll
+        for (int l = 0; l < BW_L; ++l) {
+          if ((l == 0) != (pass == 0)) continue;
+          const float2 xy = Pair<TL>::load(lp + l * (BW_P * 2));
+          const float aw = load1<TL>(ap + l * BW_P);
+          const float fW = (float)p.lv.W[l], fH = (float)p.lv.H[l];
+          float x, y;
+          if (MODE == EMRT_LOC_PIXEL_OFFSET) {
+            const float2 r = __ldg(reinterpret_cast<const float2*>(rp + 2 * l));
+            x = r.x * fW - 0.5f + xy.x;
+            y = r.y * fH - 0.5f + xy.y;
+          } else {
+            x = xy.x * fW - 0.5f;
+            y = xy.y * fH - 0.5f;
+          }
+          // live iff -1 < x < W and -1 < y < H (make_footprint's rule; rejects NaN)
+          const bool live = (x > -1.f) && (y > -1.f) && (x < fW) && (y < fH);
+          const float xs = fmaxf(x, -2.f), ys = fmaxf(y, -2.f);
+          const int xi = live ? __float2int_rd(xs) : 0, yi = live ? __float2int_rd(ys) : 0;
+          const float fx = live ? xs - (float)xi : 0.f, fy = live ? ys - (float)yi : 0.f;
+          const int wx = xi - ox[l], wy = yi - oy[l];
+          const bool inwin = live && (unsigned)wx < (unsigned)(p.WW[l] - 1) && (unsigned)wy < (unsigned)(p.WH[l] - 1);
+          const uint32_t w0 = inwin ? (uint32_t)(wy * p.WW[l] + wx)
+                                    : (live ? (BW2_SLOW | ((uint32_t)(yi + 2) << 16) | (uint32_t)(xi + 2)) : BW2_DEAD);
+          const uint32_t dst = rec_base + (uint32_t)(a_qi * BW_LP + l * BW_P + a_pp) * 16;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(w0), "r"(__float_as_uint(fx)),
+                       "r"(__float_as_uint(fy)), "r"(__float_as_uint(live ? aw : 0.f)) : "memory");
+        }
+      }
+      __syncwarp();
+
+      // ---- stage B ---------------------------------------------------------------------------------------------------
+      const int q = q_base + g;
+      const int64_t item = ((int64_t)b * p.Lq + q) * p.M + m;
+      const uint32_t grow = smem_base + p.go_off + (uint32_t)(batch * BW_QPB + g) * (BW_D * 2);
+      const uint4 gnat = bw_lds128(grow + sub * 16);
+      float gr[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        unsigned short h;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(grow + (uint32_t)sub * 16 + (koff[k] >> 1)));
+        gr[k] = __uint_as_float((uint32_t)h << 16);
+      }
+      float* gl = grad_loc + item * (BW_LP * 2);
+      float* ga_out = grad_attn + item * BW_LP;
+      const uint32_t my_rec = rec_base + (uint32_t)(g * BW_LP) * 16;
+
+#pragma unroll
+      for (int l = 0; l < BW_L; ++l) {
+        if ((l == 0) != (pass == 0)) continue;
+        const int W = p.lv.W[l], H = p.lv.H[l], WWl = p.WW[l];
+        const uint32_t vbase = smem_base + p.val_off[l] + (uint32_t)side * (BW_D * 2) + (uint32_t)sub * 16;
+        const uint32_t wbase = smem_base + p.win_off[l] + (uint32_t)side * (BW_D * 4) + (uint32_t)sub * 32;
+        const uint32_t cbase = smem_base + p.cnt_off[l] + (uint32_t)side * 4;
+        const int64_t lvl_off = (((int64_t)b * p.Lv + p.lv.start[l]) * p.M + m) * BW_D + sub * 8;
+        const float sx = (MODE == EMRT_LOC_PIXEL_OFFSET) ? 1.f : (float)W;
+        const float sy = (MODE == EMRT_LOC_PIXEL_OFFSET) ? 1.f : (float)H;
+#pragma unroll
+        for (int h = 0; h < BW_P; h += 3) {
+          uint4 rec[3], tv[3], bv[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) rec[i] = bw_lds128(my_rec + (uint32_t)(l * BW_P + h + i) * 16);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            tv[i] = make_uint4(0, 0, 0, 0); bv[i] = make_uint4(0, 0, 0, 0);
+            if (rec[i].x < BW2_SLOW) {
+              const uint32_t a = vbase + rec[i].x * (BW_D * 2);
+              tv[i] = bw_lds128(a);
+              bv[i] = bw_lds128(a + (uint32_t)WWl * (BW_D * 2));
+            } else if (rec[i].x != BW2_DEAD) {
+              // left the window but not the map: this lane's corners from global memory, with their validity
+              const int xi = (int)(rec[i].x & 0xffffu) - 2, yi = (int)((rec[i].x >> 16) & 0x7fffu) - 2;
+              const int cx = xi + side;
+              const bool vx = (unsigned)cx < (unsigned)W;
+              const __nv_bfloat16* vptr = value + lvl_off;
+              const int pix_t = (yi * W + cx) * pix_stride;
+              if (vx && (unsigned)yi < (unsigned)H) tv[i] = __ldg(reinterpret_cast<const uint4*>(vptr + pix_t));
+              if (vx && (unsigned)(yi + 1) < (unsigned)H) bv[i] = __ldg(reinterpret_cast<const uint4*>(vptr + pix_t + W * pix_stride));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int pt = h + i;
+            const float fx = __uint_as_float(rec[i].y), fy = __uint_as_float(rec[i].z), aw = __uint_as_float(rec[i].w);
+            const float d_t = bw_dot8(gnat, tv[i]), d_b = bw_dot8(gnat, bv[i]);
+            const float gy1 = 1.f - fy, wxs = side ? fx : 1.f - fx;
+            const float along = gy1 * d_t + fy * d_b;
+            float ga = wxs * along, gxp = sgn * along, gyp = wxs * (d_b - d_t);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              ga += __shfl_xor_sync(0xffffffffu, ga, o);
+              gxp += __shfl_xor_sync(0xffffffffu, gxp, o);
+              gyp += __shfl_xor_sync(0xffffffffu, gyp, o);
+            }
+            if (s == 0) {
+              ga_out[l * BW_P + pt] = ga;
+              *reinterpret_cast<float2*>(gl + (l * BW_P + pt) * 2) = make_float2(aw * sx * gxp, aw * sy * gyp);
+            }
+            const float wa = aw * wxs;
+            if (rec[i].x < BW2_SLOW) {
+              const uint32_t a_t = wbase + rec[i].x * (BW_D * 4);
+              const uint32_t a_b = a_t + (uint32_t)WWl * (BW_D * 4);
+              const float wst = wa * gy1 * scale, wsb = wa * fy * scale;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                bw_red_s32<false>(a_t + koff[k], __float_as_int(fmaf(gr[k], wst, BW_MAGIC)));
+                bw_red_s32<false>(a_b + koff[k], __float_as_int(fmaf(gr[k], wsb, BW_MAGIC)));
+              }
+              if (sub == 0) {
+                const uint32_t c_t = cbase + rec[i].x * 4;
+                bw_red_s32<false>(c_t, 1);
+                bw_red_s32<false>(c_t + (uint32_t)WWl * 4, 1);
+              }
+            } else if (rec[i].x != BW2_DEAD) {
+              const int xi = (int)(rec[i].x & 0xffffu) - 2, yi = (int)((rec[i].x >> 16) & 0x7fffu) - 2;
+              const int cx = xi + side;
+              const bool vx = (unsigned)cx < (unsigned)W;
+              float* gvptr = grad_value + lvl_off;
+              const int pix_t = (yi * W + cx) * pix_stride;
+              if (vx && (unsigned)yi < (unsigned)H) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(gvptr + pix_t + (koff[k] >> 2), gr[k] * (wa * gy1));
+              }
+              if (vx && (unsigned)(yi + 1) < (unsigned)H) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(gvptr + pix_t + W * pix_stride + (koff[k] >> 2), gr[k] * (wa * fy));
+              }
+            }
+          }
+        }
+      }
+      int next = 0;
+      if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(next) : "r"(smem_u32(&s_next)) : "memory");
+      batch = __shfl_sync(0xffffffffu, next, 0);     // also orders this batch's record reads before the next batch's writes
+    }
+    __syncthreads();
+
+    // ---- flush ---------------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int l = 0; l < BW_L; ++l) {
+      if ((l == 0) != (pass == 0)) continue;
+      const int WWl = p.WW[l], npx = WWl * p.WH[l], W = p.lv.W[l], H = p.lv.H[l];
+      float* gbase = grad_value + (((int64_t)b * p.Lv + p.lv.start[l]) * p.M + m) * BW_D;
+      for (int idx = threadIdx.x; idx < npx * 8; idx += NW * 32) {
+        const int pix = idx >> 3, c4 = idx & 7;
+        const int wyp = pix / WWl, wxp = pix - wyp * WWl;
+        const int X = ox[l] + wxp, Y = oy[l] + wyp;
+        if ((unsigned)X < (unsigned)W && (unsigned)Y < (unsigned)H) {
+          uint32_t cnt;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cnt) : "r"(smem_base + p.cnt_off[l] + (uint32_t)pix * 4));
+          if (cnt) {
+            const uint4 v = bw_lds128(smem_base + p.win_off[l] + (uint32_t)pix * (BW_D * 4) + c4 * 16);
+            const uint32_t off = cnt * (uint32_t)BW_MAGIC_BITS;
+            bw_red_add_v4(gbase + (int64_t)(Y * W + X) * pix_stride + c4 * 4, (float)(int)(v.x - off) * inv_scale,
+                          (float)(int)(v.y - off) * inv_scale, (float)(int)(v.z - off) * inv_scale,
+                          (float)(int)(v.w - off) * inv_scale);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
 static int bw_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -356,6 +659,98 @@ static int launch_bwd_win(const void* go, const void* value, const void* loc, co
   return EMRT_OK;
 }
 
+template <typename TL, int MODE, int NW>
+static int launch_bwd_win2(const void* go, const void* value, const void* loc, const void* attn, const float* ref,
+                           int64_t ref_bs, float* gv, float* gl, float* ga, int B, const Bwd2Params& p, size_t smem_bytes,
+                           cudaStream_t st) {
+  auto kern = msda_gather_bwd_win2_kernel<TL, MODE, NW>;
+  static size_t attr = 0;
+  if (smem_bytes > attr) {
+    EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    attr = smem_bytes;
+  }
+  const int n_regions = p.regions_x * p.regions_y;
+  if (B > 65535 || n_regions > 65535) return EMRT_ERR_UNSUPPORTED;
+  kern<<<dim3((unsigned)p.M, (unsigned)n_regions, (unsigned)B), NW * 32, smem_bytes, st>>>(
+      (const __nv_bfloat16*)go, (const __nv_bfloat16*)value, (const TL*)loc, (const TL*)attn, ref, ref_bs, gv, gl, ga, p);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+// v2 launcher: EMRT_ERR_UNSUPPORTED when the windows do not fit one CTA's shared memory (the caller then tries v1).
+static int gather_bwd_win2(const void* go, const void* value, const void* loc, const void* attn, const float* ref,
+                           int64_t ref_bs, float* gv, float* gl, float* ga, int B, int Lq, int Lv, int M,
+                           const LevelTable& lv, int loc_dtype, int mode, const int32_t* win_center_host, cudaStream_t st) {
+  constexpr int L = BW_L;
+  Bwd2Params p;
+  memset(&p, 0, sizeof(p));
+  p.R = bw_env_int("EMRT_BWD_WIN_R", 7);
+  p.TH = bw_env_int("EMRT_BWD_WIN_TH", 8);
+  p.TW = bw_env_int("EMRT_BWD_WIN_TW", 16);
+  if (p.R < 1 || p.TH < 4 || p.TW < 16 || (p.TH & 3) || (p.TW & (p.TW - 1)) || lv.H[0] % p.TH || lv.W[0] % p.TW) return EMRT_ERR_UNSUPPORTED;
+  for (p.tw_shift = 0; (1 << p.tw_shift) < p.TW; ++p.tw_shift) {}
+  if ((int64_t)Lv * M * BW_D >= (1LL << 30) || lv.W[0] > 32000 || lv.H[0] > 32000) return EMRT_ERR_UNSUPPORTED;
+  p.regions_x = lv.W[0] / p.TW;
+  p.regions_y = lv.H[0] / p.TH;
+  p.Lq = Lq; p.Lv = Lv; p.M = M; p.lv = lv;
+  if (win_center_host && M <= BW_MAX_M && !getenv("EMRT_WIN_NO_HINT"))
+    for (int mm = 0; mm < M; ++mm)
+      for (int l = 0; l < L; ++l)
+        for (int k = 0; k < 2; ++k)
+          p.cshift[mm][l][k] = (int8_t)std::min(std::max(win_center_host[(mm * L + l) * 2 + k], -100), 100);
+  uint32_t px[BW_L];
+  for (int l = 0; l < L; ++l) {
+    p.WW[l] = std::min((p.TW >> l) + 2 * p.R + 1, lv.W[l] + 2);
+    p.WH[l] = std::min((p.TH >> l) + 2 * p.R + 1, lv.H[l] + 2);
+    if (p.WW[l] > 256 || p.WH[l] > 256) return EMRT_ERR_UNSUPPORTED;
+    px[l] = (uint32_t)(p.WW[l] * p.WH[l]);
+  }
+  // region A (re-used by the two passes): pass 0 [window 0][counters 0]; pass 1 [window 1][window 2][counters 1][counters 2]
+  p.win_off[0] = 0;
+  p.cnt_off[0] = px[0] * (BW_D * 4);
+  p.pass_bytes[0] = (p.cnt_off[0] + px[0] * 4 + 15u) & ~15u;
+  p.win_off[1] = 0;
+  p.win_off[2] = px[1] * (BW_D * 4);
+  p.cnt_off[1] = (px[1] + px[2]) * (BW_D * 4);
+  p.cnt_off[2] = p.cnt_off[1] + px[1] * 4;
+  p.pass_bytes[1] = (p.cnt_off[2] + px[2] * 4 + 15u) & ~15u;
+  uint32_t off = (std::max(p.pass_bytes[0], p.pass_bytes[1]) + 127u) & ~127u;
+  for (int l = 0; l < L; ++l) {
+    p.val_off[l] = off;
+    off += (px[l] * (BW_D * 2) + 127u) & ~127u;
+    // one head's plane of level l inside the pixel-major [B, Lv, M, 32] tensor
+    const uint64_t dims[5] = {(uint64_t)BW_D, (uint64_t)M, (uint64_t)lv.W[l], (uint64_t)lv.H[l], (uint64_t)B};
+    const uint64_t strides[4] = {(uint64_t)BW_D * 2, (uint64_t)M * BW_D * 2, (uint64_t)lv.W[l] * M * BW_D * 2,
+                                 (uint64_t)Lv * M * BW_D * 2};
+    const uint32_t box[5] = {(uint32_t)BW_D, 1u, (uint32_t)p.WW[l], (uint32_t)p.WH[l], 1u};
+    const __nv_bfloat16* base = (const __nv_bfloat16*)value + (int64_t)lv.start[l] * M * BW_D;
+    if (int e = make_tensor_map(&p.tmap[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box,
+                                CU_TENSOR_MAP_SWIZZLE_NONE))
+      return e;
+  }
+  p.go_off = off;
+  const int n_queries = p.TH * p.TW + ((p.TH * p.TW) >> 2) + ((p.TH * p.TW) >> 4);
+  off += (uint32_t)n_queries * (BW_D * 2);
+  p.rec_off = (off + 15u) & ~15u;
+  const int warps = bw_env_int("EMRT_BWD_WIN_WARPS", 16) == 12 ? 12 : 16;
+  const size_t smem_bytes = (size_t)p.rec_off + (size_t)warps * BW_QPB * BW_LP * 16;
+  if (smem_bytes > 227 * 1024) return EMRT_ERR_UNSUPPORTED;
+  const bool pxm = (mode & EMRT_LOC_PIXEL_OFFSET) != 0;
+#define EMRT_BWIN2(TL)                                                                                             \
+  if (warps == 12)                                                                                                 \
+    return pxm ? launch_bwd_win2<TL, 1, 12>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)    \
+               : launch_bwd_win2<TL, 0, 12>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st);   \
+  return pxm ? launch_bwd_win2<TL, 1, 16>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)      \
+             : launch_bwd_win2<TL, 0, 16>(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, p, smem_bytes, st)
+  switch (loc_dtype) {
+    case EMRT_F32: EMRT_BWIN2(float);
+    case EMRT_F16: EMRT_BWIN2(__half);
+    case EMRT_BF16: EMRT_BWIN2(__nv_bfloat16);
+    default: return EMRT_ERR_UNSUPPORTED;
+  }
+#undef EMRT_BWIN2
+}
+
 // Returns EMRT_ERR_UNSUPPORTED (error text untouched) when the shape is not the regular 3-level pyramid this kernel
 // tiles; the caller then runs the generic backward.
 int gather_bwd_win(const void* go, const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs,
@@ -365,6 +760,14 @@ int gather_bwd_win(const void* go, const void* value, const void* loc, const voi
   for (int l = 1; l < L; ++l)
     if (lv.H[l] != (lv.H[0] >> l) || lv.W[l] != (lv.W[0] >> l) || (lv.H[l] << l) != lv.H[0] || (lv.W[l] << l) != lv.W[0])
       return EMRT_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(value) & 15) != 0 || (reinterpret_cast<uintptr_t>(go) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(gv) & 15) != 0)
+    return EMRT_ERR_UNSUPPORTED;
+  if (!getenv("EMRT_BWD_WIN_V1")) {
+    const int e = gather_bwd_win2(go, value, loc, attn, ref, ref_bs, gv, gl, ga, B, Lq, Lv, M, lv, loc_dtype, mode,
+                                  win_center_host, st);
+    if (e != EMRT_ERR_UNSUPPORTED) return e;
+  }
   BwdWinParams p;
   memset(&p, 0, sizeof(p));
   p.R = bw_env_int("EMRT_BWD_WIN_R", 7);

@@ -351,9 +351,10 @@ def test_gather_window_staged_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
     assert rel_err(got_n.float(), want_n) < BF16_TOL
 
 
+@pytest.mark.parametrize("version", ["v2", "v1"])
 @pytest.mark.parametrize("tile,B,spread,R,loc_dtype", [(256, 2, 1.0, None, torch.float16), (512, 1, 1.0, None, torch.float16),
                                                         (128, 2, 3.0, None, torch.float32), (256, 1, 3.0, "2", torch.float16)])
-def test_gather_bwd_windowed_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
+def test_gather_bwd_windowed_kernel(cuda_dev, tile, B, spread, R, loc_dtype, version):
     """EMRT_QUERY_PIXEL_GRID backward: grad_value accumulated in fixed point in shared-memory windows (integer
     shared-memory reductions), grad_loc / grad_attn by shuffles.  Checked against the generic backward (float
     reductions in L2) on the same bf16 inputs, against torch autograd through the float64 oracle, with and without a
@@ -376,8 +377,12 @@ def test_gather_bwd_windowed_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
     want = ops.msda_gather_bwd(gd, vd, od, ad, shapes, ref=ref_t, mode=base)
     b4 = bias.reshape(M, 3, P, 2)
     mid = np.rint((b4.max(axis=2) + b4.min(axis=2)) * 0.5).astype(np.int32)
+    # v2 (default): TMA-staged value windows + footprint records, one CTA per SM; v1: corners through L1, two CTAs per SM
+    # (what runs when v2's windows do not fit one CTA's shared memory)
     if R is not None:
         os.environ["EMRT_BWD_WIN_R"] = R
+    if version == "v1":
+        os.environ["EMRT_BWD_WIN_V1"] = "1"
     try:
         before = ops.launch_count()
         got = ops.msda_gather_bwd(gd, vd, od, ad, shapes, ref=ref_t, mode=base | L.QUERY_PIXEL_GRID)
@@ -392,6 +397,7 @@ def test_gather_bwd_windowed_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
         got_n = ops.msda_gather_bwd(gd, vd, locd, ad32, shapes, mode=L.LOC_NORMALIZED | L.QUERY_PIXEL_GRID)
     finally:
         os.environ.pop("EMRT_BWD_WIN_R", None)
+        os.environ.pop("EMRT_BWD_WIN_V1", None)
     torch.cuda.synchronize()
     for name, g, w in [("plain", got, want), ("hint", got_hint, want), ("normalized", got_n, want_n)]:
         # grad_value: fixed point with 2^-21 of the CTA's max |grad_out| per contribution; grad_loc / grad_attn: the same
