@@ -44,6 +44,7 @@ struct WinParams {
   int32_t R, TH, TW, tw_shift, regions_x, regions_y;
   int8_t cshift[WIN_MAX_M][WIN_L][2];   // per (head, level): window centre shift (x, y) in level pixels — a locality hint
   int32_t Lq, Lv, M;
+  int32_t pixel_major;           // value is [B,Lv,M,D] (5-D tensor maps, head = coordinate 1) instead of head-major [B,M,Lv,D]
   LevelTable lv;
 };
 
@@ -52,6 +53,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
           "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 
@@ -125,10 +134,13 @@ __device__ __noinline__ void slow_point(const WinParams& p, const __nv_bfloat16*
                                         float x, float y, float aw, int s, uint4* d0, uint4* d1, uint32_t* wp) {
   const int side = s >> 2;
   const Footprint f = make_footprint(x, y, p.lv.H[l], p.lv.W[l]);
-  const int64_t plane = ((int64_t)b * p.M + m) * p.Lv * WIN_D;
-  const char* base = reinterpret_cast<const char*>(value + plane + (int64_t)p.lv.start[l] * WIN_D) + (s & 3) * 16;
-  *d0 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(side ? f.i01 : f.i00) * (WIN_D * 2)));
-  *d1 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(side ? f.i11 : f.i10) * (WIN_D * 2)));
+  // first pixel of (b, level l, head m) and the distance between neighbouring pixels of one head, in elements
+  const int64_t first = p.pixel_major ? (((int64_t)b * p.Lv + p.lv.start[l]) * p.M + m) * WIN_D
+                                      : (((int64_t)b * p.M + m) * p.Lv + p.lv.start[l]) * WIN_D;
+  const int64_t pix_bytes = (p.pixel_major ? p.M : 1) * (WIN_D * 2);
+  const char* base = reinterpret_cast<const char*>(value + first) + (s & 3) * 16;
+  *d0 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(side ? f.i01 : f.i00) * pix_bytes));
+  *d1 = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(side ? f.i11 : f.i10) * pix_bytes));
   *wp = side ? pack_bf16(f.w01 * aw, f.w11 * aw) : pack_bf16(f.w00 * aw, f.w10 * aw);
 }
 
@@ -200,8 +212,10 @@ msda_gather_fwd_win_kernel(const __nv_bfloat16* __restrict__ value, const TL* __
     for (int l = 0; l < WIN_L; ++l) bytes += (uint32_t)(p.WW[l] * p.WH[l]) * (WIN_D * 2);
     mbar_arrive_expect_tx(&s_bar, bytes);
 #pragma unroll
-    for (int l = WIN_L - 1; l >= 0; --l)
-      tma_load_4d(smem_base + p.win_off[l], &p.tmap[l], &s_bar, 0, ox[l], oy[l], b * p.M + m);
+    for (int l = WIN_L - 1; l >= 0; --l) {
+      if (p.pixel_major) tma_load_5d(smem_base + p.win_off[l], &p.tmap[l], &s_bar, 0, m, ox[l], oy[l], b);
+      else tma_load_4d(smem_base + p.win_off[l], &p.tmap[l], &s_bar, 0, ox[l], oy[l], b * p.M + m);
+    }
   }
 
   const uint32_t rec_base = smem_base + p.rec_off + (uint32_t)warp * (WIN_QPB * WIN_LP * 16);
@@ -407,7 +421,7 @@ static int launch_win(const void* value, const void* loc, const void* attn, cons
 int gather_fwd_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
                    int B, int Lq, int Lv, int M, int D, int L, int P, const LevelTable& lv, int loc_dtype, int mode,
                    const int32_t* win_center_host, cudaStream_t st) {
-  if (D != WIN_D || L != WIN_L || P != WIN_P || Lq != Lv || !(mode & EMRT_VALUE_HEAD_MAJOR)) return EMRT_ERR_UNSUPPORTED;
+  if (D != WIN_D || L != WIN_L || P != WIN_P || Lq != Lv) return EMRT_ERR_UNSUPPORTED;
   for (int l = 1; l < L; ++l)
     if (lv.H[l] != (lv.H[0] >> l) || lv.W[l] != (lv.W[0] >> l) || (lv.H[l] << l) != lv.H[0] || (lv.W[l] << l) != lv.W[0])
       return EMRT_ERR_UNSUPPORTED;
@@ -423,6 +437,7 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
   p.regions_x = lv.W[0] / p.TW;
   p.regions_y = lv.H[0] / p.TH;
   p.Lq = Lq; p.Lv = Lv; p.M = M; p.lv = lv;
+  p.pixel_major = (mode & EMRT_VALUE_HEAD_MAJOR) ? 0 : 1;
   // window-centre hint [M, L, 2] (x, y) in pixels of level l: where head m's samples of level l lie relative to the
   // reference point on average (the sampling_offsets bias).  Only moves the staged windows; any sample outside them
   // still takes the global-memory path, so results never depend on it.
@@ -438,13 +453,25 @@ int gather_fwd_win(const void* value, const void* loc, const void* attn, const f
     if (p.WW[l] > 256 || p.WH[l] > 256) return EMRT_ERR_UNSUPPORTED;
     p.win_off[l] = off;
     off += ((uint32_t)(p.WW[l] * p.WH[l]) * (WIN_D * 2) + 127u) & ~127u;
-    const uint64_t dims[4] = {(uint64_t)WIN_D, (uint64_t)lv.W[l], (uint64_t)lv.H[l], (uint64_t)B * M};
-    const uint64_t strides[3] = {(uint64_t)WIN_D * 2, (uint64_t)lv.W[l] * WIN_D * 2, (uint64_t)Lv * WIN_D * 2};
-    const uint32_t box[4] = {(uint32_t)WIN_D, (uint32_t)p.WW[l], (uint32_t)p.WH[l], 1u};
-    const __nv_bfloat16* base = (const __nv_bfloat16*)value + (int64_t)lv.start[l] * WIN_D;
-    if (int e = make_tensor_map(&p.tmap[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box,
-                                CU_TENSOR_MAP_SWIZZLE_NONE))
-      return e;
+    if (p.pixel_major) {
+      // one head's plane of level l inside the reference's own [B, Lv, M, 32] layout: the head is coordinate 1
+      const uint64_t dims[5] = {(uint64_t)WIN_D, (uint64_t)M, (uint64_t)lv.W[l], (uint64_t)lv.H[l], (uint64_t)B};
+      const uint64_t strides[4] = {(uint64_t)WIN_D * 2, (uint64_t)M * WIN_D * 2, (uint64_t)lv.W[l] * M * WIN_D * 2,
+                                   (uint64_t)Lv * M * WIN_D * 2};
+      const uint32_t box[5] = {(uint32_t)WIN_D, 1u, (uint32_t)p.WW[l], (uint32_t)p.WH[l], 1u};
+      const __nv_bfloat16* base = (const __nv_bfloat16*)value + (int64_t)lv.start[l] * M * WIN_D;
+      if (int e = make_tensor_map(&p.tmap[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE))
+        return e;
+    } else {
+      const uint64_t dims[4] = {(uint64_t)WIN_D, (uint64_t)lv.W[l], (uint64_t)lv.H[l], (uint64_t)B * M};
+      const uint64_t strides[3] = {(uint64_t)WIN_D * 2, (uint64_t)lv.W[l] * WIN_D * 2, (uint64_t)Lv * WIN_D * 2};
+      const uint32_t box[4] = {(uint32_t)WIN_D, (uint32_t)p.WW[l], (uint32_t)p.WH[l], 1u};
+      const __nv_bfloat16* base = (const __nv_bfloat16*)value + (int64_t)lv.start[l] * WIN_D;
+      if (int e = make_tensor_map(&p.tmap[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE))
+        return e;
+    }
   }
   p.rec_off = off;
   // 7 warps x 6 batches covers the default 8 x 16 region (42 batches of 4 queries) exactly: static dealing, no counter

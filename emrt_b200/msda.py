@@ -89,7 +89,10 @@ class _MSDAFunction(torch.autograd.Function):
                 loc = loc.view(bs, Len_q, M, nL, P, 2)
                 attn = attn.view(bs, Len_q, M, nL, P)
             mode = L.LOC_PIXEL_OFFSET
-            g = ops.msda_gather_fwd(v.view(bs, -1, M, D), loc, attn, shapes, ref=ref, mode=mode)
+            # encoder self-attention: the window-staged forward reads the pixel-major value tensor through 5-D tensor maps
+            fgrid = L.QUERY_PIXEL_GRID if (grid and Len_q == value.shape[1] and D == 32 and nL == 3 and P == 6) else 0
+            g = ops.msda_gather_fwd(v.view(bs, -1, M, D), loc, attn, shapes, ref=ref, mode=mode | fgrid,
+                                    win_center=pk["win_center"] if fgrid else None)
             out = ops.linear(g, pk["wo"], pk["bo"], w_transposed=True, impl=impl)
         else:
             v = ops.linear(value, w_val.detach(), b_val.detach(), impl=L.IMPL_SIMT,
@@ -216,11 +219,22 @@ class MSDeformableAttention(nn.Module):
             bq = torch.cat([self.sampling_offsets.bias.detach(), self.attention_weights.bias.detach()]).float().contiguous()
             packed = dict(wv=wv, wq=wq, wo=wo, bv=self.value_proj.bias.detach().float().contiguous(), bq=bq,
                           bo=self.output_proj.bias.detach().float().contiguous())
-            # window-centre hint of the staged gather: per (head, level) the rounded mid-range of the offset bias over
-            # the points (t_e_d.py:47-55 initialises it to one direction per head, 1..P pixels out), in level pixels
-            ob = self.sampling_offsets.bias.detach().float().view(self.num_heads, self.num_levels, self.num_points, 2)
-            mid = ((ob.amax(dim=2) + ob.amin(dim=2)) * 0.5).round().clamp(-100, 100).to(torch.int32).cpu()
-            packed["win_center"] = L.i32_array(mid.reshape(-1).tolist())
+            # window-centre hint of the staged gathers: per (head, level) the rounded mid-range of the offset bias over
+            # the points (t_e_d.py:47-55 initialises it to one direction per head, 1..P pixels out), in level pixels.
+            # It needs the bias on the host (a device sync), and it is only a locality hint, so while training (weights
+            # change every step) it is refreshed every 64th re-pack instead of every time.
+            age = getattr(self, "_hint_age", None)
+            if age is None or age >= 64 or torch.cuda.is_current_stream_capturing():
+                if not torch.cuda.is_current_stream_capturing():
+                    ob = self.sampling_offsets.bias.detach().float().view(self.num_heads, self.num_levels, self.num_points, 2)
+                    mid = ((ob.amax(dim=2) + ob.amin(dim=2)) * 0.5).round().clamp(-100, 100).to(torch.int32).cpu()
+                    self._hint = L.i32_array(mid.reshape(-1).tolist())
+                    self._hint_age = 0
+                elif not hasattr(self, "_hint"):
+                    self._hint, self._hint_age = None, 0            # never computed outside a capture: no hint
+            else:
+                self._hint_age = age + 1
+            packed["win_center"] = self._hint
         self._packed = (ver, packed)
         return packed
 

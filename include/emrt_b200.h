@@ -54,7 +54,8 @@ typedef enum emrt_loc_mode {
   /* flag, OR-ed into `mode`: a locality promise, never a correctness condition.  The Lq == Lv queries are the
    * pixels of the value pyramid in level-major raster order and their reference points lie near their own pixel
    * centres (TransformerEncoder.get_reference_points, transformer_encoder_decoder.py:213-228).  Selects the
-   * window-staged forward kernel (TMA -> shared-memory windows); needs EMRT_VALUE_HEAD_MAJOR. */
+   * window-staged kernels (TMA -> shared-memory windows), forward and backward; the forward takes either value
+   * layout (4-D tensor maps over the head-major tensor, 5-D over the reference's pixel-major one). */
   EMRT_QUERY_PIXEL_GRID = 4
 } emrt_loc_mode;
 

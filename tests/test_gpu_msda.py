@@ -339,10 +339,13 @@ def test_gather_window_staged_kernel(cuda_dev, tile, B, spread, R, loc_dtype):
         wild = np.where(np.arange(M * 3 * 2) % 2 == 0, 40, -40).astype(np.int32)
         got_wild = ops.msda_gather_fwd(v_hm, od, ad, shapes, ref=ref_t, mode=base | L.QUERY_PIXEL_GRID,
                                        win_center=L.i32_array(wild.tolist()))
-        assert ops.launch_count() == before + 4
+        # the reference's own pixel-major value layout through the same kernel (5-D tensor maps): same arithmetic
+        got_pm = ops.msda_gather_fwd(d(value), od, ad, shapes, ref=ref_t, mode=L.LOC_PIXEL_OFFSET | L.QUERY_PIXEL_GRID)
+        assert ops.launch_count() == before + 5
     finally:
         os.environ.pop("EMRT_WIN_R", None)
     torch.cuda.synchronize()
+    assert torch.equal(got_pm, got)
     assert rel_err(got.float(), want) < BF16_TOL
     assert rel_err(got_hint.float(), want) < BF16_TOL
     assert rel_err(got_wild.float(), want) < BF16_TOL
