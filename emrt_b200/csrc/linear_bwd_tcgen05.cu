@@ -7,6 +7,7 @@
 // (LBO = 8192 B).  The instruction descriptor sets the a_major / b_major (transpose) bits.
 // Split-K: every output tile (128 k x 128 n) is shared by gridDim.x / tiles CTAs, each reducing a contiguous range of
 // 64-row chunks into one TMEM accumulator and adding its partial tile to dW with red.global.add.v4.f32.
+#include <cstdlib>
 #include <cstring>
 
 #include "tc_common.cuh"
@@ -161,7 +162,62 @@ colsum_kernel(const T* __restrict__ dy, float* __restrict__ db, int64_t rows, in
   }
 }
 
+// bf16, N a multiple of 8 and <= 2048: each thread owns 8 adjacent columns (one 16-byte load per row) and every
+// (256 / (N/8))-th row of the CTA's slab; the row lanes are combined in shared memory, one fp32 atomic per column and CTA.
+__global__ void __launch_bounds__(256)
+colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, int64_t rows, int N, int rows_per_cta) {
+  __shared__ float s_part[2048];
+  const int G = N / 8, RL = 256 / G;
+  const int cg = threadIdx.x % G, rl = threadIdx.x / G;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  if (rl < RL) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* src = dy + cg * 8;
+    int64_t r = r0 + rl;
+    for (; r + 3 * RL < r1; r += 4 * RL) {              // four independent loads in flight
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (r + u * RL) * N));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += __uint_as_float(w[i] << 16);
+          acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+      }
+    }
+    for (; r < r1; r += RL) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + r * N));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[rl * N + cg * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float t = 0.f;
+    for (int k = 0; k < RL; ++k) t += s_part[k * N + n];
+    atomicAdd(db + n, t);
+  }
+}
+
 int colsum(const void* dy, float* db, int64_t rows, int N, int dtype, cudaStream_t st) {
+  if (dtype == EMRT_BF16 && N % 8 == 0 && N >= 8 && N <= 2048 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+      !getenv("EMRT_COLSUM_SLOW")) {
+    const int rows_per_cta = 128;
+    const unsigned blocks = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+    colsum_bf16x8_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, db, rows, N, rows_per_cta);
+    EMRT_LAUNCH_CHECK();
+    return EMRT_OK;
+  }
   const int rows_per_cta = 256;
   const unsigned blocks = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
   if (dtype == EMRT_BF16) colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, db, rows, N, rows_per_cta);

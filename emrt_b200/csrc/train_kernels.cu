@@ -8,6 +8,7 @@
 // the parity implementation — the tcgen05 version (MN-major operands) is the next step.
 #include <cstdlib>
 
+#include <type_traits>
 #include "common.cuh"
 
 namespace emrt {
@@ -105,6 +106,74 @@ msda_qproj_bwd_kernel(const float* __restrict__ grad_loc, const float* __restric
   }
 }
 
+// Vectorised form of the above for 16-bit attn / bf16 dq, L*P even and 2*M*L*P a multiple of 4 (EMRT: 18 and 288).
+// The offset half of a dq row is an element-wise cast of the row's grad_loc (float4 in, 4 x bf16 out, scaled by
+// 1 / (W_l, H_l) in normalised mode); the logit half is one thread per (row, head) with float2 / 32-bit accesses.
+// Everything is contiguous across items, so the kernel streams at HBM speed instead of issuing 4-byte strided loads.
+template <typename TA, int MODE>
+__global__ void __launch_bounds__(256)
+msda_qproj_bwd_fast_kernel(const float* __restrict__ grad_loc, const float* __restrict__ grad_attn,
+                           const TA* __restrict__ attn, __nv_bfloat16* __restrict__ dq, int M, int L, int P,
+                           const __grid_constant__ LevelTable lv, int64_t rows) {
+  const int LP = L * P, tp = M * LP, off_len = 2 * tp, row_len = 3 * tp;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  // ---- offsets: dq[row, 0 : 2 tp] = grad_loc[row] * scale --------------------------------------------------------------
+  const int q4 = off_len / 4;
+  for (int64_t c = tid; c < rows * q4; c += nth) {
+    const int64_t row = c / q4;
+    const int j = (int)(c - row * q4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(grad_loc + row * off_len + j));
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (MODE == EMRT_LOC_NORMALIZED) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = (j + k) % (2 * LP), l = i / (2 * P);
+        o[k] *= 1.f / (float)(((j + k) & 1) ? lv.H[l] : lv.W[l]);
+      }
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dq + row * row_len + j) = pk;
+  }
+  // ---- logits: softmax backward per (row, head) -------------------------------------------------------------------------
+  const int64_t n_items = rows * M;
+  for (int64_t item = tid; item < n_items; item += nth) {
+    const int m = (int)(item % M);
+    const int64_t row = item / M;
+    const float2* ga = reinterpret_cast<const float2*>(grad_attn + item * LP);
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(attn + item * LP);
+    uint32_t* out = reinterpret_cast<uint32_t*>(dq + row * row_len + off_len + m * LP);
+    float dot = 0.f;
+    for (int i = 0; i < LP / 2; ++i) {
+      const float2 g2 = __ldg(ga + i);
+      const uint32_t aw = __ldg(a + i);
+      float a0, a1;
+      if (sizeof(TA) == 2 && std::is_same<TA, __half>::value) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&aw));
+        a0 = f.x; a1 = f.y;
+      } else {
+        a0 = __uint_as_float(aw << 16); a1 = __uint_as_float(aw & 0xffff0000u);
+      }
+      dot = fmaf(a1, g2.y, fmaf(a0, g2.x, dot));
+    }
+    for (int i = 0; i < LP / 2; ++i) {
+      const float2 g2 = __ldg(ga + i);
+      const uint32_t aw = __ldg(a + i);
+      float a0, a1;
+      if (sizeof(TA) == 2 && std::is_same<TA, __half>::value) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&aw));
+        a0 = f.x; a1 = f.y;
+      } else {
+        a0 = __uint_as_float(aw << 16); a1 = __uint_as_float(aw & 0xffff0000u);
+      }
+      __nv_bfloat162 o = __floats2bfloat162_rn(a0 * (g2.x - dot), a1 * (g2.y - dot));
+      out[i] = *reinterpret_cast<uint32_t*>(&o);
+    }
+  }
+}
+
 // dst[r, c] = src[r, c] * row_scale[r] (row_scale may be NULL), fp32 -> TO; 4 elements per thread
 template <typename TO>
 __global__ void __launch_bounds__(256)
@@ -167,6 +236,20 @@ extern "C" int emrt_msda_qproj_bwd(const float* grad_loc, const float* grad_attn
   const int64_t n_items = rows * M;
   const unsigned blocks = (unsigned)((n_items + 255) / 256);
   cudaStream_t st = as_stream(stream);
+  if (dq_dtype == EMRT_BF16 && (attn_dtype == EMRT_F16 || attn_dtype == EMRT_BF16) && ((L * P) & 1) == 0 &&
+      ((2 * M * L * P) & 3) == 0 && (reinterpret_cast<uintptr_t>(grad_loc) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(grad_attn) & 7) == 0 && (reinterpret_cast<uintptr_t>(attn) & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(dq) & 7) == 0 && !getenv("EMRT_QPROJ_BWD_SLOW")) {
+    const int64_t want = (rows * (2 * M * L * P / 4) + 255) / 256;
+    const unsigned fb = (unsigned)(want < (int64_t)num_sms() * 32 ? want : (int64_t)num_sms() * 32);
+    const bool pxf = mode == EMRT_LOC_PIXEL_OFFSET;
+#define EMRT_QBF(TA, MODE) msda_qproj_bwd_fast_kernel<TA, MODE><<<fb, 256, 0, st>>>(grad_loc, grad_attn, (const TA*)attn, (__nv_bfloat16*)dq, M, L, P, lv, rows)
+    if (attn_dtype == EMRT_F16) { if (pxf) EMRT_QBF(__half, 1); else EMRT_QBF(__half, 0); }
+    else { if (pxf) EMRT_QBF(__nv_bfloat16, 1); else EMRT_QBF(__nv_bfloat16, 0); }
+#undef EMRT_QBF
+    EMRT_LAUNCH_CHECK();
+    return EMRT_OK;
+  }
 #define EMRT_QB(TA, TO, MODE) msda_qproj_bwd_kernel<TA, TO, MODE><<<blocks, 256, 0, st>>>(grad_loc, grad_attn, (const TA*)attn, (TO*)dq, M, L, P, lv, n_items)
   const bool px = mode == EMRT_LOC_PIXEL_OFFSET;
   if (attn_dtype == EMRT_F32 && dq_dtype == EMRT_F32) { if (px) EMRT_QB(float, float, 1); else EMRT_QB(float, float, 0); }

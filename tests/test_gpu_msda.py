@@ -546,6 +546,38 @@ def test_msda_module_backward_bf16(cuda_dev, impl):
     assert not bad, errs
 
 
+@pytest.mark.parametrize("mode", ["pixel", "normalized"])
+@pytest.mark.parametrize("adt", [torch.float16, torch.bfloat16])
+def test_msda_qproj_bwd_vectorised(cuda_dev, mode, adt):
+    """Softmax + location backward (t_e_d.py:95,98-102): the vectorised kernel (16-bit weights, bf16 dq) against the
+    element-wise one and against the closed form in float64."""
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    M, P, B = 8, 6, 3
+    _, Lv = O.level_tables(shapes)
+    rng = np.random.Generator(np.random.PCG64(21))
+    gl = torch.from_numpy(O.rng_normal(rng, (B, Lv, M, 3, P, 2))).to(cuda_dev)
+    ga = torch.from_numpy(O.rng_normal(rng, (B, Lv, M, 3, P))).to(cuda_dev)
+    attn = torch.softmax(torch.from_numpy(O.rng_normal(rng, (B, Lv, M, 3 * P))), -1).view(B, Lv, M, 3, P).to(adt).to(cuda_dev)
+    md = L.LOC_PIXEL_OFFSET if mode == "pixel" else L.LOC_NORMALIZED
+    before = ops.launch_count()
+    got = ops.msda_qproj_bwd(gl, ga, attn, shapes, M, P, out_dtype=torch.bfloat16, mode=md)
+    os.environ["EMRT_QPROJ_BWD_SLOW"] = "1"
+    try:
+        ref_k = ops.msda_qproj_bwd(gl, ga, attn, shapes, M, P, out_dtype=torch.bfloat16, mode=md)
+    finally:
+        del os.environ["EMRT_QPROJ_BWD_SLOW"]
+    assert ops.launch_count() == before + 2
+    assert torch.equal(got, ref_k)                         # same arithmetic, only the access pattern differs
+    a64, g64 = attn.double().cpu().view(B, Lv, M, 18), ga.double().cpu().view(B, Lv, M, 18)
+    dlogit = a64 * (g64 - (a64 * g64).sum(-1, keepdim=True))
+    scale = torch.ones(3, 1, 2, dtype=torch.float64)
+    if mode == "normalized":
+        scale = torch.tensor([[1.0 / w, 1.0 / h] for h, w in shapes], dtype=torch.float64).view(3, 1, 2)
+    doff = gl.double().cpu() * scale
+    want = torch.cat([doff.reshape(B, Lv, -1), dlogit.reshape(B, Lv, -1)], -1)
+    assert rel_err(got.float(), want) < BF16_TOL
+
+
 @pytest.mark.parametrize("rows,K,N", [(1000, 256, 432), (129, 96, 40), (20000, 256, 256), (64, 256, 1024)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_linear_bwd_weight(cuda_dev, rows, K, N, dtype):
