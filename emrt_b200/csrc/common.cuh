@@ -86,11 +86,25 @@ template <> struct Vec16<float> {
   __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  // the 16 bytes as loaded (to keep a prefetched vector in 4 registers) and their later conversion
+  __device__ static __forceinline__ uint4 load_raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
 };
 template <> struct Vec16<__nv_bfloat16> {
   static constexpr int N = 8;
   __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[8]) {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

@@ -64,6 +64,16 @@ residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residua
 #pragma unroll
     for (int i = 0; i < PER; ++i) Vec16<T>::load(x + row * N + (i * 32 + lane) * VEC, v[r][i]);
   }
+  // conv-branch variant: its two extra streams (conv output, skip) are requested now, packed, so that all four loads of a
+  // row are in flight together instead of two after the LayerNorm statistics
+  uint4 pre_cv[GN ? PER : 1], pre_sk[GN ? PER : 1];
+  if (GN) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      pre_cv[i] = Vec16<T>::load_raw(reinterpret_cast<const T*>(gn.conv) + row0 * N + (i * 32 + lane) * VEC);
+      pre_sk[i] = Vec16<T>::load_raw(reinterpret_cast<const T*>(gn.skip) + row0 * N + (i * 32 + lane) * VEC);
+    }
+  }
   if (residual) {
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
@@ -132,8 +142,8 @@ residual_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ residua
         const float mean = st.x * inv_cnt;
         const float grstd = rsqrtf(fmaxf(st.y * inv_cnt - mean * mean, 0.f) + gn.eps);
         float cv[VEC], sk[VEC], gg[VEC], gb[VEC];
-        Vec16<T>::load(reinterpret_cast<const T*>(gn.conv) + row * N + c, cv);
-        Vec16<T>::load(reinterpret_cast<const T*>(gn.skip) + row * N + c, sk);
+        Vec16<T>::unpack(pre_cv[i], cv);        // RPW == 1 in this variant: row == row0
+        Vec16<T>::unpack(pre_sk[i], sk);
 #pragma unroll
         for (int k = 0; k < VEC; k += 4) {
           const float4 g4 = __ldg(reinterpret_cast<const float4*>(gn.gamma + l * N + c + k));

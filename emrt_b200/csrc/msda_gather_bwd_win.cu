@@ -602,7 +602,8 @@ msda_gather_bwd_win2_kernel(const __nv_bfloat16* __restrict__ grad_out, const __
       }
       int next = 0;
       if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(next) : "r"(smem_u32(&s_next)) : "memory");
-      batch = __shfl_sync(0xffffffffu, next, 0);     // also orders this batch's record reads before the next batch's writes
+      batch = __shfl_sync(0xffffffffu, next, 0);
+      __syncwarp();                                  // this batch's record reads before the next batch's record writes
     }
     __syncthreads();
 
