@@ -1,64 +1,75 @@
 // Decoder self-attention core (MultiHeadAttention over the 110 PSP query tokens, layers.py:282-301):
 //   out[b, q, m*D + d] = sum_k softmax_k(scale * <Q[b,q,m,:], K[b,k,m,:]>) V[b,k,m,d]
-// The sequences are tiny (Lq = Lk = 110, D = 32), so one CTA owns a (batch, head): K and V sit in shared memory as fp32,
-// a warp owns a query at a time — lanes over keys for the scores and the softmax reductions, lanes over channels for
-// the weighted sum.  Inputs are the projected q / k / v in the token layout [B, L, M*D] (row strides given, so the fused
-// [q | k] projection output can be read in place).
+// The sequences are tiny (Lq = Lk = 110, D = 32), so one CTA owns a (batch, head): K and V sit in shared memory as fp32
+// and every LANE owns a query — its 32 q values and 32 accumulators live in registers, the K / V rows are read as
+// broadcast LDS.128 (all lanes the same address: one wavefront per 16 bytes for 32 queries).  Two passes over the keys
+// (row maximum; then exp, sum and the weighted V sum) instead of keeping 110 scores per query.  The first version (a warp
+// per query, lanes over keys, scalar shared-memory reads) was bound by the shared-memory pipe: 350 wavefronts per query,
+// 117 us per call; this one needs 82.  Inputs are the projected q / k / v in the token layout [B, L, M*D] (row strides
+// given, so the fused [q | k] projection output can be read in place).
 #include "common.cuh"
 
 namespace emrt {
 
 constexpr int MHA_MAX_LK = 256;
+constexpr int MHA_WARPS = 4;
+
+template <int D>
+__device__ __forceinline__ float mha_dot(const float (&qv)[D], const float* __restrict__ row) {
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; d += 4) {
+    const float4 kv = *reinterpret_cast<const float4*>(row + d);
+    s = fmaf(qv[d], kv.x, s); s = fmaf(qv[d + 1], kv.y, s); s = fmaf(qv[d + 2], kv.z, s); s = fmaf(qv[d + 3], kv.w, s);
+  }
+  return s;
+}
 
 template <typename T, int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(MHA_WARPS * 32)
 mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k, int64_t k_ld, const T* __restrict__ v,
                  int64_t v_ld, T* __restrict__ out, int Lq, int Lk, int M, float scale) {
-  extern __shared__ float sm[];
-  float* ks = sm;                       // [Lk][D + 1]
-  float* vs = sm + Lk * (D + 1);        // [Lk][D]
-  float* ps = vs + Lk * D;              // [8 warps][MHA_MAX_LK]
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;                 // [Lk][D]
+  float* vs = sm + Lk * D;        // [Lk][D]
   const int m = blockIdx.x % M;
   const int64_t b = blockIdx.x / M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < Lk * D; i += blockDim.x) {
     const int kk = i / D, d = i - kk * D;
-    ks[kk * (D + 1) + d] = to_float(k[(b * Lk + kk) * k_ld + m * D + d]);
-    vs[kk * D + d] = to_float(v[(b * Lk + kk) * v_ld + m * D + d]);
+    ks[i] = to_float(k[(b * Lk + kk) * k_ld + m * D + d]);
+    vs[i] = to_float(v[(b * Lk + kk) * v_ld + m * D + d]);
   }
   __syncthreads();
-  float* pw = ps + warp * MHA_MAX_LK;
-  for (int qi = warp; qi < Lq; qi += 8) {
+  for (int q0 = (blockIdx.y * MHA_WARPS + warp) * 32; q0 < Lq; q0 += 32 * MHA_WARPS * gridDim.y) {
+    const int qi = q0 + lane;
+    const bool valid = qi < Lq;
+    const T* qrow = q + (b * Lq + (valid ? qi : Lq - 1)) * q_ld + m * D;
     float qv[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) qv[d] = to_float(q[(b * Lq + qi) * q_ld + m * D + d]) * scale;   // (q k^T) * D^-0.5
+    for (int d = 0; d < D; ++d) qv[d] = to_float(qrow[d]) * scale;           // (q k^T) * D^-0.5
     float mx = -INFINITY;
-    for (int kk = lane; kk < Lk; kk += 32) {
-      float s = 0.f;
+    for (int kk = 0; kk < Lk; ++kk) mx = fmaxf(mx, mha_dot<D>(qv, ks + kk * D));
+    float sum = 0.f, acc[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) s = fmaf(qv[d], ks[kk * (D + 1) + d], s);
-      pw[kk] = s;
-      mx = fmaxf(mx, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int kk = lane; kk < Lk; kk += 32) {
-      const float e = expf(pw[kk] - mx);
-      pw[kk] = e;
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    for (int kk = 0; kk < Lk; ++kk) {
+      const float e = expf(mha_dot<D>(qv, ks + kk * D) - mx);
       sum += e;
-    }
+      const float* vr = vs + kk * D;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncwarp();
-    const float inv = 1.f / sum;
-    // lanes over channels (D <= 32)
-    if (lane < D) {
-      float acc = 0.f;
-      for (int kk = 0; kk < Lk; ++kk) acc = fmaf(pw[kk], vs[kk * D + lane], acc);
-      out[(b * Lq + qi) * (int64_t)(M * D) + m * D + lane] = from_float<T>(acc * inv);
+      for (int d = 0; d < D; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(vr + d);
+        acc[d] = fmaf(e, vv.x, acc[d]); acc[d + 1] = fmaf(e, vv.y, acc[d + 1]);
+        acc[d + 2] = fmaf(e, vv.z, acc[d + 2]); acc[d + 3] = fmaf(e, vv.w, acc[d + 3]);
+      }
     }
-    __syncwarp();
+    if (valid) {
+      const float inv = 1.f / sum;
+      T* orow = out + (b * Lq + qi) * (int64_t)(M * D) + m * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) orow[d] = from_float<T>(acc[d] * inv);
+    }
   }
 }
 
@@ -71,7 +82,7 @@ extern "C" int emrt_mha_small(const void* q, int64_t q_ld, const void* k, int64_
   EMRT_REQUIRE(q && k && v && out && B > 0 && Lq > 0 && Lk > 0 && M > 0, "bad mha_small arguments");
   if (D != 32) return set_error(EMRT_ERR_UNSUPPORTED, "mha_small is built for head dim 32 (got %d)", D);
   if (Lk > MHA_MAX_LK) return set_error(EMRT_ERR_UNSUPPORTED, "mha_small holds K/V of one head in shared memory: Lk <= %d (got %d)", MHA_MAX_LK, Lk);
-  const size_t smem = sizeof(float) * ((size_t)Lk * (32 + 1) + (size_t)Lk * 32 + 8 * MHA_MAX_LK);
+  const size_t smem = sizeof(float) * ((size_t)Lk * 32 * 2);
   cudaStream_t st = as_stream(stream);
   static bool attr = false;
   if (!attr) {
@@ -79,11 +90,13 @@ extern "C" int emrt_mha_small(const void* q, int64_t q_ld, const void* k, int64_
     EMRT_CUDA_CHECK(cudaFuncSetAttribute(mha_small_kernel<__nv_bfloat16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  const unsigned grid = (unsigned)(B * M);
+  // one CTA (4 warps x 32 queries) per (batch, head) and 128 queries
+  const int splits = (Lq + 32 * MHA_WARPS - 1) / (32 * MHA_WARPS);
+  const dim3 grid((unsigned)(B * M), (unsigned)splits);
   if (dtype == EMRT_F32)
-    mha_small_kernel<float, 32><<<grid, 256, smem, st>>>((const float*)q, q_ld, (const float*)k, k_ld, (const float*)v, v_ld, (float*)out, Lq, Lk, M, scale);
+    mha_small_kernel<float, 32><<<grid, MHA_WARPS * 32, smem, st>>>((const float*)q, q_ld, (const float*)k, k_ld, (const float*)v, v_ld, (float*)out, Lq, Lk, M, scale);
   else if (dtype == EMRT_BF16)
-    mha_small_kernel<__nv_bfloat16, 32><<<grid, 256, smem, st>>>((const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)k, k_ld, (const __nv_bfloat16*)v, v_ld, (__nv_bfloat16*)out, Lq, Lk, M, scale);
+    mha_small_kernel<__nv_bfloat16, 32><<<grid, MHA_WARPS * 32, smem, st>>>((const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)k, k_ld, (const __nv_bfloat16*)v, v_ld, (__nv_bfloat16*)out, Lq, Lk, M, scale);
   else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
