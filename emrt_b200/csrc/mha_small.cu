@@ -14,15 +14,16 @@ namespace emrt {
 constexpr int MHA_MAX_LK = 256;
 constexpr int MHA_WARPS = 4;
 
+// four independent partial sums: a single fmaf chain of 32 would leave a warp one instruction per 4 clocks
 template <int D>
 __device__ __forceinline__ float mha_dot(const float (&qv)[D], const float* __restrict__ row) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int d = 0; d < D; d += 4) {
     const float4 kv = *reinterpret_cast<const float4*>(row + d);
-    s = fmaf(qv[d], kv.x, s); s = fmaf(qv[d + 1], kv.y, s); s = fmaf(qv[d + 2], kv.z, s); s = fmaf(qv[d + 3], kv.w, s);
+    s0 = fmaf(qv[d], kv.x, s0); s1 = fmaf(qv[d + 1], kv.y, s1); s2 = fmaf(qv[d + 2], kv.z, s2); s3 = fmaf(qv[d + 3], kv.w, s3);
   }
-  return s;
+  return (s0 + s1) + (s2 + s3);
 }
 
 template <typename T, int D>
@@ -49,10 +50,12 @@ mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k,
 #pragma unroll
     for (int d = 0; d < D; ++d) qv[d] = to_float(qrow[d]) * scale;           // (q k^T) * D^-0.5
     float mx = -INFINITY;
+#pragma unroll 2
     for (int kk = 0; kk < Lk; ++kk) mx = fmaxf(mx, mha_dot<D>(qv, ks + kk * D));
     float sum = 0.f, acc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) acc[d] = 0.f;
+#pragma unroll 2
     for (int kk = 0; kk < Lk; ++kk) {
       const float e = expf(mha_dot<D>(qv, ks + kk * D) - mx);
       sum += e;
