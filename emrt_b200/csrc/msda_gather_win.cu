@@ -17,7 +17,10 @@
 // A sample that lands outside the staged window but inside the map (|offset| > R) takes a per-point slow path
 // that reads global memory with explicit validity weights, so results do not depend on R.
 // The query -> region mapping is only a locality promise (EMRT_QUERY_PIXEL_GRID): any reference points give
-// correct results, far-away ones just run the slow path.
+// correct results, far-away ones just run the slow path.  The same holds for the optional window-centre hint (per head
+// and level, the mean sampling offset taken from the layer's bias): it only moves the windows to where that head samples.
+// Value layouts: head-major [B,M,Lv,32] (4-D tensor maps) or the reference's pixel-major [B,Lv,M,32] (5-D maps, the
+// head is a coordinate) — the training path keeps the latter.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -106,26 +109,6 @@ __device__ __forceinline__ int batch_query_base(const WinParams& p, const int (&
   const int W = l2 ? p.lv.W[2] : (l1 ? p.lv.W[1] : p.lv.W[0]);
   return (l2 ? qb[2] : (l1 ? qb[1] : qb[0])) + y * W + (x << 2);
 }
-
-template <typename TL, int MODE>
-__device__ __forceinline__ void sample_xy(const WinParams& p, const TL* __restrict__ loc, const TL* __restrict__ attn,
-                                          const float* __restrict__ ref, int64_t ref_bs, int b, int q, int m, int pt,
-                                          float& x, float& y, float& aw) {
-  const int l = pt / WIN_P;
-  const int64_t item = ((int64_t)b * p.Lq + q) * p.M + m;
-  const float2 xy = Pair<TL>::load(loc + (item * WIN_LP + pt) * 2);
-  aw = load1<TL>(attn + item * WIN_LP + pt);
-  const float W = (float)p.lv.W[l], H = (float)p.lv.H[l];
-  if (MODE == EMRT_LOC_PIXEL_OFFSET) {
-    const float2 rf = __ldg(reinterpret_cast<const float2*>(ref + b * ref_bs + ((int64_t)q * WIN_L + l) * 2));
-    x = rf.x * W - 0.5f + xy.x;
-    y = rf.y * H - 0.5f + xy.y;
-  } else {
-    x = xy.x * W - 0.5f;
-    y = xy.y * H - 0.5f;
-  }
-}
-
 
 // Slow path of one point: it left the staged window (|offset| > R) but not the map.  Global loads with the explicit
 // zero-padding weights of make_footprint, from the sample position stage A kept; out-of-line so the unrolled fast path
