@@ -62,6 +62,16 @@ class PaddleLinear(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_features))
 
 
+def window_center_hint(offset_bias, num_heads, num_levels, num_points):
+    """Window-centre hint of the staged gathers (emrt_msda_gather_fwd_hint / _bwd_hint): per (head, level) the rounded
+    mid-range, over the points, of the `sampling_offsets` bias viewed as [M, L, P, 2] (t_e_d.py:89-90) — where that head
+    samples relative to the reference point when the data-dependent part of the offset is small.  Flat list
+    [M * L * 2] of ints (x, y) in pixels of the level, clamped to +-100."""
+    ob = offset_bias.detach().float().reshape(num_heads, num_levels, num_points, 2)
+    mid = ((ob.amax(dim=2) + ob.amin(dim=2)) * 0.5).round().clamp(-100, 100).to(torch.int32).cpu()
+    return mid.reshape(-1).tolist()
+
+
 class _MSDAFunction(torch.autograd.Function):
     """fwd + bwd of MSDeformableAttention.forward (t_e_d.py:65-107) through the C ABI.  The training path keeps the
     projected value pixel-major ([B,Lv,M,D], the layout emrt_msda_gather_bwd scatters into) and saves the module's
@@ -226,9 +236,8 @@ class MSDeformableAttention(nn.Module):
             age = getattr(self, "_hint_age", None)
             if age is None or age >= 64 or torch.cuda.is_current_stream_capturing():
                 if not torch.cuda.is_current_stream_capturing():
-                    ob = self.sampling_offsets.bias.detach().float().view(self.num_heads, self.num_levels, self.num_points, 2)
-                    mid = ((ob.amax(dim=2) + ob.amin(dim=2)) * 0.5).round().clamp(-100, 100).to(torch.int32).cpu()
-                    self._hint = L.i32_array(mid.reshape(-1).tolist())
+                    self._hint = L.i32_array(window_center_hint(self.sampling_offsets.bias, self.num_heads, self.num_levels,
+                                                                self.num_points))
                     self._hint_age = 0
                 elif not hasattr(self, "_hint"):
                     self._hint, self._hint_age = None, 0            # never computed outside a capture: no hint

@@ -177,3 +177,25 @@ def test_encoder_decoder_state_dict_keys_match_the_reference_layout():
     sd = m.state_dict()
     assert set(sd) == set(p)
     assert all(tuple(sd[k].shape) == tuple(p[k].shape) for k in sd)
+
+
+def test_window_center_hint_of_reference_init():
+    """The reference initialises sampling_offsets.bias to one direction per head, 1..P pixels out (t_e_d.py:47-55): the
+    hint is the rounded mid-range 3.5 * direction of every (head, level)."""
+    import math
+    import torch
+    from emrt_b200.msda import window_center_hint
+    from oracle import emrt_oracle as O
+    M, L_, P = 8, 3, 6
+    bias = torch.from_numpy(O.msda_reset_parameters(256, M, L_, P).reshape(-1))
+    hint = torch.tensor(window_center_hint(bias, M, L_, P)).view(M, L_, 2)
+    for m in range(M):
+        th = 2.0 * math.pi * m / M
+        dx, dy = math.cos(th), math.sin(th)
+        s = max(abs(dx), abs(dy))
+        want = torch.tensor([dx / s * 3.5, dy / s * 3.5])
+        for l in range(L_):      # (the mid-range is exactly +-3.5 on the dominant axis: either neighbour is a correct rounding)
+            assert (hint[m, l].float() - want).abs().max() <= 0.5 + 1e-4, (m, l, hint[m, l], want)
+    # a zero bias (no preferred direction) gives no shift; large biases are clamped
+    assert window_center_hint(torch.zeros(M * L_ * P * 2), M, L_, P) == [0] * (M * L_ * 2)
+    assert max(window_center_hint(torch.full((M * L_ * P * 2,), 1e4), M, L_, P)) == 100
