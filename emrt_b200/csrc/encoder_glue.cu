@@ -241,16 +241,39 @@ groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int Lv, 
   float s = 0.f, ss = 0.f;
   if (slot < slots) {
     constexpr int VEC = Vec16<T>::N;
-    for (int p = blockIdx.y * slots + slot; p < npix; p += gridDim.y * slots) {
-      const T* xp = x + ((b * Lv + lv.start[l] + p) * C) + v * 8;
+    // four pixels per trip, their loads in flight together, each with its own partial sums (combined in a fixed order:
+    // the result stays independent of scheduling)
+    const T* xbase = x + ((b * Lv + lv.start[l]) * C) + v * 8;
+    const int step = gridDim.y * slots;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, ss4[4] = {0.f, 0.f, 0.f, 0.f};
+    int p = blockIdx.y * slots + slot;
+    for (; p + 3 * step < npix; p += 4 * step) {
+      uint4 raw[4][8 / VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8 / VEC; ++j) raw[u][j] = Vec16<T>::load_raw(xbase + (int64_t)(p + u * step) * C + j * VEC);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8 / VEC; ++j) {
+          float a[VEC];
+          Vec16<T>::unpack(raw[u][j], a);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) { s4[u] += a[k]; ss4[u] = fmaf(a[k], a[k], ss4[u]); }
+        }
+    }
+    for (; p < npix; p += step) {
 #pragma unroll
       for (int j = 0; j < 8 / VEC; ++j) {
         float a[VEC];
-        Vec16<T>::load(xp + j * VEC, a);
+        Vec16<T>::load(xbase + (int64_t)p * C + j * VEC, a);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) { s += a[k]; ss = fmaf(a[k], a[k], ss); }
+        for (int k = 0; k < VEC; ++k) { s4[0] += a[k]; ss4[0] = fmaf(a[k], a[k], ss4[0]); }
       }
     }
+    s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    ss = (ss4[0] + ss4[1]) + (ss4[2] + ss4[3]);
   }
   // reduce over the CTA's pixel slots and over the vectors of one group, in a fixed order
   __shared__ float sh[256][2];
