@@ -32,6 +32,7 @@ class LinearArgs(C.Structure):
         ("y2", C.c_void_p), ("qproj_group", C.c_int32),
         ("impl", C.c_int32),
         ("hm_rows", C.c_int32), ("hm_D", C.c_int32),
+        ("x2", C.c_void_p), ("x2_period", C.c_int32),
     ]
 
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     "emrt_pack_weight": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
     "emrt_linear_bwd_weight": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "emrt_msda_qproj_bwd": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I32P, _I, _I, _I, _P]),
+    "emrt_msda_ref_bwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I32P, _I, _P]),
     "emrt_scale_rows_cast": (C.c_int, [_P, _P, _P, _L, _I, _I, _P]),
     "emrt_msda_softmax_loc": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I32P, _I, _I, _P]),
     "emrt_add_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, C.c_float, _I, _P]),

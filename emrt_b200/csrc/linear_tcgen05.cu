@@ -36,6 +36,8 @@ struct GemmParams {
   CUtensorMap tma_b;   // Wt [N, K]    bf16, box {64, BLOCK_N}
   CUtensorMap tma_y;   // staged epilogue: y  as 2-byte elements (row-major 2-D or head-major 3-D), box 32 rows
   CUtensorMap tma_y2;  // staged epilogue, QPROJ only: y2
+  CUtensorMap tma_a2;  // x2 [x2_period + 127, K] bf16 (cyclic), box {64, 128}: the broadcast addend of x (with_pos_embed)
+  int32_t a2_period;   // 0 = no x2
   const float* bias;
   const float* row_scale;
   void* y;
@@ -104,6 +106,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
+    if (p.a2_period) tma_prefetch_desc(&p.tma_a2);
     if (TMA_ST) { tma_prefetch_desc(&p.tma_y); if (EPI == EPI_KIND_QPROJ) tma_prefetch_desc(&p.tma_y2); }
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -131,11 +134,17 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       }
       int stage = 0;
       uint32_t phase = 0;
+      // x2 (the broadcast addend, e.g. the position embedding): (x + x2) W = x W + x2 W, so its tiles are simply
+      // num_kb more k-blocks of the same accumulation against the same weight blocks
+      const int total_kb = p.a2_period ? 2 * num_kb : num_kb;
       for (; tw.valid(); tw.next()) {
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int row2 = p.a2_period ? (int)(((int64_t)tw.m * BM) % p.a2_period) : 0;
+        for (int kk = 0; kk < total_kb; ++kk) {
+          const int kb = kk < num_kb ? kk : kk - num_kb;
           mbar_wait(&s.empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
-          tma_load_2d(s.a[stage], &p.tma_a, &s.full[stage], kb * BK, tw.m * BM);
+          if (kk < num_kb) tma_load_2d(s.a[stage], &p.tma_a, &s.full[stage], kb * BK, tw.m * BM);
+          else tma_load_2d(s.a[stage], &p.tma_a2, &s.full[stage], kb * BK, row2);
           if (!B_RES) tma_load_2d(s.b[stage], &p.tma_b, &s.full[stage], kb * BK, tw.n * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -155,7 +164,9 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int total_kb = p.a2_period ? 2 * num_kb : num_kb;
+        for (int kk = 0; kk < total_kb; ++kk) {
+          const int kb = kk < num_kb ? kk : kk - num_kb;
           mbar_wait(&s.full[stage], phase);
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(s.a[stage]));
@@ -163,10 +174,10 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // +32 bytes (= 2 x 16 B) per K=16 step inside the 128-byte swizzle row
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kk | k) != 0 ? 1u : 0u);
           }
           umma_commit(&s.empty[stage]);                     // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&s.tmem_full[acc]);
+          if (kk == total_kb - 1) umma_commit(&s.tmem_full[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -408,6 +419,8 @@ static int launch_tc(GemmParams& p, const emrt_linear_args* a, cudaStream_t st) 
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
   if (int e = make_tma_2d(&p.tma_a, a->x, (uint64_t)a->K, (uint64_t)a->rows, BM)) return e;
   if (int e = make_tma_2d(&p.tma_b, a->w, (uint64_t)a->K, (uint64_t)a->N, BLOCK_N)) return e;
+  if (p.a2_period)
+    if (int e = make_tma_2d(&p.tma_a2, a->x2, (uint64_t)a->K, (uint64_t)a->x2_period + BM - 1, BM)) return e;
   if (TMA_ST) {
     const CUtensorMapDataType dt = a->y_dtype == EMRT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (EPI == EPI_KIND_QPROJ) {
@@ -430,11 +443,8 @@ static int launch_tc(GemmParams& p, const emrt_linear_args* a, cudaStream_t st) 
   p.tiles_m = (int)((a->rows + BM - 1) / BM);
   p.tiles_n = (a->N + BLOCK_N - 1) / BLOCK_N;
   auto kern = linear_tcgen05_kernel<BLOCK_N, STAGES, EPI, GROUP, B_RES, TMA_ST>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  // function attributes are per device / context: set every time (cheap), not once per process
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid;
   if (B_RES) {
     // n-stationary: gridDim.x is a multiple of tiles_n; every CTA owns one column slice and >= 1 row tile
@@ -459,6 +469,8 @@ static int pick_tc(GemmParams& p, const emrt_linear_args* a, bool res, bool tma_
   return launch_tc<BLOCK_N, ST_STREAM, EPI, GROUP, false, false>(p, a, st);
 }
 
+int linear_ln_tcgen05(const emrt_linear_args* a, cudaStream_t st);
+
 int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
   if (a->x_dtype != EMRT_BF16 || a->w_dtype != EMRT_BF16 || !a->w_transposed)
     return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 linear needs bf16 x and bf16 pre-packed [N,K] weights (emrt_pack_weight)");
@@ -468,8 +480,17 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
     return set_error(EMRT_ERR_INVALID_ARGUMENT, "tcgen05 linear needs 16-byte aligned x, w, y");
   if (a->y_dtype != EMRT_F32 && a->y_dtype != EMRT_BF16 && a->y_dtype != EMRT_F16)
     return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad y_dtype %d", a->y_dtype);
+  if (a->epilogue & EMRT_EPI_RESIDUAL_LN) {
+    if (a->epilogue != EMRT_EPI_RESIDUAL_LN || a->x2) return set_error(EMRT_ERR_UNSUPPORTED, "RESIDUAL_LN cannot be combined with other epilogues / x2");
+    return linear_ln_tcgen05(a, st);
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  if (a->x2) {
+    if (a->x2_period <= 0 || (reinterpret_cast<uintptr_t>(a->x2) & 15))
+      return set_error(EMRT_ERR_INVALID_ARGUMENT, "x2 needs x2_period > 0 and a 16-byte aligned pointer");
+    p.a2_period = a->x2_period;
+  }
   p.bias = a->bias; p.row_scale = a->row_scale; p.y = a->y; p.y2 = a->y2;
   p.rows = a->rows; p.K = a->K; p.N = a->N; p.y_dtype = a->y_dtype; p.flags = a->epilogue;
   const bool two_byte = a->y_dtype != EMRT_F32;

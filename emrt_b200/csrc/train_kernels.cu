@@ -190,6 +190,32 @@ scale_rows_cast_kernel(const float* __restrict__ src, const float* __restrict__ 
   }
 }
 
+
+// Gradient of the reference points (sampling_locations = reference_points + offsets / (W_l, H_l), t_e_d.py:98-102, so
+// d ref[b,q,l,:] = sum over heads and points of d loc[b,q,m,l,p,:]; in PIXEL_OFFSET mode grad_loc is per pixel and
+// d x / d ref_x = W_l).  One thread per (reference batch, query, level); a batch-shared reference (ref_batches == 1, the
+// decoder's sigmoid(Linear(query_pos_embed)), t_e_d.py:466) sums over the batch in a fixed order: no atomics.
+__global__ void msda_ref_bwd_kernel(const float* __restrict__ grad_loc, float* __restrict__ grad_ref, int B, int ref_batches,
+                                    int Lq, int M, int L, int P, LevelTable lv, int pixel_mode) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)ref_batches * Lq * L) return;
+  const int l = (int)(i % L);
+  const int q = (int)((i / L) % Lq);
+  const int rb = (int)(i / ((int64_t)L * Lq));
+  float gx = 0.f, gy = 0.f;
+  for (int b = rb; b < B; b += ref_batches) {
+    const float2* g = reinterpret_cast<const float2*>(grad_loc) + (((int64_t)b * Lq + q) * M * L + l) * P;
+    for (int m = 0; m < M; ++m)
+      for (int pp = 0; pp < P; ++pp) {
+        const float2 v = __ldg(g + (int64_t)m * L * P + pp);
+        gx += v.x;
+        gy += v.y;
+      }
+  }
+  if (pixel_mode) { gx *= (float)lv.W[l]; gy *= (float)lv.H[l]; }
+  reinterpret_cast<float2*>(grad_ref)[i] = make_float2(gx, gy);
+}
+
 }  // namespace emrt
 
 using namespace emrt;
@@ -272,6 +298,20 @@ extern "C" int emrt_scale_rows_cast(const float* src, const float* row_scale, vo
   if (dst_dtype == EMRT_F32) scale_rows_cast_kernel<float><<<blocks, 256, 0, st>>>(src, row_scale, (float*)dst, rows, cols);
   else if (dst_dtype == EMRT_BF16) scale_rows_cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, row_scale, (__nv_bfloat16*)dst, rows, cols);
   else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dst_dtype %d", dst_dtype);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
+}
+
+extern "C" int emrt_msda_ref_bwd(const float* grad_loc, float* grad_ref, int B, int ref_batches, int Lq, int M, int L, int P,
+                                 const int32_t* shapes_hw_host, int mode, void* stream) {
+  EMRT_REQUIRE(grad_loc && grad_ref, "NULL tensor pointer");
+  EMRT_REQUIRE(B > 0 && Lq > 0 && M > 0 && P > 0 && (ref_batches == 1 || ref_batches == B), "bad msda_ref_bwd dimensions");
+  EMRT_REQUIRE(mode == EMRT_LOC_NORMALIZED || mode == EMRT_LOC_PIXEL_OFFSET, "bad loc mode");
+  LevelTable lv;
+  if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, -1)) return e;
+  const int64_t n = (int64_t)ref_batches * Lq * L;
+  msda_ref_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(grad_loc, grad_ref, B, ref_batches, Lq, M, L, P,
+                                                                              lv, mode == EMRT_LOC_PIXEL_OFFSET);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
 }

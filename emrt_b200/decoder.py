@@ -110,20 +110,32 @@ class TransformerDecoderLayer(nn.Module):
         C_, M = self.d_model, self.n_head
         lin = lambda x, w, b, **kw: ops.linear(x, pk[w], pk[b], w_transposed=fast, impl=impl, **kw)
         pos = None if query_pos_embed is None else query_pos_embed.to(tgt.dtype).contiguous()
-        with_pos = lambda t: t if pos is None else ops.add_bcast(t, pos)
+        Nq = tgt.shape[1]
+        tc = fast and impl != L.IMPL_SIMT
+        # with_pos_embed folded into the projections ((tgt + pos) W = tgt W + pos W in one GEMM) on the tcgen05 path
+        fold = tc and pos is not None and pos.numel() == Nq * C_
+        x2 = dict(x2=ops.cyclic_rows_cached(query_pos_embed), x2_period=Nq) if fold else {}
+        with_pos = lambda t: t if (pos is None or fold) else ops.add_bcast(t, pos)
+
+        def lin_norm(x, w, b, res, nw, nb):
+            """LayerNorm(x W + b + res): one kernel on the tcgen05 path (EMRT_EPI_RESIDUAL_LN)."""
+            if tc and C_ == 256:
+                return ops.linear(x, pk[w], pk[b], w_transposed=True, impl=impl, epilogue=L.EPI_RESIDUAL_LN, residual=res,
+                                  ln_gamma=pk[nw], ln_beta=pk[nb])
+            y = lin(x, w, b)
+            return ops.residual_layernorm(y, res, pk[nw], pk[nb], out=y)
+
         # self attention over the query tokens (layers.py:282-301): q = k = tgt + pos, value = tgt
-        qk = lin(with_pos(tgt), "w_qk", "b_qk")
+        qk = lin(with_pos(tgt), "w_qk", "b_qk", **x2)
         v = lin(tgt, "w_v", "b_v")
         att = ops.mha_small(qk[..., :C_], qk[..., C_:], v, M, float(C_ // M) ** -0.5)
-        tgt2 = lin(att, "w_o", "b_o")
-        tgt = ops.residual_layernorm(tgt2, tgt, pk["n1w"], pk["n1b"], out=tgt2)
-        # cross attention into the encoder memory
-        tgt2 = self.cross_attn(with_pos(tgt), reference_points, memory, shapes, memory_mask)
-        tgt = ops.residual_layernorm(tgt2, tgt, pk["n2w"], pk["n2b"], out=tgt2)
-        # ffn
+        tgt = lin_norm(att, "w_o", "b_o", tgt, "n1w", "n1b")
+        # cross attention into the encoder memory (+ norm2)
+        tgt = self.cross_attn(tgt, reference_points, memory, shapes, memory_mask, query_pos=pos,
+                              residual_norm=(tgt, pk["n2w"], pk["n2b"]))
+        # ffn (+ norm3)
         h = lin(tgt, "w1", "b1", epilogue=L.EPI_RELU)
-        f = lin(h, "w2", "b2")
-        return ops.residual_layernorm(f, tgt, pk["n3w"], pk["n3b"], out=f)
+        return lin_norm(h, "w2", "b2", tgt, "n3w", "n3b")
 
 
 class TransformerDecoder(nn.Module):

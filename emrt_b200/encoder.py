@@ -96,9 +96,9 @@ class TransformerEncoderLayer(nn.Module):
         conv = ops.conv3x3_tokens(src, pk["conv_w"], shapes, impl=L.IMPL_AUTO if impl != L.IMPL_SIMT else L.IMPL_SIMT)
         gn_stats = ops.groupnorm_stats(conv, shapes, groups=32)
         # self attention (:198) + norm1 (:199-200)
-        q = src if pos_embed is None else ops.add_bcast(src, pos_embed.to(src.dtype).contiguous())
-        src2 = self.self_attn(q, reference_points, src, shapes, src_mask)
-        x = ops.residual_layernorm(src2, src, pk["n1w"], pk["n1b"], out=src2)
+        # (with_pos_embed is folded into the query projection, norm1 into the output projection: msda.py)
+        x = self.self_attn(src, reference_points, src, shapes, src_mask, query_pos=pos_embed,
+                           residual_norm=(src, pk["n1w"], pk["n1b"]))
         # ffn (:157-160) + the layer's final add of the conv branch (:203)
         if fast:
             h = ops.linear(x, pk["w1"], pk["b1"], w_transposed=True, epilogue=L.EPI_RELU, impl=impl)

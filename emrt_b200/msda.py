@@ -41,15 +41,65 @@ def shapes_to_host(value_spatial_shapes) -> Tuple[Tuple[int, int], ...]:
     return tuple((int(h), int(w)) for h, w in value_spatial_shapes)
 
 
+class _CoreFunction(torch.autograd.Function):
+    """utils.py:64-97 with the gradients Paddle autograd derives through F.grid_sample (:87-94): emrt_msda_gather_fwd /
+    emrt_msda_gather_bwd.  Gradients flow to value, sampling_locations and attention_weights."""
+
+    @staticmethod
+    def forward(ctx, value, loc, attn, shapes):
+        ctx.shapes = shapes
+        ctx.save_for_backward(value, loc, attn)
+        return ops.msda_gather_fwd(value, loc, attn, shapes, mode=L.LOC_NORMALIZED)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        value, loc, attn = ctx.saved_tensors
+        gv, gl, ga = ops.msda_gather_bwd(d_out.contiguous(), value, loc, attn, ctx.shapes, mode=L.LOC_NORMALIZED)
+        return gv.to(value.dtype), gl.to(loc.dtype), ga.to(attn.dtype), None
+
+
 def deformable_attention_core_func(value, value_spatial_shapes, sampling_locations, attention_weights):
     """Drop-in for utils.py:64-97.  value [bs,Lv,M,D]; sampling_locations [bs,Lq,M,L,P,2] in [0,1];
-    attention_weights [bs,Lq,M,L,P] -> [bs,Lq,M*D].  fp32 or bf16 value; loc/attn fp32, fp16 or bf16."""
+    attention_weights [bs,Lq,M,L,P] -> [bs,Lq,M*D].  fp32 or bf16 value; loc/attn fp32, fp16 or bf16.
+    Differentiable (value, sampling_locations, attention_weights) like the reference's composition of Paddle ops."""
     shapes = shapes_to_host(value_spatial_shapes)
     loc, attn = sampling_locations, attention_weights
     if value.dtype == torch.float32 and loc.dtype != torch.float32:
         loc, attn = loc.float(), attn.float()
-    return ops.msda_gather_fwd(value.contiguous(), loc.contiguous(), attn.contiguous(), shapes,
-                               mode=L.LOC_NORMALIZED)
+    value, loc, attn = value.contiguous(), loc.contiguous(), attn.contiguous()
+    if torch.is_grad_enabled() and (value.requires_grad or loc.requires_grad or attn.requires_grad):
+        return _CoreFunction.apply(value, loc, attn, shapes)
+    return ops.msda_gather_fwd(value, loc, attn, shapes, mode=L.LOC_NORMALIZED)
+
+
+_grid_cache = {}
+
+
+def is_pixel_grid(reference_points, shapes, Len_q, Len_v) -> bool:
+    """Whether the queries are the value pyramid's own pixels with reference points at their centres
+    (TransformerEncoder.get_reference_points, t_e_d.py:213-228) — the geometry the window-staged gather kernels tile.
+    Decided from the tensor itself, not from how it was produced: Lq == Lv, one reference batch or B, and (checked once per
+    tensor object and version, on the device, one sync) the values equal the pixel centres.  It is a locality promise
+    only — the window kernels read any sample outside their staged window from global memory — so during CUDA-graph
+    capture, where a sync is impossible, the shape test alone decides."""
+    if Len_q != Len_v or reference_points.dim() != 4 or reference_points.shape[1] != Len_v:
+        return False
+    if getattr(reference_points, "pixel_grid", False):
+        return True
+    t = reference_points
+    hit = _grid_cache.get(id(t))
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    if torch.cuda.is_current_stream_capturing():
+        return True
+    from .refpoints import get_reference_points
+    want = get_reference_points(shapes, device=t.device)
+    tol = 0.25 / max(max(h, w) for h, w in shapes)
+    ok = bool(((t.detach().float() - want).abs().amax() < tol).item())
+    if len(_grid_cache) > 64:
+        _grid_cache.clear()
+    _grid_cache[id(t)] = (weakref.ref(t), t._version, ok)
+    return ok
 
 
 class PaddleLinear(nn.Module):
@@ -88,7 +138,7 @@ class _MSDAFunction(torch.autograd.Function):
             impl = mod.gemm_impl
             v = ops.linear(value, pk["wv"], pk["bv"], w_transposed=True, impl=impl,
                            epilogue=L.EPI_ROW_MASK if mask is not None else L.EPI_NONE, row_scale=mask)
-            if impl == L.IMPL_SIMT:
+            if impl == L.IMPL_SIMT or not mod.fused_qproj_ok():
                 raw = ops.linear(query, pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float32, impl=impl)
                 tp2 = 2 * mod.total_points
                 loc, attn = ops.msda_softmax_loc(raw[..., :tp2], raw[..., tp2:], shapes, M, P, out_dtype=torch.float16,
@@ -117,6 +167,7 @@ class _MSDAFunction(torch.autograd.Function):
         ctx.grid = L.QUERY_PIXEL_GRID if (grid and fast and Len_q == value.shape[1]) else 0
         ctx.win_center = mod.packed_weights()["win_center"] if ctx.grid else None
         ctx.mod, ctx.shapes, ctx.mode, ctx.fast = mod, shapes, mode, fast
+        ctx.ref_grad = ctx.needs_input_grad[2]
         ctx.save_for_backward(query, value, ref, mask, v, loc, attn, g, w_off, w_attn, w_val, w_out)
         return out
 
@@ -143,6 +194,8 @@ class _MSDAFunction(torch.autograd.Function):
         ref_arg = ref if mode == L.LOC_PIXEL_OFFSET else None
         gv, gl, ga = ops.msda_gather_bwd(d_g, v.view(bs, -1, M, D), loc, attn, shapes, ref=ref_arg, mode=mode | ctx.grid,
                                          win_center=ctx.win_center)
+        # reference points (t_e_d.py:98-102: sampling_locations = reference_points + offsets / normaliser)
+        d_ref = ops.msda_ref_bwd(gl, shapes, ref.shape[0], mode) if ctx.ref_grad else None
         # softmax + offsets -> fused query projection
         dq = ops.msda_qproj_bwd(gl, ga, attn, shapes, M, P, out_dtype=cdt, mode=mode)
         d_query = ops.linear(dq, wq_kn, None, w_transposed=True, impl=impl)
@@ -153,7 +206,7 @@ class _MSDAFunction(torch.autograd.Function):
         d_value = ops.linear(d_v, wv_kn, None, w_transposed=True, impl=impl)
         dw_val, db_val = torch.zeros((C_, C_), **f32), torch.zeros((C_,), **f32)
         ops.linear_bwd_weight(value, d_v, dw_val, db_val)
-        return (None, d_query, None, d_value, None, None, None,
+        return (None, d_query, d_ref, d_value, None, None, None,
                 dw_q[:, :2 * tp].contiguous(), db_q[:2 * tp].contiguous(), dw_q[:, 2 * tp:].contiguous(),
                 db_q[2 * tp:].contiguous(), dw_val, db_val, dw_out, db_out)
 
@@ -247,11 +300,25 @@ class MSDeformableAttention(nn.Module):
         self._packed = (ver, packed)
         return packed
 
+    def fused_qproj_ok(self):
+        """The tcgen05 MSDA_QPROJ epilogue (offsets + softmax in the GEMM) is built for EMRT's 8 x 3 x 6 = 144 points;
+        every other configuration (e.g. the constructor's own 4 levels x 4 points) takes the generic GEMM +
+        emrt_msda_softmax_loc."""
+        return self.total_points == 144 and self.num_levels * self.num_points == 18 and self.embed_dim % 8 == 0
+
     # -- forward -----------------------------------------------------------------------------------------
-    def forward(self, query, reference_points, value, value_spatial_shapes, value_mask=None):
+    def forward(self, query, reference_points, value, value_spatial_shapes, value_mask=None, *, query_pos=None,
+                residual_norm=None):
         """
         query [bs, Lq, C]; reference_points [bs, Lq, n_levels, 2] in [0,1]; value [bs, Lv, C];
         value_spatial_shapes [n_levels, 2] (H, W); value_mask [bs, Lv] (non-zero = keep)  ->  [bs, Lq, C]
+
+        Two optional keyword extensions used by this package's own encoder / decoder layers (the reference signature,
+        t_e_d.py:65, is the positional part):
+          query_pos      [1, Lq, C] — the position embedding of `with_pos_embed` (:154-155); the query projection then
+                         computes (query + query_pos) W as query W + query_pos W inside one GEMM, no add kernel;
+          residual_norm  (residual, gamma, beta) — returns LayerNorm(output + residual) * gamma + beta (:199-200),
+                         evaluated in the output projection's epilogue.
         """
         bs, Len_q = query.shape[:2]
         Len_v = value.shape[1]
@@ -262,21 +329,29 @@ class MSDeformableAttention(nn.Module):
             raise L.EmrtError("emrt_b200.MSDeformableAttention needs CUDA tensors (no CPU fallback)")
         if query.dtype not in (torch.float32, torch.bfloat16):
             raise L.EmrtError(f"unsupported dtype {query.dtype}")
-        if torch.is_grad_enabled() and (query.requires_grad or value.requires_grad
+        if torch.is_grad_enabled() and (query.requires_grad or value.requires_grad or reference_points.requires_grad
                                         or any(p.requires_grad for p in self.parameters())):
             mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
-            ref32 = reference_points.detach().float().contiguous()
-            grid = bool(getattr(reference_points, "pixel_grid", False))
-            return _MSDAFunction.apply(self, query, ref32, value, mask, shapes, grid,
-                                       self.sampling_offsets.weight, self.sampling_offsets.bias,
-                                       self.attention_weights.weight, self.attention_weights.bias,
-                                       self.value_proj.weight, self.value_proj.bias,
-                                       self.output_proj.weight, self.output_proj.bias)
+            ref32 = reference_points.float().contiguous()        # differentiable: the decoder trains its reference points
+            grid = is_pixel_grid(reference_points, shapes, Len_q, Len_v)
+            if query_pos is not None:
+                query = query + query_pos.to(query.dtype)
+            out = _MSDAFunction.apply(self, query, ref32, value, mask, shapes, grid,
+                                      self.sampling_offsets.weight, self.sampling_offsets.bias,
+                                      self.attention_weights.weight, self.attention_weights.bias,
+                                      self.value_proj.weight, self.value_proj.bias,
+                                      self.output_proj.weight, self.output_proj.bias)
+            if residual_norm is not None:
+                raise L.EmrtError("residual_norm is an inference-path fusion; the training path composes norm1 itself")
+            return out
         if query.dtype == torch.float32:
-            return self._forward_fp32(query, reference_points, value, shapes, value_mask)
-        if query.dtype == torch.bfloat16:
-            return self._forward_bf16(query, reference_points, value, shapes, value_mask)
-        raise L.EmrtError(f"unsupported dtype {query.dtype}")
+            if query_pos is not None:
+                query = ops.add_bcast(query.contiguous(), query_pos.to(query.dtype).contiguous())
+            out = self._forward_fp32(query, reference_points, value, shapes, value_mask)
+            if residual_norm is not None:
+                out = ops.residual_layernorm(out, residual_norm[0], residual_norm[1], residual_norm[2], out=out)
+            return out
+        return self._forward_bf16(query, reference_points, value, shapes, value_mask, query_pos, residual_norm)
 
     def _forward_fp32(self, query, ref, value, shapes, value_mask):
         M, P, D = self.num_heads, self.num_points, self.head_dim
@@ -293,36 +368,51 @@ class MSDeformableAttention(nn.Module):
         out = ops.msda_gather_fwd(v.view(bs, -1, M, D), loc, attn, shapes, mode=L.LOC_NORMALIZED)
         return ops.linear(out, self.output_proj.weight.detach(), self.output_proj.bias.detach(), impl=L.IMPL_SIMT)
 
-    def _forward_bf16(self, query, ref, value, shapes, value_mask):
+    def _forward_bf16(self, query, ref, value, shapes, value_mask, query_pos=None, residual_norm=None):
         M, P, D = self.num_heads, self.num_points, self.head_dim
         LP = self.num_levels * P
         bs, Len_q = query.shape[:2]
         pk = self.packed_weights()
         mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
         impl = self.gemm_impl
+        tc = impl != L.IMPL_SIMT
+        x2, x2_period = None, 0
+        if query_pos is not None:
+            if tc and query_pos.numel() == Len_q * self.embed_dim:
+                x2, x2_period = ops.cyclic_rows_cached(query_pos), Len_q
+            else:
+                query = ops.add_bcast(query.contiguous(), query_pos.to(query.dtype).contiguous())
         # head-major value layout [B,M,Lv,D]: written by the value_proj epilogue, read by the specialised gather
         head_major = (impl != L.IMPL_SIMT and self.head_major and D == 32 and self.num_levels == 3 and P == 6)
         epi = (L.EPI_ROW_MASK if mask is not None else L.EPI_NONE) | (L.EPI_HEAD_MAJOR if head_major else 0)
         v = ops.linear(value.contiguous(), pk["wv"], pk["bv"], w_transposed=True, epilogue=epi, row_scale=mask,
                        impl=impl, hm_rows=value.shape[1] if head_major else 0, hm_D=D if head_major else 0)
         ref32 = ref if (ref.dtype == torch.float32 and ref.is_contiguous()) else ref.float().contiguous()
-        if impl == L.IMPL_SIMT:
+        if not tc or not self.fused_qproj_ok():
             raw = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float32,
-                             impl=L.IMPL_SIMT)
+                             impl=impl, x2=x2, x2_period=x2_period)
             tp2 = 2 * self.total_points
             off_px, attn = ops.msda_softmax_loc(raw[..., :tp2], raw[..., tp2:], shapes, M, P, out_dtype=torch.float16,
                                                 mode=L.LOC_PIXEL_OFFSET)
         else:
-            off_px, attn = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True,
-                                      y_dtype=torch.float16, epilogue=L.EPI_MSDA_QPROJ, qproj_group=LP, impl=impl)
+            off_px, attn = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float16,
+                                      epilogue=L.EPI_MSDA_QPROJ, qproj_group=LP, impl=impl, x2=x2, x2_period=x2_period)
             off_px = off_px.view(bs, Len_q, M, self.num_levels, P, 2)
             attn = attn.view(bs, Len_q, M, self.num_levels, P)
         if head_major:
             # encoder self-attention (queries = the pyramid's own pixels): window-staged kernel
-            grid = L.QUERY_PIXEL_GRID if (getattr(ref, "pixel_grid", False) and Len_q == value.shape[1]) else 0
+            grid = L.QUERY_PIXEL_GRID if is_pixel_grid(ref, shapes, Len_q, value.shape[1]) else 0
             out = ops.msda_gather_fwd(v.view(bs, M, -1, D), off_px, attn, shapes, ref=ref32,
                                       mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR | grid,
                                       win_center=pk["win_center"] if grid else None)
         else:
             out = ops.msda_gather_fwd(v.view(bs, -1, M, D), off_px, attn, shapes, ref=ref32, mode=L.LOC_PIXEL_OFFSET)
-        return ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl)
+        if residual_norm is None:
+            return ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl)
+        res, gamma, beta = residual_norm
+        if tc and self.embed_dim == 256:
+            # output_proj + residual + LayerNorm in one kernel (t_e_d.py:106,199-200): the fp32 accumulator is normalised
+            return ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl, epilogue=L.EPI_RESIDUAL_LN,
+                              residual=res, ln_gamma=gamma, ln_beta=beta, out=out)
+        o = ops.linear(out, pk["wo"], pk["bo"], w_transposed=True, impl=impl)
+        return ops.residual_layernorm(o, res, gamma, beta, out=o)

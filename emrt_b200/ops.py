@@ -127,8 +127,9 @@ def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NOR
 # ---- nn.Linear -----------------------------------------------------------------------------------------------
 def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_NONE, row_scale=None, residual=None,
            ln_gamma=None, ln_beta=None, ln_eps=1e-5, qproj_group=0, impl=L.IMPL_AUTO, out=None, out2=None, hm_rows=0,
-           hm_D=0):
-    """y = epilogue(x @ W + bias).  x [..., K]; W [K,N] (Paddle layout) or [N,K] when w_transposed."""
+           hm_D=0, x2=None, x2_period=0):
+    """y = epilogue((x + x2) @ W + bias).  x [..., K]; W [K,N] (Paddle layout) or [N,K] when w_transposed.
+    x2 (optional, tcgen05 path): `cyclic_rows(addend, ...)` of a [x2_period, K] broadcast addend (with_pos_embed)."""
     lib = L.load()
     K = x.shape[-1]
     rows = x.numel() // K
@@ -154,9 +155,35 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     a.qproj_group = int(qproj_group)
     a.impl = int(impl)
     a.hm_rows, a.hm_D = int(hm_rows), int(hm_D)
+    a.x2, a.x2_period = _ptr(x2), int(x2_period)
+    if x2 is not None:
+        assert x2.dtype == torch.bfloat16 and x2.shape[-1] == K and x2.numel() // K >= x2_period + 127
     with _Timed("linear", (rows, K, N, x.element_size(), out.element_size())):
         L.check(lib.emrt_linear_fwd(C.byref(a), _stream()))
     return (out, out2) if (epilogue & L.EPI_MSDA_QPROJ) else out
+
+
+def cyclic_rows(addend, extra=127):
+    """[period, K] -> bf16 [period + extra, K]: the rows continued cyclically (the x2 operand of `linear`)."""
+    period = addend.shape[0]
+    idx = torch.arange(period + extra, device=addend.device) % period
+    return addend.to(torch.bfloat16).index_select(0, idx).contiguous()
+
+
+_cyc_cache = {}
+
+
+def cyclic_rows_cached(addend):
+    """`cyclic_rows` remembered for as long as that very tensor object is alive and unmodified."""
+    import weakref
+    hit = _cyc_cache.get(id(addend))
+    if hit is not None and hit[0]() is addend and hit[1] == addend._version:
+        return hit[2]
+    val = cyclic_rows(addend.reshape(-1, addend.shape[-1]))
+    if len(_cyc_cache) > 64:
+        _cyc_cache.clear()
+    _cyc_cache[id(addend)] = (weakref.ref(addend), addend._version, val)
+    return val
 
 
 def pack_weight(src, dst, dst_row0=0):
@@ -205,6 +232,15 @@ def msda_qproj_bwd(grad_loc, grad_attn, attn, shapes, M, P, out_dtype=torch.floa
     L.check(L.load().emrt_msda_qproj_bwd(_ptr(grad_loc), _ptr(grad_attn), _ptr(attn), _ptr(dq), rows, M, nL, P, hw,
                                          _dt(attn), _DT[out_dtype], mode, _stream()))
     return dq
+
+
+def msda_ref_bwd(grad_loc, shapes, ref_batches, mode=L.LOC_NORMALIZED):
+    """grad_loc f32 [B,Lq,M,L,P,2] -> grad of the reference points f32 [ref_batches,Lq,L,2] (t_e_d.py:98-102)."""
+    B, Lq, M, nL, P, _ = grad_loc.shape
+    hw, _, _ = level_tables(shapes)
+    out = torch.empty((ref_batches, Lq, nL, 2), dtype=torch.float32, device=grad_loc.device)
+    L.check(L.load().emrt_msda_ref_bwd(_ptr(grad_loc), _ptr(out), B, ref_batches, Lq, M, nL, P, hw, mode & 1, _stream()))
+    return out
 
 
 def scale_rows_cast(src, row_scale, out_dtype):

@@ -122,7 +122,8 @@ int emrt_msda_gather_bwd_hint(const void* grad_out, const void* value, const voi
  * (w_transposed = 0) or pre-packed [N,K] (w_transposed = 1, see emrt_pack_weight).  x_dtype F32 runs the
  * fp32 SIMT path (parity mode); BF16 runs the tcgen05/TMEM/TMA path (w must then be BF16 [N,K]).
  * bias is always F32 [N].  y_dtype: F32|BF16|F16.  Extra operands by epilogue flag:
- *   ROW_MASK: row_scale F32 [rows];  RESIDUAL_LN: residual (x_dtype) [rows,N], ln_gamma/ln_beta F32 [N];
+ *   ROW_MASK: row_scale F32 [rows];  RESIDUAL_LN: residual (x_dtype) [rows,N], ln_gamma/ln_beta F32 [N] (BF16 /
+ *               tcgen05 only, N = 256, K % 64 == 0; y may alias residual or x);
  *   MSDA_QPROJ: y = pixel offsets [rows, 2N/3] (y_dtype), y2 = softmax'd weights [rows, N/3] (y_dtype),
  *               softmax group = qproj_group (= L*P).                                                      */
 typedef struct emrt_linear_args {
@@ -135,6 +136,11 @@ typedef struct emrt_linear_args {
   void* y2; int32_t qproj_group;
   int32_t impl;               /* 0 = auto, 1 = force SIMT, 2 = force tcgen05 */
   int32_t hm_rows; int32_t hm_D;   /* HEAD_MAJOR: rows per batch element (Lv) and head dim */
+  /* Optional broadcast addend of x (with_pos_embed, transformer_encoder_decoder.py:154-155,198,283,288):
+   * y = epilogue((x[r,:] + x2[r % x2_period,:]) @ W + bias), evaluated as x W + x2 W in the fp32 accumulator (the sum is
+   * never rounded to bf16 and never written).  x2 is BF16 [x2_period + 127, K]: the x2_period rows of the addend
+   * continued cyclically for 127 more rows, so that any 128-row tile reads one contiguous box.  tcgen05 path only. */
+  const void* x2; int32_t x2_period;
 } emrt_linear_args;
 int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 
@@ -154,6 +160,14 @@ int emrt_linear_bwd_weight(const void* x, const void* dy, float* dw, float* db, 
 int emrt_msda_qproj_bwd(const float* grad_loc, const float* grad_attn, const void* attn, void* dq, int64_t rows,
                         int M, int L, int P, const int32_t* shapes_hw_host, int attn_dtype, int dq_dtype, int mode,
                         void* stream);
+
+/* Gradient of the reference points (sampling_locations = reference_points[:, :, None, :, None, :] + offsets / (W_l, H_l),
+ * transformer_encoder_decoder.py:98-102; the decoder's reference points are a trained Linear + sigmoid, :466-467):
+ * grad_ref F32 [ref_batches, Lq, L, 2] = sum over heads and points of grad_loc F32 [B, Lq, M, L, P, 2] (times (W_l, H_l)
+ * in PIXEL_OFFSET mode, where grad_loc is per pixel), summed over the batch in a fixed order when ref_batches == 1.
+ * Overwrites grad_ref.                                                                                               */
+int emrt_msda_ref_bwd(const float* grad_loc, float* grad_ref, int B, int ref_batches, int Lq, int M, int L, int P,
+                      const int32_t* shapes_hw_host, int mode, void* stream);
 
 /* dst[r,c] = src[r,c] * row_scale[r] (row_scale may be NULL): value_mask backward + cast of the fp32 grad_value
  * (transformer_encoder_decoder.py:84-86).  dst_dtype F32|BF16; cols % 4 == 0.                                       */

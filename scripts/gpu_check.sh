@@ -1,15 +1,37 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, smoke, a short bench, an ncu launch list and one full capture of the gather.
-# usage: scripts/gpu_check.sh <tag> [bench flags...]
-TAG=${1:-run}; shift
+# One GPU lease = one call of this script (gpurun -- 'bash scripts/gpu_check.sh TAG [what ...]').
+#   tests      all GPU tests (+ smoke)            quick     only the tests named in $EMRT_QUICK_TESTS
+#   bench      default bench + reference arm      launches  ncu launch list of a 2-step bench -> TAG_launches.{csv,md}
+#   gather     ncu --set full of the window gather ln        ncu --set full of the fused Linear + LayerNorm GEMM
+#   train      cfg-4 training step                micro     shared-memory-pipe floor microbenchmark
+# Everything lands in gpurun_out/TAG_*; the summaries worth keeping are copied to profiles/ by hand.
+TAG=${1:-x}; shift
+WHAT=${@:-tests bench launches}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
-python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -40 > gpurun_out/${TAG}_pytest.log
-python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -60 > gpurun_out/${TAG}_pytest_all.log
-python __graft_entry__.py --smoke > gpurun_out/${TAG}_smoke.log 2>&1
-python bench.py --steps 10 --warmup 3 "$@" > gpurun_out/${TAG}_bench.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline "$@" > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_gather_fwd -s 4 -c 1 -f -o gpurun_out/${TAG}_gather \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline "$@" > gpurun_out/${TAG}_ncu_gather.log 2>&1
-tail -5 gpurun_out/${TAG}_pytest_all.log; cat gpurun_out/${TAG}_smoke.log | tail -3; tail -2 gpurun_out/${TAG}_bench.log
+for w in $WHAT; do
+case $w in
+quick)
+  timeout 900 python -m pytest $EMRT_QUICK_TESTS -m gpu -q -x --timeout 600 2>&1 | tail -25 | tee gpurun_out/${TAG}_quick.log ;;
+tests)
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -25 > gpurun_out/${TAG}_pytest.log; tail -6 gpurun_out/${TAG}_pytest.log
+  python __graft_entry__.py --smoke 2>&1 | tail -1 ;;
+bench)
+  timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 600 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>/dev/null; tail -c 200 gpurun_out/${TAG}_bench_reference.json ;;
+launches)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/${TAG}_launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > /dev/null 2>&1
+  python scripts/launch_summary.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches.md; head -24 gpurun_out/${TAG}_launches.md ;;
+gather)
+  timeout 600 ncu --set full --clock-control none --import-source on -f -k regex:msda_gather_fwd_win -s 1 -c 1 -o gpurun_out/${TAG}_gather_win \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > /dev/null 2>&1 ;;
+ln)
+  timeout 600 ncu --set full --clock-control none --import-source on -f -k regex:linear_ln_tcgen05 -s 1 -c 1 -o gpurun_out/${TAG}_linear_ln \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > /dev/null 2>&1 ;;
+train)
+  timeout 600 python scripts/bench_train.py --steps 10 2>&1 | tail -1 | tee gpurun_out/${TAG}_train.json ;;
+micro)
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/lds_floor scripts/microbench/lds_gather_floor.cu && /tmp/lds_floor | tee gpurun_out/${TAG}_lds_floor.txt ;;
+*) echo "unknown step $w" ;;
+esac
+done
