@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--images", type=int, default=8, help="1024x1024 scenes per GPU per step (9 windows each)")
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records measured after the main timing "
+                    "(cfg-4 training step, cfg-5 scene, cfg-2 tiles, copy ceiling, gather sensitivity)")
     ap.add_argument("--cpu-sample-windows", type=int, default=8)
     ap.add_argument("--msda-only", action="store_true", help="round-1 starting definition: 4 + 2 bare MSDA calls + head tail")
     ap.add_argument("--tokens", action="store_true", help="earlier definition: token inputs, encoder + 2 bare decoder MSDA + head tail")

@@ -33,6 +33,7 @@ class LinearArgs(C.Structure):
         ("impl", C.c_int32),
         ("hm_rows", C.c_int32), ("hm_D", C.c_int32),
         ("x2", C.c_void_p), ("x2_period", C.c_int32),
+        ("row_bias", C.c_void_p), ("row_bias_period", C.c_int32),
     ]
 
 

@@ -31,6 +31,12 @@ constexpr int MAX_RES_KB = 4;  // weight-stationary mode: K <= 256
 
 enum { EPI_KIND_GENERIC = 0, EPI_KIND_QPROJ = 1 };
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 struct GemmParams {
   CUtensorMap tma_a;   // x  [rows, K] bf16, box {64, 128}
   CUtensorMap tma_b;   // Wt [N, K]    bf16, box {64, BLOCK_N}
@@ -38,6 +44,8 @@ struct GemmParams {
   CUtensorMap tma_y2;  // staged epilogue, QPROJ only: y2
   CUtensorMap tma_a2;  // x2 [x2_period + 127, K] bf16 (cyclic), box {64, 128}: the broadcast addend of x (with_pos_embed)
   int32_t a2_period;   // 0 = no x2
+  CUtensorMap tma_rb;  // QPROJ only: row_bias [rb_period + 127, N] F16 (cyclic), box {BLOCK_N / 2, 32}
+  int32_t rb_period;   // 0 = no row bias
   const float* bias;
   const float* row_scale;
   void* y;
@@ -55,11 +63,13 @@ struct GemmParams {
 //   QPROJ:   32 rows x 72 columns x 2 B = 144-byte rows, no swizzle (36-bank row stride is conflict-free as is)
 template <int EPI> struct StageBytes { static constexpr int value = EPI == EPI_KIND_QPROJ ? 32 * 144 : 32 * 64; };
 
-template <int BLOCK_N, int STAGES, bool B_RES, int EPI, bool TMA_ST>
+template <int BLOCK_N, int STAGES, bool B_RES, int EPI, bool TMA_ST, bool ROWB>
 struct GemmSmem {
   __nv_bfloat16 a[STAGES][BM * BK];
   __nv_bfloat16 b[B_RES ? MAX_RES_KB : STAGES][BLOCK_N * BK];
   uint8_t stage[TMA_ST ? NUM_EPI_WARPS * StageBytes<EPI>::value : 16];
+  uint8_t rowb[ROWB ? NUM_EPI_WARPS * 32 * BLOCK_N : 16];   // per epilogue warp: 32 rows x BLOCK_N / 2 fp16 row-bias values
+  uint64_t rb_full[NUM_EPI_WARPS];
   float bias[BLOCK_N];
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
@@ -88,13 +98,13 @@ struct TileWalk {
   }
 };
 
-template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST>
+template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST, bool ROWB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
   static_assert((BLOCK_N * BK * 2) % 1024 == 0, "B stage must keep 1024-byte alignment");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using Smem = GemmSmem<BLOCK_N, STAGES, B_RES, EPI, TMA_ST>;
+  using Smem = GemmSmem<BLOCK_N, STAGES, B_RES, EPI, TMA_ST, ROWB>;
   // 1024-byte alignment (SWIZZLE_128B atoms) by offsetting inside the shared window: keeps the address space known
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
@@ -113,6 +123,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     mbar_init(&s.b_full, 1);
 #pragma unroll
     for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], NUM_EPI_WARPS); }
+    if (ROWB) { tma_prefetch_desc(&p.tma_rb); for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&s.rb_full[w], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -191,6 +202,20 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     int bias_n = -1;
+    // Row bias (QPROJ): the position embedding's contribution pos W + b, a [period, N] table shared by the whole batch
+    // ((x + pos) W + b = x W + (pos W + b), t_e_d.py:154-155,198) — added to the fp32 accumulator, so x + pos is never
+    // formed, rounded or written.  Each warp fetches its 32 x HALF_N box by TMA one tile ahead.
+    const int ew = warp - EPI_WARP0;
+    uint32_t rb_phase = 0;
+    auto load_rb = [&](const TileWalk& t) {      // lane 0 only
+      mbar_arrive_expect_tx(&s.rb_full[ew], 32u * BLOCK_N);
+      tma_load_2d(s.rowb + ew * 32 * BLOCK_N, &p.tma_rb, &s.rb_full[ew], t.n * BLOCK_N + half * HALF_N,
+                  (int)(((int64_t)t.m * BM + q * 32) % p.rb_period));
+    };
+    if (ROWB && lane == 0) {
+      TileWalk t0(B_RES, p.tiles_m, p.tiles_n);
+      if (t0.valid()) load_rb(t0);
+    }
     for (TileWalk tw(B_RES, p.tiles_m, p.tiles_n); tw.valid(); tw.next()) {
       const int n0 = tw.n * BLOCK_N;
       if (tw.n != bias_n) {
@@ -290,8 +315,33 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         uint32_t r[HALF_N / 8][8];
 #pragma unroll
         for (int c = 0; c < HALF_N / 8; ++c) TMEM_LD_X8(t_row + c * 8, r[c]);
+        if constexpr (ROWB) {
+          mbar_wait(&s.rb_full[ew], rb_phase);
+          rb_phase ^= 1u;
+        }
 #pragma unroll
         for (int c = 0; c < HALF_N / 8; ++c) TMEM_WAIT_X8(r[c]);
+        if constexpr (ROWB) {
+          // this lane's row of the box: HALF_N fp16 = HALF_N * 2 bytes (144: a 36-bank stride, conflict-free as is)
+          const uint32_t rb = smem_u32(s.rowb) + (uint32_t)(ew * 32 * BLOCK_N + lane * (HALF_N * 2));
+#pragma unroll
+          for (int c = 0; c < HALF_N / 8; ++c) {
+            const uint4 h = lds128(rb + c * 16);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+              r[c][2 * i] = __float_as_uint(__uint_as_float(r[c][2 * i]) + f.x);
+              r[c][2 * i + 1] = __float_as_uint(__uint_as_float(r[c][2 * i + 1]) + f.y);
+            }
+          }
+          __syncwarp();                        // every lane has read the box: fetch the next tile's
+          if (lane == 0) {
+            TileWalk nx = tw;
+            nx.next();
+            if (nx.valid()) load_rb(nx);
+          }
+        }
         const uint32_t stage = smem_u32(s.stage) + (uint32_t)(warp - EPI_WARP0) * StageBytes<EPI>::value;
         const int row0 = tw.m * BM + q * 32;
         if (tw.n < 2) {
@@ -412,15 +462,20 @@ static int make_tma_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST>
+template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST, bool ROWB = false>
 static int launch_tc(GemmParams& p, const emrt_linear_args* a, cudaStream_t st) {
-  using Smem = GemmSmem<BLOCK_N, STAGES, B_RES, EPI, TMA_ST>;
+  using Smem = GemmSmem<BLOCK_N, STAGES, B_RES, EPI, TMA_ST, ROWB>;
   constexpr int smem_bytes = (int)sizeof(Smem) + 1024;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
   if (int e = make_tma_2d(&p.tma_a, a->x, (uint64_t)a->K, (uint64_t)a->rows, BM)) return e;
   if (int e = make_tma_2d(&p.tma_b, a->w, (uint64_t)a->K, (uint64_t)a->N, BLOCK_N)) return e;
   if (p.a2_period)
     if (int e = make_tma_2d(&p.tma_a2, a->x2, (uint64_t)a->K, (uint64_t)a->x2_period + BM - 1, BM)) return e;
+  if (ROWB) {
+    const uint64_t d[2] = {(uint64_t)a->N, (uint64_t)a->row_bias_period + BM - 1}, sb[1] = {(uint64_t)a->N * 2};
+    const uint32_t box[2] = {(uint32_t)(BLOCK_N / 2), 32u};
+    if (int e = make_tensor_map(&p.tma_rb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a->row_bias, d, sb, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+  }
   if (TMA_ST) {
     const CUtensorMapDataType dt = a->y_dtype == EMRT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (EPI == EPI_KIND_QPROJ) {
@@ -442,7 +497,7 @@ static int launch_tc(GemmParams& p, const emrt_linear_args* a, cudaStream_t st) 
   }
   p.tiles_m = (int)((a->rows + BM - 1) / BM);
   p.tiles_n = (a->N + BLOCK_N - 1) / BLOCK_N;
-  auto kern = linear_tcgen05_kernel<BLOCK_N, STAGES, EPI, GROUP, B_RES, TMA_ST>;
+  auto kern = linear_tcgen05_kernel<BLOCK_N, STAGES, EPI, GROUP, B_RES, TMA_ST, ROWB>;
   // function attributes are per device / context: set every time (cheap), not once per process
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid;
@@ -512,8 +567,15 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
     if (!a->y2 || a->qproj_group != 18)
       return set_error(EMRT_ERR_UNSUPPORTED, "MSDA_QPROJ needs y2 and softmax group L*P = 18 (EMRT: 3 levels x 6 points), got %d", a->qproj_group);
     if ((reinterpret_cast<uintptr_t>(a->y2) & 15) != 0) tma_st = false;
+    if (a->row_bias) {
+      if (a->row_bias_period <= 0 || (reinterpret_cast<uintptr_t>(a->row_bias) & 15) || !res || !tma_st)
+        return set_error(EMRT_ERR_UNSUPPORTED, "row_bias needs row_bias_period > 0, a 16-byte aligned F16 table, K <= 256 and 2-byte outputs");
+      p.rb_period = a->row_bias_period;
+      return launch_tc<144, 4, EPI_KIND_QPROJ, 18, true, true, true>(p, a, st);
+    }
     return pick_tc<144, 6, 8, 6, EPI_KIND_QPROJ, 18>(p, a, res, tma_st, st);
   }
+  if (a->row_bias) return set_error(EMRT_ERR_UNSUPPORTED, "row_bias is built into the MSDA_QPROJ epilogue only");
   if (a->epilogue & ~(EMRT_EPI_ROW_MASK | EMRT_EPI_RELU | EMRT_EPI_HEAD_MAJOR))
     return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 linear: unsupported epilogue flags %d", a->epilogue);
   if (a->N <= 64) return pick_tc<64, 8, 8, 8, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);

@@ -306,6 +306,23 @@ class MSDeformableAttention(nn.Module):
         emrt_msda_softmax_loc."""
         return self.total_points == 144 and self.num_levels * self.num_points == 18 and self.embed_dim % 8 == 0
 
+    def _query_pos_bias(self, query_pos, Len_q):
+        """F16 [Len_q + 127, 3*MLP] = query_pos @ [sampling_offsets.weight | attention_weights.weight] + their biases (fp32
+        SIMT GEMM on the fp32 weights), continued cyclically: the row_bias operand of the fused query projection.  A
+        function of the position embedding and the weights only — computed once per (tensor, weights version)."""
+        key = (id(query_pos), query_pos._version, self._weights_version())
+        hit = getattr(self, "_rowb", None)
+        if hit is not None and hit[0] == key and hit[1]() is query_pos:
+            return hit[2]
+        with torch.no_grad():
+            w = torch.cat([self.sampling_offsets.weight.detach(), self.attention_weights.weight.detach()], 1).float().contiguous()
+            b = torch.cat([self.sampling_offsets.bias.detach(), self.attention_weights.bias.detach()]).float().contiguous()
+            tab = ops.linear(query_pos.detach().reshape(Len_q, self.embed_dim).float().contiguous(), w, b,
+                             y_dtype=torch.float16, impl=L.IMPL_SIMT)
+            tab = ops.cyclic_rows(tab, dtype=torch.float16)
+        self._rowb = (key, weakref.ref(query_pos), tab)
+        return tab
+
     # -- forward -----------------------------------------------------------------------------------------
     def forward(self, query, reference_points, value, value_spatial_shapes, value_mask=None, *, query_pos=None,
                 residual_norm=None):
@@ -376,10 +393,13 @@ class MSDeformableAttention(nn.Module):
         mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
         impl = self.gemm_impl
         tc = impl != L.IMPL_SIMT
-        x2, x2_period = None, 0
+        x2, x2_period, rowb = None, 0, None
         if query_pos is not None:
             if tc and query_pos.numel() == Len_q * self.embed_dim:
-                x2, x2_period = ops.cyclic_rows_cached(query_pos), Len_q
+                if self.fused_qproj_ok():
+                    rowb = self._query_pos_bias(query_pos, Len_q)      # (query + pos) Wq + bq = query Wq + (pos Wq + bq)
+                else:
+                    x2, x2_period = ops.cyclic_rows_cached(query_pos), Len_q
             else:
                 query = ops.add_bcast(query.contiguous(), query_pos.to(query.dtype).contiguous())
         # head-major value layout [B,M,Lv,D]: written by the value_proj epilogue, read by the specialised gather
@@ -395,8 +415,9 @@ class MSDeformableAttention(nn.Module):
             off_px, attn = ops.msda_softmax_loc(raw[..., :tp2], raw[..., tp2:], shapes, M, P, out_dtype=torch.float16,
                                                 mode=L.LOC_PIXEL_OFFSET)
         else:
-            off_px, attn = ops.linear(query.contiguous(), pk["wq"], pk["bq"], w_transposed=True, y_dtype=torch.float16,
-                                      epilogue=L.EPI_MSDA_QPROJ, qproj_group=LP, impl=impl, x2=x2, x2_period=x2_period)
+            off_px, attn = ops.linear(query.contiguous(), pk["wq"], None if rowb is not None else pk["bq"], w_transposed=True,
+                                      y_dtype=torch.float16, epilogue=L.EPI_MSDA_QPROJ, qproj_group=LP, impl=impl,
+                                      row_bias=rowb, row_bias_period=Len_q if rowb is not None else 0)
             off_px = off_px.view(bs, Len_q, M, self.num_levels, P, 2)
             attn = attn.view(bs, Len_q, M, self.num_levels, P)
         if head_major:

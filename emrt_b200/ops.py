@@ -127,7 +127,7 @@ def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NOR
 # ---- nn.Linear -----------------------------------------------------------------------------------------------
 def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_NONE, row_scale=None, residual=None,
            ln_gamma=None, ln_beta=None, ln_eps=1e-5, qproj_group=0, impl=L.IMPL_AUTO, out=None, out2=None, hm_rows=0,
-           hm_D=0, x2=None, x2_period=0):
+           hm_D=0, x2=None, x2_period=0, row_bias=None, row_bias_period=0):
     """y = epilogue((x + x2) @ W + bias).  x [..., K]; W [K,N] (Paddle layout) or [N,K] when w_transposed.
     x2 (optional, tcgen05 path): `cyclic_rows(addend, ...)` of a [x2_period, K] broadcast addend (with_pos_embed)."""
     lib = L.load()
@@ -156,6 +156,9 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     a.impl = int(impl)
     a.hm_rows, a.hm_D = int(hm_rows), int(hm_D)
     a.x2, a.x2_period = _ptr(x2), int(x2_period)
+    a.row_bias, a.row_bias_period = _ptr(row_bias), int(row_bias_period)
+    if row_bias is not None:
+        assert row_bias.dtype == torch.float16 and row_bias.shape[-1] == N and row_bias.numel() // N >= row_bias_period + 127
     if x2 is not None:
         assert x2.dtype == torch.bfloat16 and x2.shape[-1] == K and x2.numel() // K >= x2_period + 127
     with _Timed("linear", (rows, K, N, x.element_size(), out.element_size())):
@@ -163,11 +166,12 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     return (out, out2) if (epilogue & L.EPI_MSDA_QPROJ) else out
 
 
-def cyclic_rows(addend, extra=127):
-    """[period, K] -> bf16 [period + extra, K]: the rows continued cyclically (the x2 operand of `linear`)."""
+def cyclic_rows(addend, extra=127, dtype=torch.bfloat16):
+    """[period, K] -> `dtype` [period + extra, K]: the rows continued cyclically (the x2 / row_bias operand of `linear`:
+    any 128-row tile of a [B * period, .] activation then reads its addend rows as one contiguous box)."""
     period = addend.shape[0]
     idx = torch.arange(period + extra, device=addend.device) % period
-    return addend.to(torch.bfloat16).index_select(0, idx).contiguous()
+    return addend.to(dtype).index_select(0, idx).contiguous()
 
 
 _cyc_cache = {}

@@ -141,6 +141,10 @@ typedef struct emrt_linear_args {
    * never rounded to bf16 and never written).  x2 is BF16 [x2_period + 127, K]: the x2_period rows of the addend
    * continued cyclically for 127 more rows, so that any 128-row tile reads one contiguous box.  tcgen05 path only. */
   const void* x2; int32_t x2_period;
+  /* The same addend for a projection whose weights are fixed between calls, precomputed: row_bias F16
+   * [row_bias_period + 127, N] = x2 W + bias (cyclic like x2; pass bias = NULL), added to the fp32 accumulator in the
+   * epilogue — (x + pos) W + b = x W + (pos W + b) with no extra MMA work.  MSDA_QPROJ epilogue only.            */
+  const void* row_bias; int32_t row_bias_period;
 } emrt_linear_args;
 int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 
