@@ -158,7 +158,7 @@ class MSDeformableAttention(nn.Layer):
         self.attention_weights = nn.Linear(embed_dim, self.total_points)
         self.value_proj = nn.Linear(embed_dim, embed_dim)
         self.output_proj = nn.Linear(embed_dim, embed_dim)
-        self._packed = None
+        self._packed, self._packed_ver = None, None
         self._reset_parameters()
 
     def _reset_parameters(self):   # transformer_encoder_decoder.py:46-63
@@ -176,10 +176,19 @@ class MSDeformableAttention(nn.Layer):
             lin.weight.set_value(paddle.uniform(lin.weight.shape, min=-bound, max=bound))
             lin.bias.set_value(paddle.zeros_like(lin.bias))
 
+    def _weights_version(self):
+        """(device pointer, in-place version) of the 8 parameters: set_value / set_state_dict / an optimiser step bump
+        the version, a re-allocated parameter changes the pointer — either way the packs below are rebuilt."""
+        ps = (self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
+              self.attention_weights.bias, self.value_proj.weight, self.value_proj.bias, self.output_proj.weight,
+              self.output_proj.bias)
+        return tuple((int(p.data_ptr()), int(getattr(p, "inplace_version", 0))) for p in ps)
+
     def _packed_weights(self):
-        """bf16 K-major [out,in] operands (emrt_pack_weight); re-packed when the module is told weights changed
-        (call ``invalidate_packed()`` after loading a checkpoint or an optimiser step)."""
-        if self._packed is not None:
+        """bf16 K-major [out,in] operands (emrt_pack_weight), rebuilt whenever a parameter changed (same rule as the torch
+        adapter's MSDeformableAttention.packed_weights); ``invalidate_packed()`` forces it."""
+        ver = self._weights_version()
+        if self._packed is not None and self._packed_ver == ver:
             return self._packed
         C_, tp = self.embed_dim, self.total_points
         lib = L.load()
@@ -197,6 +206,7 @@ class MSDeformableAttention(nn.Layer):
         bq = paddle.concat([self.sampling_offsets.bias, self.attention_weights.bias]).astype("float32")
         self._packed = dict(wv=wv, wq=wq, wo=wo, bv=self.value_proj.bias.astype("float32"), bq=bq,
                             bo=self.output_proj.bias.astype("float32"))
+        self._packed_ver = ver
         return self._packed
 
     def invalidate_packed(self):
@@ -252,6 +262,61 @@ def _stitch_argmax_fused(half_logits, win_img, win_y0, win_x0, n_img, H, W, labe
     return labels
 
 
+def _ss_slide_fused(model, imgs, img_hw, crop_size, stride_size, window_batch=64):
+    """val.py:145's call when the model exposes ``forward_half_logits`` (install_half_logits below): the windows' class
+    logits BEFORE UpHead's last x2 upsample go through the fused upsample + stitch + softmax + argmax kernel
+    (emrt_stitch_argmax_fused) — no full-resolution fp32 logits, canvas or count tensor exists."""
+    plan, H, W = plan_windows(img_hw, crop_size, stride_size)
+    sizes = {(wh, ww) for (_, _, _, wh, ww) in plan}
+    if len(sizes) != 1:
+        return None
+    (wh, ww), = sizes
+    halves = []
+    for s0 in range(0, len(plan), window_batch):
+        part = plan[s0:s0 + window_batch]
+        batch = paddle.stack([imgs[i][:, y0:y0 + wh, x0:x0 + ww] for (i, y0, x0, _, _) in part], 0)
+        halves.append(model.forward_half_logits(batch))
+    half = halves[0] if len(halves) == 1 else paddle.concat(halves, 0)
+    idx = paddle.to_tensor([w[0] for w in plan], dtype=paddle.int32)
+    ys = paddle.to_tensor([w[1] for w in plan], dtype=paddle.int32)
+    xs = paddle.to_tensor([w[2] for w in plan], dtype=paddle.int32)
+    labels = _stitch_argmax_fused(half.contiguous(), idx, ys, xs, len(imgs), H, W)
+    return [labels[i:i + 1] for i in range(len(imgs))]
+
+
+def install_half_logits(emrt_cls, uphead_cls):
+    """Gives the reference's ``EMRT`` (paddle_EMRT.py:184-304) a ``forward_half_logits(inputs)`` method: the model's own
+    forward with ``UpHead``'s LAST x2 bilinear upsample (paddle_EMRT.py:178-180) left out, i.e. the class logits at half
+    resolution that the fused stitch kernel upsamples itself.  ``UpHead.forward`` is wrapped, not replaced: without the
+    flag, and for every configuration other than EMRT's own (num_conv == 3, align_corners False), the reference code runs."""
+    if getattr(uphead_cls, "_emrt_wrapped", False):
+        return
+    ref_forward = uphead_cls.forward
+
+    def forward(self, x):
+        if not getattr(self, "_emrt_half", False) or self.num_conv != 3 or self.align_corners:
+            return ref_forward(self, x)
+        up2 = lambda t: F.interpolate(t, [2 * v for v in t.shape[2:]], mode="bilinear", align_corners=self.align_corners)
+        x = up2(F.relu(self.syncbn_fc_0(self.conv_0(x))))          # paddle_EMRT.py:164-168
+        x = up2(F.relu(self.syncbn_fc_1(self.conv_1(x))))          # :169-173
+        x = F.relu(self.syncbn_fc_2(self.conv_2(x)))               # :174-176
+        return self.conv_3(x)                                      # :177 — :178-180 (the last upsample) is the kernel's
+
+    def forward_half_logits(self, inputs):
+        head = self.uphead
+        if head.num_conv != 3 or head.align_corners:
+            raise L.EmrtError("forward_half_logits needs EMRT's own UpHead (num_conv=3, align_corners=False)")
+        head._emrt_half = True
+        try:
+            return self.forward(inputs)[0]
+        finally:
+            head._emrt_half = False
+
+    uphead_cls.forward = forward
+    uphead_cls._emrt_wrapped = True
+    emrt_cls.forward_half_logits = forward_half_logits
+
+
 def slide_inference(model, imgs, crop_size, stride_size, num_classes, window_batch=64):
     """Drop-in for src/api/infer.py:22-80 (windows batched; accumulate / divide in head.cu)."""
     img_hw = [(int(i.shape[-2]), int(i.shape[-1])) for i in imgs]
@@ -286,6 +351,13 @@ def ss_inference(model, img, ori_shape, is_slide, base_size, stride_size, crop_s
         import src.api.infer as ref_infer                      # keep the reference behaviour for the paths we do not own
         return ref_infer._emrt_original_ss_inference(model, img, ori_shape, is_slide, base_size, stride_size, crop_size,
                                                      num_classes, rescale_from_ori)
+    if ori_shape is not None and hasattr(model, "forward_half_logits"):
+        img_hw = [(int(i.shape[-2]), int(i.shape[-1])) for i in img]
+        same = all(tuple(int(v) for v in ori_shape[i]) == img_hw[i] for i in range(len(img)))
+        if same and len(set(img_hw)) == 1:
+            fused = _ss_slide_fused(model, img, img_hw, crop_size, stride_size)
+            if fused is not None:
+                return fused
     logit_list = slide_inference(model, img, crop_size, stride_size, num_classes)
     if ori_shape is None:
         return logit_list
@@ -328,7 +400,7 @@ def make_fast_encoder_decoder(ref_cls):
             import torch
             import emrt_b200
             params = dict(self.named_parameters())
-            ver = tuple((k, int(getattr(p, "inplace_version", 0))) for k, p in params.items())
+            ver = tuple((k, int(p.data_ptr()), int(getattr(p, "inplace_version", 0))) for k, p in params.items())
             if self._emrt_native is not None and self._emrt_native[0] == ver:
                 return self._emrt_native[1]
             C_ = params["level_embed.weight"].shape[1]
@@ -358,9 +430,16 @@ def make_fast_encoder_decoder(ref_cls):
         def forward(self, src_feats, src_psp, src_mask=None):
             if self.training or src_mask is not None or paddle.is_grad_enabled():
                 return super().forward(src_feats, src_psp, src_mask)
+            import torch
             m = self._native_module()
-            hs, memory = m([_to_torch(f) for f in src_feats], _to_torch(src_psp))
-            return _from_torch(hs), _from_torch(memory)
+            # The launches of emrt_b200.EncoderDecoder go to torch's CURRENT stream: make that Paddle's current stream,
+            # so they are ordered after the kernels that produced src_feats and before whatever consumes hs / memory —
+            # one stream, no cross-stream event needed (torch's allocator also sees the blocks used on this stream).
+            ext = torch.cuda.ExternalStream(int(paddle.device.cuda.current_stream().cuda_stream))
+            with torch.cuda.stream(ext):
+                hs, memory = m([_to_torch(f) for f in src_feats], _to_torch(src_psp))
+                hs, memory = _from_torch(hs), _from_torch(memory)
+            return hs, memory
 
     EncoderDecoder.__name__ = ref_cls.__name__
     EncoderDecoder.__qualname__ = ref_cls.__qualname__
@@ -391,6 +470,16 @@ def patch_reference(encoder_decoder=True):
                 if other is not None and getattr(other, "EncoderDecoder", None) is ref_cls:
                     other.EncoderDecoder = fast
     U.deformable_attention_core_func = deformable_attention_core_func
-    infer._emrt_original_ss_inference = infer.ss_inference
+    if not hasattr(infer, "_emrt_original_ss_inference"):       # idempotent: a second call must not save our own shim
+        infer._emrt_original_ss_inference = infer.ss_inference
     infer.slide_inference = slide_inference
     infer.ss_inference = ss_inference
+    # val.py:145 / predict.py then reach the fused upsample + stitch + argmax kernel through the unmodified model class
+    emrt_mod = sys.modules.get("src.models.paddle_EMRT")
+    if emrt_mod is None:
+        try:
+            import src.models.paddle_EMRT as emrt_mod
+        except Exception:                                        # the model file needs the whole repo's imports
+            emrt_mod = None
+    if emrt_mod is not None and hasattr(emrt_mod, "EMRT") and hasattr(emrt_mod, "UpHead"):
+        install_half_logits(emrt_mod.EMRT, emrt_mod.UpHead)

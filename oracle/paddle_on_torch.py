@@ -110,6 +110,10 @@ class Tensor(torch.Tensor):
     def stop_gradient(self, v):
         _T.requires_grad_(self, not v)
 
+    @property
+    def inplace_version(self):      # paddle.Tensor.inplace_version: bumped by every in-place write (set_value, optimiser)
+        return _T._version.__get__(self)
+
     def numpy(self):
         a = _raw(self).detach().cpu().numpy()
         return a.reshape(1) if a.ndim == 0 else a          # Paddle < 2.5: scalars are shape [1]

@@ -185,6 +185,91 @@ def test_binding_patch_reference_installs_the_drop_ins(binding):
                 sys.modules[n] = m
 
 
+def test_binding_packs_follow_the_parameters(binding):
+    """The bf16 weight packs are keyed on (data_ptr, inplace_version) of the parameters: a later set_value (checkpoint load,
+    optimiser step) is seen by the next forward without any invalidate call."""
+    PS, paddle = binding
+    c = G.msda_inputs()
+    m = PS.MSDeformableAttention(c["C"], c["M"], len(c["shapes"]), c["P"])
+    for name, arr in c["params"].items():
+        mod, leaf = name.split(".")
+        getattr(getattr(m, mod), leaf).set_value(paddle.to_tensor(arr))
+    T = paddle.to_tensor
+    args = lambda: (T(c["query"]).astype("bfloat16"), T(c["ref"]), T(c["value"]).astype("bfloat16"), T(c["shapes"], dtype="int64"))
+    with paddle.no_grad():
+        a = raw(m(*args())).float().clone()
+        m.output_proj.bias.set_value(paddle.to_tensor(c["params"]["output_proj.bias"] + 1.0))
+        b = raw(m(*args())).float()
+    assert (b - a - 1.0).abs().max().item() < 5e-2
+
+
+def test_binding_patch_reference_is_idempotent_and_installs_half_logits(binding):
+    """patch_reference() twice keeps the REFERENCE's ss_inference as the saved original (a second call used to save the
+    shim itself -> infinite recursion for is_slide=False), and gives the model class `forward_half_logits`."""
+    PS, paddle = binding
+    names = ["src", "src.api", "src.api.infer", "src.models", "src.models.paddle_EMRT", "src.models.EMRT_utils",
+             "src.models.EMRT_utils.transformer_encoder_decoder", "src.models.EMRT_utils.utils"]
+    saved = {n: sys.modules.get(n) for n in names}
+    try:
+        for n in names:
+            sys.modules[n] = types.ModuleType(n)
+        for n in names[1:]:
+            parent, leaf = n.rsplit(".", 1)
+            setattr(sys.modules[parent], leaf, sys.modules[n])
+        infer = sys.modules["src.api.infer"]
+        original = infer.ss_inference = lambda *a, **k: "reference"
+        infer.slide_inference = object()
+        emrt_mod = sys.modules["src.models.paddle_EMRT"]
+
+        class UpHead:
+            num_conv, align_corners = 3, False
+            def forward(self, x):
+                return "full"
+
+        class EMRT:
+            pass
+        emrt_mod.UpHead, emrt_mod.EMRT = UpHead, EMRT
+        PS.patch_reference()
+        PS.patch_reference()
+        assert infer._emrt_original_ss_inference is original
+        assert PS.ss_inference(None, [0], None, False, None, None, None, 6) == "reference"      # no recursion
+        assert hasattr(EMRT, "forward_half_logits") and UpHead._emrt_wrapped
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+
+
+def test_binding_ss_inference_takes_the_fused_kernel_with_half_logits(binding):
+    """val.py:145's call on a model that exposes forward_half_logits (what install_half_logits gives the reference's EMRT):
+    the shim's ss_inference runs emrt_stitch_argmax_fused on the half-resolution logits — same labels as the canvas path."""
+    PS, paddle = binding
+    from oracle import paddle_on_torch as P
+    from emrt_b200 import ops
+    g, c = load("ref_slide"), G.slide_inputs()
+    wconv = torch.from_numpy(c["wconv"]).cuda()
+
+    class Model:
+        calls = 0
+        def __call__(self, batch):
+            half = torch.nn.functional.conv2d(raw(batch).float(), wconv, stride=2).contiguous()
+            return (P._wrap(ops.upsample2x(half)),)
+        def forward_half_logits(self, batch):
+            Model.calls += 1
+            return P._wrap(torch.nn.functional.conv2d(raw(batch).float(), wconv, stride=2).contiguous())
+    rng = np.random.Generator(np.random.PCG64(91))
+    imgs = [paddle.to_tensor(O.rng_normal(rng, (3, 56, 72))) for _ in range(3)]        # one even size: the fused path applies
+    ori = [(56, 72)] * 3
+    preds = PS.ss_inference(Model(), imgs, ori, True, None, c["stride"], c["crop"], c["nc"])
+    assert Model.calls >= 1
+    unfused = PS.ss_inference(lambda b: Model()(b), imgs, ori, True, None, c["stride"], c["crop"], c["nc"])
+    assert len(preds) == len(unfused) == 3
+    for a, b in zip(preds, unfused):
+        assert a.shape == b.shape and (raw(a) == raw(b)).float().mean().item() >= 0.999
+
+
 def _fake_reference_encoder_decoder(P, params):
     """A Layer with exactly the reference EncoderDecoder's parameter tree (the reference class itself is not on the GPU
     box; tests/test_reference_pin.py::test_fast_encoder_decoder_subclasses_the_reference_class covers the real one on CPU).

@@ -184,3 +184,43 @@ def test_fast_encoder_decoder_subclasses_the_reference_class():
     hs, mem = m([paddle.to_tensor(f) for f in c["feats"]], paddle.to_tensor(c["psp"]))
     close(torch.as_tensor(mem).detach(), g["memory"], 1e-7)
     close(torch.as_tensor(hs).detach(), g["hs"], 1e-7)
+
+
+@live
+def test_install_half_logits_on_the_reference_uphead():
+    """emrt_b200/paddle_shim.py::install_half_logits on the REAL reference UpHead (paddle_EMRT.py:115-181): with the flag
+    the wrapped forward returns conv_3's output — upsampling it x2 (the kernel's job) reproduces the reference forward bit
+    for bit; without the flag the reference code runs untouched.  A model class gets `forward_half_logits`."""
+    ref = R.load()
+    import paddle
+    import paddle.nn.functional as F
+    import emrt_b200.paddle_shim as PS
+    UpHead = ref.emrt.UpHead
+    saved = UpHead.forward
+    try:
+        class Model(paddle.nn.Layer):                    # stands for EMRT: forward returns (logits, aux) (paddle_EMRT.py:297-304)
+            def __init__(self):
+                super().__init__()
+                self.uphead = UpHead(embed_dim=256, num_conv=3, num_upsample_layer=1, align_corners=False, num_classes=6)
+
+            def forward(self, x):
+                return (self.uphead(x), None)
+        PS.install_half_logits(Model, UpHead)
+        PS.install_half_logits(Model, UpHead)            # idempotent
+        torch.manual_seed(3)
+        m = Model()
+        m.eval()
+        x = paddle.to_tensor(np.random.default_rng(5).standard_normal((2, 256, 8, 8)).astype(np.float32))
+        with paddle.no_grad():
+            full = m(x)[0]
+            half = m.forward_half_logits(x)
+            assert not m.uphead._emrt_half
+            again = m(x)[0]
+        assert list(full.shape) == [2, 6, 64, 64] and list(half.shape) == [2, 6, 32, 32]
+        up = F.interpolate(half, [64, 64], mode="bilinear", align_corners=False)
+        assert torch.equal(torch.as_tensor(up), torch.as_tensor(full)) and torch.equal(torch.as_tensor(again), torch.as_tensor(full))
+        close(O.upsample2x(torch.as_tensor(half).detach()), torch.as_tensor(full).detach().numpy(), 1e-6)
+    finally:
+        UpHead.forward = saved
+        if hasattr(UpHead, "_emrt_wrapped"):
+            del UpHead._emrt_wrapped
