@@ -125,16 +125,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def measured_traffic(B):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, keyed by windows per launch), or None."""
+def measured_traffic(B, live=True):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) and where the figure
+    comes from.  `live`: measured NOW, by running scripts/gather_once.py (the same kernel on the same geometry) under ncu
+    in a subprocess after the timed region — nothing timed runs under the profiler; otherwise, or when ncu is unavailable,
+    the committed capture profiles/traffic.json (keyed by windows per launch)."""
+    if live:
+        try:
+            cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+                   "-k", "regex:msda_gather_fwd_win", "-s", "1", "-c", "1", sys.executable,
+                   os.path.join(ROOT, "scripts", "gather_once.py"), str(B)]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            tot, seen = 0.0, 0
+            for line in r.stdout.splitlines():
+                f = [x.strip('"') for x in line.split('","')]
+                if len(f) > 3 and f[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[-2]]
+                    tot += float(f[-1].replace(",", "")) * scale
+                    seen += 1
+            if seen == 2:
+                return tot, "ncu subprocess in this run (scripts/gather_once.py, same kernel and geometry)"
+        except Exception:
+            pass
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         d = json.load(open(p))
         e = d["msda_gather_fwd_win"].get(str(B))
-        return None if e is None else float(e["dram_bytes_read"]) + float(e["dram_bytes_write"])
+        return (None, None) if e is None else (float(e["dram_bytes_read"]) + float(e["dram_bytes_write"]), "profiles/traffic.json (committed capture)")
     except Exception:
-        return None
+        return None, None
 
 
 def bind_to_gpu_numa_node(local):
@@ -261,6 +280,9 @@ def run_reference(args):
         "mpix_per_s": ips * TILE * TILE / 1e6,
         "config": {"workload": f"cfg3-shaped: {TILE}x{TILE} windows of 1024x1024 LoveDA scenes, {NC} classes, "
                                "window 512 stride 384; " + WORKLOAD_TAIL[args.mode],
+                   "sample": f"each step = {nwin} of the {args.images * WINDOWS_PER_IMAGE} windows of our arm's step; steps clamped to "
+                             f"{max(1, min(args.steps, 3))} and warm-up to {1 if args.warmup > 0 else 0} (requested {args.steps} / "
+                             f"{args.warmup}) so the CPU arm ends within minutes",
                    "note": "reference = CPU restatement of the reference's Paddle op composition (oracle/, torch-CPU "
                            "fp32, verified equal to the reference's own sources in tests/test_reference_pin.py); "
                            "PaddlePaddle itself cannot be installed in this image"},
@@ -321,18 +343,32 @@ def run_ours(args):
             b["feats"] = [b.pop("c3"), b.pop("c4"), b.pop("c5")]
         b.update(pos=pos, qpos=qpos, mask=mask, **win)
         return b
-    rnd = lambda shape, std=1.0: (torch.randn(shape, generator=g) * std).bfloat16().pin_memory()
-    host_sets, dev_sets = [], []
+    # every input set is ONE contiguous pinned buffer (one host->device copy per step); the tensors are views into it
+    if full:        # ResNet-50 C3..C5 feature maps [B, 512|1024|2048, T/8|T/16|T/32, .] and the PSP tokens [B, 256, 110]
+        layout = [(name, (B, c, TILE // st, TILE // st), 0.5) for name, c, st in zip(("c3", "c4", "c5"), FEAT_CH, (8, 16, 32))]
+        layout.append(("psp", (B, C, Nq), 0.5))
+    else:
+        layout = [("src", (B, Lv, C), 1.0), ("tgt", (B, Nq, C), 1.0)]
+    layout.append(("half_logits", (B, NC, TILE // 2, TILE // 2), 1.0))
+
+    def views(flat):
+        out, off = {}, 0
+        for name, shape, _ in layout:
+            n = int(np.prod(shape))
+            out[name] = flat[off:off + n].view(shape)
+            off += (n + 127) // 128 * 128                    # 256-byte aligned starts (TMA / 16-byte vector loads)
+        return out
+    flat_elems = sum((int(np.prod(sh)) + 127) // 128 * 128 for _, sh, _ in layout)
+    host_flats, host_sets, dev_sets = [], [], []
     for s in range(N_SETS):
-        if full:        # ResNet-50 C3..C5 feature maps [B, 512|1024|2048, T/8|T/16|T/32, .] and the PSP tokens [B, 256, 110]
-            h = {name: rnd((B, c, TILE // st, TILE // st), 0.5) for name, c, st in zip(("c3", "c4", "c5"), FEAT_CH, (8, 16, 32))}
-            h["psp"] = rnd((B, C, Nq), 0.5)
-        else:
-            h = dict(src=rnd((B, Lv, C)), tgt=rnd((B, Nq, C)))
-        h["half_logits"] = rnd((B, NC, TILE // 2, TILE // 2))
-        host_sets.append(h)
-        dev_sets.append(as_batch({k: v.to(dev) for k, v in h.items()}))
-    in_bytes = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+        hf = torch.empty(flat_elems, dtype=torch.bfloat16).pin_memory()
+        hv = views(hf)
+        for name, shape, std in layout:
+            hv[name].copy_((torch.randn(shape, generator=g) * std).bfloat16())
+        host_flats.append(hf)
+        host_sets.append(hv)
+        dev_sets.append(as_batch(views(hf.to(dev))))
+    in_bytes = flat_elems * 2
     labels_dev = torch.empty((n_img, 1, H, W), dtype=torch.uint8, device=dev)
     labels_host = torch.empty((n_img, 1, H, W), dtype=torch.uint8).pin_memory()
     hs_host = torch.empty((B, Nq, C), dtype=torch.bfloat16).pin_memory()
@@ -376,30 +412,31 @@ def run_ours(args):
         ms_total = max_over_ranks(e0.elapsed_time(e1))
 
         # ---- e2e: host buffers in, host labels out, every step -------------------------------------------
-        # Three streams: H2D of step i+1 (pinned -> device slot) overlaps the kernels of step i, and the D2H of step
-        # i's labels / decoder states overlaps step i+1.  Every step's copies are inside the timed region.
+        # Three streams, three device slots: the H2D copies of steps i+1, i+2 (one contiguous pinned buffer -> one device
+        # slot, a single cudaMemcpyAsync per step) overlap the kernels of step i, and the D2H of step i's labels / decoder
+        # states overlaps step i+1.  Every step's copies are inside the timed region.
         cur = torch.cuda.current_stream()
         h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
-        slots = [{k: torch.empty_like(v, device=dev) for k, v in host_sets[0].items()} for _ in range(2)]
-        lab_slots = [torch.empty_like(labels_dev) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
-        done = [torch.cuda.Event() for _ in range(2)]
-        drained = [torch.cuda.Event() for _ in range(2)]
-        hs_keep = [None, None]
+        NSLOT = 3
+        slot_flats = [torch.empty(flat_elems, dtype=torch.bfloat16, device=dev) for _ in range(NSLOT)]
+        slots = [views(f) for f in slot_flats]
+        lab_slots = [torch.empty_like(labels_dev) for _ in range(NSLOT)]
+        ready = [torch.cuda.Event() for _ in range(NSLOT)]
+        free = [torch.cuda.Event() for _ in range(NSLOT)]
+        done = [torch.cuda.Event() for _ in range(NSLOT)]
+        drained = [torch.cuda.Event() for _ in range(NSLOT)]
+        hs_keep = [None] * NSLOT
         for ev in free + drained:
             ev.record(cur)
 
         def e2e_step(i):
-            sl = i % 2
-            h = host_sets[i % N_SETS]
+            sl = i % NSLOT
             with torch.cuda.stream(h2d):
-                h2d.wait_event(free[sl])               # the kernels of step i-2 are done with this slot
-                for k, v in h.items():
-                    slots[sl][k].copy_(v, non_blocking=True)
+                h2d.wait_event(free[sl])               # the kernels of step i-NSLOT are done with this slot
+                slot_flats[sl].copy_(host_flats[i % N_SETS], non_blocking=True)     # ONE copy: the whole input set
                 ready[sl].record(h2d)
             cur.wait_event(ready[sl])
-            cur.wait_event(drained[sl])                # step i-2's labels have left lab_slots[sl]
+            cur.wait_event(drained[sl])                # step i-NSLOT's labels have left lab_slots[sl]
             lab, hs = hp.step(as_batch(slots[sl]), lab_slots[sl])
             hs_keep[sl] = hs
             free[sl].record(cur)
@@ -427,9 +464,43 @@ def run_ours(args):
         sync_all()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
 
+        # pure-copy ceiling of the platform at this N: the same buffer, the same copy, nothing else running
+        import bench_extras as X
+        ceil_gbs, ceil_ms = X.h2d_ceiling(host_flats[0], slot_flats[0], dev, world)
+
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
     e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+    copy_bound = world * B / (ceil_ms * 1e-3)                  # images/s if the step were nothing but its H2D copy
+    e2e_rec = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+               "ms_per_step": ms_e2e / args.steps, "h2d_gbs_per_gpu": in_bytes / (ms_e2e / args.steps * 1e-3) / 1e9,
+               "h2d_ceiling_gbs": ceil_gbs, "h2d_ceiling_ms": ceil_ms,
+               "h2d_ceiling_what": f"{in_bytes / 1e6:.0f} MB pinned -> device, one cudaMemcpyAsync, all {world} rank(s) at once, "
+                                   "nothing else running (max over ranks)",
+               "bound": "copy" if copy_bound < value else "compute",
+               "frac_of_bound": e2e_value / min(value, copy_bound),
+               "copies": "one contiguous pinned staging buffer per step, 3 device slots, H2D / kernels / D2H on 3 streams"}
+
+    # ---- the other configurations and splits, short, after the main timing --------------------------------
+    extras = {}
+    if not args.no_extras and args.mode == "full":
+        del dev_sets, slot_flats, slots
+        torch.cuda.empty_cache()
+        for name, fn in (("train_step", lambda: X.train_step(dev, rank, world)),
+                         ("scene6000", lambda: X.scene6000(dev, rank, world)),
+                         ("tiles256", lambda: X.tiles256(dev, rank, world))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:                              # a sub-record must never take the headline down
+                extras[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                if world > 1:
+                    raise
+            torch.cuda.empty_cache()
+        if world == 1:
+            try:
+                extras["sensitivity"] = X.gather_sensitivity(dev, B)
+            except Exception as exc:
+                extras["sensitivity"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- roofline of the dominant kernel (the encoder gather) --------------------------------------------
     enc = [(dims, ev[0].elapsed_time(ev[1])) for (name, dims, ev) in events if name == "msda_gather_fwd" and dims[1] == Lv]
@@ -465,7 +536,7 @@ def run_ours(args):
         gb = gather_bytes(*enc[0][0]) / 1e9
         ach = gb / (avg_ms * 1e-3)
         roof = {"kernel": "msda_gather_fwd (encoder call, Lq=Lv=%d, B=%d)" % (Lv, B), "bound": "hbm",
-                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": measured_traffic(B),
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                 "algorithmic_bytes": gb * 1e9, "avg_launch_ms": avg_ms, "launches_timed": len(enc),
                 "share_of_step": avg_ms * len(enc) / args.steps / ms_step, "peak_source": peak_src}
         # what actually bounds it: every (query, head) reads L*P*4 corners x D x 2 B from shared memory
@@ -493,8 +564,7 @@ def run_ours(args):
                          "each step also streams > 1 GB of intermediates",
                    "parallelism": f"windows sharded over {world} GPU(s), no collective",
                    "host_affinity": f"rank threads bound to {numa_cpus} GPU-local cores" if numa_cpus else "default"},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": ms_e2e / args.steps},
+        "e2e": e2e_rec,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -503,6 +573,11 @@ def run_ours(args):
                                          "timed inside a long step; a tile kernel can exceed it) and bf16_tflops (burst)",
                           "rows": dense_rows},
     }
+    line.update({k: v for k, v in extras.items() if k != "sensitivity"})
+    if roof is not None:
+        if "sensitivity" in extras:
+            roof["sensitivity"] = extras["sensitivity"]
+        roof["traffic"], roof["traffic_source"] = measured_traffic(B, live=(world == 1 and not args.no_extras))
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         ips, dt = cpu_hot_path(max(1, args.cpu_sample_windows), cores, repeats=2, warmup=1, mode=args.mode)
