@@ -296,6 +296,132 @@ struct StitchEval {
   uint8_t* color;                // [n_img, H, W, 3] or NULL
 };
 
+// a5 + a6 + a7, one 16 x 2 strip of label pixels per thread (bf16 logits, label map only).  The quad kernel above is bound by
+// instruction issue: 9 two-byte loads per class and window for four labels.  Here a thread owns 16 consecutive label columns
+// of a row pair, so for a window whose origin is a multiple of 16 (x) and 2 (y) — every origin of the reference's 512 / 384
+// plans — one class of one window costs three 16-byte loads (half-resolution rows k-1, k, k+1, columns j..j+7) plus the
+// two neighbour columns, and 6 flops per label.  Classes run in the OUTER loop (one accumulator strip + running first-max),
+// windows in list order inside: per pixel the same sums in the same order, with the same expressions
+// (a + f * (b - a), make_tap's fractions 0.75 / 0.25, clamped edge taps), as the one-pixel kernel — labels are bit-equal.
+// Windows at other origins take the per-pixel path inside the same loop.
+constexpr int STRIP_W = 16, STRIP_TILE_X = 32 * STRIP_W, STRIP_TILE_Y = 16;
+
+__device__ __forceinline__ float lerp_tap(float a, float b, float f) { return a + f * (b - a); }
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+stitch_argmax_strip_kernel(const __nv_bfloat16* __restrict__ half_logits, void* __restrict__ labels, int label_dtype,
+                           int n_win, int nc, int hc, int wc, int H, int W, const int32_t* __restrict__ win_img,
+                           const int32_t* __restrict__ win_y0, const int32_t* __restrict__ win_x0) {
+  __shared__ WinList wl;
+  __shared__ int warp_cnt[8];
+  __shared__ int s_y0[MAX_LIST], s_x0[MAX_LIST];
+  const int img = blockIdx.z;
+  const int tx0 = blockIdx.x * STRIP_TILE_X, ty0 = blockIdx.y * STRIP_TILE_Y;
+  build_window_list(wl, warp_cnt, n_win, img, ty0, tx0, STRIP_TILE_Y, STRIP_TILE_X, hc, wc, win_img, win_y0, win_x0);
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  if (wl.n >= 0 && t < wl.n) { s_y0[t] = __ldg(win_y0 + wl.idx[t]); s_x0[t] = __ldg(win_x0 + wl.idx[t]); }
+  __syncthreads();
+  const int X = tx0 + threadIdx.x * STRIP_W, y = ty0 + threadIdx.y * 2;
+  if (X >= W || y >= H) return;
+  const int hh = hc / 2, hw = wc / 2;
+  const int n = wl.n < 0 ? n_win : wl.n;
+  float best[2][STRIP_W];
+  uint32_t bidx[2][2] = {{0u, 0u}, {0u, 0u}};          // 4 bits per pixel
+  for (int c = 0; c < nc; ++c) {
+    float acc[2][STRIP_W];
+#pragma unroll
+    for (int x = 0; x < STRIP_W; ++x) acc[0][x] = acc[1][x] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      int w, wy0, wx0;
+      if (wl.n < 0) {
+        w = i;
+        if (__ldg(win_img + w) != img) continue;
+        wy0 = __ldg(win_y0 + w); wx0 = __ldg(win_x0 + w);
+      } else {
+        w = wl.idx[i]; wy0 = s_y0[i]; wx0 = s_x0[i];
+      }
+      const int ly = y - wy0, lx = X - wx0;
+      if (ly + 1 < 0 || ly >= hc || lx + STRIP_W - 1 < 0 || lx >= wc) continue;
+      const __nv_bfloat16* pl = half_logits + ((int64_t)w * nc + c) * hh * hw;
+      if (((wy0 & 1) | (wx0 & (STRIP_W - 1))) == 0) {
+        // aligned window: the strip is wholly inside it
+        const int k = ly >> 1, j0 = lx >> 1;
+        const int jl = max(j0 - 1, 0), jr = min(j0 + 8, hw - 1);
+        const int rows[3] = {max(k - 1, 0) * hw, k * hw, min(k + 1, hh - 1) * hw};
+        float h[3][10];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(pl + rows[r] + j0));
+          h[r][0] = __bfloat162float(pl[rows[r] + jl]);
+          h[r][9] = __bfloat162float(pl[rows[r] + jr]);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            h[r][1 + 2 * q] = __uint_as_float(u[q] << 16);
+            h[r][2 + 2 * q] = __uint_as_float(u[q] & 0xffff0000u);
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < STRIP_W; ++x) {
+          // even local column 2j: taps (j-1, j), f = 0.75; odd 2j+1: taps (j, j+1), f = 0.25 (make_tap, scale 0.5)
+          const int a = (x >> 1) + (x & 1);
+          const float f = (x & 1) ? 0.25f : 0.75f;
+          const float t0 = lerp_tap(h[0][a], h[0][a + 1], f);
+          const float t1 = lerp_tap(h[1][a], h[1][a + 1], f);
+          const float t2 = lerp_tap(h[2][a], h[2][a + 1], f);
+          acc[0][x] += lerp_tap(t0, t1, 0.75f);
+          acc[1][x] += lerp_tap(t1, t2, 0.25f);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int py = ly + r;
+          if (py < 0 || py >= hc) continue;
+          const Tap ty = make_tap(py, hh, 0.5f);
+#pragma unroll
+          for (int x = 0; x < STRIP_W; ++x) {
+            const int px = lx + x;
+            if (px < 0 || px >= wc) continue;
+            acc[r][x] += bilerp<__nv_bfloat16>(pl, hw, ty, make_tap(px, hw, 0.5f));
+          }
+        }
+      }
+    }
+    // first-max rule (infer.py:152-153): strictly greater replaces, classes in increasing order
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int x = 0; x < STRIP_W; ++x) {
+        const bool up = c == 0 || acc[r][x] > best[r][x];
+        best[r][x] = up ? acc[r][x] : best[r][x];
+        const uint32_t sh = 4 * (x & 7);
+        bidx[r][x >> 3] = up ? ((bidx[r][x >> 3] & ~(0xFu << sh)) | ((uint32_t)c << sh)) : bidx[r][x >> 3];
+      }
+  }
+  const int64_t plane = (int64_t)H * W;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int64_t o = (int64_t)img * plane + (int64_t)(y + r) * W + X;
+    if (label_dtype == EMRT_U8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t nib = bidx[r][q >> 1] >> (16 * (q & 1));
+        pk[q] = (nib & 0xFu) | ((nib & 0xF0u) << 4) | ((nib & 0xF00u) << 8) | ((nib & 0xF000u) << 12);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(labels) + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t nib = bidx[r][q >> 1] >> (16 * (q & 1));
+        *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(labels) + o + 4 * q) =
+            make_int4(nib & 0xF, (nib >> 4) & 0xF, (nib >> 8) & 0xF, (nib >> 12) & 0xF);
+      }
+    }
+  }
+}
+
 template <typename T, int NC, bool EVAL>
 __global__ void __launch_bounds__(256)
 stitch_argmax_quad_kernel(const T* __restrict__ half_logits, void* __restrict__ labels, int label_dtype,
@@ -535,6 +661,17 @@ static int stitch_argmax_launch(const void* half_logits, int in_dtype, void* lab
   EMRT_REQUIRE(label_dtype == EMRT_I32 || label_dtype == EMRT_U8, "label_dtype must be I32 or U8");
   if (nc > 32) return set_error(EMRT_ERR_UNSUPPORTED, "nc=%d > 32", nc);
   cudaStream_t st = as_stream(stream);
+  // label map only, bf16 logits, 16-pixel column alignment: the strip kernel (windows at unaligned origins are handled
+  // inside it, per pixel).  EMRT_STITCH_QUAD=1 keeps the quad kernel (the bit-equality test compares the two).
+  if (!eval && !logits_out && in_dtype == EMRT_BF16 && H % 2 == 0 && W % STRIP_W == 0 && wc % STRIP_W == 0 && nc <= 8 &&
+      (reinterpret_cast<uintptr_t>(half_logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(labels) & 15) == 0 &&
+      !getenv("EMRT_STITCH_QUAD") && !getenv("EMRT_STITCH_PIXEL")) {
+    dim3 sgrid((W + STRIP_TILE_X - 1) / STRIP_TILE_X, (H + STRIP_TILE_Y - 1) / STRIP_TILE_Y, n_img), sblock(32, 8);
+    stitch_argmax_strip_kernel<8><<<sgrid, sblock, 0, st>>>((const __nv_bfloat16*)half_logits, labels, label_dtype, n_win, nc,
+                                                            hc, wc, H, W, win_img, win_y0, win_x0);
+    EMRT_LAUNCH_CHECK();
+    return EMRT_OK;
+  }
   if (H % 2 == 0 && W % 2 == 0 && nc <= 8 && (eval || !getenv("EMRT_STITCH_PIXEL"))) {
     dim3 qgrid((W + QTILE - 1) / QTILE, (H + QTILE - 1) / QTILE, n_img), qblock(16, 16);
     StitchEval ev;

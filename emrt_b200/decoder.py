@@ -233,16 +233,15 @@ class EncoderDecoder(nn.Module):
         return c
 
     @torch.no_grad()
-    def forward(self, src_feats: Sequence[torch.Tensor], src_psp, src_mask=None):
-        if src_mask is not None:
-            raise L.EmrtError("EMRT never passes src_mask (paddle_EMRT.py:265); the masked path is not built")
+    def project_inputs(self, src_feats: Sequence[torch.Tensor]):
+        """input_proj (:417-419) + flatten / concat (:434-452): 1x1 conv as a GEMM on tokens, GroupNorm written straight
+        into the level's token slot.  -> (src [B, Lv, C], level shapes, the cached constants of `_constants`)."""
         x0 = src_feats[0]
         B, dtype, dev = x0.shape[0], x0.dtype, x0.device
         shapes = tuple((int(f.shape[2]), int(f.shape[3])) for f in src_feats)
         Lv = sum(h * w for h, w in shapes)
         c = self._constants(shapes, dev, dtype)
         fast = dtype == torch.bfloat16
-        # input_proj (:417-419): 1x1 conv as a GEMM on tokens, GroupNorm written straight into the level's token slot
         src = torch.empty((B, Lv, self.hidden_dim), dtype=dtype, device=dev)
         off = 0
         for l, f in enumerate(src_feats):
@@ -250,6 +249,14 @@ class EncoderDecoder(nn.Module):
             y = ops.linear(tok, c["w"][l], c["b"][l], w_transposed=fast, impl=L.IMPL_AUTO if fast else L.IMPL_SIMT)
             ops.groupnorm_tokens_into(y, c["gw"][l], c["gb"][l], src, off, groups=32)
             off += shapes[l][0] * shapes[l][1]
+        return src, shapes, c
+
+    @torch.no_grad()
+    def forward(self, src_feats: Sequence[torch.Tensor], src_psp, src_mask=None):
+        if src_mask is not None:
+            raise L.EmrtError("EMRT never passes src_mask (paddle_EMRT.py:265); the masked path is not built")
+        src, shapes, c = self.project_inputs(src_feats)
+        B, Lv, dev = src.shape[0], src.shape[1], src.device
         mask = torch.ones((B, Lv), dtype=torch.float32, device=dev)                    # mask_flatten (:451)
         memory = self.encoder(src, shapes, mask, c["pos"])
         tgt = ops.nchw_to_tokens(src_psp)                                              # src_psp.transpose([0, 2, 1]) (:469)

@@ -34,7 +34,7 @@ __all__ = [
     "upsample2x", "upsample2x_loop", "interpolate_bilinear", "window_origins", "slide_inference",
     "ss_inference_tail", "ss_inference", "calculate_area", "position_embedding_sine",
     "multi_head_attention", "encoder_layer_forward", "decoder_layer_forward", "encoder_decoder_forward",
-    "make_encoder_decoder_params", "rng_normal", "rng_uniform",
+    "make_encoder_decoder_params", "rng_normal", "rng_uniform", "kernel_storage_rounding",
 ]
 
 
@@ -48,6 +48,38 @@ def level_tables(shapes: Sequence[Tuple[int, int]]):
         start.append(acc)
         acc += int(h) * int(w)
     return start, acc
+
+
+# ----------------------------------------------------------------------------------------------
+# storage-rounding mode: the restatement evaluated with the B200 path's STORAGE formats
+# ----------------------------------------------------------------------------------------------
+# The bf16 path keeps every tensor that crosses HBM in a 16-bit format: activations bf16, sampling offsets
+# (in pixels of their level) and softmax weights fp16; all arithmetic between two stores is fp32.  Inside
+# `kernel_storage_rounding()` the functions below apply exactly those roundings — and nothing else — at the points where
+# the kernels store, while still computing in the caller's dtype (float64 in the tests).  Two uses:
+#   * kernel vs this = the kernels' OWN error (accumulation order, exp / erf approximations), asserted tight (tests/);
+#   * this vs the exact evaluation = what the storage formats cost at depth, measured on the CPU alone
+#     (tests/test_oracle.py) — the part of the bf16 tolerance that no kernel can remove.
+_ROUND = {"on": False}
+
+
+class kernel_storage_rounding:
+    def __enter__(self):
+        self.prev = _ROUND["on"]
+        _ROUND["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _ROUND["on"] = self.prev
+        return False
+
+
+def _store(x, kind="act"):
+    """Identity, or (storage-rounding mode) x rounded to the format the kernels store this tensor in."""
+    if not _ROUND["on"]:
+        return x
+    fmt = torch.bfloat16 if kind == "act" else torch.float16
+    return x.to(fmt).to(x.dtype)
 
 
 def rng_normal(rng: np.random.Generator, shape, std=1.0, dtype=np.float32):
@@ -70,6 +102,10 @@ def deformable_attention_core_func(value, value_spatial_shapes, sampling_locatio
     value = torch.as_tensor(value)
     sampling_locations = torch.as_tensor(sampling_locations)
     attention_weights = torch.as_tensor(attention_weights)
+    if _ROUND["on"] and sampling_locations.shape[1] == value.shape[1]:
+        # encoder self-attention geometry (one query per value pixel): the window-staged kernels' corner-weight rounding;
+        # the decoder's kernel (msda_gather_v1.cu) keeps fp32 corner weights — nothing to round there
+        return _gather_bf16_corner_weights(value, value_spatial_shapes, sampling_locations, attention_weights)
     bs, Len_v, n_head, c = value.shape
     _, Len_q, _, n_levels, n_points, _ = sampling_locations.shape
     shapes = [(int(h), int(w)) for h, w in value_spatial_shapes]
@@ -87,6 +123,33 @@ def deformable_attention_core_func(value, value_spatial_shapes, sampling_locatio
     output = (torch.stack(sampling_value_list, dim=-2).flatten(-2) * attention_weights).sum(-1)  # :94
     output = output.reshape(bs, n_head * c, Len_q)                                                # :95
     return output.permute(0, 2, 1).contiguous()                                                   # :97
+
+
+def _gather_bf16_corner_weights(value, shapes, loc, attn):
+    """Storage-rounding mode of the gather: the closed form of `gather_corner_loop` with each of the four corner weights
+    ((1-fx)*aw)*(1-fy) ... rounded to bf16 — the B200 gather kernels multiply bf16 values by bf16 corner weights into an
+    fp32 accumulator (`fma.rn.f32.bf16`, msda_win_common.cuh) — everything else in the caller's dtype."""
+    B, Lv, M, D = value.shape
+    _, Lq, _, L, P, _ = loc.shape
+    shapes = [(int(h), int(w)) for h, w in shapes]
+    start, total = level_tables(shapes)
+    out = torch.zeros((B, Lq, M, D), dtype=value.dtype)
+    bi = torch.arange(B)[:, None, None]
+    mi = torch.arange(M)[None, None, :]
+    for l, (H, W) in enumerate(shapes):
+        for p in range(P):
+            x = loc[:, :, :, l, p, 0] * W - 0.5
+            y = loc[:, :, :, l, p, 1] * H - 0.5
+            x0, y0 = torch.floor(x), torch.floor(y)
+            fx, fy = x - x0, y - y0
+            aw = attn[:, :, :, l, p]
+            for dy, dx in ((0, 0), (0, 1), (1, 0), (1, 1)):
+                xi, yi = (x0 + dx).long(), (y0 + dy).long()
+                w = _store(((fx if dx else 1.0 - fx) * aw) * (fy if dy else 1.0 - fy))
+                inside = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+                idx = start[l] + yi.clamp(0, H - 1) * W + xi.clamp(0, W - 1)
+                out += torch.where(inside, w, torch.zeros_like(w))[..., None] * value[bi, idx, mi]
+    return out.reshape(B, Lq, M * D)
 
 
 def gather_corner_loop(value, shapes, loc, attn):
@@ -163,7 +226,7 @@ def _t(x, dtype):
 
 
 def msda_intermediates(params, query, reference_points, value, shapes, value_mask=None,
-                       num_heads=8, num_points=6, dtype=torch.float32):
+                       num_heads=8, num_points=6, dtype=torch.float32, query_pos=None):
     """Steps (1)-(4) of MSDeformableAttention.forward (transformer_encoder_decoder.py:79-102).
     Returns (value_proj'd value [B,Lv,M,D], sampling_locations [B,Lq,M,L,P,2], attention [B,Lq,M,L,P])."""
     q = _t(query, dtype)
@@ -178,12 +241,20 @@ def msda_intermediates(params, query, reference_points, value, shapes, value_mas
     v = v @ P_["value_proj.weight"] + P_["value_proj.bias"]                            # :83
     if value_mask is not None:
         v = v * _t(value_mask, dtype).unsqueeze(-1)                                    # :84-86
-    v = v.reshape(bs, Len_v, num_heads, C // num_heads)                                # :88
-    off = (q @ P_["sampling_offsets.weight"] + P_["sampling_offsets.bias"]).reshape(
-        bs, Len_q, num_heads, L, num_points, 2)                                        # :89-90
-    aw = (q @ P_["attention_weights.weight"] + P_["attention_weights.bias"]).reshape(
-        bs, Len_q, num_heads, L * num_points)                                          # :92-93
-    aw = F.softmax(aw, -1).reshape(bs, Len_q, num_heads, L, num_points)                # :95-96
+    v = _store(v).reshape(bs, Len_v, num_heads, C // num_heads)                        # :88
+    if query_pos is None:
+        off = q @ P_["sampling_offsets.weight"] + P_["sampling_offsets.bias"]
+        aw = q @ P_["attention_weights.weight"] + P_["attention_weights.bias"]
+    else:       # (query + pos) W + b evaluated as query W + (pos W + b): the second term is a stored fp16 table (msda.py)
+        # the table is computed once from the fp32 master weights (keys "<name>#fp32" when the caller rounded the matrices)
+        qp = _t(query_pos, dtype)
+        w_off = P_.get("sampling_offsets.weight#fp32", P_["sampling_offsets.weight"])
+        w_aw = P_.get("attention_weights.weight#fp32", P_["attention_weights.weight"])
+        off = q @ P_["sampling_offsets.weight"] + _store(qp @ w_off + P_["sampling_offsets.bias"], "f16")
+        aw = q @ P_["attention_weights.weight"] + _store(qp @ w_aw + P_["attention_weights.bias"], "f16")
+    off = _store(off, "f16").reshape(bs, Len_q, num_heads, L, num_points, 2)           # :89-90 (stored in pixels, fp16)
+    aw = aw.reshape(bs, Len_q, num_heads, L * num_points)                              # :92-93
+    aw = _store(F.softmax(aw, -1), "f16").reshape(bs, Len_q, num_heads, L, num_points)  # :95-96
     normalizer = torch.tensor([[float(w), float(h)] for h, w in shapes], dtype=dtype).reshape(
         1, 1, 1, L, 1, 2)                                                              # :98-99  (flip -> (W,H))
     loc = ref.reshape(bs, Len_q, 1, L, 1, 2) + off / normalizer                        # :101-102
@@ -191,11 +262,12 @@ def msda_intermediates(params, query, reference_points, value, shapes, value_mas
 
 
 def msda_forward(params, query, reference_points, value, shapes, value_mask=None,
-                 num_heads=8, num_points=6, dtype=torch.float32):
-    """MSDeformableAttention.forward (transformer_encoder_decoder.py:65-107)."""
+                 num_heads=8, num_points=6, dtype=torch.float32, query_pos=None):
+    """MSDeformableAttention.forward (transformer_encoder_decoder.py:65-107).  `query_pos` (only meaningful in
+    storage-rounding mode): `query` is then the un-embedded query and with_pos_embed is evaluated the way the kernels do."""
     v, loc, aw = msda_intermediates(params, query, reference_points, value, shapes, value_mask,
-                                    num_heads, num_points, dtype)
-    out = deformable_attention_core_func(v, shapes, loc, aw)                            # :104
+                                    num_heads, num_points, dtype, query_pos)
+    out = _store(deformable_attention_core_func(v, shapes, loc, aw))                    # :104
     return out @ _t(params["output_proj.weight"], dtype) + _t(params["output_proj.bias"], dtype)   # :106
 
 
@@ -373,12 +445,12 @@ def multi_head_attention(p, prefix, query, key, value, num_heads=8):
     Wi, bi = p[prefix + "in_proj_weight"], p[prefix + "in_proj_bias"]
 
     def proj(t, i):
-        y = t @ Wi[:, i * C:(i + 1) * C] + bi[i * C:(i + 1) * C]
+        y = _store(t @ Wi[:, i * C:(i + 1) * C] + bi[i * C:(i + 1) * C])
         return y.reshape(y.shape[0], y.shape[1], num_heads, D).permute(0, 2, 1, 3)
     q, k, v = proj(query, 0), proj(key, 1), proj(value, 2)
     prod = (q @ k.transpose(-1, -2)) * (float(D) ** -0.5)
     w = F.softmax(prod, dim=-1)
-    out = (w @ v).permute(0, 2, 1, 3).reshape(query.shape[0], query.shape[1], C)
+    out = _store((w @ v).permute(0, 2, 1, 3).reshape(query.shape[0], query.shape[1], C))
     return out @ p[prefix + "out_proj.weight"] + p[prefix + "out_proj.bias"]
 
 
@@ -394,39 +466,47 @@ def encoder_layer_forward(p, prefix, src, ref, shapes, mask, pos):
     branch = []
     for l, (h, w) in enumerate(shapes):                                                   # :163-196
         x = src[:, start[l]:start[l] + h * w].permute(0, 2, 1).reshape(bs, c, h, w)
-        y = F.conv2d(x, p[f"{prefix}conv{l}.0.weight"], None, 1, 1)
+        y = _store(F.conv2d(x, p[f"{prefix}conv{l}.0.weight"], None, 1, 1))
         y = F.group_norm(y, 32, p[f"{prefix}conv{l}.1.weight"], p[f"{prefix}conv{l}.1.bias"], 1e-5)
         y = F.gelu(y) + x
         branch.append(y.flatten(2).permute(0, 2, 1))
     src_flatten = torch.cat(branch, 1)
-    src2 = msda_forward(_sub(p, prefix + "self_attn."), src + pos, ref, src, shapes, mask, dtype=src.dtype)  # :198
-    src = _ln(src + src2, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"])            # :199-200
-    ffn = F.relu(src @ p[prefix + "linear1.weight"] + p[prefix + "linear1.bias"]) @ p[prefix + "linear2.weight"] \
-        + p[prefix + "linear2.bias"]                                                        # :157-158
+    if _ROUND["on"]:        # with_pos_embed folded into the query projection (row-bias table), as the kernels do
+        src2 = msda_forward(_sub(p, prefix + "self_attn."), src, ref, src, shapes, mask, dtype=src.dtype, query_pos=pos[:1])
+    else:
+        src2 = msda_forward(_sub(p, prefix + "self_attn."), src + pos, ref, src, shapes, mask, dtype=src.dtype)  # :198
+    src = _store(_ln(src + src2, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]))    # :199-200
+    ffn = _store(_store(F.relu(src @ p[prefix + "linear1.weight"] + p[prefix + "linear1.bias"])) @ p[prefix + "linear2.weight"]
+                 + p[prefix + "linear2.bias"])                                              # :157-158
     src = _ln(src + ffn, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])             # :159-160
-    return src + src_flatten                                                                # :203
+    return _store(src + src_flatten)                                                        # :203
 
 
 def decoder_layer_forward(p, prefix, tgt, ref, memory, shapes, mask, query_pos):
     """TransformerDecoderLayer.forward (transformer_encoder_decoder.py:282-295), eval mode."""
     q = tgt + query_pos
     tgt2 = multi_head_attention(p, prefix + "self_attn.", q, q, tgt)
-    tgt = _ln(tgt + tgt2, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"])
-    tgt2 = msda_forward(_sub(p, prefix + "cross_attn."), tgt + query_pos, ref, memory, shapes, mask, dtype=tgt.dtype)
-    tgt = _ln(tgt + tgt2, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])
-    ffn = F.relu(tgt @ p[prefix + "linear1.weight"] + p[prefix + "linear1.bias"]) @ p[prefix + "linear2.weight"] \
+    tgt = _store(_ln(tgt + tgt2, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]))
+    if _ROUND["on"]:
+        tgt2 = msda_forward(_sub(p, prefix + "cross_attn."), tgt, ref, memory, shapes, mask, dtype=tgt.dtype, query_pos=query_pos[:1])
+    else:
+        tgt2 = msda_forward(_sub(p, prefix + "cross_attn."), tgt + query_pos, ref, memory, shapes, mask, dtype=tgt.dtype)
+    tgt = _store(_ln(tgt + tgt2, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]))
+    ffn = _store(F.relu(tgt @ p[prefix + "linear1.weight"] + p[prefix + "linear1.bias"])) @ p[prefix + "linear2.weight"] \
         + p[prefix + "linear2.bias"]
-    return _ln(tgt + ffn, p[prefix + "norm3.weight"], p[prefix + "norm3.bias"])
+    return _store(_ln(tgt + ffn, p[prefix + "norm3.weight"], p[prefix + "norm3.bias"]))
 
 
-def encoder_decoder_forward(p, src_feats, src_psp, num_enc=4, num_dec=2):
+def encoder_decoder_forward(p, src_feats, src_psp, num_enc=4, num_dec=2, trace=None):
     """EncoderDecoder.forward (transformer_encoder_decoder.py:416-473), src_mask=None, eval mode.
     p: dict of torch tensors with Paddle state-dict keys (Linear [in,out], conv [out,in,kh,kw]).
-    src_feats: [c2,c3,c4] NCHW; src_psp [B,256,110].  -> (hs [1,B,110,256], memory [B,Lv,256])."""
+    src_feats: [c2,c3,c4] NCHW; src_psp [B,256,110].  -> (hs [1,B,110,256], memory [B,Lv,256]).
+    trace: optional dict, filled with the tensors between the layers (src, pos, enc[i], ref_dec, query_pos, dec[i]) — the
+    per-layer (teacher-forced) parity tests feed each layer the evaluation's own input."""
     srcs, shapes = [], []
     for i, f in enumerate(src_feats):                                                       # :417-419
-        y = F.conv2d(f, p[f"input_proj.{i}.0.weight"], p[f"input_proj.{i}.0.bias"])
-        y = F.group_norm(y, 32, p[f"input_proj.{i}.1.weight"], p[f"input_proj.{i}.1.bias"], 1e-5)
+        y = _store(F.conv2d(f, p[f"input_proj.{i}.0.weight"], p[f"input_proj.{i}.0.bias"]))
+        y = _store(F.group_norm(y, 32, p[f"input_proj.{i}.1.weight"], p[f"input_proj.{i}.1.bias"], 1e-5))
         srcs.append(y)
     src_flatten, pos_flatten = [], []
     for level, s in enumerate(srcs):                                                        # :434-452
@@ -436,20 +516,28 @@ def encoder_decoder_forward(p, src_feats, src_psp, num_enc=4, num_dec=2):
         pos = position_embedding_sine(h, w, c // 2, dtype=s.dtype)
         pos_flatten.append((pos + p["level_embed.weight"][level].reshape(1, -1))[None].expand(bs, -1, -1))
     src = torch.cat(src_flatten, 1)
-    pos = torch.cat(pos_flatten, 1)
+    pos = _store(torch.cat(pos_flatten, 1))
     bs = src.shape[0]
     mask = torch.ones(bs, src.shape[1], dtype=src.dtype)                                    # :451
     ref = encoder_reference_points(shapes, bs, src.dtype)
     out = src
+    if trace is not None:
+        trace.update(src=src, pos=pos, enc=[], dec=[])
     for i in range(num_enc):                                                                # :230-239
         out = encoder_layer_forward(p, f"encoder.layers.{i}.", out, ref, shapes, mask, pos)
+        if trace is not None:
+            trace["enc"].append(out)
     memory = out
     query_embed = p["query_pos_embed.weight"][None].expand(bs, -1, -1)                      # :464
     rp = torch.sigmoid(query_embed @ p["reference_points.weight"] + p["reference_points.bias"])  # :466
     rp = rp[:, :, None, :].expand(-1, -1, len(shapes), -1)                                  # :467 (valid_ratios == 1)
     tgt = src_psp.permute(0, 2, 1)                                                          # :469
+    if trace is not None:
+        trace.update(ref_dec=rp, query_pos=_store(query_embed), tgt=tgt)
     for i in range(num_dec):
-        tgt = decoder_layer_forward(p, f"decoder.layers.{i}.", tgt, rp, memory, shapes, mask, query_embed)
+        tgt = decoder_layer_forward(p, f"decoder.layers.{i}.", tgt, rp, memory, shapes, mask, _store(query_embed))
+        if trace is not None:
+            trace["dec"].append(tgt)
     return tgt[None], memory, shapes
 
 

@@ -8,6 +8,8 @@ import oracle as O
 import emrt_b200
 from emrt_b200 import ops, sharding, _lib as L
 
+from parity import assert_bf16_parity, oracle_encdec_pair
+
 pytestmark = pytest.mark.gpu
 
 
@@ -202,13 +204,6 @@ def _l2(got, want):
     return ((got.detach().double().cpu() - want).norm() / want.norm()).item()
 
 
-def _oracle_encdec(st, feats, psp, idx):
-    r16 = lambda v: torch.as_tensor(v).bfloat16().double()
-    keep = lambda k: k.endswith("embed.weight") or k == "reference_points.weight"
-    p64 = {k: (r16(v) if v.ndim >= 2 and not keep(k) else torch.as_tensor(v).double()) for k, v in st.items()}
-    return O.encoder_decoder_forward(p64, [f[idx].double() for f in feats], psp[idx].double(), num_enc=4, num_dec=2)
-
-
 def test_cfg2_whole_encoder_decoder_batch64_256_tiles(cuda_dev):
     """cfg 2 geometry through the whole EncoderDecoder drop-in (bf16): two of the 64 tiles against the float64 oracle, and
     batch consistency (a tile's result is bit-identical whatever its batch) and run-to-run reproducibility."""
@@ -218,8 +213,9 @@ def test_cfg2_whole_encoder_decoder_batch64_256_tiles(cuda_dev):
     hs, mem = m([f.to(cuda_dev) for f in feats], psp.to(cuda_dev))
     assert tuple(hs.shape) == (1, 64, 110, 256) and tuple(mem.shape) == (64, 1344, 256)
     idx = [5, 63]
-    whs, wmem, _ = _oracle_encdec(st, feats, psp, idx)
-    assert _l2(mem[idx].float(), wmem) < 2e-2 and _l2(hs[0, idx].float(), whs[0]) < 2e-2
+    (whs, wmem), (rhs, rmem) = oracle_encdec_pair(st, feats, psp, 4, 2, idx)
+    assert_bf16_parity(mem[idx].float(), wmem, rmem, "cfg2 memory")
+    assert_bf16_parity(hs[0, idx].float(), whs[0], rhs[0], "cfg2 hs")
     sub = [0, 17, 40]
     hs1, mem1 = m([f[sub].to(cuda_dev) for f in feats], psp[sub].to(cuda_dev))
     # the forward has no floating-point atomics (GroupNorm sums are reduced in a fixed order) and every row / pixel / query
@@ -238,8 +234,9 @@ def test_cfg3_whole_encoder_decoder_512_windows_to_labels(cuda_dev):
     feats, psp = _feats(rng, 9, 512)
     hs, mem = m([f.to(cuda_dev) for f in feats], psp.to(cuda_dev))
     assert tuple(mem.shape) == (9, 5376, 256)
-    whs, wmem, _ = _oracle_encdec(st, feats, psp, [4])
-    assert _l2(mem[4:5].float(), wmem) < 2e-2 and _l2(hs[0, 4:5].float(), whs[0]) < 2e-2
+    (whs, wmem), (rhs, rmem) = oracle_encdec_pair(st, feats, psp, 4, 2, [4])
+    assert_bf16_parity(mem[4:5].float(), wmem, rmem, "cfg3 memory")
+    assert_bf16_parity(hs[0, 4:5].float(), whs[0], rhs[0], "cfg3 hs")
     nc = 7
     half = torch.from_numpy(O.rng_normal(rng, (9, nc, 256, 256))).bfloat16()
     plan, H, W = emrt_b200.plan_windows([(1024, 1024)], (512, 512), (384, 384))

@@ -190,3 +190,49 @@ def test_fused_eval_areas_and_palette_match_unfused(cuda_dev, dtype, gt_dtype):
     assert c2 is None and torch.equal(a2, areas)
     _, a3, c3 = emrt_b200.ss_inference_eval(model, imgs, None, (stride, stride), (crop, crop), nc, palette=palette)
     assert a3 is None and torch.equal(c3, color)
+
+
+@pytest.mark.parametrize("label_dtype", [torch.uint8, torch.int32])
+@pytest.mark.parametrize("case", ["cfg3", "mixed", "uncovered"])
+def test_strip_stitch_kernel_equals_quad_and_pixel_kernels(cuda_dev, label_dtype, case):
+    """The 16x2-strip stitch kernel (label map only, bf16 logits) must give the SAME labels, bit for bit, as the quad and
+    the one-pixel kernels: cfg-3 plan (origins {0, 384, 512}: all 16-aligned -> vector path), a plan mixing aligned and
+    unaligned / odd origins (per-pixel path inside the strip kernel, strips cut by window borders), and a plan that
+    leaves pixels uncovered (sum 0 for every class -> label 0)."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    nc = 7
+    if case == "cfg3":
+        n_img, H, W, hc, wc = 2, 1024, 1024, 512, 512
+        plan, _, _ = emrt_b200.plan_windows([(H, W)] * n_img, (wc, hc), (384, 384))
+        wins = [(p[0], p[1], p[2]) for p in plan]
+    else:
+        n_img, H, W, hc, wc = 2, 96, 160, 32, 48
+        wins = [(0, 0, 0), (0, 0, 48), (0, 16, 112), (0, 17, 5), (0, 38, 11), (0, 64, 96), (0, 3, 33), (1, 0, 0), (1, 64, 112), (1, 19, 21),
+                (1, 32, 16), (0, 32, 32)]
+        if case == "mixed":
+            for img in range(n_img):
+                for y in list(range(0, H - hc + 1, 16)) + [H - hc]:
+                    for x in list(range(0, W - wc + 1, 32)) + [W - wc]:
+                        wins.append((img, y, x))
+        wins.sort(key=lambda w: w[0])
+    half = torch.from_numpy(O.rng_normal(rng, (len(wins), nc, hc // 2, wc // 2))).to(cuda_dev).bfloat16()
+    # ties: make a few windows' classes exactly equal so the first-max rule is exercised
+    half[0, 1] = half[0, 0]
+    half[-1, 3] = half[-1, 2]
+    t = lambda k: torch.tensor([w[k] for w in wins], dtype=torch.int32, device=cuda_dev)
+    run = lambda: ops.stitch_argmax_fused(half, t(0), t(1), t(2), n_img, H, W, label_dtype=label_dtype)[0]
+    lab_s = run()
+    outs = {}
+    for env in ("EMRT_STITCH_QUAD", "EMRT_STITCH_PIXEL"):
+        os.environ[env] = "1"
+        try:
+            outs[env] = run()
+        finally:
+            del os.environ[env]
+    assert torch.equal(lab_s, outs["EMRT_STITCH_QUAD"]) and torch.equal(lab_s, outs["EMRT_STITCH_PIXEL"])
+    assert lab_s.dtype == label_dtype and int(lab_s.max()) < nc
+    if case == "uncovered":
+        cover = torch.zeros(n_img, H, W)
+        for (i, y, x) in wins:
+            cover[i, y:y + hc, x:x + wc] += 1
+        assert (cover == 0).any() and bool((lab_s.cpu()[:, 0][cover == 0] == 0).all())
