@@ -79,6 +79,17 @@ SIGNATURES = {
     "emrt_stitch_argmax_fused": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "emrt_stitch_argmax_eval": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "emrt_calculate_area": (C.c_int, [_P, _P, _L, _I, _I, _P, _P]),
+    "emrt_layernorm_bwd_workspace_floats": (C.c_int64, [_L, _I]),
+    "emrt_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, C.c_float, _I, _P]),
+    "emrt_groupnorm_bwd_workspace_floats": (C.c_int64, [_I, _I, _I, _I]),
+    "emrt_groupnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_float, _I32P, _I, _I, _P]),
+    "emrt_relu_bwd": (C.c_int, [_P, _P, _P, _L, _I, _P]),
+    "emrt_batch_sum": (C.c_int, [_P, _P, _I, _L, _I, _P]),
+    "emrt_column_sum": (C.c_int, [_P, _P, _L, _I, _I, _P]),
+    "emrt_sigmoid_fwd": (C.c_int, [_P, _P, _L, _P]),
+    "emrt_sigmoid_bwd": (C.c_int, [_P, _P, _P, _L, _P]),
+    "emrt_mha_small_bwd": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, C.c_float, _I, _P]),
+    "emrt_conv3x3_tokens_bwd_weight": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I32P, _I, _I, _P]),
 }
 
 _lib = None

@@ -4,7 +4,9 @@
   * ``TransformerDecoder``       — :298-334
   * ``EncoderDecoder``           — :337-473 (input_proj 1x1 conv + GroupNorm, sine position embedding + level embed,
                                     query embeddings, reference-point Linear + sigmoid, encoder, decoder)
-Same constructor arguments, parameter names (state-dict keys) and forward signatures; inference only.  All arithmetic on
+Same constructor arguments, parameter names (state-dict keys) and forward signatures.  Inference runs the fused kernels;
+when gradients are required (cfg 4: the reference trains the whole EncoderDecoder) every layer runs as a differentiable
+composition whose forward AND backward steps are kernels (emrt_b200/autograd.py).  All arithmetic on
 activations runs in libemrt_b200.so; what is computed on the host is input-independent and cached: the sine position
 embedding (position_encoding.py:51-75 with an all-ones mask) + level embedding, and the decoder reference points
 sigmoid(Linear(query_pos_embed.weight)) (:466) — functions of the weights and the level shapes only.
@@ -41,6 +43,9 @@ def position_embedding_sine_host(h: int, w: int, num_pos_feats=128, temperature=
     pos_x = np.stack((np.sin(pos_x[..., 0::2]), np.cos(pos_x[..., 1::2])), axis=3).reshape(h, w, -1)
     pos_y = np.stack((np.sin(pos_y[..., 0::2]), np.cos(pos_y[..., 1::2])), axis=3).reshape(h, w, -1)
     return np.concatenate((pos_y, pos_x), axis=2).reshape(h * w, -1).astype(f)
+
+
+TRAINABLE = True      # the whole EncoderDecoder has a backward (emrt_b200/train.py::build_train_step uses it for cfg 4)
 
 
 class MultiHeadAttention(nn.Module):
@@ -100,8 +105,40 @@ class TransformerDecoderLayer(nn.Module):
         self._packed = (ver, pk)
         return pk
 
-    @torch.no_grad()
+    _emrt_train = False
+
+    def train(self, mode: bool = True):
+        self._emrt_train = bool(mode)          # see TransformerEncoderLayer.train
+        return super().train(mode)
+
     def forward(self, tgt, reference_points, memory, memory_spatial_shapes, memory_mask=None, query_pos_embed=None):
+        if self._emrt_train and torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in (tgt, memory, reference_points, query_pos_embed))
+                                        or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(tgt, reference_points, memory, memory_spatial_shapes, memory_mask, query_pos_embed)
+        with torch.no_grad():
+            return self._forward_eval(tgt, reference_points, memory, memory_spatial_shapes, memory_mask, query_pos_embed)
+
+    def _forward_train(self, tgt, reference_points, memory, memory_spatial_shapes, memory_mask=None, query_pos_embed=None):
+        """t_e_d.py:282-295 as a differentiable composition of kernel-backed autograd Functions (emrt_b200/autograd.py)."""
+        from . import autograd as A
+        shapes = shapes_to_host(memory_spatial_shapes)
+        impl = self.gemm_impl if tgt.dtype == torch.bfloat16 else L.IMPL_SIMT
+        C_, M = self.d_model, self.n_head
+        sa = self.self_attn
+        with_pos = lambda t: t if query_pos_embed is None else A.add(t, query_pos_embed)
+        # self attention (layers.py:221-234,282-301): q = k = tgt + pos, value = tgt; in_proj_weight [C, 3C] sliced per use
+        qk = A.linear(with_pos(tgt), sa.in_proj_weight[:, :2 * C_], sa.in_proj_bias[:2 * C_], impl=impl)
+        v = A.linear(tgt, sa.in_proj_weight[:, 2 * C_:], sa.in_proj_bias[2 * C_:], impl=impl)
+        att = A.SelfAttentionCoreFn.apply(qk, v, M, float(C_ // M) ** -0.5)
+        tgt2 = A.linear(att, sa.out_proj.weight, sa.out_proj.bias, impl=impl)
+        tgt = A.add_layernorm(tgt, tgt2, self.norm1)
+        tgt2 = self.cross_attn(with_pos(tgt), reference_points, memory, shapes, memory_mask)
+        tgt = A.add_layernorm(tgt, tgt2, self.norm2)
+        h = A.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True, impl=impl)
+        f = A.linear(h, self.linear2.weight, self.linear2.bias, impl=impl)
+        return A.add_layernorm(tgt, f, self.norm3)
+
+    def _forward_eval(self, tgt, reference_points, memory, memory_spatial_shapes, memory_mask=None, query_pos_embed=None):
         shapes = shapes_to_host(memory_spatial_shapes)
         tgt = tgt.contiguous()
         fast = tgt.dtype == torch.bfloat16
@@ -145,7 +182,6 @@ class TransformerDecoder(nn.Module):
         self.num_layers = num_layers
         self.return_intermediate = return_intermediate
 
-    @torch.no_grad()
     def forward(self, tgt, memory, reference_points, memory_spatial_shapes, memory_mask=None, query_pos_embed=None,
                 valid_ratios=None):
         output = tgt
@@ -251,10 +287,59 @@ class EncoderDecoder(nn.Module):
             off += shapes[l][0] * shapes[l][1]
         return src, shapes, c
 
-    @torch.no_grad()
+    _emrt_train = False
+
+    def train(self, mode: bool = True):
+        """`.train()` (train.py:139) selects the differentiable path, `.eval()` the fused inference kernels; a freshly
+        constructed model runs the inference path."""
+        self._emrt_train = bool(mode)
+        return super().train(mode)
+
     def forward(self, src_feats: Sequence[torch.Tensor], src_psp, src_mask=None):
         if src_mask is not None:
             raise L.EmrtError("EMRT never passes src_mask (paddle_EMRT.py:265); the masked path is not built")
+        if self._emrt_train and torch.is_grad_enabled() and (any(t.requires_grad for t in list(src_feats) + [src_psp])
+                                        or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(src_feats, src_psp)
+        with torch.no_grad():
+            return self._forward_eval(src_feats, src_psp)
+
+    def _forward_train(self, src_feats: Sequence[torch.Tensor], src_psp):
+        """t_e_d.py:416-473 with gradients to every parameter the reference trains (input_proj, level_embed, encoder,
+        query_pos_embed, reference_points, decoder; tgt_embed is unused, :368) and to the inputs: a composition of
+        kernel-backed autograd Functions (emrt_b200/autograd.py)."""
+        from . import autograd as A
+        x0 = src_feats[0]
+        B, dtype, dev = x0.shape[0], x0.dtype, x0.device
+        shapes = tuple((int(f.shape[2]), int(f.shape[3])) for f in src_feats)
+        impl = L.IMPL_AUTO if dtype == torch.bfloat16 else L.IMPL_SIMT
+        srcs = []
+        for l, f in enumerate(src_feats):                                                # input_proj (:417-419)
+            conv, gn = getattr(self.input_proj[l], "0"), getattr(self.input_proj[l], "1")
+            w_kn = conv.weight.reshape(conv.weight.shape[0], -1).t()                      # [Cin, C] = Linear [in, out]
+            y = A.linear(A.TokensFn.apply(f), w_kn, conv.bias, impl=impl)
+            srcs.append(A.GroupNormTokensFn.apply(y, gn.weight, gn.bias, 1e-5))
+        src = torch.cat(srcs, 1)
+        pos = A.PosEmbedFn.apply(self.level_embed.weight, self._sine(shapes, dev), shapes, dtype)
+        mask = torch.ones((B, src.shape[1]), dtype=torch.float32, device=dev)
+        memory = self.encoder(src, shapes, mask, pos)
+        ref_dec = A.ReferencePointsFn.apply(self.query_pos_embed.weight, self.reference_points.weight,
+                                            self.reference_points.bias, len(shapes))
+        qpos = self.query_pos_embed.weight[None].to(dtype)
+        tgt = A.TokensFn.apply(src_psp)
+        hs = self.decoder(tgt, memory, ref_dec, shapes, mask, qpos)
+        return hs, memory
+
+    def _sine(self, shapes, device):
+        """Sine position embedding of every level, fp32 [Lv, C] on the device (input-independent; cached per shape)."""
+        key = (shapes, str(device))
+        hit = getattr(self, "_sine_cache", None)
+        if hit is None or hit[0] != key:
+            sine = np.concatenate([position_embedding_sine_host(h, w, self.hidden_dim // 2) for (h, w) in shapes], 0)
+            self._sine_cache = (key, torch.from_numpy(sine).to(device))
+        return self._sine_cache[1]
+
+    def _forward_eval(self, src_feats: Sequence[torch.Tensor], src_psp):
         src, shapes, c = self.project_inputs(src_feats)
         B, Lv, dev = src.shape[0], src.shape[1], src.device
         mask = torch.ones((B, Lv), dtype=torch.float32, device=dev)                    # mask_flatten (:451)

@@ -3,8 +3,10 @@
   * ``TransformerEncoder``      — :207-239
 Same constructor arguments, sub-layer names (state-dict keys: ``self_attn.*``, ``norm1``, ``linear1``, ``linear2``,
 ``norm2``, ``conv{0,1,2}.0.weight`` [Cout,Cin,3,3], ``conv{l}.1.weight/bias`` GroupNorm) and forward signatures.
-Inference only (dropout is the identity in eval mode); all arithmetic runs in libemrt_b200.so on the token layout
-[B, Lv, C], so the reference's seq2_2D / flatten / transpose / concat copies (:163-196) do not exist here.
+Dropout is the identity (eval-mode semantics).  Inference runs the fused kernels; when gradients are required the same
+layer runs as a differentiable composition whose forward and backward steps are all kernels (emrt_b200/autograd.py).  All
+arithmetic runs in libemrt_b200.so on the token layout [B, Lv, C], so the reference's seq2_2D / flatten / transpose /
+concat copies (:163-196) do not exist here.
 """
 from __future__ import annotations
 
@@ -82,8 +84,45 @@ class TransformerEncoderLayer(nn.Module):
         self._packed = (ver, pk)
         return pk
 
-    @torch.no_grad()
+    _emrt_train = False
+
+    def train(self, mode: bool = True):
+        """`.train()` (train.py:139) switches to the differentiable path, `.eval()` back to the fused inference kernels.  A
+        freshly constructed layer runs the inference path (nn.Module's own default `training = True` does not count)."""
+        self._emrt_train = bool(mode)
+        return super().train(mode)
+
+    def _wants_grad(self, *tensors):
+        return self._emrt_train and torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors)
+                                                                 or any(p.requires_grad for p in self.parameters()))
+
     def forward(self, src, reference_points, spatial_shapes, src_mask=None, pos_embed=None):
+        if self._wants_grad(src, pos_embed):
+            return self._forward_train(src, reference_points, spatial_shapes, src_mask, pos_embed)
+        with torch.no_grad():
+            return self._forward_eval(src, reference_points, spatial_shapes, src_mask, pos_embed)
+
+    def _forward_train(self, src, reference_points, spatial_shapes, src_mask=None, pos_embed=None):
+        """The same layer (t_e_d.py:184-204) as a differentiable composition: every step is an autograd.Function whose
+        forward and backward are kernels of libemrt_b200.so (emrt_b200/autograd.py).  Dropout is the identity
+        (the mirrors implement eval-mode dropout; train with dropout = 0 for parity with the reference's step)."""
+        from . import autograd as A
+        shapes = shapes_to_host(spatial_shapes)
+        if len(shapes) != 3:
+            raise L.EmrtError("the reference's encoder layer is written for 3 feature levels (conv0..conv2)")
+        impl = self.gemm_impl if src.dtype == torch.bfloat16 else L.IMPL_SIMT
+        convs = [getattr(self, f"conv{l}") for l in range(3)]
+        branch = A.ConvBranchFn.apply(src, shapes, impl, 1e-5, *[getattr(c, "0").weight for c in convs],
+                                      *[getattr(c, "1").weight for c in convs], *[getattr(c, "1").bias for c in convs])
+        q = src if pos_embed is None else A.add(src, pos_embed)                                     # with_pos_embed (:198)
+        src2 = self.self_attn(q, reference_points, src, shapes, src_mask)
+        x = A.add_layernorm(src, src2, self.norm1)                                                  # :199-200
+        h = A.linear(x, self.linear1.weight, self.linear1.bias, relu=True, impl=impl)               # :157-158
+        f = A.linear(h, self.linear2.weight, self.linear2.bias, impl=impl)
+        y = A.add_layernorm(x, f, self.norm2)                                                       # :159-160
+        return A.add(y, branch)                                                                     # :203
+
+    def _forward_eval(self, src, reference_points, spatial_shapes, src_mask=None, pos_embed=None):
         shapes = shapes_to_host(spatial_shapes)
         if len(shapes) != 3:
             raise L.EmrtError("the reference's encoder layer is written for 3 feature levels (conv0..conv2)")
@@ -121,7 +160,6 @@ class TransformerEncoder(nn.Module):
 
     get_reference_points = staticmethod(get_reference_points)
 
-    @torch.no_grad()
     def forward(self, src, spatial_shapes, src_mask=None, pos_embed=None, valid_ratios=None):
         output = src
         reference_points = get_reference_points(spatial_shapes, valid_ratios, device=src.device)

@@ -300,8 +300,9 @@ def conv3x3_tokens(x, w_packed, shapes, impl=L.IMPL_AUTO, out=None):
     return out
 
 
-def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, out=None):
-    """GELU(GroupNorm_l(conv)) + x per level; gamma / beta f32 [L, C]."""
+def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, out=None, return_stats=False):
+    """GELU(GroupNorm_l(conv)) + x per level; gamma / beta f32 [L, C].  return_stats: also the statistics workspace
+    (its first 2 * B * L * groups floats are the (sum, sum of squares) the backward needs)."""
     B, Lv, C = x.shape
     hw, _, _ = level_tables(shapes)
     if out is None:
@@ -309,7 +310,7 @@ def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, o
     ws = torch.empty((int(L.load().emrt_groupnorm_workspace_floats(B, len(shapes), groups)),), dtype=torch.float32, device=x.device)
     L.check(L.load().emrt_groupnorm_gelu_residual(_ptr(conv), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(ws), B, Lv,
                                                   C, len(shapes), groups, float(eps), hw, _dt(x), _stream()))
-    return out
+    return (out, ws) if return_stats else out
 
 
 def groupnorm_stats(x, shapes, groups=32):
@@ -345,7 +346,7 @@ def nchw_to_tokens(x):
     return y
 
 
-def groupnorm_tokens_into(x, gamma, beta, out, token_offset, groups=32, eps=1e-5):
+def groupnorm_tokens_into(x, gamma, beta, out, token_offset, groups=32, eps=1e-5, return_stats=False):
     """GroupNorm of one level's tokens x [B, P, C] written into out[:, token_offset:token_offset+P, :] (out [B, Lv, C])."""
     B, P, C_ = x.shape
     assert out.is_contiguous() and out.shape[0] == B and out.shape[2] == C_ and out.dtype == x.dtype
@@ -353,7 +354,7 @@ def groupnorm_tokens_into(x, gamma, beta, out, token_offset, groups=32, eps=1e-5
     dst = C.c_void_p(out.data_ptr() + token_offset * C_ * out.element_size())
     L.check(L.load().emrt_groupnorm_tokens(_ptr(x), _ptr(gamma), _ptr(beta), dst, out.shape[1] * C_, _ptr(ws), B, P, C_,
                                            groups, float(eps), _dt(x), _stream()))
-    return out
+    return (out, ws) if return_stats else out
 
 
 def mha_small(q, k, v, num_heads, scale):
@@ -455,3 +456,108 @@ def calculate_area(pred, label, num_classes, ignore_index=255):
     L.check(L.load().emrt_calculate_area(_ptr(pred), _ptr(label), pred.numel(), num_classes, int(ignore_index),
                                          _ptr(areas), _stream()))
     return areas
+
+
+# ---- backward of the encoder / decoder glue (cfg 4) -----------------------------------------------------------------
+def layernorm_bwd(a, b, gamma, dy, dgamma, dbeta, eps=1e-5):
+    """Backward of y = LayerNorm(a + b) * gamma + beta: returns dz (the gradient of a and of b); dgamma / dbeta f32 [N] are
+    accumulated in place."""
+    N = a.shape[-1]
+    rows = a.numel() // N
+    lib = L.load()
+    ws = torch.empty((int(lib.emrt_layernorm_bwd_workspace_floats(rows, N)) + 2 * N,), dtype=torch.float32, device=a.device)
+    dz = torch.empty_like(a)
+    L.check(lib.emrt_layernorm_bwd(_ptr(a), _ptr(b), _ptr(gamma), _ptr(dy), _ptr(dz), _ptr(dgamma), _ptr(dbeta), _ptr(ws),
+                                   rows, N, float(eps), _dt(a), _stream()))
+    return dz
+
+
+def groupnorm_bwd(x, dy, stats, gamma, beta, dgamma, dbeta, shapes, groups=32, eps=1e-5, gelu=False):
+    """Backward of GroupNorm_l (+ GELU) on tokens x [B, Lv, C]: returns dx; dgamma / dbeta f32 [L, C] accumulated in place.
+    stats: groupnorm_stats(x) (or the workspace a forward returned with return_stats=True)."""
+    B, Lv, C = x.shape
+    hw, _, total = level_tables(shapes)
+    assert total == Lv
+    lib = L.load()
+    ws = torch.empty((int(lib.emrt_groupnorm_bwd_workspace_floats(B, len(shapes), C, groups)),), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    L.check(lib.emrt_groupnorm_bwd(_ptr(x), _ptr(dy), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                   _ptr(ws), B, Lv, C, len(shapes), groups, float(eps), hw, int(bool(gelu)), _dt(x), _stream()))
+    return dx
+
+
+def relu_bwd(dy, y, out=None):
+    if out is None:
+        out = torch.empty_like(dy)
+    L.check(L.load().emrt_relu_bwd(_ptr(dy), _ptr(y), _ptr(out), dy.numel(), _dt(dy), _stream()))
+    return out
+
+
+def batch_sum(x):
+    """x [B, ...] -> f32 [...]: sum over the leading dimension."""
+    B = x.shape[0]
+    out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+    L.check(L.load().emrt_batch_sum(_ptr(x), _ptr(out), B, x.numel() // B, _dt(x), _stream()))
+    return out
+
+
+def column_sum(x, out=None):
+    """x [rows, N] -> f32 [N] (accumulated into `out` when given)."""
+    N = x.shape[-1]
+    if out is None:
+        out = torch.zeros((N,), dtype=torch.float32, device=x.device)
+    L.check(L.load().emrt_column_sum(_ptr(x), _ptr(out), x.numel() // N, N, _dt(x), _stream()))
+    return out
+
+
+def sigmoid(x):
+    y = torch.empty_like(x)
+    L.check(L.load().emrt_sigmoid_fwd(_ptr(x), _ptr(y), x.numel(), _stream()))
+    return y
+
+
+def sigmoid_bwd(dy, y):
+    dx = torch.empty_like(y)
+    L.check(L.load().emrt_sigmoid_bwd(_ptr(dy), _ptr(y), _ptr(dx), y.numel(), _stream()))
+    return dx
+
+
+def mha_small_bwd(q, k, v, d_out, num_heads, scale):
+    """Backward of mha_small: -> (dqk [B, L, 2C] = [dq | dk] when Lq == Lk else (dq, dk), dv)."""
+    B, Lq, C_ = q.shape
+    Lk = k.shape[1]
+    dev = q.device
+    if Lq == Lk:
+        dqk = torch.empty((B, Lq, 2 * C_), dtype=q.dtype, device=dev)
+        dq, dk = dqk[..., :C_], dqk[..., C_:]
+    else:
+        dqk = None
+        dq = torch.empty((B, Lq, C_), dtype=q.dtype, device=dev)
+        dk = torch.empty((B, Lk, C_), dtype=q.dtype, device=dev)
+    dv = torch.empty((B, Lk, C_), dtype=q.dtype, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    L.check(L.load().emrt_mha_small_bwd(p(q), q.stride(1), p(k), k.stride(1), p(v), v.stride(1), _ptr(d_out.contiguous()),
+                                        p(dq), dq.stride(1), p(dk), dk.stride(1), p(dv), dv.stride(1), B, Lq, Lk, num_heads,
+                                        C_ // num_heads, float(scale), _dt(q), _stream()))
+    return (dqk if dqk is not None else (dq, dk)), dv
+
+
+def conv3x3_tokens_bwd_weight(x, dy, shapes, impl=L.IMPL_AUTO):
+    """-> dw f32 [L, Cout, Cin, 3, 3]: the weight gradient of conv3x3_tokens per level (Paddle Conv2D layout)."""
+    B, Lv, C_ = x.shape
+    hw, _, total = level_tables(shapes)
+    assert total == Lv
+    nL = len(shapes)
+    dw = torch.zeros((nL, C_, C_, 3, 3), dtype=torch.float32, device=x.device)
+    ws = torch.empty((nL * 9 * C_ * C_,), dtype=torch.float32, device=x.device)
+    L.check(L.load().emrt_conv3x3_tokens_bwd_weight(_ptr(x), _ptr(dy), _ptr(dw), _ptr(ws), B, Lv, C_, nL, hw, _dt(x), int(impl),
+                                                    _stream()))
+    return dw
+
+
+def tokens_to_nchw(y, spatial):
+    """[B, P, C] -> [B, C, *spatial]: the inverse of nchw_to_tokens (the same batched transpose with the roles swapped)."""
+    B, P, C_ = y.shape
+    x = torch.empty((B, C_, P), dtype=y.dtype, device=y.device)
+    L.check(L.load().emrt_nchw_to_tokens(_ptr(y.contiguous()), _ptr(x), B, P, C_, _dt(y), _stream()))
+    return x.view(B, C_, *spatial)

@@ -306,6 +306,53 @@ int emrt_stitch_argmax_eval(const void* half_logits, int in_dtype, void* labels,
 int emrt_calculate_area(const int32_t* pred, const int32_t* label, int64_t n, int nc, int ignore_index,
                         long long* areas, void* stream);
 
+
+/* ---- cfg 4: backward of the encoder / decoder glue (the reference trains the whole EncoderDecoder: train.py:146-159 drives
+ * Paddle autograd through transformer_encoder_decoder.py:184-204,282-295 and layers.py:236-311).  Parameter gradients are
+ * ACCUMULATED into fp32 tensors (the all-reduce buckets) and reduced in a fixed order: no floating-point atomics except the
+ * split-K adds of the two tcgen05 weight-gradient kernels.  dtype F32|BF16 everywhere.
+ *
+ * LayerNorm backward (nn.LayerNorm, t_e_d.py:116,123,199-200,159-160): y = LN(a + b) * gamma + beta (b may be NULL);
+ * dz [rows, N] (the gradient of a and of b), dgamma / dbeta F32 [N] accumulated.  N in {64,128,256,512}.
+ * workspace: emrt_layernorm_bwd_workspace_floats(rows, N) + 2 * N floats.                                                */
+int64_t emrt_layernorm_bwd_workspace_floats(int64_t rows, int N);
+int emrt_layernorm_bwd(const void* a, const void* b, const float* gamma, const void* dy, void* dz, float* dgamma,
+                       float* dbeta, float* workspace, int64_t rows, int N, float eps, int dtype, void* stream);
+
+/* GroupNorm (+ exact GELU when gelu != 0) backward on tokens (conv{l}.1 + GELU, t_e_d.py:125-144,187-189; input_proj.{l}.1,
+ * :417-419 with L = 1): x, dy, dx [B, Lv, C]; stats = emrt_groupnorm_stats' sums [B, L, groups, 2] of x; gamma / beta
+ * F32 [L, C]; dgamma / dbeta F32 [L, C] accumulated.  workspace: emrt_groupnorm_bwd_workspace_floats floats.            */
+int64_t emrt_groupnorm_bwd_workspace_floats(int B, int L, int C, int groups);
+int emrt_groupnorm_bwd(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta, void* dx,
+                       float* dgamma, float* dbeta, float* workspace, int B, int Lv, int C, int L, int groups, float eps,
+                       const int32_t* shapes_hw_host, int gelu, int dtype, void* stream);
+
+/* dx = y > 0 ? dy : 0 (F.relu of the FFN, t_e_d.py:157,293); in place allowed.                                           */
+int emrt_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, void* stream);
+
+/* out F32 [n] = sum_b x[b, :] (gradient of a batch-shared addend: with_pos_embed, t_e_d.py:154-155).                     */
+int emrt_batch_sum(const void* x, float* out, int B, int64_t n, int dtype, void* stream);
+
+/* out F32 [N] += column sums of x [rows, N] (bias / level_embed gradients).                                               */
+int emrt_column_sum(const void* x, float* out, int64_t rows, int N, int dtype, void* stream);
+
+/* F.sigmoid of the decoder's reference-point head (t_e_d.py:466) and its backward dx = dy * y * (1 - y); F32.            */
+int emrt_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
+int emrt_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+
+/* Backward of emrt_mha_small (layers.py:282-301): dq / dk / dv with row strides (elements), same q / k / v views as the
+ * forward, d_out [B, Lq, M*D] contiguous.  D = 32; one head's Q, K, V, dO and P must fit 200 KB of shared memory.        */
+int emrt_mha_small_bwd(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld,
+                       const void* d_out, void* dq, int64_t dq_ld, void* dk, int64_t dk_ld, void* dv, int64_t dv_ld, int B,
+                       int Lq, int Lk, int M, int D, float scale, int dtype, void* stream);
+
+/* Weight gradient of emrt_conv3x3_tokens_fwd: dw F32 [L, Cout, Cin, 3, 3] (Paddle Conv2D layout per level) +=
+ * sum_{b, pixel} x[b, pixel + tap, ci] dy[b, pixel, co].  bf16: tcgen05 (the conv's shifted 4-D TMA boxes as the MN-major
+ * A operand, split-K); otherwise / impl = 1: SIMT.  workspace: L * 9 * C * C floats.  (The data gradient is
+ * emrt_conv3x3_tokens_fwd itself on dy with the flipped, transposed weights.)                                            */
+int emrt_conv3x3_tokens_bwd_weight(const void* x, const void* dy, float* dw, float* workspace, int B, int Lv, int C, int L,
+                                   const int32_t* shapes_hw_host, int dtype, int impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

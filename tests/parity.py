@@ -9,18 +9,23 @@ on the same bf16-rounded inputs and matrices:
   rounded  float64 arithmetic with the kernels' roundings applied (oracle.kernel_storage_rounding): bf16 activations, fp16
            pixel offsets / softmax weights / row-bias tables, bf16 corner weights in the window gather — nothing else;
 and hold the kernels to two rules:
+  STAGE RULE (tests/test_gpu_rounding_stages.py) — every KERNEL, fed the rounded oracle's own stored operands, reproduces
+      the rounded oracle's stored output within 5e-4 relative L2: the kernels' own error (accumulation order, exp / erf
+      approximations), observable only one store at a time.
   LAYER RULE (assert_layers_match) — every layer (input_proj, each encoder layer, each decoder layer), FED THE ROUNDED
-      ORACLE'S OWN INPUT, reproduces the rounded oracle's output within OWN_TOL = 1e-3 relative L2.  This is the kernels'
-      own error (accumulation order, exp / erf approximations, the rare 1-ulp flip where fp32 and float64 land on
-      different sides of a rounding boundary).  It has to be checked per layer: rounding is discontinuous, so two
-      evaluations that differ by 3e-4 after layer 1 round ~8 % of layer 2's elements to different neighbours, and their
-      END-TO-END distance grows to ~sqrt(own x ulp) per store whatever the kernels do.
+      ORACLE'S OWN INPUT, reproduces the rounded oracle's output within OWN_TOL = 1e-3 (encoder: three chained stores) /
+      DEC_LAYER_TOL = 3e-3 (decoder: six).  Rounding is discontinuous: two evaluations that differ by delta before a store
+      round ~delta / ulp of its elements to different neighbours, so their distance after it is ~sqrt(delta x ulp) — it
+      compounds towards the rounding noise itself (~1 - 2e-3) whatever the kernels do, which is why the chain is cut at
+      every layer here and at every kernel in the stage rule.
   DEPTH RULE (assert_bf16_parity) — end to end, the kernels are no further from the exact evaluation than the storage
       formats alone put the rounded oracle: |kernels - exact| <= 1.15 |rounded - exact| + 5e-4, and never above HARD_TOL.
 No threshold above 1e-2 is applied to anything the kernels themselves contribute."""
 import torch
 
-OWN_TOL = 1e-3       # per layer, kernels vs the same-rounding-points oracle on the oracle's own input
+OWN_TOL = 1e-3       # per encoder layer / input_proj, kernels vs the same-rounding-points oracle on the oracle's own input
+DEC_LAYER_TOL = 3e-3  # per decoder layer: six chained stores — 1-ulp flips compound towards the rounding noise itself
+                      # (delta -> sqrt(delta x ulp) per store); every KERNEL of it is held to 5e-4 in test_gpu_rounding_stages.py
 HARD_TOL = 2e-2      # end to end, never exceeded whatever the split says
 
 
@@ -87,6 +92,6 @@ def assert_layers_match(model, feats, trace, dev, own_tol=OWN_TOL):
             errs[f"decoder.layers.{i}"] = l2(got.float(), trace["dec"][i])
             t_in = trace["dec"][i]
     print("per layer, kernels vs same-rounding oracle on the oracle's input: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
-    bad = {k: v for k, v in errs.items() if v > own_tol}
+    bad = {k: v for k, v in errs.items() if v > (DEC_LAYER_TOL if k.startswith("decoder") else own_tol)}
     assert not bad, bad
     return errs
