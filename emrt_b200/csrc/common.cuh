@@ -126,14 +126,17 @@ template <> struct Vec16<__nv_bfloat16> {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  // per device ordinal (a process may drive several GPUs); benign race: every thread writes the same value
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  if (n[slot] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[slot] = v > 0 ? v : 148;
   }
-  return n;
+  return n[slot];
 }
 
 }  // namespace emrt

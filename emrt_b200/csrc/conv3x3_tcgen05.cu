@@ -229,11 +229,8 @@ int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int L
   const uint32_t bw[2] = {(uint32_t)CV_BK, (uint32_t)CV_N};
   if (int e = make_tensor_map(&p.tma_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   const int smem_bytes = (int)sizeof(ConvSmem) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tokens_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  // per launch: function attributes are per context (a second GPU in the same process needs its own opt-in) and this is cheap
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tokens_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv3x3_tokens_tc_kernel<<<grid, CV_THREADS, smem_bytes, st>>>(p);
   EMRT_LAUNCH_CHECK();

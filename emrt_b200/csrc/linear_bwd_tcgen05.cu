@@ -247,11 +247,7 @@ int linear_bwd_weight_tc(const void* x, const void* dy, float* dw, int64_t rows,
   if (p.splits < 1) p.splits = 1;
   if (p.splits > p.chunks) p.splits = p.chunks;
   const int smem_bytes = (int)sizeof(DwSmem) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(linear_bwd_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(linear_bwd_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));   // per context
   linear_bwd_weight_tc_kernel<<<tiles * p.splits, DW_THREADS, smem_bytes, st>>>(p);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;

@@ -87,12 +87,9 @@ extern "C" int emrt_mha_small(const void* q, int64_t q_ld, const void* k, int64_
   if (Lk > MHA_MAX_LK) return set_error(EMRT_ERR_UNSUPPORTED, "mha_small holds K/V of one head in shared memory: Lk <= %d (got %d)", MHA_MAX_LK, Lk);
   const size_t smem = sizeof(float) * ((size_t)Lk * 32 * 2);
   cudaStream_t st = as_stream(stream);
-  static bool attr = false;
-  if (!attr) {
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(mha_small_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(mha_small_kernel<__nv_bfloat16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(mha_small_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(mha_small_kernel<__nv_bfloat16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+
   // one CTA (4 warps x 32 queries) per (batch, head) and 128 queries
   const int splits = (Lq + 32 * MHA_WARPS - 1) / (32 * MHA_WARPS);
   const dim3 grid((unsigned)(B * M), (unsigned)splits);

@@ -647,11 +647,7 @@ static int launch_bwd_win(const void* go, const void* value, const void* loc, co
                           int64_t ref_bs, float* gv, float* gl, float* ga, int B, const BwdWinParams& p,
                           size_t smem_bytes, cudaStream_t st) {
   auto kern = msda_gather_bwd_win_kernel<TL, MODE, BW_WARPS, PLAIN>;
-  static size_t attr = 0;
-  if (smem_bytes > attr) {
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    attr = smem_bytes;
-  }
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));   // per context
   const int n_regions = p.regions_x * p.regions_y;
   if (B > 65535 || n_regions > 65535) return EMRT_ERR_UNSUPPORTED;
   kern<<<dim3((unsigned)p.M, (unsigned)n_regions, (unsigned)B), BW_WARPS * 32, smem_bytes, st>>>(
@@ -665,11 +661,7 @@ static int launch_bwd_win2(const void* go, const void* value, const void* loc, c
                            int64_t ref_bs, float* gv, float* gl, float* ga, int B, const Bwd2Params& p, size_t smem_bytes,
                            cudaStream_t st) {
   auto kern = msda_gather_bwd_win2_kernel<TL, MODE, NW>;
-  static size_t attr = 0;
-  if (smem_bytes > attr) {
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    attr = smem_bytes;
-  }
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));   // per context
   const int n_regions = p.regions_x * p.regions_y;
   if (B > 65535 || n_regions > 65535) return EMRT_ERR_UNSUPPORTED;
   kern<<<dim3((unsigned)p.M, (unsigned)n_regions, (unsigned)B), NW * 32, smem_bytes, st>>>(

@@ -267,11 +267,7 @@ template <typename TL, int MODE, int NW, bool STATIC>
 static int launch_win(const void* value, const void* loc, const void* attn, const float* ref, int64_t ref_bs, void* out,
                       int B, const WinParams& p, size_t smem_bytes, cudaStream_t st) {
   auto kern = msda_gather_fwd_win_kernel<TL, MODE, NW, STATIC>;
-  static size_t attr = 0;
-  if (smem_bytes > attr) {
-    EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    attr = smem_bytes;
-  }
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));   // per context
   const int n_regions = p.regions_x * p.regions_y;
   if (B > 65535 || n_regions > 65535) return EMRT_ERR_UNSUPPORTED;
   kern<<<dim3((unsigned)p.M, (unsigned)n_regions, (unsigned)B), NW * 32, smem_bytes, st>>>(

@@ -52,6 +52,10 @@ def _ptr(t: Optional[torch.Tensor]):
         raise L.EmrtError("emrt_b200 ops need CUDA tensors (no CPU fallback)")
     if not t.is_contiguous():
         raise L.EmrtError("emrt_b200 ops need contiguous tensors")
+    if t.device.index != torch.cuda.current_device():
+        # the launch goes to the CURRENT device's current stream: a tensor living elsewhere would be a wrong-device launch
+        raise L.EmrtError(f"tensor on {t.device} but the current device is cuda:{torch.cuda.current_device()}: "
+                          "wrap the call in `with torch.cuda.device(tensor.device):`")
     return C.c_void_p(t.data_ptr())
 
 

@@ -4,6 +4,7 @@
 #   bench      default bench + reference arm      launches  ncu launch list of a 2-step bench -> TAG_launches.{csv,md}
 #   gather     ncu --set full of the window gather ln        ncu --set full of the fused Linear + LayerNorm GEMM
 #   train      cfg-4 training step                micro     shared-memory-pipe floor microbenchmark
+#   multi      bench under torchrun at NGPU ranks (use with gpurun --gpus N)
 # Everything lands in gpurun_out/TAG_*; the summaries worth keeping are copied to profiles/ by hand.
 TAG=${1:-x}; shift
 WHAT=${@:-tests bench launches}
@@ -30,6 +31,11 @@ ln)
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > /dev/null 2>&1 ;;
 train)
   timeout 600 python scripts/bench_train.py --steps 10 2>&1 | tail -1 | tee gpurun_out/${TAG}_train.json ;;
+multi)
+  # under `gpurun --gpus N`: the bench exactly as the driver launches it at N ranks (NGPU from the environment, default 2)
+  N=${NGPU:-2}
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+      bench.py --gpus $N > gpurun_out/${TAG}_bench_n${N}.json 2> gpurun_out/${TAG}_bench_n${N}.err; tail -c 2500 gpurun_out/${TAG}_bench_n${N}.json; tail -3 gpurun_out/${TAG}_bench_n${N}.err ;;
 micro)
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/lds_floor scripts/microbench/lds_gather_floor.cu && /tmp/lds_floor | tee gpurun_out/${TAG}_lds_floor.txt ;;
 *) echo "unknown step $w" ;;
