@@ -21,6 +21,11 @@ class EmrtError(RuntimeError):
     pass
 
 
+class GnBranch(C.Structure):
+    _fields_ = [("conv", C.c_void_p), ("skip", C.c_void_p), ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("L", C.c_int32), ("groups", C.c_int32), ("Lv", C.c_int32), ("eps", C.c_float), ("shapes_hw", C.c_int32 * 16)]
+
+
 class LinearArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("y", C.c_void_p),
@@ -34,6 +39,36 @@ class LinearArgs(C.Structure):
         ("hm_rows", C.c_int32), ("hm_D", C.c_int32),
         ("x2", C.c_void_p), ("x2_period", C.c_int32),
         ("row_bias", C.c_void_p), ("row_bias_period", C.c_int32),
+        ("gn", C.POINTER(GnBranch)),
+    ]
+
+
+class MsdaArgs(C.Structure):
+    _fields_ = [
+        ("query", C.c_void_p), ("value", C.c_void_p), ("ref", C.c_void_p), ("ref_batches", C.c_int32),
+        ("query_pos", C.c_void_p), ("query_pos_rows", C.c_int32), ("query_scratch", C.c_void_p), ("query_eff", C.c_void_p),
+        ("value_mask", C.c_void_p),
+        ("w_value", C.c_void_p), ("b_value", C.c_void_p), ("w_offsets", C.c_void_p), ("b_offsets", C.c_void_p),
+        ("w_attn", C.c_void_p), ("b_attn", C.c_void_p), ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+        ("wv_packed", C.c_void_p), ("wq_packed", C.c_void_p), ("wo_packed", C.c_void_p), ("b_query", C.c_void_p),
+        ("row_bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
+        ("out", C.c_void_p), ("workspace", C.c_void_p),
+        ("B", C.c_int32), ("Lq", C.c_int32), ("Lv", C.c_int32), ("C", C.c_int32), ("M", C.c_int32), ("L", C.c_int32), ("P", C.c_int32),
+        ("shapes_hw", C.c_int32 * 16),
+        ("dtype", C.c_int32), ("flags", C.c_int32), ("keep_pixel_major", C.c_int32),
+        ("window_center", C.POINTER(C.c_int32)),
+        ("timing_events", C.c_void_p * 8),
+    ]
+
+
+class MsdaGrads(C.Structure):
+    _fields_ = [
+        ("d_out", C.c_void_p), ("d_query", C.c_void_p), ("d_value", C.c_void_p), ("d_ref", C.c_void_p),
+        ("dw_query", C.c_void_p), ("db_query", C.c_void_p), ("dw_value", C.c_void_p), ("db_value", C.c_void_p),
+        ("dw_out", C.c_void_p), ("db_out", C.c_void_p),
+        ("wq_cat", C.c_void_p), ("w_value_cast", C.c_void_p), ("w_out_cast", C.c_void_p),
+        ("workspace", C.c_void_p),
     ]
 
 
@@ -79,6 +114,10 @@ SIGNATURES = {
     "emrt_stitch_argmax_fused": (C.c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "emrt_stitch_argmax_eval": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "emrt_calculate_area": (C.c_int, [_P, _P, _L, _I, _I, _P, _P]),
+    "emrt_msda_fused_workspace_bytes": (C.c_int64, [_I, _I, _I, _I, _I, _I, _I, _I]),
+    "emrt_msda_fused_fwd": (C.c_int, [C.POINTER(MsdaArgs), _P]),
+    "emrt_msda_fused_bwd_workspace_bytes": (C.c_int64, [_I, _I, _I, _I, _I, _I, _I, _I]),
+    "emrt_msda_fused_bwd": (C.c_int, [C.POINTER(MsdaArgs), C.POINTER(MsdaGrads), _P]),
     "emrt_layernorm_bwd_workspace_floats": (C.c_int64, [_L, _I]),
     "emrt_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, C.c_float, _I, _P]),
     "emrt_groupnorm_bwd_workspace_floats": (C.c_int64, [_I, _I, _I, _I]),

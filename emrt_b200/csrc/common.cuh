@@ -124,6 +124,22 @@ template <> struct Vec16<__nv_bfloat16> {
   }
 };
 
+// Exact (erf-form) GELU, nn.GELU's default: h * Phi(h), Phi(h) = erfc(-h / sqrt 2) / 2.  erfc(z), z >= 0, by Abramowitz &
+// Stegun 7.1.26 (|error| <= 1.5e-7 absolute) — one branch-free sequence with one MUFU.RCP and one MUFU.EX2 instead of
+// erff's two divergent branches; the negative side is evaluated as erfc directly, so there is no 1 - erf cancellation.
+__device__ __forceinline__ float gelu_erf(float h) {
+  const float z = fabsf(h) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));        // 1 ulp: far below 1.5e-7
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (z * -1.4426950408889634f)));   // exp(-z^2)
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float hh = h * (0.5f * p * t * e);                    // h * erfc(z) / 2
+  return h >= 0.f ? h - hh : hh;
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int num_sms() {
   // per device ordinal (a process may drive several GPUs); benign race: every thread writes the same value

@@ -12,22 +12,6 @@
 
 namespace emrt {
 
-// Exact (erf-form) GELU, nn.GELU's default: h * Phi(h), Phi(h) = erfc(-h / sqrt 2) / 2.  erfc(z), z >= 0, by Abramowitz &
-// Stegun 7.1.26 (|error| <= 1.5e-7 absolute) — one branch-free sequence with one MUFU.RCP and one MUFU.EX2 instead of
-// erff's two divergent branches; the negative side is evaluated as erfc directly, so there is no 1 - erf cancellation.
-__device__ __forceinline__ float gelu_erf(float h) {
-  const float z = fabsf(h) * 0.70710678118654752f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));        // 1 ulp: far below 1.5e-7
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (z * -1.4426950408889634f)));   // exp(-z^2)
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  const float hh = h * (0.5f * p * t * e);                    // h * erfc(z) / 2
-  return h >= 0.f ? h - hh : hh;
-}
-
 // ---- LayerNorm(x + residual) (+ post_add): one warp per row, 16-byte vectors, N <= 1024, N % (32 * VEC) == 0 ----------
 // GN = true: post_add is not a tensor but the encoder layer's conv branch evaluated on the fly,
 //   post_add[row, c] = GELU(GroupNorm_l(conv)[row, c]) + skip[row, c]      (transformer_encoder_decoder.py:187-189,203)

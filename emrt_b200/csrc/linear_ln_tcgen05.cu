@@ -46,13 +46,26 @@ struct LnGemmParams {
   const float* beta;
   float eps;
   int32_t K, tiles_m;
+  // GN variant: + GELU(GroupNorm_l(conv)) + skip behind the LayerNorm (the encoder layer's conv branch, t_e_d.py:187-189,203)
+  CUtensorMap tma_conv;  // conv [rows, 256] bf16, box {32, 32}, SWIZZLE_64B
+  CUtensorMap tma_skip;  // skip [rows, 256] bf16, same box
+  const float* gn_stats; // [B, L, 32, 2] (sum, sum of squares) of conv per (image, level, group)
+  const float* gn_gamma; // [L, 256]
+  const float* gn_beta;
+  float gn_eps;
+  int32_t L, Lv, B;
+  LevelTable lv;
 };
+constexpr int GN_MAX_L = 4, GN_GROUPS = 32;
 
-template <int STAGES, bool B_RES>
+template <int STAGES, bool B_RES, bool GN = false>
 struct LnSmem {
   __nv_bfloat16 a[STAGES][BM * BK];
   __nv_bfloat16 b[B_RES ? 4 : STAGES][BN * BK];
   uint8_t buf[NUM_EPI_WARPS][2][BUF_BYTES];
+  uint8_t buf2[GN ? NUM_EPI_WARPS : 1][2][GN ? BUF_BYTES : 16];   // GN: the skip chunks (the conv chunks reuse `buf`)
+  float gn_gamma[GN ? GN_MAX_L : 1][GN ? BN : 4], gn_beta[GN ? GN_MAX_L : 1][GN ? BN : 4];
+  uint64_t gn_full[NUM_EPI_WARPS][2];
   float bias[BN], gamma[BN], beta[BN];
   float xch[2][2][2][BM];                  // [tile parity][pass][column half][row]
   uint64_t full[STAGES], empty[STAGES];
@@ -72,14 +85,19 @@ struct LnSmem {
                  "r"(taddr)                                                                                       \
                : "memory")
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-template <int STAGES, bool B_RES>
+template <int STAGES, bool B_RES, bool GN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_ln_tcgen05_kernel(const __grid_constant__ LnGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using Smem = LnSmem<STAGES, B_RES>;
+  using Smem = LnSmem<STAGES, B_RES, GN>;
   Smem& s = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,7 +115,11 @@ linear_ln_tcgen05_kernel(const __grid_constant__ LnGemmParams p) {
     mbar_init(&s.b_full, 1);
 #pragma unroll
     for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], NUM_EPI_WARPS); }
-    for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(&s.res_full[w][0], 1); mbar_init(&s.res_full[w][1], 1); }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) {
+      mbar_init(&s.res_full[w][0], 1); mbar_init(&s.res_full[w][1], 1);
+      mbar_init(&s.gn_full[w][0], 1); mbar_init(&s.gn_full[w][1], 1);
+    }
+    if (GN) { tma_prefetch_desc(&p.tma_conv); tma_prefetch_desc(&p.tma_skip); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -108,6 +130,8 @@ linear_ln_tcgen05_kernel(const __grid_constant__ LnGemmParams p) {
     s.bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
     s.gamma[i] = __ldg(p.gamma + i);
     s.beta[i] = __ldg(p.beta + i);
+    if (GN)
+      for (int l = 0; l < p.L; ++l) { s.gn_gamma[l][i] = __ldg(p.gn_gamma + l * BN + i); s.gn_beta[l][i] = __ldg(p.gn_beta + l * BN + i); }
   }
   tc_fence_before();
   __syncthreads();
@@ -179,6 +203,16 @@ linear_ln_tcgen05_kernel(const __grid_constant__ LnGemmParams p) {
       tma_load_2d(s.buf[ew][c & 1], &p.tma_res, &rbar[c & 1], col0 + c * CHUNK, m * BM + q * 32);
     };
     if (lane == 0 && (int)blockIdx.x < p.tiles_m) { load_res(blockIdx.x, 0); load_res(blockIdx.x, 1); }
+    // GN: conv chunk c -> buf[c & 1] (free once pass 1 has consumed the residual; the output is staged over it in place),
+    //     skip chunk c -> buf2[c & 1]; one barrier per buffer pair
+    uint64_t* gbar = s.gn_full[ew];
+    uint32_t gphase = 0u;
+    const uint32_t buf2_0 = smem_u32(s.buf2[GN ? ew : 0][0]);
+    auto load_gn = [&](int m, int c) {      // lane 0 only
+      mbar_arrive_expect_tx(&gbar[c & 1], 2 * BUF_BYTES);
+      tma_load_2d(s.buf[ew][c & 1], &p.tma_conv, &gbar[c & 1], col0 + c * CHUNK, m * BM + q * 32);
+      tma_load_2d(s.buf2[GN ? ew : 0][c & 1], &p.tma_skip, &gbar[c & 1], col0 + c * CHUNK, m * BM + q * 32);
+    };
 
     for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
       const int row = q * 32 + lane;        // row inside the tile
@@ -219,6 +253,7 @@ linear_ln_tcgen05_kernel(const __grid_constant__ LnGemmParams p) {
         __syncwarp();                       // every lane has read this buffer: refill it with the chunk after next
         if (lane == 0 && c + 2 < CHUNKS) load_res(m, c + 2);
       }
+      if (GN && lane == 0) { load_gn(m, 0); load_gn(m, 1); }      // both buffers are free: their latency hides behind pass 2
       s.xch[par][0][half][row] = sum;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       const float mean = (s.xch[par][0][0][row] + s.xch[par][0][1][row]) * (1.f / BN);
@@ -238,32 +273,75 @@ linear_ln_tcgen05_kernel(const __grid_constant__ LnGemmParams p) {
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       const float rstd = rsqrtf((s.xch[par][1][0][row] + s.xch[par][1][1][row]) * (1.f / BN) + p.eps);
 
-      // ---- pass 3: normalise, round, stage, TMA store -------------------------------------------------------
+      // ---- pass 3: normalise (+ conv branch), round, stage, TMA store --------------------------------------------
+      // GN: this lane's row -> (image, level) -> the group statistics of its 8-column pieces (one group per 16-byte piece)
+      int gl = 0;
+      const float* gst = nullptr;
+      float ginv = 0.f;
+      if (GN) {
+        const int64_t rg = (int64_t)m * BM + row;
+        int b = (int)(rg / p.Lv);
+        b = b < p.B ? b : p.B - 1;
+        const int t = (int)(rg - (int64_t)b * p.Lv);
+        while (gl + 1 < p.L && t >= p.lv.start[gl + 1]) ++gl;
+        gst = p.gn_stats + ((int64_t)(b * p.L + gl) * GN_GROUPS) * 2;
+        ginv = 1.f / (float)(p.lv.H[gl] * p.lv.W[gl] * (BN / GN_GROUPS));
+      }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
         TMEM_LD_X32(t_row + c * CHUNK, r);
-        if (c >= 2) {                       // the store of chunk c - 2 has drained this buffer
+        if (!GN && c >= 2) {                // the store of chunk c - 2 has drained this buffer
           if (lane == 0) tma_store_wait_read_1();
           __syncwarp();
         }
-        TMEM_WAIT_X32(r);
         const uint32_t sb = buf0 + (uint32_t)(c & 1) * BUF_BYTES + my_row;
+        uint4 cv[4] = {}, sk[4] = {};
+        if (GN) {
+          mbar_wait(&gbar[c & 1], (gphase >> (c & 1)) & 1u);
+          gphase ^= 1u << (c & 1);
+          const uint32_t kb2 = buf2_0 + (uint32_t)(c & 1) * BUF_BYTES + my_row;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            cv[h] = lds128(sb + ((((uint32_t)h) ^ swz) << 4));
+            sk[h] = lds128(kb2 + ((((uint32_t)h) ^ swz) << 4));
+          }
+        }
+        TMEM_WAIT_X32(r);
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           uint32_t o[4];
+          float gmean = 0.f, grstd = 0.f;
+          if (GN) {
+            const float2 st2 = __ldg(reinterpret_cast<const float2*>(gst) + ((col0 + c * CHUNK) >> 3) + h);
+            gmean = st2.x * ginv;
+            grstd = rsqrtf(fmaxf(st2.y * ginv - gmean * gmean, 0.f) + p.gn_eps);
+          }
+          const uint32_t cw[4] = {cv[h].x, cv[h].y, cv[h].z, cv[h].w}, sw[4] = {sk[h].x, sk[h].y, sk[h].z, sk[h].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j = h * 8 + 2 * i, col = col0 + c * CHUNK + j;
-            const float y0 = (__uint_as_float(r[j]) - mean) * rstd * s.gamma[col] + s.beta[col];
-            const float y1 = (__uint_as_float(r[j + 1]) - mean) * rstd * s.gamma[col + 1] + s.beta[col + 1];
+            float y0 = (__uint_as_float(r[j]) - mean) * rstd * s.gamma[col] + s.beta[col];
+            float y1 = (__uint_as_float(r[j + 1]) - mean) * rstd * s.gamma[col + 1] + s.beta[col + 1];
+            if (GN) {
+              const float c0 = __uint_as_float(cw[i] << 16), c1 = __uint_as_float(cw[i] & 0xffff0000u);
+              y0 += gelu_erf(fmaf(c0 - gmean, grstd * s.gn_gamma[gl][col], s.gn_beta[gl][col])) + __uint_as_float(sw[i] << 16);
+              y1 += gelu_erf(fmaf(c1 - gmean, grstd * s.gn_gamma[gl][col + 1], s.gn_beta[gl][col + 1])) + __uint_as_float(sw[i] & 0xffff0000u);
+            }
             o[i] = pack2(y0, y1, EMRT_BF16);
           }
           sts128(sb + ((((uint32_t)h) ^ swz) << 4), o[0], o[1], o[2], o[3]);
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) { tma_store_2d(&p.tma_y, buf0 + (uint32_t)(c & 1) * BUF_BYTES, col0 + c * CHUNK, row0); tma_store_commit(); }
+        if (lane == 0) {
+          tma_store_2d(&p.tma_y, buf0 + (uint32_t)(c & 1) * BUF_BYTES, col0 + c * CHUNK, row0);
+          tma_store_commit();
+          if (GN && c + 2 < CHUNKS) {       // chunk c + 2 goes into the buffers of chunk c: wait until the store has read them
+            tma_store_wait_read();
+            load_gn(m, c + 2);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -291,12 +369,12 @@ linear_ln_tcgen05_kernel(const __grid_constant__ LnGemmParams p) {
   }
 }
 
-template <int STAGES, bool B_RES>
+template <int STAGES, bool B_RES, bool GN = false>
 int launch_ln(LnGemmParams& p, cudaStream_t st) {
-  using Smem = LnSmem<STAGES, B_RES>;
+  using Smem = LnSmem<STAGES, B_RES, GN>;
   constexpr int smem_bytes = (int)sizeof(Smem) + 1024;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
-  auto kern = linear_ln_tcgen05_kernel<STAGES, B_RES>;
+  auto kern = linear_ln_tcgen05_kernel<STAGES, B_RES, GN>;
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int grid = p.tiles_m < num_sms() ? p.tiles_m : num_sms();
   kern<<<grid, NUM_THREADS, smem_bytes, st>>>(p);
@@ -337,6 +415,24 @@ int linear_ln_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
     const uint32_t box[2] = {(uint32_t)CHUNK, 32u};
     if (int e = make_tensor_map(&p.tma_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->residual, d, sb, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     if (int e = make_tensor_map(&p.tma_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->y, d, sb, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+  }
+  if (a->gn) {
+    const emrt_gn_branch* g = a->gn;
+    if (!g->conv || !g->skip || !g->stats || !g->gamma || !g->beta)
+      return set_error(EMRT_ERR_INVALID_ARGUMENT, "RESIDUAL_LN + conv branch: NULL pointer in emrt_gn_branch");
+    if (g->groups != GN_GROUPS || g->L < 1 || g->L > GN_MAX_L || g->Lv <= 0 || a->rows % g->Lv != 0)
+      return set_error(EMRT_ERR_UNSUPPORTED, "RESIDUAL_LN + conv branch: needs 32 groups, 1..4 levels and rows %% Lv == 0");
+    if ((reinterpret_cast<uintptr_t>(g->conv) | reinterpret_cast<uintptr_t>(g->skip)) & 15)
+      return set_error(EMRT_ERR_INVALID_ARGUMENT, "RESIDUAL_LN + conv branch: conv / skip must be 16-byte aligned");
+    if (int e = fill_levels(p.lv, g->L, g->shapes_hw, nullptr, g->Lv)) return e;
+    p.gn_stats = g->stats; p.gn_gamma = g->gamma; p.gn_beta = g->beta; p.gn_eps = g->eps;
+    p.L = g->L; p.Lv = g->Lv; p.B = (int)(a->rows / g->Lv);
+    const uint64_t d[2] = {(uint64_t)BN, (uint64_t)a->rows}, sb[1] = {(uint64_t)BN * 2};
+    const uint32_t box[2] = {(uint32_t)CHUNK, 32u};
+    if (int e = make_tensor_map(&p.tma_conv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->conv, d, sb, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    if (int e = make_tensor_map(&p.tma_skip, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->skip, d, sb, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    if (a->K <= 4 * BK) return set_error(EMRT_ERR_UNSUPPORTED, "RESIDUAL_LN + conv branch is built for the streamed-B form (K > 256: linear2 of the FFN)");
+    return launch_ln<3, false, true>(p, st);
   }
   if (a->K <= 4 * BK) return launch_ln<3, true>(p, st);
   return launch_ln<3, false>(p, st);

@@ -58,6 +58,7 @@ class TransformerEncoderLayer(nn.Module):
         nn.init.xavier_uniform_(self.linear1.weight)
         nn.init.xavier_uniform_(self.linear2.weight)
         self.gemm_impl = L.IMPL_AUTO
+        self.fuse_ffn2_norm2 = True          # tests may switch the fused linear2 + norm2 + conv-branch epilogue off
         self._packed = None
 
     def _version(self):
@@ -141,6 +142,13 @@ class TransformerEncoderLayer(nn.Module):
         # ffn (:157-160) + the layer's final add of the conv branch (:203)
         if fast:
             h = ops.linear(x, pk["w1"], pk["b1"], w_transposed=True, epilogue=L.EPI_RELU, impl=impl)
+            if impl != L.IMPL_SIMT and self.d_model == 256 and self.fuse_ffn2_norm2:
+                # linear2 + residual + norm2 + the conv branch + the layer's final add in ONE kernel: the LayerNorm runs on the
+                # fp32 accumulator and GELU(GroupNorm(conv)) + src is added in the same epilogue (:157-160,187-189,203)
+                return ops.linear(h, pk["w2"], pk["b2"], w_transposed=True, impl=impl, epilogue=L.EPI_RESIDUAL_LN, residual=x,
+                                  ln_gamma=pk["n2w"], ln_beta=pk["n2b"],
+                                  gn_branch=dict(conv=conv, skip=src, stats=gn_stats, gamma=pk["gn_w"], beta=pk["gn_b"],
+                                                 shapes=shapes, groups=32, eps=1e-5))
             f = ops.linear(h, pk["w2"], pk["b2"], w_transposed=True, impl=impl)
         else:
             h = ops.linear(x, self.linear1.weight.detach(), pk["b1"], epilogue=L.EPI_RELU, impl=L.IMPL_SIMT)

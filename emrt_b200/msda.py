@@ -133,6 +133,21 @@ class _MSDAFunction(torch.autograd.Function):
         bs, Len_q = query.shape[:2]
         query, value = query.contiguous(), value.contiguous()
         fast = query.dtype == torch.bfloat16
+        if mod.gemm_impl == L.IMPL_AUTO:
+            # ONE C call (emrt_msda_fused_fwd); the workspace it fills holds what emrt_msda_fused_bwd needs
+            f32 = lambda t: t.detach().float().contiguous()
+            wts = dict(w_value=f32(w_val), b_value=f32(b_val), w_offsets=f32(w_off), b_offsets=f32(b_off), w_attn=f32(w_attn),
+                       b_attn=f32(b_attn), w_out=f32(w_out), b_out=f32(b_out))
+            pgrid = bool(grid and fast and Len_q == value.shape[1])
+            if fast:
+                wts.update(mod.packed_weights())
+            out, keep = ops.msda_fused_fwd(query, value, ref, shapes, M, P, wts, mask=mask, pixel_grid=pgrid,
+                                           win_center=wts.get("win_center") if pgrid else None, keep_pixel_major=True)
+            ctx.keep, ctx.fused, ctx.fast = keep, True, fast
+            ctx.ref_grad = ctx.needs_input_grad[2]
+            ctx.save_for_backward(w_off, w_attn, w_val, w_out)
+            return out
+        ctx.fused = False
         if fast:
             pk = mod.packed_weights()
             impl = mod.gemm_impl
@@ -173,6 +188,17 @@ class _MSDAFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        if ctx.fused:
+            w_off, w_attn, w_val, w_out = ctx.saved_tensors
+            cdt = torch.bfloat16 if ctx.fast else torch.float32
+            tp2 = w_off.shape[1]
+            wq_cat = torch.cat([w_off.detach(), w_attn.detach()], 1).to(cdt).contiguous()
+            cast = (lambda w: w.detach().to(cdt).contiguous()) if ctx.fast else (lambda w: None)
+            dq, dv, d_ref, dw_q, db_q, dw_v, db_v, dw_o, db_o = ops.msda_fused_bwd(ctx.keep, d_out, wq_cat, cast(w_val), cast(w_out),
+                                                                                   want_ref_grad=ctx.ref_grad)
+            ctx.keep = None
+            return (None, dq, d_ref, dv, None, None, None, dw_q[:, :tp2].contiguous(), db_q[:tp2].contiguous(),
+                    dw_q[:, tp2:].contiguous(), db_q[tp2:].contiguous(), dw_v, db_v, dw_o, db_o)
         mod, shapes, mode, fast = ctx.mod, ctx.shapes, ctx.mode, ctx.fast
         query, value, ref, mask, v, loc, attn, g, w_off, w_attn, w_val, w_out = ctx.saved_tensors
         M, P, D, nL = mod.num_heads, mod.num_points, mod.head_dim, mod.num_levels
@@ -361,6 +387,9 @@ class MSDeformableAttention(nn.Module):
             if residual_norm is not None:
                 raise L.EmrtError("residual_norm is an inference-path fusion; the training path composes norm1 itself")
             return out
+        if self.gemm_impl == L.IMPL_AUTO:
+            return self._forward_one_call(query, reference_points, value, shapes, value_mask, query_pos, residual_norm)
+        # a forced GEMM implementation (tests): the same forward composed launch by launch
         if query.dtype == torch.float32:
             if query_pos is not None:
                 query = ops.add_bcast(query.contiguous(), query_pos.to(query.dtype).contiguous())
@@ -369,6 +398,41 @@ class MSDeformableAttention(nn.Module):
                 out = ops.residual_layernorm(out, residual_norm[0], residual_norm[1], residual_norm[2], out=out)
             return out
         return self._forward_bf16(query, reference_points, value, shapes, value_mask, query_pos, residual_norm)
+
+    def _forward_one_call(self, query, ref, value, shapes, value_mask, query_pos=None, residual_norm=None):
+        """The whole forward as ONE call of the C ABI (emrt_msda_fused_fwd): the library owns the composition
+        (projections, softmax + offsets, gather, output projection (+ LayerNorm)) and the kernel selection."""
+        M, P = self.num_heads, self.num_points
+        bs, Len_q = query.shape[:2]
+        query, value = query.contiguous(), value.contiguous()
+        mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
+        ref32 = ref if (ref.dtype == torch.float32 and ref.is_contiguous()) else ref.float().contiguous()
+        if query.dtype == torch.float32:
+            f32 = lambda t: t.detach().float().contiguous()
+            wts = dict(w_value=f32(self.value_proj.weight), b_value=f32(self.value_proj.bias),
+                       w_offsets=f32(self.sampling_offsets.weight), b_offsets=f32(self.sampling_offsets.bias),
+                       w_attn=f32(self.attention_weights.weight), b_attn=f32(self.attention_weights.bias),
+                       w_out=f32(self.output_proj.weight), b_out=f32(self.output_proj.bias))
+            qp, rows_p = None, 0
+            if query_pos is not None:
+                qp = query_pos.to(torch.float32).reshape(-1, self.embed_dim).contiguous()
+                rows_p = qp.shape[0]
+            return ops.msda_fused_fwd(query, value, ref32, shapes, M, P, wts, mask=mask, query_pos=qp, query_pos_rows=rows_p,
+                                      residual_norm=residual_norm)[0]
+        pk = self.packed_weights()
+        rowb, x2, x2_period = None, None, 0
+        if query_pos is not None:
+            if query_pos.numel() == Len_q * self.embed_dim:
+                if self.fused_qproj_ok():
+                    rowb = self._query_pos_bias(query_pos, Len_q)      # (query + pos) Wq + bq = query Wq + (pos Wq + bq)
+                else:
+                    x2, x2_period = ops.cyclic_rows_cached(query_pos), Len_q
+            else:
+                query = ops.add_bcast(query, query_pos.to(query.dtype).contiguous())
+        grid = is_pixel_grid(ref, shapes, Len_q, value.shape[1])
+        return ops.msda_fused_fwd(query, value, ref32, shapes, M, P, pk, mask=mask, query_pos=x2, query_pos_rows=x2_period,
+                                  row_bias=rowb, residual_norm=residual_norm, pixel_grid=grid,
+                                  win_center=pk["win_center"] if grid else None, keep_pixel_major=not self.head_major)[0]
 
     def _forward_fp32(self, query, ref, value, shapes, value_mask):
         M, P, D = self.num_heads, self.num_points, self.head_dim

@@ -131,9 +131,11 @@ def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NOR
 # ---- nn.Linear -----------------------------------------------------------------------------------------------
 def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_NONE, row_scale=None, residual=None,
            ln_gamma=None, ln_beta=None, ln_eps=1e-5, qproj_group=0, impl=L.IMPL_AUTO, out=None, out2=None, hm_rows=0,
-           hm_D=0, x2=None, x2_period=0, row_bias=None, row_bias_period=0):
+           hm_D=0, x2=None, x2_period=0, row_bias=None, row_bias_period=0, gn_branch=None):
     """y = epilogue((x + x2) @ W + bias).  x [..., K]; W [K,N] (Paddle layout) or [N,K] when w_transposed.
-    x2 (optional, tcgen05 path): `cyclic_rows(addend, ...)` of a [x2_period, K] broadcast addend (with_pos_embed)."""
+    x2 (optional, tcgen05 path): `cyclic_rows(addend, ...)` of a [x2_period, K] broadcast addend (with_pos_embed).
+    gn_branch (EPI_RESIDUAL_LN only): dict(conv, skip, stats, gamma, beta, shapes, groups=32, eps=1e-5) — the encoder layer's
+    conv branch GELU(GroupNorm_l(conv)) + skip added behind the LayerNorm inside the same epilogue."""
     lib = L.load()
     K = x.shape[-1]
     rows = x.numel() // K
@@ -161,6 +163,17 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     a.hm_rows, a.hm_D = int(hm_rows), int(hm_D)
     a.x2, a.x2_period = _ptr(x2), int(x2_period)
     a.row_bias, a.row_bias_period = _ptr(row_bias), int(row_bias_period)
+    gnb = None
+    if gn_branch is not None:
+        gnb = L.GnBranch()
+        gnb.conv, gnb.skip, gnb.stats = _ptr(gn_branch["conv"]), _ptr(gn_branch["skip"]), _ptr(gn_branch["stats"])
+        gnb.gamma, gnb.beta = _ptr(gn_branch["gamma"]), _ptr(gn_branch["beta"])
+        shapes = gn_branch["shapes"]
+        gnb.L, gnb.groups, gnb.eps = len(shapes), int(gn_branch.get("groups", 32)), float(gn_branch.get("eps", 1e-5))
+        gnb.Lv = sum(int(h) * int(w) for h, w in shapes)
+        for i, (h, w) in enumerate(shapes):
+            gnb.shapes_hw[2 * i], gnb.shapes_hw[2 * i + 1] = int(h), int(w)
+        a.gn = C.pointer(gnb)
     if row_bias is not None:
         assert row_bias.dtype == torch.float16 and row_bias.shape[-1] == N and row_bias.numel() // N >= row_bias_period + 127
     if x2 is not None:
@@ -565,3 +578,104 @@ def tokens_to_nchw(y, spatial):
     x = torch.empty((B, C_, P), dtype=y.dtype, device=y.device)
     L.check(L.load().emrt_nchw_to_tokens(_ptr(y.contiguous()), _ptr(x), B, P, C_, _dt(y), _stream()))
     return x.view(B, C_, *spatial)
+
+
+# ---- a2 in one call ---------------------------------------------------------------------------------------------------
+class _Keep:
+    """the ctypes argument struct of a fused MSDA call together with every tensor it points to"""
+
+    def __init__(self, args, tensors):
+        self.args, self.tensors = args, tensors
+
+
+def msda_fused_fwd(query, value, ref, shapes, M, P, weights, *, mask=None, query_pos=None, query_pos_rows=0, row_bias=None,
+                   residual_norm=None, pixel_grid=False, win_center=None, keep_pixel_major=False, out=None):
+    """emrt_msda_fused_fwd: MSDeformableAttention.forward (t_e_d.py:65-107) in ONE C call.  query [B,Lq,C], value [B,Lv,C]
+    (fp32 -> parity path, bf16 -> B200 path), ref f32 [1|B,Lq,L,2].  `weights`: fp32 path dict(w_value, b_value, w_offsets,
+    b_offsets, w_attn, b_attn, w_out, b_out) in Paddle layout; bf16 path dict(wv, wq, wo, bv, bq, bo) packed (+ the fp32-path
+    keys when a backward will follow).  Returns (out, keep): `keep` holds the argument struct and the workspace with the
+    intermediates (what msda_fused_bwd needs)."""
+    lib = L.load()
+    B, Lq, C_ = query.shape
+    Lv = value.shape[1]
+    nL = len(shapes)
+    dt = _dt(query)
+    a = L.MsdaArgs()
+    keep = [query, value, ref, mask, query_pos, row_bias, weights]
+    a.query, a.value, a.ref, a.ref_batches = _ptr(query), _ptr(value), _ptr(ref), int(ref.shape[0])
+    a.value_mask = _ptr(mask)
+    for k_c, k_py in (("w_value", "w_value"), ("b_value", "b_value"), ("w_offsets", "w_offsets"), ("b_offsets", "b_offsets"),
+                      ("w_attn", "w_attn"), ("b_attn", "b_attn"), ("w_out", "w_out"), ("b_out", "b_out"),
+                      ("wv_packed", "wv"), ("wq_packed", "wq"), ("wo_packed", "wo"), ("b_query", "bq")):
+        if weights.get(k_py) is not None:
+            setattr(a, k_c, _ptr(weights[k_py]))
+    if dt == L.BF16:
+        a.b_value, a.b_out = _ptr(weights["bv"]), _ptr(weights["bo"])
+    tp = M * nL * P
+    scratch = None
+    if query_pos is not None:
+        a.query_pos, a.query_pos_rows = _ptr(query_pos), int(query_pos_rows)
+        if dt == L.F32:
+            scratch = torch.empty_like(query)
+            a.query_eff = _ptr(scratch)
+    if dt == L.BF16 and not (tp == 144 and nL * P == 18):
+        scratch = torch.empty((B, Lq, 3 * tp), dtype=torch.float32, device=query.device)
+    a.query_scratch = _ptr(scratch)
+    a.row_bias = _ptr(row_bias)
+    if residual_norm is not None:
+        res, gamma, beta = residual_norm
+        a.residual, a.ln_gamma, a.ln_beta, a.ln_eps = _ptr(res), _ptr(gamma), _ptr(beta), 1e-5
+        keep += [res, gamma, beta]
+    if out is None:
+        out = torch.empty((B, Lq, C_), dtype=query.dtype, device=query.device)
+    ws = torch.empty((int(lib.emrt_msda_fused_workspace_bytes(B, Lq, Lv, C_, M, nL, P, dt)),), dtype=torch.uint8, device=query.device)
+    a.out, a.workspace = _ptr(out), _ptr(ws)
+    a.B, a.Lq, a.Lv, a.C, a.M, a.L, a.P = B, Lq, Lv, C_, M, nL, P
+    for i, (h, w) in enumerate(shapes):
+        a.shapes_hw[2 * i], a.shapes_hw[2 * i + 1] = int(h), int(w)
+    a.dtype, a.flags, a.keep_pixel_major = dt, (L.QUERY_PIXEL_GRID if pixel_grid else 0), int(bool(keep_pixel_major))
+    if win_center is not None and pixel_grid:
+        a.window_center = C.cast(win_center, C.POINTER(C.c_int32))
+        keep.append(win_center)
+    evs = None
+    if kernel_events is not None and dt == L.BF16:
+        # bench.py: CUDA events around each sub-launch, recorded by the C entry on the launching stream.  Each event is
+        # recorded once here so that torch has created it (and knows it as recorded); the C side records it again in place.
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+        for i, ev in enumerate(evs):
+            ev.record()
+            a.timing_events[i] = ev.cuda_event
+    L.check(lib.emrt_msda_fused_fwd(C.byref(a), _stream()))
+    if evs is not None:
+        es = query.element_size()
+        kernel_events.append(("linear", (B * Lv, C_, C_, es, es), (evs[0], evs[1])))
+        kernel_events.append(("linear", (B * Lq, C_, 3 * tp, es, 2), (evs[2], evs[3])))
+        kernel_events.append(("msda_gather_fwd", (B, Lq, Lv, M, C_ // M, nL, P, es, 2), (evs[4], evs[5])))
+        kernel_events.append(("linear", (B * Lq, C_, C_, es, es), (evs[6], evs[7])))
+    return out, _Keep(a, keep + [scratch, ws, out, evs])
+
+
+def msda_fused_bwd(keep, d_out, wq_cat, w_value_cast=None, w_out_cast=None, want_ref_grad=False):
+    """emrt_msda_fused_bwd on the argument struct a msda_fused_fwd(..., keep_pixel_major=True) returned.
+    -> (d_query, d_value, d_ref | None, dw_query [C,3MLP], db_query, dw_value, db_value, dw_out, db_out), weights grads f32."""
+    lib = L.load()
+    a = keep.args
+    B, Lq, Lv, C_, M, nL, P = a.B, a.Lq, a.Lv, a.C, a.M, a.L, a.P
+    tp = M * nL * P
+    dev = d_out.device
+    adt = d_out.dtype
+    f32 = dict(dtype=torch.float32, device=dev)
+    g = L.MsdaGrads()
+    d_out = d_out.contiguous()
+    d_query = torch.empty((B, Lq, C_), dtype=adt, device=dev)
+    d_value = torch.empty((B, Lv, C_), dtype=adt, device=dev)
+    d_ref = torch.empty((a.ref_batches, Lq, nL, 2), **f32) if want_ref_grad else None
+    dw_q, db_q = torch.zeros((C_, 3 * tp), **f32), torch.zeros((3 * tp,), **f32)
+    dw_v, db_v = torch.zeros((C_, C_), **f32), torch.zeros((C_,), **f32)
+    dw_o, db_o = torch.zeros((C_, C_), **f32), torch.zeros((C_,), **f32)
+    ws = torch.empty((int(lib.emrt_msda_fused_bwd_workspace_bytes(B, Lq, Lv, C_, M, nL, P, a.dtype)),), dtype=torch.uint8, device=dev)
+    g.d_out, g.d_query, g.d_value, g.d_ref = _ptr(d_out), _ptr(d_query), _ptr(d_value), _ptr(d_ref)
+    g.dw_query, g.db_query, g.dw_value, g.db_value, g.dw_out, g.db_out = (_ptr(t) for t in (dw_q, db_q, dw_v, db_v, dw_o, db_o))
+    g.wq_cat, g.w_value_cast, g.w_out_cast, g.workspace = _ptr(wq_cat), _ptr(w_value_cast), _ptr(w_out_cast), _ptr(ws)
+    L.check(lib.emrt_msda_fused_bwd(C.byref(a), C.byref(g), _stream()))
+    return d_query, d_value, d_ref, dw_q, db_q, dw_v, db_v, dw_o, db_o

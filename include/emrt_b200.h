@@ -126,6 +126,16 @@ int emrt_msda_gather_bwd_hint(const void* grad_out, const void* value, const voi
  *               tcgen05 only, N = 256, K % 64 == 0; y may alias residual or x);
  *   MSDA_QPROJ: y = pixel offsets [rows, 2N/3] (y_dtype), y2 = softmax'd weights [rows, N/3] (y_dtype),
  *               softmax group = qproj_group (= L*P).                                                      */
+/* Optional operand of the RESIDUAL_LN epilogue: the encoder layer's conv branch added BEHIND the LayerNorm,
+ *   y = LayerNorm(residual + x W + b) * gamma + beta + GELU(GroupNorm_l(conv)) + skip     (t_e_d.py:159-160,187-189,203)
+ * conv / skip BF16 [rows, N]; stats = emrt_groupnorm_stats' sums [B, L, groups, 2] of conv; gamma / beta F32 [L, N];
+ * rows = B * Lv tokens of the level pyramid shapes_hw = {H0,W0,H1,W1,...}.  N = 256, groups = 32, K > 256 (linear2).  */
+typedef struct emrt_gn_branch {
+  const void* conv; const void* skip; const float* stats; const float* gamma; const float* beta;
+  int32_t L; int32_t groups; int32_t Lv; float eps;
+  int32_t shapes_hw[2 * EMRT_MAX_LEVELS];
+} emrt_gn_branch;
+
 typedef struct emrt_linear_args {
   const void* x; const void* w; const float* bias; void* y;
   int64_t rows; int32_t K; int32_t N;
@@ -145,6 +155,7 @@ typedef struct emrt_linear_args {
    * [row_bias_period + 127, N] = x2 W + bias (cyclic like x2; pass bias = NULL), added to the fp32 accumulator in the
    * epilogue — (x + pos) W + b = x W + (pos W + b) with no extra MMA work.  MSDA_QPROJ epilogue only.            */
   const void* row_bias; int32_t row_bias_period;
+  const emrt_gn_branch* gn;   /* RESIDUAL_LN only; NULL = plain LayerNorm epilogue */
 } emrt_linear_args;
 int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 
@@ -306,6 +317,58 @@ int emrt_stitch_argmax_eval(const void* half_logits, int in_dtype, void* labels,
 int emrt_calculate_area(const int32_t* pred, const int32_t* label, int64_t n, int nc, int ignore_index,
                         long long* areas, void* stream);
 
+
+/* ---- a2 in one call: MSDeformableAttention.forward and its backward (transformer_encoder_decoder.py:65-107) -------------------
+ * emrt_msda_fused_fwd composes, on `stream`: value_proj (+ value_mask, :83-86) -> [sampling_offsets | attention_weights]
+ * projection with softmax over L*P and the location arithmetic (:89-102) -> sampling gather (:104, utils.py:64-97) ->
+ * output_proj (:106), optionally followed by LayerNorm(residual + .) (:199-200) in the same epilogue.
+ * dtype F32: the parity path — Paddle-layout fp32 weights w_* [in,out], SIMT GEMMs, normalised locations.
+ * dtype BF16: the B200 path — packed bf16 [out,in] operands (emrt_pack_weight; wq_packed = [sampling_offsets ; attention_weights],
+ *   b_query = their concatenated biases), tcgen05 GEMMs, fp16 pixel offsets / softmax weights, window-staged gather when
+ *   flags carries EMRT_QUERY_PIXEL_GRID (queries = the pyramid's own pixels; window_center = the optional hint of
+ *   emrt_msda_gather_fwd_hint).  with_pos_embed (:154-155): query_pos BF16 cyclic rows [query_pos_rows + 127, C] (see x2 of
+ *   emrt_linear_args) or, better, row_bias F16 [Lq + 127, 3*MLP] = query_pos W_q + b_query; F32 path: query_pos F32
+ *   [query_pos_rows, C] and query_scratch F32 [B, Lq, C] for the sum.
+ * workspace (emrt_msda_fused_workspace_bytes) receives, 256-byte aligned and in this order, the tensors the backward needs:
+ *   projected value [B, Lv, C] | offsets (BF16 path: F16 pixels; F32 path: F32 normalised locations) [B, Lq, 2*MLP] |
+ *   softmax weights [B, Lq, MLP] | gathered tokens [B, Lq, C] | (F32 path) raw projections F32 [B, Lq, 3*MLP].
+ * keep_pixel_major = 1 keeps the projected value [B, Lv, M, D] (required when emrt_msda_fused_bwd follows); otherwise the
+ * BF16 path writes it head-major [B, M, Lv, D] for the specialised gathers.                                                   */
+typedef struct emrt_msda_args {
+  const void* query; const void* value; const float* ref; int32_t ref_batches;      /* ref F32 [ref_batches, Lq, L, 2] */
+  const void* query_pos; int32_t query_pos_rows; void* query_scratch; const void* query_eff;
+  const float* value_mask;                                                          /* F32 [B * Lv] or NULL */
+  const void* w_value; const float* b_value; const void* w_offsets; const float* b_offsets;
+  const void* w_attn; const float* b_attn; const void* w_out; const float* b_out;  /* Paddle layout [in, out] */
+  const void* wv_packed; const void* wq_packed; const void* wo_packed; const float* b_query; const void* row_bias;
+  const void* residual; const float* ln_gamma; const float* ln_beta; float ln_eps;
+  void* out; void* workspace;
+  int32_t B, Lq, Lv, C, M, L, P;
+  int32_t shapes_hw[2 * EMRT_MAX_LEVELS];
+  int32_t dtype; int32_t flags; int32_t keep_pixel_major;
+  const int32_t* window_center;
+  /* measurement hook (bench.py): when non-NULL, cudaEvent_t handles recorded on `stream` before / after the value projection
+   * [0,1], the query projection [2,3], the gather [4,5] and the output projection [6,7]                                     */
+  void* timing_events[8];
+} emrt_msda_args;
+int64_t emrt_msda_fused_workspace_bytes(int B, int Lq, int Lv, int C, int M, int L, int P, int dtype);
+int emrt_msda_fused_fwd(const emrt_msda_args* args, void* stream);
+
+/* Backward of the same call (what Paddle autograd derives through :83-106): `args` as given to the forward (same workspace,
+ * keep_pixel_major = 1, no residual; query_eff = the tensor the query projection actually multiplied, i.e. query + pos when
+ * the caller formed it), plus the Paddle-layout weights in the activation dtype as the K-major operands of dx = dy W^T:
+ * wq_cat [C, 3*MLP] = [sampling_offsets.weight | attention_weights.weight], w_value_cast, w_out_cast (NULL = args' w_*).
+ * Outputs: d_query [B, Lq, C], d_value [B, Lv, C] (activation dtype), d_ref F32 [ref_batches, Lq, L, 2] or NULL; parameter
+ * gradients F32, ACCUMULATED: dw_query [C, 3*MLP], db_query [3*MLP], dw_value / dw_out [C, C], db_value / db_out [C].
+ * workspace: emrt_msda_fused_bwd_workspace_bytes.                                                                            */
+typedef struct emrt_msda_grads {
+  const void* d_out; void* d_query; void* d_value; float* d_ref;
+  float* dw_query; float* db_query; float* dw_value; float* db_value; float* dw_out; float* db_out;
+  const void* wq_cat; const void* w_value_cast; const void* w_out_cast;
+  void* workspace;
+} emrt_msda_grads;
+int64_t emrt_msda_fused_bwd_workspace_bytes(int B, int Lq, int Lv, int C, int M, int L, int P, int dtype);
+int emrt_msda_fused_bwd(const emrt_msda_args* args, const emrt_msda_grads* grads, void* stream);
 
 /* ---- cfg 4: backward of the encoder / decoder glue (the reference trains the whole EncoderDecoder: train.py:146-159 drives
  * Paddle autograd through transformer_encoder_decoder.py:184-204,282-295 and layers.py:236-311).  Parameter gradients are

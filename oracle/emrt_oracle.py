@@ -476,8 +476,9 @@ def encoder_layer_forward(p, prefix, src, ref, shapes, mask, pos):
     else:
         src2 = msda_forward(_sub(p, prefix + "self_attn."), src + pos, ref, src, shapes, mask, dtype=src.dtype)  # :198
     src = _store(_ln(src + src2, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]))    # :199-200
-    ffn = _store(_store(F.relu(src @ p[prefix + "linear1.weight"] + p[prefix + "linear1.bias"])) @ p[prefix + "linear2.weight"]
-                 + p[prefix + "linear2.bias"])                                              # :157-158
+    # (linear2's output is not a store: norm2 and the final add run in its epilogue on the fp32 accumulator)
+    ffn = _store(F.relu(src @ p[prefix + "linear1.weight"] + p[prefix + "linear1.bias"])) @ p[prefix + "linear2.weight"] \
+        + p[prefix + "linear2.bias"]                                                        # :157-158
     src = _ln(src + ffn, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])             # :159-160
     return _store(src + src_flatten)                                                        # :203
 

@@ -143,6 +143,13 @@ def run(tile=256):
             yy = F.group_norm(outs[l].bfloat16().double().permute(0, 2, 1).reshape(B, C, h_, w_), 32, p64[f"{pre}conv{l}.1.weight"], p64[f"{pre}conv{l}.1.bias"], 1e-5)
             br.append((F.gelu(yy) + x).flatten(2).permute(0, 2, 1))
         yo = (O.emrt_oracle._ln(x1o + fo.double(), p64[pre + "norm2.weight"], p64[pre + "norm2.bias"]) + torch.cat(br, 1)).bfloat16()
+        yf = ops.linear(ho.to(dev), pk["w2"], pk["b2"], w_transposed=True, epilogue=L.EPI_RESIDUAL_LN, residual=x1o.bfloat16().to(dev),
+                        ln_gamma=pk["n2w"], ln_beta=pk["n2b"],
+                        gn_branch=dict(conv=torch.cat(outs, 1).bfloat16().to(dev), skip=src.to(dev), stats=gn, gamma=pk["gn_w"],
+                                       beta=pk["gn_b"], shapes=shapes))
+        yfo = (O.emrt_oracle._ln(x1o + ho.double() @ p64[pre + "linear2.weight"] + p64[pre + "linear2.bias"], p64[pre + "norm2.weight"],
+                                 p64[pre + "norm2.bias"]) + torch.cat(br, 1)).bfloat16()
+        print(f"  linear2 + residual + LN2 + GroupNorm + GELU + skip (fused): own {rec('FFN linear2 + residual + LN2 + conv branch (fused)', l2(yf.float(), yfo)):.2e}")
         print(f"  LN2 + GroupNorm + GELU + skip: own {rec("LN2 + GroupNorm + GELU + skip", l2(y.float(), yo)):.2e}")
 
     # 3. decoder layer, stage by stage on the oracle's operands

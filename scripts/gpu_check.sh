@@ -29,6 +29,10 @@ gather)
 ln)
   timeout 600 ncu --set full --clock-control none --import-source on -f -k regex:linear_ln_tcgen05 -s 1 -c 1 -o gpurun_out/${TAG}_linear_ln \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > /dev/null 2>&1 ;;
+op)
+  # single-kernel capture: EMRT_OP = qproj | ffn1 | ffn2 | value, EMRT_OP_KERNEL = kernel-name regex (default: linear)
+  timeout 600 ncu --set full --clock-control none --import-source on -f -k regex:${EMRT_OP_KERNEL:-linear} -s 2 -c 1 -o gpurun_out/${TAG}_${EMRT_OP:-qproj} \
+      python scripts/op_once.py ${EMRT_OP:-qproj} > /dev/null 2>&1; python scripts/op_once.py ${EMRT_OP:-qproj} ;;
 train)
   timeout 600 python scripts/bench_train.py --steps 10 2>&1 | tail -1 | tee gpurun_out/${TAG}_train.json ;;
 multi)
