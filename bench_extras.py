@@ -87,10 +87,29 @@ def train_step(dev, rank, world, batch=16, steps=4, warmup=2):
     from emrt_b200 import ops, synthetic
     from emrt_b200.train import GradientBuckets, build_train_step
     step, buckets, what = build_train_step(dev, rank, batch)
-    ms = _timed(lambda: (step(), buckets.all_reduce()), steps, warmup, dev, world)
-    ms_compute = _timed(step, steps, 1, dev, world)
-    rec = {"what": what, "batch_per_gpu": batch, "ms": ms, "ms_fwd_bwd": ms_compute, "tiles_per_s": world * batch / (ms * 1e-3),
-           "bytes": buckets.nbytes, "buckets": len(buckets.buckets)}
+    ms_eager = _timed(lambda: (step(), buckets.all_reduce()), steps, warmup, dev, world)
+    # The eager step is bound by ~700 host-side launches (388 of this library's kernels + torch's gradient accumulation),
+    # not by the kernels: capture forward + backward + bucket zeroing in ONE CUDA graph (the all-reduce stays outside it,
+    # on NCCL's own stream) and time replays.  Falls back to the eager step if capture is not possible.
+    run, graphed = step, False
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        graph.replay()
+        torch.cuda.synchronize()
+        run, graphed = graph.replay, True
+    except Exception:
+        torch.cuda.synchronize()
+    ms = _timed(lambda: (run(), buckets.all_reduce()), steps, warmup, dev, world) if graphed else ms_eager
+    ms_compute = _timed(run, steps, 1, dev, world)
+    rec = {"what": what, "batch_per_gpu": batch, "ms": ms, "ms_eager": ms_eager, "ms_fwd_bwd": ms_compute, "cuda_graph": graphed,
+           "tiles_per_s": world * batch / (ms * 1e-3), "bytes": buckets.nbytes, "buckets": len(buckets.buckets)}
     if world > 1:
         ar = _timed(buckets.all_reduce, 10, 3, dev, world)
         rec["allreduce_ms"] = ar

@@ -31,6 +31,7 @@ constexpr int MAX_RES_KB = 4;  // weight-stationary mode: K <= 256
 
 enum { EPI_KIND_GENERIC = 0, EPI_KIND_QPROJ = 1 };
 
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -67,7 +68,7 @@ template <int BLOCK_N, int STAGES, bool B_RES, int EPI, bool TMA_ST, bool ROWB>
 struct GemmSmem {
   __nv_bfloat16 a[STAGES][BM * BK];
   __nv_bfloat16 b[B_RES ? MAX_RES_KB : STAGES][BLOCK_N * BK];
-  uint8_t stage[TMA_ST ? NUM_EPI_WARPS * StageBytes<EPI>::value : 16];
+  uint8_t stage[TMA_ST ? NUM_EPI_WARPS * (EPI == EPI_KIND_GENERIC ? 2 : 1) * StageBytes<EPI>::value : 16];   // generic: double-buffered
   uint8_t rowb[ROWB ? NUM_EPI_WARPS * 32 * BLOCK_N : 16];   // per epilogue warp: 32 rows x BLOCK_N / 2 fp16 row-bias values
   uint64_t rb_full[NUM_EPI_WARPS];
   float bias[BLOCK_N];
@@ -207,6 +208,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     // formed, rounded or written.  Each warp fetches its 32 x HALF_N box by TMA one tile ahead.
     const int ew = warp - EPI_WARP0;
     uint32_t rb_phase = 0;
+    uint32_t st_par = 0;                                     // generic staged epilogue: which of the warp's two staging tiles is next
     auto load_rb = [&](const TileWalk& t) {      // lane 0 only
       mbar_arrive_expect_tx(&s.rb_full[ew], 32u * BLOCK_N);
       tma_load_2d(s.rowb + ew * 32 * BLOCK_N, &p.tma_rb, &s.rb_full[ew], t.n * BLOCK_N + half * HALF_N,
@@ -244,16 +246,14 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           hm_base = (b * p.hm_heads * p.hm_rows + (row - b * p.hm_rows)) << p.hm_shift;
         }
         const int64_t hm_head_stride = (int64_t)p.hm_rows << p.hm_shift;
-        const uint32_t stage = smem_u32(s.stage) + (uint32_t)(warp - EPI_WARP0) * StageBytes<EPI>::value;
+        const uint32_t stage0 = smem_u32(s.stage) + (uint32_t)(warp - EPI_WARP0) * 2u * StageBytes<EPI>::value;
         const int row0 = tw.m * BM + q * 32;       // first row of this warp's 32-row slab
-#pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
-          uint32_t r[32];
-          TMEM_LD_X32(t_row + c, r);
-          TMEM_WAIT_X32(r);
-          const int cl = half * HALF_N + c;       // column inside the tile
-          if constexpr (TMA_ST) {
-            if (n0 + cl >= p.N) break;
+        if constexpr (TMA_ST) {
+          // Two staging tiles per warp and the next chunk's TMEM load in flight while this one is converted and stored:
+          // the single-buffered form waited for every TMA store to drain before the next chunk could be staged.
+          auto emit = [&](const uint32_t (&r)[32], int c) {
+            const int cl = half * HALF_N + c;       // column inside the tile
+            if (n0 + cl >= p.N) return;
             uint32_t o[16];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -269,7 +269,9 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) o[h * 4 + i] = pack2(v[2 * i], v[2 * i + 1], p.y_dtype);
             }
-            if (lane == 0) tma_store_wait_read();          // the previous store has drained the staging tile
+            const uint32_t stage = stage0 + (st_par ? (uint32_t)StageBytes<EPI>::value : 0u);
+            st_par ^= 1u;
+            if (lane == 0) tma_store_wait_read_1();        // the store issued two chunks ago has drained this tile
             __syncwarp();
 #pragma unroll
             for (int h = 0; h < 4; ++h)                      // SWIZZLE_64B: 16-byte chunk h of row `lane`
@@ -286,6 +288,29 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
               }
               tma_store_commit();
             }
+          };
+          constexpr int NCH = HALF_N / 32;
+          uint32_t ra[32], rb[32];
+          TMEM_LD_X32(t_row, ra);
+#pragma unroll
+          for (int ci = 0; ci < NCH; ci += 2) {
+            TMEM_WAIT_X32(ra);
+            if (ci + 1 < NCH) TMEM_LD_X32(t_row + (ci + 1) * 32, rb);
+            emit(ra, ci * 32);
+            if (ci + 1 < NCH) {
+              TMEM_WAIT_X32(rb);
+              if (ci + 2 < NCH) TMEM_LD_X32(t_row + (ci + 2) * 32, ra);
+              emit(rb, (ci + 1) * 32);
+            }
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; !TMA_ST && c < HALF_N; c += 32) {
+          uint32_t r[32];
+          TMEM_LD_X32(t_row + c, r);
+          TMEM_WAIT_X32(r);
+          const int cl = half * HALF_N + c;       // column inside the tile
+          if constexpr (TMA_ST) {
           } else {
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -580,6 +605,10 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
     return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 linear: unsupported epilogue flags %d", a->epilogue);
   if (a->N <= 64) return pick_tc<64, 8, 8, 8, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
   if (a->N <= 128 || getenv("EMRT_GEMM_BN128")) return pick_tc<128, 8, 8, 6, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
+  if (const char* e = getenv("EMRT_GEMM_STAGES")) {      // experiment: A-ring depth of the weight-stationary N-tile-256 kernel
+    if (atoi(e) == 2) return pick_tc<256, 2, 5, 4, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
+    if (atoi(e) == 3) return pick_tc<256, 3, 5, 4, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
+  }
   return pick_tc<256, 4, 5, 4, EPI_KIND_GENERIC, 2>(p, a, res, tma_st, st);
 }
 

@@ -41,9 +41,10 @@ layernorm_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const flo
   float gm[PER], dg[PER], db[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) { gm[i] = __ldg(gamma + lane + 32 * i); dg[i] = 0.f; db[i] = 0.f; }
-  const int64_t r0 = ((int64_t)blockIdx.x * LNB_WARPS + warp) * LNB_ROWS_PER_WARP;
+  // grid-stride over blocks of LNB_WARPS * LNB_ROWS_PER_WARP rows: the number of partials is the (bounded) number of CTAs
+  for (int64_t blk = blockIdx.x; blk * (LNB_WARPS * LNB_ROWS_PER_WARP) < rows; blk += gridDim.x)
   for (int rr = 0; rr < LNB_ROWS_PER_WARP; ++rr) {
-    const int64_t r = r0 + rr;
+    const int64_t r = (blk * LNB_WARPS + warp) * LNB_ROWS_PER_WARP + rr;
     if (r >= rows) break;
     float z[PER], d[PER];
     float s = 0.f;
@@ -162,29 +163,41 @@ groupnorm_bwd_reduce_kernel(const float* __restrict__ gp, const float* __restric
   }
 }
 
-// pass B: dx = rstd * (g - S1 / n - xhat * S2 / n)
+// pass B: dx = rstd * (g - S1 / n - xhat * S2 / n).  One 16-byte vector per thread (VEC channels of one group: VEC <= C / G).
 template <typename T, bool GELU>
 __global__ void __launch_bounds__(256)
 groupnorm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ stats,
                            const float* __restrict__ gs, const float* __restrict__ gamma, const float* __restrict__ beta,
                            T* __restrict__ dx, int Lv, int C, int L, int G, float eps, const __grid_constant__ LevelTable lv) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;       // element inside this image
-  if (i >= (int64_t)Lv * C) return;
-  const int t = (int)(i / C), c = (int)(i - (int64_t)t * C), b = blockIdx.y;
+  constexpr int VEC = Vec16<T>::N;
+  const uint32_t vec_per_tok = (uint32_t)C / VEC;
+  const uint32_t vi = blockIdx.x * 256u + threadIdx.x;           // vector index inside this image
+  if (vi >= (uint32_t)Lv * vec_per_tok) return;
+  const uint32_t t = vi / vec_per_tok;
+  const int c0 = (int)(vi - t * vec_per_tok) * VEC;
+  const int b = blockIdx.y;
   int l = 0;
-  while (l + 1 < L && t >= lv.start[l + 1]) ++l;
-  const int cpg = C / G, g = c / cpg;
+  while (l + 1 < L && (int)t >= lv.start[l + 1]) ++l;
+  const int cpg = C / G, g = c0 / cpg;
   const float inv_cnt = 1.f / (float)(lv.H[l] * lv.W[l] * cpg);
   const float* st = stats + (((int64_t)b * L + l) * G + g) * 2;
   const float mean = st[0] * inv_cnt;
   const float rstd = rsqrtf(fmaxf(st[1] * inv_cnt - mean * mean, 0.f) + eps);
-  const float* s = gs + (((int64_t)b * L + l) * G + g) * 2;
-  const float gm = gamma[l * C + c];
-  const int64_t o = (int64_t)b * Lv * C + i;
-  const float xh = (to_float(x[o]) - mean) * rstd;
-  float d = to_float(dy[o]);
-  if (GELU) d *= gelu_grad(fmaf(xh, gm, beta[l * C + c]));
-  dx[o] = from_float<T>(rstd * (d * gm - s[0] * inv_cnt - xh * s[1] * inv_cnt));
+  const float* sg = gs + (((int64_t)b * L + l) * G + g) * 2;
+  const float a1 = sg[0] * inv_cnt, a2 = sg[1] * inv_cnt;
+  const int64_t o = ((int64_t)b * Lv * vec_per_tok + vi) * VEC;
+  float xv[VEC], dv[VEC], out[VEC];
+  Vec16<T>::load(x + o, xv);
+  Vec16<T>::load(dy + o, dv);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float gm = __ldg(gamma + l * C + c0 + k);
+    const float xh = (xv[k] - mean) * rstd;
+    float d = dv[k];
+    if (GELU) d *= gelu_grad(fmaf(xh, gm, __ldg(beta + l * C + c0 + k)));
+    out[k] = rstd * (d * gm - a1 - xh * a2);
+  }
+  Vec16<T>::store(dx + o, out);
 }
 
 // ---- small elementwise / reduction pieces ------------------------------------------------------------------------------
@@ -348,10 +361,11 @@ conv3x3_dw_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, i
 
 using namespace emrt;
 
-extern "C" int64_t emrt_layernorm_bwd_workspace_floats(int64_t rows, int N) {
-  const int64_t ctas = (rows + LNB_WARPS * LNB_ROWS_PER_WARP - 1) / (LNB_WARPS * LNB_ROWS_PER_WARP);
-  return ctas * 2 * N;
+static int64_t lnb_ctas(int64_t rows) {
+  const int64_t want = (rows + LNB_WARPS * LNB_ROWS_PER_WARP - 1) / (LNB_WARPS * LNB_ROWS_PER_WARP);
+  return want < 2 * 148 ? want : 2 * 148;
 }
+extern "C" int64_t emrt_layernorm_bwd_workspace_floats(int64_t rows, int N) { return lnb_ctas(rows) * 2 * N; }
 
 extern "C" int emrt_layernorm_bwd(const void* a, const void* b, const float* gamma, const void* dy, void* dz, float* dgamma,
                                   float* dbeta, float* workspace, int64_t rows, int N, float eps, int dtype, void* stream) {
@@ -360,7 +374,7 @@ extern "C" int emrt_layernorm_bwd(const void* a, const void* b, const float* gam
   if (N != 256 && N != 64 && N != 128 && N != 512)
     return set_error(EMRT_ERR_UNSUPPORTED, "layernorm_bwd: N must be one of 64, 128, 256, 512 (got %d)", N);
   cudaStream_t st = as_stream(stream);
-  const unsigned ctas = (unsigned)((rows + LNB_WARPS * LNB_ROWS_PER_WARP - 1) / (LNB_WARPS * LNB_ROWS_PER_WARP));
+  const unsigned ctas = (unsigned)lnb_ctas(rows);
 #define EMRT_LNB(T, PER)                                                                                                   \
   layernorm_bwd_kernel<T, PER><<<ctas, LNB_WARPS * 32, 0, st>>>((const T*)a, (const T*)b, gamma, (const T*)dy, (T*)dz,      \
                                                                 workspace, rows, eps)
@@ -400,7 +414,9 @@ extern "C" int emrt_groupnorm_bwd(const void* x, const void* dy, const float* st
   float* gs = cp + (int64_t)B * L * GNB_CHUNKS * 2 * C;
   const dim3 sgrid(GNB_CHUNKS, (unsigned)(B * L));
   const size_t sh = sizeof(float) * 2 * C;
-  const dim3 agrid((unsigned)(((int64_t)Lv * C + 255) / 256), (unsigned)B);
+  const int vec = dtype == EMRT_F32 ? 4 : 8;
+  EMRT_REQUIRE((C / groups) % vec == 0 && C % vec == 0, "groupnorm_bwd: channels per group must be a multiple of the 16-byte vector (4 fp32 / 8 bf16)");
+  const dim3 agrid((unsigned)(((int64_t)Lv * (C / vec) + 255) / 256), (unsigned)B);
   const int n_red = B * L * groups * 2 + 2 * L * C;
 #define EMRT_GNB(T, G_)                                                                                                         \
   do {                                                                                                                          \

@@ -195,25 +195,31 @@ scale_rows_cast_kernel(const float* __restrict__ src, const float* __restrict__ 
 // d ref[b,q,l,:] = sum over heads and points of d loc[b,q,m,l,p,:]; in PIXEL_OFFSET mode grad_loc is per pixel and
 // d x / d ref_x = W_l).  One thread per (reference batch, query, level); a batch-shared reference (ref_batches == 1, the
 // decoder's sigmoid(Linear(query_pos_embed)), t_e_d.py:466) sums over the batch in a fixed order: no atomics.
+// One WARP per (reference batch, query, level): lane j sums items j, j + 32, ... of the (batch, head, point) list, then a
+// fixed shuffle tree — deterministic, and 32 loads in flight instead of one serial chain of B * M * P.
 __global__ void msda_ref_bwd_kernel(const float* __restrict__ grad_loc, float* __restrict__ grad_ref, int B, int ref_batches,
                                     int Lq, int M, int L, int P, LevelTable lv, int pixel_mode) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= (int64_t)ref_batches * Lq * L) return;
   const int l = (int)(i % L);
   const int q = (int)((i / L) % Lq);
   const int rb = (int)(i / ((int64_t)L * Lq));
+  const int nb = (B - rb + ref_batches - 1) / ref_batches, MP = M * P;
   float gx = 0.f, gy = 0.f;
-  for (int b = rb; b < B; b += ref_batches) {
-    const float2* g = reinterpret_cast<const float2*>(grad_loc) + (((int64_t)b * Lq + q) * M * L + l) * P;
-    for (int m = 0; m < M; ++m)
-      for (int pp = 0; pp < P; ++pp) {
-        const float2 v = __ldg(g + (int64_t)m * L * P + pp);
-        gx += v.x;
-        gy += v.y;
-      }
+  for (int j = lane; j < nb * MP; j += 32) {
+    const int bi = j / MP, r = j - bi * MP, m = r / P, pp = r - m * P;
+    const int b = rb + bi * ref_batches;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(grad_loc) + ((((int64_t)b * Lq + q) * M + m) * L + l) * P + pp);
+    gx += v.x;
+    gy += v.y;
   }
-  if (pixel_mode) { gx *= (float)lv.W[l]; gy *= (float)lv.H[l]; }
-  reinterpret_cast<float2*>(grad_ref)[i] = make_float2(gx, gy);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { gx += __shfl_xor_sync(0xffffffffu, gx, o); gy += __shfl_xor_sync(0xffffffffu, gy, o); }
+  if (lane == 0) {
+    if (pixel_mode) { gx *= (float)lv.W[l]; gy *= (float)lv.H[l]; }
+    reinterpret_cast<float2*>(grad_ref)[i] = make_float2(gx, gy);
+  }
 }
 
 }  // namespace emrt
@@ -310,7 +316,7 @@ extern "C" int emrt_msda_ref_bwd(const float* grad_loc, float* grad_ref, int B, 
   LevelTable lv;
   if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, -1)) return e;
   const int64_t n = (int64_t)ref_batches * Lq * L;
-  msda_ref_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(grad_loc, grad_ref, B, ref_batches, Lq, M, L, P,
+  msda_ref_bwd_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, as_stream(stream)>>>(grad_loc, grad_ref, B, ref_batches, Lq, M, L, P,
                                                                               lv, mode == EMRT_LOC_PIXEL_OFFSET);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
