@@ -297,7 +297,10 @@ class EncoderDecoder(nn.Module):
 
     def forward(self, src_feats: Sequence[torch.Tensor], src_psp, src_mask=None):
         if src_mask is not None:
-            raise L.EmrtError("EMRT never passes src_mask (paddle_EMRT.py:265); the masked path is not built")
+            if self._emrt_train and torch.is_grad_enabled():
+                raise L.EmrtError("the masked path (src_mask) is built for inference; EMRT never passes a mask (paddle_EMRT.py:265)")
+            with torch.no_grad():
+                return self._forward_eval(src_feats, src_psp, src_mask)
         if self._emrt_train and torch.is_grad_enabled() and (any(t.requires_grad for t in list(src_feats) + [src_psp])
                                         or any(p.requires_grad for p in self.parameters())):
             return self._forward_train(src_feats, src_psp)
@@ -339,11 +342,52 @@ class EncoderDecoder(nn.Module):
             self._sine_cache = (key, torch.from_numpy(sine).to(device))
         return self._sine_cache[1]
 
-    def _forward_eval(self, src_feats: Sequence[torch.Tensor], src_psp):
+    def _masked_constants(self, src_mask, shapes, device, dtype):
+        """The input-dependent tensors of the masked path (t_e_d.py:408-415,440-451,466-467), from the padding mask alone:
+        per-level nearest-resized masks -> mask_flatten [B, Lv], valid ratios [B, L, 2], the masked sine position embedding
+        + level embedding [B, Lv, C].  Index / table work on a [B, H, W] mask: done on the host in the reference's float32
+        operation order (one device -> host read of the mask); the activations never leave the device."""
+        m = src_mask.detach().to("cpu", torch.float32) != 0
+        B, H, W = m.shape
+        C_ = self.hidden_dim
+        npf = C_ // 2
+        lvl = self.level_embed.weight.detach().float().cpu()
+        masks, pos, vr = [], [], []
+        # host torch ops in the reference's own order (position_encoding.py:60-75).  Padded columns / rows make the normalised
+        # coordinate (0 - 0.5) / (0 + 1e-6) * 2 pi ~ -3e6: sin / cos of that is ill-conditioned in float32, so the values at
+        # PADDED tokens depend on the library's range reduction (they are garbage positions in the reference too).
+        dim_t = 2 * (torch.arange(npf) // 2).to(torch.float32)
+        dim_t = 10000.0 ** (dim_t / npf)
+        for l, (h, w) in enumerate(shapes):
+            iy = torch.floor(torch.arange(h) * (H / h)).long()               # F.interpolate(mode='nearest'), :440
+            ix = torch.floor(torch.arange(w) * (W / w)).long()
+            ml = m[:, iy][:, :, ix].to(torch.float32)                        # [B, h, w]
+            vr.append(torch.stack([ml[:, 0, :].sum(1) / w, ml[:, :, 0].sum(1) / h], -1))          # (w, h) order, :408-415
+            y_embed = ml.cumsum(1, dtype=torch.float32)
+            x_embed = ml.cumsum(2, dtype=torch.float32)
+            y_embed = (y_embed + -0.5) / (y_embed[:, -1:, :] + 1e-6) * (2 * math.pi)
+            x_embed = (x_embed + -0.5) / (x_embed[:, :, -1:] + 1e-6) * (2 * math.pi)
+            px, py = x_embed.unsqueeze(-1) / dim_t, y_embed.unsqueeze(-1) / dim_t
+            px = torch.stack((px[:, :, :, 0::2].sin(), px[:, :, :, 1::2].cos()), dim=4).flatten(3)
+            py = torch.stack((py[:, :, :, 0::2].sin(), py[:, :, :, 1::2].cos()), dim=4).flatten(3)
+            pos.append(torch.cat((py, px), dim=3).reshape(B, h * w, -1) + lvl[l].reshape(1, 1, -1))
+            masks.append(ml.reshape(B, h * w))
+        to = lambda t: t.contiguous().to(device)
+        return (to(torch.cat(masks, 1)), to(torch.stack(vr, 1)), to(torch.cat(pos, 1)).to(dtype).contiguous())
+
+    def _forward_eval(self, src_feats: Sequence[torch.Tensor], src_psp, src_mask=None):
         src, shapes, c = self.project_inputs(src_feats)
         B, Lv, dev = src.shape[0], src.shape[1], src.device
-        mask = torch.ones((B, Lv), dtype=torch.float32, device=dev)                    # mask_flatten (:451)
-        memory = self.encoder(src, shapes, mask, c["pos"])
         tgt = ops.nchw_to_tokens(src_psp)                                              # src_psp.transpose([0, 2, 1]) (:469)
-        hs = self.decoder(tgt, memory, c["ref_dec"], shapes, mask, c["qpos"])
+        if src_mask is None:
+            mask = torch.ones((B, Lv), dtype=torch.float32, device=dev)                # mask_flatten (:451)
+            memory = self.encoder(src, shapes, mask, c["pos"])
+            hs = self.decoder(tgt, memory, c["ref_dec"], shapes, mask, c["qpos"])
+            return hs, memory
+        # masked path (:440-447,466-467): per-image valid ratios scale the reference points, the position embedding follows
+        # the mask, padded value pixels are zeroed inside MSDeformableAttention (value_mask)
+        mask, vr, pos = self._masked_constants(src_mask, shapes, dev, src.dtype)
+        memory = self.encoder(src, shapes, mask, pos, vr)
+        ref_dec = (c["ref_dec"][:, :, :1, :] * vr[:, None]).contiguous()               # rp.unsqueeze(2) * valid_ratios.unsqueeze(1)
+        hs = self.decoder(tgt, memory, ref_dec, shapes, mask, c["qpos"])
         return hs, memory

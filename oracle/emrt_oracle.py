@@ -498,12 +498,30 @@ def decoder_layer_forward(p, prefix, tgt, ref, memory, shapes, mask, query_pos):
     return _store(_ln(tgt + ffn, p[prefix + "norm3.weight"], p[prefix + "norm3.bias"]))
 
 
-def encoder_decoder_forward(p, src_feats, src_psp, num_enc=4, num_dec=2, trace=None):
+def masked_position_embedding_sine(mask, num_pos_feats=128, temperature=10000.0, offset=-0.5, eps=1e-6, scale=2 * math.pi):
+    """PositionEmbedding.forward (position_encoding.py:51-75) for a [B, h, w] 0/1 mask -> [B, h*w, 2*num_pos_feats]."""
+    dtype = mask.dtype
+    y_embed = mask.cumsum(1)
+    x_embed = mask.cumsum(2)
+    y_embed = (y_embed + offset) / (y_embed[:, -1:, :] + eps) * scale
+    x_embed = (x_embed + offset) / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = 2 * (torch.arange(num_pos_feats) // 2).to(dtype)
+    dim_t = temperature ** (dim_t / num_pos_feats)
+    pos_x = x_embed[..., None] / dim_t
+    pos_y = y_embed[..., None] / dim_t
+    pos_x = torch.stack((pos_x[..., 0::2].sin(), pos_x[..., 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[..., 0::2].sin(), pos_y[..., 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).flatten(1, 2)
+
+
+def encoder_decoder_forward(p, src_feats, src_psp, num_enc=4, num_dec=2, trace=None, src_mask=None):
     """EncoderDecoder.forward (transformer_encoder_decoder.py:416-473), src_mask=None, eval mode.
     p: dict of torch tensors with Paddle state-dict keys (Linear [in,out], conv [out,in,kh,kw]).
     src_feats: [c2,c3,c4] NCHW; src_psp [B,256,110].  -> (hs [1,B,110,256], memory [B,Lv,256]).
     trace: optional dict, filled with the tensors between the layers (src, pos, enc[i], ref_dec, query_pos, dec[i]) — the
     per-layer (teacher-forced) parity tests feed each layer the evaluation's own input."""
+    if src_mask is not None:
+        return _encoder_decoder_forward_masked(p, src_feats, src_psp, num_enc, num_dec, src_mask)
     srcs, shapes = [], []
     for i, f in enumerate(src_feats):                                                       # :417-419
         y = _store(F.conv2d(f, p[f"input_proj.{i}.0.weight"], p[f"input_proj.{i}.0.bias"]))
@@ -539,6 +557,50 @@ def encoder_decoder_forward(p, src_feats, src_psp, num_enc=4, num_dec=2, trace=N
         tgt = decoder_layer_forward(p, f"decoder.layers.{i}.", tgt, rp, memory, shapes, mask, _store(query_embed))
         if trace is not None:
             trace["dec"].append(tgt)
+    return tgt[None], memory, shapes
+
+
+def _encoder_decoder_forward_masked(p, src_feats, src_psp, num_enc, num_dec, src_mask):
+    """EncoderDecoder.forward with src_mask [B, H, W] (non-zero = valid), transformer_encoder_decoder.py:408-473."""
+    dt = src_psp.dtype
+    srcs = []
+    for i, f in enumerate(src_feats):                                                       # :417-419
+        y = F.conv2d(f, p[f"input_proj.{i}.0.weight"], p[f"input_proj.{i}.0.bias"])
+        srcs.append(F.group_norm(y, 32, p[f"input_proj.{i}.1.weight"], p[f"input_proj.{i}.1.bias"], 1e-5))
+    src_flatten, mask_flatten, pos_flatten, shapes, valid_ratios = [], [], [], [], []
+    sm = torch.as_tensor(src_mask).to(dt)
+    for level, s in enumerate(srcs):                                                        # :434-452
+        bs, c, h, w = s.shape
+        shapes.append((h, w))
+        src_flatten.append(s.flatten(2).permute(0, 2, 1))
+        mask = (F.interpolate(sm[None], size=(h, w))[0] != 0).to(dt)                         # :440 (nearest), bool
+        vr_h = mask[:, :, 0].sum(1) / h                                                      # :408-415
+        vr_w = mask[:, 0, :].sum(1) / w
+        valid_ratios.append(torch.stack([vr_w, vr_h], -1))
+        pos = masked_position_embedding_sine(mask, c // 2)                                   # :446
+        pos_flatten.append(pos + p["level_embed.weight"][level].reshape(1, 1, -1))           # :447
+        mask_flatten.append(mask.flatten(1))
+    src, pos, mask = torch.cat(src_flatten, 1), torch.cat(pos_flatten, 1), torch.cat(mask_flatten, 1)
+    vr = torch.stack(valid_ratios, 1)                                                       # [bs, L, 2]
+    bs = src.shape[0]
+    # TransformerEncoder.get_reference_points (:213-228)
+    pts = []
+    for i, (H, W) in enumerate(shapes):
+        ry, rx = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=dt), torch.linspace(0.5, W - 0.5, W, dtype=dt), indexing="ij")
+        ry = ry.flatten()[None] / (vr[:, None, i, 1] * H)
+        rx = rx.flatten()[None] / (vr[:, None, i, 0] * W)
+        pts.append(torch.stack((rx, ry), -1))
+    ref = torch.cat(pts, 1)[:, :, None] * vr[:, None]                                       # [bs, Lv, L, 2]
+    out = src
+    for i in range(num_enc):
+        out = encoder_layer_forward(p, f"encoder.layers.{i}.", out, ref, shapes, mask, pos)
+    memory = out
+    query_embed = p["query_pos_embed.weight"][None].expand(bs, -1, -1)
+    rp = torch.sigmoid(query_embed @ p["reference_points.weight"] + p["reference_points.bias"])
+    rp = rp[:, :, None, :] * vr[:, None]                                                    # :467
+    tgt = src_psp.permute(0, 2, 1)
+    for i in range(num_dec):
+        tgt = decoder_layer_forward(p, f"decoder.layers.{i}.", tgt, rp, memory, shapes, mask, query_embed)
     return tgt[None], memory, shapes
 
 

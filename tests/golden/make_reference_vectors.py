@@ -66,6 +66,14 @@ def encdec_inputs(tile, B, seed, num_enc, num_dec):
     return dict(params=params, feats=feats, psp=psp)
 
 
+def masked_src_mask():
+    """[2, 64, 64] float32, 1 = valid: image 0 is padded on the right / bottom (valid 48 rows x 40 columns), image 1 is full."""
+    m = np.zeros((2, 64, 64), np.float32)
+    m[0, :48, :40] = 1.0
+    m[1] = 1.0
+    return m
+
+
 def mha_inputs():
     rng = np.random.Generator(np.random.PCG64(21))
     params = {k[len("decoder.layers.0.self_attn."):]: v for k, v in O.make_encoder_decoder_params(20, num_enc=0, num_dec=1).items()
@@ -170,6 +178,17 @@ def main():
                                           keys=np.array(sorted(model.state_dict().keys())),
                                           check=checksum([*c["feats"], c["psp"], *[v.numpy() for v in c["params"].values()]]))
 
+    # the masked path (t_e_d.py:408-415,440-447,466-467: src_mask -> per-level nearest mask, valid ratios, masked sine embedding,
+    # scaled reference points, value masking); EMRT itself never passes a mask (paddle_EMRT.py:265)
+    c = encdec_inputs(64, 2, 70, 2, 1)
+    model = ref.ted.EncoderDecoder(hidden_dim=256, dim_feedforward=1024, backbone_num_channels=[512, 1024, 2048], dropout=0.1,
+                                   activation="relu", num_feature_levels=3, nhead=8, num_encoder_layers=2, num_decoder_layers=1,
+                                   num_encoder_points=6, num_decoder_points=6, nclass=6)
+    R.load_params(model, c["params"])
+    hs, memory = model([T(f) for f in c["feats"]], T(c["psp"]), T(masked_src_mask()))
+    files["ref_encdec_masked"] = dict(hs=f32(hs), memory=f32(memory), src_mask=masked_src_mask(),
+                                      check=checksum([*c["feats"], c["psp"], *[v.numpy() for v in c["params"].values()]]))
+
     # a5: UpHead (paddle_EMRT.py:115-181) as EMRT builds it (:197-198); the logits before the last x2 are captured
     c = uphead_inputs()
     up = R.load_params(ref.emrt.UpHead(embed_dim=256, num_conv=3, num_upsample_layer=1, align_corners=False, num_classes=c["nc"]),
@@ -201,7 +220,10 @@ def main():
     files["ref_area"] = dict(intersect=f32(ia), pred=f32(pa), label=f32(la), check=checksum([c["pred"], c["label"]]))
 
     for name, arrays in files.items():
-        np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+        path = os.path.join(OUT, name + ".npz")
+        if os.path.exists(path) and "--all" not in sys.argv:      # committed vectors stay byte-identical unless --all
+            continue
+        np.savez_compressed(path, **arrays)
     for f in sorted(os.listdir(OUT)):
         if f.startswith("ref_"):
             print(f"{f:28s} {os.path.getsize(os.path.join(OUT, f)) / 1024:8.1f} KB")

@@ -141,6 +141,40 @@ def test_encoder_decoder_bf16_matches_reference(cuda_dev):
     assert_bf16_parity(hs.float(), g["hs"], rhs, "hs vs reference")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_encoder_decoder_masked_path_matches_reference(cuda_dev, dtype):
+    """EncoderDecoder.forward(src_feats, src_psp, src_mask) — the padding-mask path EMRT itself never takes
+    (t_e_d.py:408-415,440-447,466-467): per-level nearest masks, valid ratios scaling the encoder / decoder reference points,
+    the masked sine embedding, value masking — against the vectors the reference's own code produced (fp32 5e-4; bf16 by the
+    depth rule against the same-rounding oracle is not available for this path: 2e-2 L2, three layers deep)."""
+    g = load("ref_encdec_masked")
+    c = G.encdec_inputs(64, 2, 70, 2, 1)
+    m = emrt_b200.EncoderDecoder(hidden_dim=256, dim_feedforward=1024, backbone_num_channels=[512, 1024, 2048], dropout=0.1,
+                                 activation="relu", num_feature_levels=3, nhead=8, num_encoder_layers=2, num_decoder_layers=1,
+                                 num_encoder_points=6, num_decoder_points=6, nclass=6)
+    m = _load(m, c["params"]).to(cuda_dev)
+    d = lambda a: torch.from_numpy(a).to(cuda_dev).to(dtype)
+    hs, mem = m([d(f) for f in c["feats"]], d(c["psp"]), torch.from_numpy(g["src_mask"]).to(cuda_dev))
+    assert tuple(hs.shape) == tuple(g["hs"].shape) and tuple(mem.shape) == tuple(g["memory"].shape)
+    # tokens whose own position embedding is well conditioned: everything except the padded rows / columns of image 0 (their
+    # normalised coordinate is ~ -3e6: sin / cos of it depends on the library's float32 range reduction — in the reference too)
+    valid = torch.ones(2, 84, dtype=torch.bool)
+    off = 0
+    for (h, w), (vh, vw) in zip(((8, 8), (4, 4), (2, 2)), ((6, 5), (3, 3), (2, 2))):
+        v = torch.zeros(h, w, dtype=torch.bool)
+        v[:vh, :vw] = True
+        valid[0, off:off + h * w] = v.flatten()
+        off += h * w
+    if dtype == torch.float32:
+        assert rel_err(mem.cpu()[valid], g["memory"][valid.numpy()]) < 5e-4 and rel_err(hs, g["hs"]) < 5e-4
+        assert rel_err(mem, g["memory"]) < 5e-3
+    else:
+        assert l2_err(mem.float().cpu()[valid], g["memory"][valid.numpy()]) < 2e-2 and l2_err(hs.float(), g["hs"]) < 2e-2
+    # the mask matters: the unmasked forward is far from these vectors
+    hs0, mem0 = m([d(f) for f in c["feats"]], d(c["psp"]))
+    assert rel_err(mem0.float(), g["memory"]) > 5e-2
+
+
 def test_multi_head_attention_matches_reference(cuda_dev):
     g, c = load("ref_mha"), G.mha_inputs()
     p = {k: torch.as_tensor(v).to(cuda_dev) for k, v in c["params"].items()}

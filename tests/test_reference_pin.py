@@ -224,3 +224,16 @@ def test_install_half_logits_on_the_reference_uphead():
         UpHead.forward = saved
         if hasattr(UpHead, "_emrt_wrapped"):
             del UpHead._emrt_wrapped
+
+
+def test_oracle_masked_encoder_decoder_equals_reference_vectors():
+    """oracle.encoder_decoder_forward(..., src_mask=...) restates the padding-mask path (t_e_d.py:408-415,440-447,466-467);
+    it must equal what the reference's own EncoderDecoder.forward produced for the same mask (tests/golden/ref_encdec_masked.npz)."""
+    import make_reference_vectors as G
+    g = np.load(os.path.join(GOLD, "ref_encdec_masked.npz"))
+    c = G.encdec_inputs(64, 2, 70, 2, 1)
+    p = {k: torch.as_tensor(v) for k, v in c["params"].items()}
+    hs, mem, _ = O.encoder_decoder_forward(p, [torch.as_tensor(f) for f in c["feats"]], torch.as_tensor(c["psp"]), 2, 1,
+                                           src_mask=g["src_mask"])
+    close(mem, g["memory"], 2e-5)
+    close(hs, g["hs"], 2e-5)
