@@ -15,6 +15,7 @@
 // carries only A.  Other shapes stream A and B through the ring.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -36,6 +37,28 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+
+// acc0 += lo(hw), acc1 += hi(hw): an fp16 pair added to two fp32 accumulators, one FHFMA each (fma.rn.f32.f16 with the
+// constant 1.0: exact product, one rounding — the same result as converting to fp32 and adding)
+__device__ __forceinline__ void add_f16x2(uint32_t& acc0, uint32_t& acc1, uint32_t hw) {
+  float a0 = __uint_as_float(acc0), a1 = __uint_as_float(acc1);
+  asm("{\n .reg .b16 lo, hi, one;\n mov.b32 {lo, hi}, %2;\n mov.b16 one, 0x3C00;\n"
+      " fma.rn.f32.f16 %0, lo, one, %0;\n fma.rn.f32.f16 %1, hi, one, %1;\n}\n"
+      : "+f"(a0), "+f"(a1) : "r"(hw));
+  acc0 = __float_as_uint(a0);
+  acc1 = __float_as_uint(a1);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack2t(float lo, float hi) {
+  uint32_t r;
+  if (F16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 struct GemmParams {
@@ -71,7 +94,7 @@ struct GemmSmem {
   uint8_t stage[TMA_ST ? NUM_EPI_WARPS * (EPI == EPI_KIND_GENERIC ? 2 : 1) * StageBytes<EPI>::value : 16];   // generic: double-buffered
   uint8_t rowb[ROWB ? NUM_EPI_WARPS * 32 * BLOCK_N : 16];   // per epilogue warp: 32 rows x BLOCK_N / 2 fp16 row-bias values
   uint64_t rb_full[NUM_EPI_WARPS];
-  float bias[BLOCK_N];
+  alignas(16) float bias[BLOCK_N];
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
   uint64_t b_full;
@@ -251,58 +274,77 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if constexpr (TMA_ST) {
           // Two staging tiles per warp and the next chunk's TMEM load in flight while this one is converted and stored:
           // the single-buffered form waited for every TMA store to drain before the next chunk could be staged.
-          auto emit = [&](const uint32_t (&r)[32], int c) {
-            const int cl = half * HALF_N + c;       // column inside the tile
-            if (n0 + cl >= p.N) return;
-            uint32_t o[16];
+          // MODE 0: run-time flags (row mask / ReLU / fp16 output); MODE 1: bias only, bf16; MODE 2: bias + ReLU, bf16 —
+          // the two shapes the encoder runs (value / FFN1), one FADD per element and one F2FP(.RELU) per pair.
+          auto run_tile = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            auto emit = [&](const uint32_t (&r)[32], int c) {
+              const int cl = half * HALF_N + c;       // column inside the tile
+              if (n0 + cl >= p.N) return;
+              uint32_t o[16];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const float4 b0 = *reinterpret_cast<const float4*>(&s.bias[cl + h * 8]);
-              const float4 b1 = *reinterpret_cast<const float4*>(&s.bias[cl + h * 8 + 4]);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              float v[8];
+              for (int h = 0; h < 4; ++h) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&s.bias[cl + h * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&s.bias[cl + h * 8 + 4]);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float v[8];
+                if constexpr (MODE == 0) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x = (__uint_as_float(r[h * 8 + i]) + bb[i]) * rs;
-                v[i] = relu ? fmaxf(x, 0.f) : x;
+                  for (int i = 0; i < 8; ++i) {
+                    const float x = (__uint_as_float(r[h * 8 + i]) + bb[i]) * rs;
+                    v[i] = relu ? fmaxf(x, 0.f) : x;
+                  }
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) o[h * 4 + i] = pack2(v[2 * i], v[2 * i + 1], p.y_dtype);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h * 8 + i]) + bb[i];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if (MODE == 2) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o[h * 4 + i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+                    else o[h * 4 + i] = pack2t<false>(v[2 * i], v[2 * i + 1]);
+                  }
+                }
               }
+              const uint32_t stage = stage0 + (st_par ? (uint32_t)StageBytes<EPI>::value : 0u);
+              st_par ^= 1u;
+              if (lane == 0) tma_store_wait_read_1();        // the store issued two chunks ago has drained this tile
+              __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 4; ++i) o[h * 4 + i] = pack2(v[2 * i], v[2 * i + 1], p.y_dtype);
-            }
-            const uint32_t stage = stage0 + (st_par ? (uint32_t)StageBytes<EPI>::value : 0u);
-            st_par ^= 1u;
-            if (lane == 0) tma_store_wait_read_1();        // the store issued two chunks ago has drained this tile
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < 4; ++h)                      // SWIZZLE_64B: 16-byte chunk h of row `lane`
-              sts128(stage + lane * 64 + ((h ^ ((lane >> 1) & 3)) << 4), o[h * 4], o[h * 4 + 1], o[h * 4 + 2], o[h * 4 + 3]);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              const int col = n0 + cl;
-              if (hm) {   // [B*heads, hm_rows, D = 32]: this chunk is exactly one head
-                const int bidx = row0 / p.hm_rows;
-                tma_store_3d(&p.tma_y, stage, 0, row0 - bidx * p.hm_rows, bidx * p.hm_heads + (col >> 5));
-              } else {
-                tma_store_2d(&p.tma_y, stage, col, row0);
+              for (int h = 0; h < 4; ++h)                      // SWIZZLE_64B: 16-byte chunk h of row `lane`
+                sts128(stage + lane * 64 + ((h ^ ((lane >> 1) & 3)) << 4), o[h * 4], o[h * 4 + 1], o[h * 4 + 2], o[h * 4 + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                const int col = n0 + cl;
+                if (hm) {   // [B*heads, hm_rows, D = 32]: this chunk is exactly one head
+                  const int bidx = row0 / p.hm_rows;
+                  tma_store_3d(&p.tma_y, stage, 0, row0 - bidx * p.hm_rows, bidx * p.hm_heads + (col >> 5));
+                } else {
+                  tma_store_2d(&p.tma_y, stage, col, row0);
+                }
+                tma_store_commit();
               }
-              tma_store_commit();
+            };
+            constexpr int NCH = HALF_N / 32;
+            uint32_t ra[32], rb[32];
+            TMEM_LD_X32(t_row, ra);
+#pragma unroll
+            for (int ci = 0; ci < NCH; ci += 2) {
+              TMEM_WAIT_X32(ra);
+              if (ci + 1 < NCH) TMEM_LD_X32(t_row + (ci + 1) * 32, rb);
+              emit(ra, ci * 32);
+              if (ci + 1 < NCH) {
+                TMEM_WAIT_X32(rb);
+                if (ci + 2 < NCH) TMEM_LD_X32(t_row + (ci + 2) * 32, ra);
+                emit(rb, (ci + 1) * 32);
+              }
             }
           };
-          constexpr int NCH = HALF_N / 32;
-          uint32_t ra[32], rb[32];
-          TMEM_LD_X32(t_row, ra);
-#pragma unroll
-          for (int ci = 0; ci < NCH; ci += 2) {
-            TMEM_WAIT_X32(ra);
-            if (ci + 1 < NCH) TMEM_LD_X32(t_row + (ci + 1) * 32, rb);
-            emit(ra, ci * 32);
-            if (ci + 1 < NCH) {
-              TMEM_WAIT_X32(rb);
-              if (ci + 2 < NCH) TMEM_LD_X32(t_row + (ci + 2) * 32, ra);
-              emit(rb, (ci + 1) * 32);
-            }
-          }
+          const bool plain = !(p.flags & EMRT_EPI_ROW_MASK) && p.y_dtype == EMRT_BF16;
+          if (plain && relu) run_tile(std::integral_constant<int, 2>{});
+          else if (plain) run_tile(std::integral_constant<int, 1>{});
+          else run_tile(std::integral_constant<int, 0>{});
         }
 #pragma unroll 1
         for (int c = 0; !TMA_ST && c < HALF_N; c += 32) {
@@ -347,18 +389,16 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
         for (int c = 0; c < HALF_N / 8; ++c) TMEM_WAIT_X8(r[c]);
         if constexpr (ROWB) {
-          // this lane's row of the box: HALF_N fp16 = HALF_N * 2 bytes (144: a 36-bank stride, conflict-free as is)
+          // this lane's row of the box: HALF_N fp16 = HALF_N * 2 bytes (144: a 36-bank stride, conflict-free as is).  The
+          // table already holds the bias (host contract: bias == NULL with row_bias), so no bias pass exists on this path.
           const uint32_t rb = smem_u32(s.rowb) + (uint32_t)(ew * 32 * BLOCK_N + lane * (HALF_N * 2));
 #pragma unroll
           for (int c = 0; c < HALF_N / 8; ++c) {
             const uint4 h = lds128(rb + c * 16);
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-              r[c][2 * i] = __float_as_uint(__uint_as_float(r[c][2 * i]) + f.x);
-              r[c][2 * i + 1] = __float_as_uint(__uint_as_float(r[c][2 * i + 1]) + f.y);
-            }
+            add_f16x2(r[c][0], r[c][1], h.x);
+            add_f16x2(r[c][2], r[c][3], h.y);
+            add_f16x2(r[c][4], r[c][5], h.z);
+            add_f16x2(r[c][6], r[c][7], h.w);
           }
           __syncwarp();                        // every lane has read the box: fetch the next tile's
           if (lane == 0) {
@@ -366,71 +406,88 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             nx.next();
             if (nx.valid()) load_rb(nx);
           }
+        } else {
+          // bias: 16-byte shared-memory reads (s.bias is 16-byte aligned, cl a multiple of 8)
+#pragma unroll
+          for (int c = 0; c < HALF_N / 8; ++c) {
+            const float4 b0 = *reinterpret_cast<const float4*>(&s.bias[cl + c * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&s.bias[cl + c * 8 + 4]);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[c][i] = __float_as_uint(__uint_as_float(r[c][i]) + bb[i]);
+          }
         }
         const uint32_t stage = smem_u32(s.stage) + (uint32_t)(warp - EPI_WARP0) * StageBytes<EPI>::value;
         const int row0 = tw.m * BM + q * 32;
-        if (tw.n < 2) {
-          if constexpr (TMA_ST) {
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < HALF_N / 8; ++c) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[c][i]) + s.bias[cl + c * 8 + i];
-              sts128(stage + lane * (HALF_N * 2) + c * 16, pack2(v[0], v[1], p.y_dtype), pack2(v[2], v[3], p.y_dtype),
-                     pack2(v[4], v[5], p.y_dtype), pack2(v[6], v[7], p.y_dtype));
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) { tma_store_2d(&p.tma_y, stage, n0 + cl, row0); tma_store_commit(); }
-          } else if (row_ok) {
-#pragma unroll
-            for (int c = 0; c < HALF_N / 8; ++c) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[c][i]) + s.bias[cl + c * 8 + i];
-              store8(p.y, p.y_dtype, row * (2 * tp) + n0 + cl + c * 8, v);
-            }
-          }
-        } else {
-          // softmax over each group of GROUP consecutive logits (t_e_d.py:92-96); this thread's half row lives in
-          // registers (static indexing)
-          uint32_t o[HALF_N / 2];
-#pragma unroll
-          for (int g = 0; g < HALF_N / GROUP; ++g) {
-            float v[GROUP];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < GROUP; ++i) {
-              const int col = g * GROUP + i;
-              v[i] = __uint_as_float(r[col / 8][col % 8]) + s.bias[cl + col];
-              mx = fmaxf(mx, v[i]);
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < GROUP; ++i) { v[i] = __expf(v[i] - mx); sum += v[i]; }
-            const float inv = 1.f / sum;
+        // the output type is kernel-uniform: both forms are compiled, one warp-uniform branch picks
+        auto finish = [&](auto f16_tag) {
+          constexpr bool F16 = decltype(f16_tag)::value;
+          if (tw.n < 2) {
             if constexpr (TMA_ST) {
+              uint32_t o[HALF_N / 2];
 #pragma unroll
-              for (int i = 0; i < GROUP; i += 2) o[(g * GROUP + i) / 2] = pack2(v[i] * inv, v[i + 1] * inv, p.y_dtype);
+              for (int c = 0; c < HALF_N / 8; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[c * 4 + i] = pack2t<F16>(__uint_as_float(r[c][2 * i]), __uint_as_float(r[c][2 * i + 1]));
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < HALF_N / 8; ++c)
+                sts128(stage + lane * (HALF_N * 2) + c * 16, o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&p.tma_y, stage, n0 + cl, row0); tma_store_commit(); }
             } else if (row_ok) {
 #pragma unroll
-              for (int i = 0; i < GROUP; i += 2)
-                store2(p.y2, p.y_dtype, row * tp + cl + g * GROUP + i, v[i] * inv, v[i + 1] * inv);
+              for (int c = 0; c < HALF_N / 8; ++c) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[c][i]);
+                store8(p.y, p.y_dtype, row * (2 * tp) + n0 + cl + c * 8, v);
+              }
+            }
+          } else {
+            // softmax over each group of GROUP consecutive logits (t_e_d.py:92-96); this thread's half row lives in
+            // registers (static indexing).  exp(v - max) = ex2(v * log2e - max * log2e): one FFMA + one MUFU per logit.
+            uint32_t o[HALF_N / 2];
+#pragma unroll
+            for (int g = 0; g < HALF_N / GROUP; ++g) {
+              float v[GROUP];
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < GROUP; ++i) {
+                const int col = g * GROUP + i;
+                v[i] = __uint_as_float(r[col / 8][col % 8]);
+                mx = fmaxf(mx, v[i]);
+              }
+              const float nmx = -mx * 1.4426950408889634f;
+              float sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < GROUP; ++i) { v[i] = ex2_approx(fmaf(v[i], 1.4426950408889634f, nmx)); sum += v[i]; }
+              const float inv = 1.f / sum;
+              if constexpr (TMA_ST) {
+#pragma unroll
+                for (int i = 0; i < GROUP; i += 2) o[(g * GROUP + i) / 2] = pack2t<F16>(v[i] * inv, v[i + 1] * inv);
+              } else if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < GROUP; i += 2)
+                  store2(p.y2, p.y_dtype, row * tp + cl + g * GROUP + i, v[i] * inv, v[i + 1] * inv);
+              }
+            }
+            if constexpr (TMA_ST) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+#pragma unroll
+              for (int c = 0; c < HALF_N / 8; ++c)
+                sts128(stage + lane * (HALF_N * 2) + c * 16, o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&p.tma_y2, stage, cl, row0); tma_store_commit(); }
             }
           }
-          if constexpr (TMA_ST) {
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < HALF_N / 8; ++c)
-              sts128(stage + lane * (HALF_N * 2) + c * 16, o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) { tma_store_2d(&p.tma_y2, stage, cl, row0); tma_store_commit(); }
-          }
-        }
+        };
+        if (p.y_dtype == EMRT_F16) finish(std::true_type{});
+        else finish(std::false_type{});
       }
       tc_fence_before();
       __syncwarp();
@@ -595,6 +652,7 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
     if (a->row_bias) {
       if (a->row_bias_period <= 0 || (reinterpret_cast<uintptr_t>(a->row_bias) & 15) || !res || !tma_st)
         return set_error(EMRT_ERR_UNSUPPORTED, "row_bias needs row_bias_period > 0, a 16-byte aligned F16 table, K <= 256 and 2-byte outputs");
+      if (a->bias) return set_error(EMRT_ERR_INVALID_ARGUMENT, "row_bias already holds the bias (x2 W + bias): pass bias = NULL");
       p.rb_period = a->row_bias_period;
       return launch_tc<144, 4, EPI_KIND_QPROJ, 18, true, true, true>(p, a, st);
     }

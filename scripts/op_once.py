@@ -44,10 +44,11 @@ with torch.no_grad():
         raise SystemExit("unknown op " + what)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = int(os.environ.get("EMRT_OP_ITERS", "3"))
     fn()
     e0.record()
-    for _ in range(3):
+    for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    print(what, "avg ms", e0.elapsed_time(e1) / 3)
+    print(what, "avg ms", e0.elapsed_time(e1) / iters)
