@@ -43,6 +43,15 @@ class LinearArgs(C.Structure):
     ]
 
 
+class FfnArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
+        ("y", C.c_void_p), ("rows", C.c_int64), ("d_model", C.c_int32), ("d_ff", C.c_int32),
+        ("gn", C.POINTER(GnBranch)),
+    ]
+
+
 class MsdaArgs(C.Structure):
     _fields_ = [
         ("query", C.c_void_p), ("value", C.c_void_p), ("ref", C.c_void_p), ("ref_batches", C.c_int32),
@@ -89,6 +98,7 @@ SIGNATURES = {
     "emrt_msda_gather_bwd_hint": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I32P, _I32P,
                                             _I, _I, _I, _I32P, _P]),
     "emrt_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _P]),
+    "emrt_ffn_fused_fwd": (C.c_int, [C.POINTER(FfnArgs), _P]),
     "emrt_pack_weight": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
     "emrt_linear_bwd_weight": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "emrt_msda_qproj_bwd": (C.c_int, [_P, _P, _P, _P, _L, _I, _I, _I, _I32P, _I, _I, _I, _P]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libemrt_b200.so")
-SOURCES = ["core.cu", "msda_gather.cu", "msda_gather_v1.cu", "msda_gather_win.cu", "msda_gather_win7.cu", "msda_gather_bwd_win.cu", "msda_aux.cu", "linear_simt.cu", "linear_tcgen05.cu", "linear_ln_tcgen05.cu", "head.cu", "train_kernels.cu", "linear_bwd_tcgen05.cu", "encoder_glue.cu", "conv3x3_tcgen05.cu", "mha_small.cu", "train_glue.cu", "msda_fused.cu"]
+SOURCES = ["core.cu", "msda_gather.cu", "msda_gather_v1.cu", "msda_gather_win.cu", "msda_gather_win7.cu", "msda_gather_bwd_win.cu", "msda_aux.cu", "linear_simt.cu", "linear_tcgen05.cu", "linear_ln_tcgen05.cu", "ffn_fused_tcgen05.cu", "head.cu", "train_kernels.cu", "linear_bwd_tcgen05.cu", "encoder_glue.cu", "conv3x3_tcgen05.cu", "mha_small.cu", "train_glue.cu", "msda_fused.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -80,6 +80,8 @@ struct GemmParams {
   int32_t flags;
   int32_t hm_rows, hm_heads, hm_shift;   // HEAD_MAJOR: rows per batch element, heads, log2(head dim)
   int32_t tiles_m, tiles_n;
+  int32_t l2_prefetch;                   // row tiles of A requested into L2 ahead of the shared-memory ring (0 = off)
+  int32_t debug;                         // timing experiments (wrong results): 1 = no output stores, 2 = empty epilogue
 };
 
 // Staged epilogue: every epilogue warp owns a 32-row staging tile that one TMA store drains.
@@ -172,7 +174,17 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       // x2 (the broadcast addend, e.g. the position embedding): (x + x2) W = x W + x2 W, so its tiles are simply
       // num_kb more k-blocks of the same accumulation against the same weight blocks
       const int total_kb = p.a2_period ? 2 * num_kb : num_kb;
+      // The ring holds about one row tile of A, so by itself it keeps one tile's bytes in flight and every tile waits a
+      // full HBM latency (tile period = latency + one k-block).  A second walker requests the A tiles `l2_prefetch` tiles
+      // ahead into L2; the ring's own loads then complete at L2 latency.
+      TileWalk pf(B_RES, p.tiles_m, p.tiles_n);
+      for (int i = 0; i < p.l2_prefetch && pf.valid(); ++i, pf.next())
+        if (i > 0) for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_2d(&p.tma_a, kb * BK, pf.m * BM);
       for (; tw.valid(); tw.next()) {
+        if (p.l2_prefetch && pf.valid()) {
+          for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_2d(&p.tma_a, kb * BK, pf.m * BM);
+          pf.next();
+        }
         const int row2 = p.a2_period ? (int)(((int64_t)tw.m * BM) % p.a2_period) : 0;
         for (int kk = 0; kk < total_kb; ++kk) {
           const int kb = kk < num_kb ? kk : kk - num_kb;
@@ -315,7 +327,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 sts128(stage + lane * 64 + ((h ^ ((lane >> 1) & 3)) << 4), o[h * 4], o[h * 4 + 1], o[h * 4 + 2], o[h * 4 + 3]);
               fence_proxy_async();
               __syncwarp();
-              if (lane == 0) {
+              if (lane == 0 && !(p.debug & 1)) {
                 const int col = n0 + cl;
                 if (hm) {   // [B*heads, hm_rows, D = 32]: this chunk is exactly one head
                   const int bidx = row0 / p.hm_rows;
@@ -342,7 +354,8 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             }
           };
           const bool plain = !(p.flags & EMRT_EPI_ROW_MASK) && p.y_dtype == EMRT_BF16;
-          if (plain && relu) run_tile(std::integral_constant<int, 2>{});
+          if (p.debug & 2) {}
+          else if (plain && relu) run_tile(std::integral_constant<int, 2>{});
           else if (plain) run_tile(std::integral_constant<int, 1>{});
           else run_tile(std::integral_constant<int, 0>{});
         }
@@ -579,6 +592,8 @@ static int launch_tc(GemmParams& p, const emrt_linear_args* a, cudaStream_t st) 
   }
   p.tiles_m = (int)((a->rows + BM - 1) / BM);
   p.tiles_n = (a->N + BLOCK_N - 1) / BLOCK_N;
+  { const char* e = getenv("EMRT_GEMM_L2_PREFETCH"); p.l2_prefetch = e ? atoi(e) : 0; }
+  { const char* e = getenv("EMRT_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; }
   auto kern = linear_tcgen05_kernel<BLOCK_N, STAGES, EPI, GROUP, B_RES, TMA_ST, ROWB>;
   // function attributes are per device / context: set every time (cheap), not once per process
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

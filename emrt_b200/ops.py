@@ -183,6 +183,41 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     return (out, out2) if (epilogue & L.EPI_MSDA_QPROJ) else out
 
 
+def _gn_struct(gn_branch):
+    gnb = L.GnBranch()
+    gnb.conv, gnb.skip, gnb.stats = _ptr(gn_branch["conv"]), _ptr(gn_branch["skip"]), _ptr(gn_branch["stats"])
+    gnb.gamma, gnb.beta = _ptr(gn_branch["gamma"]), _ptr(gn_branch["beta"])
+    shapes = gn_branch["shapes"]
+    gnb.L, gnb.groups, gnb.eps = len(shapes), int(gn_branch.get("groups", 32)), float(gn_branch.get("eps", 1e-5))
+    gnb.Lv = sum(int(h) * int(w) for h, w in shapes)
+    for i, (h, w) in enumerate(shapes):
+        gnb.shapes_hw[2 * i], gnb.shapes_hw[2 * i + 1] = int(h), int(w)
+    return gnb
+
+
+def ffn_fused(x, w1, b1, w2, b2, ln_gamma, ln_beta, *, ln_eps=1e-5, gn_branch=None, out=None):
+    """y = LayerNorm(x + linear2(relu(linear1(x)))) * ln_gamma + ln_beta (+ conv branch): forward_ffn (t_e_d.py:157-160)
+    and the layer's final add (:203) in one kernel; the hidden tensor never reaches HBM.  x bf16 [..., 256]; w1 / w2 the
+    packed bf16 [d_ff, 256] / [256, d_ff] weights; gn_branch as in `linear`."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    d_model = x.shape[-1]
+    d_ff = w1.shape[0]
+    assert w1.shape == (d_ff, d_model) and w2.shape == (d_model, d_ff)
+    if out is None:
+        out = torch.empty_like(x)
+    a = L.FfnArgs()
+    a.x, a.w1, a.b1, a.w2, a.b2 = _ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2)
+    a.ln_gamma, a.ln_beta, a.ln_eps = _ptr(ln_gamma), _ptr(ln_beta), float(ln_eps)
+    a.y, a.rows, a.d_model, a.d_ff = _ptr(out), x.numel() // d_model, d_model, d_ff
+    gnb = None
+    if gn_branch is not None:
+        gnb = _gn_struct(gn_branch)
+        a.gn = C.pointer(gnb)
+    with _Timed("ffn_fused", (a.rows, d_model, d_ff, x.element_size())):
+        L.check(L.load().emrt_ffn_fused_fwd(C.byref(a), _stream()))
+    return out
+
+
 def cyclic_rows(addend, extra=127, dtype=torch.bfloat16):
     """[period, K] -> `dtype` [period + extra, K]: the rows continued cyclically (the x2 / row_bias operand of `linear`:
     any 128-row tile of a [B * period, .] activation then reads its addend rows as one contiguous box)."""

@@ -159,6 +159,22 @@ typedef struct emrt_linear_args {
 } emrt_linear_args;
 int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 
+/* ---- TransformerEncoderLayer.forward_ffn in one kernel (transformer_encoder_decoder.py:157-160, + :187-189,203) ------
+ * y = LayerNorm(x + linear2(relu(linear1(x)))) * ln_gamma + ln_beta  (+ GELU(GroupNorm_l(conv)) + skip when gn != NULL).
+ * The hidden activations [rows, d_ff] never reach HBM: each CTA walks d_ff in 64-unit chunks, the first GEMM's
+ * accumulator chunk is converted (bias, ReLU, bf16) into the shared-memory A operand of the second, whose accumulator
+ * (one 256-column TMEM row per token) feeds the LayerNorm epilogue.  BF16 / tcgen05 only: x, y BF16 [rows, 256];
+ * w1 BF16 [d_ff, 256] and w2 BF16 [256, d_ff] pre-packed (emrt_pack_weight); b1 F32 [d_ff], b2 / ln_gamma / ln_beta F32
+ * [256]; d_model = 256, d_ff % 64 == 0; every pointer 16-byte aligned.  y must not alias x (x is re-read as the
+ * residual while other tiles are being written).                                                                    */
+typedef struct emrt_ffn_args {
+  const void* x; const void* w1; const float* b1; const void* w2; const float* b2;
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
+  void* y; int64_t rows; int32_t d_model; int32_t d_ff;
+  const emrt_gn_branch* gn;   /* NULL = plain LayerNorm epilogue */
+} emrt_ffn_args;
+int emrt_ffn_fused_fwd(const emrt_ffn_args* args, void* stream);
+
 /* ---- backward of nn.Linear (what Paddle autograd derives for transformer_encoder_decoder.py:83,89,92,106) --------
  * Data gradient dx = dy W^T needs no entry point of its own: call emrt_linear_fwd with x = dy, K = N_fwd,
  * N = K_fwd, bias = NULL and w = the Paddle-layout weight [in,out] passed as w_transposed = 1.

@@ -40,6 +40,13 @@ with torch.no_grad():
         stats = ops.groupnorm_stats(conv, shapes, groups=32)
         fn = lambda: ops.linear(h, lp["w2"], lp["b2"], w_transposed=True, epilogue=L.EPI_RESIDUAL_LN, residual=src, ln_gamma=lp["n2w"],
                                 ln_beta=lp["n2b"], gn_branch=dict(conv=conv, skip=src, stats=stats, gamma=lp["gn_w"], beta=lp["gn_b"], shapes=shapes))
+    elif what == "ffn":
+        conv = torch.randn((B, Lv, 256), generator=g, device=dev).bfloat16()
+        stats = ops.groupnorm_stats(conv, shapes, groups=32)
+        x_in = torch.randn((B, Lv, 256), generator=g, device=dev).bfloat16()
+        out = torch.empty_like(src)
+        fn = lambda: ops.ffn_fused(x_in, lp["w1"], lp["b1"], lp["w2"], lp["b2"], lp["n2w"], lp["n2b"], out=out,
+                                   gn_branch=dict(conv=conv, skip=src, stats=stats, gamma=lp["gn_w"], beta=lp["gn_b"], shapes=shapes))
     else:
         raise SystemExit("unknown op " + what)
     torch.cuda.synchronize()
