@@ -4,26 +4,34 @@
 // Why: as two GEMMs the hidden tensor [rows, 1024] crosses HBM twice — 793 MB written by linear1 (which runs AT this GPU's
 // pure-write ceiling, 3.9 TB/s: profiles/r2o_hbm_write_read.txt) and 793 MB read back by linear2: 1.6 GB of the layer's
 // 2.6 GB of FFN traffic and 0.5 ms of its 1.9 ms.  Here the hidden activations never leave the SM: a CTA owns a 128-token
-// row tile and walks the hidden dimension in chunks of 64 units:
-//     GEMM1(c):  hacc[c&1] (TMEM, 64 cols)  = x[128 x 256] @ W1[c*64 .. +64, :]^T          (4 k-blocks, UMMA N = 64)
-//     convert:   h_c = bf16(relu(hacc + b1))  -> shared memory, canonical K-major SWIZZLE_128B tile (the A operand of GEMM2)
-//     GEMM2(c):  y (TMEM, 256 cols)        += h_c[128 x 64] @ W2[:, c*64 .. +64]^T          (1 k-block, UMMA N = 256)
-// and the weights (1 MB per row tile) stream from L2 through a 3 x 32 KB TMA ring, the way the 3x3 conv streams its taps.
-// The LayerNorm + conv-branch epilogue of linear_ln_tcgen05.cu follows on the same tile.
+// row tile and walks the hidden dimension in chunks of 128 units:
+//     GEMM1(c):  hacc (TMEM, 128 cols)  = x[128 x 256] @ W1[128 c .. +128, :]^T              (4 k-blocks, UMMA N = 128)
+//     convert:   h_c = bf16(relu(hacc + b1)) -> shared memory, two canonical K-major SWIZZLE_128B [128 x 64] tiles
+//     GEMM2(c):  y (TMEM, 256 cols)    += h_c[128 x 128] @ W2[:, 128 c .. +128]^T            (2 k-blocks, UMMA N = 256)
+// and the weights (1 MB per row tile) stream from L2 through a ring of six 16 KB TMA units, the way the 3x3 conv streams its
+// taps.  The LayerNorm + conv-branch epilogue of linear_ln_tcgen05.cu follows on the same tile.
+//
+// What paces it (measured, EMRT_FFN_PROF): the tensor pipe's OPERAND FETCH.  A cta_group::1 tcgen05.mma reads A and B from
+// shared memory at 64 B/clk, so one M = 128, K = 16 instruction costs (4096 + 32 N) / 64 = 64 + N/2 clocks, not the N/2 of
+// the arithmetic: N = 256 runs at 67 % of the nominal rate (which is where cuBLAS's measured 1.6 PFLOP/s sits against the
+// nominal 2.4), N = 128 at 50 %, N = 64 at 33 %.  The first version of this kernel (64-unit chunks: N = 64 for GEMM1) and the
+// second (N = 128 everywhere) both ran at exactly the time this model gives.  Hence: GEMM2 with N = 256, GEMM1 with the
+// largest N the 512 TMEM columns leave room for (128).
 //
 // Warp roles (448 threads, one CTA per SM, persistent over row tiles):
-//   warp 0        TMA producer: x tile (64 KB, once per tile), then W1(0), W1(1), W2(0), W1(2), W2(1), ... in MMA order
-//   warp 1        tcgen05.mma issuer: G1(0), [G1(c+1), G2(c)] ... — G1(c+1) runs while chunk c is being converted
-//   warps 2..9    H warps: TMEM -> +b1 -> ReLU -> bf16 -> swizzled shared memory (two warps per TMEM lane quarter)
-//   warps 10..13  LN warps (one per lane quarter, a thread owns a token): pass 1 adds bias + residual to the y accumulator,
-//                 rounds to bf16 and parks the row in 128 spare TMEM columns (packed pairs) — that frees y for the next tile's
-//                 GEMM2 after ~1 us instead of after the whole epilogue; passes 2 / 3 (centred variance; normalise + GELU(
-//                 GroupNorm(conv)) + skip, TMA store) then run from the parked copy while the tensor pipe works on the next tile.
-// TMEM: y [0,256) | hacc0 [256,320) | hacc1 [320,384) | parked pre-LayerNorm row, bf16 pairs [384,512).
+//   warp 0        TMA producer: x tile (64 KB, once per tile), then the weight units in MMA order
+//   warp 1        tcgen05.mma issuer: G1(0), then [G1(c+1), G2(c)] — GEMM2(c-1) and GEMM1(c+1) run while chunk c is converted
+//   warps 2..5    H warps (one per TMEM lane quarter): TMEM -> +b1 -> ReLU -> bf16 -> swizzled shared memory
+//   warps 6..13   LN warps (two per lane quarter, 128 columns each; a thread owns half a token): pass 1 adds bias + residual
+//                 to the y accumulator, rounds to bf16 and parks the row in 128 spare TMEM columns (packed pairs) — that frees
+//                 y for the next tile's GEMM2 after ~1 us instead of after the whole epilogue; passes 2 / 3 (centred variance;
+//                 normalise + GELU(GroupNorm(conv)) + skip, TMA store) run from the parked copy under the next tile's MMAs.
+// TMEM: y [0,256) | hacc [256,384) | parked pre-LayerNorm row, bf16 pairs [384,512).
 // Numerics: linear1's output is rounded to bf16 (as the two-kernel form stores it); linear2 + bias + residual is rounded to
-// bf16 once before the LayerNorm (the two-kernel form rounded linear2's output in its first version; oracle: `ffn_fused`).
+// bf16 once before the LayerNorm (oracle: kernel_storage_rounding models both).
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -34,22 +42,25 @@ int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const vo
 
 namespace {
 
-constexpr int BM = 128, BK = 64, DM = 256, CH = 64, UMMA_K = 16;
-constexpr int H_WARP0 = 2, NUM_H_WARPS = 8, LN_WARP0 = 10, NUM_LN_WARPS = 4;
+constexpr int BM = 128, BK = 64, DM = 256, CH = 128, UMMA_K = 16;
+constexpr int H_WARP0 = 2, NUM_H_WARPS = 4, LN_WARP0 = 6, NUM_LN_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (LN_WARP0 + NUM_LN_WARPS);
 constexpr int TMEM_COLS = 512, Y_COL = 0, HACC_COL = 256, XP_COL = 384;
-constexpr int W_STAGES = 3;
-constexpr uint32_t W_STAGE_BYTES = 32768;          // W1 chunk: 4 k-blocks x [64 x 64] bf16; W2 chunk: one [256 x 64] k-block
-constexpr int CHUNK = 32;                          // LayerNorm epilogue: columns per step
-constexpr int CHUNKS = DM / CHUNK;                 // 8
-constexpr uint32_t BUF_BYTES = 32 * CHUNK * 2;     // one staged chunk: 32 rows x 64 bytes
+constexpr int W_UNITS = 6;                         // weight ring: units of one [128 rows x 64 k] bf16 box; a W2 k-block takes two
+constexpr uint32_t W_UNIT_BYTES = 128 * BK * 2;    // 16 KB
+constexpr int HS_SLOTS = 2;                        // hidden k-block tiles [128 x 64] between the H warps and GEMM2
+constexpr int LCH = 16;                            // LayerNorm epilogue: columns per step
+constexpr int LN_COLS = DM / 2;                    // columns per LN warp
+constexpr int LCHUNKS = LN_COLS / LCH;             // 8
+constexpr int LN_BUFS = 4;                         // chunk buffers per LN warp
+constexpr uint32_t LBUF_BYTES = 32 * LCH * 2;      // one staged chunk: 32 rows x 32 bytes
 constexpr int GN_MAX_L = 4, GN_GROUPS = 32;
 
 struct FfnParams {
   CUtensorMap tma_x;     // x  [rows, 256] bf16, box {64, 128}, SWIZZLE_128B
-  CUtensorMap tma_w1;    // W1 [F, 256]    bf16, box {64, 64},  SWIZZLE_128B
+  CUtensorMap tma_w1;    // W1 [F, 256]    bf16, box {64, 128}, SWIZZLE_128B
   CUtensorMap tma_w2;    // W2 [256, F]    bf16, box {64, 256}, SWIZZLE_128B
-  CUtensorMap tma_res;   // x  [rows, 256] bf16, box {32, 32},  SWIZZLE_64B (the residual, read back from L2)
+  CUtensorMap tma_res;   // x  [rows, 256] bf16, box {16, 32},  SWIZZLE_32B (the residual, read back from L2)
   CUtensorMap tma_y;     // y  [rows, 256] bf16, same box
   CUtensorMap tma_conv;  // conv / skip [rows, 256] bf16, same box
   CUtensorMap tma_skip;
@@ -65,29 +76,28 @@ struct FfnParams {
   int32_t L, Lv, B;
   LevelTable lv;
   int32_t tiles_m, num_chunks;
+  int32_t debug;         // timing experiments (wrong results): 1 = LN warps stop after pass 1
+  long long* prof;       // EMRT_FFN_PROF: per CTA, cycles the MMA thread spent waiting on each barrier kind
 };
 
 struct FfnSmem {
   __nv_bfloat16 x[DM / BK][BM * BK];               // 64 KB: the row tile, A operand of every GEMM1
-  __nv_bfloat16 hs[2][BM * CH];                    // 2 x 16 KB: relu(linear1) chunk, A operand of GEMM2
-  uint8_t w[W_STAGES][W_STAGE_BYTES];              // 96 KB weight ring
-  uint8_t buf[NUM_LN_WARPS][2][BUF_BYTES];         // residual chunks (pass 1), conv chunks / output staging (pass 3)
-  uint8_t buf2[NUM_LN_WARPS][2][BUF_BYTES];        // skip chunks
+  __nv_bfloat16 hs[HS_SLOTS][BM * BK];             // 2 x 16 KB: relu(linear1) k-blocks, A operand of GEMM2
+  uint8_t w[W_UNITS][W_UNIT_BYTES];                // 96 KB weight ring
+  uint8_t lbuf[NUM_LN_WARPS][LN_BUFS][LBUF_BYTES]; // per LN warp: ring of 1 KB chunk buffers (residual | conv, skip / output)
+  float xch[2][2][BM];                             // [pass][column half][row]: partial row sums of the two LN warps of a row
   uint64_t x_full, x_empty;
-  uint64_t w_full[W_STAGES], w_empty[W_STAGES];
-  uint64_t hacc_full[2], hacc_empty[2];
-  uint64_t hs_full[2], hs_empty[2];
+  uint64_t w_full[W_UNITS], w_empty[W_UNITS];
+  uint64_t hacc_full, hacc_empty;
+  uint64_t hs_full[HS_SLOTS], hs_empty[HS_SLOTS];
   uint64_t y_full, y_empty;
-  uint64_t res_full[NUM_LN_WARPS][2], gn_full[NUM_LN_WARPS][2];
+  uint64_t l_full[NUM_LN_WARPS][LN_BUFS];
   uint32_t tmem_base;
 };
 
-#define TMEM_ST_X16(taddr, r)                                                                                     \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" \
-               ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),          \
-                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),    \
-                 "r"(taddr)                                                                                       \
-               : "memory")
+#define TMEM_ST_X8(taddr, r)                                                                                      \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"                            \
+               ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(taddr) : "memory")
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -95,7 +105,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -113,7 +123,18 @@ template <bool GN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  FfnSmem& s = *reinterpret_cast<FfnSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const uint32_t align_off = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  FfnSmem& s = *reinterpret_cast<FfnSmem*>(smem_raw + align_off);
+  {
+    // the launch asks for sizeof(FfnSmem) plus whatever slack the 227 KB limit leaves: fail loudly if the window's base is
+    // not aligned well enough for the struct to fit behind the SWIZZLE_128B alignment
+    uint32_t dyn;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (align_off + (uint32_t)sizeof(FfnSmem) > dyn) {
+      if (threadIdx.x == 0 && blockIdx.x == 0) printf("ffn_fused: shared window misaligned by %u bytes, %u available\n", align_off, dyn);
+      __trap();
+    }
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NC = p.num_chunks;
@@ -128,16 +149,15 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
     mbar_init(&s.x_full, 1);
     mbar_init(&s.x_empty, 1);
 #pragma unroll
-    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+    for (int i = 0; i < W_UNITS; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+    mbar_init(&s.hacc_full, 1);
+    mbar_init(&s.hacc_empty, NUM_H_WARPS);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.hacc_full[i], 1); mbar_init(&s.hacc_empty[i], NUM_H_WARPS);
-      mbar_init(&s.hs_full[i], NUM_H_WARPS); mbar_init(&s.hs_empty[i], 1);
-    }
+    for (int i = 0; i < HS_SLOTS; ++i) { mbar_init(&s.hs_full[i], NUM_H_WARPS); mbar_init(&s.hs_empty[i], 1); }
     mbar_init(&s.y_full, 1);
     mbar_init(&s.y_empty, NUM_LN_WARPS);
     for (int w = 0; w < NUM_LN_WARPS; ++w)
-      for (int i = 0; i < 2; ++i) { mbar_init(&s.res_full[w][i], 1); mbar_init(&s.gn_full[w][i], 1); }
+      for (int i = 0; i < LN_BUFS; ++i) mbar_init(&s.l_full[w][i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -154,18 +174,23 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
     if (lane == 0) {
       int ws = 0;
       uint32_t wph = 0, xph = 0;
-      auto load_w1 = [&](int c) {
-        mbar_wait(&s.w_empty[ws], wph ^ 1);
-        mbar_arrive_expect_tx(&s.w_full[ws], W_STAGE_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < DM / BK; ++kb) tma_load_2d(s.w[ws] + kb * (CH * BK * 2), &p.tma_w1, &s.w_full[ws], kb * BK, c * CH);
-        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+      auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
+      auto load_w1 = [&](int c) {            // four units: the [128 hidden x 64 k] boxes of chunk c
+        for (int kb = 0; kb < DM / BK; ++kb) {
+          mbar_wait(&s.w_empty[ws], wph ^ 1);
+          mbar_arrive_expect_tx(&s.w_full[ws], W_UNIT_BYTES);
+          tma_load_2d(s.w[ws], &p.tma_w1, &s.w_full[ws], kb * BK, c * CH);
+          advance();
+        }
       };
-      auto load_w2 = [&](int c) {
+      auto load_w2 = [&](int j) {            // two adjacent units (ws is even here): the [256 out x 64 k] box of hidden k-block j
         mbar_wait(&s.w_empty[ws], wph ^ 1);
-        mbar_arrive_expect_tx(&s.w_full[ws], W_STAGE_BYTES);
-        tma_load_2d(s.w[ws], &p.tma_w2, &s.w_full[ws], c * CH, 0);
-        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+        mbar_wait(&s.w_empty[ws + 1], wph ^ 1);
+        mbar_arrive_expect_tx(&s.w_full[ws], 2 * W_UNIT_BYTES);
+        mbar_arrive(&s.w_full[ws + 1]);      // the second unit's barrier only keeps its phase in step
+        tma_load_2d(s.w[ws], &p.tma_w2, &s.w_full[ws], j * BK, 0);
+        advance();
+        advance();
       };
       for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
         mbar_wait(&s.x_empty, xph ^ 1);      // the previous tile's last GEMM1 has read x
@@ -176,7 +201,8 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         load_w1(0);
         for (int c = 0; c < NC; ++c) {
           if (c + 1 < NC) load_w1(c + 1);
-          load_w2(c);
+          load_w2(2 * c);
+          load_w2(2 * c + 1);
         }
       }
     }
@@ -185,119 +211,165 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc1 = make_idesc(BM, CH), idesc2 = make_idesc(BM, DM);
       int ws = 0;
-      uint32_t wph = 0, xph = 0, yph = 0;
-      uint32_t hacc_e = 0, hs_f = 0;          // bit b: phase parity of buffer b
+      uint32_t wph = 0, xph = 0, yph = 0, hacc_e = 0;
+      uint32_t jg = 0;                        // hidden k-blocks consumed so far (runs across tiles): hs slot = jg & 1
+      long long t_x = 0, t_w = 0, t_hacc = 0, t_hs = 0, t_y = 0;
+      const long long t_begin = clock64();
+#define PROF_WAIT(acc, ...) do { if (p.prof) { const long long t0_ = clock64(); __VA_ARGS__; acc += clock64() - t0_; } else { __VA_ARGS__; } } while (0)
+      auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
       for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
-        mbar_wait(&s.x_full, xph);
+        PROF_WAIT(t_x, mbar_wait(&s.x_full, xph));
         xph ^= 1;
         tc_fence_after();
         auto g1 = [&](int c) {
-          const int b = c & 1;
-          mbar_wait(&s.hacc_empty[b], ((hacc_e >> b) & 1u) ^ 1u);
-          hacc_e ^= 1u << b;
-          mbar_wait(&s.w_full[ws], wph);
+          PROF_WAIT(t_hacc, mbar_wait(&s.hacc_empty, hacc_e ^ 1u));   // the H warps have read the previous chunk out of hacc
+          hacc_e ^= 1u;
           tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(HACC_COL + b * CH);
+          const uint32_t d = tmem_base + (uint32_t)HACC_COL;
 #pragma unroll
           for (int kb = 0; kb < DM / BK; ++kb) {
+            PROF_WAIT(t_w, mbar_wait(&s.w_full[ws], wph));
+            tc_fence_after();
             const uint64_t da = make_smem_desc(smem_u32(s.x[kb]));
-            const uint64_t db = make_smem_desc(smem_u32(s.w[ws] + kb * (CH * BK * 2)));
+            const uint64_t db = make_smem_desc(smem_u32(s.w[ws]));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&s.w_empty[ws]);
+            advance();
           }
-          umma_commit(&s.w_empty[ws]);
-          umma_commit(&s.hacc_full[b]);
+          umma_commit(&s.hacc_full);
           if (c == NC - 1) umma_commit(&s.x_empty);
-          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
         };
-        auto g2 = [&](int c) {
-          const int b = c & 1;
-          mbar_wait(&s.hs_full[b], (hs_f >> b) & 1u);
-          hs_f ^= 1u << b;
-          if (c == 0) {                        // the LN warps have taken the previous tile's row sums out of y
-            mbar_wait(&s.y_empty, yph ^ 1);
+        auto g2 = [&](int j) {                 // hidden k-block j of this tile: y += h[:, 64 j .. +64] @ W2[:, 64 j .. +64]^T
+          const uint32_t slot = jg & 1u;
+          PROF_WAIT(t_hs, mbar_wait(&s.hs_full[slot], (jg >> 1) & 1u));
+          ++jg;
+          if (j == 0) {                        // the LN warps have taken the previous tile's row out of y
+            PROF_WAIT(t_y, mbar_wait(&s.y_empty, yph ^ 1));
             yph ^= 1;
           }
-          mbar_wait(&s.w_full[ws], wph);
+          PROF_WAIT(t_w, mbar_wait(&s.w_full[ws], wph));
+          PROF_WAIT(t_w, mbar_wait(&s.w_full[ws + 1], wph));
           tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(s.hs[b]));
+          const uint64_t da = make_smem_desc(smem_u32(s.hs[slot]));
           const uint64_t db = make_smem_desc(smem_u32(s.w[ws]));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(tmem_base + Y_COL, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (c | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base + (uint32_t)Y_COL, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
           umma_commit(&s.w_empty[ws]);
-          umma_commit(&s.hs_empty[b]);
-          if (c == NC - 1) umma_commit(&s.y_full);
-          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+          umma_commit(&s.w_empty[ws + 1]);
+          umma_commit(&s.hs_empty[slot]);
+          if (j == 2 * NC - 1) umma_commit(&s.y_full);
+          advance();
+          advance();
         };
+        // G1(c+1) is queued before G2(c): while chunk c is converted (TMEM -> registers -> shared memory) the tensor pipe
+        // has G2(c-1) and G1(c+1) to run
         g1(0);
         for (int c = 0; c < NC; ++c) {
           if (c + 1 < NC) g1(c + 1);
-          g2(c);
+          g2(2 * c);
+          g2(2 * c + 1);
         }
       }
+      if (p.prof) {
+        long long* o = p.prof + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - t_begin; o[1] = t_x; o[2] = t_w; o[3] = t_hacc; o[4] = t_hs; o[5] = t_y;
+      }
+#undef PROF_WAIT
     }
   } else if (warp < LN_WARP0) {
     // ===================== H warps: relu(linear1) chunk -> bf16 A operand in shared memory =====================
+    // warp q: rows [32 q, +32) of the chunk's 128 accumulator columns = two k-blocks; per k-block one full 128-byte swizzled
+    // row per lane of the [128 x 64] tile
     const int q = warp & 3;                                 // TMEM lane quarter
-    const int hh = (warp - H_WARP0) >> 2;                   // which 32 of the chunk's 64 columns
     const int row = q * 32 + lane;
-    uint32_t hacc_f = 0, hs_e = 0;
+    uint32_t hacc_f = 0;
+    uint32_t cg = 0;                                        // chunks converted so far (runs across tiles)
     const uint32_t my_row = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t t_h = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)HACC_COL;
     for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
-      for (int c = 0; c < NC; ++c) {
-        const int b = c & 1;
-        mbar_wait(&s.hacc_full[b], (hacc_f >> b) & 1u);
-        hacc_f ^= 1u << b;
+      for (int c = 0; c < NC; ++c, ++cg) {
+        // the chunk's linear1 bias (the same for every lane: L1 broadcast); the first quarter before the wait, so that its
+        // latency is not part of the conversion's critical path
+        const float4* b1v = reinterpret_cast<const float4*>(p.b1 + c * CH);
+        float4 bias[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bias[j] = __ldg(b1v + j);
+        mbar_wait(&s.hacc_full, hacc_f);
+        hacc_f ^= 1u;
         tc_fence_after();
-        uint32_t r[32];
-        TMEM_LD_X32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(HACC_COL + b * CH + hh * 32), r);
-        TMEM_WAIT_X32(r);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.hacc_empty[b]);
-        const float4* b1v = reinterpret_cast<const float4*>(p.b1 + c * CH + hh * 32);
-        uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = __ldg(b1v + j);
-          o[2 * j] = pack_relu_bf16x2(__uint_as_float(r[4 * j]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y);
-          o[2 * j + 1] = pack_relu_bf16x2(__uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
+        for (int kk = 0; kk < 2; ++kk) {       // hidden k-block kk of the chunk: accumulator columns [64 kk, +64)
+          uint32_t ra[32], rb[32];
+          TMEM_LD_X32(t_h + kk * 64, ra);
+          TMEM_LD_X32(t_h + kk * 64 + 32, rb);
+          TMEM_WAIT_X32(ra);
+          TMEM_WAIT_X32(rb);
+          if (kk == 1) {                       // hacc has been read completely: GEMM1 of the next chunk may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.hacc_empty);
+          }
+          uint32_t o[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = kk == 0 ? bias[j] : __ldg(b1v + 16 + j);
+            o[2 * j] = pack_relu_bf16x2(__uint_as_float(ra[4 * j]) + bb.x, __uint_as_float(ra[4 * j + 1]) + bb.y);
+            o[2 * j + 1] = pack_relu_bf16x2(__uint_as_float(ra[4 * j + 2]) + bb.z, __uint_as_float(ra[4 * j + 3]) + bb.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b1v + kk * 16 + 8 + j);
+            o[16 + 2 * j] = pack_relu_bf16x2(__uint_as_float(rb[4 * j]) + bb.x, __uint_as_float(rb[4 * j + 1]) + bb.y);
+            o[16 + 2 * j + 1] = pack_relu_bf16x2(__uint_as_float(rb[4 * j + 2]) + bb.z, __uint_as_float(rb[4 * j + 3]) + bb.w);
+          }
+          // slot kk has been used cg times before: the GEMM2 of its previous use (k-block kk of chunk cg - 1) is done
+          mbar_wait(&s.hs_empty[kk], (cg & 1u) ^ 1u);
+          const uint32_t dst = smem_u32(s.hs[kk]) + my_row;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)          // 16-byte piece j of the row's 128 bytes, at its SWIZZLE_128B position
+            sts128(dst + ((((uint32_t)j) ^ swz) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.hs_full[kk]);
         }
-        mbar_wait(&s.hs_empty[b], ((hs_e >> b) & 1u) ^ 1u);  // GEMM2(c - 2) has read this buffer
-        hs_e ^= 1u << b;
-        const uint32_t dst = smem_u32(s.hs[b]) + my_row;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)            // 16-byte piece hh*4 + j of the row's 128 bytes, SWIZZLE_128B position
-          sts128(dst + ((((uint32_t)(hh * 4 + j)) ^ swz) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.hs_full[b]);
       }
     }
   } else {
     // ===================== LN warps: bias + residual + LayerNorm (+ conv branch) =====================
+    // Two warps per TMEM lane quarter, 128 columns each; the two partial row sums meet in shared memory (named barrier per
+    // quarter).  Streams (residual in pass 1; conv + skip in and the output out in pass 3) move in 16-column chunks — boxes
+    // of 32 rows x 32 bytes, SWIZZLE_32B, one row per lane — through the warp's ring of four 1 KB buffers.
     const int lw = warp - LN_WARP0;
     const int q = warp & 3;
-    const uint32_t buf0 = smem_u32(s.buf[lw][0]);
-    const uint32_t buf2_0 = smem_u32(s.buf2[lw][0]);
-    uint64_t* rbar = s.res_full[lw];
-    uint64_t* gbar = s.gn_full[lw];
-    uint32_t rphase = 0u, gphase = 0u, yph = 0u;
-    const uint32_t my_row = (uint32_t)lane * 64u;
-    const uint32_t swz = (uint32_t)((lane >> 1) & 3);
-    auto load_res = [&](int m, int c) {     // lane 0 only
-      mbar_arrive_expect_tx(&rbar[c & 1], BUF_BYTES);
-      tma_load_2d(s.buf[lw][c & 1], &p.tma_res, &rbar[c & 1], c * CHUNK, m * BM + q * 32);
+    const int half = lw >> 2;
+    const int col0 = half * LN_COLS;
+    const uint32_t lb0 = smem_u32(s.lbuf[lw][0]);
+    uint64_t* lbar = s.l_full[lw];
+    uint32_t lphase = 0u;                    // bit i: phase parity of buffer i
+    uint32_t yph = 0u;
+    const uint32_t my_row = (uint32_t)lane * 32u;
+    const uint32_t swz = (uint32_t)((lane >> 2) & 1);
+    auto load_res = [&](int m, int c) {     // lane 0 only: residual chunk c -> buffer c % 4
+      const int i = c & (LN_BUFS - 1);
+      mbar_arrive_expect_tx(&lbar[i], LBUF_BYTES);
+      tma_load_2d(s.lbuf[lw][i], &p.tma_res, &lbar[i], col0 + c * LCH, m * BM + q * 32);
     };
-    auto load_gn = [&](int m, int c) {      // lane 0 only
-      mbar_arrive_expect_tx(&gbar[c & 1], 2 * BUF_BYTES);
-      tma_load_2d(s.buf[lw][c & 1], &p.tma_conv, &gbar[c & 1], c * CHUNK, m * BM + q * 32);
-      tma_load_2d(s.buf2[lw][c & 1], &p.tma_skip, &gbar[c & 1], c * CHUNK, m * BM + q * 32);
+    auto load_gn = [&](int m, int c) {      // lane 0 only: conv chunk c -> buffer 2 (c % 2), skip chunk c -> the next one
+      const int i = 2 * (c & 1);
+      mbar_arrive_expect_tx(&lbar[i], 2 * LBUF_BYTES);
+      tma_load_2d(s.lbuf[lw][i], &p.tma_conv, &lbar[i], col0 + c * LCH, m * BM + q * 32);
+      tma_load_2d(s.lbuf[lw][i + 1], &p.tma_skip, &lbar[i], col0 + c * LCH, m * BM + q * 32);
     };
-    if (lane == 0 && (int)blockIdx.x < p.tiles_m) { load_res(blockIdx.x, 0); load_res(blockIdx.x, 1); }
+    auto wait_buf = [&](int i) {
+      mbar_wait(&lbar[i], (lphase >> i) & 1u);
+      lphase ^= 1u << i;
+    };
+    if (lane == 0 && (int)blockIdx.x < p.tiles_m)
+      for (int c = 0; c < LN_BUFS; ++c) load_res(blockIdx.x, c);
 
     for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
       const int row = q * 32 + lane;
@@ -305,26 +377,26 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       mbar_wait(&s.y_full, yph);
       yph ^= 1;
       tc_fence_after();
-      const uint32_t t_y = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Y_COL;
-      const uint32_t t_xp = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)XP_COL;
+      const uint32_t t_y = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Y_COL + col0);
+      const uint32_t t_xp = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(XP_COL + col0 / 2);
 
       // ---- pass 1: x = bf16(acc + bias + residual) parked in TMEM as packed pairs; row sum of the rounded values --------
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        uint32_t r[32];
-        TMEM_LD_X32(t_y + c * CHUNK, r);
-        mbar_wait(&rbar[c & 1], (rphase >> (c & 1)) & 1u);
-        rphase ^= 1u << (c & 1);
-        const uint32_t rb = buf0 + (uint32_t)(c & 1) * BUF_BYTES + my_row;
-        uint4 rv[4];
+      for (int c = 0; c < LCHUNKS; ++c) {
+        uint32_t r[16];
+        TMEM_LD_X16(t_y + c * LCH, r);
+        const int bi = c & (LN_BUFS - 1);
+        wait_buf(bi);
+        const uint32_t rb = lb0 + (uint32_t)bi * LBUF_BYTES + my_row;
+        uint4 rv[2];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) rv[h] = lds128(rb + ((((uint32_t)h) ^ swz) << 4));
-        TMEM_WAIT_X32(r);
-        uint32_t o[16];
-        const float4* b2v = reinterpret_cast<const float4*>(p.b2 + c * CHUNK);
+        for (int h = 0; h < 2; ++h) rv[h] = lds128(rb + ((((uint32_t)h) ^ swz) << 4));
+        TMEM_WAIT_X16(r);
+        uint32_t o[8];
+        const float4* b2v = reinterpret_cast<const float4*>(p.b2 + col0 + c * LCH);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+        for (int h = 0; h < 2; ++h) {
           const uint32_t w[4] = {rv[h].x, rv[h].y, rv[h].z, rv[h].w};
           const float4 ba = __ldg(b2v + 2 * h), bb = __ldg(b2v + 2 * h + 1);
           const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
@@ -338,24 +410,34 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
             sum += bf16_lo(pk) + bf16_hi(pk);
           }
         }
-        TMEM_ST_X16(t_xp + c * (CHUNK / 2), o);
-        __syncwarp();                       // every lane has read this buffer: refill it with the chunk after next
-        if (lane == 0 && c + 2 < CHUNKS) load_res(m, c + 2);
+        TMEM_ST_X8(t_xp + c * (LCH / 2), o);
+        __syncwarp();                       // every lane has read this buffer: refill it with the chunk 4 further on
+        if (lane == 0 && c + LN_BUFS < LCHUNKS) load_res(m, c + LN_BUFS);
       }
-      // y has been read completely: the next tile's GEMM2 may overwrite it
+      // this warp's half of y has been read completely: when all eight have, the next tile's GEMM2 may overwrite it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.y_empty);
-      if (GN && lane == 0) { load_gn(m, 0); load_gn(m, 1); }
-      const float mean = sum * (1.f / DM);
+      if (lane == 0) {
+        mbar_arrive(&s.y_empty);
+        if (GN && !(p.debug & 1)) { load_gn(m, 0); load_gn(m, 1); }     // every buffer is free: two (conv, skip) pairs
+      }
+      if (p.debug & 1) {
+        __syncwarp();
+        const int mn = m + gridDim.x;
+        if (lane == 0 && mn < p.tiles_m) for (int c = 0; c < LN_BUFS; ++c) load_res(mn, c);
+        continue;
+      }
+      s.xch[0][half][row] = sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      const float mean = (s.xch[0][0][row] + s.xch[0][1][row]) * (1.f / DM);
       tmem_wait_st();
 
       // ---- pass 2: centred second moment of the parked row --------------------------------------------------
       float sq = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; c += 2) {
+      for (int c = 0; c < LN_COLS / 2; c += 32) {
         uint32_t r[32];
-        TMEM_LD_X32(t_xp + c * (CHUNK / 2), r);
+        TMEM_LD_X32(t_xp + c, r);
         TMEM_WAIT_X32(r);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -364,7 +446,9 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
           sq = fmaf(d1, d1, sq);
         }
       }
-      const float rstd = rsqrtf(sq * (1.f / DM) + p.eps);
+      s.xch[1][half][row] = sq;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      const float rstd = rsqrtf((s.xch[1][0][row] + s.xch[1][1][row]) * (1.f / DM) + p.eps);
 
       // ---- pass 3: normalise (+ conv branch), round, stage, TMA store ------------------------------------------
       int gl = 0;
@@ -380,36 +464,43 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         ginv = 1.f / (float)(p.lv.H[gl] * p.lv.W[gl] * (DM / GN_GROUPS));
       }
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        uint32_t r[16];
-        TMEM_LD_X16(t_xp + c * (CHUNK / 2), r);
-        if (!GN && c >= 2) {                // the store of chunk c - 2 has drained this buffer
-          if (lane == 0) tma_store_wait_read_1();
+      for (int c = 0; c < LCHUNKS; ++c) {
+        uint32_t r[8];
+        TMEM_LD_X8(t_xp + c * (LCH / 2), r);
+        // GN: conv in buffer 2 (c % 2), skip in the next one, output staged over conv.  Plain: output staged in buffer c % 4.
+        const int bi = GN ? 2 * (c & 1) : (c & (LN_BUFS - 1));
+        // the other pair held chunk c - 1, whose store was issued at the end of the previous step: as soon as that store has
+        // read its buffer, chunk c + 1 is requested there — a whole step ahead of its use
+        if (GN && lane == 0 && c >= 1 && c + 1 < LCHUNKS) {
+          tma_store_wait_read();
+          load_gn(m, c + 1);
+        }
+        if (!GN && c >= LN_BUFS) {          // the store of chunk c - 4 has drained this buffer
+          if (lane == 0) tma_store_wait_read_n<LN_BUFS - 1>();
           __syncwarp();
         }
-        const uint32_t sb = buf0 + (uint32_t)(c & 1) * BUF_BYTES + my_row;
-        uint4 cv[4] = {}, sk[4] = {};
+        const uint32_t sb = lb0 + (uint32_t)bi * LBUF_BYTES + my_row;
+        uint4 cv[2] = {}, sk[2] = {};
         if (GN) {
-          mbar_wait(&gbar[c & 1], (gphase >> (c & 1)) & 1u);
-          gphase ^= 1u << (c & 1);
-          const uint32_t kb2 = buf2_0 + (uint32_t)(c & 1) * BUF_BYTES + my_row;
+          wait_buf(bi);
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < 2; ++h) {
             cv[h] = lds128(sb + ((((uint32_t)h) ^ swz) << 4));
-            sk[h] = lds128(kb2 + ((((uint32_t)h) ^ swz) << 4));
+            sk[h] = lds128(sb + LBUF_BYTES + ((((uint32_t)h) ^ swz) << 4));
           }
         }
-        TMEM_WAIT_X16(r);
-        const float4* gav = reinterpret_cast<const float4*>(p.gamma + c * CHUNK);
-        const float4* bev = reinterpret_cast<const float4*>(p.beta + c * CHUNK);
-        const float4* ggv = reinterpret_cast<const float4*>(p.gn_gamma + (GN ? gl * DM : 0) + c * CHUNK);
-        const float4* gbv = reinterpret_cast<const float4*>(p.gn_beta + (GN ? gl * DM : 0) + c * CHUNK);
+        TMEM_WAIT_X8(r);
+        const int cc = col0 + c * LCH;
+        const float4* gav = reinterpret_cast<const float4*>(p.gamma + cc);
+        const float4* bev = reinterpret_cast<const float4*>(p.beta + cc);
+        const float4* ggv = reinterpret_cast<const float4*>(p.gn_gamma + (GN ? gl * DM : 0) + cc);
+        const float4* gbv = reinterpret_cast<const float4*>(p.gn_beta + (GN ? gl * DM : 0) + cc);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+        for (int h = 0; h < 2; ++h) {
           uint32_t o[4];
           float gmean = 0.f, grstd = 0.f;
           if (GN) {
-            const float2 st2 = __ldg(reinterpret_cast<const float2*>(gst) + ((c * CHUNK) >> 3) + h);
+            const float2 st2 = __ldg(reinterpret_cast<const float2*>(gst) + (cc >> 3) + h);
             gmean = st2.x * ginv;
             grstd = rsqrtf(fmaxf(st2.y * ginv - gmean * gmean, 0.f) + p.gn_eps);
           }
@@ -439,22 +530,16 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&p.tma_y, buf0 + (uint32_t)(c & 1) * BUF_BYTES, c * CHUNK, row0);
+          tma_store_2d(&p.tma_y, lb0 + (uint32_t)bi * LBUF_BYTES, cc, row0);
           tma_store_commit();
-          if (GN && c + 2 < CHUNKS) {       // chunk c + 2 goes into the buffers of chunk c: wait until the store has read them
-            tma_store_wait_read();
-            load_gn(m, c + 2);
-          }
         }
       }
       __syncwarp();
       if (lane == 0) {
-        const int mn = m + gridDim.x;       // the next tile's first two residual chunks, as soon as the stores have drained
+        const int mn = m + gridDim.x;       // the next tile's first four residual chunks, as soon as the stores have drained
         if (mn < p.tiles_m) {
-          tma_store_wait_read_1();
-          load_res(mn, 0);
           tma_store_wait_read();
-          load_res(mn, 1);
+          for (int c = 0; c < LN_BUFS; ++c) load_res(mn, c);
         }
       }
     }
@@ -471,11 +556,30 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
 
 template <bool GN>
 int launch_ffn(FfnParams& p, cudaStream_t st) {
-  constexpr int smem_bytes = (int)sizeof(FfnSmem) + 1024;
-  static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
+  // the struct plus whatever alignment slack the 227 KB limit leaves (the kernel checks that it fits behind its 1024-byte
+  // alignment: the dynamic window of a kernel without static shared memory starts aligned)
+  constexpr int smem_bytes = (int)sizeof(FfnSmem) + 1024 <= 232448 ? (int)sizeof(FfnSmem) + 1024 : 232448;
+  static_assert(sizeof(FfnSmem) <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
   auto kern = ffn_fused_tcgen05_kernel<GN>;
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int grid = p.tiles_m < num_sms() ? p.tiles_m : num_sms();
+  if (getenv("EMRT_FFN_PROF")) {          // diagnosis only: where the MMA thread waits (synchronous, prints to stderr)
+    long long* d = nullptr;
+    EMRT_CUDA_CHECK(cudaMalloc(&d, (size_t)grid * 8 * sizeof(long long)));
+    EMRT_CUDA_CHECK(cudaMemset(d, 0, (size_t)grid * 8 * sizeof(long long)));
+    p.prof = d;
+    kern<<<grid, NUM_THREADS, smem_bytes, st>>>(p);
+    EMRT_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<long long> h((size_t)grid * 8);
+    EMRT_CUDA_CHECK(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < grid; ++i) for (int k = 0; k < 6; ++k) a[k] += (double)h[(size_t)i * 8 + k] / grid;
+    fprintf(stderr, "ffn_fused MMA thread, cycles per CTA (avg of %d): total %.0f | wait x %.0f, weights %.0f, hacc_empty %.0f, hs_full %.0f, y_empty %.0f | tiles/CTA %.1f\n",
+            grid, a[0], a[1], a[2], a[3], a[4], a[5], (double)p.tiles_m / grid);
+    count_launch();
+    return EMRT_OK;
+  }
   kern<<<grid, NUM_THREADS, smem_bytes, st>>>(p);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
@@ -491,7 +595,7 @@ extern "C" int emrt_ffn_fused_fwd(const emrt_ffn_args* a, void* stream) {
   EMRT_REQUIRE(a->x && a->w1 && a->w2 && a->y && a->b1 && a->b2 && a->ln_gamma && a->ln_beta, "NULL pointer in emrt_ffn_args");
   EMRT_REQUIRE(a->rows > 0 && a->rows < (1LL << 31), "rows out of range");
   if (a->d_model != DM) return set_error(EMRT_ERR_UNSUPPORTED, "fused FFN is built for d_model = 256 (one accumulator row), got %d", a->d_model);
-  if (a->d_ff < CH || a->d_ff % CH != 0) return set_error(EMRT_ERR_UNSUPPORTED, "fused FFN needs d_ff %% 64 == 0, got %d", a->d_ff);
+  if (a->d_ff < CH || a->d_ff % CH != 0) return set_error(EMRT_ERR_UNSUPPORTED, "fused FFN needs d_ff %% 128 == 0, got %d", a->d_ff);
   if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w1) | reinterpret_cast<uintptr_t>(a->w2) |
        reinterpret_cast<uintptr_t>(a->y) | reinterpret_cast<uintptr_t>(a->b1) | reinterpret_cast<uintptr_t>(a->b2) |
        reinterpret_cast<uintptr_t>(a->ln_gamma) | reinterpret_cast<uintptr_t>(a->ln_beta)) & 15)
@@ -503,17 +607,18 @@ extern "C" int emrt_ffn_fused_fwd(const emrt_ffn_args* a, void* stream) {
   p.b1 = a->b1; p.b2 = a->b2; p.gamma = a->ln_gamma; p.beta = a->ln_beta; p.eps = a->ln_eps;
   p.tiles_m = (int)((a->rows + BM - 1) / BM);
   p.num_chunks = a->d_ff / CH;
+  { const char* e = getenv("EMRT_FFN_DEBUG"); p.debug = e ? atoi(e) : 0; }
   {
     const uint64_t d[2] = {(uint64_t)DM, (uint64_t)a->rows}, sb[1] = {(uint64_t)DM * 2};
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
     if (int e = make_tensor_map(&p.tma_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->x, d, sb, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-    const uint32_t box2[2] = {(uint32_t)CHUNK, 32u};
-    if (int e = make_tensor_map(&p.tma_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->x, d, sb, box2, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
-    if (int e = make_tensor_map(&p.tma_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->y, d, sb, box2, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    const uint32_t box2[2] = {(uint32_t)LCH, 32u};
+    if (int e = make_tensor_map(&p.tma_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->x, d, sb, box2, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
+    if (int e = make_tensor_map(&p.tma_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->y, d, sb, box2, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
   }
   {
     const uint64_t d[2] = {(uint64_t)DM, (uint64_t)a->d_ff}, sb[1] = {(uint64_t)DM * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)CH};
+    const uint32_t box[2] = {(uint32_t)BK, 128u};
     if (int e = make_tensor_map(&p.tma_w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->w1, d, sb, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
   {
@@ -534,9 +639,9 @@ extern "C" int emrt_ffn_fused_fwd(const emrt_ffn_args* a, void* stream) {
     p.gn_stats = g->stats; p.gn_gamma = g->gamma; p.gn_beta = g->beta; p.gn_eps = g->eps;
     p.L = g->L; p.Lv = g->Lv; p.B = (int)(a->rows / g->Lv);
     const uint64_t d[2] = {(uint64_t)DM, (uint64_t)a->rows}, sb[1] = {(uint64_t)DM * 2};
-    const uint32_t box[2] = {(uint32_t)CHUNK, 32u};
-    if (int e = make_tensor_map(&p.tma_conv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->conv, d, sb, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
-    if (int e = make_tensor_map(&p.tma_skip, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->skip, d, sb, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    const uint32_t box[2] = {(uint32_t)LCH, 32u};
+    if (int e = make_tensor_map(&p.tma_conv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->conv, d, sb, box, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
+    if (int e = make_tensor_map(&p.tma_skip, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->skip, d, sb, box, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
     return launch_ffn<true>(p, st);
   }
   p.gn_gamma = a->ln_gamma; p.gn_beta = a->ln_beta;     // never read; keeps the pointer arithmetic defined

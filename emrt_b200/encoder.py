@@ -59,6 +59,7 @@ class TransformerEncoderLayer(nn.Module):
         nn.init.xavier_uniform_(self.linear2.weight)
         self.gemm_impl = L.IMPL_AUTO
         self.fuse_ffn2_norm2 = True          # tests may switch the fused linear2 + norm2 + conv-branch epilogue off
+        self.fuse_ffn = True                 # ... and the whole-FFN kernel (falls back to linear1 -> fused linear2 epilogue)
         self._packed = None
 
     def _version(self):
@@ -140,6 +141,12 @@ class TransformerEncoderLayer(nn.Module):
         x = self.self_attn(src, reference_points, src, shapes, src_mask, query_pos=pos_embed,
                            residual_norm=(src, pk["n1w"], pk["n1b"]))
         # ffn (:157-160) + the layer's final add of the conv branch (:203)
+        if fast and impl != L.IMPL_SIMT and self.fuse_ffn and self.d_model == 256 and pk["w1"].shape[0] % 128 == 0:
+            # linear1 + ReLU + linear2 + residual + norm2 + the conv branch + the layer's final add in ONE kernel: the hidden
+            # activations never leave the SM (emrt_ffn_fused_fwd; :157-160,187-189,203)
+            return ops.ffn_fused(x, pk["w1"], pk["b1"], pk["w2"], pk["b2"], pk["n2w"], pk["n2b"],
+                                 gn_branch=dict(conv=conv, skip=src, stats=gn_stats, gamma=pk["gn_w"], beta=pk["gn_b"],
+                                                shapes=shapes, groups=32, eps=1e-5))
         if fast:
             h = ops.linear(x, pk["w1"], pk["b1"], w_transposed=True, epilogue=L.EPI_RELU, impl=impl)
             if impl != L.IMPL_SIMT and self.d_model == 256 and self.fuse_ffn2_norm2:

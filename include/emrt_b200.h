@@ -161,11 +161,11 @@ int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 
 /* ---- TransformerEncoderLayer.forward_ffn in one kernel (transformer_encoder_decoder.py:157-160, + :187-189,203) ------
  * y = LayerNorm(x + linear2(relu(linear1(x)))) * ln_gamma + ln_beta  (+ GELU(GroupNorm_l(conv)) + skip when gn != NULL).
- * The hidden activations [rows, d_ff] never reach HBM: each CTA walks d_ff in 64-unit chunks, the first GEMM's
+ * The hidden activations [rows, d_ff] never reach HBM: each CTA walks d_ff in 128-unit chunks, the first GEMM's
  * accumulator chunk is converted (bias, ReLU, bf16) into the shared-memory A operand of the second, whose accumulator
  * (one 256-column TMEM row per token) feeds the LayerNorm epilogue.  BF16 / tcgen05 only: x, y BF16 [rows, 256];
  * w1 BF16 [d_ff, 256] and w2 BF16 [256, d_ff] pre-packed (emrt_pack_weight); b1 F32 [d_ff], b2 / ln_gamma / ln_beta F32
- * [256]; d_model = 256, d_ff % 64 == 0; every pointer 16-byte aligned.  y must not alias x (x is re-read as the
+ * [256]; d_model = 256, d_ff % 128 == 0; every pointer 16-byte aligned.  y must not alias x (x is re-read as the
  * residual while other tiles are being written).                                                                    */
 typedef struct emrt_ffn_args {
   const void* x; const void* w1; const float* b1; const void* w2; const float* b2;

@@ -476,10 +476,12 @@ def encoder_layer_forward(p, prefix, src, ref, shapes, mask, pos):
     else:
         src2 = msda_forward(_sub(p, prefix + "self_attn."), src + pos, ref, src, shapes, mask, dtype=src.dtype)  # :198
     src = _store(_ln(src + src2, p[prefix + "norm1.weight"], p[prefix + "norm1.bias"]))    # :199-200
-    # (linear2's output is not a store: norm2 and the final add run in its epilogue on the fp32 accumulator)
+    # (the fused FFN kernel, emrt_ffn_fused_fwd: the hidden activations are rounded to bf16 on their way from the first
+    # GEMM's accumulator to the second GEMM's operand — they never reach HBM, but the operand format is bf16 — and
+    # x + linear2(...) is rounded to bf16 once when it is parked for the LayerNorm; norm2 and the final add follow in fp32)
     ffn = _store(F.relu(src @ p[prefix + "linear1.weight"] + p[prefix + "linear1.bias"])) @ p[prefix + "linear2.weight"] \
         + p[prefix + "linear2.bias"]                                                        # :157-158
-    src = _ln(src + ffn, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])             # :159-160
+    src = _ln(_store(src + ffn), p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])     # :159-160
     return _store(src + src_flatten)                                                        # :203
 
 

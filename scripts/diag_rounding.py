@@ -151,6 +151,13 @@ def run(tile=256):
                                  p64[pre + "norm2.bias"]) + torch.cat(br, 1)).bfloat16()
         print(f"  linear2 + residual + LN2 + GroupNorm + GELU + skip (fused): own {rec('FFN linear2 + residual + LN2 + conv branch (fused)', l2(yf.float(), yfo)):.2e}")
         print(f"  LN2 + GroupNorm + GELU + skip: own {rec("LN2 + GroupNorm + GELU + skip", l2(y.float(), yo)):.2e}")
+        # the whole FFN in one kernel (emrt_ffn_fused_fwd): hidden chunk rounded to bf16 on chip, x + linear2 parked as bf16
+        yff = ops.ffn_fused(x1o.bfloat16().to(dev), pk["w1"], pk["b1"], pk["w2"], pk["b2"], pk["n2w"], pk["n2b"],
+                            gn_branch=dict(conv=torch.cat(outs, 1).bfloat16().to(dev), skip=src.to(dev), stats=gn, gamma=pk["gn_w"],
+                                           beta=pk["gn_b"], shapes=shapes))
+        pre_ln = (x1o + ho.double() @ p64[pre + "linear2.weight"] + p64[pre + "linear2.bias"]).bfloat16().double()
+        yffo = (O.emrt_oracle._ln(pre_ln, p64[pre + "norm2.weight"], p64[pre + "norm2.bias"]) + torch.cat(br, 1)).bfloat16()
+        print(f"  whole FFN + LN2 + conv branch in one kernel: own {rec('FFN (linear1 + ReLU + linear2) + residual + LN2 + conv branch (one kernel)', l2(yff.float(), yffo)):.2e}")
 
     # 3. decoder layer, stage by stage on the oracle's operands
     print("decoder layer")

@@ -78,9 +78,9 @@ def reference(case):
 
 @pytest.mark.parametrize("B,shapes,d_ff,gn", [
     (3, [(16, 16), (8, 8), (4, 4)], 1024, True),       # 1008 rows: 7 full tiles + a partial one
-    (2, [(16, 16), (8, 8), (4, 4)], 128, True),        # two hidden chunks
-    (1, [(8, 8), (4, 4), (2, 2)], 64, False),          # one chunk, less than a tile, plain LayerNorm
-    (5, [(8, 16), (4, 8), (2, 4)], 1024, False),
+    (2, [(16, 16), (8, 8), (4, 4)], 256, True),        # two hidden chunks
+    (1, [(8, 8), (4, 4), (2, 2)], 128, False),         # one chunk, less than a tile, plain LayerNorm
+    (5, [(8, 16), (4, 8), (2, 4)], 384, False),         # three chunks: the hidden k-block ring (3 slots) wraps differently per tile
     (60, [(16, 16), (8, 8), (4, 4)], 1024, True),      # 20160 rows: more tiles than SMs (two tiles on some CTAs)
 ])
 def test_ffn_fused_matches_float64_and_two_kernel_form(cuda_dev, B, shapes, d_ff, gn):
