@@ -46,8 +46,12 @@ constexpr int BM = 128, BK = 64, DM = 256, CH = 128, UMMA_K = 16;
 constexpr int H_WARP0 = 2, NUM_H_WARPS = 4, LN_WARP0 = 6, NUM_LN_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (LN_WARP0 + NUM_LN_WARPS);
 constexpr int TMEM_COLS = 512, Y_COL = 0, HACC_COL = 256, XP_COL = 384;
-constexpr int W_UNITS = 6;                         // weight ring: units of one [128 rows x 64 k] bf16 box; a W2 k-block takes two
-constexpr uint32_t W_UNIT_BYTES = 128 * BK * 2;    // 16 KB
+// weight ring (96 KB): units of one [128 / CG rows x 64 k] bf16 box — a W1 k-block of this CTA's share of the chunk; a W2
+// k-block (this CTA's 256 / CG output rows) takes two adjacent units.  CG = 2: the CTA pair splits every B operand in half.
+template <int CG> struct Ring {
+  static constexpr int UNITS = 6 * CG;
+  static constexpr uint32_t UNIT_BYTES = (128 / CG) * BK * 2;
+};
 constexpr int HS_SLOTS = 2;                        // hidden k-block tiles [128 x 64] between the H warps and GEMM2
 constexpr int LCH = 16;                            // LayerNorm epilogue: columns per step
 constexpr int LN_COLS = DM / 2;                    // columns per LN warp
@@ -80,14 +84,15 @@ struct FfnParams {
   long long* prof;       // EMRT_FFN_PROF: per CTA, cycles the MMA thread spent waiting on each barrier kind
 };
 
+template <int CG>
 struct FfnSmem {
   __nv_bfloat16 x[DM / BK][BM * BK];               // 64 KB: the row tile, A operand of every GEMM1
   __nv_bfloat16 hs[HS_SLOTS][BM * BK];             // 2 x 16 KB: relu(linear1) k-blocks, A operand of GEMM2
-  uint8_t w[W_UNITS][W_UNIT_BYTES];                // 96 KB weight ring
+  uint8_t w[Ring<CG>::UNITS][Ring<CG>::UNIT_BYTES];   // 96 KB weight ring
   uint8_t lbuf[NUM_LN_WARPS][LN_BUFS][LBUF_BYTES]; // per LN warp: ring of 1 KB chunk buffers (residual | conv, skip / output)
   float xch[2][2][BM];                             // [pass][column half][row]: partial row sums of the two LN warps of a row
   uint64_t x_full, x_empty;
-  uint64_t w_full[W_UNITS], w_empty[W_UNITS];
+  uint64_t w_full[Ring<CG>::UNITS], w_empty[Ring<CG>::UNITS];
   uint64_t hacc_full, hacc_empty;
   uint64_t hs_full[HS_SLOTS], hs_empty[HS_SLOTS];
   uint64_t y_full, y_empty;
@@ -119,18 +124,83 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <bool GN>
+// ---- CTA-pair plumbing (CG = 2) ------------------------------------------------------------------------------
+// One thread of the pair's leader (cluster rank 0) issues tcgen05.mma.cta_group::2 for both CTAs: M = 256 (128 rows from each
+// CTA's own A tile), each CTA holding half of the B rows at the same shared-memory offset.  Barriers the issuing thread WAITS
+// on live in the leader: the peer's TMA loads complete their bytes there (.cta_group::2 form of the copy) and the peer's
+// warps arrive there with a cluster-scope arrive.  Barriers the MMAs SIGNAL are committed with multicast to both CTAs, so
+// every other warp only ever waits on its own CTA's copy.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the shared::cluster address of the leader's copy of a barrier (the same address for CG = 1)
+template <int CG> __device__ __forceinline__ uint32_t leader_addr(const void* local) {
+  uint32_t a = smem_u32(local);
+  if (CG == 2) asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a) : "r"(a));
+  return a;
+}
+// the issuing thread's waits: cluster-scope acquire when the arrivals (and the shared-memory writes they publish) come from
+// the peer CTA as well
+template <int CG> __device__ __forceinline__ void wait_lead(uint64_t* bar, uint32_t parity) {
+  if (CG == 2)
+    asm volatile(
+        "{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n"
+        " bra LAB_WAIT;\n DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+  else
+    mbar_wait(bar, parity);
+}
+template <int CG> __device__ __forceinline__ void arrive_leader(uint32_t leader_bar) {
+  if (CG == 2) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_bar) : "memory");
+  else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(leader_bar) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_lead(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  if (CG == 2)
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_cg(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2)
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+template <int CG> __device__ __forceinline__ void commit_cg(uint64_t* bar) {   // arrives on `bar` in every CTA of the pair
+  if (CG == 2)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3) : "memory");
+  else
+    umma_commit(bar);
+}
+
+template <bool GN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
+  using R = Ring<CG>;
+  constexpr int W_UNITS = R::UNITS;
+  constexpr uint32_t W_UNIT_BYTES = R::UNIT_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t align_off = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
-  FfnSmem& s = *reinterpret_cast<FfnSmem*>(smem_raw + align_off);
+  FfnSmem<CG>& s = *reinterpret_cast<FfnSmem<CG>*>(smem_raw + align_off);
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int cluster_id = (int)blockIdx.x / CG, num_clusters = (int)gridDim.x / CG;
+  const int npairs = (p.tiles_m + CG - 1) / CG;       // row tiles are dealt to the pair two at a time: tile CG * mp + rank
   {
     // the launch asks for sizeof(FfnSmem) plus whatever slack the 227 KB limit leaves: fail loudly if the window's base is
     // not aligned well enough for the struct to fit behind the SWIZZLE_128B alignment
     uint32_t dyn;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    if (align_off + (uint32_t)sizeof(FfnSmem) > dyn) {
+    if (align_off + (uint32_t)sizeof(FfnSmem<CG>) > dyn) {
       if (threadIdx.x == 0 && blockIdx.x == 0) printf("ffn_fused: shared window misaligned by %u bytes, %u available\n", align_off, dyn);
       __trap();
     }
@@ -151,53 +221,66 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
 #pragma unroll
     for (int i = 0; i < W_UNITS; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
     mbar_init(&s.hacc_full, 1);
-    mbar_init(&s.hacc_empty, NUM_H_WARPS);
+    mbar_init(&s.hacc_empty, CG * NUM_H_WARPS);        // (the leader's copy collects the arrivals of both CTAs)
 #pragma unroll
-    for (int i = 0; i < HS_SLOTS; ++i) { mbar_init(&s.hs_full[i], NUM_H_WARPS); mbar_init(&s.hs_empty[i], 1); }
+    for (int i = 0; i < HS_SLOTS; ++i) { mbar_init(&s.hs_full[i], CG * NUM_H_WARPS); mbar_init(&s.hs_empty[i], 1); }
     mbar_init(&s.y_full, 1);
-    mbar_init(&s.y_empty, NUM_LN_WARPS);
+    mbar_init(&s.y_empty, CG * NUM_LN_WARPS);
     for (int w = 0; w < NUM_LN_WARPS; ++w)
       for (int i = 0; i < LN_BUFS; ++i) mbar_init(&s.l_full[w][i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // both CTAs' barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
+  const uint32_t L_hacc_empty = leader_addr<CG>(&s.hacc_empty), L_y_empty = leader_addr<CG>(&s.y_empty);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // (both CTAs of a pair run it: each loads its own x tile and its own half of every weight box; the bytes of both are
+    // counted on the leader's barrier, which only the leader arms)
     if (lane == 0) {
       int ws = 0;
       uint32_t wph = 0, xph = 0;
+      const uint32_t L_x_full = leader_addr<CG>(&s.x_full);
       auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
-      auto load_w1 = [&](int c) {            // four units: the [128 hidden x 64 k] boxes of chunk c
+      auto load_w1 = [&](int c) {            // four units: this CTA's [128 / CG hidden x 64 k] boxes of chunk c
         for (int kb = 0; kb < DM / BK; ++kb) {
           mbar_wait(&s.w_empty[ws], wph ^ 1);
-          mbar_arrive_expect_tx(&s.w_full[ws], W_UNIT_BYTES);
-          tma_load_2d(s.w[ws], &p.tma_w1, &s.w_full[ws], kb * BK, c * CH);
+          if (rank == 0) mbar_arrive_expect_tx(&s.w_full[ws], CG * W_UNIT_BYTES);
+          tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH + (int)rank * (CH / CG));
           advance();
         }
       };
-      auto load_w2 = [&](int j) {            // two adjacent units (ws is even here): the [256 out x 64 k] box of hidden k-block j
+      auto load_w2 = [&](int j) {            // two adjacent units (ws is even here): this CTA's [256 / CG out x 64 k] box of k-block j
         mbar_wait(&s.w_empty[ws], wph ^ 1);
         mbar_wait(&s.w_empty[ws + 1], wph ^ 1);
-        mbar_arrive_expect_tx(&s.w_full[ws], 2 * W_UNIT_BYTES);
-        mbar_arrive(&s.w_full[ws + 1]);      // the second unit's barrier only keeps its phase in step
-        tma_load_2d(s.w[ws], &p.tma_w2, &s.w_full[ws], j * BK, 0);
+        if (rank == 0) {
+          mbar_arrive_expect_tx(&s.w_full[ws], CG * 2 * W_UNIT_BYTES);
+          mbar_arrive(&s.w_full[ws + 1]);    // the second unit's barrier only keeps its phase in step
+        }
+        tma_load_2d_lead<CG>(s.w[ws], &p.tma_w2, leader_addr<CG>(&s.w_full[ws]), j * BK, (int)rank * (DM / CG));
         advance();
         advance();
       };
-      for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
+      for (int mp = cluster_id; mp < npairs; mp += num_clusters) {
+        const int m = mp * CG + (int)rank;
         mbar_wait(&s.x_empty, xph ^ 1);      // the previous tile's last GEMM1 has read x
         xph ^= 1;
-        mbar_arrive_expect_tx(&s.x_full, (uint32_t)(BM * DM * 2));
+        if (rank == 0) mbar_arrive_expect_tx(&s.x_full, (uint32_t)(CG * BM * DM * 2));
 #pragma unroll
-        for (int kb = 0; kb < DM / BK; ++kb) tma_load_2d(s.x[kb], &p.tma_x, &s.x_full, kb * BK, m * BM);
+        for (int kb = 0; kb < DM / BK; ++kb) tma_load_2d_lead<CG>(s.x[kb], &p.tma_x, L_x_full, kb * BK, m * BM);
         load_w1(0);
         for (int c = 0; c < NC; ++c) {
           if (c + 1 < NC) load_w1(c + 1);
@@ -208,8 +291,8 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc(BM, CH), idesc2 = make_idesc(BM, DM);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc1 = make_idesc(BM * CG, CH), idesc2 = make_idesc(BM * CG, DM);
       int ws = 0;
       uint32_t wph = 0, xph = 0, yph = 0, hacc_e = 0;
       uint32_t jg = 0;                        // hidden k-blocks consumed so far (runs across tiles): hs slot = jg & 1
@@ -217,50 +300,50 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       const long long t_begin = clock64();
 #define PROF_WAIT(acc, ...) do { if (p.prof) { const long long t0_ = clock64(); __VA_ARGS__; acc += clock64() - t0_; } else { __VA_ARGS__; } } while (0)
       auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
-      for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
-        PROF_WAIT(t_x, mbar_wait(&s.x_full, xph));
+      for (int mp = cluster_id; mp < npairs; mp += num_clusters) {
+        PROF_WAIT(t_x, wait_lead<CG>(&s.x_full, xph));
         xph ^= 1;
         tc_fence_after();
         auto g1 = [&](int c) {
-          PROF_WAIT(t_hacc, mbar_wait(&s.hacc_empty, hacc_e ^ 1u));   // the H warps have read the previous chunk out of hacc
+          PROF_WAIT(t_hacc, wait_lead<CG>(&s.hacc_empty, hacc_e ^ 1u));   // the H warps have read the previous chunk out of hacc
           hacc_e ^= 1u;
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)HACC_COL;
 #pragma unroll
           for (int kb = 0; kb < DM / BK; ++kb) {
-            PROF_WAIT(t_w, mbar_wait(&s.w_full[ws], wph));
+            PROF_WAIT(t_w, wait_lead<CG>(&s.w_full[ws], wph));
             tc_fence_after();
             const uint64_t da = make_smem_desc(smem_u32(s.x[kb]));
             const uint64_t db = make_smem_desc(smem_u32(s.w[ws]));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&s.w_empty[ws]);
+              umma_cg<CG>(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
+            commit_cg<CG>(&s.w_empty[ws]);
             advance();
           }
-          umma_commit(&s.hacc_full);
-          if (c == NC - 1) umma_commit(&s.x_empty);
+          commit_cg<CG>(&s.hacc_full);
+          if (c == NC - 1) commit_cg<CG>(&s.x_empty);
         };
         auto g2 = [&](int j) {                 // hidden k-block j of this tile: y += h[:, 64 j .. +64] @ W2[:, 64 j .. +64]^T
           const uint32_t slot = jg & 1u;
-          PROF_WAIT(t_hs, mbar_wait(&s.hs_full[slot], (jg >> 1) & 1u));
+          PROF_WAIT(t_hs, wait_lead<CG>(&s.hs_full[slot], (jg >> 1) & 1u));
           ++jg;
           if (j == 0) {                        // the LN warps have taken the previous tile's row out of y
-            PROF_WAIT(t_y, mbar_wait(&s.y_empty, yph ^ 1));
+            PROF_WAIT(t_y, wait_lead<CG>(&s.y_empty, yph ^ 1));
             yph ^= 1;
           }
-          PROF_WAIT(t_w, mbar_wait(&s.w_full[ws], wph));
-          PROF_WAIT(t_w, mbar_wait(&s.w_full[ws + 1], wph));
+          PROF_WAIT(t_w, wait_lead<CG>(&s.w_full[ws], wph));
+          PROF_WAIT(t_w, wait_lead<CG>(&s.w_full[ws + 1], wph));
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(s.hs[slot]));
           const uint64_t db = make_smem_desc(smem_u32(s.w[ws]));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(tmem_base + (uint32_t)Y_COL, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
-          umma_commit(&s.w_empty[ws]);
-          umma_commit(&s.w_empty[ws + 1]);
-          umma_commit(&s.hs_empty[slot]);
-          if (j == 2 * NC - 1) umma_commit(&s.y_full);
+            umma_cg<CG>(tmem_base + (uint32_t)Y_COL, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
+          commit_cg<CG>(&s.w_empty[ws]);
+          commit_cg<CG>(&s.w_empty[ws + 1]);
+          commit_cg<CG>(&s.hs_empty[slot]);
+          if (j == 2 * NC - 1) commit_cg<CG>(&s.y_full);
           advance();
           advance();
         };
@@ -290,7 +373,8 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
     const uint32_t my_row = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t t_h = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)HACC_COL;
-    for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
+    const uint32_t L_hs_full[2] = {leader_addr<CG>(&s.hs_full[0]), leader_addr<CG>(&s.hs_full[1])};
+    for (int mp = cluster_id; mp < npairs; mp += num_clusters) {
       for (int c = 0; c < NC; ++c, ++cg) {
         // the chunk's linear1 bias (the same for every lane: L1 broadcast); the first quarter before the wait, so that its
         // latency is not part of the conversion's critical path
@@ -311,7 +395,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
           if (kk == 1) {                       // hacc has been read completely: GEMM1 of the next chunk may overwrite it
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s.hacc_empty);
+            if (lane == 0) arrive_leader<CG>(L_hacc_empty);
           }
           uint32_t o[32];
 #pragma unroll
@@ -334,7 +418,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
             sts128(dst + ((((uint32_t)j) ^ swz) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s.hs_full[kk]);
+          if (lane == 0) arrive_leader<CG>(L_hs_full[kk]);
         }
       }
     }
@@ -368,10 +452,11 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       mbar_wait(&lbar[i], (lphase >> i) & 1u);
       lphase ^= 1u << i;
     };
-    if (lane == 0 && (int)blockIdx.x < p.tiles_m)
-      for (int c = 0; c < LN_BUFS; ++c) load_res(blockIdx.x, c);
+    if (lane == 0 && cluster_id < npairs)
+      for (int c = 0; c < LN_BUFS; ++c) load_res(cluster_id * CG + (int)rank, c);
 
-    for (int m = blockIdx.x; m < p.tiles_m; m += gridDim.x) {
+    for (int mp = cluster_id; mp < npairs; mp += num_clusters) {
+      const int m = mp * CG + (int)rank;
       const int row = q * 32 + lane;
       const int row0 = m * BM + q * 32;
       mbar_wait(&s.y_full, yph);
@@ -418,13 +503,12 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&s.y_empty);
+        arrive_leader<CG>(L_y_empty);
         if (GN && !(p.debug & 1)) { load_gn(m, 0); load_gn(m, 1); }     // every buffer is free: two (conv, skip) pairs
       }
       if (p.debug & 1) {
         __syncwarp();
-        const int mn = m + gridDim.x;
-        if (lane == 0 && mn < p.tiles_m) for (int c = 0; c < LN_BUFS; ++c) load_res(mn, c);
+        if (lane == 0 && mp + num_clusters < npairs) for (int c = 0; c < LN_BUFS; ++c) load_res((mp + num_clusters) * CG + (int)rank, c);
         continue;
       }
       s.xch[0][half][row] = sum;
@@ -536,10 +620,10 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       }
       __syncwarp();
       if (lane == 0) {
-        const int mn = m + gridDim.x;       // the next tile's first four residual chunks, as soon as the stores have drained
-        if (mn < p.tiles_m) {
+        // the next tile's first four residual chunks, as soon as the stores have drained
+        if (mp + num_clusters < npairs) {
           tma_store_wait_read();
-          for (int c = 0; c < LN_BUFS; ++c) load_res(mn, c);
+          for (int c = 0; c < LN_BUFS; ++c) load_res((mp + num_clusters) * CG + (int)rank, c);
         }
       }
     }
@@ -548,39 +632,53 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // neither CTA leaves (or frees TMEM) while the pair's MMAs / arrivals can touch it
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
-template <bool GN>
+template <bool GN, int CG>
 int launch_ffn(FfnParams& p, cudaStream_t st) {
   // the struct plus whatever alignment slack the 227 KB limit leaves (the kernel checks that it fits behind its 1024-byte
   // alignment: the dynamic window of a kernel without static shared memory starts aligned)
-  constexpr int smem_bytes = (int)sizeof(FfnSmem) + 1024 <= 232448 ? (int)sizeof(FfnSmem) + 1024 : 232448;
-  static_assert(sizeof(FfnSmem) <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
-  auto kern = ffn_fused_tcgen05_kernel<GN>;
+  constexpr int smem_bytes = (int)sizeof(FfnSmem<CG>) + 1024 <= 232448 ? (int)sizeof(FfnSmem<CG>) + 1024 : 232448;
+  static_assert(sizeof(FfnSmem<CG>) <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
+  auto kern = ffn_fused_tcgen05_kernel<GN, CG>;
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  const int grid = p.tiles_m < num_sms() ? p.tiles_m : num_sms();
+  const int npairs = (p.tiles_m + CG - 1) / CG;
+  const int max_clusters = num_sms() / CG;
+  const int grid = CG * (npairs < max_clusters ? npairs : max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (getenv("EMRT_FFN_PROF")) {          // diagnosis only: where the MMA thread waits (synchronous, prints to stderr)
     long long* d = nullptr;
     EMRT_CUDA_CHECK(cudaMalloc(&d, (size_t)grid * 8 * sizeof(long long)));
     EMRT_CUDA_CHECK(cudaMemset(d, 0, (size_t)grid * 8 * sizeof(long long)));
     p.prof = d;
-    kern<<<grid, NUM_THREADS, smem_bytes, st>>>(p);
+    EMRT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
     EMRT_CUDA_CHECK(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)grid * 8);
     EMRT_CUDA_CHECK(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(d);
     double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < grid; ++i) for (int k = 0; k < 6; ++k) a[k] += (double)h[(size_t)i * 8 + k] / grid;
+    for (int i = 0; i < grid; i += CG) for (int k = 0; k < 6; ++k) a[k] += (double)h[(size_t)i * 8 + k] / (grid / CG);
     fprintf(stderr, "ffn_fused MMA thread, cycles per CTA (avg of %d): total %.0f | wait x %.0f, weights %.0f, hacc_empty %.0f, hs_full %.0f, y_empty %.0f | tiles/CTA %.1f\n",
             grid, a[0], a[1], a[2], a[3], a[4], a[5], (double)p.tiles_m / grid);
     count_launch();
     return EMRT_OK;
   }
-  kern<<<grid, NUM_THREADS, smem_bytes, st>>>(p);
+  EMRT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
 }
@@ -608,6 +706,7 @@ extern "C" int emrt_ffn_fused_fwd(const emrt_ffn_args* a, void* stream) {
   p.tiles_m = (int)((a->rows + BM - 1) / BM);
   p.num_chunks = a->d_ff / CH;
   { const char* e = getenv("EMRT_FFN_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  const bool one_cta = getenv("EMRT_FFN_1CTA") != nullptr;      // the cta_group::1 form (one CTA per tile, full B operand per SM)
   {
     const uint64_t d[2] = {(uint64_t)DM, (uint64_t)a->rows}, sb[1] = {(uint64_t)DM * 2};
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
@@ -642,8 +741,8 @@ extern "C" int emrt_ffn_fused_fwd(const emrt_ffn_args* a, void* stream) {
     const uint32_t box[2] = {(uint32_t)LCH, 32u};
     if (int e = make_tensor_map(&p.tma_conv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->conv, d, sb, box, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
     if (int e = make_tensor_map(&p.tma_skip, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->skip, d, sb, box, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
-    return launch_ffn<true>(p, st);
+    return one_cta ? launch_ffn<true, 1>(p, st) : launch_ffn<true, 2>(p, st);
   }
   p.gn_gamma = a->ln_gamma; p.gn_beta = a->ln_beta;     // never read; keeps the pointer arithmetic defined
-  return launch_ffn<false>(p, st);
+  return one_cta ? launch_ffn<false, 1>(p, st) : launch_ffn<false, 2>(p, st);
 }
