@@ -113,28 +113,32 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(CV_BM, CV_N);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+    // warp-uniform loop, one elected lane issues (tc_common.cuh, elect_one)
+    constexpr uint32_t idesc = make_idesc(CV_BM, CV_N);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t a_base = smem_u32(s.a[0]), b_base = smem_u32(s.b[0]);
+    const uint64_t desc_hi = make_smem_desc(0);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CV_N);
+      for (int ks = 0; ks < 9 * KB; ++ks) {
+        mbar_wait(&s.full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CV_N);
-        for (int ks = 0; ks < 9 * KB; ++ks) {
-          mbar_wait(&s.full[stage], phase);
-          tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(s.a[stage]));
-          const uint64_t db = make_smem_desc(smem_u32(s.b[stage]));
+        const uint64_t da = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * (uint32_t)sizeof(s.a[0])) & 0x3FFFFu) >> 4);
+        const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * (uint32_t)sizeof(s.b[0])) & 0x3FFFFu) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < CV_BK / 16; ++k)
             umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
           umma_commit(&s.empty[stage]);
           if (ks == 9 * KB - 1) umma_commit(&s.tmem_full[acc]);
-          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int q = warp & 3, half = (warp - CV_EPI_WARP0) >> 2;

@@ -93,7 +93,7 @@ struct FfnSmem {
   float xch[2][2][BM];                             // [pass][column half][row]: partial row sums of the two LN warps of a row
   uint64_t x_full, x_empty;
   uint64_t w_full[Ring<CG>::UNITS], w_empty[Ring<CG>::UNITS];
-  uint64_t hacc_full, hacc_empty;
+  uint64_t hacc_full[2], hacc_empty[2];             // per 64-column half of the GEMM1 accumulator
   uint64_t hs_full[HS_SLOTS], hs_empty[HS_SLOTS];
   uint64_t y_full, y_empty;
   uint64_t l_full[NUM_LN_WARPS][LN_BUFS];
@@ -124,6 +124,24 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+#ifdef EMRT_FFN_WATCHDOG
+// debug build: every wait of this file reports what it is stuck on instead of hanging the GPU
+__device__ __noinline__ void wd_wait(uint64_t* bar, uint32_t parity, int line) {
+  for (long long it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if (it > 4000000) {
+      printf("ffn_fused watchdog: block %d warp %d lane %d stuck at line %d (parity %u)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+             (int)(threadIdx.x & 31), line, parity);
+      __trap();
+    }
+  }
+}
+#define mbar_wait(bar, parity) wd_wait(bar, parity, __LINE__)
+#endif
+
 // ---- CTA-pair plumbing (CG = 2) ------------------------------------------------------------------------------
 // One thread of the pair's leader (cluster rank 0) issues tcgen05.mma.cta_group::2 for both CTAs: M = 256 (128 rows from each
 // CTA's own A tile), each CTA holding half of the B rows at the same shared-memory offset.  Barriers the issuing thread WAITS
@@ -146,7 +164,7 @@ template <int CG> __device__ __forceinline__ uint32_t leader_addr(const void* lo
 }
 // the issuing thread's waits: cluster-scope acquire when the arrivals (and the shared-memory writes they publish) come from
 // the peer CTA as well
-template <int CG> __device__ __forceinline__ void wait_lead(uint64_t* bar, uint32_t parity) {
+template <int CG> __device__ __forceinline__ void wait_lead_impl(uint64_t* bar, uint32_t parity) {
   if (CG == 2)
     asm volatile(
         "{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n"
@@ -154,8 +172,16 @@ template <int CG> __device__ __forceinline__ void wait_lead(uint64_t* bar, uint3
   else
     mbar_wait(bar, parity);
 }
+#ifdef EMRT_FFN_WATCHDOG
+#define wait_lead_line(CGV, bar, parity) wd_wait(bar, parity, __LINE__)
+#else
+#define wait_lead_line(CGV, bar, parity) wait_lead_impl<CGV>(bar, parity)
+#endif
 template <int CG> __device__ __forceinline__ void arrive_leader(uint32_t leader_bar) {
-  if (CG == 2) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_bar) : "memory");
+  // (default semantics — release at CTA scope, like CUTLASS's ClusterBarrier::arrive on a mapa address: what is published
+  // here is either nothing but "I have read TMEM" or shared-memory data already fenced into the async proxy; a cluster-scope
+  // release costs a full memory barrier per arrive and stalled the H warps for ~2 k clocks per chunk)
+  if (CG == 2) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_bar) : "memory");
   else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(leader_bar) : "memory");
 }
 template <int CG>
@@ -220,8 +246,11 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
     mbar_init(&s.x_empty, 1);
 #pragma unroll
     for (int i = 0; i < W_UNITS; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
-    mbar_init(&s.hacc_full, 1);
-    mbar_init(&s.hacc_empty, CG * NUM_H_WARPS);        // (the leader's copy collects the arrivals of both CTAs)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.hacc_full[i], 1);
+      mbar_init(&s.hacc_empty[i], CG * NUM_H_WARPS);   // (the leader's copy collects the arrivals of both CTAs)
+    }
 #pragma unroll
     for (int i = 0; i < HS_SLOTS; ++i) { mbar_init(&s.hs_full[i], CG * NUM_H_WARPS); mbar_init(&s.hs_empty[i], 1); }
     mbar_init(&s.y_full, 1);
@@ -244,7 +273,8 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
   if (CG == 2) cluster_sync_all();          // both CTAs' barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
-  const uint32_t L_hacc_empty = leader_addr<CG>(&s.hacc_empty), L_y_empty = leader_addr<CG>(&s.y_empty);
+  const uint32_t L_hacc_empty[2] = {leader_addr<CG>(&s.hacc_empty[0]), leader_addr<CG>(&s.hacc_empty[1])};
+  const uint32_t L_y_empty = leader_addr<CG>(&s.y_empty);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -259,7 +289,14 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         for (int kb = 0; kb < DM / BK; ++kb) {
           mbar_wait(&s.w_empty[ws], wph ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&s.w_full[ws], CG * W_UNIT_BYTES);
-          tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH + (int)rank * (CH / CG));
+          // the unit holds this CTA's B rows of the chunk's two 64-unit halves, half a first: the pair's CTAs split each half
+          // (rows [32 r, +32) of it each), so that a half's 64 hidden units stay contiguous across the pair
+          if (CG == 2) {
+            tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH + (int)rank * 32);
+            tma_load_2d_lead<CG>(s.w[ws] + W_UNIT_BYTES / 2, &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH + 64 + (int)rank * 32);
+          } else {
+            tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH);
+          }
           advance();
         }
       };
@@ -291,8 +328,12 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc1 = make_idesc(BM * CG, CH), idesc2 = make_idesc(BM * CG, DM);
+    // The whole warp runs this loop (warp-uniform control flow, barrier waits by every lane) and one elected lane issues the
+    // tcgen05 instructions: the descriptors then live in uniform registers.  Under `if (lane == 0)` the compiler wrapped
+    // every tcgen05.mma in a per-active-lane election loop and moved each operand through R2UR — ~65 instructions per four
+    // MMAs on one thread's dependency chain, which (not the tensor pipe, 40 % active) was what set the pace.
+    if (rank == 0) {
+      constexpr uint32_t idesc1 = make_idesc(BM * CG, CH / 2), idesc2 = make_idesc(BM * CG, DM);
       int ws = 0;
       uint32_t wph = 0, xph = 0, yph = 0, hacc_e = 0;
       uint32_t jg = 0;                        // hidden k-blocks consumed so far (runs across tiles): hs slot = jg & 1
@@ -300,50 +341,72 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       const long long t_begin = clock64();
 #define PROF_WAIT(acc, ...) do { if (p.prof) { const long long t0_ = clock64(); __VA_ARGS__; acc += clock64() - t0_; } else { __VA_ARGS__; } } while (0)
       auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
+      const uint32_t x_base = smem_u32(s.x[0]), w_base = smem_u32(s.w[0]), hs_base = smem_u32(s.hs[0]);
+      const uint64_t desc_hi = make_smem_desc(0);           // everything but the start address
+      auto desc_of = [&](uint32_t addr) { return desc_hi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
       for (int mp = cluster_id; mp < npairs; mp += num_clusters) {
-        PROF_WAIT(t_x, wait_lead<CG>(&s.x_full, xph));
+        PROF_WAIT(t_x, wait_lead_line(CG, &s.x_full, xph));
         xph ^= 1;
         tc_fence_after();
+        // GEMM1 of chunk c in two N = 64 halves, each into its own 64 accumulator columns: the H warps read half a while the
+        // tensor pipe fills half b, and the next chunk's half a only needs THAT half read — the accumulator is double-buffered
+        // inside the 128 columns the LayerNorm's parked row leaves free.  Both halves read the chunk's four W1 units (half b
+        // releases them).
         auto g1 = [&](int c) {
-          PROF_WAIT(t_hacc, wait_lead<CG>(&s.hacc_empty, hacc_e ^ 1u));   // the H warps have read the previous chunk out of hacc
-          hacc_e ^= 1u;
-          tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)HACC_COL;
+          constexpr uint32_t HALF_B_BYTES = W_UNIT_BYTES / 2;
+          const int ws0 = ws;
+          const uint32_t wph0 = wph;
 #pragma unroll
-          for (int kb = 0; kb < DM / BK; ++kb) {
-            PROF_WAIT(t_w, wait_lead<CG>(&s.w_full[ws], wph));
+          for (int hf = 0; hf < 2; ++hf) {
+            PROF_WAIT(t_hacc, wait_lead_line(CG, &s.hacc_empty[hf], hacc_e ^ 1u));   // the H warps have read this half of the previous chunk
             tc_fence_after();
-            const uint64_t da = make_smem_desc(smem_u32(s.x[kb]));
-            const uint64_t db = make_smem_desc(smem_u32(s.w[ws]));
+            const uint32_t d = tmem_base + (uint32_t)(HACC_COL + hf * 64);
+            ws = ws0;
+            wph = wph0;
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_cg<CG>(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
-            commit_cg<CG>(&s.w_empty[ws]);
-            advance();
+            for (int kb = 0; kb < DM / BK; ++kb) {
+              if (hf == 0) { PROF_WAIT(t_w, wait_lead_line(CG, &s.w_full[ws], wph)); tc_fence_after(); }
+              const uint64_t da = desc_of(x_base + (uint32_t)kb * (BM * BK * 2));
+              const uint64_t db = desc_of(w_base + (uint32_t)ws * W_UNIT_BYTES + (uint32_t)hf * HALF_B_BYTES);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  umma_cg<CG>(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
+                if (hf == 1) commit_cg<CG>(&s.w_empty[ws]);
+                if (kb == DM / BK - 1) {
+                  commit_cg<CG>(&s.hacc_full[hf]);
+                  if (hf == 1 && c == NC - 1) commit_cg<CG>(&s.x_empty);
+                }
+              }
+              __syncwarp();
+              advance();
+            }
           }
-          commit_cg<CG>(&s.hacc_full);
-          if (c == NC - 1) commit_cg<CG>(&s.x_empty);
+          hacc_e ^= 1u;
         };
         auto g2 = [&](int j) {                 // hidden k-block j of this tile: y += h[:, 64 j .. +64] @ W2[:, 64 j .. +64]^T
           const uint32_t slot = jg & 1u;
-          PROF_WAIT(t_hs, wait_lead<CG>(&s.hs_full[slot], (jg >> 1) & 1u));
+          PROF_WAIT(t_hs, wait_lead_line(CG, &s.hs_full[slot], (jg >> 1) & 1u));
           ++jg;
           if (j == 0) {                        // the LN warps have taken the previous tile's row out of y
-            PROF_WAIT(t_y, wait_lead<CG>(&s.y_empty, yph ^ 1));
+            PROF_WAIT(t_y, wait_lead_line(CG, &s.y_empty, yph ^ 1));
             yph ^= 1;
           }
-          PROF_WAIT(t_w, wait_lead<CG>(&s.w_full[ws], wph));
-          PROF_WAIT(t_w, wait_lead<CG>(&s.w_full[ws + 1], wph));
+          PROF_WAIT(t_w, wait_lead_line(CG, &s.w_full[ws], wph));
+          PROF_WAIT(t_w, wait_lead_line(CG, &s.w_full[ws + 1], wph));
           tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(s.hs[slot]));
-          const uint64_t db = make_smem_desc(smem_u32(s.w[ws]));
+          const uint64_t da = desc_of(hs_base + slot * (uint32_t)(BM * BK * 2));
+          const uint64_t db = desc_of(w_base + (uint32_t)ws * W_UNIT_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_cg<CG>(tmem_base + (uint32_t)Y_COL, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
-          commit_cg<CG>(&s.w_empty[ws]);
-          commit_cg<CG>(&s.w_empty[ws + 1]);
-          commit_cg<CG>(&s.hs_empty[slot]);
-          if (j == 2 * NC - 1) commit_cg<CG>(&s.y_full);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_cg<CG>(tmem_base + (uint32_t)Y_COL, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (j | k) != 0 ? 1u : 0u);
+            commit_cg<CG>(&s.w_empty[ws]);
+            commit_cg<CG>(&s.w_empty[ws + 1]);
+            commit_cg<CG>(&s.hs_empty[slot]);
+            if (j == 2 * NC - 1) commit_cg<CG>(&s.y_full);
+          }
+          __syncwarp();
           advance();
           advance();
         };
@@ -356,7 +419,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
           g2(2 * c + 1);
         }
       }
-      if (p.prof) {
+      if (p.prof && lane == 0) {
         long long* o = p.prof + (size_t)blockIdx.x * 8;
         o[0] = clock64() - t_begin; o[1] = t_x; o[2] = t_w; o[3] = t_hacc; o[4] = t_hs; o[5] = t_y;
       }
@@ -382,21 +445,19 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         float4 bias[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bias[j] = __ldg(b1v + j);
-        mbar_wait(&s.hacc_full, hacc_f);
-        hacc_f ^= 1u;
-        tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {       // hidden k-block kk of the chunk: accumulator columns [64 kk, +64)
+        for (int kk = 0; kk < 2; ++kk) {       // hidden k-block kk of the chunk: accumulator columns [64 kk, +64), its own barrier pair
+          mbar_wait(&s.hacc_full[kk], hacc_f);
+          tc_fence_after();
           uint32_t ra[32], rb[32];
           TMEM_LD_X32(t_h + kk * 64, ra);
           TMEM_LD_X32(t_h + kk * 64 + 32, rb);
           TMEM_WAIT_X32(ra);
           TMEM_WAIT_X32(rb);
-          if (kk == 1) {                       // hacc has been read completely: GEMM1 of the next chunk may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) arrive_leader<CG>(L_hacc_empty);
-          }
+          // this half of hacc has been read: GEMM1 of the next chunk may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader<CG>(L_hacc_empty[kk]);
           uint32_t o[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -420,6 +481,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
           __syncwarp();
           if (lane == 0) arrive_leader<CG>(L_hs_full[kk]);
         }
+        hacc_f ^= 1u;
       }
     }
   } else {
@@ -702,11 +764,12 @@ extern "C" int emrt_ffn_fused_fwd(const emrt_ffn_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   FfnParams p;
   memset(&p, 0, sizeof(p));
+  const bool one_cta = getenv("EMRT_FFN_1CTA") != nullptr;      // the cta_group::1 form (one CTA per tile, full B operand per SM)
+  const uint32_t cg = one_cta ? 1u : 2u;                          // every weight box holds this CTA's share of the B rows
   p.b1 = a->b1; p.b2 = a->b2; p.gamma = a->ln_gamma; p.beta = a->ln_beta; p.eps = a->ln_eps;
   p.tiles_m = (int)((a->rows + BM - 1) / BM);
   p.num_chunks = a->d_ff / CH;
   { const char* e = getenv("EMRT_FFN_DEBUG"); p.debug = e ? atoi(e) : 0; }
-  const bool one_cta = getenv("EMRT_FFN_1CTA") != nullptr;      // the cta_group::1 form (one CTA per tile, full B operand per SM)
   {
     const uint64_t d[2] = {(uint64_t)DM, (uint64_t)a->rows}, sb[1] = {(uint64_t)DM * 2};
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
@@ -717,12 +780,12 @@ extern "C" int emrt_ffn_fused_fwd(const emrt_ffn_args* a, void* stream) {
   }
   {
     const uint64_t d[2] = {(uint64_t)DM, (uint64_t)a->d_ff}, sb[1] = {(uint64_t)DM * 2};
-    const uint32_t box[2] = {(uint32_t)BK, 128u};
+    const uint32_t box[2] = {(uint32_t)BK, cg == 2 ? 32u : (uint32_t)CH};    // CTA pair: a quarter of the chunk per load (two per unit)
     if (int e = make_tensor_map(&p.tma_w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->w1, d, sb, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
   {
     const uint64_t d[2] = {(uint64_t)a->d_ff, (uint64_t)DM}, sb[1] = {(uint64_t)a->d_ff * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)DM};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)DM / cg};
     if (int e = make_tensor_map(&p.tma_w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->w2, d, sb, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
   if (a->gn) {

@@ -90,6 +90,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of the converged warp.  The MMA-issuing warps run their loops warp-uniformly (every lane waits on the barriers)
+// and issue the tcgen05 instructions under this predicate: the operands then live in uniform registers.  Under
+// `if (lane == 0)` the compiler wraps each tcgen05.mma in a per-active-lane election loop and moves every operand through
+// R2UR — enough instructions on one thread's dependency chain to pace the kernel instead of the tensor pipe.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

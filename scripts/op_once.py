@@ -40,6 +40,8 @@ with torch.no_grad():
         stats = ops.groupnorm_stats(conv, shapes, groups=32)
         fn = lambda: ops.linear(h, lp["w2"], lp["b2"], w_transposed=True, epilogue=L.EPI_RESIDUAL_LN, residual=src, ln_gamma=lp["n2w"],
                                 ln_beta=lp["n2b"], gn_branch=dict(conv=conv, skip=src, stats=stats, gamma=lp["gn_w"], beta=lp["gn_b"], shapes=shapes))
+    elif what == "conv":
+        fn = lambda: ops.conv3x3_tokens(src, lp["conv_w"], shapes)
     elif what == "ffn":
         conv = torch.randn((B, Lv, 256), generator=g, device=dev).bfloat16()
         stats = ops.groupnorm_stats(conv, shapes, groups=32)
