@@ -7,6 +7,7 @@
 // all 36 k-blocks accumulating into one TMEM tile: D[128 pixels x 256] = sum_tap A_tap[128 x 256] W_tap^T.
 // Same warp-specialised skeleton as linear_tcgen05.cu (TMA producer / MMA issuer / 8 epilogue warps, two TMEM
 // accumulators, staged TMA-store epilogue); one launch covers the three levels (different weights per level).
+#include <cstdlib>
 #include <cstring>
 
 #include "tc_common.cuh"
@@ -16,7 +17,12 @@ namespace emrt {
 int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
 
-constexpr int CV_BM = 128, CV_BK = 64, CV_N = 256, CV_STAGES = 4;
+constexpr int CV_BM = 128, CV_BK = 64, CV_N = 256;
+// CG = 2 (CTA pair, tcgen05.mma.cta_group::2): each CTA brings its own 128-pixel A tile and HALF of the weight slab, so a stage
+// is 32 KB instead of 48 KB and the ring is six stages deep in the same 192 KB.  Why it matters: with one CTA per tile the
+// kernel is bound by the SM's shared-memory bandwidth — per k-block the tensor pipe reads 48 KB of operands and TMA writes 48 KB
+// of new ones, 96 KB at 128 B/clk = 750 clocks for 512 clocks of MMAs (measured 814).  Halving B makes it 64 KB = 500 clocks.
+template <int CG> struct ConvCfg { static constexpr int STAGES = CG == 2 ? 6 : 4; static constexpr int B_ROWS = CV_N / CG; };
 constexpr int CV_EPI_WARP0 = 2, CV_EPI_WARPS = 8, CV_THREADS = 32 * (CV_EPI_WARP0 + CV_EPI_WARPS);
 constexpr int CV_MAX_L = 4;
 
@@ -32,12 +38,13 @@ struct ConvParams {
   int32_t L;
 };
 
+template <int CG>
 struct ConvSmem {
-  __nv_bfloat16 a[CV_STAGES][CV_BM * CV_BK];
-  __nv_bfloat16 b[CV_STAGES][CV_N * CV_BK];
+  __nv_bfloat16 a[ConvCfg<CG>::STAGES][CV_BM * CV_BK];
+  __nv_bfloat16 b[ConvCfg<CG>::STAGES][ConvCfg<CG>::B_ROWS * CV_BK];
   uint8_t stage[CV_EPI_WARPS * 32 * 64];
-  uint64_t full[CV_STAGES];
-  uint64_t empty[CV_STAGES];
+  uint64_t full[ConvCfg<CG>::STAGES];
+  uint64_t empty[ConvCfg<CG>::STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -59,22 +66,34 @@ __device__ __forceinline__ ConvTile conv_tile(const ConvParams& p, int t) {
   return c;
 }
 
-__device__ __forceinline__ void tma_load_4d_cv(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+template <int CG>
+__device__ __forceinline__ void tma_load_4d_cv(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
                                                int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
-          "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
+  if (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 
+template <int CG>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int CV_STAGES = ConvCfg<CG>::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  ConvSmem<CG>& s = *reinterpret_cast<ConvSmem<CG>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tile_start[p.L];
-  constexpr uint32_t STAGE_BYTES = (CV_BM * CV_BK + CV_N * CV_BK) * 2;
+  constexpr uint32_t STAGE_BYTES = (CV_BM * CV_BK + ConvCfg<CG>::B_ROWS * CV_BK) * 2;
   constexpr int KB = CV_N / CV_BK;          // k-blocks per tap (Cin = 256)
+  // CTA pair: tiles 2 k and 2 k + 1 (same level: the host only picks this form when every level has an even tile count)
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int first = (int)blockIdx.x / CG * CG + (int)rank;
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < p.L; ++l) { tma_prefetch_desc(&p.tma_x[l]); tma_prefetch_desc(&p.tma_y[l]); }
@@ -82,15 +101,21 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
     for (int i = 0; i < CV_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], CV_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], CG * CV_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
 
@@ -98,47 +123,51 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      // (both CTAs of a pair: own A tile, own half of the weight rows; the bytes of both count on the leader's barrier)
+      for (int t = first; t < num_tiles; t += gridDim.x) {
         const ConvTile c = conv_tile(p, t);
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&s.empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
-            tma_load_4d_cv(s.a[stage], &p.tma_x[c.l], &s.full[stage], kb * CV_BK, kx - 1, c.y0 + ky - 1, c.b0);
-            tma_load_2d(s.b[stage], &p.tma_w, &s.full[stage], kb * CV_BK, (c.l * 9 + tap) * CV_N);
+            if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], CG * STAGE_BYTES);
+            const uint32_t lb = leader_addr<CG>(&s.full[stage]);
+            tma_load_4d_cv<CG>(s.a[stage], &p.tma_x[c.l], lb, kb * CV_BK, kx - 1, c.y0 + ky - 1, c.b0);
+            tma_load_2d_lead<CG>(s.b[stage], &p.tma_w, lb, kb * CV_BK, (c.l * 9 + tap) * CV_N + (int)rank * ConvCfg<CG>::B_ROWS);
             if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // warp-uniform loop, one elected lane issues (tc_common.cuh, elect_one)
-    constexpr uint32_t idesc = make_idesc(CV_BM, CV_N);
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
-    const uint32_t a_base = smem_u32(s.a[0]), b_base = smem_u32(s.b[0]);
-    const uint64_t desc_hi = make_smem_desc(0);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CV_N);
-      for (int ks = 0; ks < 9 * KB; ++ks) {
-        mbar_wait(&s.full[stage], phase);
+    // warp-uniform loop, one elected lane issues (tc_common.cuh, elect_one); in a CTA pair only the leader's warp
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(CV_BM * CG, CV_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t a_base = smem_u32(s.a[0]), b_base = smem_u32(s.b[0]);
+      const uint64_t desc_hi = make_smem_desc(0);
+      for (int t = first; t < num_tiles; t += gridDim.x) {
+        wait_lead<CG>(&s.tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint64_t da = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * (uint32_t)sizeof(s.a[0])) & 0x3FFFFu) >> 4);
-        const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * (uint32_t)sizeof(s.b[0])) & 0x3FFFFu) >> 4);
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CV_N);
+        for (int ks = 0; ks < 9 * KB; ++ks) {
+          wait_lead<CG>(&s.full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * (uint32_t)sizeof(s.a[0])) & 0x3FFFFu) >> 4);
+          const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * (uint32_t)sizeof(s.b[0])) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < CV_BK / 16; ++k)
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
-          umma_commit(&s.empty[stage]);
-          if (ks == 9 * KB - 1) umma_commit(&s.tmem_full[acc]);
+            for (int k = 0; k < CV_BK / 16; ++k)
+              umma_cg<CG>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+            commit_cg<CG>(&s.empty[stage]);
+            if (ks == 9 * KB - 1) commit_cg<CG>(&s.tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int q = warp & 3, half = (warp - CV_EPI_WARP0) >> 2;
@@ -146,7 +175,8 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
     const uint32_t stage_addr = smem_u32(s.stage) + (uint32_t)(warp - CV_EPI_WARP0) * (32 * 64);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const uint32_t L_tmem_empty[2] = {leader_addr<CG>(&s.tmem_empty[0]), leader_addr<CG>(&s.tmem_empty[1])};
+    for (int t = first; t < num_tiles; t += gridDim.x) {
       const ConvTile c = conv_tile(p, t);
       mbar_wait(&s.tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -177,17 +207,42 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);
+      if (lane == 0) arrive_leader<CG>(L_tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+}
+
+template <int CG>
+static int launch_conv(const ConvParams& p, int tiles, cudaStream_t st) {
+  const int smem_bytes = (int)sizeof(ConvSmem<CG>) + 1024;
+  auto kern = conv3x3_tokens_tc_kernel<CG>;
+  // per launch: function attributes are per context (a second GPU in the same process needs its own opt-in) and this is cheap
+  EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  grid = grid / CG * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CV_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EMRT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
 }
 
 // Returns EMRT_ERR_UNSUPPORTED (error text untouched) for shapes this kernel does not tile.
@@ -230,15 +285,12 @@ int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int L
   p.tile_start[L] = tiles;
   const uint64_t dw[2] = {(uint64_t)C, (uint64_t)L * 9 * C};
   const uint64_t sw[1] = {(uint64_t)C * 2};
-  const uint32_t bw[2] = {(uint32_t)CV_BK, (uint32_t)CV_N};
+  // CTA pairs need tile 2 k and 2 k + 1 on the same level (same weights): every level's tile count even
+  bool pair = getenv("EMRT_CONV_1CTA") == nullptr && tiles >= 2;
+  for (int l = 0; l <= L; ++l) pair = pair && (p.tile_start[l] % 2 == 0);
+  const uint32_t bw[2] = {(uint32_t)CV_BK, (uint32_t)(pair ? CV_N / 2 : CV_N)};
   if (int e = make_tensor_map(&p.tma_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  const int smem_bytes = (int)sizeof(ConvSmem) + 1024;
-  // per launch: function attributes are per context (a second GPU in the same process needs its own opt-in) and this is cheap
-  EMRT_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tokens_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv3x3_tokens_tc_kernel<<<grid, CV_THREADS, smem_bytes, st>>>(p);
-  EMRT_LAUNCH_CHECK();
-  return EMRT_OK;
+  return pair ? launch_conv<2>(p, tiles, st) : launch_conv<1>(p, tiles, st);
 }
 
 }  // namespace emrt

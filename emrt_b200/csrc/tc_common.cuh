@@ -122,6 +122,69 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- CTA-pair plumbing (CG = 2) ------------------------------------------------------------------------------
+// One thread of the pair's leader (cluster rank 0) issues tcgen05.mma.cta_group::2 for both CTAs: M = 256 (128 rows from each
+// CTA's own A tile), each CTA holding half of the B rows at the same shared-memory offset.  Barriers the issuing thread WAITS
+// on live in the leader: the peer's TMA loads complete their bytes there (.cta_group::2 form of the copy) and the peer's
+// warps arrive there with a cluster-scope arrive.  Barriers the MMAs SIGNAL are committed with multicast to both CTAs, so
+// every other warp only ever waits on its own CTA's copy.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the shared::cluster address of the leader's copy of a barrier (the same address for CG = 1)
+template <int CG> __device__ __forceinline__ uint32_t leader_addr(const void* local) {
+  uint32_t a = smem_u32(local);
+  if (CG == 2) asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a) : "r"(a));
+  return a;
+}
+// the issuing thread's waits: cluster-scope acquire when the arrivals (and the shared-memory writes they publish) come from
+// the peer CTA as well
+template <int CG> __device__ __forceinline__ void wait_lead(uint64_t* bar, uint32_t parity) {
+  if (CG == 2)
+    asm volatile(
+        "{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n"
+        " bra LAB_WAIT;\n DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+  else
+    mbar_wait(bar, parity);
+}
+template <int CG> __device__ __forceinline__ void arrive_leader(uint32_t leader_bar) {
+  // (default semantics — release at CTA scope, like CUTLASS's ClusterBarrier::arrive on a mapa address: what is published
+  // here is either nothing but "I have read TMEM" or shared-memory data already fenced into the async proxy; a cluster-scope
+  // release costs a full memory barrier per arrive and stalled the H warps for ~2 k clocks per chunk)
+  if (CG == 2) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_bar) : "memory");
+  else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(leader_bar) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_lead(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  if (CG == 2)
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_cg(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2)
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+template <int CG> __device__ __forceinline__ void commit_cg(uint64_t* bar) {   // arrives on `bar` in every CTA of the pair
+  if (CG == 2)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3) : "memory");
+  else
+    umma_commit(bar);
+}
+
+
 #define TMEM_LD_X16(taddr, r)                                                                                     \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
