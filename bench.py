@@ -514,6 +514,11 @@ def run_ours(args):
             rows_, K_, N_, sx, sy = dims
             key = f"linear rows={rows_} K={K_} N={N_}"
             flops, byts = 2.0 * rows_ * K_ * N_, rows_ * (K_ * sx + N_ * sy) + K_ * N_ * sx
+        elif name == "ffn_fused" and dims[0] == B * Lv:
+            rows_, C_, F_, sx = dims
+            key = f"ffn_fused rows={rows_} d_model={C_} d_ff={F_} (linear1 + ReLU + linear2 + residual + norm2 + conv branch)"
+            # x, conv, skip in; y out; both weight matrices once
+            flops, byts = 4.0 * rows_ * C_ * F_, 4.0 * rows_ * C_ * sx + 2.0 * C_ * F_ * sx
         elif name == "conv3x3" and dims[0] == B * Lv:
             rows_, C_, sx = dims
             key = f"conv3x3 rows={rows_} C={C_}"

@@ -35,3 +35,6 @@ for src in build.SOURCES:
     tma_dims = collections.Counter(re.findall(r"UTMALDG\.(\dD)", out))
     if tma_dims:
         print("  UTMALDG by box rank: " + "  ".join(f"{k} {v}" for k, v in sorted(tma_dims.items())))
+    two = {k: len(re.findall(k + r"[A-Z0-9_.]*\.2CTA", out)) for k in ("UTCHMMA", "UTMALDG", "UTCBAR")}
+    if any(two.values()):       # CTA-pair forms: tcgen05.mma.cta_group::2, the .cta_group::2 TMA load, multicast commit
+        print("  of which .2CTA (cta_group::2): " + "  ".join(f"{k} {v}" for k, v in two.items() if v))
