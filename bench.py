@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records measured after the main timing "
                     "(cfg-4 training step, cfg-5 scene, cfg-2 tiles, copy ceiling, gather sensitivity)")
     ap.add_argument("--cpu-sample-windows", type=int, default=8)
+    ap.add_argument("--e2e-sub-batches", action="store_true", help="e2e: 4 sub-batches of whole scenes per step (shorter pipeline fill, "
+                    "4x the launches: measured slower, 11.56 vs 11.28 ms per step at 20 steps) instead of one copy + one pass per step")
     ap.add_argument("--msda-only", action="store_true", help="round-1 starting definition: 4 + 2 bare MSDA calls + head tail")
     ap.add_argument("--tokens", action="store_true", help="earlier definition: token inputs, encoder + 2 bare decoder MSDA + head tail")
     a = ap.parse_args()
@@ -412,15 +414,50 @@ def run_ours(args):
         ms_total = max_over_ranks(e0.elapsed_time(e1))
 
         # ---- e2e: host buffers in, host labels out, every step -------------------------------------------
-        # Three streams, three device slots: the H2D copies of steps i+1, i+2 (one contiguous pinned buffer -> one device
-        # slot, a single cudaMemcpyAsync per step) overlap the kernels of step i, and the D2H of step i's labels / decoder
-        # states overlaps step i+1.  Every step's copies are inside the timed region.
+        # A step's input set is ONE contiguous pinned buffer -> one cudaMemcpyAsync into one of three device slots: the copies of
+        # steps i+1, i+2 overlap the kernels of step i and the D2H of step i's labels / decoder states overlaps step i+1.  Every
+        # step's copies are inside the timed region, which starts and ends with nothing in flight: K steps cost K copies + one
+        # step of kernels (the drain) — 11.28 ms per step at K = 20 with a 10.8 ms copy.  --e2e-sub-batches sends the set as
+        # four sub-batches of whole scenes instead (a quarter of the fill / drain, four times the launches: measured slower).
         cur = torch.cuda.current_stream()
         h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
         NSLOT = 3
-        slot_flats = [torch.empty(flat_elems, dtype=torch.bfloat16, device=dev) for _ in range(NSLOT)]
-        slots = [views(f) for f in slot_flats]
-        lab_slots = [torch.empty_like(labels_dev) for _ in range(NSLOT)]
+        NSUB = 4 if (full and n_img % 4 == 0 and args.e2e_sub_batches) else 1
+        n_img_s, B_s = n_img // NSUB, B // NSUB
+        plan_s, H_s, W_s = window_tables(n_img_s)
+        win_s = dict(win_img=ti([p[0] for p in plan_s]), win_y0=ti([p[1] for p in plan_s]), win_x0=ti([p[2] for p in plan_s]),
+                     n_img=n_img_s, H=H_s, W=W_s)
+        layout_s = [(name, (B_s,) + tuple(shape[1:]), std) for name, shape, std in layout]
+        sub_elems = sum((int(np.prod(sh)) + 127) // 128 * 128 for _, sh, _ in layout_s)
+
+        def views_s(flat):
+            out, off = {}, 0
+            for name, shape, _ in layout_s:
+                n = int(np.prod(shape))
+                out[name] = flat[off:off + n].view(shape)
+                off += (n + 127) // 128 * 128
+            return out
+
+        def as_batch_s(d):
+            b = dict(d)
+            if full:
+                b["feats"] = [b.pop("c3"), b.pop("c4"), b.pop("c5")]
+            b.update(pos=pos, qpos=qpos, mask=mask[:B_s], **win_s)
+            return b
+        # the same input sets, re-laid per sub-batch (windows [j B_s, (j + 1) B_s) of every tensor) in pinned memory
+        host_subs = []
+        for sset in range(N_SETS):
+            subs = []
+            for j in range(NSUB):
+                hf = torch.empty(sub_elems, dtype=torch.bfloat16).pin_memory()
+                hv = views_s(hf)
+                for name, _, _ in layout_s:
+                    hv[name].copy_(host_sets[sset][name][j * B_s:(j + 1) * B_s])
+                subs.append(hf)
+            host_subs.append(subs)
+        slot_flats = [torch.empty(sub_elems, dtype=torch.bfloat16, device=dev) for _ in range(NSLOT)]
+        slots = [views_s(f) for f in slot_flats]
+        lab_slots = [torch.empty((n_img_s, 1, H_s, W_s), dtype=torch.uint8, device=dev) for _ in range(NSLOT)]
         ready = [torch.cuda.Event() for _ in range(NSLOT)]
         free = [torch.cuda.Event() for _ in range(NSLOT)]
         done = [torch.cuda.Event() for _ in range(NSLOT)]
@@ -428,25 +465,29 @@ def run_ours(args):
         hs_keep = [None] * NSLOT
         for ev in free + drained:
             ev.record(cur)
+        sub_counter = [0]
 
         def e2e_step(i):
-            sl = i % NSLOT
-            with torch.cuda.stream(h2d):
-                h2d.wait_event(free[sl])               # the kernels of step i-NSLOT are done with this slot
-                slot_flats[sl].copy_(host_flats[i % N_SETS], non_blocking=True)     # ONE copy: the whole input set
-                ready[sl].record(h2d)
-            cur.wait_event(ready[sl])
-            cur.wait_event(drained[sl])                # step i-NSLOT's labels have left lab_slots[sl]
-            lab, hs = hp.step(as_batch(slots[sl]), lab_slots[sl])
-            hs_keep[sl] = hs
-            free[sl].record(cur)
-            done[sl].record(cur)
-            with torch.cuda.stream(d2h):
-                d2h.wait_event(done[sl])
-                labels_host.copy_(lab, non_blocking=True)
-                hs_host.copy_(hs, non_blocking=True)
-                hs.record_stream(d2h)
-                drained[sl].record(d2h)
+            for j in range(NSUB):
+                g_ = sub_counter[0]
+                sub_counter[0] += 1
+                sl = g_ % NSLOT
+                with torch.cuda.stream(h2d):
+                    h2d.wait_event(free[sl])               # the kernels of sub-batch g - NSLOT are done with this slot
+                    slot_flats[sl].copy_(host_subs[i % N_SETS][j], non_blocking=True)     # ONE copy: the whole sub-batch
+                    ready[sl].record(h2d)
+                cur.wait_event(ready[sl])
+                cur.wait_event(drained[sl])                # sub-batch g - NSLOT's labels have left lab_slots[sl]
+                lab, hs = hp.step(as_batch_s(slots[sl]), lab_slots[sl])
+                hs_keep[sl] = hs
+                free[sl].record(cur)
+                done[sl].record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(done[sl])
+                    labels_host[j * n_img_s:(j + 1) * n_img_s].copy_(lab, non_blocking=True)
+                    hs_host[j * B_s:(j + 1) * B_s].copy_(hs, non_blocking=True)
+                    hs.record_stream(d2h)
+                    drained[sl].record(d2h)
 
         def e2e_sync():
             h2d.synchronize(); d2h.synchronize()
@@ -466,7 +507,9 @@ def run_ours(args):
 
         # pure-copy ceiling of the platform at this N: the same buffer, the same copy, nothing else running
         import bench_extras as X
-        ceil_gbs, ceil_ms = X.h2d_ceiling(host_flats[0], slot_flats[0], dev, world)
+        ceil_flat = torch.empty(flat_elems, dtype=torch.bfloat16, device=dev)
+        ceil_gbs, ceil_ms = X.h2d_ceiling(host_flats[0], ceil_flat, dev, world)
+        del ceil_flat
 
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
@@ -479,12 +522,13 @@ def run_ours(args):
                                    "nothing else running (max over ranks)",
                "bound": "copy" if copy_bound < value else "compute",
                "frac_of_bound": e2e_value / min(value, copy_bound),
-               "copies": "one contiguous pinned staging buffer per step, 3 device slots, H2D / kernels / D2H on 3 streams"}
+               "copies": f"{NSUB} sub-batch(es) of whole scenes per step, each one contiguous pinned buffer -> one copy, 3 device slots, "
+                         "H2D / kernels / D2H on 3 streams"}
 
     # ---- the other configurations and splits, short, after the main timing --------------------------------
     extras = {}
     if not args.no_extras and args.mode == "full":
-        del dev_sets, slot_flats, slots
+        del dev_sets, slot_flats, slots, host_subs
         torch.cuda.empty_cache()
         for name, fn in (("train_step", lambda: X.train_step(dev, rank, world)),
                          ("scene6000", lambda: X.scene6000(dev, rank, world)),
