@@ -15,6 +15,7 @@ F32, BF16, F16, I32, U8 = 0, 1, 2, 3, 4
 LOC_NORMALIZED, LOC_PIXEL_OFFSET, VALUE_HEAD_MAJOR, QUERY_PIXEL_GRID = 0, 1, 2, 4
 EPI_NONE, EPI_ROW_MASK, EPI_RELU, EPI_RESIDUAL_LN, EPI_MSDA_QPROJ, EPI_HEAD_MAJOR = 0, 1, 2, 4, 8, 16
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+ERR_UNSUPPORTED = -3
 
 
 class EmrtError(RuntimeError):
@@ -109,6 +110,8 @@ SIGNATURES = {
     "emrt_residual_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _I, C.c_float, _I, _P]),
     "emrt_pack_conv3x3_weight": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "emrt_conv3x3_tokens_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I32P, _I, _I, _I, _P]),
+    "emrt_conv3x3_stats_workspace_floats": (C.c_longlong, [_I, _I, _I]),
+    "emrt_conv3x3_tokens_stats_fwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I32P, _I, _P]),
     "emrt_groupnorm_gelu_residual": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_float, _I32P, _I, _P]),
     "emrt_groupnorm_stats": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I32P, _I, _P]),
     "emrt_groupnorm_workspace_floats": (C.c_longlong, [_I, _I, _I]),
@@ -164,7 +167,9 @@ def load():
 def check(status: int):
     if status != 0:
         msg = load().emrt_last_error()
-        raise EmrtError(f"emrt_b200 error {status}: {msg.decode() if msg else ''}")
+        err = EmrtError(f"emrt_b200 error {status}: {msg.decode() if msg else ''}")
+        err.status = int(status)
+        raise err
 
 
 def i32_array(values):

@@ -36,6 +36,7 @@ struct ConvParams {
   int32_t rows_per_tile[CV_MAX_L];
   int32_t W[CV_MAX_L], HW[CV_MAX_L];
   int32_t L;
+  float* gn_partial;   // STATS: [tile][lane quarter][32 groups][sum, sum of squares] of the stored (bf16-rounded) output
 };
 
 template <int CG>
@@ -81,7 +82,10 @@ __device__ __forceinline__ void tma_load_4d_cv(void* smem_dst, const CUtensorMap
         : "memory");
 }
 
-template <int CG>
+// STATS: the epilogue also leaves the GroupNorm(32) statistics of what it stores — per (tile, 32-pixel slab, group) partial
+// sums, combined per (image, level) in a fixed order by conv_gn_finalize_kernel — so that the statistics pass over the conv
+// output (one more read of the tensor, 43 us per layer at 72 windows) does not exist.
+template <int CG, bool STATS>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
   constexpr int CV_STAGES = ConvCfg<CG>::STAGES;
@@ -193,6 +197,27 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
         uint32_t o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), EMRT_BF16);
+        if (STATS) {
+          // four groups of eight channels in this chunk; sums of the ROUNDED values (what GroupNorm will read back), the 32
+          // pixels of the slab combined by a fixed xor tree: deterministic
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float sm = 0.f, sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float a = __uint_as_float(o[g * 4 + i] << 16), b = __uint_as_float(o[g * 4 + i] & 0xffff0000u);
+              sm += a + b;
+              sq = fmaf(a, a, fmaf(b, b, sq));
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              sm += __shfl_xor_sync(0xffffffffu, sm, off);
+              sq += __shfl_xor_sync(0xffffffffu, sq, off);
+            }
+            if (lane == 0)
+              *reinterpret_cast<float2*>(p.gn_partial + (((size_t)t * 4 + q) * 32 + (half * HALF_N + cc) / 8 + g) * 2) = make_float2(sm, sq);
+          }
+        }
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
 #pragma unroll
@@ -222,10 +247,31 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
   }
 }
 
-template <int CG>
+// stats[b][l][g] = (sum, sum of squares) over the (image, level)'s slabs, in tile / slab order
+__global__ void conv_gn_finalize_kernel(const __grid_constant__ ConvParams p, float* __restrict__ stats, int B) {
+  const int bl = blockIdx.x, l = bl % p.L, b = bl / p.L, g = threadIdx.x;
+  float sm = 0.f, sq = 0.f;
+  int tile0, ntiles, q0, nq;
+  if (p.tiles_per_img[l] > 0) {
+    tile0 = p.tile_start[l] + b * p.tiles_per_img[l]; ntiles = p.tiles_per_img[l]; q0 = 0; nq = 4;
+  } else {
+    const int slabs = p.HW[l] / 32;                 // 32-pixel slabs per image (HW < 128: 1 or 2)
+    tile0 = p.tile_start[l] + b / p.imgs_per_tile[l]; ntiles = 1; q0 = (b % p.imgs_per_tile[l]) * slabs; nq = slabs;
+  }
+  for (int t = tile0; t < tile0 + ntiles; ++t)
+    for (int q = q0; q < q0 + nq; ++q) {
+      const float2 v = *reinterpret_cast<const float2*>(p.gn_partial + (((size_t)t * 4 + q) * 32 + g) * 2);
+      sm += v.x;
+      sq += v.y;
+    }
+  *reinterpret_cast<float2*>(stats + ((size_t)(b * p.L + l) * 32 + g) * 2) = make_float2(sm, sq);
+  (void)B;
+}
+
+template <int CG, bool STATS>
 static int launch_conv(const ConvParams& p, int tiles, cudaStream_t st) {
   const int smem_bytes = (int)sizeof(ConvSmem<CG>) + 1024;
-  auto kern = conv3x3_tokens_tc_kernel<CG>;
+  auto kern = conv3x3_tokens_tc_kernel<CG, STATS>;
   // per launch: function attributes are per context (a second GPU in the same process needs its own opt-in) and this is cheap
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = tiles < num_sms() ? tiles : num_sms();
@@ -246,8 +292,11 @@ static int launch_conv(const ConvParams& p, int tiles, cudaStream_t st) {
 }
 
 // Returns EMRT_ERR_UNSUPPORTED (error text untouched) for shapes this kernel does not tile.
+// stats_ws (optional): F32 [2 * B * L * 32 sums | tiles * 256 partials] -> the GroupNorm(32) sums of y per (image, level, group)
+int64_t conv3x3_stats_workspace_floats(int B, int Lv, int L) { return 2LL * B * L * 32 + ((int64_t)B * Lv / CV_BM + (int64_t)B * L + L) * 256; }
+
 int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L, const LevelTable& lv,
-                      cudaStream_t st) {
+                      cudaStream_t st, float* stats_ws) {
   if (C != CV_N || L > CV_MAX_L) return EMRT_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(y)) & 15) return EMRT_ERR_UNSUPPORTED;
   ConvParams p;
@@ -290,7 +339,13 @@ int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int L
   for (int l = 0; l <= L; ++l) pair = pair && (p.tile_start[l] % 2 == 0);
   const uint32_t bw[2] = {(uint32_t)CV_BK, (uint32_t)(pair ? CV_N / 2 : CV_N)};
   if (int e = make_tensor_map(&p.tma_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  return pair ? launch_conv<2>(p, tiles, st) : launch_conv<1>(p, tiles, st);
+  if (!stats_ws) return pair ? launch_conv<2, false>(p, tiles, st) : launch_conv<1, false>(p, tiles, st);
+  if ((int64_t)tiles * 256 + 2LL * B * L * 32 > conv3x3_stats_workspace_floats(B, Lv, L)) return EMRT_ERR_UNSUPPORTED;
+  p.gn_partial = stats_ws + 2LL * B * L * 32;
+  if (int e = pair ? launch_conv<2, true>(p, tiles, st) : launch_conv<1, true>(p, tiles, st)) return e;
+  conv_gn_finalize_kernel<<<B * L, 32, 0, st>>>(p, stats_ws, B);
+  EMRT_LAUNCH_CHECK();
+  return EMRT_OK;
 }
 
 }  // namespace emrt

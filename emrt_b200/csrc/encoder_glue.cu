@@ -470,8 +470,9 @@ groupnorm_tokens_rows_kernel(const T* __restrict__ x, const float* __restrict__ 
 using namespace emrt;
 
 namespace emrt {
+int64_t conv3x3_stats_workspace_floats(int B, int Lv, int L);
 int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L, const LevelTable& lv,
-                      cudaStream_t st);
+                      cudaStream_t st, float* stats_ws = nullptr);
 }
 
 static int launch_residual_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
@@ -590,6 +591,19 @@ extern "C" int emrt_conv3x3_tokens_fwd(const void* x, const void* w_packed, void
   else return set_error(EMRT_ERR_UNSUPPORTED, "conv3x3_tokens: x / w dtypes must both be F32 or both BF16");
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
+}
+
+extern "C" long long emrt_conv3x3_stats_workspace_floats(int B, int Lv, int L) { return conv3x3_stats_workspace_floats(B, Lv, L); }
+
+extern "C" int emrt_conv3x3_tokens_stats_fwd(const void* x, const void* w_packed, void* y, float* stats_workspace, int B, int Lv,
+                                             int C, int L, const int32_t* shapes_hw_host, int groups, void* stream) {
+  EMRT_REQUIRE(x && w_packed && y && stats_workspace && B > 0 && C > 0, "bad conv3x3_tokens_stats arguments");
+  if (groups != 32 || C != 256) return set_error(EMRT_ERR_UNSUPPORTED, "conv3x3 + GroupNorm statistics is built for C = 256, 32 groups");
+  LevelTable lv;
+  if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, Lv)) return e;
+  const int e = conv3x3_tokens_tc(x, w_packed, y, B, Lv, C, L, lv, as_stream(stream), stats_workspace);
+  if (e == EMRT_ERR_UNSUPPORTED) return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 conv3x3 does not tile this shape (use emrt_conv3x3_tokens_fwd + emrt_groupnorm_stats)");
+  return e;
 }
 
 extern "C" int emrt_groupnorm_gelu_residual(const void* conv, const void* x, const float* gamma, const float* beta,

@@ -60,6 +60,7 @@ class TransformerEncoderLayer(nn.Module):
         self.gemm_impl = L.IMPL_AUTO
         self.fuse_ffn2_norm2 = True          # tests may switch the fused linear2 + norm2 + conv-branch epilogue off
         self.fuse_ffn = True                 # ... and the whole-FFN kernel (falls back to linear1 -> fused linear2 epilogue)
+        self.conv_stats_fused = True         # GroupNorm statistics from the conv's epilogue (else the separate statistics kernel)
         self._packed = None
 
     def _version(self):
@@ -134,8 +135,16 @@ class TransformerEncoderLayer(nn.Module):
         impl = self.gemm_impl if fast else L.IMPL_SIMT
         # conv branch (:185-196): conv3x3 -> GroupNorm(32) -> GELU, + skip, on the token layout
         # (GroupNorm + GELU + skip are applied inside the last LayerNorm pass below: the branch tensor never exists)
-        conv = ops.conv3x3_tokens(src, pk["conv_w"], shapes, impl=L.IMPL_AUTO if impl != L.IMPL_SIMT else L.IMPL_SIMT)
-        gn_stats = ops.groupnorm_stats(conv, shapes, groups=32)
+        conv = gn_stats = None
+        if fast and impl != L.IMPL_SIMT and self.d_model == 256 and self.conv_stats_fused:
+            try:        # the conv's epilogue leaves the GroupNorm statistics: no separate pass over its output
+                conv, gn_stats = ops.conv3x3_tokens_stats(src, pk["conv_w"], shapes, groups=32)
+            except L.EmrtError as exc:
+                if getattr(exc, "status", 0) != L.ERR_UNSUPPORTED:      # a shape the tcgen05 conv does not tile: two-kernel form
+                    raise
+        if conv is None:
+            conv = ops.conv3x3_tokens(src, pk["conv_w"], shapes, impl=L.IMPL_AUTO if impl != L.IMPL_SIMT else L.IMPL_SIMT)
+            gn_stats = ops.groupnorm_stats(conv, shapes, groups=32)
         # self attention (:198) + norm1 (:199-200)
         # (with_pos_embed is folded into the query projection, norm1 into the output projection: msda.py)
         x = self.self_attn(src, reference_points, src, shapes, src_mask, query_pos=pos_embed,

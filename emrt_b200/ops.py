@@ -352,6 +352,23 @@ def conv3x3_tokens(x, w_packed, shapes, impl=L.IMPL_AUTO, out=None):
     return out
 
 
+def conv3x3_tokens_stats(x, w_packed, shapes, groups=32, out=None):
+    """conv3x3_tokens on the tcgen05 path + the GroupNorm(groups) statistics of its stored output from the same kernel's
+    epilogue -> (y, stats workspace: its first 2 * B * L * groups floats are the sums [B, L, groups, 2], as groupnorm_stats').
+    Raises EmrtError(UNSUPPORTED) for shapes the tcgen05 conv does not tile."""
+    B, Lv, C = x.shape
+    hw, _, total = level_tables(shapes)
+    assert total == Lv and x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(x)
+    lib = L.load()
+    st = torch.empty((int(lib.emrt_conv3x3_stats_workspace_floats(B, Lv, len(shapes))),), dtype=torch.float32, device=x.device)
+    with _Timed("conv3x3", (B * Lv, C, x.element_size())):
+        L.check(lib.emrt_conv3x3_tokens_stats_fwd(_ptr(x), _ptr(w_packed), _ptr(out), _ptr(st), B, Lv, C, len(shapes), hw,
+                                                  int(groups), _stream()))
+    return out, st
+
+
 def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, out=None, return_stats=False):
     """GELU(GroupNorm_l(conv)) + x per level; gamma / beta f32 [L, C].  return_stats: also the statistics workspace
     (its first 2 * B * L * groups floats are the (sum, sum of squares) the backward needs)."""

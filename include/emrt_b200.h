@@ -242,6 +242,14 @@ int emrt_pack_conv3x3_weight(const float* src, void* dst, int C, int level, int 
 int emrt_conv3x3_tokens_fwd(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L,
                             const int32_t* shapes_hw_host, int dtype, int w_dtype, int impl, void* stream);
 
+/* The same convolutions (BF16, tcgen05 path only) whose epilogue also leaves the GroupNorm(32) statistics of the stored
+ * output: stats_workspace F32 [emrt_conv3x3_stats_workspace_floats(B, Lv, L)], its first 2 * B * L * 32 floats the sums
+ * [B, L, 32, 2] that emrt_groupnorm_stats would compute (per-slab partial sums combined in a fixed order: bit-reproducible
+ * and independent of the batch a tile is processed in).  The separate statistics pass over the conv output disappears.  */
+long long emrt_conv3x3_stats_workspace_floats(int B, int Lv, int L);
+int emrt_conv3x3_tokens_stats_fwd(const void* x, const void* w_packed, void* y, float* stats_workspace, int B, int Lv, int C,
+                                  int L, const int32_t* shapes_hw_host, int groups, void* stream);
+
 /* y = GELU(GroupNorm_l(conv)) + x per level (GroupNorm(groups, C) eps, exact erf GELU, :187-189); conv, x, y
  * [B, Lv, C] (dtype F32|BF16); gamma, beta F32 [L, C]; stats_workspace F32
  * [emrt_groupnorm_workspace_floats(B, L, groups)] (scratch: sums, per-CTA partials, ticket counters — the statistics are

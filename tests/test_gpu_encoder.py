@@ -188,3 +188,30 @@ def test_encoder_bf16_two_layers_matches_oracle(cuda_dev, tile):
         assert own < OWN_TOL
         x_in = per_layer[i]
     assert_bf16_parity(got.float(), want, rounded, f"2-layer encoder, tile {tile}")
+
+
+@pytest.mark.parametrize("B,shapes", [(3, [(32, 32), (16, 16), (8, 8)]), (5, [(16, 32), (8, 16), (4, 8)]), (2, [(64, 64), (32, 32), (16, 16)])])
+def test_conv_epilogue_groupnorm_statistics(cuda_dev, B, shapes):
+    """emrt_conv3x3_tokens_stats_fwd: the same conv output bit for bit, and GroupNorm sums that equal the separate statistics
+    kernel's up to fp32 summation order (both sum the stored bf16 values) — single-CTA and CTA-pair forms."""
+    import os
+    rng = np.random.Generator(np.random.PCG64(B))
+    Lv = sum(h * w for h, w in shapes)
+    x = torch.from_numpy(O.rng_normal(rng, (B, Lv, 256))).to(cuda_dev).bfloat16()
+    ws = [torch.from_numpy(O.rng_uniform(rng, (256, 256, 3, 3), 0.05)).to(cuda_dev) for _ in shapes]
+    wp = ops.pack_conv3x3_weights(ws, torch.bfloat16)
+    want_y = ops.conv3x3_tokens(x, wp, shapes)
+    want_s = ops.groupnorm_stats(want_y, shapes, groups=32)[: 2 * B * len(shapes) * 32]
+    for one_cta in (False, True):
+        if one_cta:
+            os.environ["EMRT_CONV_1CTA"] = "1"
+        try:
+            y, st = ops.conv3x3_tokens_stats(x, wp, shapes)
+            y2, st2 = ops.conv3x3_tokens_stats(x, wp, shapes)
+        finally:
+            os.environ.pop("EMRT_CONV_1CTA", None)
+        assert torch.equal(y, want_y)
+        got_s = st[: 2 * B * len(shapes) * 32]
+        assert torch.equal(got_s, st2[: 2 * B * len(shapes) * 32])          # deterministic
+        scale = want_s.abs().max().item()
+        assert (got_s - want_s).abs().max().item() <= 2e-5 * scale
