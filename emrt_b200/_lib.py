@@ -41,6 +41,7 @@ class LinearArgs(C.Structure):
         ("x2", C.c_void_p), ("x2_period", C.c_int32),
         ("row_bias", C.c_void_p), ("row_bias_period", C.c_int32),
         ("gn", C.POINTER(GnBranch)),
+        ("x_nchw_hw", C.c_int32),
     ]
 
 

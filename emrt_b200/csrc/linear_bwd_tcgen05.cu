@@ -39,16 +39,6 @@ struct DwSmem {
   uint32_t tmem_base;
 };
 
-// MN-major SWIZZLE_128B descriptor: LBO = 8192 B (next 64-element block), SBO = 1024 B (next 8 reduction rows)
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 // kind::f16 instruction descriptor, D = f32, A = B = bf16, both operands MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

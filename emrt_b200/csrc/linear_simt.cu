@@ -153,6 +153,7 @@ extern "C" int emrt_linear_fwd(const emrt_linear_args* a, void* stream) {
   int impl = a->impl;
   if (impl == 0) impl = (a->x_dtype == EMRT_BF16 && a->w_dtype == EMRT_BF16 && a->w_transposed) ? 2 : 1;
   if (impl == 2) return linear_tcgen05(a, st);
+  if (a->x_nchw_hw > 0) return set_error(EMRT_ERR_UNSUPPORTED, "channel-major x (x_nchw_hw) is a tcgen05-path operand");
   return linear_simt(a, st);
 }
 

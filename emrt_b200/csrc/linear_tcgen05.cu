@@ -82,6 +82,7 @@ struct GemmParams {
   int32_t tiles_m, tiles_n;
   int32_t l2_prefetch;                   // row tiles of A requested into L2 ahead of the shared-memory ring (0 = off)
   int32_t debug;                         // timing experiments (wrong results): 1 = no output stores, 2 = empty epilogue
+  int32_t a_hw;                          // A_MN: pixels per image of the channel-major x [B, K, a_hw]
 };
 
 // Staged epilogue: every epilogue warp owns a 32-row staging tile that one TMA store drains.
@@ -124,7 +125,9 @@ struct TileWalk {
   }
 };
 
-template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST, bool ROWB>
+// A_MN: x is channel-major [B, K, hw] (NCHW): the A tile of a k-block is two TMA boxes {64 pixels, 64 channels} — the
+// canonical MN-major SWIZZLE_128B operand (make_smem_desc_mn), 16 channel rows per K = 16 step.
+template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST, bool ROWB, bool A_MN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
@@ -190,7 +193,11 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           const int kb = kk < num_kb ? kk : kk - num_kb;
           mbar_wait(&s.empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
-          if (kk < num_kb) tma_load_2d(s.a[stage], &p.tma_a, &s.full[stage], kb * BK, tw.m * BM);
+          if (A_MN) {
+            const int img = (int)(((int64_t)tw.m * BM) / p.a_hw), p0 = (int)((int64_t)tw.m * BM - (int64_t)img * p.a_hw);
+            tma_load_3d(s.a[stage], &p.tma_a, &s.full[stage], p0, kb * BK, img);
+            tma_load_3d(s.a[stage] + (BM / 2) * BK, &p.tma_a, &s.full[stage], p0 + BM / 2, kb * BK, img);
+          } else if (kk < num_kb) tma_load_2d(s.a[stage], &p.tma_a, &s.full[stage], kb * BK, tw.m * BM);
           else tma_load_2d(s.a[stage], &p.tma_a2, &s.full[stage], kb * BK, row2);
           if (!B_RES) tma_load_2d(s.b[stage], &p.tma_b, &s.full[stage], kb * BK, tw.n * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -200,7 +207,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(BM, BLOCK_N) | (A_MN ? (1u << 15) : 0u);     // bit 15: A is MN-major
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -216,12 +223,12 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           const int kb = kk < num_kb ? kk : kk - num_kb;
           mbar_wait(&s.full[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(s.a[stage]));
+          const uint64_t da = A_MN ? make_smem_desc_mn(smem_u32(s.a[stage])) : make_smem_desc(smem_u32(s.a[stage]));
           const uint64_t db = make_smem_desc(smem_u32(s.b[B_RES ? kb : stage]));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // +32 bytes (= 2 x 16 B) per K=16 step inside the 128-byte swizzle row
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kk | k) != 0 ? 1u : 0u);
+            // K-major: +32 bytes (= 2 x 16 B) per K=16 step inside the 128-byte swizzle row; MN-major: 16 rows x 128 B
+            umma_bf16(d_tmem, da + (uint64_t)((A_MN ? 128 : 2) * k), db + (uint64_t)(2 * k), idesc, (kk | k) != 0 ? 1u : 0u);
           }
           umma_commit(&s.empty[stage]);                     // frees the smem slot when these MMAs retire
           if (kk == total_kb - 1) umma_commit(&s.tmem_full[acc]);
@@ -557,12 +564,18 @@ static int make_tma_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST, bool ROWB = false>
+template <int BLOCK_N, int STAGES, int EPI, int GROUP, bool B_RES, bool TMA_ST, bool ROWB = false, bool A_MN = false>
 static int launch_tc(GemmParams& p, const emrt_linear_args* a, cudaStream_t st) {
   using Smem = GemmSmem<BLOCK_N, STAGES, B_RES, EPI, TMA_ST, ROWB>;
   constexpr int smem_bytes = (int)sizeof(Smem) + 1024;
   static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit of one CTA");
-  if (int e = make_tma_2d(&p.tma_a, a->x, (uint64_t)a->K, (uint64_t)a->rows, BM)) return e;
+  if (A_MN) {
+    const uint64_t hw = (uint64_t)a->x_nchw_hw;
+    const uint64_t d[3] = {hw, (uint64_t)a->K, (uint64_t)a->rows / hw}, sb[2] = {hw * 2, (uint64_t)a->K * hw * 2};
+    const uint32_t box[3] = {(uint32_t)(BM / 2), (uint32_t)BK, 1u};
+    if (int e = make_tensor_map(&p.tma_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->x, d, sb, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    p.a_hw = a->x_nchw_hw;
+  } else if (int e = make_tma_2d(&p.tma_a, a->x, (uint64_t)a->K, (uint64_t)a->rows, BM)) return e;
   if (int e = make_tma_2d(&p.tma_b, a->w, (uint64_t)a->K, (uint64_t)a->N, BLOCK_N)) return e;
   if (p.a2_period)
     if (int e = make_tma_2d(&p.tma_a2, a->x2, (uint64_t)a->K, (uint64_t)a->x2_period + BM - 1, BM)) return e;
@@ -594,7 +607,7 @@ static int launch_tc(GemmParams& p, const emrt_linear_args* a, cudaStream_t st) 
   p.tiles_n = (a->N + BLOCK_N - 1) / BLOCK_N;
   { const char* e = getenv("EMRT_GEMM_L2_PREFETCH"); p.l2_prefetch = e ? atoi(e) : 0; }
   { const char* e = getenv("EMRT_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; }
-  auto kern = linear_tcgen05_kernel<BLOCK_N, STAGES, EPI, GROUP, B_RES, TMA_ST, ROWB>;
+  auto kern = linear_tcgen05_kernel<BLOCK_N, STAGES, EPI, GROUP, B_RES, TMA_ST, ROWB, A_MN>;
   // function attributes are per device / context: set every time (cheap), not once per process
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid;
@@ -632,6 +645,8 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
     return set_error(EMRT_ERR_INVALID_ARGUMENT, "tcgen05 linear needs 16-byte aligned x, w, y");
   if (a->y_dtype != EMRT_F32 && a->y_dtype != EMRT_BF16 && a->y_dtype != EMRT_F16)
     return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad y_dtype %d", a->y_dtype);
+  if (a->x_nchw_hw > 0 && a->epilogue != 0)
+    return set_error(EMRT_ERR_UNSUPPORTED, "channel-major x (x_nchw_hw) takes a bias-only epilogue");
   if (a->epilogue & EMRT_EPI_RESIDUAL_LN) {
     if (a->epilogue != EMRT_EPI_RESIDUAL_LN || a->x2) return set_error(EMRT_ERR_UNSUPPORTED, "RESIDUAL_LN cannot be combined with other epilogues / x2");
     return linear_ln_tcgen05(a, st);
@@ -658,6 +673,12 @@ int linear_tcgen05(const emrt_linear_args* a, cudaStream_t st) {
     tma_st = tma_st && D == 32 && a->hm_rows % 32 == 0;
   }
   const bool res = a->K <= MAX_RES_KB * BK;
+  if (a->x_nchw_hw > 0) {
+    if (a->x_nchw_hw % BM != 0 || a->K % BK != 0 || a->rows % a->x_nchw_hw != 0 || a->epilogue != 0 || a->x2 || a->row_bias || a->N > 256)
+      return set_error(EMRT_ERR_UNSUPPORTED, "channel-major x needs H*W %% 128 == 0, K %% 64 == 0, N <= 256 and a bias-only epilogue");
+    if (res) return launch_tc<256, 4, EPI_KIND_GENERIC, 2, true, false, false, true>(p, a, st);
+    return launch_tc<256, 4, EPI_KIND_GENERIC, 2, false, false, false, true>(p, a, st);
+  }
   if (a->epilogue & EMRT_EPI_MSDA_QPROJ) {
     if (a->epilogue != EMRT_EPI_MSDA_QPROJ) return set_error(EMRT_ERR_UNSUPPORTED, "MSDA_QPROJ cannot be combined");
     if (a->N != 3 * 144) return set_error(EMRT_ERR_UNSUPPORTED, "MSDA_QPROJ epilogue is built for M*L*P = 144 (N = 432), got N=%d", a->N);

@@ -226,6 +226,7 @@ class EncoderDecoder(nn.Module):
         if len(backbone_num_channels) != num_feature_levels:
             raise L.EmrtError("extra stride-2 input_proj levels (t_e_d.py:380-387) are not used by EMRT and not built")
         self.hidden_dim, self.nhead, self.num_feature_levels = hidden_dim, nhead, num_feature_levels
+        self.input_proj_channel_major = True    # input_proj reads the NCHW maps directly (tests may force the transposed copy)
         self.encoder = TransformerEncoder(TransformerEncoderLayer(hidden_dim, nhead, dim_feedforward, dropout, activation,
                                                                   num_feature_levels, num_encoder_points), num_encoder_layers)
         self.decoder = TransformerDecoder(TransformerDecoderLayer(hidden_dim, nhead, dim_feedforward, dropout, activation,
@@ -281,8 +282,13 @@ class EncoderDecoder(nn.Module):
         src = torch.empty((B, Lv, self.hidden_dim), dtype=dtype, device=dev)
         off = 0
         for l, f in enumerate(src_feats):
-            tok = ops.nchw_to_tokens(f)
-            y = ops.linear(tok, c["w"][l], c["b"][l], w_transposed=fast, impl=L.IMPL_AUTO if fast else L.IMPL_SIMT)
+            hw = shapes[l][0] * shapes[l][1]
+            if fast and self.input_proj_channel_major and hw % 128 == 0 and f.shape[1] % 64 == 0 and f.is_contiguous():
+                # the 1x1 conv reads the NCHW feature map as it is (pixel-contiguous A operand): no transposed copy
+                y = ops.linear(f, c["w"][l], c["b"][l], w_transposed=True, x_nchw=True)
+            else:
+                tok = ops.nchw_to_tokens(f)
+                y = ops.linear(tok, c["w"][l], c["b"][l], w_transposed=fast, impl=L.IMPL_AUTO if fast else L.IMPL_SIMT)
             ops.groupnorm_tokens_into(y, c["gw"][l], c["gb"][l], src, off, groups=32)
             off += shapes[l][0] * shapes[l][1]
         return src, shapes, c

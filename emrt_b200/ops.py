@@ -131,14 +131,21 @@ def msda_gather_bwd(grad_out, value, loc, attn, shapes, ref=None, mode=L.LOC_NOR
 # ---- nn.Linear -----------------------------------------------------------------------------------------------
 def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_NONE, row_scale=None, residual=None,
            ln_gamma=None, ln_beta=None, ln_eps=1e-5, qproj_group=0, impl=L.IMPL_AUTO, out=None, out2=None, hm_rows=0,
-           hm_D=0, x2=None, x2_period=0, row_bias=None, row_bias_period=0, gn_branch=None):
+           hm_D=0, x2=None, x2_period=0, row_bias=None, row_bias_period=0, gn_branch=None, x_nchw=False):
     """y = epilogue((x + x2) @ W + bias).  x [..., K]; W [K,N] (Paddle layout) or [N,K] when w_transposed.
     x2 (optional, tcgen05 path): `cyclic_rows(addend, ...)` of a [x2_period, K] broadcast addend (with_pos_embed).
     gn_branch (EPI_RESIDUAL_LN only): dict(conv, skip, stats, gamma, beta, shapes, groups=32, eps=1e-5) — the encoder layer's
     conv branch GELU(GroupNorm_l(conv)) + skip added behind the LayerNorm inside the same epilogue."""
     lib = L.load()
-    K = x.shape[-1]
-    rows = x.numel() // K
+    if x_nchw:
+        # x [B, K, H, W] (or [B, K, hw]): the GEMM rows are the pixels, read channel-major by the tensor pipe (no transposed copy)
+        assert x.dim() >= 3 and x.is_contiguous()
+        K = x.shape[1]
+        hw = x.numel() // (x.shape[0] * K)
+        rows = x.shape[0] * hw
+    else:
+        K = x.shape[-1]
+        rows = x.numel() // K
     N = w.shape[0] if w_transposed else w.shape[1]
     assert (w.shape[1] if w_transposed else w.shape[0]) == K, "weight/in-feature mismatch"
     ydt = y_dtype if y_dtype is not None else x.dtype
@@ -149,7 +156,7 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
         if out2 is None:
             out2 = torch.empty((*x.shape[:-1], n_pts), dtype=ydt, device=x.device)
     elif out is None:
-        out = torch.empty((*x.shape[:-1], N), dtype=ydt, device=x.device)
+        out = torch.empty(((x.shape[0], hw, N) if x_nchw else (*x.shape[:-1], N)), dtype=ydt, device=x.device)
     a = L.LinearArgs()
     a.x, a.w, a.bias, a.y = _ptr(x), _ptr(w), _ptr(bias), _ptr(out)
     a.rows, a.K, a.N = rows, K, N
@@ -163,6 +170,7 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
     a.hm_rows, a.hm_D = int(hm_rows), int(hm_D)
     a.x2, a.x2_period = _ptr(x2), int(x2_period)
     a.row_bias, a.row_bias_period = _ptr(row_bias), int(row_bias_period)
+    a.x_nchw_hw = int(hw) if x_nchw else 0
     gnb = None
     if gn_branch is not None:
         gnb = L.GnBranch()

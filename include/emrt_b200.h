@@ -156,6 +156,11 @@ typedef struct emrt_linear_args {
    * epilogue — (x + pos) W + b = x W + (pos W + b) with no extra MMA work.  MSDA_QPROJ epilogue only.            */
   const void* row_bias; int32_t row_bias_period;
   const emrt_gn_branch* gn;   /* RESIDUAL_LN only; NULL = plain LayerNorm epilogue */
+  /* x given channel-major: x is [B, K, x_nchw_hw] (an NCHW feature map, x_nchw_hw = H * W pixels per image) and the GEMM
+   * row r = b * x_nchw_hw + pixel reads x[b, :, pixel] — the 1x1 convolutions of input_proj (t_e_d.py:417-419) without a
+   * transposed copy of the feature maps: the tensor pipe takes A pixel-contiguous (MN-major).  0 = x is [rows, K].
+   * tcgen05 path only; x_nchw_hw % 128 == 0, K % 64 == 0, bias-only epilogue.                                            */
+  int32_t x_nchw_hw;
 } emrt_linear_args;
 int emrt_linear_fwd(const emrt_linear_args* args, void* stream);
 

@@ -292,3 +292,24 @@ def test_encoder_layer_fused_equals_unfused(cuda_dev):
     e_f, e_u = l2_err(fused.float(), want), l2_err(unfused.float(), want)
     assert e_f < 1e-2 and e_u < 1e-2, (e_f, e_u)
     assert l2_err(fused.float(), unfused.float().cpu()) < 1e-2
+
+
+@pytest.mark.parametrize("B,C,H,W,N", [(3, 512, 16, 16, 256), (2, 1024, 16, 8, 256), (5, 2048, 8, 16, 256), (2, 256, 32, 32, 256),
+                                       (1, 128, 16, 16, 128)])
+def test_linear_reads_channel_major_feature_maps(cuda_dev, B, C, H, W, N):
+    """x_nchw: the 1x1 convolution of input_proj (t_e_d.py:417-419) as a GEMM whose A operand is the NCHW map itself
+    (MN-major tcgen05 operand) — bit-equal to transposing to tokens first: same products, same accumulation order."""
+    rng = np.random.Generator(np.random.PCG64(B * C + N))
+    f = torch.from_numpy(O.rng_normal(rng, (B, C, H, W))).to(cuda_dev).bfloat16()
+    w = torch.from_numpy(O.rng_uniform(rng, (C, N), (6.0 / (C + N)) ** 0.5)).to(cuda_dev)
+    b = torch.from_numpy(O.rng_uniform(rng, (N,), 0.1)).to(cuda_dev)
+    wp = torch.empty((N, C), dtype=torch.bfloat16, device=cuda_dev)
+    ops.pack_weight(w, wp)
+    want = ops.linear(ops.nchw_to_tokens(f), wp, b, w_transposed=True)
+    got = ops.linear(f, wp, b, w_transposed=True, x_nchw=True)
+    assert got.shape == want.shape == (B, H * W, N)
+    assert torch.equal(got, want)
+    ref = f.double().flatten(2).transpose(1, 2) @ wp.double().T + b.double()
+    assert rel_err(got.float(), ref.cpu()) < 8e-3
+    with pytest.raises(L.EmrtError):
+        ops.linear(f, wp, b, w_transposed=True, x_nchw=True, epilogue=L.EPI_RELU)
