@@ -198,8 +198,11 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), EMRT_BF16);
         if (STATS) {
-          // four groups of eight channels in this chunk; sums of the ROUNDED values (what GroupNorm will read back), the 32
-          // pixels of the slab combined by a fixed xor tree: deterministic
+          // four groups of eight channels in this chunk: (sum, sum of squares) of the ROUNDED values (what GroupNorm reads
+          // back), eight numbers per lane.  Reduced over the slab's 32 pixels by recursive halving — exchange half of the
+          // numbers with lane ^ 16, half of the rest with ^ 8, then ^ 4, then two plain butterfly steps: 9 shuffles instead
+          // of 40, a fixed tree (deterministic); lane 4 k ends up holding number k.
+          float v8[8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float sm = 0.f, sq = 0.f;
@@ -209,14 +212,26 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
               sm += a + b;
               sq = fmaf(a, a, fmaf(b, b, sq));
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-              sm += __shfl_xor_sync(0xffffffffu, sm, off);
-              sq += __shfl_xor_sync(0xffffffffu, sq, off);
-            }
-            if (lane == 0)
-              *reinterpret_cast<float2*>(p.gn_partial + (((size_t)t * 4 + q) * 32 + (half * HALF_N + cc) / 8 + g) * 2) = make_float2(sm, sq);
+            v8[2 * g] = sm;
+            v8[2 * g + 1] = sq;
           }
+          float v4[4], v2[2];
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float mine = h16 ? v8[4 + i] : v8[i], other = h16 ? v8[i] : v8[4 + i];
+            v4[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float mine = h8 ? v4[2 + i] : v4[i], other = h8 ? v4[i] : v4[2 + i];
+            v2[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+          }
+          float v1 = (h4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? v2[0] : v2[1], 4);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+          if ((lane & 3) == 0)      // number k = lane / 4: group k / 2 of the chunk, component k % 2
+            p.gn_partial[(((size_t)t * 4 + q) * 32 + (half * HALF_N + cc) / 8) * 2 + (lane >> 2)] = v1;
         }
         if (lane == 0) tma_store_wait_read();
         __syncwarp();

@@ -42,6 +42,8 @@ with torch.no_grad():
                                 ln_beta=lp["n2b"], gn_branch=dict(conv=conv, skip=src, stats=stats, gamma=lp["gn_w"], beta=lp["gn_b"], shapes=shapes))
     elif what == "conv":
         fn = lambda: ops.conv3x3_tokens(src, lp["conv_w"], shapes)
+    elif what == "convs":
+        fn = lambda: ops.conv3x3_tokens_stats(src, lp["conv_w"], shapes)
     elif what == "ffn":
         conv = torch.randn((B, Lv, 256), generator=g, device=dev).bfloat16()
         stats = ops.groupnorm_stats(conv, shapes, groups=32)
