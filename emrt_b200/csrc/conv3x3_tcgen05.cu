@@ -262,25 +262,32 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
   }
 }
 
-// stats[b][l][g] = (sum, sum of squares) over the (image, level)'s slabs, in tile / slab order
-__global__ void conv_gn_finalize_kernel(const __grid_constant__ ConvParams p, float* __restrict__ stats, int B) {
-  const int bl = blockIdx.x, l = bl % p.L, b = bl / p.L, g = threadIdx.x;
-  float sm = 0.f, sq = 0.f;
-  int tile0, ntiles, q0, nq;
+// stats[b][l][g] = (sum, sum of squares) over the (image, level)'s slabs.  One CTA per (image, level): thread (g, part) adds
+// slabs part, part + 8, ... in order, the eight parts are then combined in order: a fixed tree, so the sums do not depend on
+// scheduling or on the batch (a serial walk over the up to 128 slabs by one thread per group took 20 us of load latency).
+__global__ void __launch_bounds__(256) conv_gn_finalize_kernel(const __grid_constant__ ConvParams p, float* __restrict__ stats) {
+  const int bl = blockIdx.x, l = bl % p.L, b = bl / p.L, g = threadIdx.x & 31, part = threadIdx.x >> 5;
+  int slab0, nslab;                                   // slabs are numbered tile * 4 + lane quarter
   if (p.tiles_per_img[l] > 0) {
-    tile0 = p.tile_start[l] + b * p.tiles_per_img[l]; ntiles = p.tiles_per_img[l]; q0 = 0; nq = 4;
+    slab0 = (p.tile_start[l] + b * p.tiles_per_img[l]) * 4; nslab = p.tiles_per_img[l] * 4;
   } else {
-    const int slabs = p.HW[l] / 32;                 // 32-pixel slabs per image (HW < 128: 1 or 2)
-    tile0 = p.tile_start[l] + b / p.imgs_per_tile[l]; ntiles = 1; q0 = (b % p.imgs_per_tile[l]) * slabs; nq = slabs;
+    const int slabs = p.HW[l] / 32;                   // 32-pixel slabs per image (HW < 128: 1 or 2)
+    slab0 = (p.tile_start[l] + b / p.imgs_per_tile[l]) * 4 + (b % p.imgs_per_tile[l]) * slabs; nslab = slabs;
   }
-  for (int t = tile0; t < tile0 + ntiles; ++t)
-    for (int q = q0; q < q0 + nq; ++q) {
-      const float2 v = *reinterpret_cast<const float2*>(p.gn_partial + (((size_t)t * 4 + q) * 32 + g) * 2);
-      sm += v.x;
-      sq += v.y;
-    }
-  *reinterpret_cast<float2*>(stats + ((size_t)(b * p.L + l) * 32 + g) * 2) = make_float2(sm, sq);
-  (void)B;
+  float sm = 0.f, sq = 0.f;
+  for (int i = part; i < nslab; i += 8) {
+    const float2 v = *reinterpret_cast<const float2*>(p.gn_partial + ((size_t)(slab0 + i) * 32 + g) * 2);
+    sm += v.x;
+    sq += v.y;
+  }
+  __shared__ float2 sh[8][32];
+  sh[part][g] = make_float2(sm, sq);
+  __syncthreads();
+  if (part == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { sm += sh[k][g].x; sq += sh[k][g].y; }
+    *reinterpret_cast<float2*>(stats + ((size_t)(b * p.L + l) * 32 + g) * 2) = make_float2(sm, sq);
+  }
 }
 
 template <int CG, bool STATS>
@@ -358,7 +365,7 @@ int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int L
   if ((int64_t)tiles * 256 + 2LL * B * L * 32 > conv3x3_stats_workspace_floats(B, Lv, L)) return EMRT_ERR_UNSUPPORTED;
   p.gn_partial = stats_ws + 2LL * B * L * 32;
   if (int e = pair ? launch_conv<2, true>(p, tiles, st) : launch_conv<1, true>(p, tiles, st)) return e;
-  conv_gn_finalize_kernel<<<B * L, 32, 0, st>>>(p, stats_ws, B);
+  conv_gn_finalize_kernel<<<B * L, 256, 0, st>>>(p, stats_ws);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
 }
