@@ -466,8 +466,11 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       const uint32_t t_y = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Y_COL + col0);
       const uint32_t t_xp = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(XP_COL + col0 / 2);
 
-      // ---- pass 1: x = bf16(acc + bias + residual) parked in TMEM as packed pairs; row sum of the rounded values --------
-      float sum = 0.f;
+      // ---- pass 1: x = bf16(acc + bias + residual) parked in TMEM as packed pairs; shifted sums of the rounded values ----
+      // (sum and sum of squares of x - shift, shift = the thread's first element: one pass gives the mean and the centred
+      // second moment without the cancellation of E[x^2] - mean^2; the two column halves are merged with Chan's formula.
+      // The earlier separate variance pass re-read the parked row: 64 KB of TMEM reads per tile on a port the H warps need.)
+      float sum = 0.f, sum2 = 0.f, shift = 0.f;
 #pragma unroll 1
       for (int c = 0; c < LCHUNKS; ++c) {
         uint32_t r[16];
@@ -493,7 +496,10 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
             const float x1 = __uint_as_float(r[j + 1]) + bias[2 * i + 1] + bf16_hi(w[i]);
             const uint32_t pk = pack_bf16x2(x0, x1);
             o[h * 4 + i] = pk;
-            sum += bf16_lo(pk) + bf16_hi(pk);
+            if (c == 0 && h == 0 && i == 0) shift = bf16_lo(pk);
+            const float d0 = bf16_lo(pk) - shift, d1 = bf16_hi(pk) - shift;
+            sum += d0 + d1;
+            sum2 = fmaf(d0, d0, fmaf(d1, d1, sum2));
           }
         }
         TMEM_ST_X8(t_xp + c * (LCH / 2), o);
@@ -512,28 +518,21 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         if (lane == 0 && mp + num_clusters < npairs) for (int c = 0; c < LN_BUFS; ++c) load_res((mp + num_clusters) * CG + (int)rank, c);
         continue;
       }
-      s.xch[0][half][row] = sum;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      const float mean = (s.xch[0][0][row] + s.xch[0][1][row]) * (1.f / DM);
-      tmem_wait_st();
-
-      // ---- pass 2: centred second moment of the parked row --------------------------------------------------
-      float sq = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < LN_COLS / 2; c += 32) {
-        uint32_t r[32];
-        TMEM_LD_X32(t_xp + c, r);
-        TMEM_WAIT_X32(r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d0 = bf16_lo(r[j]) - mean, d1 = bf16_hi(r[j]) - mean;
-          sq = fmaf(d0, d0, sq);
-          sq = fmaf(d1, d1, sq);
-        }
+      // this half: mean_h and M2_h = sum (x - mean_h)^2 over its 128 columns; merge the two halves
+      {
+        const float mh = shift + sum * (1.f / LN_COLS);
+        s.xch[0][half][row] = mh;
+        s.xch[1][half][row] = sum2 - sum * sum * (1.f / LN_COLS);
       }
-      s.xch[1][half][row] = sq;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      const float rstd = rsqrtf((s.xch[1][0][row] + s.xch[1][1][row]) * (1.f / DM) + p.eps);
+      const float ma = s.xch[0][0][row], mb = s.xch[0][1][row];
+      const float mean = 0.5f * (ma + mb);
+      const float m2 = s.xch[1][0][row] + s.xch[1][1][row] + (ma - mb) * (ma - mb) * (0.5f * LN_COLS);
+      const float rstd = rsqrtf(fmaxf(m2, 0.f) * (1.f / DM) + p.eps);
+      tmem_wait_st();
+      // (the next tile's pass 1 may not overwrite xch before the partner has read it: both warps of the pair pass this
+      // point again — the barrier below — only after their reads)
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
 
       // ---- pass 3: normalise (+ conv branch), round, stage, TMA store ------------------------------------------
       int gl = 0;
