@@ -110,3 +110,17 @@ def test_ffn_fused_rejects_what_it_is_not_built_for(cuda_dev):
     v = torch.zeros((128,), dtype=torch.float32, device=cuda_dev)
     with pytest.raises(L.EmrtError):
         ops.ffn_fused(x, w1, v[:64].contiguous(), w2, v, v, v)
+
+
+def test_ffn_fused_single_cta_form_equals_cta_pair_form(cuda_dev, monkeypatch):
+    """EMRT_FFN_1CTA=1 (cta_group::1, one CTA per row tile) and the default CTA-pair form (cta_group::2) run the same
+    arithmetic in the same order per output element: bit-equal."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    case = make_case(rng, cuda_dev, 7, [(16, 16), (8, 8), (4, 4)], 1024, True)      # 2352 rows: an odd number of tiles (19)
+    args = (case["x"], case["w1p"], case["b1"], case["w2p"], case["b2"], case["g"], case["bt"])
+    pair = ops.ffn_fused(*args, gn_branch=case["gn"])
+    monkeypatch.setenv("EMRT_FFN_1CTA", "1")
+    single = ops.ffn_fused(*args, gn_branch=case["gn"])
+    monkeypatch.delenv("EMRT_FFN_1CTA")
+    assert torch.equal(pair, single)
+    assert l2_err(pair.float(), reference(case)) < 3e-3
