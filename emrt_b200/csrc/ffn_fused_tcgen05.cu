@@ -80,7 +80,7 @@ struct FfnParams {
   int32_t L, Lv, B;
   LevelTable lv;
   int32_t tiles_m, num_chunks;
-  int32_t debug;         // timing experiments (wrong results): 1 = LN warps stop after pass 1
+  int32_t debug;         // timing experiments (wrong results): 1 = LN warps stop after pass 1, 4 = no conv / skip loads and no stores
   long long* prof;       // EMRT_FFN_PROF: per CTA, cycles the MMA thread spent waiting on each barrier kind
 };
 
@@ -224,9 +224,12 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       uint32_t wph = 0, xph = 0;
       const uint32_t L_x_full = leader_addr<CG>(&s.x_full);
       auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
+      long long t_pw = 0;
+      const long long t_p0 = clock64();
       auto load_w1 = [&](int c) {            // four units: this CTA's [128 / CG hidden x 64 k] boxes of chunk c
         for (int kb = 0; kb < DM / BK; ++kb) {
-          mbar_wait(&s.w_empty[ws], wph ^ 1);
+          if (p.prof) { const long long t0_ = clock64(); mbar_wait(&s.w_empty[ws], wph ^ 1); t_pw += clock64() - t0_; }
+          else mbar_wait(&s.w_empty[ws], wph ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&s.w_full[ws], CG * W_UNIT_BYTES);
           // the unit holds this CTA's B rows of the chunk's two 64-unit halves, half a first: the pair's CTAs split each half
           // (rows [32 r, +32) of it each), so that a half's 64 hidden units stay contiguous across the pair
@@ -240,8 +243,8 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         }
       };
       auto load_w2 = [&](int j) {            // two adjacent units (ws is even here): this CTA's [256 / CG out x 64 k] box of k-block j
-        mbar_wait(&s.w_empty[ws], wph ^ 1);
-        mbar_wait(&s.w_empty[ws + 1], wph ^ 1);
+        if (p.prof) { const long long t0_ = clock64(); mbar_wait(&s.w_empty[ws], wph ^ 1); mbar_wait(&s.w_empty[ws + 1], wph ^ 1); t_pw += clock64() - t0_; }
+        else { mbar_wait(&s.w_empty[ws], wph ^ 1); mbar_wait(&s.w_empty[ws + 1], wph ^ 1); }
         if (rank == 0) {
           mbar_arrive_expect_tx(&s.w_full[ws], CG * 2 * W_UNIT_BYTES);
           mbar_arrive(&s.w_full[ws + 1]);    // the second unit's barrier only keeps its phase in step
@@ -250,20 +253,29 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         advance();
         advance();
       };
-      for (int mp = cluster_id; mp < npairs; mp += num_clusters) {
+      auto load_x = [&](int mp) {
         const int m = mp * CG + (int)rank;
         mbar_wait(&s.x_empty, xph ^ 1);      // the previous tile's last GEMM1 has read x
         xph ^= 1;
         if (rank == 0) mbar_arrive_expect_tx(&s.x_full, (uint32_t)(CG * BM * DM * 2));
 #pragma unroll
         for (int kb = 0; kb < DM / BK; ++kb) tma_load_2d_lead<CG>(s.x[kb], &p.tma_x, L_x_full, kb * BK, m * BM);
+      };
+      // The weight units form one stream across tiles (ring order = MMA order).  The NEXT tile's x is requested inside this
+      // tile's last chunk — right where its buffer frees (the last GEMM1) — so that the wait for it does not hold back the
+      // next tile's first weight units: with the x wait at the top of the tile the issuing thread idled ~5 k clocks per tile
+      // pair on weights that could have been in flight (EMRT_FFN_PROF).
+      if (cluster_id < npairs) load_x(cluster_id);
+      for (int mp = cluster_id; mp < npairs; mp += num_clusters) {
         load_w1(0);
         for (int c = 0; c < NC; ++c) {
           if (c + 1 < NC) load_w1(c + 1);
+          if (c == NC - 1 && mp + num_clusters < npairs) load_x(mp + num_clusters);
           load_w2(2 * c);
           load_w2(2 * c + 1);
         }
       }
+      if (p.prof && rank == 0) { p.prof[(size_t)blockIdx.x * 8 + 6] = t_pw; p.prof[(size_t)blockIdx.x * 8 + 7] = clock64() - t_p0; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -511,7 +523,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       __syncwarp();
       if (lane == 0) {
         arrive_leader<CG>(L_y_empty);
-        if (GN && !(p.debug & 1)) { load_gn(m, 0); load_gn(m, 1); }     // every buffer is free: two (conv, skip) pairs
+        if (GN && !(p.debug & 5)) { load_gn(m, 0); load_gn(m, 1); }     // every buffer is free: two (conv, skip) pairs
       }
       if (p.debug & 1) {
         __syncwarp();
@@ -557,7 +569,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         // read its buffer, chunk c + 1 is requested there — a whole step ahead of its use
         if (GN && lane == 0 && c >= 1 && c + 1 < LCHUNKS) {
           tma_store_wait_read();
-          load_gn(m, c + 1);
+          if (!(p.debug & 4)) load_gn(m, c + 1);
         }
         if (!GN && c >= LN_BUFS) {          // the store of chunk c - 4 has drained this buffer
           if (lane == 0) tma_store_wait_read_n<LN_BUFS - 1>();
@@ -566,7 +578,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         const uint32_t sb = lb0 + (uint32_t)bi * LBUF_BYTES + my_row;
         uint4 cv[2] = {}, sk[2] = {};
         if (GN) {
-          wait_buf(bi);
+          if (!(p.debug & 4)) wait_buf(bi);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             cv[h] = lds128(sb + ((((uint32_t)h) ^ swz) << 4));
@@ -614,8 +626,10 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&p.tma_y, lb0 + (uint32_t)bi * LBUF_BYTES, cc, row0);
-          tma_store_commit();
+          if (!(p.debug & 4)) {
+            tma_store_2d(&p.tma_y, lb0 + (uint32_t)bi * LBUF_BYTES, cc, row0);
+            tma_store_commit();
+          }
         }
       }
       __syncwarp();
@@ -671,10 +685,10 @@ int launch_ffn(FfnParams& p, cudaStream_t st) {
     std::vector<long long> h((size_t)grid * 8);
     EMRT_CUDA_CHECK(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(d);
-    double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < grid; i += CG) for (int k = 0; k < 6; ++k) a[k] += (double)h[(size_t)i * 8 + k] / (grid / CG);
-    fprintf(stderr, "ffn_fused MMA thread, cycles per CTA (avg of %d): total %.0f | wait x %.0f, weights %.0f, hacc_empty %.0f, hs_full %.0f, y_empty %.0f | tiles/CTA %.1f\n",
-            grid, a[0], a[1], a[2], a[3], a[4], a[5], (double)p.tiles_m / grid);
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < grid; i += CG) for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)i * 8 + k] / (grid / CG);
+    fprintf(stderr, "ffn_fused MMA thread, cycles per CTA (avg of %d): total %.0f | wait x %.0f, weights %.0f, hacc_empty %.0f, hs_full %.0f, y_empty %.0f | tiles/CTA %.1f | producer: total %.0f, waiting for a free ring unit %.0f\n",
+            grid, a[0], a[1], a[2], a[3], a[4], a[5], (double)p.tiles_m / grid, a[7], a[6]);
     count_launch();
     return EMRT_OK;
   }
