@@ -43,7 +43,7 @@ int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const vo
 namespace {
 
 constexpr int BM = 128, BK = 64, DM = 256, CH = 128, UMMA_K = 16;
-constexpr int H_WARP0 = 2, NUM_H_WARPS = 4, LN_WARP0 = 6, NUM_LN_WARPS = 8;
+constexpr int NUM_H_WARPS = 4, LN_WARP0 = 6, NUM_LN_WARPS = 8;      // warps 0 / 1: TMA producer / MMA issuer, 2..5: H, 6..13: LN
 constexpr int NUM_THREADS = 32 * (LN_WARP0 + NUM_LN_WARPS);
 constexpr int TMEM_COLS = 512, Y_COL = 0, HACC_COL = 256, XP_COL = 384;
 // weight ring (96 KB): units of one [128 / CG rows x 64 k] bf16 box — a W1 k-block of this CTA's share of the chunk; a W2

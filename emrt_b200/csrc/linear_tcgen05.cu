@@ -442,6 +442,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         // the output type is kernel-uniform: both forms are compiled, one warp-uniform branch picks
         auto finish = [&](auto f16_tag) {
           constexpr bool F16 = decltype(f16_tag)::value;
+          (void)F16;                           // (unused in the direct-store instantiations)
           if (tw.n < 2) {
             if constexpr (TMA_ST) {
               uint32_t o[HALF_N / 2];
@@ -470,6 +471,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             // softmax over each group of GROUP consecutive logits (t_e_d.py:92-96); this thread's half row lives in
             // registers (static indexing).  exp(v - max) = ex2(v * log2e - max * log2e): one FFMA + one MUFU per logit.
             uint32_t o[HALF_N / 2];
+            (void)o;
 #pragma unroll
             for (int g = 0; g < HALF_N / GROUP; ++g) {
               float v[GROUP];
