@@ -140,6 +140,38 @@ __device__ __forceinline__ float gelu_erf(float h) {
   return h >= 0.f ? h - hh : hh;
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction and lane) ---------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2_t pk2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void upk2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// gelu_erf of two values, the same operations in the same order (bit-equal per element), 21 instructions per pair instead of 34
+__device__ __forceinline__ f32x2_t gelu_erf2(f32x2_t h) {
+  float h0, h1;
+  upk2(h, h0, h1);
+  const f32x2_t z = pk2(fabsf(h0) * 0.70710678118654752f, fabsf(h1) * 0.70710678118654752f);
+  float d0, d1, t0, t1, a0, a1, e0, e1;
+  upk2(fma2(pk2(0.3275911f), z, pk2(1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  upk2(mul2(z, mul2(z, pk2(-1.4426950408889634f))), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2_t t = pk2(t0, t1);
+  f32x2_t p = fma2(t, pk2(1.061405429f), pk2(-1.453152027f));
+  p = fma2(t, p, pk2(1.421413741f));
+  p = fma2(t, p, pk2(-0.284496736f));
+  p = fma2(t, p, pk2(0.254829592f));
+  float r0, r1;
+  upk2(mul2(h, mul2(mul2(mul2(pk2(0.5f), p), t), pk2(e0, e1))), r0, r1);          // h * erfc(z) / 2
+  return pk2(h0 >= 0.f ? h0 - r0 : r0, h1 >= 0.f ? h1 - r1 : r1);
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int num_sms() {
   // per device ordinal (a process may drive several GPUs); benign race: every thread writes the same value

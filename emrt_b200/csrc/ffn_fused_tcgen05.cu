@@ -121,6 +121,11 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t pack_relu_pair(f32x2_t v) {
+  float a, b;
+  upk2(v, a, b);
+  return pack_relu_bf16x2(a, b);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
@@ -413,14 +418,14 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = kk == 0 ? bias[j] : __ldg(b1v + 16 + j);
-            o[2 * j] = pack_relu_bf16x2(__uint_as_float(ra[4 * j]) + bb.x, __uint_as_float(ra[4 * j + 1]) + bb.y);
-            o[2 * j + 1] = pack_relu_bf16x2(__uint_as_float(ra[4 * j + 2]) + bb.z, __uint_as_float(ra[4 * j + 3]) + bb.w);
+            o[2 * j] = pack_relu_pair(add2(pk2(__uint_as_float(ra[4 * j]), __uint_as_float(ra[4 * j + 1])), pk2(bb.x, bb.y)));
+            o[2 * j + 1] = pack_relu_pair(add2(pk2(__uint_as_float(ra[4 * j + 2]), __uint_as_float(ra[4 * j + 3])), pk2(bb.z, bb.w)));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = __ldg(b1v + kk * 16 + 8 + j);
-            o[16 + 2 * j] = pack_relu_bf16x2(__uint_as_float(rb[4 * j]) + bb.x, __uint_as_float(rb[4 * j + 1]) + bb.y);
-            o[16 + 2 * j + 1] = pack_relu_bf16x2(__uint_as_float(rb[4 * j + 2]) + bb.z, __uint_as_float(rb[4 * j + 3]) + bb.w);
+            o[16 + 2 * j] = pack_relu_pair(add2(pk2(__uint_as_float(rb[4 * j]), __uint_as_float(rb[4 * j + 1])), pk2(bb.x, bb.y)));
+            o[16 + 2 * j + 1] = pack_relu_pair(add2(pk2(__uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3])), pk2(bb.z, bb.w)));
           }
           // slot kk has been used cg times before: the GEMM2 of its previous use (k-block kk of chunk cg - 1) is done
           mbar_wait(&s.hs_empty[kk], (cg & 1u) ^ 1u);
@@ -482,7 +487,8 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       // (sum and sum of squares of x - shift, shift = the thread's first element: one pass gives the mean and the centred
       // second moment without the cancellation of E[x^2] - mean^2; the two column halves are merged with Chan's formula.
       // The earlier separate variance pass re-read the parked row: 64 KB of TMEM reads per tile on a port the H warps need.)
-      float sum = 0.f, sum2 = 0.f, shift = 0.f;
+      float shift = 0.f;
+      f32x2_t sum_p = pk2(0.f), sum2_p = pk2(0.f);      // (even columns, odd columns): combined after the loop
 #pragma unroll 1
       for (int c = 0; c < LCHUNKS; ++c) {
         uint32_t r[16];
@@ -504,14 +510,15 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j = h * 8 + 2 * i;
-            const float x0 = __uint_as_float(r[j]) + bias[2 * i] + bf16_lo(w[i]);
-            const float x1 = __uint_as_float(r[j + 1]) + bias[2 * i + 1] + bf16_hi(w[i]);
+            float x0, x1;
+            upk2(add2(add2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pk2(bias[2 * i], bias[2 * i + 1])),
+                      pk2(bf16_lo(w[i]), bf16_hi(w[i]))), x0, x1);
             const uint32_t pk = pack_bf16x2(x0, x1);
             o[h * 4 + i] = pk;
             if (c == 0 && h == 0 && i == 0) shift = bf16_lo(pk);
-            const float d0 = bf16_lo(pk) - shift, d1 = bf16_hi(pk) - shift;
-            sum += d0 + d1;
-            sum2 = fmaf(d0, d0, fmaf(d1, d1, sum2));
+            const f32x2_t d = sub2(pk2(bf16_lo(pk), bf16_hi(pk)), pk2(shift));
+            sum_p = add2(sum_p, d);
+            sum2_p = fma2(d, d, sum2_p);
           }
         }
         TMEM_ST_X8(t_xp + c * (LCH / 2), o);
@@ -531,6 +538,14 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         continue;
       }
       // this half: mean_h and M2_h = sum (x - mean_h)^2 over its 128 columns; merge the two halves
+      float sum, sum2;
+      {
+        float a0, a1, b0, b1;
+        upk2(sum_p, a0, a1);
+        upk2(sum2_p, b0, b1);
+        sum = a0 + a1;
+        sum2 = b0 + b1;
+      }
       {
         const float mh = shift + sum * (1.f / LN_COLS);
         s.xch[0][half][row] = mh;
@@ -610,15 +625,20 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
             gb[0] = c0.x; gb[1] = c0.y; gb[2] = c0.z; gb[3] = c0.w; gb[4] = c1.x; gb[5] = c1.y; gb[6] = c1.z; gb[7] = c1.w;
           }
           const uint32_t cw[4] = {cv[h].x, cv[h].y, cv[h].z, cv[h].w}, sw[4] = {sk[h].x, sk[h].y, sk[h].z, sk[h].w};
+          // two columns per instruction (FFMA2 / FMUL2 / FADD2): the LN warps' instruction count is what they cost the
+          // H warps and the issuing warp, so it is worth halving
+          const f32x2_t mean2 = pk2(mean), rstd2 = pk2(rstd), gmean2 = pk2(gmean), grstd2 = pk2(grstd);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t xw = r[h * 4 + i];
-            float y0 = (bf16_lo(xw) - mean) * rstd * ga[2 * i] + be[2 * i];
-            float y1 = (bf16_hi(xw) - mean) * rstd * ga[2 * i + 1] + be[2 * i + 1];
+            f32x2_t y = fma2(mul2(sub2(pk2(bf16_lo(xw), bf16_hi(xw)), mean2), rstd2), pk2(ga[2 * i], ga[2 * i + 1]), pk2(be[2 * i], be[2 * i + 1]));
             if (GN) {
-              y0 += gelu_erf(fmaf(bf16_lo(cw[i]) - gmean, grstd * gg[2 * i], gb[2 * i])) + bf16_lo(sw[i]);
-              y1 += gelu_erf(fmaf(bf16_hi(cw[i]) - gmean, grstd * gg[2 * i + 1], gb[2 * i + 1])) + bf16_hi(sw[i]);
+              const f32x2_t u = fma2(sub2(pk2(bf16_lo(cw[i]), bf16_hi(cw[i])), gmean2), mul2(grstd2, pk2(gg[2 * i], gg[2 * i + 1])),
+                                     pk2(gb[2 * i], gb[2 * i + 1]));
+              y = add2(y, add2(gelu_erf2(u), pk2(bf16_lo(sw[i]), bf16_hi(sw[i]))));
             }
+            float y0, y1;
+            upk2(y, y0, y1);
             o[i] = pack_bf16x2(y0, y1);
           }
           sts128(sb + ((((uint32_t)h) ^ swz) << 4), o[0], o[1], o[2], o[3]);
