@@ -205,15 +205,18 @@ conv3x3_tokens_tc_kernel(const __grid_constant__ ConvParams p) {
           float v8[8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float sm = 0.f, sq = 0.f;
+            f32x2_t sm2 = pk2(0.f), sq2 = pk2(0.f);            // (even channels, odd channels): FADD2 / FFMA2
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float a = __uint_as_float(o[g * 4 + i] << 16), b = __uint_as_float(o[g * 4 + i] & 0xffff0000u);
-              sm += a + b;
-              sq = fmaf(a, a, fmaf(b, b, sq));
+              const f32x2_t d = pk2(__uint_as_float(o[g * 4 + i] << 16), __uint_as_float(o[g * 4 + i] & 0xffff0000u));
+              sm2 = add2(sm2, d);
+              sq2 = fma2(d, d, sq2);
             }
-            v8[2 * g] = sm;
-            v8[2 * g + 1] = sq;
+            float a0, a1, b0, b1;
+            upk2(sm2, a0, a1);
+            upk2(sq2, b0, b1);
+            v8[2 * g] = a0 + a1;
+            v8[2 * g + 1] = b0 + b1;
           }
           float v4[4], v2[2];
           const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
