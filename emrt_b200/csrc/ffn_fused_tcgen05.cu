@@ -82,6 +82,7 @@ struct FfnParams {
   int32_t tiles_m, num_chunks;
   int32_t debug;         // timing experiments (wrong results): 1 = LN warps stop after pass 1, 4 = no conv / skip loads and no stores
   long long* prof;       // EMRT_FFN_PROF: per CTA, cycles the MMA thread spent waiting on each barrier kind
+  long long* prof_w;     // ... and the weight waits split: first W1 unit of a chunk / other W1 units / W2 units
 };
 
 template <int CG>
@@ -231,18 +232,30 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
       long long t_pw = 0;
       const long long t_p0 = clock64();
-      auto load_w1 = [&](int c) {            // four units: this CTA's [128 / CG hidden x 64 k] boxes of chunk c
+      // four units: this CTA's [128 / CG hidden x 64 k] boxes of chunk c.  ONE full barrier for the chunk (its first unit's,
+      // armed with the bytes of all four): every barrier the issuing warp has to poll costs it ~80 clocks even when the
+      // data is long there, and twelve polls per chunk were a fifth of its time (EMRT_FFN_PROF)
+      auto load_w1 = [&](int c) {
+        const int ws0 = ws;
+        const uint32_t wph0 = wph;
         for (int kb = 0; kb < DM / BK; ++kb) {
           if (p.prof) { const long long t0_ = clock64(); mbar_wait(&s.w_empty[ws], wph ^ 1); t_pw += clock64() - t0_; }
           else mbar_wait(&s.w_empty[ws], wph ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(&s.w_full[ws], CG * W_UNIT_BYTES);
+          advance();
+        }
+        ws = ws0;
+        wph = wph0;
+        const uint32_t lead = leader_addr<CG>(&s.w_full[ws0]);
+        if (rank == 0) mbar_arrive_expect_tx(&s.w_full[ws0], CG * (DM / BK) * W_UNIT_BYTES);
+        for (int kb = 0; kb < DM / BK; ++kb) {
+          if (rank == 0 && kb > 0) mbar_arrive(&s.w_full[ws]);        // keeps the unit's barrier phase in step
           // the unit holds this CTA's B rows of the chunk's two 64-unit halves, half a first: the pair's CTAs split each half
           // (rows [32 r, +32) of it each), so that a half's 64 hidden units stay contiguous across the pair
           if (CG == 2) {
-            tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH + (int)rank * 32);
-            tma_load_2d_lead<CG>(s.w[ws] + W_UNIT_BYTES / 2, &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH + 64 + (int)rank * 32);
+            tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, lead, kb * BK, c * CH + (int)rank * 32);
+            tma_load_2d_lead<CG>(s.w[ws] + W_UNIT_BYTES / 2, &p.tma_w1, lead, kb * BK, c * CH + 64 + (int)rank * 32);
           } else {
-            tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, leader_addr<CG>(&s.w_full[ws]), kb * BK, c * CH);
+            tma_load_2d_lead<CG>(s.w[ws], &p.tma_w1, lead, kb * BK, c * CH);
           }
           advance();
         }
@@ -293,7 +306,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       int ws = 0;
       uint32_t wph = 0, xph = 0, yph = 0, hacc_e = 0;
       uint32_t jg = 0;                        // hidden k-blocks consumed so far (runs across tiles): hs slot = jg & 1
-      long long t_x = 0, t_w = 0, t_hacc = 0, t_hs = 0, t_y = 0;
+      long long t_x = 0, t_w = 0, t_hacc = 0, t_hs = 0, t_y = 0, t_w1a = 0, t_w2 = 0;
       const long long t_begin = clock64();
 #define PROF_WAIT(acc, ...) do { if (p.prof) { const long long t0_ = clock64(); __VA_ARGS__; acc += clock64() - t0_; } else { __VA_ARGS__; } } while (0)
       auto advance = [&]() { if (++ws == W_UNITS) { ws = 0; wph ^= 1; } };
@@ -321,7 +334,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
             wph = wph0;
 #pragma unroll
             for (int kb = 0; kb < DM / BK; ++kb) {
-              if (hf == 0) { PROF_WAIT(t_w, wait_lead_line(CG, &s.w_full[ws], wph)); tc_fence_after(); }
+              if (hf == 0 && kb == 0) { PROF_WAIT(t_w1a, wait_lead_line(CG, &s.w_full[ws], wph)); tc_fence_after(); }   // one barrier per chunk
               const uint64_t da = desc_of(x_base + (uint32_t)kb * (BM * BK * 2));
               const uint64_t db = desc_of(w_base + (uint32_t)ws * W_UNIT_BYTES + (uint32_t)hf * HALF_B_BYTES);
               if (elect_one()) {
@@ -348,8 +361,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
             PROF_WAIT(t_y, wait_lead_line(CG, &s.y_empty, yph ^ 1));
             yph ^= 1;
           }
-          PROF_WAIT(t_w, wait_lead_line(CG, &s.w_full[ws], wph));
-          PROF_WAIT(t_w, wait_lead_line(CG, &s.w_full[ws + 1], wph));
+          PROF_WAIT(t_w2, wait_lead_line(CG, &s.w_full[ws], wph));       // (the pair's second barrier only keeps its phase)
           tc_fence_after();
           const uint64_t da = desc_of(hs_base + slot * (uint32_t)(BM * BK * 2));
           const uint64_t db = desc_of(w_base + (uint32_t)ws * W_UNIT_BYTES);
@@ -377,7 +389,8 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       }
       if (p.prof && lane == 0) {
         long long* o = p.prof + (size_t)blockIdx.x * 8;
-        o[0] = clock64() - t_begin; o[1] = t_x; o[2] = t_w; o[3] = t_hacc; o[4] = t_hs; o[5] = t_y;
+        o[0] = clock64() - t_begin; o[1] = t_x; o[2] = t_w + t_w1a + t_w2; o[3] = t_hacc; o[4] = t_hs; o[5] = t_y;
+        if (p.prof_w) { p.prof_w[(size_t)blockIdx.x * 4] = t_w1a; p.prof_w[(size_t)blockIdx.x * 4 + 1] = t_w; p.prof_w[(size_t)blockIdx.x * 4 + 2] = t_w2; }
       }
 #undef PROF_WAIT
     }
@@ -700,10 +713,20 @@ int launch_ffn(FfnParams& p, cudaStream_t st) {
     EMRT_CUDA_CHECK(cudaMalloc(&d, (size_t)grid * 8 * sizeof(long long)));
     EMRT_CUDA_CHECK(cudaMemset(d, 0, (size_t)grid * 8 * sizeof(long long)));
     p.prof = d;
+    long long* dw = nullptr;
+    EMRT_CUDA_CHECK(cudaMalloc(&dw, (size_t)grid * 4 * sizeof(long long)));
+    EMRT_CUDA_CHECK(cudaMemset(dw, 0, (size_t)grid * 4 * sizeof(long long)));
+    p.prof_w = dw;
     EMRT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
     EMRT_CUDA_CHECK(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)grid * 8);
     EMRT_CUDA_CHECK(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    std::vector<long long> hw((size_t)grid * 4);
+    EMRT_CUDA_CHECK(cudaMemcpy(hw.data(), dw, hw.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(dw);
+    double w3[3] = {0, 0, 0};
+    for (int i = 0; i < grid; i += CG) for (int k = 0; k < 3; ++k) w3[k] += (double)hw[(size_t)i * 4 + k] / (grid / CG);
+    fprintf(stderr, "ffn_fused weight waits: first W1 unit of a chunk %.0f, other W1 units %.0f, W2 units %.0f\n", w3[0], w3[1], w3[2]);
     cudaFree(d);
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < grid; i += CG) for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)i * 8 + k] / (grid / CG);
