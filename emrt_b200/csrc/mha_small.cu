@@ -29,17 +29,29 @@ __device__ __forceinline__ float mha_dot(const float (&qv)[D], const float* __re
 template <typename T, int D>
 __global__ void __launch_bounds__(MHA_WARPS * 32)
 mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k, int64_t k_ld, const T* __restrict__ v,
-                 int64_t v_ld, T* __restrict__ out, int Lq, int Lk, int M, float scale) {
+                 int64_t v_ld, T* __restrict__ out, int Lq, int Lk, int M, float scale, bool vec_io) {
   extern __shared__ __align__(16) float sm[];
   float* ks = sm;                 // [Lk][D]
   float* vs = sm + Lk * D;        // [Lk][D]
   const int m = blockIdx.x % M;
   const int64_t b = blockIdx.x / M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < Lk * D; i += blockDim.x) {
-    const int kk = i / D, d = i - kk * D;
-    ks[i] = to_float(k[(b * Lk + kk) * k_ld + m * D + d]);
-    vs[i] = to_float(v[(b * Lk + kk) * v_ld + m * D + d]);
+  if (vec_io) {
+    constexpr int VEC = Vec16<T>::N;
+    for (int i = threadIdx.x * VEC; i < Lk * D; i += blockDim.x * VEC) {
+      const int kk = i / D, d = i - kk * D;
+      float tk[VEC], tv[VEC];
+      Vec16<T>::load(k + (b * Lk + kk) * k_ld + m * D + d, tk);
+      Vec16<T>::load(v + (b * Lk + kk) * v_ld + m * D + d, tv);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { ks[i + j] = tk[j]; vs[i + j] = tv[j]; }
+    }
+  } else {
+    for (int i = threadIdx.x; i < Lk * D; i += blockDim.x) {
+      const int kk = i / D, d = i - kk * D;
+      ks[i] = to_float(k[(b * Lk + kk) * k_ld + m * D + d]);
+      vs[i] = to_float(v[(b * Lk + kk) * v_ld + m * D + d]);
+    }
   }
   __syncthreads();
   for (int q0 = (blockIdx.y * MHA_WARPS + warp) * 32; q0 < Lq; q0 += 32 * MHA_WARPS * gridDim.y) {
@@ -47,8 +59,21 @@ mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k,
     const bool valid = qi < Lq;
     const T* qrow = q + (b * Lq + (valid ? qi : Lq - 1)) * q_ld + m * D;
     float qv[D];
+    // a lane's query row is 32 contiguous values: 16-byte loads (every lane another row — element-wise loads cost 32
+    // wavefronts each, 1024 per warp for the row; the alignment of the row is checked on the host)
+    if (vec_io) {
+      constexpr int VEC = Vec16<T>::N;
 #pragma unroll
-    for (int d = 0; d < D; ++d) qv[d] = to_float(qrow[d]) * scale;           // (q k^T) * D^-0.5
+      for (int d = 0; d < D; d += VEC) {
+        float t[VEC];
+        Vec16<T>::load(qrow + d, t);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) qv[d + k] = t[k] * scale;               // (q k^T) * D^-0.5
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) qv[d] = to_float(qrow[d]) * scale;
+    }
     float mx = -INFINITY;
 #pragma unroll 2
     for (int kk = 0; kk < Lk; ++kk) mx = fmaxf(mx, mha_dot<D>(qv, ks + kk * D));
@@ -70,8 +95,19 @@ mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k,
     if (valid) {
       const float inv = 1.f / sum;
       T* orow = out + (b * Lq + qi) * (int64_t)(M * D) + m * D;
+      if (vec_io) {
+        constexpr int VEC = Vec16<T>::N;
 #pragma unroll
-      for (int d = 0; d < D; ++d) orow[d] = from_float<T>(acc[d] * inv);
+        for (int d = 0; d < D; d += VEC) {
+          float t[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) t[k] = acc[d + k] * inv;
+          Vec16<T>::store(orow + d, t);
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) orow[d] = from_float<T>(acc[d] * inv);
+      }
     }
   }
 }
@@ -93,10 +129,15 @@ extern "C" int emrt_mha_small(const void* q, int64_t q_ld, const void* k, int64_
   // one CTA (4 warps x 32 queries) per (batch, head) and 128 queries
   const int splits = (Lq + 32 * MHA_WARPS - 1) / (32 * MHA_WARPS);
   const dim3 grid((unsigned)(B * M), (unsigned)splits);
+  // 16-byte accesses need 16-byte aligned rows: base pointers and row strides (elements) multiples of 16 bytes
+  const int esz = dtype == EMRT_F32 ? 4 : 2;
+  const bool vec_io = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                        reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                      ((q_ld | k_ld | v_ld) * esz) % 16 == 0 && ((int64_t)M * D * esz) % 16 == 0;
   if (dtype == EMRT_F32)
-    mha_small_kernel<float, 32><<<grid, MHA_WARPS * 32, smem, st>>>((const float*)q, q_ld, (const float*)k, k_ld, (const float*)v, v_ld, (float*)out, Lq, Lk, M, scale);
+    mha_small_kernel<float, 32><<<grid, MHA_WARPS * 32, smem, st>>>((const float*)q, q_ld, (const float*)k, k_ld, (const float*)v, v_ld, (float*)out, Lq, Lk, M, scale, vec_io);
   else if (dtype == EMRT_BF16)
-    mha_small_kernel<__nv_bfloat16, 32><<<grid, MHA_WARPS * 32, smem, st>>>((const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)k, k_ld, (const __nv_bfloat16*)v, v_ld, (__nv_bfloat16*)out, Lq, Lk, M, scale);
+    mha_small_kernel<__nv_bfloat16, 32><<<grid, MHA_WARPS * 32, smem, st>>>((const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)k, k_ld, (const __nv_bfloat16*)v, v_ld, (__nv_bfloat16*)out, Lq, Lk, M, scale, vec_io);
   else return set_error(EMRT_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;
