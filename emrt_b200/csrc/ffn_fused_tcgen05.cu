@@ -328,29 +328,32 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             PROF_WAIT(t_hacc, wait_lead_line(CG, &s.hacc_empty[hf], hacc_e ^ 1u));   // the H warps have read this half of the previous chunk
+            if (hf == 0) PROF_WAIT(t_w1a, wait_lead_line(CG, &s.w_full[ws0], wph0));      // one barrier for the chunk's four units
             tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)(HACC_COL + hf * 64);
-            ws = ws0;
-            wph = wph0;
+            // one elected block for the half's sixteen MMAs (nothing to wait for between the chunk's four units any more):
+            // at N = 64 an MMA is 32 tensor clocks, so every instruction between two of them counts
+            if (elect_one()) {
+              int u = ws0;
 #pragma unroll
-            for (int kb = 0; kb < DM / BK; ++kb) {
-              if (hf == 0 && kb == 0) { PROF_WAIT(t_w1a, wait_lead_line(CG, &s.w_full[ws], wph)); tc_fence_after(); }   // one barrier per chunk
-              const uint64_t da = desc_of(x_base + (uint32_t)kb * (BM * BK * 2));
-              const uint64_t db = desc_of(w_base + (uint32_t)ws * W_UNIT_BYTES + (uint32_t)hf * HALF_B_BYTES);
-              if (elect_one()) {
+              for (int kb = 0; kb < DM / BK; ++kb) {
+                const uint64_t da = desc_of(x_base + (uint32_t)kb * (BM * BK * 2));
+                const uint64_t db = desc_of(w_base + (uint32_t)u * W_UNIT_BYTES + (uint32_t)hf * HALF_B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k)
                   umma_cg<CG>(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
-                if (hf == 1) commit_cg<CG>(&s.w_empty[ws]);
-                if (kb == DM / BK - 1) {
-                  commit_cg<CG>(&s.hacc_full[hf]);
-                  if (hf == 1 && c == NC - 1) commit_cg<CG>(&s.x_empty);
-                }
+                if (hf == 1) commit_cg<CG>(&s.w_empty[u]);
+                if (++u == W_UNITS) u = 0;
               }
-              __syncwarp();
-              advance();
+              commit_cg<CG>(&s.hacc_full[hf]);
+              if (hf == 1 && c == NC - 1) commit_cg<CG>(&s.x_empty);
             }
+            __syncwarp();
           }
+          ws = ws0;
+          wph = wph0;
+#pragma unroll
+          for (int kb = 0; kb < DM / BK; ++kb) advance();
           hacc_e ^= 1u;
         };
         auto g2 = [&](int j) {                 // hidden k-block j of this tile: y += h[:, 64 j .. +64] @ W2[:, 64 j .. +64]^T
