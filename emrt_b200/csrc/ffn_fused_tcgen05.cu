@@ -83,6 +83,7 @@ struct FfnParams {
   int32_t debug;         // timing experiments (wrong results): 1 = LN warps stop after pass 1, 4 = no conv / skip loads and no stores
   long long* prof;       // EMRT_FFN_PROF: per CTA, cycles the MMA thread spent waiting on each barrier kind
   long long* prof_w;     // ... and the weight waits split: first W1 unit of a chunk / other W1 units / W2 units
+  long long* prof_ln;    // ... and LN warp 0 of each CTA: waiting for y_full / pass 1 / merge of the halves / pass 3
 };
 
 template <int CG>
@@ -493,8 +494,10 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       const int m = mp * CG + (int)rank;
       const int row = q * 32 + lane;
       const int row0 = m * BM + q * 32;
+      const long long tl0 = p.prof_ln ? clock64() : 0;
       mbar_wait(&s.y_full, yph);
       yph ^= 1;
+      const long long tl1 = p.prof_ln ? clock64() : 0;
       tc_fence_after();
       const uint32_t t_y = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Y_COL + col0);
       const uint32_t t_xp = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(XP_COL + col0 / 2);
@@ -544,6 +547,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       // this warp's half of y has been read completely: when all eight have, the next tile's GEMM2 may overwrite it
       tc_fence_before();
       __syncwarp();
+      const long long tl2 = p.prof_ln ? clock64() : 0;
       if (lane == 0) {
         arrive_leader<CG>(L_y_empty);
         if (GN && !(p.debug & 5)) { load_gn(m, 0); load_gn(m, 1); }     // every buffer is free: two (conv, skip) pairs
@@ -577,6 +581,7 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
       // point again — the barrier below — only after their reads)
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
 
+      const long long tl3 = p.prof_ln ? clock64() : 0;
       // ---- pass 3: normalise (+ conv branch), round, stage, TMA store ------------------------------------------
       int gl = 0;
       const float* gst = nullptr;
@@ -669,6 +674,10 @@ ffn_fused_tcgen05_kernel(const __grid_constant__ FfnParams p) {
         }
       }
       __syncwarp();
+      if (p.prof_ln && lw == 0 && lane == 0) {
+        long long* o = p.prof_ln + (size_t)blockIdx.x * 4;
+        o[0] += tl1 - tl0; o[1] += tl2 - tl1; o[2] += tl3 - tl2; o[3] += clock64() - tl3;
+      }
       if (lane == 0) {
         // the next tile's first four residual chunks, as soon as the stores have drained
         if (mp + num_clusters < npairs) {
@@ -720,6 +729,10 @@ int launch_ffn(FfnParams& p, cudaStream_t st) {
     EMRT_CUDA_CHECK(cudaMalloc(&dw, (size_t)grid * 4 * sizeof(long long)));
     EMRT_CUDA_CHECK(cudaMemset(dw, 0, (size_t)grid * 4 * sizeof(long long)));
     p.prof_w = dw;
+    long long* dl = nullptr;
+    EMRT_CUDA_CHECK(cudaMalloc(&dl, (size_t)grid * 4 * sizeof(long long)));
+    EMRT_CUDA_CHECK(cudaMemset(dl, 0, (size_t)grid * 4 * sizeof(long long)));
+    p.prof_ln = dl;
     EMRT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
     EMRT_CUDA_CHECK(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)grid * 8);
@@ -727,6 +740,14 @@ int launch_ffn(FfnParams& p, cudaStream_t st) {
     std::vector<long long> hw((size_t)grid * 4);
     EMRT_CUDA_CHECK(cudaMemcpy(hw.data(), dw, hw.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(dw);
+    {
+      std::vector<long long> hl((size_t)grid * 4);
+      EMRT_CUDA_CHECK(cudaMemcpy(hl.data(), dl, hl.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(dl);
+      double l4[4] = {0, 0, 0, 0};
+      for (int i = 0; i < grid; ++i) for (int k = 0; k < 4; ++k) l4[k] += (double)hl[(size_t)i * 4 + k] / grid;
+      fprintf(stderr, "ffn_fused LN warp 0, cycles per CTA: waiting for y_full %.0f, pass 1 %.0f, merge %.0f, pass 3 %.0f\n", l4[0], l4[1], l4[2], l4[3]);
+    }
     double w3[3] = {0, 0, 0};
     for (int i = 0; i < grid; i += CG) for (int k = 0; k < 3; ++k) w3[k] += (double)hw[(size_t)i * 4 + k] / (grid / CG);
     fprintf(stderr, "ffn_fused weight waits: first W1 unit of a chunk %.0f, other W1 units %.0f, W2 units %.0f\n", w3[0], w3[1], w3[2]);
