@@ -558,6 +558,10 @@ def run_ours(args):
             rows_, K_, N_, sx, sy = dims
             key = f"linear rows={rows_} K={K_} N={N_}"
             flops, byts = 2.0 * rows_ * K_ * N_, rows_ * (K_ * sx + N_ * sy) + K_ * N_ * sx
+        elif name == "linear_ln" and dims[0] == B * Lv:
+            rows_, K_, N_, sx, sy = dims
+            key = f"linear + residual + LayerNorm rows={rows_} K={K_} N={N_} (output_proj + norm1)"
+            flops, byts = 2.0 * rows_ * K_ * N_, rows_ * (K_ * sx + 2 * N_ * sy) + K_ * N_ * sx      # x and the residual in, y out
         elif name == "ffn_fused" and dims[0] == B * Lv:
             rows_, C_, F_, sx = dims
             key = f"ffn_fused rows={rows_} d_model={C_} d_ff={F_} (linear1 + ReLU + linear2 + residual + norm2 + conv branch)"

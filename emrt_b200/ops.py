@@ -186,7 +186,7 @@ def linear(x, w, bias=None, *, w_transposed=False, y_dtype=None, epilogue=L.EPI_
         assert row_bias.dtype == torch.float16 and row_bias.shape[-1] == N and row_bias.numel() // N >= row_bias_period + 127
     if x2 is not None:
         assert x2.dtype == torch.bfloat16 and x2.shape[-1] == K and x2.numel() // K >= x2_period + 127
-    with _Timed("linear", (rows, K, N, x.element_size(), out.element_size())):
+    with _Timed("linear_ln" if (epilogue & L.EPI_RESIDUAL_LN) else "linear", (rows, K, N, x.element_size(), out.element_size())):
         L.check(lib.emrt_linear_fwd(C.byref(a), _stream()))
     return (out, out2) if (epilogue & L.EPI_MSDA_QPROJ) else out
 
@@ -711,7 +711,9 @@ def msda_fused_fwd(query, value, ref, shapes, M, P, weights, *, mask=None, query
         kernel_events.append(("linear", (B * Lv, C_, C_, es, es), (evs[0], evs[1])))
         kernel_events.append(("linear", (B * Lq, C_, 3 * tp, es, 2), (evs[2], evs[3])))
         kernel_events.append(("msda_gather_fwd", (B, Lq, Lv, M, C_ // M, nL, P, es, 2), (evs[4], evs[5])))
-        kernel_events.append(("linear", (B * Lq, C_, C_, es, es), (evs[6], evs[7])))
+        # the output projection carries residual + LayerNorm in its epilogue when residual_norm is given: its own row (it
+        # also reads the residual), not one more sample of the plain K = N = C projection
+        kernel_events.append(("linear_ln" if residual_norm is not None else "linear", (B * Lq, C_, C_, es, es), (evs[6], evs[7])))
     return out, _Keep(a, keep + [scratch, ws, out, evs])
 
 
