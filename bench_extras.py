@@ -207,7 +207,8 @@ def tiles256(dev, rank, world, total=64, nc=6):
 def gather_sensitivity(dev, B=72):
     """Encoder-gather time (CUDA events around the launch, 4 launches each) against the spread of the sampling offsets:
     sigma = std of sampling_offsets.weight (the data-dependent part; the bench's weights use 0.05), and with the
-    window-centre hint off.  The window-staged kernel reads samples outside its staged window from global memory."""
+    window-centre hint off.  The window-staged kernel reads samples outside its staged window from global memory; the last
+    row is the L1-path kernel a model with wide offsets would select (MSDeformableAttention.window_gather = False)."""
     import emrt_b200
     from emrt_b200 import ops, synthetic, _lib as L
     shapes = synthetic.level_shapes(TILE)
@@ -217,8 +218,9 @@ def gather_sensitivity(dev, B=72):
     pos = torch.randn((1, Lv, 256), generator=g, device=dev).bfloat16()
     ref = emrt_b200.get_reference_points(shapes, device=dev)
     rows = []
-    for sigma, hint in ((0.05, True), (0.15, True), (0.3, True), (0.05, False)):
+    for sigma, hint, window in ((0.05, True, True), (0.15, True, True), (0.3, True, True), (0.05, False, True), (0.3, True, False)):
         m = emrt_b200.MSDeformableAttention(256, 8, 3, 6).to(dev)
+        m.window_gather = window                  # False: the L1-path kernel, whose time does not depend on the spread
         with torch.no_grad():
             for name, arr in synthetic.msda_state(1234, offset_std=sigma).items():
                 mod, leaf = name.split(".")
@@ -238,5 +240,6 @@ def gather_sensitivity(dev, B=72):
         finally:
             os.environ.pop("EMRT_WIN_NO_HINT", None)
         t = [e[0].elapsed_time(e[1]) for (name, dims, e) in ev if name == "msda_gather_fwd"]
-        rows.append({"offset_weight_sigma": sigma, "hint": hint, "gather_ms": sum(t) / len(t)})
+        rows.append({"offset_weight_sigma": sigma, "hint": hint, "kernel": "window-staged" if window else "l1-path (window_gather=False)",
+                     "gather_ms": sum(t) / len(t)})
     return rows

@@ -260,6 +260,13 @@ class MSDeformableAttention(nn.Module):
         self.output_proj = PaddleLinear(embed_dim, embed_dim)
         self.lr_mult = lr_mult
         self.gemm_impl = L.IMPL_AUTO      # tests may force L.IMPL_SIMT / L.IMPL_TCGEN05
+        # Encoder self-attention (queries = the pyramid's own pixels) runs on the window-staged gather kernels, whose time
+        # depends on how far the samples stray from their reference points: 0.67 ms per call at the bench geometry while
+        # they stay inside the staged windows, 1.2 - 2.1 ms once the offsets have a spread of several pixels (the outliers
+        # are read from global memory one by one).  The L1-path kernel is flat at 1.0 ms (profiles/r3q_gather_sensitivity.txt);
+        # a model whose trained offsets are that wide sets this to False.  Either way within the bf16 tolerance of the reference
+        # (3.5e-3 relative L2 between the two: the window kernels carry bf16 tap weights).
+        self.window_gather = True
         self.head_major = True            # bf16 path: value_proj writes [B,M,Lv,D] for the specialised gather
         self._packed = None
         self._reset_parameters()
@@ -376,7 +383,7 @@ class MSDeformableAttention(nn.Module):
                                         or any(p.requires_grad for p in self.parameters())):
             mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
             ref32 = reference_points.float().contiguous()        # differentiable: the decoder trains its reference points
-            grid = is_pixel_grid(reference_points, shapes, Len_q, Len_v)
+            grid = self.window_gather and is_pixel_grid(reference_points, shapes, Len_q, Len_v)
             if query_pos is not None:
                 query = query + query_pos.to(query.dtype)
             out = _MSDAFunction.apply(self, query, ref32, value, mask, shapes, grid,
@@ -429,7 +436,7 @@ class MSDeformableAttention(nn.Module):
                     x2, x2_period = ops.cyclic_rows_cached(query_pos), Len_q
             else:
                 query = ops.add_bcast(query, query_pos.to(query.dtype).contiguous())
-        grid = is_pixel_grid(ref, shapes, Len_q, value.shape[1])
+        grid = self.window_gather and is_pixel_grid(ref, shapes, Len_q, value.shape[1])
         return ops.msda_fused_fwd(query, value, ref32, shapes, M, P, pk, mask=mask, query_pos=x2, query_pos_rows=x2_period,
                                   row_bias=rowb, residual_norm=residual_norm, pixel_grid=grid,
                                   win_center=pk["win_center"] if grid else None, keep_pixel_major=not self.head_major)[0]
@@ -486,7 +493,7 @@ class MSDeformableAttention(nn.Module):
             attn = attn.view(bs, Len_q, M, self.num_levels, P)
         if head_major:
             # encoder self-attention (queries = the pyramid's own pixels): window-staged kernel
-            grid = L.QUERY_PIXEL_GRID if is_pixel_grid(ref, shapes, Len_q, value.shape[1]) else 0
+            grid = L.QUERY_PIXEL_GRID if (self.window_gather and is_pixel_grid(ref, shapes, Len_q, value.shape[1])) else 0
             out = ops.msda_gather_fwd(v.view(bs, M, -1, D), off_px, attn, shapes, ref=ref32,
                                       mode=L.LOC_PIXEL_OFFSET | L.VALUE_HEAD_MAJOR | grid,
                                       win_center=pk["win_center"] if grid else None)

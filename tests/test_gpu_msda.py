@@ -604,3 +604,30 @@ def test_linear_bwd_weight(cuda_dev, rows, K, N, dtype):
         finally:
             del os.environ["EMRT_DW_SIMT"]
         assert rel_err(dw2, want_w) < tol
+
+
+def test_module_window_gather_switch(cuda_dev):
+    """MSDeformableAttention.window_gather = False takes the encoder self-attention through the L1-path gather (flat time,
+    for models whose sampling offsets stray far from their reference points) instead of the window-staged kernels: same
+    module output up to fp32 summation order, here with offsets wide enough (sigma 0.3) to leave the staged windows."""
+    from emrt_b200 import synthetic
+    shapes = synthetic.level_shapes(256)
+    Lv = sum(h * w for h, w in shapes)
+    g = torch.Generator(device=cuda_dev).manual_seed(11)
+    src = torch.randn((2, Lv, 256), generator=g, device=cuda_dev).bfloat16()
+    pos = torch.randn((1, Lv, 256), generator=g, device=cuda_dev).bfloat16()
+    ref = emrt_b200.get_reference_points(shapes, device=cuda_dev)
+    m = emrt_b200.MSDeformableAttention(256, 8, 3, 6).to(cuda_dev)
+    with torch.no_grad():
+        for name, arr in synthetic.msda_state(1234, offset_std=0.3).items():
+            mod, leaf = name.split(".")
+            getattr(getattr(m, mod), leaf).copy_(torch.from_numpy(arr))
+    m.requires_grad_(False)
+    assert m.window_gather is True
+    with torch.no_grad():
+        win = m(src, ref, src, shapes, query_pos=pos)
+        m.window_gather = False
+        l1 = m(src, ref, src, shapes, query_pos=pos)
+    assert win.dtype == torch.bfloat16 and torch.isfinite(win.float()).all()
+    d = (win.float() - l1.float()).norm() / win.float().norm()
+    assert d.item() < 6e-3, d.item()
