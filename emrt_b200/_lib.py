@@ -70,6 +70,7 @@ class MsdaArgs(C.Structure):
         ("dtype", C.c_int32), ("flags", C.c_int32), ("keep_pixel_major", C.c_int32),
         ("window_center", C.POINTER(C.c_int32)),
         ("timing_events", C.c_void_p * 8),
+        ("gather_start_event", C.c_void_p),
     ]
 
 
@@ -113,6 +114,7 @@ SIGNATURES = {
     "emrt_conv3x3_tokens_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I32P, _I, _I, _I, _P]),
     "emrt_conv3x3_stats_workspace_floats": (C.c_longlong, [_I, _I, _I]),
     "emrt_conv3x3_tokens_stats_fwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I32P, _I, _P]),
+    "emrt_conv3x3_tokens_stats_part_fwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I32P, _I, _I, _P]),
     "emrt_groupnorm_gelu_residual": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_float, _I32P, _I, _P]),
     "emrt_groupnorm_stats": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I32P, _I, _P]),
     "emrt_groupnorm_workspace_floats": (C.c_longlong, [_I, _I, _I]),

@@ -294,12 +294,15 @@ __global__ void __launch_bounds__(256) conv_gn_finalize_kernel(const __grid_cons
 }
 
 template <int CG, bool STATS>
-static int launch_conv(const ConvParams& p, int tiles, cudaStream_t st) {
+static int launch_conv(const ConvParams& p, int tiles, cudaStream_t st, int max_ctas) {
   const int smem_bytes = (int)sizeof(ConvSmem<CG>) + 1024;
   auto kern = conv3x3_tokens_tc_kernel<CG, STATS>;
   // per launch: function attributes are per context (a second GPU in the same process needs its own opt-in) and this is cheap
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = tiles < num_sms() ? tiles : num_sms();
+  // a caller that runs this kernel beside another one (second stream) leaves the other SMs to it: the tile loop is persistent,
+  // any grid size walks all tiles (profiles/r3t_conv_gather_overlap.txt)
+  if (max_ctas >= CG && max_ctas < grid) grid = max_ctas;
   grid = grid / CG * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -321,7 +324,7 @@ static int launch_conv(const ConvParams& p, int tiles, cudaStream_t st) {
 int64_t conv3x3_stats_workspace_floats(int B, int Lv, int L) { return 2LL * B * L * 32 + ((int64_t)B * Lv / CV_BM + (int64_t)B * L + L) * 256; }
 
 int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L, const LevelTable& lv,
-                      cudaStream_t st, float* stats_ws) {
+                      cudaStream_t st, float* stats_ws, int max_ctas) {
   if (C != CV_N || L > CV_MAX_L) return EMRT_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(y)) & 15) return EMRT_ERR_UNSUPPORTED;
   ConvParams p;
@@ -364,10 +367,10 @@ int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int L
   for (int l = 0; l <= L; ++l) pair = pair && (p.tile_start[l] % 2 == 0);
   const uint32_t bw[2] = {(uint32_t)CV_BK, (uint32_t)(pair ? CV_N / 2 : CV_N)};
   if (int e = make_tensor_map(&p.tma_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  if (!stats_ws) return pair ? launch_conv<2, false>(p, tiles, st) : launch_conv<1, false>(p, tiles, st);
+  if (!stats_ws) return pair ? launch_conv<2, false>(p, tiles, st, max_ctas) : launch_conv<1, false>(p, tiles, st, max_ctas);
   if ((int64_t)tiles * 256 + 2LL * B * L * 32 > conv3x3_stats_workspace_floats(B, Lv, L)) return EMRT_ERR_UNSUPPORTED;
   p.gn_partial = stats_ws + 2LL * B * L * 32;
-  if (int e = pair ? launch_conv<2, true>(p, tiles, st) : launch_conv<1, true>(p, tiles, st)) return e;
+  if (int e = pair ? launch_conv<2, true>(p, tiles, st, max_ctas) : launch_conv<1, true>(p, tiles, st, max_ctas)) return e;
   conv_gn_finalize_kernel<<<B * L, 256, 0, st>>>(p, stats_ws);
   EMRT_LAUNCH_CHECK();
   return EMRT_OK;

@@ -472,7 +472,7 @@ using namespace emrt;
 namespace emrt {
 int64_t conv3x3_stats_workspace_floats(int B, int Lv, int L);
 int conv3x3_tokens_tc(const void* x, const void* w_packed, void* y, int B, int Lv, int C, int L, const LevelTable& lv,
-                      cudaStream_t st, float* stats_ws = nullptr);
+                      cudaStream_t st, float* stats_ws = nullptr, int max_ctas = 0);
 }
 
 static int launch_residual_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
@@ -597,11 +597,17 @@ extern "C" long long emrt_conv3x3_stats_workspace_floats(int B, int Lv, int L) {
 
 extern "C" int emrt_conv3x3_tokens_stats_fwd(const void* x, const void* w_packed, void* y, float* stats_workspace, int B, int Lv,
                                              int C, int L, const int32_t* shapes_hw_host, int groups, void* stream) {
-  EMRT_REQUIRE(x && w_packed && y && stats_workspace && B > 0 && C > 0, "bad conv3x3_tokens_stats arguments");
+  return emrt_conv3x3_tokens_stats_part_fwd(x, w_packed, y, stats_workspace, B, Lv, C, L, shapes_hw_host, groups, 0, stream);
+}
+
+extern "C" int emrt_conv3x3_tokens_stats_part_fwd(const void* x, const void* w_packed, void* y, float* stats_workspace, int B,
+                                                  int Lv, int C, int L, const int32_t* shapes_hw_host, int groups, int max_ctas,
+                                                  void* stream) {
+  EMRT_REQUIRE(x && w_packed && y && stats_workspace && B > 0 && C > 0 && max_ctas >= 0, "bad conv3x3_tokens_stats arguments");
   if (groups != 32 || C != 256) return set_error(EMRT_ERR_UNSUPPORTED, "conv3x3 + GroupNorm statistics is built for C = 256, 32 groups");
   LevelTable lv;
   if (int e = fill_levels(lv, L, shapes_hw_host, nullptr, Lv)) return e;
-  const int e = conv3x3_tokens_tc(x, w_packed, y, B, Lv, C, L, lv, as_stream(stream), stats_workspace);
+  const int e = conv3x3_tokens_tc(x, w_packed, y, B, Lv, C, L, lv, as_stream(stream), stats_workspace, max_ctas);
   if (e == EMRT_ERR_UNSUPPORTED) return set_error(EMRT_ERR_UNSUPPORTED, "tcgen05 conv3x3 does not tile this shape (use emrt_conv3x3_tokens_fwd + emrt_groupnorm_stats)");
   return e;
 }

@@ -142,7 +142,9 @@ extern "C" int emrt_msda_fused_fwd(const emrt_msda_args* a, void* stream) {
                                       EMRT_F16, EMRT_LOC_PIXEL_OFFSET, stream)) return e;
   }
   const int mode = EMRT_LOC_PIXEL_OFFSET | (head_major ? EMRT_VALUE_HEAD_MAJOR : 0) | (grid ? EMRT_QUERY_PIXEL_GRID : 0);
-  tick(3); tick(4);
+  tick(3);
+  if (a->gather_start_event) EMRT_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->gather_start_event), as_stream(stream)));
+  tick(4);
   if (int e = emrt_msda_gather_fwd_hint(v, loc, attn, a->ref, rbs, g, a->B, a->Lq, a->Lv, a->M, D, a->L, a->P, a->shapes_hw, start, EMRT_BF16,
                                         EMRT_F16, mode, grid ? a->window_center : nullptr, stream)) return e;
   tick(5); tick(6);

@@ -358,7 +358,7 @@ class MSDeformableAttention(nn.Module):
 
     # -- forward -----------------------------------------------------------------------------------------
     def forward(self, query, reference_points, value, value_spatial_shapes, value_mask=None, *, query_pos=None,
-                residual_norm=None):
+                residual_norm=None, gather_start_event=None):
         """
         query [bs, Lq, C]; reference_points [bs, Lq, n_levels, 2] in [0,1]; value [bs, Lv, C];
         value_spatial_shapes [n_levels, 2] (H, W); value_mask [bs, Lv] (non-zero = keep)  ->  [bs, Lq, C]
@@ -368,7 +368,10 @@ class MSDeformableAttention(nn.Module):
           query_pos      [1, Lq, C] — the position embedding of `with_pos_embed` (:154-155); the query projection then
                          computes (query + query_pos) W as query W + query_pos W inside one GEMM, no add kernel;
           residual_norm  (residual, gamma, beta) — returns LayerNorm(output + residual) * gamma + beta (:199-200),
-                         evaluated in the output projection's epilogue.
+                         evaluated in the output projection's epilogue;
+          gather_start_event  a torch.cuda.Event recorded on the current stream right before the sampling gather is
+                         launched (at entry on the paths that are not one C call): the encoder layer starts its 3x3
+                         convolution on a second stream at that moment.
         """
         bs, Len_q = query.shape[:2]
         Len_v = value.shape[1]
@@ -379,6 +382,8 @@ class MSDeformableAttention(nn.Module):
             raise L.EmrtError("emrt_b200.MSDeformableAttention needs CUDA tensors (no CPU fallback)")
         if query.dtype not in (torch.float32, torch.bfloat16):
             raise L.EmrtError(f"unsupported dtype {query.dtype}")
+        if gather_start_event is not None:
+            gather_start_event.record()      # the one-call bf16 path records it again, right before its gather
         if torch.is_grad_enabled() and (query.requires_grad or value.requires_grad or reference_points.requires_grad
                                         or any(p.requires_grad for p in self.parameters())):
             mask = None if value_mask is None else value_mask.reshape(-1).to(torch.float32).contiguous()
@@ -395,7 +400,8 @@ class MSDeformableAttention(nn.Module):
                 raise L.EmrtError("residual_norm is an inference-path fusion; the training path composes norm1 itself")
             return out
         if self.gemm_impl == L.IMPL_AUTO:
-            return self._forward_one_call(query, reference_points, value, shapes, value_mask, query_pos, residual_norm)
+            return self._forward_one_call(query, reference_points, value, shapes, value_mask, query_pos, residual_norm,
+                                          gather_start_event)
         # a forced GEMM implementation (tests): the same forward composed launch by launch
         if query.dtype == torch.float32:
             if query_pos is not None:
@@ -406,7 +412,7 @@ class MSDeformableAttention(nn.Module):
             return out
         return self._forward_bf16(query, reference_points, value, shapes, value_mask, query_pos, residual_norm)
 
-    def _forward_one_call(self, query, ref, value, shapes, value_mask, query_pos=None, residual_norm=None):
+    def _forward_one_call(self, query, ref, value, shapes, value_mask, query_pos=None, residual_norm=None, gather_start_event=None):
         """The whole forward as ONE call of the C ABI (emrt_msda_fused_fwd): the library owns the composition
         (projections, softmax + offsets, gather, output projection (+ LayerNorm)) and the kernel selection."""
         M, P = self.num_heads, self.num_points
@@ -439,7 +445,8 @@ class MSDeformableAttention(nn.Module):
         grid = self.window_gather and is_pixel_grid(ref, shapes, Len_q, value.shape[1])
         return ops.msda_fused_fwd(query, value, ref32, shapes, M, P, pk, mask=mask, query_pos=x2, query_pos_rows=x2_period,
                                   row_bias=rowb, residual_norm=residual_norm, pixel_grid=grid,
-                                  win_center=pk["win_center"] if grid else None, keep_pixel_major=not self.head_major)[0]
+                                  win_center=pk["win_center"] if grid else None, keep_pixel_major=not self.head_major,
+                                  gather_start_event=gather_start_event)[0]
 
     def _forward_fp32(self, query, ref, value, shapes, value_mask):
         M, P, D = self.num_heads, self.num_points, self.head_dim

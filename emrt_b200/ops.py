@@ -360,21 +360,30 @@ def conv3x3_tokens(x, w_packed, shapes, impl=L.IMPL_AUTO, out=None):
     return out
 
 
-def conv3x3_tokens_stats(x, w_packed, shapes, groups=32, out=None):
+def conv3x3_tokens_stats(x, w_packed, shapes, groups=32, out=None, stats=None, max_ctas=0):
     """conv3x3_tokens on the tcgen05 path + the GroupNorm(groups) statistics of its stored output from the same kernel's
     epilogue -> (y, stats workspace: its first 2 * B * L * groups floats are the sums [B, L, groups, 2], as groupnorm_stats').
-    Raises EmrtError(UNSUPPORTED) for shapes the tcgen05 conv does not tile."""
+    Raises EmrtError(UNSUPPORTED) for shapes the tcgen05 conv does not tile.  max_ctas > 0: on at most that many SMs (for a
+    caller that runs it on a second stream beside another kernel; `out` / `stats` = conv3x3_stats_buffers(...) allocated on
+    the consumer's stream)."""
     B, Lv, C = x.shape
     hw, _, total = level_tables(shapes)
     assert total == Lv and x.dtype == torch.bfloat16 and w_packed.dtype == torch.bfloat16
     if out is None:
         out = torch.empty_like(x)
     lib = L.load()
-    st = torch.empty((int(lib.emrt_conv3x3_stats_workspace_floats(B, Lv, len(shapes))),), dtype=torch.float32, device=x.device)
+    st = stats if stats is not None else conv3x3_stats_buffers(x, shapes)[1]
     with _Timed("conv3x3", (B * Lv, C, x.element_size())):
-        L.check(lib.emrt_conv3x3_tokens_stats_fwd(_ptr(x), _ptr(w_packed), _ptr(out), _ptr(st), B, Lv, C, len(shapes), hw,
-                                                  int(groups), _stream()))
+        L.check(lib.emrt_conv3x3_tokens_stats_part_fwd(_ptr(x), _ptr(w_packed), _ptr(out), _ptr(st), B, Lv, C, len(shapes), hw,
+                                                       int(groups), int(max_ctas), _stream()))
     return out, st
+
+
+def conv3x3_stats_buffers(x, shapes):
+    """(output, statistics workspace) of conv3x3_tokens_stats for an input like x, allocated on the current stream."""
+    B, Lv, C = x.shape
+    n = int(L.load().emrt_conv3x3_stats_workspace_floats(B, Lv, len(shapes)))
+    return torch.empty_like(x), torch.empty((n,), dtype=torch.float32, device=x.device)
 
 
 def groupnorm_gelu_residual(conv, x, gamma, beta, shapes, groups=32, eps=1e-5, out=None, return_stats=False):
@@ -649,7 +658,8 @@ class _Keep:
 
 
 def msda_fused_fwd(query, value, ref, shapes, M, P, weights, *, mask=None, query_pos=None, query_pos_rows=0, row_bias=None,
-                   residual_norm=None, pixel_grid=False, win_center=None, keep_pixel_major=False, out=None):
+                   residual_norm=None, pixel_grid=False, win_center=None, keep_pixel_major=False, out=None,
+                   gather_start_event=None):
     """emrt_msda_fused_fwd: MSDeformableAttention.forward (t_e_d.py:65-107) in ONE C call.  query [B,Lq,C], value [B,Lv,C]
     (fp32 -> parity path, bf16 -> B200 path), ref f32 [1|B,Lq,L,2].  `weights`: fp32 path dict(w_value, b_value, w_offsets,
     b_offsets, w_attn, b_attn, w_out, b_out) in Paddle layout; bf16 path dict(wv, wq, wo, bv, bq, bo) packed (+ the fp32-path
@@ -697,6 +707,9 @@ def msda_fused_fwd(query, value, ref, shapes, M, P, weights, *, mask=None, query
     if win_center is not None and pixel_grid:
         a.window_center = C.cast(win_center, C.POINTER(C.c_int32))
         keep.append(win_center)
+    if gather_start_event is not None:      # a torch.cuda.Event the C entry records right before the gather launch
+        gather_start_event.record()         # (recorded once here so that torch has created it; re-recorded in place)
+        a.gather_start_event = gather_start_event.cuda_event
     evs = None
     if kernel_events is not None and dt == L.BF16:
         # bench.py: CUDA events around each sub-launch, recorded by the C entry on the launching stream.  Each event is

@@ -254,6 +254,13 @@ int emrt_conv3x3_tokens_fwd(const void* x, const void* w_packed, void* y, int B,
 long long emrt_conv3x3_stats_workspace_floats(int B, int Lv, int L);
 int emrt_conv3x3_tokens_stats_fwd(const void* x, const void* w_packed, void* y, float* stats_workspace, int B, int Lv, int C,
                                   int L, const int32_t* shapes_hw_host, int groups, void* stream);
+/* The same on at most max_ctas SMs (0 = all; same results bit for bit: the tile loop is persistent and the statistics are
+ * per-tile partial sums).  For a caller that runs the convolution on a second stream BESIDE the sampling gather of the same
+ * layer (the conv branch t_e_d.py:185-196 does not depend on the attention branch :198-200): the tensor-pipe kernel is
+ * power-limited when it owns the whole GPU and costs 28 % less SM time on a share of it, while the gather, bound by the
+ * shared-memory pipe, takes the other SMs (emrt_msda_args.gather_start_event marks the moment).                           */
+int emrt_conv3x3_tokens_stats_part_fwd(const void* x, const void* w_packed, void* y, float* stats_workspace, int B, int Lv,
+                                       int C, int L, const int32_t* shapes_hw_host, int groups, int max_ctas, void* stream);
 
 /* y = GELU(GroupNorm_l(conv)) + x per level (GroupNorm(groups, C) eps, exact erf GELU, :187-189); conv, x, y
  * [B, Lv, C] (dtype F32|BF16); gamma, beta F32 [L, C]; stats_workspace F32
@@ -379,6 +386,9 @@ typedef struct emrt_msda_args {
   /* measurement hook (bench.py): when non-NULL, cudaEvent_t handles recorded on `stream` before / after the value projection
    * [0,1], the query projection [2,3], the gather [4,5] and the output projection [6,7]                                     */
   void* timing_events[8];
+  /* optional cudaEvent_t recorded on `stream` right before the gather is launched: a second stream that waits for it starts its
+   * work (the layer's 3x3 convolution, emrt_conv3x3_tokens_stats_part_fwd) together with the gather                          */
+  void* gather_start_event;
 } emrt_msda_args;
 int64_t emrt_msda_fused_workspace_bytes(int B, int Lq, int Lv, int C, int M, int L, int P, int dtype);
 int emrt_msda_fused_fwd(const emrt_msda_args* args, void* stream);

@@ -215,3 +215,48 @@ def test_conv_epilogue_groupnorm_statistics(cuda_dev, B, shapes):
         assert torch.equal(got_s, st2[: 2 * B * len(shapes) * 32])          # deterministic
         scale = want_s.abs().max().item()
         assert (got_s - want_s).abs().max().item() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("tile,B,ctas", [(256, 2, 4), (512, 3, 64), (256, 5, 2)])
+def test_encoder_layer_conv_beside_gather_is_bit_equal(cuda_dev, tile, B, ctas):
+    """TransformerEncoderLayer.overlap_conv: the 3x3 conv on `ctas` SMs of a side stream, started by the event the fused MSDA
+    call records right before its gather — against the same layer in order on one stream (overlap_conv = 0).  Same kernels,
+    persistent tile loops, per-tile statistics partials: the outputs must be identical bit for bit, call after call (the
+    events order the two streams: a race would show as a difference)."""
+    shapes = [(tile // 8,) * 2, (tile // 16,) * 2, (tile // 32,) * 2]
+    C = 256
+    params = O.make_encoder_decoder_params(29, num_enc=2, num_dec=0)
+    rng = np.random.Generator(np.random.PCG64(30))
+    _, Lv = O.level_tables(shapes)
+    src = torch.as_tensor(O.rng_normal(rng, (B, Lv, C), 0.5)).bfloat16().to(cuda_dev)
+    pos = torch.as_tensor(O.rng_normal(rng, (1, Lv, C), 0.5)).bfloat16().to(cuda_dev)
+    layer = emrt_b200.TransformerEncoderLayer(C, 8, 1024, 0.1, "relu", 3, 6)
+    enc = emrt_b200.TransformerEncoder(layer, 2)
+    for i in range(2):
+        _load_layer(enc.layers[i], params, f"encoder.layers.{i}.")
+    enc = enc.to(cuda_dev)
+    assert enc.layers[0].overlap_conv > 0
+    outs = {}
+    for k in (0, ctas, 0, ctas):
+        for lyr in enc.layers:
+            lyr.overlap_conv = k
+        outs.setdefault(k, []).append(enc(src, torch.tensor(shapes), None, pos))
+    torch.cuda.synchronize()
+    for o in outs[ctas] + outs[0][1:]:
+        assert torch.equal(o, outs[0][0])
+    assert torch.isfinite(outs[0][0].float()).all()
+
+
+def test_conv3x3_stats_on_a_share_of_the_sms(cuda_dev):
+    """emrt_conv3x3_tokens_stats_part_fwd: any max_ctas (odd values round down to whole CTA pairs) gives the conv output and the
+    GroupNorm sums of the full-grid launch, bit for bit."""
+    shapes = [(64, 64), (32, 32), (16, 16)]
+    B, C = 4, 256
+    g = torch.Generator(device="cpu").manual_seed(31)
+    x = (torch.randn((B, sum(h * w for h, w in shapes), C), generator=g) * 0.5).bfloat16().to(cuda_dev)
+    w = ops.pack_conv3x3_weights([(torch.randn((C, C, 3, 3), generator=g) * 0.02).to(cuda_dev) for _ in shapes], torch.bfloat16)
+    y0, s0 = ops.conv3x3_tokens_stats(x, w, shapes)
+    n = 2 * B * len(shapes) * 32
+    for k in (1, 2, 7, 40, 1000):
+        y, s = ops.conv3x3_tokens_stats(x, w, shapes, max_ctas=k)
+        assert torch.equal(y, y0) and torch.equal(s[:n], s0[:n]), k
