@@ -54,7 +54,11 @@ void level_start(const emrt_msda_args* a, int32_t* start) {
 // bench.py's per-kernel CUDA events (emrt_msda_args.timing_events), recorded on the launching stream
 struct Tick {
   const emrt_msda_args* a; cudaStream_t st;
-  void operator()(int i) const { if (a->timing_events[i]) cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->timing_events[i]), st); }
+  // (the end of one sub-launch and the start of the next may be the SAME event handle: recorded once)
+  void operator()(int i) const {
+    if (a->timing_events[i] && (i == 0 || a->timing_events[i] != a->timing_events[i - 1]))
+      cudaEventRecord(reinterpret_cast<cudaEvent_t>(a->timing_events[i]), st);
+  }
 };
 
 emrt_linear_args lin(const void* x, const void* w, const float* b, void* y, int64_t rows, int K, int N, int xd, int wd, int yd,

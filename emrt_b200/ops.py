@@ -17,6 +17,24 @@ _TD = {v: k for k, v in _DT.items()}
 
 
 kernel_events = None   # set to a list to collect (name, dims, (start, end)) CUDA-event pairs per launch
+_EVENT_POOL = []
+
+
+def prewarm_events(n):
+    """Create n timing events now (torch creates the cudaEvent at the first record, so each is recorded once, here, on the
+    current stream): the C entries that record events in place then take them from this pool."""
+    for _ in range(n):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        _EVENT_POOL.append(ev)
+
+
+def _pooled_events(n):
+    if len(_EVENT_POOL) < n:
+        prewarm_events(n - len(_EVENT_POOL))
+    out = _EVENT_POOL[-n:]
+    del _EVENT_POOL[-n:]
+    return out
 
 
 class _Timed:
@@ -714,9 +732,11 @@ def msda_fused_fwd(query, value, ref, shapes, M, P, weights, *, mask=None, query
     if kernel_events is not None and dt == L.BF16:
         # bench.py: CUDA events around each sub-launch, recorded by the C entry on the launching stream.  Each event is
         # recorded once here so that torch has created it (and knows it as recorded); the C side records it again in place.
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+        # Five events for the four sub-launches (the end of one is the start of the next), taken from the pool bench.py filled
+        # before its timed region when it did: fewer records inside it.
+        five = _pooled_events(5)
+        evs = [five[0], five[1], five[1], five[2], five[2], five[3], five[3], five[4]]
         for i, ev in enumerate(evs):
-            ev.record()
             a.timing_events[i] = ev.cuda_event
     L.check(lib.emrt_msda_fused_fwd(C.byref(a), _stream()))
     if evs is not None:

@@ -384,7 +384,8 @@ typedef struct emrt_msda_args {
   int32_t dtype; int32_t flags; int32_t keep_pixel_major;
   const int32_t* window_center;
   /* measurement hook (bench.py): when non-NULL, cudaEvent_t handles recorded on `stream` before / after the value projection
-   * [0,1], the query projection [2,3], the gather [4,5] and the output projection [6,7]                                     */
+   * [0,1], the query projection [2,3], the gather [4,5] and the output projection [6,7]; equal neighbouring handles
+   * ([1] == [2], ...) are recorded once                                                                                    */
   void* timing_events[8];
   /* optional cudaEvent_t recorded on `stream` right before the gather is launched: a second stream that waits for it starts its
    * work (the layer's 3x3 convolution, emrt_conv3x3_tokens_stats_part_fwd) together with the gather                          */
