@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Experiment: the encoder layer's 3x3 conv (tensor-pipe bound, power-limited when it owns all 148 SMs) on K SMs of a side
 stream WHILE the sampling gather (shared-memory-pipe bound) runs on the rest, against the two back to back.
-python scripts/exp_overlap_conv_gather.py [K ...]   (needs a build with EMRT_CONV_MAX_CTAS)"""
+python scripts/exp_overlap_conv_gather.py [K ...]"""
 import os
 import sys
 
@@ -44,7 +44,7 @@ ops.msda_gather_fwd = real_gather
 torch.cuda.synchronize()
 ga, gk = captured["a"], captured["k"]
 gather = lambda: real_gather(*ga, **gk)
-conv = lambda: ops.conv3x3_tokens_stats(src, conv_w, shapes)
+conv = lambda k=0: ops.conv3x3_tokens_stats(src, conv_w, shapes, max_ctas=k)
 
 
 def timed(fn, iters=10):
@@ -65,13 +65,11 @@ main = torch.cuda.current_stream()
 
 def both(k):
     def fn():
-        os.environ["EMRT_CONV_MAX_CTAS"] = str(k)
         fork = torch.cuda.Event(); fork.record(main)
         with torch.cuda.stream(side):
             side.wait_event(fork)
-            conv()
+            conv(k)
             done = torch.cuda.Event(); done.record(side)
-        os.environ.pop("EMRT_CONV_MAX_CTAS", None)
         gather()
         main.wait_event(done)
     return fn
