@@ -2,10 +2,12 @@
 //   out[b, q, m*D + d] = sum_k softmax_k(scale * <Q[b,q,m,:], K[b,k,m,:]>) V[b,k,m,d]
 // The sequences are tiny (Lq = Lk = 110, D = 32), so one CTA owns a (batch, head): K and V sit in shared memory as fp32
 // and every LANE owns a query — its 32 q values and 32 accumulators live in registers, the K / V rows are read as
-// broadcast LDS.128 (all lanes the same address: one wavefront per 16 bytes for 32 queries).  Two passes over the keys
-// (row maximum; then exp, sum and the weighted V sum) instead of keeping 110 scores per query.  The first version (a warp
-// per query, lanes over keys, scalar shared-memory reads) was bound by the shared-memory pipe: 350 wavefronts per query,
-// 117 us per call; this one needs 82.  Inputs are the projected q / k / v in the token layout [B, L, M*D] (row strides
+// broadcast LDS.128 (all lanes the same address: one wavefront per 16 bytes for 32 queries).  ONE pass over the keys in
+// blocks of eight with a running maximum (the accumulators are rescaled by exp(old max - new max) once per block, branch
+// free), and the dot products / weighted V sums on fp32 PAIRS (FFMA2: the K / V rows arrive as aligned register pairs from
+// the LDS.128): a third of the instructions of the two-pass scalar form (65 us per call, issue-bound at 16 warps per SM).
+// The first version (a warp per query, lanes over keys, scalar shared-memory reads) was bound by the shared-memory pipe:
+// 350 wavefronts per query, 117 us per call.  Inputs are the projected q / k / v in the token layout [B, L, M*D] (row strides
 // given, so the fused [q | k] projection output can be read in place).
 #include "common.cuh"
 
@@ -14,15 +16,21 @@ namespace emrt {
 constexpr int MHA_MAX_LK = 256;
 constexpr int MHA_WARPS = 4;
 
-// four independent partial sums: a single fmaf chain of 32 would leave a warp one instruction per 4 clocks
+constexpr int MHA_KB = 8;        // keys per block of the running-maximum pass
+
+// four independent partial sums (two packed chains): a single fmaf chain of 32 would leave a warp one instruction per 4 clocks
 template <int D>
-__device__ __forceinline__ float mha_dot(const float (&qv)[D], const float* __restrict__ row) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+__device__ __forceinline__ float mha_dot(const f32x2_t (&qv)[D / 2], const float* __restrict__ row) {
+  f32x2_t s01 = pk2(0.f, 0.f), s23 = pk2(0.f, 0.f);
 #pragma unroll
   for (int d = 0; d < D; d += 4) {
     const float4 kv = *reinterpret_cast<const float4*>(row + d);
-    s0 = fmaf(qv[d], kv.x, s0); s1 = fmaf(qv[d + 1], kv.y, s1); s2 = fmaf(qv[d + 2], kv.z, s2); s3 = fmaf(qv[d + 3], kv.w, s3);
+    s01 = fma2(qv[d / 2], pk2(kv.x, kv.y), s01);
+    s23 = fma2(qv[d / 2 + 1], pk2(kv.z, kv.w), s23);
   }
+  float s0, s1, s2, s3;
+  upk2(s01, s0, s1);
+  upk2(s23, s2, s3);
   return (s0 + s1) + (s2 + s3);
 }
 
@@ -31,8 +39,9 @@ __global__ void __launch_bounds__(MHA_WARPS * 32)
 mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k, int64_t k_ld, const T* __restrict__ v,
                  int64_t v_ld, T* __restrict__ out, int Lq, int Lk, int M, float scale, bool vec_io) {
   extern __shared__ __align__(16) float sm[];
-  float* ks = sm;                 // [Lk][D]
-  float* vs = sm + Lk * D;        // [Lk][D]
+  const int Lkp = (Lk + MHA_KB - 1) / MHA_KB * MHA_KB;      // rows up to a whole block: K anything finite, V zero
+  float* ks = sm;                 // [Lkp][D]
+  float* vs = sm + Lkp * D;       // [Lkp][D]
   const int m = blockIdx.x % M;
   const int64_t b = blockIdx.x / M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,12 +62,13 @@ mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k,
       vs[i] = to_float(v[(b * Lk + kk) * v_ld + m * D + d]);
     }
   }
+  for (int i = Lk * D + threadIdx.x; i < Lkp * D; i += blockDim.x) { ks[i] = 0.f; vs[i] = 0.f; }
   __syncthreads();
   for (int q0 = (blockIdx.y * MHA_WARPS + warp) * 32; q0 < Lq; q0 += 32 * MHA_WARPS * gridDim.y) {
     const int qi = q0 + lane;
     const bool valid = qi < Lq;
     const T* qrow = q + (b * Lq + (valid ? qi : Lq - 1)) * q_ld + m * D;
-    float qv[D];
+    float qf[D];
     // a lane's query row is 32 contiguous values: 16-byte loads (every lane another row — element-wise loads cost 32
     // wavefronts each, 1024 per warp for the row; the alignment of the row is checked on the host)
     if (vec_io) {
@@ -68,30 +78,52 @@ mha_small_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k,
         float t[VEC];
         Vec16<T>::load(qrow + d, t);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) qv[d + k] = t[k] * scale;               // (q k^T) * D^-0.5
+        for (int k = 0; k < VEC; ++k) qf[d + k] = t[k] * scale;               // (q k^T) * D^-0.5
       }
     } else {
 #pragma unroll
-      for (int d = 0; d < D; ++d) qv[d] = to_float(qrow[d]) * scale;
+      for (int d = 0; d < D; ++d) qf[d] = to_float(qrow[d]) * scale;
     }
-    float mx = -INFINITY;
-#pragma unroll 2
-    for (int kk = 0; kk < Lk; ++kk) mx = fmaxf(mx, mha_dot<D>(qv, ks + kk * D));
-    float sum = 0.f, acc[D];
+    f32x2_t qv[D / 2];
 #pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.f;
-#pragma unroll 2
-    for (int kk = 0; kk < Lk; ++kk) {
-      const float e = expf(mha_dot<D>(qv, ks + kk * D) - mx);
-      sum += e;
-      const float* vr = vs + kk * D;
+    for (int d = 0; d < D; d += 2) qv[d / 2] = pk2(qf[d], qf[d + 1]);
+    float mx = -INFINITY, sum = 0.f;
+    f32x2_t acc2[D / 2];
 #pragma unroll
-      for (int d = 0; d < D; d += 4) {
-        const float4 vv = *reinterpret_cast<const float4*>(vr + d);
-        acc[d] = fmaf(e, vv.x, acc[d]); acc[d + 1] = fmaf(e, vv.y, acc[d + 1]);
-        acc[d + 2] = fmaf(e, vv.z, acc[d + 2]); acc[d + 3] = fmaf(e, vv.w, acc[d + 3]);
+    for (int d = 0; d < D / 2; ++d) acc2[d] = pk2(0.f, 0.f);
+#pragma unroll 1
+    for (int kb = 0; kb < Lk; kb += MHA_KB) {
+      float sc[MHA_KB];
+      float bm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < MHA_KB; ++j) {
+        sc[j] = kb + j < Lk ? mha_dot<D>(qv, ks + (kb + j) * D) : -INFINITY;       // (uniform: every lane has the same keys)
+        bm = fmaxf(bm, sc[j]);
+      }
+      const float nm = fmaxf(mx, bm);
+      const float corr = expf(mx - nm);              // first block: exp(-inf) = 0 on zero accumulators
+      mx = nm;
+      sum *= corr;
+      const f32x2_t corr2 = pk2(corr, corr);
+#pragma unroll
+      for (int d = 0; d < D / 2; ++d) acc2[d] = mul2(acc2[d], corr2);
+#pragma unroll
+      for (int j = 0; j < MHA_KB; ++j) {
+        const float e = expf(sc[j] - nm);            // padded keys: exp(-inf) = 0 on zero V rows
+        sum += e;
+        const f32x2_t e2 = pk2(e, e);
+        const float* vr = vs + (kb + j) * D;
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          const float4 vv = *reinterpret_cast<const float4*>(vr + d);
+          acc2[d / 2] = fma2(e2, pk2(vv.x, vv.y), acc2[d / 2]);
+          acc2[d / 2 + 1] = fma2(e2, pk2(vv.z, vv.w), acc2[d / 2 + 1]);
+        }
       }
     }
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; d += 2) upk2(acc2[d / 2], acc[d], acc[d + 1]);
     if (valid) {
       const float inv = 1.f / sum;
       T* orow = out + (b * Lq + qi) * (int64_t)(M * D) + m * D;
@@ -121,7 +153,7 @@ extern "C" int emrt_mha_small(const void* q, int64_t q_ld, const void* k, int64_
   EMRT_REQUIRE(q && k && v && out && B > 0 && Lq > 0 && Lk > 0 && M > 0, "bad mha_small arguments");
   if (D != 32) return set_error(EMRT_ERR_UNSUPPORTED, "mha_small is built for head dim 32 (got %d)", D);
   if (Lk > MHA_MAX_LK) return set_error(EMRT_ERR_UNSUPPORTED, "mha_small holds K/V of one head in shared memory: Lk <= %d (got %d)", MHA_MAX_LK, Lk);
-  const size_t smem = sizeof(float) * ((size_t)Lk * 32 * 2);
+  const size_t smem = sizeof(float) * ((size_t)((Lk + MHA_KB - 1) / MHA_KB * MHA_KB) * 32 * 2);
   cudaStream_t st = as_stream(stream);
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(mha_small_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   EMRT_CUDA_CHECK(cudaFuncSetAttribute(mha_small_kernel<__nv_bfloat16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
