@@ -43,7 +43,7 @@ with torch.no_grad():
     elif what == "conv":
         fn = lambda: ops.conv3x3_tokens(src, lp["conv_w"], shapes)
     elif what == "convs":
-        fn = lambda: ops.conv3x3_tokens_stats(src, lp["conv_w"], shapes)
+        fn = lambda: ops.conv3x3_tokens_stats(src, lp["conv_w"], shapes, max_ctas=int(os.environ.get("EMRT_CONV_MAX_CTAS", "0")))
     elif what == "ffn":
         conv = torch.randn((B, Lv, 256), generator=g, device=dev).bfloat16()
         stats = ops.groupnorm_stats(conv, shapes, groups=32)
